@@ -1,0 +1,85 @@
+"""ctypes binding of libadvgrpo_b200.so (the C ABI declared in include/advgrpo_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, an exception is
+raised -- the product path never silently degrades to PyTorch/CPU arithmetic.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libadvgrpo_b200.so")
+
+_P, _I64, _I, _F, _D, _U64, _SZ = c_void_p, c_int64, c_int, c_float, c_double, c_uint64, c_size_t
+
+# name -> (restype, argtypes); mirrors include/advgrpo_b200.h one to one.
+SIGNATURES = {
+    "advgrpo_abi_version": (c_int, []),
+    "advgrpo_last_error": (c_char_p, []),
+    "advgrpo_device_check": (c_int, [_I]),
+    "advgrpo_sde_step_workspace_bytes": (_SZ, [_I64, _I64]),
+    "advgrpo_cfg_sde_step_logprob": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P,
+                                             _I64, _I64, _F, _F, _U64, _U64, _P, _SZ, _P]),
+    "advgrpo_cfg_sde_logprob_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64,
+                                            _I64, _F, _F, _P]),
+    "advgrpo_group_advantage_workspace_bytes": (_SZ, [_I64, _I64]),
+    "advgrpo_group_advantage": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _SZ, _P]),
+    "advgrpo_grpo_clip_loss": (c_int, [_P, _P, _P, _I64, _I64, _D, _D, _D, _P, _P, _P]),
+    "advgrpo_ln_modulate_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _F, _P]),
+    "advgrpo_ln_modulate_bwd": (c_int, [_P, _P, _P, _I64, _P, _P, _P, _I, _I64, _I64, _I64, _F, _P]),
+    "advgrpo_qk_norm_concat_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P]),
+    "advgrpo_qk_norm_concat_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64,
+                                           _I64, _F, _P]),
+    "advgrpo_attn_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P]),
+    "advgrpo_attn_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
+    "advgrpo_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P, _SZ, _P]),
+    "advgrpo_gemm_bf16": (c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _I64,
+                                  _I64, _I, _P, _I64, _P, _I64, _I64, _P]),
+    "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
+    "advgrpo_clip_preprocess": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
+}
+# test/bench hooks that are exported but not part of include/advgrpo_b200.h
+_EXTRA = {
+    "advgrpo_attn_fwd_variant": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class AdvGrpoError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m adv_grpo_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in {**SIGNATURES, **_EXTRA}.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.advgrpo_abi_version() != 1:
+        raise ImportError("libadvgrpo_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.advgrpo_last_error().decode("utf-8", "replace")
+        raise AdvGrpoError(f"{name} failed ({rc}): {msg}")
+    return rc
+
+
+def query(name, *args):
+    """Invoke a size_t-returning helper."""
+    return getattr(load(), name)(*args)

@@ -1,0 +1,97 @@
+// Shared host/device helpers for libadvgrpo_b200: error reporting across the C ABI,
+// warp/block reductions, bf16 vector access, TMA tensor-map creation.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/advgrpo_b200.h"
+
+namespace advgrpo {
+
+// ---- error state (thread-local: the ABI is re-entrant, reward thread + main thread) ----
+extern thread_local char g_last_error[512];
+int set_error(int code, const char* fmt, ...);
+
+#define ADVGRPO_CHECK_ARG(cond, ...)                                       \
+  do {                                                                     \
+    if (!(cond)) return ::advgrpo::set_error(ADVGRPO_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define ADVGRPO_CUDA_LAUNCH_CHECK()                                                        \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess)                                                                \
+      return ::advgrpo::set_error(ADVGRPO_ERR_CUDA, "%s:%d CUDA error %d: %s", __FILE__, __LINE__, \
+                                  (int)e__, cudaGetErrorString(e__));                      \
+  } while (0)
+
+#define ADVGRPO_CUDA_CALL(x)                                                               \
+  do {                                                                                     \
+    cudaError_t e__ = (x);                                                                 \
+    if (e__ != cudaSuccess)                                                                \
+      return ::advgrpo::set_error(ADVGRPO_ERR_CUDA, "%s:%d CUDA error %d: %s", __FILE__, __LINE__, \
+                                  (int)e__, cudaGetErrorString(e__));                      \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int sm_count();
+
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda) ----
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1. bf16 elements.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum; every thread gets the result. `scratch` holds >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? scratch[l] : 0.f;
+  return warp_sum(t);
+}
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+#endif
+
+}  // namespace advgrpo

@@ -1,0 +1,298 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 + TMA for sm_100a with fused epilogues:
+//   C[M,N] = epi( A[M,K] W[N,K]^T (+ A2[M,K2] W2[N,K2]^T) + bias )
+// Both operands are K-major (activations row-major, nn.Linear weights [out, in]) so one
+// 128B-swizzled TMA box per operand per 64-wide K block feeds tcgen05.mma directly.
+//   warp 4 : TMA producer (STAGES-deep smem ring)          warp 5 : MMA issuer (one thread)
+//   warps 0-3 : epilogue (TMEM -> registers -> bias / GELU / gate*x + residual -> bf16 stores)
+// Tile 128 x BN (BN = 256 or 128), K block 64.  Two TMEM accumulators (2 x BN columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.  One CTA per SM, static round-robin
+// tile schedule with N fastest (neighbouring CTAs share the A row block in L2).
+// The optional second product accumulates the LoRA update into the same accumulator.
+//
+// Replaces the nn.Linear / peft lora.Linear layers under SD3Transformer2DModel
+// (reference call sites fast.py:630-637, train_sd3_fast_pickscore.py:235-255,488-505).
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace advgrpo {
+namespace {
+
+using namespace sm100;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct GCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BN;   // 512 or 256
+  static constexpr int kThreads = 192;
+};
+
+struct GParams {
+  __nv_bfloat16* C;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* gate;
+  int64_t ldc, ldr, gate_stride, rows_per_gate;
+  int M, N, kb1, kb2;   // k blocks of the main and of the second product
+  int epilogue;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+            const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
+            const GParams p) {
+  using G = GCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::kStages * G::kStageBytes);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + G::kStages;
+  uint64_t* bar_acc_full = bar_empty + G::kStages;   // 2
+  uint64_t* bar_acc_empty = bar_acc_full + 2;        // 2
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kb_total = p.kb1 + p.kb2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G::kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_acc_full[i], 1);
+      mbar_init(&bar_acc_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_base_smem, G::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      prefetch_tmap(&tm_a);
+      prefetch_tmap(&tm_w);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int st = it % G::kStages;
+          mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
+          uint8_t* sa = smem + st * G::kStageBytes;
+          uint8_t* sb = sa + G::kABytes;
+          mbar_expect_tx(&bar_full[st], G::kStageBytes);
+          if (kb < p.kb1) {
+            tma_load_2d(sa, &tm_a, &bar_full[st], kb * BK, m0);
+            tma_load_2d(sb, &tm_w, &bar_full[st], kb * BK, n0);
+          } else {
+            tma_load_2d(sa, &tm_a2, &bar_full[st], (kb - p.kb1) * BK, m0);
+            tma_load_2d(sb, &tm_w2, &bar_full[st], (kb - p.kb1) * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&bar_acc_empty[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int st = it % G::kStages;
+          mbar_wait(&bar_full[st], (it / G::kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * G::kStageBytes);
+          const uint32_t sb = sa + G::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            mma_ss(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                   make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&bar_empty[st]);
+        }
+        mma_commit(&bar_acc_full[acc]);
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      const int row = m0 + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&bar_acc_full[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * BN + lane_addr;
+      __nv_bfloat16* crow = p.C + (int64_t)row * p.ldc + n0;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + (int64_t)row * p.ldr + n0 : nullptr;
+      const __nv_bfloat16* grow =
+          (p.gate && row_ok) ? p.gate + (int64_t)(row / p.rows_per_gate) * p.gate_stride + n0 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_acc + c * 32, r);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int col = n0 + c * 32 + i;
+            if (col < p.N) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i + j]);
+              if (p.bias) {
+                float bb[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), bb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += bb[j];
+              }
+              if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+              } else if (p.epilogue == ADVGRPO_EPI_GELU_ERF) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+              } else if (p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+                float gg[8], rr[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(grow + c * 32 + i), gg);
+                unpack8(*reinterpret_cast<const bf16x8*>(rrow + c * 32 + i), rr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(gg[j], f[j], rr[j]);
+              }
+              *reinterpret_cast<bf16x8*>(crow + c * 32 + i) = pack8(f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ta2,
+                const CUtensorMap& tw2, GParams& p, cudaStream_t st) {
+  using G = GCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  int tiles = p.tiles_m * p.tiles_n;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  gemm_kernel<BN><<<grid, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, p);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+}  // namespace
+}  // namespace advgrpo
+
+using namespace advgrpo;
+
+extern "C" {
+
+int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
+                      int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
+                      void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
+                      const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
+                      int64_t rows_per_gate, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(A && W && C, "gemm_bf16: null pointer");
+  ADVGRPO_CHECK_ARG(M >= 1 && N >= 8 && K >= 64, "gemm_bf16: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0, "gemm_bf16: K must be a multiple of 64 and N of 8 (K=%lld N=%lld)", (long long)K, (long long)N);
+  ADVGRPO_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_bf16: leading dimensions must be multiples of 8");
+  ADVGRPO_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(C) && (!bias || aligned16(bias)), "gemm_bf16: 16-byte alignment");
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_bf16: unknown epilogue %d", epilogue);
+  const bool has2 = A2 != nullptr;
+  if (has2) {
+    ADVGRPO_CHECK_ARG(W2 && K2 >= 64 && K2 % 64 == 0 && lda2 % 8 == 0 && ldw2 % 8 == 0 && aligned16(A2) && aligned16(W2),
+                      "gemm_bf16: second product needs W2, K2 %% 64 == 0, aligned operands");
+  }
+  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+    ADVGRPO_CHECK_ARG(residual && gate && rows_per_gate >= 1 && ldr % 8 == 0 && gate_stride % 8 == 0 &&
+                          aligned16(residual) && aligned16(gate),
+                      "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
+  }
+  CUtensorMap ta, tw, ta2, tw2;
+  const int BN = (N >= 256 && N % 256 == 0) ? 256 : 128;
+  {
+    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t sa[2] = {0, (uint64_t)lda * 2};
+    const uint32_t ba[2] = {BK, BM};
+    int rc = make_tmap_bf16(&ta, A, 2, da, sa, ba, true);
+    if (rc) return rc;
+    const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t sw[2] = {0, (uint64_t)ldw * 2};
+    const uint32_t bw[2] = {BK, (uint32_t)BN};
+    rc = make_tmap_bf16(&tw, W, 2, dw, sw, bw, true);
+    if (rc) return rc;
+    if (has2) {
+      const uint64_t da2[2] = {(uint64_t)K2, (uint64_t)M};
+      const uint64_t sa2[2] = {0, (uint64_t)lda2 * 2};
+      rc = make_tmap_bf16(&ta2, A2, 2, da2, sa2, ba, true);
+      if (rc) return rc;
+      const uint64_t dw2[2] = {(uint64_t)K2, (uint64_t)N};
+      const uint64_t sw2[2] = {0, (uint64_t)ldw2 * 2};
+      rc = make_tmap_bf16(&tw2, W2, 2, dw2, sw2, bw, true);
+      if (rc) return rc;
+    } else {
+      ta2 = ta;
+      tw2 = tw;
+    }
+  }
+  GParams p;
+  p.C = (__nv_bfloat16*)C;
+  p.bias = (const __nv_bfloat16*)bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.gate = (const __nv_bfloat16*)gate;
+  p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  p.M = (int)M; p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = has2 ? (int)(K2 / BK) : 0;
+  p.epilogue = epilogue;
+  if (BN == 256) return launch_gemm<256>(ta, tw, ta2, tw2, p, (cudaStream_t)stream);
+  return launch_gemm<128>(ta, tw, ta2, tw2, p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

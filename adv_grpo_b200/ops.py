@@ -1,0 +1,392 @@
+"""Torch-facing wrappers of the libadvgrpo_b200 C ABI.
+
+PyTorch is plumbing here: device memory, streams and autograd bookkeeping.  Every
+numerical result on the hot path comes from the sm_100a kernels; there is no
+PyTorch/CPU fallback -- non-CUDA tensors raise.
+"""
+import math
+import threading
+
+import torch
+
+from . import _lib
+
+_ws_cache = {}
+_ws_lock = threading.Lock()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.AdvGrpoError("adv_grpo_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _workspace(tag, nbytes, device):
+    """Per (op, device, stream) scratch buffer so concurrent streams never share one."""
+    key = (tag, device.index, _stream())
+    with _ws_lock:
+        buf = _ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            _ws_cache[key] = buf
+    return buf
+
+
+def _bf16c(t):
+    if t.dtype != torch.bfloat16:
+        raise _lib.AdvGrpoError(f"expected bfloat16 tensor, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------- A4 + A5
+def cfg_sde_step_logprob(v_uncond, v_text, x, timesteps, sched_timesteps, sigmas, guidance_scale,
+                         noise_level, prev_sample=None, noise=None, seed=0, offset=0,
+                         want_mean=False, want_prev=True):
+    """Fused CFG + Flow-CPS step + log-prob. Returns (prev_sample_bf16|None, log_prob f32[B],
+    prev_sample_mean f32|None, std_dev_t f32[B])."""
+    _need_cuda(v_text, x)
+    v_text, x = _bf16c(v_text), _bf16c(x)
+    v_uncond = None if v_uncond is None else _bf16c(v_uncond)
+    B = x.shape[0]
+    n = x.numel() // B
+    dev = x.device
+    timesteps = timesteps.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+    sched_timesteps = sched_timesteps.to(device=dev, dtype=torch.float32).contiguous()
+    sigmas = sigmas.to(device=dev, dtype=torch.float32).contiguous()
+    T = sched_timesteps.numel()
+    if sigmas.numel() != T + 1:
+        raise _lib.AdvGrpoError("sigmas must have len(sched_timesteps) + 1 entries")
+    prev_in = None if prev_sample is None else _bf16c(prev_sample)
+    if noise is not None:
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+    prev_out = torch.empty_like(x) if (prev_in is None and want_prev) else None
+    mean_out = torch.empty(x.shape, dtype=torch.float32, device=dev) if want_mean else None
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    std = torch.empty(B, dtype=torch.float32, device=dev)
+    ws_bytes = _lib.query("advgrpo_sde_step_workspace_bytes", B, n)
+    ws = _workspace("sde", ws_bytes, dev)
+    _lib.call("advgrpo_cfg_sde_step_logprob", _ptr(v_uncond), _ptr(v_text), _ptr(x), _ptr(prev_in),
+              _ptr(noise), _ptr(timesteps), timesteps.numel(), _ptr(sched_timesteps), _ptr(sigmas), T,
+              _ptr(prev_out), _ptr(mean_out), _ptr(logp), _ptr(std), B, n, float(guidance_scale),
+              float(noise_level), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _ptr(ws),
+              ws.numel(), _stream())
+    return prev_out, logp, mean_out, std
+
+
+class _SdeLogProbReplay(torch.autograd.Function):
+    """log_prob of a stored transition under the current model output; differentiable w.r.t.
+    the (CFG-batched) transformer output (train_sd3_fast_pickscore.py:233-267)."""
+
+    @staticmethod
+    def forward(ctx, noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
+                noise_level, cfg, want_mean):
+        noise_pred = _bf16c(noise_pred)
+        if cfg:
+            vu, vt = noise_pred.chunk(2)
+        else:
+            vu, vt = None, noise_pred
+        _, logp, mean, std = cfg_sde_step_logprob(vu, vt, x, timesteps, sched_timesteps, sigmas,
+                                                  guidance_scale, noise_level, prev_sample=prev_sample,
+                                                  want_mean=want_mean)
+        ctx.save_for_backward(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas)
+        ctx.meta = (float(guidance_scale), float(noise_level), bool(cfg))
+        ctx.mark_non_differentiable(std)
+        if mean is None:
+            mean = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(mean)
+        return logp, mean, std
+
+    @staticmethod
+    def backward(ctx, g_logp, _gm, _gs):
+        noise_pred, x, prev, timesteps, sched_t, sigmas = ctx.saved_tensors
+        gs, nl, cfg = ctx.meta
+        B = x.shape[0]
+        n = x.numel() // B
+        dev = x.device
+        grad = torch.empty_like(noise_pred)
+        if cfg:
+            vu, vt = noise_pred.chunk(2)
+            gvu, gvt = grad[:B], grad[B:]
+        else:
+            vu, vt, gvu, gvt = None, noise_pred, None, grad
+        x, prev = _bf16c(x), _bf16c(prev)
+        timesteps = timesteps.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+        g_logp = g_logp.to(torch.float32).contiguous()
+        _lib.call("advgrpo_cfg_sde_logprob_bwd", _ptr(vu), _ptr(vt), _ptr(x), _ptr(prev), _ptr(timesteps),
+                  timesteps.numel(), _ptr(sched_t), _ptr(sigmas), sched_t.numel(), _ptr(g_logp), _ptr(gvu),
+                  _ptr(gvt), B, n, gs, nl, _stream())
+        return grad, None, None, None, None, None, None, None, None, None
+
+
+def sde_logprob_replay(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
+                       noise_level, cfg=True, want_mean=False):
+    dev = x.device
+    sched_timesteps = sched_timesteps.to(device=dev, dtype=torch.float32).contiguous()
+    sigmas = sigmas.to(device=dev, dtype=torch.float32).contiguous()
+    logp, mean, std = _SdeLogProbReplay.apply(noise_pred, _bf16c(x), _bf16c(prev_sample), timesteps,
+                                              sched_timesteps, sigmas, guidance_scale, noise_level, cfg,
+                                              want_mean)
+    return logp, (mean if want_mean else None), std
+
+
+# --------------------------------------------------------------------------- A9
+def group_advantage(rewards, group_keys, global_std=True, want_stats=True):
+    """rewards f32 [N] or [N,T] (CUDA); group_keys int64 [N] or [N,L] (CUDA).
+    Returns (advantages f64 same shape as rewards, stats f64[4] or None)."""
+    _need_cuda(rewards, group_keys)
+    squeeze = rewards.dim() == 1
+    r = rewards.to(torch.float32).reshape(rewards.shape[0], -1).contiguous()
+    N, T = r.shape
+    keys = group_keys.to(torch.int64).reshape(N, -1).contiguous()
+    adv = torch.empty((N, T), dtype=torch.float64, device=r.device)
+    stats = torch.zeros(4, dtype=torch.float64, device=r.device) if want_stats else None
+    ws_bytes = _lib.query("advgrpo_group_advantage_workspace_bytes", N, T)
+    ws = _workspace("adv", ws_bytes, r.device)
+    _lib.call("advgrpo_group_advantage", _ptr(r), _ptr(keys), keys.shape[1], N, T, int(bool(global_std)),
+              _ptr(adv), _ptr(stats), _ptr(ws), ws.numel(), _stream())
+    return (adv[:, 0] if squeeze else adv), stats
+
+
+# --------------------------------------------------------------------------- A11
+class _GrpoClipLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_prob, old_log_prob, advantages, clip_range, adv_clip_max, grad_scale):
+        _need_cuda(log_prob, old_log_prob, advantages)
+        lp = log_prob.to(torch.float32).contiguous()
+        lpo = old_log_prob.to(torch.float32).contiguous()
+        adv = advantages.to(torch.float64)
+        B = lp.numel()
+        out = torch.empty(6, dtype=torch.float64, device=lp.device)
+        g = torch.empty(B, dtype=torch.float32, device=lp.device)
+        stride = adv.stride(0) if adv.dim() == 1 else 1
+        if adv.dim() != 1:
+            adv = adv.reshape(-1).contiguous()
+        _lib.call("advgrpo_grpo_clip_loss", _ptr(lp), _ptr(lpo), _ptr(adv), stride, B, float(clip_range),
+                  float(adv_clip_max), float(grad_scale), _ptr(out), _ptr(g), _stream())
+        ctx.save_for_backward(g)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        (g,) = ctx.saved_tensors
+        return (g * g_loss.to(torch.float32)), None, None, None, None, None
+
+
+def grpo_clip_loss(log_prob, old_log_prob, advantages, clip_range, adv_clip_max, grad_scale=1.0):
+    """Returns (loss f64 scalar, stats f64[6] = loss, approx_kl, clipfrac, clipfrac_gt_one,
+    clipfrac_lt_one, policy_loss).  `grad_scale` folds the gradient-accumulation divisor in."""
+    return _GrpoClipLoss.apply(log_prob, old_log_prob, advantages, clip_range, adv_clip_max, grad_scale)
+
+
+# --------------------------------------------------------------------------- adaLN LayerNorm-modulate
+class _LnModulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift, scale, shift2, scale2, eps):
+        _need_cuda(x)
+        x = _bf16c(x)
+        B, S, D = x.shape
+        stride = shift.stride(0)
+        for m in (shift, scale, shift2, scale2):
+            if m is not None and (m.stride(-1) != 1 or m.stride(0) != stride or m.dtype != torch.bfloat16):
+                raise _lib.AdvGrpoError("modulation chunks must be bf16 row views of one [B, k*D] matrix")
+        y = torch.empty_like(x)
+        y2 = torch.empty_like(x) if shift2 is not None else None
+        _lib.call("advgrpo_ln_modulate_fwd", _ptr(x), _ptr(shift), _ptr(scale), _ptr(shift2), _ptr(scale2),
+                  stride, _ptr(y), _ptr(y2), B, S, D, float(eps), _stream())
+        ctx.save_for_backward(x, scale, scale2)
+        ctx.eps = float(eps)
+        if y2 is None:
+            return y
+        return y, y2
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        x, scale, scale2 = ctx.saved_tensors
+        B, S, D = x.shape
+        dy = _bf16c(dy)
+        dy2 = None if dy2 is None else _bf16c(dy2)
+        dx = torch.empty_like(x)
+        _lib.call("advgrpo_ln_modulate_bwd", _ptr(x), _ptr(scale), _ptr(scale2), scale.stride(0), _ptr(dy),
+                  _ptr(dy2), _ptr(dx), 0, B, S, D, ctx.eps, _stream())
+        return dx, None, None, None, None, None
+
+
+def ln_modulate(x, shift, scale, shift2=None, scale2=None, eps=1e-6):
+    """LayerNorm(no affine)(x) * (1 + scale[:, None]) + shift[:, None]; optional second modulation.
+    Gradient flows to x only (the modulation comes from frozen adaLN weights)."""
+    return _LnModulate.apply(x, shift, scale, shift2, scale2, eps)
+
+
+# --------------------------------------------------------------------------- q/k RMSNorm + concat
+class _QkNormConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D, eps):
+        _need_cuda(qkv_img)
+        qkv_img = _bf16c(qkv_img)
+        qkv_txt = None if qkv_txt is None else _bf16c(qkv_txt)
+        B, S_img, _ = qkv_img.shape
+        S_txt = 0 if qkv_txt is None else qkv_txt.shape[1]
+        out = torch.empty((B, S_img + S_txt, 3, H, D), dtype=torch.bfloat16, device=qkv_img.device)
+        _lib.call("advgrpo_qk_norm_concat_fwd", _ptr(qkv_img), _ptr(qkv_txt), _ptr(wq_img), _ptr(wk_img),
+                  _ptr(wq_txt), _ptr(wk_txt), _ptr(out), B, S_img, S_txt, H, D, float(eps), _stream())
+        ctx.save_for_backward(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt)
+        ctx.meta = (H, D, float(eps))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt = ctx.saved_tensors
+        H, D, eps = ctx.meta
+        B, S_img, _ = qkv_img.shape
+        S_txt = 0 if qkv_txt is None else qkv_txt.shape[1]
+        dout = _bf16c(dout)
+        d_img = torch.empty_like(qkv_img)
+        d_txt = None if qkv_txt is None else torch.empty_like(qkv_txt)
+        _lib.call("advgrpo_qk_norm_concat_bwd", _ptr(qkv_img), _ptr(qkv_txt), _ptr(wq_img), _ptr(wk_img),
+                  _ptr(wq_txt), _ptr(wk_txt), _ptr(dout), _ptr(d_img), _ptr(d_txt), B, S_img, S_txt, H, D,
+                  eps, _stream())
+        return d_img, d_txt, None, None, None, None, None, None, None
+
+
+def qk_norm_concat(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D=64, eps=1e-6):
+    """[B,S_img,3HD] (+ [B,S_txt,3HD]) -> joint token-major [B,S,3,H,D] with per-head RMSNorm on q,k."""
+    return _QkNormConcat.apply(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D, eps)
+
+
+# --------------------------------------------------------------------------- attention
+def attention_fwd(qkv, scale=None, causal=False, want_lse=True, variant=0):
+    _need_cuda(qkv)
+    qkv = _bf16c(qkv)
+    B, S, three, H, D = qkv.shape
+    assert three == 3
+    scale = (1.0 / math.sqrt(D)) if scale is None else scale
+    out = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device) if want_lse else None
+    if variant:
+        _lib.call("advgrpo_attn_fwd_variant", _ptr(qkv), _ptr(out), _ptr(lse), B, S, H, D, float(scale),
+                  int(causal), int(variant), _stream())
+    else:
+        _lib.call("advgrpo_attn_fwd", _ptr(qkv), _ptr(out), _ptr(lse), B, S, H, D, float(scale), int(causal),
+                  _stream())
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, scale=None, causal=False):
+    qkv, out, dout = _bf16c(qkv), _bf16c(out), _bf16c(dout)
+    B, S, _, H, D = qkv.shape
+    scale = (1.0 / math.sqrt(D)) if scale is None else scale
+    dqkv = torch.empty_like(qkv)
+    ws_bytes = _lib.query("advgrpo_attn_bwd_workspace_bytes", B, S, H, D)
+    ws = _workspace("attn_bwd", ws_bytes, qkv.device)
+    _lib.call("advgrpo_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), B, S, H, D,
+              float(scale), int(causal), _ptr(ws), ws.numel(), _stream())
+    return dqkv
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, scale, causal):
+        out, lse = attention_fwd(qkv, scale, causal, want_lse=True)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        scale, causal = ctx.meta
+        return attention_bwd(qkv, out, dout, lse, scale, causal), None, None
+
+
+def attention(qkv, scale=None, causal=False):
+    """qkv bf16 [B,S,3,H,D] -> out bf16 [B,S,H,D]; differentiable."""
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        return _Attention.apply(qkv, scale, causal)
+    return attention_fwd(qkv, scale, causal, want_lse=False)[0]
+
+
+# --------------------------------------------------------------------------- GEMM
+EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL = 0, 1, 2, 3
+
+
+def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, gate=None,
+         rows_per_gate=1, out=None):
+    """C = epi(a @ w.T (+ a2 @ w2.T) + bias).  a [M,K], w [N,K] bf16 row-major (strided rows ok)."""
+    _need_cuda(a, w)
+    lead = a.shape[:-1]
+    a2d = a.reshape(-1, a.shape[-1])
+    if a2d.stride(-1) != 1:
+        a2d = a2d.contiguous()
+    M, K = a2d.shape
+    N = w.shape[0]
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    c = out if out is not None else torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    c2d = c.reshape(M, N)
+    K2 = 0
+    if a2 is not None:
+        a2 = a2.reshape(M, -1)
+        K2 = a2.shape[1]
+    r2d = None if residual is None else residual.reshape(M, N)
+    _lib.call("advgrpo_gemm_bf16", _ptr(a2d), a2d.stride(0), _ptr(w), w.stride(0), _ptr(a2),
+              0 if a2 is None else a2.stride(0), _ptr(w2), 0 if w2 is None else w2.stride(0), K2, _ptr(bias),
+              _ptr(c2d), c2d.stride(0), M, N, K, int(epilogue), _ptr(r2d), 0 if r2d is None else r2d.stride(0),
+              _ptr(gate), 0 if gate is None else gate.stride(0), int(rows_per_gate), _stream())
+    return c2d.reshape(*lead, N)
+
+
+# --------------------------------------------------------------------------- reward preprocessing
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+_const_cache = {}
+
+
+def _const3(vals, device):
+    key = (vals, device.index)
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.tensor(vals, dtype=torch.float32, device=device)
+        _const_cache[key] = t
+    return t
+
+
+def clip_preprocess(images, out_size=224, dtype=torch.bfloat16, want_u8=False):
+    """bf16 [B,3,H,W] in [0,1] -> CLIPProcessor pixel_values [B,3,out,out] (PIL-exact 8-bit resize)."""
+    _need_cuda(images)
+    images = _bf16c(images)
+    B, C, H, W = images.shape
+    assert C == 3
+    dev = images.device
+    pix = torch.empty((B, 3, out_size, out_size), dtype=dtype, device=dev)
+    u8 = torch.empty((B, 3, out_size, out_size), dtype=torch.uint8, device=dev) if want_u8 else None
+    ws_bytes = _lib.query("advgrpo_clip_preprocess_workspace_bytes", B, H, W, out_size)
+    ws = _workspace("clip_pre", ws_bytes, dev)
+    _lib.call("advgrpo_clip_preprocess", _ptr(images), B, H, W, out_size, _ptr(_const3(CLIP_MEAN, dev)),
+              _ptr(_const3(CLIP_STD, dev)), _ptr(pix), int(dtype == torch.float32), _ptr(u8), _ptr(ws),
+              ws.numel(), _stream())
+    return (pix, u8) if want_u8 else pix
+
+
+def dino_preprocess(images, out_size=518):
+    """[B,3,H,W] (bf16 or f32, [0,1]) -> bicubic out x out, ImageNet-normalised, bf16."""
+    _need_cuda(images)
+    if images.dtype not in (torch.bfloat16, torch.float32):
+        images = images.float()
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    dev = images.device
+    pix = torch.empty((B, 3, out_size, out_size), dtype=torch.bfloat16, device=dev)
+    _lib.call("advgrpo_dino_preprocess", _ptr(images), int(images.dtype == torch.float32), B, H, W, out_size,
+              _ptr(_const3(IMAGENET_MEAN, dev)), _ptr(_const3(IMAGENET_STD, dev)), _ptr(pix), _stream())
+    return pix

@@ -1,0 +1,224 @@
+/* libadvgrpo_b200 -- C ABI of the B200-native (sm_100a) kernels behind the Adv-GRPO
+ * rollout -> score -> advantage -> update hot path.
+ *
+ * The reference (showlab/Adv-GRPO @ 8287f90) is pure Python over
+ * diffusers/transformers/peft and has no FFI of its own; each entry point below
+ * names the reference code (file:line under /root/reference) whose arithmetic it
+ * replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *   - the caller owns every buffer including workspaces; nothing here allocates;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises with the host;
+ *   - return value: 0 on success, a negative ADVGRPO_ERR_* code otherwise, with a
+ *     message retrievable (per calling thread) from advgrpo_last_error();
+ *   - re-entrant: no global mutable state besides the per-thread error string, so
+ *     the reward thread pool (train_sd3_fast_pickscore.py:668,816-817) and the main
+ *     thread may call concurrently on different streams.
+ *   - bf16 tensors are raw uint16 storage (torch.bfloat16); "f32"/"f64" are IEEE.
+ */
+#ifndef ADVGRPO_B200_H_
+#define ADVGRPO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVGRPO_ABI_VERSION 1
+
+#define ADVGRPO_OK 0
+#define ADVGRPO_ERR_BAD_ARG (-1)
+#define ADVGRPO_ERR_CUDA (-2)
+#define ADVGRPO_ERR_UNSUPPORTED (-3)
+#define ADVGRPO_ERR_WORKSPACE (-4)
+
+typedef void* advgrpo_stream_t; /* cudaStream_t */
+
+int advgrpo_abi_version(void);
+/* Message of the last failing call made by the calling thread ("" if none). */
+const char* advgrpo_last_error(void);
+/* 0 if device `dev` is an sm_100 part this library can run on, ADVGRPO_ERR_UNSUPPORTED otherwise. */
+int advgrpo_device_check(int dev);
+
+/* ------------------------------------------------------------------------------------
+ * A4 + A5: classifier-free-guidance combine + Flow-CPS SDE step + per-sample log-prob.
+ * Replaces adv_grpo/diffusers_patch/sd3_sde_with_logprob.py:100-139
+ * (sde_step_with_logprob_new) and the CFG combine at
+ * adv_grpo/diffusers_patch/sd3_pipeline_with_logprob_fast.py:640-642 /
+ * scripts/train_sd3_fast_pickscore.py:242-247, including the host-synchronising
+ * index_for_timestep lookups (sde.py:106,110), which happen on the device here.
+ *
+ *   v = v_uncond + guidance * (v_text - v_uncond)     (each op rounded to bf16, as the
+ *                                                      reference's bf16 tensor ops do)
+ *   sigma = sigmas[idx(t)], sigma' = sigmas[idx(t)+1], std = sigma' * sin(noise_level*pi/2)
+ *   mu = (x - sigma v)(1 - sigma') + (x + (1 - sigma) v) sqrt(sigma'^2 - std^2)
+ *   rollout: prev = mu + std * eps ; replay: prev given
+ *   log_prob[b] = -mean_n (prev - mu)^2
+ *
+ * v_uncond may be NULL (no guidance: v = v_text).  v_*: bf16 [B, n]; x: bf16 [B, n].
+ * timesteps: f32 [B] or [1] (t_count = B or 1; 1 broadcasts as in the rollout,
+ * fast.py:649).  sched_timesteps: f32 [T]; sigmas: f32 [T+1].
+ * noise: f32 [B, n] injected noise, or NULL to draw it in-kernel from Philox4x32-10
+ * keyed by (seed, offset).  prev_in: bf16 [B, n] (replay) or NULL (rollout).
+ * Outputs: prev_out bf16 [B, n] (rollout only; the bf16-rounded next latents that the
+ * reference stores, fast.py:654-655; may be NULL in replay), prev_mean_out f32 [B, n]
+ * (optional, NULL to skip), log_prob f32 [B], std_out f32 [B] (optional).
+ * workspace: advgrpo_sde_step_workspace_bytes(B, n) bytes.
+ */
+size_t advgrpo_sde_step_workspace_bytes(int64_t B, int64_t n);
+int advgrpo_cfg_sde_step_logprob(const void* v_uncond, const void* v_text, const void* x,
+                                 const void* prev_in, const float* noise, const float* timesteps,
+                                 int64_t t_count, const float* sched_timesteps, const float* sigmas,
+                                 int64_t T, void* prev_out, float* prev_mean_out, float* log_prob,
+                                 float* std_out, int64_t B, int64_t n, float guidance,
+                                 float noise_level, uint64_t seed, uint64_t offset, void* workspace,
+                                 size_t workspace_bytes, advgrpo_stream_t stream);
+/* Backward of the replay form w.r.t. the transformer output (what autograd derives at
+ * train_sd3_fast_pickscore.py:1165 through :258-267 and :242-247):
+ *   d log_prob[b] / d v = (2/n) (prev - mu) * ((1 - sigma) sqrt(sigma'^2 - std^2) - sigma (1 - sigma'))
+ * chained through the bf16 CFG combine.  grad_log_prob: f32 [B].  Writes grad_v_uncond
+ * (bf16 [B, n], may be NULL when v_uncond is NULL) and grad_v_text (bf16 [B, n]). */
+int advgrpo_cfg_sde_logprob_bwd(const void* v_uncond, const void* v_text, const void* x,
+                                const void* prev_in, const float* timesteps, int64_t t_count,
+                                const float* sched_timesteps, const float* sigmas, int64_t T,
+                                const float* grad_log_prob, void* grad_v_uncond, void* grad_v_text,
+                                int64_t B, int64_t n, float guidance, float noise_level,
+                                advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A9: group-relative advantage.  Replaces adv_grpo/stat_tracking.py:18-47
+ * (PerPromptStatTracker.update, type='grpo') together with the prompt-identity
+ * round trip of scripts/train_sd3_fast_pickscore.py:962-970 and the statistics of
+ * calculate_zero_std_ratio (:195-229).
+ *   adv[i,t] = (r[i,t] - mean_{j in group(i)} r[j,t]) / (std + 1e-4),
+ *   std = population std over all N rewards of column t (global_std != 0) or over the group.
+ * rewards: f32 [N, T].  Group identity: either group_keys int64 [N] (key_len = 1) or the
+ * tokenised prompt rows int64 [N, key_len] (the reference's `prompt_ids`, key_len = 256);
+ * rows with identical keys form a group.  advantages: f64 [N, T] (the reference returns
+ * float64, quirk Q5).  stats (optional, f64 [4]): {n_groups, mean group size,
+ * zero_std_ratio, mean per-group std of column 0}.
+ */
+size_t advgrpo_group_advantage_workspace_bytes(int64_t N, int64_t T);
+int advgrpo_group_advantage(const float* rewards, const int64_t* group_keys, int64_t key_len,
+                            int64_t N, int64_t T, int global_std, double* advantages,
+                            double* stats, void* workspace, size_t workspace_bytes,
+                            advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A11: GRPO clipped policy-gradient loss, its logged statistics and the backward seed.
+ * Replaces scripts/train_sd3_fast_pickscore.py:1111-1162 (float64 arithmetic, Q5).
+ *   A = clamp(adv, +-adv_clip_max); rho = exp(lp - lp_old);
+ *   loss = mean(max(-A rho, -A clamp(rho, 1 - clip, 1 + clip)))
+ * log_prob, old_log_prob: f32 [B]; advantages: f64 [B] with element stride adv_stride
+ * (so a column of the [N, T] advantage matrix can be passed in place).
+ * out: f64 [6] = {loss, approx_kl, clipfrac, clipfrac_gt_one, clipfrac_lt_one, policy_loss}.
+ * grad_log_prob: f32 [B] = grad_scale * d loss / d log_prob (may be NULL).
+ */
+int advgrpo_grpo_clip_loss(const float* log_prob, const float* old_log_prob,
+                           const double* advantages, int64_t adv_stride, int64_t B,
+                           double clip_range, double adv_clip_max, double grad_scale, double* out,
+                           float* grad_log_prob, advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A3 glue (MMDiT block, diffusers AdaLayerNormZero / SD35AdaLayerNormZeroX /
+ * AdaLayerNormContinuous as called from SD3Transformer2DModel, reference call site
+ * fast.py:630-637): y = LayerNorm(x; no affine, eps) * (1 + scale[b]) + shift[b].
+ * x: bf16 [B, S, D]; shift/scale: bf16 rows of an adaLN embedding, row stride
+ * mod_stride elements ([B, k*D] matrices: pass the chunk base pointers).  y2 (with
+ * shift2/scale2) is the second modulation of the dual-attention blocks; pass NULL to skip.
+ * D must be a multiple of 256 and <= 2048.
+ */
+int advgrpo_ln_modulate_fwd(const void* x, const void* shift, const void* scale, const void* shift2,
+                            const void* scale2, int64_t mod_stride, void* y, void* y2, int64_t B,
+                            int64_t S, int64_t D, float eps, advgrpo_stream_t stream);
+/* dx (+)= d/dx [ y , y2 ] given dy (and dy2, may be NULL).  accumulate != 0 adds into dx. */
+int advgrpo_ln_modulate_bwd(const void* x, const void* scale, const void* scale2,
+                            int64_t mod_stride, const void* dy, const void* dy2, void* dx,
+                            int accumulate, int64_t B, int64_t S, int64_t D, float eps,
+                            advgrpo_stream_t stream);
+
+/* Per-head RMSNorm of q and k (diffusers RMSNorm(head_dim, eps) inside
+ * JointAttnProcessor2_0) fused with the [image, text] sequence concat: builds the joint
+ * token-major buffer qkv_joint bf16 [B, S_img + S_txt, 3, H, D] that the attention
+ * kernel reads through TMA.  qkv_img: bf16 [B, S_img, 3*H*D] (fused to_q/to_k/to_v
+ * output); qkv_txt: bf16 [B, S_txt, 3*H*D] or NULL (S_txt = 0, dual attention attn2).
+ * w_*: bf16 [D] RMSNorm weights, or NULL for no normalisation (SD3-medium). D = 64. */
+int advgrpo_qk_norm_concat_fwd(const void* qkv_img, const void* qkv_txt, const void* wq_img,
+                               const void* wk_img, const void* wq_txt, const void* wk_txt,
+                               void* qkv_joint, int64_t B, int64_t S_img, int64_t S_txt, int64_t H,
+                               int64_t D, float eps, advgrpo_stream_t stream);
+int advgrpo_qk_norm_concat_bwd(const void* qkv_img, const void* qkv_txt, const void* wq_img,
+                               const void* wk_img, const void* wq_txt, const void* wk_txt,
+                               const void* dqkv_joint, void* dqkv_img, void* dqkv_txt, int64_t B,
+                               int64_t S_img, int64_t S_txt, int64_t H, int64_t D, float eps,
+                               advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Attention (tcgen05 + TMA).  Replaces F.scaled_dot_product_attention inside
+ * diffusers JointAttnProcessor2_0 (MMDiT joint text-image attention and the SD3.5
+ * image-only attn2; reference call site fast.py:630-637, train_sd3_fast_pickscore.py:
+ * 235-255), transformers CLIPAttention (PickScore ViT-H/14 towers,
+ * adv_grpo/pickscore_scorer.py:40-43) and timm Attention (DINOv2-B/14,
+ * adv_grpo/rewards.py:397).
+ * qkv: bf16 [B, S, 3, H, D] token-major; out: bf16 [B, S, H, D];
+ * lse: f32 [B, H, S] natural-log-sum-exp of the scaled scores (NULL to skip; needed by bwd).
+ * D in {64, 128}; any S >= 1 (ragged tail masked); causal != 0 applies the lower-
+ * triangular mask (CLIP text tower).
+ */
+int advgrpo_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
+                     int64_t D, float scale, int causal, advgrpo_stream_t stream);
+/* dqkv: bf16 [B, S, 3, H, D].  workspace: advgrpo_attn_bwd_workspace_bytes(...) bytes. */
+size_t advgrpo_attn_bwd_workspace_bytes(int64_t B, int64_t S, int64_t H, int64_t D);
+int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                     void* dqkv, int64_t B, int64_t S, int64_t H, int64_t D, float scale,
+                     int causal, void* workspace, size_t workspace_bytes,
+                     advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense contraction with fused epilogue (tcgen05 + TMA), the nn.Linear / peft
+ * lora.Linear layers of SD3Transformer2DModel and of the reward ViTs:
+ *   C[M, N] = epilogue( A[M, K] @ W[N, K]^T  (+ A2[M, K2] @ W2[N, K2]^T)  + bias[N] )
+ * A, W, A2, W2, C, residual: bf16 row-major with the given leading dimensions (elements);
+ * bias: bf16 [N] or NULL.  The optional second product is the LoRA update
+ * (A2 = x A_lora^T, W2 = scale * B_lora; train_sd3_fast_pickscore.py:488-505).
+ * epilogue: ADVGRPO_EPI_*.  GATE_RESIDUAL: C = residual + gate[row / rows_per_gate] * (.)
+ * with gate bf16 rows of stride gate_stride (the adaLN gate chunk).
+ * K, K2 multiples of 64; N multiple of 16; M arbitrary.
+ */
+#define ADVGRPO_EPI_NONE 0
+#define ADVGRPO_EPI_GELU_TANH 1
+#define ADVGRPO_EPI_GELU_ERF 2
+#define ADVGRPO_EPI_GATE_RESIDUAL 3
+int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
+                      int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
+                      void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
+                      const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
+                      int64_t rows_per_gate, advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A8a preprocessing: the reward image path of adv_grpo/rewards.py:581-584 +
+ * adv_grpo/pickscore_scorer.py:21-28 (CLIPProcessor) without the host round trip:
+ *   u8 = clamp(round(bf16(img) * 255), 0, 255)           (bf16 arithmetic, quirk Q6)
+ *   PIL-compatible antialiased bicubic resize to out_size x out_size (two passes, 8-bit
+ *   intermediate, Pillow's 22-bit fixed-point coefficients) -> /255 -> (x - mean) / std.
+ * images: bf16 [B, 3, H, W] in [0,1]; pixels: bf16 or f32 [B, 3, out, out];
+ * u8_out (optional): uint8 [B, 3, out, out] resized bytes for bit-exact checks.
+ * workspace: advgrpo_clip_preprocess_workspace_bytes(B, H, W, out) bytes.
+ */
+size_t advgrpo_clip_preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, int64_t out);
+int advgrpo_clip_preprocess(const void* images, int64_t B, int64_t H, int64_t W, int64_t out,
+                            const float* mean3, const float* std3, void* pixels, int pixels_f32,
+                            uint8_t* u8_out, void* workspace, size_t workspace_bytes,
+                            advgrpo_stream_t stream);
+/* A8b preprocessing (adv_grpo/rewards.py:379-391): bicubic (A = -0.75, align_corners =
+ * False, no antialias) resize to out x out, ImageNet normalisation, cast to bf16. */
+int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64_t H, int64_t W,
+                            int64_t out, const float* mean3, const float* std3, void* pixels,
+                            advgrpo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVGRPO_B200_H_ */

@@ -1,0 +1,53 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/advgrpo_b200.h declares.
+No compute calls here (no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from adv_grpo_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "advgrpo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(advgrpo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    from adv_grpo_b200 import build
+    build.build()
+    lib = _lib.load()
+    assert lib.advgrpo_abi_version() == 1
+    assert lib.advgrpo_last_error() == b""
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/advgrpo_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in adv_grpo_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_bad_arguments_return_error_codes_not_crashes():
+    lib = _lib.load()
+    # null pointers are rejected before any CUDA call
+    with pytest.raises(_lib.AdvGrpoError, match="null"):
+        _lib.call("advgrpo_grpo_clip_loss", None, None, None, 1, 4, 1e-5, 5.0, 1.0, None, None, None)
+    assert b"null" in lib.advgrpo_last_error()
+    with pytest.raises(_lib.AdvGrpoError, match="head_dim"):
+        _lib.call("advgrpo_attn_fwd", 16, 16, None, 1, 128, 4, 80, 0.1, 0, None)
+    assert _lib.query("advgrpo_sde_step_workspace_bytes", 8, 65536) > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from adv_grpo_b200 import ops
+    with pytest.raises(_lib.AdvGrpoError, match="CUDA"):
+        ops.group_advantage(torch.zeros(4), torch.zeros(4, dtype=torch.int64))
