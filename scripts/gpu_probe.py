@@ -1,0 +1,138 @@
+"""Diagnostics for the tcgen05 kernels on a real B200: each probe runs in its own process so a trapped
+kernel (sticky CUDA error) cannot poison the others.  Usage: python scripts/gpu_probe.py [probe ...]"""
+import math
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def probe_gemm_small():
+    import torch
+    from adv_grpo_b200 import ops
+    for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 256, 128), (256, 512, 256), (1229, 1536, 1536)]:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        w = torch.randn(N, K, device="cuda", generator=g).bfloat16() / 8
+        c = ops.gemm(a, w)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().T
+        err = (c.float() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"gemm {M}x{N}x{K}: rel err {err:.3e}", flush=True)
+        if err > 1e-2:
+            print(" got", c[0, :8].float().tolist())
+            print(" ref", ref[0, :8].tolist())
+            print(" got row1", c[1, :4].float().tolist(), "ref", ref[1, :4].tolist())
+            # which K-slices / rows are right?  identity-like probes
+            a2 = torch.zeros_like(a); a2[:, 0] = 1
+            c2 = ops.gemm(a2, w).float()
+            print(" col0 probe err", (c2 - w.float()[:, 0][None]).abs().max().item())
+            a3 = torch.zeros_like(a); a3[:, min(17, K - 1)] = 1
+            c3 = ops.gemm(a3, w).float()
+            print(" col17 probe err", (c3 - w.float()[:, min(17, K - 1)][None]).abs().max().item())
+
+
+def _attn(variant, D=64, S=256, causal=False):
+    import torch
+    from adv_grpo_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, H = 1, 2
+    qkv = torch.randn(B, S, 3, H, D, device="cuda", generator=g).bfloat16()
+    out, lse = ops.attention_fwd(qkv, variant=variant, causal=causal)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).permute(0, 2, 1, 3)
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(D)
+    if causal:
+        s = s.masked_fill(torch.ones(S, S, device="cuda", dtype=torch.bool).triu(1), float("-inf"))
+    lse_ref = torch.logsumexp(s, -1)
+    print(f"attn variant={variant} D={D} S={S} causal={causal}: rel err {err:.3e}  lse err {(lse - lse_ref).abs().max().item():.3e}", flush=True)
+    if err > 2e-2:
+        print(" got", out[0, 0, 0, :6].float().tolist())
+        print(" ref", ref[0, 0, 0, :6].tolist())
+        print(" got r77", out[0, 77, 1, :4].float().tolist(), "ref", ref[0, 77, 1, :4].tolist())
+
+
+def probe_attn_v1():
+    _attn(1, S=128)
+    _attn(1, S=256)
+    _attn(1, S=1229)
+
+
+def probe_attn_v2():
+    _attn(2, S=256)
+    _attn(2, S=1229)
+
+
+def probe_attn_d128():
+    _attn(1, D=128, S=257)
+
+
+def probe_attn_causal():
+    _attn(1, S=77, causal=True)
+    _attn(1, S=300, causal=True)
+
+
+def probe_perf():
+    import torch
+    from adv_grpo_b200 import ops
+    B, S, H, D = 16, 1229, 24, 64
+    qkv = torch.randn(B, S, 3, H, D, device="cuda").bfloat16()
+    flops = 4 * B * H * S * S * D
+    for variant in (1, 2):
+        for _ in range(3):
+            ops.attention_fwd(qkv, variant=variant, want_lse=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attention_fwd(qkv, variant=variant, want_lse=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"attn fwd variant {variant}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    for _ in range(3):
+        torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"torch SDPA (library baseline): {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for (M, N, K) in [(19664, 4608, 1536), (19664, 1536, 1536), (19664, 6144, 1536), (19664, 1536, 6144)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        w = torch.randn(N, K, device="cuda").bfloat16()
+        for name, fn in (("ours", lambda: ops.gemm(a, w)), ("cublas", lambda: torch.nn.functional.linear(a, w))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"gemm {M}x{N}x{K} {name}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+PROBES = {k[6:]: v for k, v in globals().items() if k.startswith("probe_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        PROBES[sys.argv[2]]()
+        sys.exit(0)
+    names = sys.argv[1:] or list(PROBES)
+    for n in names:
+        print(f"===== probe {n} =====", flush=True)
+        r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
+        print(r.stdout[-4000:])
+        if r.returncode != 0:
+            print(f"  [probe {n} exit code {r.returncode}]\n{r.stderr[-1500:]}")

@@ -1,0 +1,306 @@
+"""GPU parity tests (through the C ABI) of the HBM-bound kernels against the CPU oracle and the
+golden vectors produced by the reference's own files.  Tolerances are stated per test."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import grpo_loss as loss_o
+from oracle import preprocess as pre_o
+from oracle import sde as sde_o
+from oracle import stat_tracking as st_o
+from oracle.scheduler import FlowMatchEulerOracle
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from adv_grpo_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def sched():
+    s = FlowMatchEulerOracle()
+    s.set_timesteps(10)
+    return s
+
+
+# ------------------------------------------------------------------ A4/A5 SDE step
+@pytest.mark.parametrize("B,shape", [(2, (16, 32, 32)), (8, (16, 64, 64)), (3, (16, 8, 8))])
+def test_sde_rollout_matches_oracle_bit_exact(ops, sched, B, shape):
+    g = torch.Generator().manual_seed(B)
+    vu = torch.randn(B, *shape, generator=g).bfloat16()
+    vt = torch.randn(B, *shape, generator=g).bfloat16()
+    x = torch.randn(B, *shape, generator=g).bfloat16()
+    noise = torch.randn(B, *shape, generator=g)
+    step = 1
+    v = sde_o.cfg_combine(vu, vt, 4.5)                       # bf16 ops on CPU, like the reference on GPU
+    prev_o, lp_o, mean_o, std_o = sde_o.sde_step_with_logprob_new(sched.sigmas, [step], v, x, 0.8, noise=noise)
+    prev, lp, mean, std = ops.cfg_sde_step_logprob(vu.to(DEV), vt.to(DEV), x.to(DEV), sched.timesteps[step:step + 1],
+                                                   sched.timesteps, sched.sigmas, 4.5, 0.8, noise=noise.to(DEV),
+                                                   want_mean=True)
+    assert torch.equal(mean.cpu(), mean_o), "prev_sample_mean must be bit-identical to the fp32 oracle"
+    assert torch.equal(prev.cpu(), prev_o.bfloat16()), "stored next latents = bf16(prev_sample) (fast.py:654-655)"
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_o.numpy(), rtol=2e-6, atol=0)   # fp32 sum order only
+    np.testing.assert_array_equal(std.cpu().numpy(), np.full(B, std_o.item(), dtype=np.float32))
+
+
+def test_sde_replay_golden_g8(ops, sched, golden, golden_dir):
+    """Replay form with per-sample timesteps against the verbatim reference output (golden G8)."""
+    t = torch.load(os.path.join(golden_dir, "g8_tensors.pt"))
+    ts = sched.timesteps[golden["G8_step_index"]]
+    _, lp, mean, std = ops.cfg_sde_step_logprob(None, t["v"].bfloat16().to(DEV), t["x"].bfloat16().to(DEV), ts,
+                                                sched.timesteps, sched.sigmas, 1.0, 0.8,
+                                                prev_sample=t["prev"].bfloat16().to(DEV), want_mean=True)
+    assert torch.equal(mean.cpu(), t["mean"])
+    np.testing.assert_allclose(lp.cpu().numpy(), np.array(golden["G8_log_prob"], dtype=np.float32), rtol=2e-6)
+    np.testing.assert_array_equal(std.cpu().numpy(), np.array(golden["G8_std"], dtype=np.float32))
+
+
+def test_sde_last_step_has_zero_std_and_logprob(ops, sched):
+    x = torch.randn(2, 16, 16, 16).bfloat16().to(DEV)
+    v = torch.randn(2, 16, 16, 16).bfloat16().to(DEV)
+    prev, lp, _, std = ops.cfg_sde_step_logprob(None, v, x, sched.timesteps[9:10], sched.timesteps, sched.sigmas,
+                                                1.0, 0.8, seed=1)
+    assert lp.tolist() == [0.0, 0.0] and std.tolist() == [0.0, 0.0]      # quirk Q1
+    x0 = (x.float() - sched.sigmas[9].item() * v.float())
+    assert torch.allclose(prev.float(), x0.bfloat16().float(), atol=1e-2)
+
+
+def test_sde_unknown_timestep_yields_nan(ops, sched):
+    x = torch.zeros(1, 16, 8, 8, dtype=torch.bfloat16, device=DEV)
+    _, lp, _, _ = ops.cfg_sde_step_logprob(None, x, x, torch.tensor([123.456]), sched.timesteps, sched.sigmas, 1.0,
+                                           0.8, seed=1)
+    assert math.isnan(lp.item())
+
+
+def test_sde_philox_noise_statistics_and_determinism(ops, sched):
+    B, n = 4, 16 * 64 * 64
+    z = torch.zeros(B, n, dtype=torch.bfloat16, device=DEV)
+    # x = v = 0 -> mu = 0 -> prev = std * eps
+    kw = dict(timesteps=sched.timesteps[0:1], sched_timesteps=sched.timesteps, sigmas=sched.sigmas,
+              guidance_scale=1.0, noise_level=0.8)
+    p1, lp1, _, std = ops.cfg_sde_step_logprob(None, z, z, seed=7, offset=0, **kw)
+    p2, lp2, _, _ = ops.cfg_sde_step_logprob(None, z, z, seed=7, offset=0, **kw)
+    p3, _, _, _ = ops.cfg_sde_step_logprob(None, z, z, seed=7, offset=B * n // 4, **kw)
+    assert torch.equal(p1, p2) and torch.equal(lp1, lp2)
+    assert not torch.equal(p1, p3)
+    eps = p1.float() / std[0]
+    assert abs(eps.mean().item()) < 0.01 and abs(eps.std().item() - 1.0) < 0.01
+    assert abs((eps ** 4).mean().item() - 3.0) < 0.1                     # Gaussian kurtosis
+    assert abs(torch.corrcoef(torch.stack([eps[0], eps[1]]))[0, 1].item()) < 0.02
+    np.testing.assert_allclose((-lp1 / std ** 2).cpu().numpy(), np.ones(B), rtol=0.02)
+
+
+def test_sde_replay_backward_matches_autograd_of_oracle(ops, sched):
+    B, shape = 4, (16, 16, 16)
+    g = torch.Generator().manual_seed(11)
+    npred = torch.randn(2 * B, *shape, generator=g).bfloat16()
+    x = torch.randn(B, *shape, generator=g).bfloat16()
+    prev = (x.float() + 0.3 * torch.randn(B, *shape, generator=g)).bfloat16()
+    idx = [0, 1, 1, 5]
+    w = torch.randn(B, generator=g)
+    # oracle in fp32 with straight-through bf16 CFG (autograd of the reference expression)
+    npo = npred.float().requires_grad_(True)
+    vu, vt = npo.chunk(2)
+    v = vu + 4.5 * (vt - vu)
+    _, lp_o, _, _ = sde_o.sde_step_with_logprob_new(sched.sigmas, idx, v, x, 0.8, prev_sample=prev)
+    (lp_o * w).sum().backward()
+    npd = npred.to(DEV).requires_grad_(True)
+    lp, _, _ = ops.sde_logprob_replay(npd, x.to(DEV), prev.to(DEV), sched.timesteps[idx], sched.timesteps,
+                                      sched.sigmas, 4.5, 0.8, cfg=True)
+    (lp * w.to(DEV)).sum().backward()
+    got, ref = npd.grad.float().cpu(), npo.grad
+    # bf16 gradient storage + bf16 CFG rounding in the forward: 2% of the gradient scale
+    assert (got - ref).abs().max() <= 0.02 * ref.abs().max()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+    assert cos > 0.9995
+
+
+# ------------------------------------------------------------------ A9 advantage
+def _keys_from_prompts(prompts, L=8):
+    table = {}
+    rows = []
+    for p in prompts:
+        if p not in table:
+            rng = np.random.RandomState(len(table) + 100)
+            table[p] = rng.randint(0, 49407, size=L)
+        rows.append(table[p])
+    return torch.tensor(np.stack(rows), dtype=torch.int64)
+
+
+def test_advantage_golden_g1_g2_g3(ops, golden):
+    p = ['a', 'b', 'a', 'c', 'b', 'a']
+    keys = _keys_from_prompts(p).to(DEV)
+    r = torch.tensor([1, 2, 3, 4, 5, 6], dtype=torch.float32, device=DEV)
+    a1, st = ops.group_advantage(r, keys, global_std=False)
+    a2, _ = ops.group_advantage(r, keys, global_std=True)
+    assert a1.dtype == torch.float64
+    np.testing.assert_allclose(a1.cpu().numpy(), golden["G1"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(a2.cpu().numpy(), golden["G2"], rtol=1e-12, atol=1e-12)
+    assert st[0].item() == 3 and abs(st[1].item() - golden["G1_stats"][0]) < 1e-12
+    keys = _keys_from_prompts(['p', 'p', 'q', 'q']).to(DEV)
+    r = torch.tensor([[1, 1], [2, 2], [3, 3], [4, 4]], dtype=torch.float32, device=DEV)
+    a3, _ = ops.group_advantage(r, keys, global_std=True)
+    np.testing.assert_allclose(a3.cpu().numpy(), golden["G3"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("global_std", [True, False])
+def test_advantage_seeded_groups_golden_g7(ops, golden, global_std):
+    prompts = golden["G7_prompts"]
+    r = torch.tensor(golden["G7_rewards"], dtype=torch.float32)
+    r2 = r[:, None].repeat(1, 2)
+    adv, st = ops.group_advantage(r2.to(DEV), _keys_from_prompts(prompts, L=256).to(DEV), global_std=global_std)
+    # tolerance: float64 summation order only
+    np.testing.assert_allclose(adv.cpu().numpy(), golden[f"G7_adv_global{int(global_std)}"], rtol=1e-10, atol=1e-10)
+    ratio, mean_std = st_o.zero_std_ratio(prompts, r.numpy())
+    assert st[0].item() == 6 and st[1].item() == 8
+    assert abs(st[2].item() - ratio) < 1e-12
+    assert abs(st[3].item() - mean_std) < 1e-6            # the reference computes this one in float32
+
+
+def test_advantage_large_ragged_groups(ops):
+    rng = np.random.RandomState(3)
+    N = 1500
+    ids = rng.randint(0, 97, size=N)
+    prompts = [f"p{i}" for i in ids]
+    r = rng.randn(N, 3).astype(np.float32)
+    adv, _ = ops.group_advantage(torch.tensor(r).to(DEV), torch.tensor(ids, dtype=torch.int64).to(DEV), True)
+    np.testing.assert_allclose(adv.cpu().numpy(), st_o.grpo_advantages(prompts, r, True), rtol=1e-9, atol=1e-9)
+    adv, _ = ops.group_advantage(torch.tensor(r).to(DEV), torch.tensor(ids, dtype=torch.int64).to(DEV), False)
+    np.testing.assert_allclose(adv.cpu().numpy(), st_o.grpo_advantages(prompts, r, False), rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ A11 loss
+@pytest.mark.parametrize("B", [1, 8, 33])
+def test_grpo_clip_loss_and_grad(ops, B):
+    g = torch.Generator().manual_seed(B)
+    lp_old = -torch.rand(B, generator=g)
+    lp = lp_old + 4e-5 * torch.randn(B, generator=g)          # ratios straddle 1 +- 1e-5
+    adv = 3 * torch.randn(B, generator=g, dtype=torch.float64)
+    adv[0] = 7.5                                              # exercises adv_clip_max
+    if B > 2:
+        adv[2] = 0.0
+    lpo = lp.clone().requires_grad_(True)
+    loss_ref, info = loss_o.grpo_clip_loss(lpo, lp_old, adv, 1e-5, 5.0)
+    loss_ref.backward()
+    lpd = lp.to(DEV).requires_grad_(True)
+    loss, stats = ops.grpo_clip_loss(lpd, lp_old.to(DEV), adv.to(DEV), 1e-5, 5.0)
+    loss.backward()
+    assert loss.dtype == torch.float64
+    # advantages/step losses within 1e-3 rel (north_star); we are far inside it
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(stats[1].item(), info["approx_kl"].item(), rtol=1e-5, atol=1e-15)
+    for k, name in ((2, "clipfrac"), (3, "clipfrac_gt_one"), (4, "clipfrac_lt_one")):
+        assert abs(stats[k].item() - info[name].item()) < 1e-6   # the reference holds these in float32
+    np.testing.assert_allclose(lpd.grad.cpu().numpy(), lpo.grad.numpy(), rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------ adaLN LN-modulate, QK norm
+@pytest.mark.parametrize("D,S,dual", [(1536, 77, True), (1536, 33, False), (256, 5, True), (768, 9, False)])
+def test_ln_modulate_fwd_bwd(ops, D, S, dual):
+    B = 3
+    g = torch.Generator().manual_seed(D + S)
+    x = (torch.randn(B, S, D, generator=g) * 2 + 0.5).bfloat16()
+    emb = (0.3 * torch.randn(B, 9 * D, generator=g)).bfloat16()
+    sh, sc, sh2, sc2 = emb[:, :D], emb[:, D:2 * D], emb[:, 6 * D:7 * D], emb[:, 7 * D:8 * D]
+    xr = x.float().requires_grad_(True)
+    n = torch.nn.functional.layer_norm(xr, (D,), eps=1e-6)
+    y_ref = n * (1 + sc.float()[:, None]) + sh.float()[:, None]
+    y2_ref = n * (1 + sc2.float()[:, None]) + sh2.float()[:, None]
+    gy = torch.randn(B, S, D, generator=g).bfloat16()
+    gy2 = torch.randn(B, S, D, generator=g).bfloat16()
+    ((y_ref * gy.float()).sum() + ((y2_ref * gy2.float()).sum() if dual else 0)).backward()
+    xd = x.to(DEV).requires_grad_(True)
+    embd = emb.to(DEV)
+    chunks = (embd[:, :D], embd[:, D:2 * D], embd[:, 6 * D:7 * D], embd[:, 7 * D:8 * D])
+    if dual:
+        y, y2 = ops.ln_modulate(xd, chunks[0], chunks[1], chunks[2], chunks[3])
+        ((y.float() * gy.to(DEV).float()).sum() + (y2.float() * gy2.to(DEV).float()).sum()).backward()
+        assert (y2.float().cpu() - y2_ref).abs().max() <= 2 ** -7 * y2_ref.abs().max()
+    else:
+        y = ops.ln_modulate(xd, chunks[0], chunks[1])
+        (y.float() * gy.to(DEV).float()).sum().backward()
+    # one bf16 rounding of the output: half an ulp relative to the largest magnitude
+    assert (y.float().cpu() - y_ref.detach()).abs().max() <= 2 ** -7 * y_ref.abs().max()
+    gref = xr.grad
+    assert (xd.grad.float().cpu() - gref).abs().max() <= 2 ** -6 * gref.abs().max()
+
+
+@pytest.mark.parametrize("S_txt", [0, 13])
+def test_qk_norm_concat_fwd_bwd(ops, S_txt):
+    B, S_img, H, D = 2, 20, 8, 64
+    g = torch.Generator().manual_seed(5 + S_txt)
+    qi = torch.randn(B, S_img, 3 * H * D, generator=g).bfloat16()
+    qt = torch.randn(B, S_txt, 3 * H * D, generator=g).bfloat16() if S_txt else None
+    ws = [(1 + 0.1 * torch.randn(D, generator=g)).bfloat16() for _ in range(4)]
+
+    def ref(qi, qt):
+        def norm(t, wq, wk):
+            t = t.view(t.shape[0], t.shape[1], 3, H, D)
+            q, k, v = t[:, :, 0], t[:, :, 1], t[:, :, 2]
+            rn = lambda z, w: z * torch.rsqrt(z.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()
+            return torch.stack([rn(q, wq), rn(k, wk), v], dim=2)
+        parts = [norm(qi, ws[0], ws[1])]
+        if qt is not None:
+            parts.append(norm(qt, ws[2], ws[3]))
+        return torch.cat(parts, dim=1)
+
+    qir = qi.float().requires_grad_(True)
+    qtr = qt.float().requires_grad_(True) if S_txt else None
+    out_ref = ref(qir, qtr)
+    go = torch.randn(out_ref.shape, generator=g).bfloat16()
+    (out_ref * go.float()).sum().backward()
+    qid = qi.to(DEV).requires_grad_(True)
+    qtd = qt.to(DEV).requires_grad_(True) if S_txt else None
+    wd = [w.to(DEV) for w in ws]
+    out = ops.qk_norm_concat(qid, qtd, wd[0], wd[1], wd[2] if S_txt else None, wd[3] if S_txt else None, H, D)
+    (out.float() * go.to(DEV).float()).sum().backward()
+    assert out.shape == (B, S_img + S_txt, 3, H, D)
+    assert (out.float().cpu() - out_ref.detach()).abs().max() <= 2 ** -7 * out_ref.abs().max()
+    assert (qid.grad.float().cpu() - qir.grad).abs().max() <= 2 ** -6 * qir.grad.abs().max()
+    if S_txt:
+        assert (qtd.grad.float().cpu() - qtr.grad).abs().max() <= 2 ** -6 * qtr.grad.abs().max()
+    # no-norm variant (SD3-medium): pure concat
+    out2 = ops.qk_norm_concat(qid.detach(), qtd.detach() if S_txt else None, None, None, None, None, H, D)
+    assert torch.equal(out2[:, :S_img].reshape(B, S_img, -1), qid.detach())
+
+
+# ------------------------------------------------------------------ reward preprocessing
+@pytest.mark.parametrize("H", [512, 256])
+def test_clip_preprocess_bit_exact_with_pillow(ops, H):
+    from PIL import Image
+    g = torch.Generator().manual_seed(H)
+    img = torch.rand(2, 3, H, H, generator=g)
+    img[0, :, : H // 2] = torch.linspace(0, 1, H)[None, None, :].expand(3, H // 2, H)   # smooth region
+    img = img.bfloat16()
+    pix, u8 = ops.clip_preprocess(img.to(DEV), 224, dtype=torch.float32, want_u8=True)
+    q = pre_o.quantise_bf16(img)                                   # rewards.py:581 on the bf16 tensor
+    ref_u8 = pre_o.pil_bicubic_resize_u8(q.numpy(), 224)
+    assert np.array_equal(u8.cpu().numpy(), ref_u8), "resized bytes must be bit-exact (integer work)"
+    for b in range(2):                                             # and against Pillow itself
+        pil = np.array(Image.fromarray(q[b].permute(1, 2, 0).numpy()).resize((224, 224), resample=Image.BICUBIC))
+        assert np.array_equal(u8[b].permute(1, 2, 0).cpu().numpy(), pil)
+    np.testing.assert_allclose(pix.cpu().numpy(), pre_o.clip_pixel_values(ref_u8), rtol=0, atol=2e-7)
+    pix_bf16 = ops.clip_preprocess(img.to(DEV), 224)
+    assert torch.equal(pix_bf16.cpu(), torch.from_numpy(pre_o.clip_pixel_values(ref_u8)).bfloat16()) or \
+        (pix_bf16.float().cpu() - torch.from_numpy(pre_o.clip_pixel_values(ref_u8))).abs().max() < 2 ** -6
+
+
+def test_dino_preprocess_matches_torch_bicubic(ops):
+    from oracle import dinov2 as dino_o
+    img = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(1))
+    ref = dino_o.preprocess(img)
+    got = ops.dino_preprocess(img.to(DEV), 518).float().cpu()
+    assert got.shape == (2, 3, 518, 518)
+    # fp32 interpolation + one bf16 rounding of values up to ~2.7
+    assert (got - ref).abs().max() < 2 ** -6
+    got_bf = ops.dino_preprocess(img.bfloat16().to(DEV), 518).float().cpu()
+    ref_bf = dino_o.preprocess(img.bfloat16().float())
+    assert (got_bf - ref_bf).abs().max() < 0.05

@@ -1,0 +1,129 @@
+"""GPU parity tests of the tcgen05 kernels (GEMM with fused epilogues, flash attention) against
+plain PyTorch fp32 references of the same op on the same bf16 inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from adv_grpo_b200 import ops as _ops
+    return _ops
+
+
+def _rel_err(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (300, 1536, 1536), (1229, 4608, 1536),
+                                   (77, 128, 256), (2458, 6144, 1536), (16, 9216, 1536), (500, 64, 1536)])
+def test_gemm_plain_and_bias(ops, M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g).bfloat16()
+    ref = a.float() @ w.float().T
+    got = ops.gemm(a, w)
+    # bf16 output rounding (2^-8 relative) on fp32-accumulated products
+    assert _rel_err(got, ref) < 6e-3
+    got_b = ops.gemm(a, w, bias=bias)
+    assert _rel_err(got_b, ref + bias.float()) < 6e-3
+
+
+def test_gemm_epilogues_and_lora(ops):
+    B, S, K, N, R = 2, 333, 1536, 1536, 64
+    g = torch.Generator(device=DEV).manual_seed(0)
+    a = torch.randn(B * S, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g).bfloat16()
+    ref = a.float() @ w.float().T + bias.float()
+    got = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU_TANH)
+    assert _rel_err(got, torch.nn.functional.gelu(ref, approximate="tanh")) < 6e-3
+    got = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU_ERF)
+    assert _rel_err(got, torch.nn.functional.gelu(ref)) < 6e-3
+    res = torch.randn(B * S, N, device=DEV, generator=g).bfloat16()
+    gate_mat = torch.randn(B, 3 * N, device=DEV, generator=g).bfloat16()
+    gate = gate_mat[:, N:2 * N]
+    got = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GATE_RESIDUAL, residual=res, gate=gate, rows_per_gate=S)
+    ref_g = res.float() + gate.float().repeat_interleave(S, 0) * ref
+    assert _rel_err(got, ref_g) < 6e-3
+    # LoRA second product
+    a2 = torch.randn(B * S, R, device=DEV, generator=g).bfloat16()
+    w2 = (0.1 * torch.randn(N, R, device=DEV, generator=g)).bfloat16()
+    got = ops.gemm(a, w, bias=bias, a2=a2, w2=w2)
+    assert _rel_err(got, ref + a2.float() @ w2.float().T) < 6e-3
+
+
+def test_gemm_strided_operands(ops):
+    g = torch.Generator(device=DEV).manual_seed(3)
+    big = torch.randn(200, 3 * 256, device=DEV, generator=g).bfloat16()
+    a = big[:, 256:512]                                   # row stride 768
+    w = (torch.randn(128, 256, device=DEV, generator=g) / 16).bfloat16()
+    assert _rel_err(ops.gemm(a, w), a.float() @ w.float().T) < 6e-3
+
+
+# ------------------------------------------------------------------ attention
+def _ref_attention(qkv, scale, causal):
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        S = s.shape[-1]
+        s = s.masked_fill(torch.ones(S, S, device=s.device, dtype=torch.bool).triu(1), float("-inf"))
+    return o.permute(0, 2, 1, 3), torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (2, 461, 4), (1, 1024, 2), (2, 1229, 3), (1, 1370, 2), (1, 77, 2),
+                                   (1, 4301, 1)])
+def test_attention_fwd_d64(ops, variant, B, S, H):
+    g = torch.Generator(device=DEV).manual_seed(S + H)
+    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g).bfloat16()
+    out, lse = ops.attention_fwd(qkv, variant=variant)
+    ref, lse_ref = _ref_attention(qkv, 0.125, False)
+    # P is rounded to bf16 before P@V and O to bf16 on store: ~2^-8 relative to max |O|
+    assert (out.float() - ref).abs().max().item() < 1.5e-2 * ref.abs().max().item()
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
+def test_attention_fwd_large_logits_and_lazy_rescale(ops):
+    """Rows whose running max grows by more than the lazy-rescale threshold across KV tiles."""
+    B, S, H = 1, 640, 2
+    g = torch.Generator(device=DEV).manual_seed(9)
+    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g)
+    qkv[:, :, 1] *= torch.linspace(0.2, 6.0, S, device=DEV)[None, :, None, None]   # later keys dominate
+    qkv = qkv.bfloat16()
+    out, lse = ops.attention_fwd(qkv)
+    ref, lse_ref = _ref_attention(qkv, 0.125, False)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert (lse - lse_ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("S", [77, 300])
+def test_attention_fwd_causal(ops, S):
+    g = torch.Generator(device=DEV).manual_seed(S)
+    qkv = torch.randn(2, S, 3, 4, 64, device=DEV, generator=g).bfloat16()
+    out, lse = ops.attention_fwd(qkv, causal=True)
+    ref, lse_ref = _ref_attention(qkv, 0.125, True)
+    assert (out.float() - ref).abs().max().item() < 1.5e-2 * ref.abs().max().item()
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("S", [257, 50])
+def test_attention_fwd_d128_padded_clip_heads(ops, S):
+    """CLIP ViT-H heads are 80 wide: zero-padded to 128 with the 1/sqrt(80) scale."""
+    g = torch.Generator(device=DEV).manual_seed(S)
+    qkv = torch.zeros(2, S, 3, 4, 128, device=DEV)
+    qkv[..., :80] = torch.randn(2, S, 3, 4, 80, device=DEV, generator=g)
+    qkv = qkv.bfloat16()
+    scale = 80 ** -0.5
+    out, lse = ops.attention_fwd(qkv, scale=scale)
+    ref, lse_ref = _ref_attention(qkv, scale, False)
+    assert (out.float() - ref).abs().max().item() < 1.5e-2 * ref.abs().max().item()
+    assert out[..., 80:].abs().max().item() == 0
+    assert (lse - lse_ref).abs().max().item() < 2e-3
