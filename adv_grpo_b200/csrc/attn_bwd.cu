@@ -1,22 +1,469 @@
-// Flash-attention backward (placeholder until the tcgen05 kernel lands in this file).
+// Flash-attention backward on tcgen05 + TMA for sm_100a (head_dim 64).
+//
+// One CTA owns one 128-row K/V tile of one (batch, head) and streams the query tiles.  The
+// scores are computed TRANSPOSED (S^T = K Q^T, lanes = kv rows) so that P^T and dS^T are directly
+// the A operands of the dV / dK products:
+//   S^T  = K_j Q_i^T            (SS)            dP^T = V_j dO_i^T            (SS)
+//   P^T  = exp2(S^T c - lse_i)  (registers -> TMEM, bf16)
+//   dS^T = P^T (dP^T - delta_i) (registers -> shared, bf16, 128B-swizzled by hand)
+//   dV_j += P^T dO_i            (A = P^T from TMEM,   B = dO_i  MN-major)
+//   dK_j += dS^T Q_i            (A = dS^T K-major,    B = Q_i   MN-major)
+//   dQ_i  = dS K_j              (A = dS^T read MN-major, B = K_j MN-major) -> fp32 TMA reduce-add
+// Warp roles (448 threads): warps 0-7 compute (thread = kv row; two warpgroups split the 128
+// query columns), warps 8-11 drain dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk.tensor add into
+// the fp32 dQ accumulator), warp 12 TMA producer, warp 13 MMA issuer.
+// TMEM columns: S^T 0-127 | dP^T 128-255 | P^T 256-319 | dV 320-383 | dK 384-447 | dQ 448-511.
+// A prologue kernel computes delta = rowsum(dO . O), converts lse to the log2 domain into a
+// 128-padded layout (+inf on padding so padded query columns give P = 0) and clears the dQ
+// accumulator; an epilogue kernel scales and casts dQ to bf16 into dqkv.
+//
+// Replaces autograd through F.scaled_dot_product_attention at
+// scripts/train_sd3_fast_pickscore.py:1165 (MMDiT joint attention and attn2 in the replay step).
+#include <math.h>
+
 #include "common.cuh"
+#include "sm100.cuh"
+
+namespace advgrpo {
+namespace {
+
+using namespace sm100;
+
+constexpr int T = 128;          // tile rows (both q and kv)
+constexpr int D = 64;
+constexpr int QSTAGES = 2;
+constexpr int kTile = T * D * 2;            // 16 KB  bf16 [128 x 64]
+constexpr int kDsBytes = T * T * 2;         // 32 KB  bf16 [128 x 128]
+constexpr int kStatBytes = 2 * T * 4;       // lse2 + delta
+constexpr int kDqBytes = T * D * 4;         // 32 KB  fp32 [128 x 64]
+constexpr int OFF_K = 0;
+constexpr int OFF_V = OFF_K + kTile;
+constexpr int OFF_Q = OFF_V + kTile;                      // QSTAGES
+constexpr int OFF_DO = OFF_Q + QSTAGES * kTile;           // QSTAGES
+constexpr int OFF_DS = OFF_DO + QSTAGES * kTile;          // 2
+constexpr int OFF_DQ = OFF_DS + 2 * kDsBytes;             // 1
+constexpr int OFF_STAT = OFF_DQ + kDqBytes;               // QSTAGES
+constexpr int OFF_BAR = OFF_STAT + QSTAGES * kStatBytes;
+constexpr int kSmemBytes = OFF_BAR + 256 + 1024;
+constexpr int kThreads = 448;
+constexpr int COL_S = 0, COL_DP = 128, COL_P = 256, COL_DV = 320, COL_DK = 384, COL_DQ = 448;
+
+struct BParams {
+  __nv_bfloat16* dqkv;     // [B, S, 3, H, D]
+  const float* lse2;       // [B, H, S_pad]  (log2 domain, +inf on padding)
+  const float* delta;      // [B, H, S_pad]
+  int S, S_pad, H;
+  float scale, scale_log2;
+  int causal;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_dq, const BParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* bar_kv_full = bars;                 // 1
+  uint64_t* bar_q_full = bars + 1;              // QSTAGES
+  uint64_t* bar_q_empty = bar_q_full + QSTAGES; // QSTAGES
+  uint64_t* bar_s_full = bar_q_empty + QSTAGES; // 1   S^T and dP^T in TMEM
+  uint64_t* bar_s_free = bar_s_full + 1;        // 1   compute finished reading them (256)
+  uint64_t* bar_p_full = bar_s_free + 1;        // 1   P^T in TMEM (256)
+  uint64_t* bar_pv_done = bar_p_full + 1;       // 1   dV MMA finished reading P^T
+  uint64_t* bar_ds_full = bar_pv_done + 1;      // 2   dS^T in smem (256)
+  uint64_t* bar_ds_empty = bar_ds_full + 2;     // 2   dK / dQ MMAs finished reading it
+  uint64_t* bar_dq_full = bar_ds_empty + 2;     // 1
+  uint64_t* bar_dq_free = bar_dq_full + 1;      // 1   drain finished reading dQ TMEM (128)
+  uint64_t* bar_dkv_full = bar_dq_free + 1;     // 1
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_dkv_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * T;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int S = p.S;
+  const int nq_total = (S + T - 1) / T;
+  const int i_begin = p.causal ? (kv0 / T) : 0;      // query tiles strictly above the diagonal see nothing
+  const int nq = nq_total - i_begin;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv_full, 1);
+    for (int i = 0; i < QSTAGES; ++i) {
+      mbar_init(&bar_q_full[i], 1);
+      mbar_init(&bar_q_empty[i], 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 256);
+    mbar_init(bar_p_full, 256);
+    mbar_init(bar_pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_ds_full[i], 256);
+      mbar_init(&bar_ds_empty[i], 1);
+    }
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_free, 128);
+    mbar_init(bar_dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  const int64_t stat_row = ((int64_t)b * p.H + h) * p.S_pad;
+
+  if (warp == 12) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      prefetch_tmap(&tm_qkv);
+      prefetch_tmap(&tm_do);
+      mbar_expect_tx(bar_kv_full, 2 * kTile);
+      tma_load_4d(smem + OFF_K, &tm_qkv, bar_kv_full, 0, 1 * p.H + h, kv0, b);
+      tma_load_4d(smem + OFF_V, &tm_qkv, bar_kv_full, 0, 2 * p.H + h, kv0, b);
+      for (int it = 0; it < nq; ++it) {
+        const int i = i_begin + it;
+        const int st = it % QSTAGES;
+        mbar_wait(&bar_q_empty[st], ((it / QSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&bar_q_full[st], 2 * kTile + kStatBytes);
+        tma_load_4d(smem + OFF_Q + st * kTile, &tm_qkv, &bar_q_full[st], 0, 0 * p.H + h, i * T, b);
+        tma_load_4d(smem + OFF_DO + st * kTile, &tm_do, &bar_q_full[st], 0, h, i * T, b);
+        bulk_load_1d(smem + OFF_STAT + st * kStatBytes, p.lse2 + stat_row + i * T, T * 4, &bar_q_full[st]);
+        bulk_load_1d(smem + OFF_STAT + st * kStatBytes + T * 4, p.delta + stat_row + i * T, T * 4, &bar_q_full[st]);
+      }
+    }
+  } else if (warp == 13) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(T, T, 0, 0);     // A K-major, B K-major, N = 128
+      constexpr uint32_t idesc_kn = make_idesc_bf16(T, D, 0, 1);    // A K-major (smem or TMEM), B MN-major
+      constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
+      const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
+      auto back_half = [&](int it) {
+        const int st = it % QSTAGES, bb = it & 1;
+        const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
+        const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
+        const uint32_t ds_s = smem_u32(smem + OFF_DS + bb * kDsBytes);
+        // dV += P^T dO
+        mbar_wait(bar_p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < T / 16; ++k)
+          mma_ts(tmem_base + COL_DV, tmem_base + COL_P + k * 8,
+                 make_smem_desc_sw128(do_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+        mma_commit(bar_pv_done);
+        // dK += dS^T Q
+        mbar_wait(&bar_ds_full[bb], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < T / 16; ++k)
+          mma_ss(tmem_base + COL_DK, make_smem_desc_sw128(ds_s + (k / 4) * 16384 + (k % 4) * 32, 16, 1024),
+                 make_smem_desc_sw128(q_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+        // dQ = dS K   (fresh accumulator every query tile)
+        if (it > 0) {
+          mbar_wait(bar_dq_free, (it - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < T / 16; ++k)
+          mma_ss(tmem_base + COL_DQ, make_smem_desc_sw128(ds_s + k * 2048, 16384, 1024),
+                 make_smem_desc_sw128(k_s + k * 2048, 16384, 1024), idesc_mn, k > 0 ? 1u : 0u);
+        mma_commit(&bar_ds_empty[bb]);
+        mma_commit(bar_dq_full);
+        mma_commit(&bar_q_empty[st]);
+      };
+      mbar_wait(bar_kv_full, 0);
+      for (int it = 0; it < nq; ++it) {
+        const int st = it % QSTAGES;
+        mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);
+        if (it > 0) mbar_wait(bar_s_free, (it - 1) & 1);
+        tc_fence_after();
+        const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
+        const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_ss(tmem_base + COL_S, make_smem_desc_sw128(k_s + k * 32, 16, 1024),
+                 make_smem_desc_sw128(q_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_ss(tmem_base + COL_DP, make_smem_desc_sw128(v_s + k * 32, 16, 1024),
+                 make_smem_desc_sw128(do_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        mma_commit(bar_s_full);
+        if (it > 0) back_half(it - 1);
+      }
+      if (nq > 0) back_half(nq - 1);
+      mma_commit(bar_dkv_full);
+    }
+  } else if (warp < 8) {
+    // ============================== compute: P^T and dS^T ==============================
+    const int wg = warp / 4;                          // which half of the query columns
+    const int row = (warp % 4) * 32 + lane;           // kv row inside the tile == TMEM lane
+    const int kv_idx = kv0 + row;
+    const bool kv_ok = kv_idx < S;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp % 4) * 32) << 16;
+    const uint32_t t_s = tmem_base + COL_S + lane_addr;
+    const uint32_t t_dp = tmem_base + COL_DP + lane_addr;
+    const uint32_t t_p = tmem_base + COL_P + lane_addr;
+    for (int it = 0; it < nq; ++it) {
+      const int i = i_begin + it;
+      const int st = it % QSTAGES, bb = it & 1;
+      const float* lse2 = reinterpret_cast<const float*>(smem + OFF_STAT + st * kStatBytes);
+      const float* delta = lse2 + T;
+      uint8_t* ds_row = smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128;   // 64-col block = wg
+      mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);     // lse2 / delta visible
+      mbar_wait(bar_s_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(bar_pv_done, (it - 1) & 1);   // P^T region free
+      if (it >= 2) mbar_wait(&bar_ds_empty[bb], ((it - 2) >> 1) & 1);   // dS buffer free
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = wg * 2 + cc;                    // 32-column chunk of the query axis
+        uint32_t rs[32], rp[32];
+        tmem_ld32(t_s + c * 32, rs);
+        tmem_ld32(t_dp + c * 32, rp);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int q_a = i * T + c * 32 + e;
+          float p0 = ex2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2[c * 32 + e]));
+          float p1 = ex2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2[c * 32 + e + 1]));
+          if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
+          if (p.causal) {
+            if (q_a < kv_idx) p0 = 0.f;
+            if (q_a + 1 < kv_idx) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(rp[e]) - delta[c * 32 + e]);
+          const float d1 = p1 * (__uint_as_float(rp[e + 1]) - delta[c * 32 + e + 1]);
+          pk[e / 2] = pack_bf16(p0, p1);
+          dk[e / 2] = pack_bf16(d0, d1);
+        }
+        tmem_st16(t_p + c * 16, pk);
+        // dS^T row: 64 bytes of this chunk = four 16-byte pieces, hand swizzled (128B pattern)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int piece = cc * 4 + k;
+          *reinterpret_cast<uint4*>(ds_row + ((piece ^ (row & 7)) * 16)) =
+              make_uint4(dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_s_free);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_full);
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_ds_full[bb]);
+    }
+    // ---- epilogue: dK, dV -> bf16 ----
+    if (wg == 0) {
+      mbar_wait(bar_dkv_full, 0);
+      tc_fence_after();
+      __nv_bfloat16* base = p.dqkv + ((int64_t)b * S + kv_idx) * 3 * p.H * D;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {       // 0: dV, 1: dK
+        const uint32_t t_acc = tmem_base + (which == 0 ? COL_DV : COL_DK) + lane_addr;
+        const float sc = which == 0 ? 1.0f : p.scale;
+        __nv_bfloat16* dst = base + ((which == 0 ? 2 : 1) * p.H + h) * D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_wait_ld();
+          if (kv_ok) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(r[e + 0]) * sc, __uint_as_float(r[e + 1]) * sc);
+              v.y = pack_bf16(__uint_as_float(r[e + 2]) * sc, __uint_as_float(r[e + 3]) * sc);
+              v.z = pack_bf16(__uint_as_float(r[e + 4]) * sc, __uint_as_float(r[e + 5]) * sc);
+              v.w = pack_bf16(__uint_as_float(r[e + 6]) * sc, __uint_as_float(r[e + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + c * 32 + e) = v;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== dQ drain (warps 8-11) ==============================
+    const int row = (warp % 4) * 32 + lane;           // query row inside the tile == TMEM lane
+    const uint32_t t_dq = tmem_base + COL_DQ + (static_cast<uint32_t>((warp % 4) * 32) << 16);
+    uint8_t* stage = smem + OFF_DQ;
+    const int tid = threadIdx.x - 256;
+    for (int it = 0; it < nq; ++it) {
+      const int i = i_begin + it;
+      mbar_wait(bar_dq_full, it & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_dq, r0);
+      tmem_ld32(t_dq + 32, r1);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_dq_free);
+      // previous reduce must have finished reading the staging tile
+      if (tid == 0) tma_store_wait_read();
+      named_bar_sync(1, 128);
+      // two [128 rows x 32 fp32] boxes, 128B-swizzled rows
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        *reinterpret_cast<uint4*>(stage + row * 128 + ((k ^ (row & 7)) * 16)) =
+            make_uint4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
+        *reinterpret_cast<uint4*>(stage + 16384 + row * 128 + ((k ^ (row & 7)) * 16)) =
+            make_uint4(r1[4 * k], r1[4 * k + 1], r1[4 * k + 2], r1[4 * k + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        const int grow = (int)(stat_row + (int64_t)i * T);
+        tma_reduce_add_2d(&tm_dq, stage, 0, grow);
+        tma_reduce_add_2d(&tm_dq, stage + 16384, 32, grow);
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta = rowsum(dO . O); lse -> log2 domain, padded; clear the dQ accumulator.
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                     const float* __restrict__ lse, float* __restrict__ lse2,
+                                     float* __restrict__ delta, float* __restrict__ dq_acc, int B, int S,
+                                     int S_pad, int H) {
+  // one 8-lane group per (b, h, s_pad) row
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  const int sub = threadIdx.x & 7;
+  const int64_t total = (int64_t)B * H * S_pad;
+  if (gid >= total) return;
+  const int s = (int)(gid % S_pad);
+  const int h = (int)((gid / S_pad) % H);
+  const int b = (int)(gid / ((int64_t)S_pad * H));
+  float acc = 0.f;
+  if (s < S) {
+    const int64_t off = (((int64_t)b * S + s) * H + h) * D + sub * 8;
+    float fo[8], fd[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(out + off), fo);
+    unpack8(*reinterpret_cast<const bf16x8*>(dout + off), fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(fo[j], fd[j], acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0) {
+    delta[gid] = acc;
+    lse2[gid] = s < S ? lse[((int64_t)b * H + h) * S + s] * 1.4426950408889634f : INFINITY;
+  }
+  float4* dq = reinterpret_cast<float4*>(dq_acc + gid * D + sub * 8);
+  dq[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  dq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
+                                          int B, int S, int S_pad, int H, float scale) {
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
+  const int sub = threadIdx.x & 7;
+  const int64_t total = (int64_t)B * H * S;
+  if (gid >= total) return;
+  const int s = (int)(gid % S);
+  const int h = (int)((gid / S) % H);
+  const int b = (int)(gid / ((int64_t)S * H));
+  const float4* src = reinterpret_cast<const float4*>(dq_acc + ((((int64_t)b * H + h) * S_pad + s) * D + sub * 8));
+  float4 a = src[0], c = src[1];
+  float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, c.x * scale, c.y * scale, c.z * scale, c.w * scale};
+  *reinterpret_cast<bf16x8*>(dqkv + ((((int64_t)b * S + s) * 3 + 0) * H + h) * D + sub * 8) = pack8(f);
+}
+
+inline int64_t pad128(int64_t s) { return (s + 127) / 128 * 128; }
+
+}  // namespace
+}  // namespace advgrpo
 
 using namespace advgrpo;
 
 extern "C" {
 
 size_t advgrpo_attn_bwd_workspace_bytes(int64_t B, int64_t S, int64_t H, int64_t D) {
-  (void)D;
-  return (size_t)B * H * S * sizeof(float) + 256;
+  const int64_t sp = pad128(S);
+  return (size_t)(B * H * sp * D * 4 + 2 * B * H * sp * 4 + 1024);
 }
 
 int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                      void* dqkv, int64_t B, int64_t S, int64_t H, int64_t D, float scale,
                      int causal, void* workspace, size_t workspace_bytes,
                      advgrpo_stream_t stream) {
-  (void)qkv; (void)out; (void)dout; (void)lse; (void)dqkv; (void)B; (void)S; (void)H; (void)D;
-  (void)scale; (void)causal; (void)workspace; (void)workspace_bytes; (void)stream;
-  return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_bwd: not implemented yet");
+  ADVGRPO_CHECK_ARG(qkv && out && dout && lse && dqkv, "attn_bwd: null pointer");
+  if (D != 64) return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_bwd: head_dim %lld not supported (64 only)", (long long)D);
+  ADVGRPO_CHECK_ARG(B >= 1 && S >= 1 && H >= 1 && B <= 65535 && H <= 65535, "attn_bwd: bad sizes");
+  ADVGRPO_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), "attn_bwd: 16-byte alignment");
+  if (!workspace || workspace_bytes < advgrpo_attn_bwd_workspace_bytes(B, S, H, D))
+    return set_error(ADVGRPO_ERR_WORKSPACE, "attn_bwd: workspace too small");
+  ADVGRPO_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "attn_bwd: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t sp = pad128(S);
+  float* dq_acc = (float*)workspace;
+  float* lse2 = dq_acc + B * H * sp * D;
+  float* delta = lse2 + B * H * sp;
+  {
+    const int64_t groups = B * H * sp;
+    const int threads = 256;
+    const int64_t blocks = (groups * 8 + threads - 1) / threads;
+    attn_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
+                                                               lse, lse2, delta, dq_acc, (int)B, (int)S, (int)sp, (int)H);
+    ADVGRPO_CUDA_LAUNCH_CHECK();
+  }
+  CUtensorMap tm_qkv, tm_do, tm_dq;
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+    const uint64_t str[4] = {0, (uint64_t)D * 2, (uint64_t)(3 * H * D) * 2, (uint64_t)(S * 3 * H * D) * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    int rc = make_tmap_bf16(&tm_qkv, qkv, 4, dims, str, box, true);
+    if (rc) return rc;
+    const uint64_t dims2[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+    const uint64_t str2[4] = {0, (uint64_t)D * 2, (uint64_t)(H * D) * 2, (uint64_t)(S * H * D) * 2};
+    rc = make_tmap_bf16(&tm_do, dout, 4, dims2, str2, box, true);
+    if (rc) return rc;
+    const uint64_t dims3[2] = {(uint64_t)D, (uint64_t)(B * H * sp)};
+    const uint64_t str3[2] = {0, (uint64_t)D * 4};
+    const uint32_t box3[2] = {32, 128};
+    rc = make_tmap(&tm_dq, dq_acc, 2, dims3, str3, box3, true, true);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  BParams p;
+  p.dqkv = (__nv_bfloat16*)dqkv;
+  p.lse2 = lse2;
+  p.delta = delta;
+  p.S = (int)S; p.S_pad = (int)sp; p.H = (int)H;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  dim3 grid((unsigned)(sp / T), (unsigned)H, (unsigned)B);
+  attn_bwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_qkv, tm_do, tm_dq, p);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  {
+    const int64_t groups = B * H * S;
+    const int threads = 256;
+    const int64_t blocks = (groups * 8 + threads - 1) / threads;
+    attn_bwd_dq_finish_kernel<<<(unsigned)blocks, threads, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (int)B, (int)S, (int)sp,
+                                                                    (int)H, scale);
+    ADVGRPO_CUDA_LAUNCH_CHECK();
+  }
+  return ADVGRPO_OK;
 }
 
 }  // extern "C"

@@ -44,9 +44,10 @@ struct Cfg {
 };
 
 struct Params {
-  __nv_bfloat16* out;   // [B, S, H, D]
+  __nv_bfloat16* out;   // [B, S, H, D]   (rows [0, S_split) when out2 is set: [B, S_split, H, D])
+  __nv_bfloat16* out2;  // rows [S_split, S): [B, S - S_split, H, D], or null
   float* lse;           // [B, H, S] or null
-  int S, H;
+  int S, H, S_split;
   float scale_log2;     // softmax scale * log2(e)
   int causal;
 };
@@ -279,7 +280,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     tc_fence_after();
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const bool valid = q_idx < S;
-    __nv_bfloat16* orow = p.out + (((int64_t)b * S + q_idx) * p.H + h) * D;
+    __nv_bfloat16* orow;
+    if (p.out2 == nullptr) orow = p.out + (((int64_t)b * S + q_idx) * p.H + h) * D;
+    else if (q_idx < p.S_split) orow = p.out + (((int64_t)b * p.S_split + q_idx) * p.H + h) * D;
+    else orow = p.out2 + (((int64_t)b * (S - p.S_split) + (q_idx - p.S_split)) * p.H + h) * D;
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t r[32];
@@ -312,7 +316,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 }
 
 template <int D, int NQ>
-int launch(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H, float scale,
+int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H, float scale,
            int causal, cudaStream_t st) {
   using C = Cfg<D, NQ>;
   CUtensorMap tmap;
@@ -328,6 +332,8 @@ int launch(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t
   }
   Params p;
   p.out = (__nv_bfloat16*)out;
+  p.out2 = (__nv_bfloat16*)out2;
+  p.S_split = (int)S_split;
   p.lse = lse;
   p.S = (int)S;
   p.H = (int)H;
@@ -342,13 +348,13 @@ int launch(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t
 }  // namespace
 
 // variant: 0 = auto, 1 = one query tile per CTA (2 CTAs/SM), 2 = two query tiles per CTA
-int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
+int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
                       int64_t D, float scale, int causal, int variant, cudaStream_t st) {
   if (D == 64) {
-    if (variant == 2) return launch<64, 2>(qkv, out, lse, B, S, H, scale, causal, st);
-    return launch<64, 1>(qkv, out, lse, B, S, H, scale, causal, st);
+    if (variant == 2) return launch<64, 2>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
+    return launch<64, 1>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
   }
-  if (D == 128) return launch<128, 1>(qkv, out, lse, B, S, H, scale, causal, st);
+  if (D == 128) return launch<128, 1>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
   return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_fwd: head_dim %lld not in {64, 128}", (long long)D);
 }
 
@@ -358,13 +364,15 @@ using namespace advgrpo;
 
 extern "C" {
 
-int advgrpo_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
-                     int64_t D, float scale, int causal, advgrpo_stream_t stream) {
+int advgrpo_attn_fwd(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B,
+                     int64_t S, int64_t H, int64_t D, float scale, int causal,
+                     advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
+  ADVGRPO_CHECK_ARG(!out2 || (S_split > 0 && S_split < S && aligned16(out2)), "attn_fwd: out2 needs 0 < S_split < S");
   ADVGRPO_CHECK_ARG(B >= 1 && S >= 1 && H >= 1 && B <= 65535 && H <= 65535, "attn_fwd: bad sizes B=%lld S=%lld H=%lld",
                     (long long)B, (long long)S, (long long)H);
   ADVGRPO_CHECK_ARG(aligned16(qkv) && aligned16(out), "attn_fwd: tensors must be 16-byte aligned");
-  return attn_fwd_dispatch(qkv, out, lse, B, S, H, D, scale, causal, 0, (cudaStream_t)stream);
+  return attn_fwd_dispatch(qkv, out, out2, S_split, lse, B, S, H, D, scale, causal, 0, (cudaStream_t)stream);
 }
 
 // Test/bench hook (not part of the reference-facing surface): pick the CTA shape explicitly.
@@ -372,7 +380,7 @@ int advgrpo_attn_fwd_variant(const void* qkv, void* out, float* lse, int64_t B, 
                              int64_t D, float scale, int causal, int variant,
                              advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
-  return attn_fwd_dispatch(qkv, out, lse, B, S, H, D, scale, causal, variant, (cudaStream_t)stream);
+  return attn_fwd_dispatch(qkv, out, nullptr, 0, lse, B, S, H, D, scale, causal, variant, (cudaStream_t)stream);
 }
 
 }  // extern "C"

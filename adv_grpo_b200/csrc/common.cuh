@@ -45,6 +45,8 @@ int sm_count();
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1. bf16 elements.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool f32);
 
 // ---- device helpers ----
 #ifdef __CUDACC__

@@ -35,6 +35,7 @@ struct GCfg {
 
 struct GParams {
   __nv_bfloat16* C;
+  __nv_bfloat16* preact;   // optional: bf16 pre-activation (acc + bias) for the GELU backward
   const __nv_bfloat16* bias;
   const __nv_bfloat16* residual;
   const __nv_bfloat16* gate;
@@ -178,12 +179,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += bb[j];
               }
-              if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
+              if (p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF) {
+                // the activation is applied to the bf16-rounded pre-activation so that the fused
+                // forward is bit-identical to "store z in bf16, then GELU(z)" (training replay)
+                const bf16x8 z = pack8(f);
+                if (p.preact) *reinterpret_cast<bf16x8*>(p.preact + (int64_t)row * p.ldc + n0 + c * 32 + i) = z;
+                unpack8(z, f);
+                if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
-              } else if (p.epilogue == ADVGRPO_EPI_GELU_ERF) {
+                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+                  for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+                }
               } else if (p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
                 float gg[8], rr[8];
                 unpack8(*reinterpret_cast<const bf16x8*>(grow + c * 32 + i), gg);
@@ -239,8 +247,9 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
                       const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
-                      int64_t rows_per_gate, advgrpo_stream_t stream) {
+                      int64_t rows_per_gate, void* preact_out, advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(A && W && C, "gemm_bf16: null pointer");
+  ADVGRPO_CHECK_ARG(!preact_out || aligned16(preact_out), "gemm_bf16: preact_out alignment");
   ADVGRPO_CHECK_ARG(M >= 1 && N >= 8 && K >= 64, "gemm_bf16: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0, "gemm_bf16: K must be a multiple of 64 and N of 8 (K=%lld N=%lld)", (long long)K, (long long)N);
   ADVGRPO_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_bf16: leading dimensions must be multiples of 8");
@@ -285,6 +294,7 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
   }
   GParams p;
   p.C = (__nv_bfloat16*)C;
+  p.preact = (__nv_bfloat16*)preact_out;
   p.bias = (const __nv_bfloat16*)bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.gate = (const __nv_bfloat16*)gate;

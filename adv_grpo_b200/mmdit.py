@@ -1,0 +1,375 @@
+"""SD3 / SD3.5-medium MMDiT(-X) on the libadvgrpo_b200 kernels: the `pipeline.transformer` object of
+the reference's rollout (`fast.py:630-637`) and replay (`train_sd3_fast_pickscore.py:233-255`),
+i.e. diffusers' `SD3Transformer2DModel` wrapped by the peft LoRA of
+`train_sd3_fast_pickscore.py:488-505`, re-designed for B200:
+
+  * token-major bf16 activations end to end, no head transposes: the fused QKV projection writes
+    [B, S, 3*H*D]; one kernel applies the per-head q/k RMSNorm and concatenates image + text rows
+    into the joint buffer the attention kernel reads through TMA; the attention kernel writes the
+    image / text rows of O into two contiguous buffers for the two out-projections;
+  * every linear is the tcgen05 GEMM with its epilogue fused (bias, GELU-tanh, gate * y + residual)
+    and the LoRA update accumulated into the same TMEM accumulator as a second product;
+  * all adaLN modulation vectors of all 24 blocks come from ONE weight-bandwidth-bound GEMM per
+    forward (the conditioning vector is shared by every block);
+  * rollout (no_grad) and training replay run the SAME fused forward arithmetic, so
+    ratio = exp(logp - logp_old) is exactly 1 for unchanged weights and identical inputs.
+
+Gradients flow to the LoRA A/B matrices only (everything else is frozen); the backward of each
+linear is dX = dY W (one tcgen05 GEMM against the pre-transposed weight, plus the LoRA term as a
+second product); the tiny LoRA weight gradients are plain library GEMMs (cuBLAS via torch.matmul).
+
+State-dict names follow diffusers / peft so released checkpoints map one to one.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .weights import LORA_TARGETS
+
+
+# ------------------------------------------------------------------------------ helpers
+def _sincos_1d(dim, pos):
+    omega = torch.arange(dim // 2, dtype=torch.float64, device=pos.device) / (dim / 2.0)
+    omega = 1.0 / 10000 ** omega
+    out = pos.reshape(-1).to(torch.float64)[:, None] * omega[None]
+    return torch.cat([out.sin(), out.cos()], dim=1)
+
+
+def cropped_pos_embed(dim, h, w, max_size, base_size, device):
+    """Centre crop of diffusers' fixed 2-D sincos table (PatchEmbed.cropped_pos_embed), built
+    directly for the crop instead of materialising the 384 x 384 x dim buffer."""
+    top, left = (max_size - h) // 2, (max_size - w) // 2
+    gh = torch.arange(top, top + h, dtype=torch.float64, device=device) / (max_size / base_size)
+    gw = torch.arange(left, left + w, dtype=torch.float64, device=device) / (max_size / base_size)
+    g0 = gw[None, :].expand(h, w)
+    g1 = gh[:, None].expand(h, w)
+    emb = torch.cat([_sincos_1d(dim // 2, g0), _sincos_1d(dim // 2, g1)], dim=1)
+    return emb.to(torch.float32).reshape(1, h * w, dim)
+
+
+def timestep_embedding(t, dim=256, max_period=10000):
+    half = dim // 2
+    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half
+    emb = t.float()[:, None] * exponent.exp()[None]
+    return torch.cat([emb.cos(), emb.sin()], dim=-1)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = epi(x W^T + (x A^T)(sB)^T + b) on the tcgen05 GEMM; backward w.r.t. x and the LoRA factors."""
+
+    @staticmethod
+    def forward(ctx, x, w, wt_holder, bias, lora_a, lora_w2, epilogue, residual, gate, rows_per_gate):
+        M = x.numel() // x.shape[-1]
+        t = None
+        if lora_a is not None:
+            t = ops.gemm(x, lora_a)                                   # [.., r_pad]
+        need_grad = torch.is_grad_enabled() or any(ctx.needs_input_grad)
+        preact = None
+        if epilogue in (ops.EPI_GELU_TANH, ops.EPI_GELU_ERF) and any(ctx.needs_input_grad):
+            preact = torch.empty((M, w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        y = ops.gemm(x, w, bias=bias, a2=t, w2=lora_w2, epilogue=epilogue, residual=residual, gate=gate,
+                     rows_per_gate=rows_per_gate, preact_out=preact)
+        ctx.save_for_backward(x, t, lora_a, lora_w2, gate, preact)
+        ctx.meta = (wt_holder, epilogue, rows_per_gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, t, lora_a, lora_w2, gate, preact = ctx.saved_tensors
+        wt_holder, epilogue, rows_per_gate = ctx.meta
+        dy = dy.contiguous()
+        lead = dy.shape[:-1]
+        N = dy.shape[-1]
+        dy2 = dy.reshape(-1, N)
+        d_res = None
+        if epilogue == ops.EPI_GATE_RESIDUAL:
+            d_res = dy
+            g = gate.reshape(gate.shape[0], 1, N)
+            dy2 = (dy2.reshape(gate.shape[0], rows_per_gate, N) * g).reshape(-1, N)
+        elif epilogue == ops.EPI_GELU_TANH:
+            dy2 = torch.ops.aten.gelu_backward(dy2, preact, approximate="tanh")
+        elif epilogue == ops.EPI_GELU_ERF:
+            dy2 = torch.ops.aten.gelu_backward(dy2, preact, approximate="none")
+        dx = da = dw2 = None
+        dt = None
+        if lora_a is not None:
+            dt = ops.gemm(dy2, lora_w2.t().contiguous())               # dY (sB) -> [M, r_pad]
+            x2 = x.reshape(-1, x.shape[-1])
+            if ctx.needs_input_grad[4]:
+                da = (dt.t() @ x2)                                     # [r_pad, K]   (library GEMM)
+            if ctx.needs_input_grad[5]:
+                dw2 = (dy2.t() @ t.reshape(-1, t.shape[-1]))           # [N, r_pad]   (library GEMM)
+        if ctx.needs_input_grad[0]:
+            wt = wt_holder()
+            if dt is not None:
+                dx = ops.gemm(dy2, wt, a2=dt, w2=lora_a.t().contiguous())
+            else:
+                dx = ops.gemm(dy2, wt)
+            dx = dx.reshape(*lead, wt.shape[0])
+        return dx, None, None, None, da, dw2, None, d_res, None, None
+
+
+class _WT:
+    """Lazily materialised transposed copy of a frozen weight (only layers that back-propagate
+    to their input ever build one)."""
+
+    def __init__(self, w):
+        self.w, self.wt = w, None
+
+    def __call__(self):
+        if self.wt is None:
+            self.wt = self.w.t().contiguous()
+        return self.wt
+
+
+class SD3Transformer2DModel(torch.nn.Module):
+    def __init__(self, cfg, params, lora_rank=32, lora_alpha=64, lora=None, device="cuda"):
+        super().__init__()
+        self.cfg = dict(cfg)
+        self.config = type("Config", (), dict(in_channels=cfg["in_channels"], patch_size=cfg["patch_size"],
+                                              sample_size=cfg["base_size"] * cfg["patch_size"],
+                                              joint_attention_dim=cfg["joint_dim"]))()
+        self.device_ = torch.device(device)
+        d = cfg["heads"] * cfg["head_dim"]
+        self.d = d
+        p = {k: v.to(device=self.device_, dtype=torch.bfloat16) for k, v in params.items()}
+        self.p = p
+        L = cfg["num_layers"]
+        # ---- pack per-block weights (the originals stay reachable as views: state_dict()) ----
+        self.blocks = []
+        ada_w, ada_b, self.ada_off = [], [], []
+        off = 0
+        for i in range(L):
+            b = f"transformer_blocks.{i}"
+            last, dual = i == L - 1, i in cfg["dual_layers"]
+            blk = dict(last=last, dual=dual, idx=i)
+
+            def cat(names, suffix):
+                return torch.cat([p[f"{b}.{n}.{suffix}"] for n in names], 0).contiguous()
+
+            blk["w_qkv"], blk["b_qkv"] = cat(("attn.to_q", "attn.to_k", "attn.to_v"), "weight"), cat(("attn.to_q", "attn.to_k", "attn.to_v"), "bias")
+            blk["w_cqkv"] = cat(("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj"), "weight")
+            blk["b_cqkv"] = cat(("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj"), "bias")
+            if dual:
+                blk["w_qkv2"], blk["b_qkv2"] = cat(("attn2.to_q", "attn2.to_k", "attn2.to_v"), "weight"), cat(("attn2.to_q", "attn2.to_k", "attn2.to_v"), "bias")
+            for key, name in (("out", "attn.to_out.0"), ("cout", "attn.to_add_out"), ("out2", "attn2.to_out.0"),
+                              ("ff1", "ff.net.0.proj"), ("ff2", "ff.net.2"), ("cff1", "ff_context.net.0.proj"),
+                              ("cff2", "ff_context.net.2")):
+                if f"{b}.{name}.weight" in p:
+                    blk["w_" + key], blk["b_" + key] = p[f"{b}.{name}.weight"], p[f"{b}.{name}.bias"]
+            for key in [k for k in blk if k.startswith("w_")]:
+                blk["wt_" + key[2:]] = _WT(blk[key])
+            if cfg["qk_norm"]:
+                for key, name in (("nq", "attn.norm_q"), ("nk", "attn.norm_k"), ("ncq", "attn.norm_added_q"),
+                                  ("nck", "attn.norm_added_k"), ("nq2", "attn2.norm_q"), ("nk2", "attn2.norm_k")):
+                    if f"{b}.{name}.weight" in p:
+                        blk[key] = p[f"{b}.{name}.weight"]
+            nx = 9 if dual else 6
+            nc = 2 if last else 6
+            ada_w += [p[f"{b}.norm1.linear.weight"], p[f"{b}.norm1_context.linear.weight"]]
+            ada_b += [p[f"{b}.norm1.linear.bias"], p[f"{b}.norm1_context.linear.bias"]]
+            self.ada_off.append((off, off + nx * d))
+            off += (nx + nc) * d
+            self.blocks.append(blk)
+        ada_w += [p["norm_out.linear.weight"]]
+        ada_b += [p["norm_out.linear.bias"]]
+        self.ada_out_off = off
+        self.ada_w = torch.cat(ada_w, 0).contiguous()
+        self.ada_b = torch.cat(ada_b, 0).contiguous()
+        self.w_patch = p["pos_embed.proj.weight"].reshape(d, -1).contiguous()
+        self._pos_cache = {}
+        # ---- LoRA (fp32 master parameters, peft layout) ----
+        self.lora_rank, self.lora_scale = lora_rank, lora_alpha / lora_rank
+        self.lora_A = torch.nn.ParameterDict()
+        self.lora_B = torch.nn.ParameterDict()
+        self._lora_names = []
+        if lora_rank:
+            for i in range(L):
+                for t in LORA_TARGETS:
+                    name = f"transformer_blocks.{i}.{t}"
+                    if name + ".weight" not in p:
+                        continue
+                    key = name.replace(".", "_")
+                    if lora is not None:
+                        a, bb = lora[name]
+                    else:
+                        a = torch.randn(lora_rank, d) / lora_rank
+                        bb = torch.zeros(d, lora_rank)
+                    self.lora_A[key] = torch.nn.Parameter(a.to(self.device_, torch.float32))
+                    self.lora_B[key] = torch.nn.Parameter(bb.to(self.device_, torch.float32))
+                    self._lora_names.append(name)
+        self._lora_cache = None
+        self._lora_enabled = True
+
+    # ------------------------------------------------------------------ peft-like surface
+    def trainable_parameters(self):
+        return list(self.lora_A.values()) + list(self.lora_B.values())
+
+    def lora_state_dict(self):
+        out = {}
+        for name in self._lora_names:
+            key = name.replace(".", "_")
+            out[f"base_model.model.{name}.lora_A.weight"] = self.lora_A[key].detach()
+            out[f"base_model.model.{name}.lora_B.weight"] = self.lora_B[key].detach()
+        return out
+
+    def invalidate_lora_cache(self):
+        """Call after an optimizer step / EMA swap changed the LoRA parameters."""
+        self._lora_cache = None
+
+    class _Disable:
+        def __init__(self, m):
+            self.m = m
+
+        def __enter__(self):
+            self.prev = self.m._lora_enabled
+            self.m._lora_enabled = False
+
+        def __exit__(self, *a):
+            self.m._lora_enabled = self.prev
+
+    def disable_adapter(self):
+        return SD3Transformer2DModel._Disable(self)
+
+    # ------------------------------------------------------------------ LoRA operand packing
+    def _pack_lora(self):
+        """bf16 GEMM operands of the LoRA second product per fused linear: (A_pad [r_pad, K], sB_pad
+        [N, r_pad]) with r_pad a multiple of 64 (zero padded; block-diagonal for fused QKV)."""
+        if not self.lora_rank or not self._lora_enabled:
+            return [dict() for _ in self.blocks]
+        grad = torch.is_grad_enabled() and any(q.requires_grad for q in self.lora_A.values())
+        if not grad and self._lora_cache is not None:
+            return self._lora_cache
+        r, s, d = self.lora_rank, self.lora_scale, self.d
+        packs = []
+        for blk in self.blocks:
+            i = blk["idx"]
+            pk = {}
+
+            def get(t):
+                key = f"transformer_blocks.{i}.{t}".replace(".", "_")
+                return (self.lora_A[key], self.lora_B[key]) if key in self.lora_A else None
+
+            def fused(names):
+                ab = [get(n) for n in names]
+                rp = ((len(ab) * r + 63) // 64) * 64
+                a = torch.cat([x[0] for x in ab] + [torch.zeros(rp - len(ab) * r, d, device=self.device_)], 0)
+                w2 = torch.zeros(len(ab) * d, rp, device=self.device_)
+                cols = [F.pad(s * x[1], (j * r, rp - (j + 1) * r)) for j, x in enumerate(ab)]
+                w2 = torch.cat(cols, 0)
+                return a.to(torch.bfloat16), w2.to(torch.bfloat16)
+
+            pk["qkv"] = fused(("attn.to_q", "attn.to_k", "attn.to_v"))
+            pk["cqkv"] = fused(("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj"))
+            pk["out"] = fused(("attn.to_out.0",))
+            if get("attn.to_add_out") is not None:
+                pk["cout"] = fused(("attn.to_add_out",))
+            packs.append(pk)
+        if not grad:
+            self._lora_cache = packs
+        return packs
+
+    # ------------------------------------------------------------------ building blocks
+    def _lin(self, x, blk, key, lora_pack=None, epilogue=ops.EPI_NONE, residual=None, gate=None, rows=1):
+        a = w2 = None
+        if lora_pack is not None and key in lora_pack:
+            a, w2 = lora_pack[key]
+        return _LinearFn.apply(x, blk["w_" + key], blk["wt_" + key], blk["b_" + key], a, w2, epilogue, residual,
+                               gate, rows)
+
+    def _attention(self, joint, split):
+        if torch.is_grad_enabled() and joint.requires_grad:
+            o = ops.attention(joint)                               # [B, S, H, D]
+            B, S = o.shape[:2]
+            o = o.reshape(B, S, self.d)
+            if split:
+                return o[:, :split].contiguous(), o[:, split:].contiguous()
+            return o, None
+        o, _ = ops.attention_fwd(joint, want_lse=False, split=split)
+        if split:
+            return o[0].reshape(o[0].shape[0], -1, self.d), o[1].reshape(o[1].shape[0], -1, self.d)
+        return o.reshape(o.shape[0], -1, self.d), None
+
+    def _block(self, blk, x, c, emb, pk):
+        d, H, D = self.d, self.cfg["heads"], self.cfg["head_dim"]
+        B, N, _ = x.shape
+        Nc = c.shape[1]
+        o0, o1 = self.ada_off[blk["idx"]]
+        ex = emb[:, o0:o1]
+        ec = emb[:, o1:o1 + (2 if blk["last"] else 6) * d]
+        ch = lambda e, k: e[:, k * d:(k + 1) * d]
+        # image stream: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (, shift2, scale2, gate2)
+        if blk["dual"]:
+            x1, x2 = ops.ln_modulate(x, ch(ex, 0), ch(ex, 1), ch(ex, 6), ch(ex, 7))
+        else:
+            x1 = ops.ln_modulate(x, ch(ex, 0), ch(ex, 1))
+        if blk["last"]:
+            c1 = ops.ln_modulate(c, ch(ec, 1), ch(ec, 0))           # AdaLayerNormContinuous: (scale, shift)
+        else:
+            c1 = ops.ln_modulate(c, ch(ec, 0), ch(ec, 1))
+        qkv_x = self._lin(x1, blk, "qkv", pk)
+        qkv_c = self._lin(c1, blk, "cqkv", pk)
+        joint = ops.qk_norm_concat(qkv_x, qkv_c, blk.get("nq"), blk.get("nk"), blk.get("ncq"), blk.get("nck"), H, D)
+        ox, oc = self._attention(joint, N)
+        x = self._lin(ox, blk, "out", pk, ops.EPI_GATE_RESIDUAL, x, ch(ex, 2), N)
+        if blk["dual"]:
+            qkv2 = self._lin(x2, blk, "qkv2")
+            j2 = ops.qk_norm_concat(qkv2, None, blk.get("nq2"), blk.get("nk2"), None, None, H, D)
+            o2, _ = self._attention(j2, 0)
+            x = self._lin(o2, blk, "out2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 8), N)
+        xm = ops.ln_modulate(x, ch(ex, 3), ch(ex, 4))
+        hmid = self._lin(xm, blk, "ff1", None, ops.EPI_GELU_TANH)
+        x = self._lin(hmid, blk, "ff2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 5), N)
+        if blk["last"]:
+            return x, None
+        c = self._lin(oc, blk, "cout", pk, ops.EPI_GATE_RESIDUAL, c, ch(ec, 2), Nc)
+        cm = ops.ln_modulate(c, ch(ec, 3), ch(ec, 4))
+        hmid = self._lin(cm, blk, "cff1", None, ops.EPI_GELU_TANH)
+        c = self._lin(hmid, blk, "cff2", None, ops.EPI_GATE_RESIDUAL, c, ch(ec, 5), Nc)
+        return x, c
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, hidden_states, timestep, encoder_hidden_states, pooled_projections,
+                joint_attention_kwargs=None, return_dict=False, upto=None):
+        cfg, p, d = self.cfg, self.p, self.d
+        ps = cfg["patch_size"]
+        B, C, Hh, Ww = hidden_states.shape
+        h, w = Hh // ps, Ww // ps
+        bf = torch.bfloat16
+        # patch embed = GEMM over unfolded 2x2 patches (+ fixed sincos positions)
+        xp = hidden_states.to(bf).reshape(B, C, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * h * w, C * ps * ps)
+        key = (h, w)
+        if key not in self._pos_cache:
+            self._pos_cache[key] = cropped_pos_embed(d, h, w, cfg["pos_embed_max_size"], cfg["base_size"],
+                                                     self.device_).to(bf)
+        x = ops.gemm(xp.contiguous(), self.w_patch, bias=p["pos_embed.proj.bias"]).reshape(B, h * w, d)
+        x = x + self._pos_cache[key]
+        # conditioning vector and every block's adaLN modulation in one GEMM
+        te = timestep_embedding(timestep.to(self.device_)).to(bf)
+        lin = lambda n, v: F.linear(v, p[n + ".weight"], p[n + ".bias"])
+        temb = lin("time_text_embed.timestep_embedder.linear_2", F.silu(lin("time_text_embed.timestep_embedder.linear_1", te)))
+        temb = temb + lin("time_text_embed.text_embedder.linear_2",
+                          F.silu(lin("time_text_embed.text_embedder.linear_1", pooled_projections.to(bf))))
+        emb = ops.gemm(F.silu(temb).contiguous(), self.ada_w, bias=self.ada_b)            # [B, sum]
+        c = ops.gemm(encoder_hidden_states.to(bf).contiguous(), p["context_embedder.weight"],
+                     bias=p["context_embedder.bias"])
+        pk = self._pack_lora()
+        nblk = len(self.blocks) if upto is None else upto
+        for blk, lp in zip(self.blocks[:nblk], pk):
+            x, c = self._block(blk, x, c, emb, lp)
+        if upto is not None:
+            return x, c
+        eo = emb[:, self.ada_out_off:self.ada_out_off + 2 * d]
+        x = ops.ln_modulate(x, eo[:, d:], eo[:, :d])                                       # (scale, shift) order
+        x = _LinearFn.apply(x, p["proj_out.weight"], self._proj_wt(), p["proj_out.bias"], None, None, ops.EPI_NONE,
+                            None, None, 1)
+        cin = cfg["in_channels"]
+        x = x.reshape(B, h, w, ps, ps, cin).permute(0, 5, 1, 3, 2, 4).reshape(B, cin, h * ps, w * ps)
+        return (x,)
+
+    def _proj_wt(self):
+        if not hasattr(self, "_proj_wt_holder"):
+            self._proj_wt_holder = _WT(self.p["proj_out.weight"])
+        return self._proj_wt_holder

@@ -263,21 +263,28 @@ def qk_norm_concat(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D=64, ep
 
 
 # --------------------------------------------------------------------------- attention
-def attention_fwd(qkv, scale=None, causal=False, want_lse=True, variant=0):
+def attention_fwd(qkv, scale=None, causal=False, want_lse=True, variant=0, split=0):
+    """Returns (out, lse); with 0 < split < S, out is the pair (out[:, :split], out[:, split:]) written
+    as two contiguous tensors (image rows / text rows of the joint sequence)."""
     _need_cuda(qkv)
     qkv = _bf16c(qkv)
     B, S, three, H, D = qkv.shape
     assert three == 3
     scale = (1.0 / math.sqrt(D)) if scale is None else scale
-    out = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=qkv.device)
+    out2 = None
+    if split:
+        out = torch.empty((B, split, H, D), dtype=torch.bfloat16, device=qkv.device)
+        out2 = torch.empty((B, S - split, H, D), dtype=torch.bfloat16, device=qkv.device)
+    else:
+        out = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device) if want_lse else None
     if variant:
         _lib.call("advgrpo_attn_fwd_variant", _ptr(qkv), _ptr(out), _ptr(lse), B, S, H, D, float(scale),
                   int(causal), int(variant), _stream())
     else:
-        _lib.call("advgrpo_attn_fwd", _ptr(qkv), _ptr(out), _ptr(lse), B, S, H, D, float(scale), int(causal),
-                  _stream())
-    return out, lse
+        _lib.call("advgrpo_attn_fwd", _ptr(qkv), _ptr(out), _ptr(out2), int(split), _ptr(lse), B, S, H, D,
+                  float(scale), int(causal), _stream())
+    return ((out, out2) if split else out), lse
 
 
 def attention_bwd(qkv, out, dout, lse, scale=None, causal=False):
@@ -319,7 +326,7 @@ EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL = 0, 1, 2, 3
 
 
 def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, gate=None,
-         rows_per_gate=1, out=None):
+         rows_per_gate=1, out=None, preact_out=None):
     """C = epi(a @ w.T (+ a2 @ w2.T) + bias).  a [M,K], w [N,K] bf16 row-major (strided rows ok)."""
     _need_cuda(a, w)
     lead = a.shape[:-1]
@@ -340,7 +347,7 @@ def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, ga
     _lib.call("advgrpo_gemm_bf16", _ptr(a2d), a2d.stride(0), _ptr(w), w.stride(0), _ptr(a2),
               0 if a2 is None else a2.stride(0), _ptr(w2), 0 if w2 is None else w2.stride(0), K2, _ptr(bias),
               _ptr(c2d), c2d.stride(0), M, N, K, int(epilogue), _ptr(r2d), 0 if r2d is None else r2d.stride(0),
-              _ptr(gate), 0 if gate is None else gate.stride(0), int(rows_per_gate), _stream())
+              _ptr(gate), 0 if gate is None else gate.stride(0), int(rows_per_gate), _ptr(preact_out), _stream())
     return c2d.reshape(*lead, N)
 
 

@@ -162,13 +162,16 @@ int advgrpo_qk_norm_concat_bwd(const void* qkv_img, const void* qkv_txt, const v
  * 235-255), transformers CLIPAttention (PickScore ViT-H/14 towers,
  * adv_grpo/pickscore_scorer.py:40-43) and timm Attention (DINOv2-B/14,
  * adv_grpo/rewards.py:397).
- * qkv: bf16 [B, S, 3, H, D] token-major; out: bf16 [B, S, H, D];
+ * qkv: bf16 [B, S, 3, H, D] token-major; out: bf16 [B, S, H, D].  If out2 != NULL the output
+ * rows are split like the joint sequence (JointAttnProcessor2_0: image rows, then text rows):
+ * rows [0, S_split) -> out [B, S_split, H, D], rows [S_split, S) -> out2 [B, S - S_split, H, D].
  * lse: f32 [B, H, S] natural-log-sum-exp of the scaled scores (NULL to skip; needed by bwd).
  * D in {64, 128}; any S >= 1 (ragged tail masked); causal != 0 applies the lower-
  * triangular mask (CLIP text tower).
  */
-int advgrpo_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
-                     int64_t D, float scale, int causal, advgrpo_stream_t stream);
+int advgrpo_attn_fwd(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B,
+                     int64_t S, int64_t H, int64_t D, float scale, int causal,
+                     advgrpo_stream_t stream);
 /* dqkv: bf16 [B, S, 3, H, D].  workspace: advgrpo_attn_bwd_workspace_bytes(...) bytes. */
 size_t advgrpo_attn_bwd_workspace_bytes(int64_t B, int64_t S, int64_t H, int64_t D);
 int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
@@ -185,7 +188,9 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
  * (A2 = x A_lora^T, W2 = scale * B_lora; train_sd3_fast_pickscore.py:488-505).
  * epilogue: ADVGRPO_EPI_*.  GATE_RESIDUAL: C = residual + gate[row / rows_per_gate] * (.)
  * with gate bf16 rows of stride gate_stride (the adaLN gate chunk).
- * K, K2 multiples of 64; N multiple of 16; M arbitrary.
+ * GELU_*: applied to the bf16-rounded pre-activation z = bf16(acc + bias); if preact_out != NULL,
+ * z is also stored there (bf16 [M, N], leading dimension ldc) for the backward pass.
+ * K, K2 multiples of 64; N multiple of 8; M arbitrary.
  */
 #define ADVGRPO_EPI_NONE 0
 #define ADVGRPO_EPI_GELU_TANH 1
@@ -195,7 +200,7 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
                       const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
-                      int64_t rows_per_gate, advgrpo_stream_t stream);
+                      int64_t rows_per_gate, void* preact_out, advgrpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * A8a preprocessing: the reward image path of adv_grpo/rewards.py:581-584 +

@@ -76,6 +76,63 @@ def probe_attn_causal():
     _attn(1, S=300, causal=True)
 
 
+def probe_attn_bwd():
+    import torch
+    from adv_grpo_b200 import ops
+    for (B, S, H) in [(1, 128, 1), (1, 256, 1), (1, 1229, 2)]:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        qkv = torch.randn(B, S, 3, H, 64, device="cuda", generator=g).bfloat16()
+        dout = torch.randn(B, S, H, 64, device="cuda", generator=g).bfloat16()
+        out, lse = ops.attention_fwd(qkv)
+        dqkv = ops.attention_bwd(qkv, out, dout, lse)
+        torch.cuda.synchronize()
+        ref_in = qkv.float().requires_grad_(True)
+        q, k, v = (ref_in[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3)
+        (o * dout.float()).sum().backward()
+        for i, n in enumerate("qkv"):
+            got, ref = dqkv[:, :, i].float(), ref_in.grad[:, :, i]
+            err = (got - ref).abs().max().item() / ref.abs().max().item()
+            print(f"attn bwd S={S} d{n}: rel err {err:.3e}", flush=True)
+            if err > 3e-2:
+                print("  got", got[0, 0, 0, :4].tolist(), "ref", ref[0, 0, 0, :4].tolist())
+                print("  got r70", got[0, 70 % S, 0, :4].tolist(), "ref", ref[0, 70 % S, 0, :4].tolist())
+
+
+def probe_perf_bwd():
+    import torch
+    from adv_grpo_b200 import ops
+    B, S, H, D = 16, 1229, 24, 64
+    qkv = torch.randn(B, S, 3, H, D, device="cuda").bfloat16()
+    dout = torch.randn(B, S, H, D, device="cuda").bfloat16()
+    out, lse = ops.attention_fwd(qkv)
+    flops = 10 * B * H * S * S * D
+    for _ in range(3):
+        ops.attention_bwd(qkv, out, dout, lse)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.attention_bwd(qkv, out, dout, lse)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"attn bwd: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    go = dout.permute(0, 2, 1, 3)
+    for _ in range(3):
+        torch.autograd.grad(o, (q, k, v), go, retain_graph=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        torch.autograd.grad(o, (q, k, v), go, retain_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"torch SDPA bwd (library baseline): {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def probe_perf():
     import torch
     from adv_grpo_b200 import ops

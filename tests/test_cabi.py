@@ -42,7 +42,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
         _lib.call("advgrpo_grpo_clip_loss", None, None, None, 1, 4, 1e-5, 5.0, 1.0, None, None, None)
     assert b"null" in lib.advgrpo_last_error()
     with pytest.raises(_lib.AdvGrpoError, match="head_dim"):
-        _lib.call("advgrpo_attn_fwd", 16, 16, None, 1, 128, 4, 80, 0.1, 0, None)
+        _lib.call("advgrpo_attn_fwd", 16, 16, None, 0, None, 1, 128, 4, 80, 0.1, 0, None)
     assert _lib.query("advgrpo_sde_step_workspace_bytes", 8, 65536) > 0
 
 

@@ -127,3 +127,35 @@ def test_attention_fwd_d128_padded_clip_heads(ops, S):
     assert (out.float() - ref).abs().max().item() < 1.5e-2 * ref.abs().max().item()
     assert out[..., 80:].abs().max().item() == 0
     assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------ attention backward
+@pytest.mark.parametrize("B,S,H,causal", [(1, 128, 1, False), (1, 256, 2, False), (2, 461, 3, False),
+                                          (1, 1229, 2, False), (1, 1024, 1, False), (2, 300, 2, True)])
+def test_attention_bwd_d64(ops, B, S, H, causal):
+    g = torch.Generator(device=DEV).manual_seed(S + H)
+    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, S, H, 64, device=DEV, generator=g).bfloat16()
+    out, lse = ops.attention_fwd(qkv, causal=causal)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, causal=causal)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = (ref_in[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).permute(0, 2, 1, 3)
+    (o * dout.float()).sum().backward()
+    ref = ref_in.grad
+    for i, name in enumerate("qkv"):
+        got_i, ref_i = dqkv[:, :, i].float(), ref[:, :, i]
+        # P and dS are rounded to bf16 before the dV / dK / dQ products, grads stored in bf16
+        err = (got_i - ref_i).abs().max().item() / ref_i.abs().max().item()
+        assert err < 2e-2, (name, err)
+        cos = torch.nn.functional.cosine_similarity(got_i.flatten(), ref_i.flatten(), dim=0).item()
+        assert cos > 0.9995, (name, cos)
+
+
+def test_attention_autograd_function(ops):
+    g = torch.Generator(device=DEV).manual_seed(0)
+    qkv = torch.randn(2, 333, 3, 4, 64, device=DEV, generator=g).bfloat16().requires_grad_(True)
+    w = torch.randn(2, 333, 4, 64, device=DEV, generator=g)
+    out = ops.attention(qkv)
+    (out.float() * w).sum().backward()
+    assert qkv.grad is not None and qkv.grad.shape == qkv.shape and torch.isfinite(qkv.grad.float()).all()
