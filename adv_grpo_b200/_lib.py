@@ -36,7 +36,7 @@ SIGNATURES = {
     "advgrpo_gemm_bf16": (c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _I64,
                                   _I64, _I, _P, _I64, _P, _I64, _I64, _P, _P]),
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
-    "advgrpo_clip_preprocess": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
+    "advgrpo_clip_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
 }
 # test/bench hooks that are exported but not part of include/advgrpo_b200.h
@@ -70,10 +70,26 @@ def load():
     return lib
 
 
+# kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
+_KERNELS_PER_CALL = {"advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2,
+                     "advgrpo_device_check": 0}
+_launches = [0]
+
+
+def launch_count():
+    return _launches[0]
+
+
+def add_launches(n):
+    """CUDA-graph replays re-launch the kernels recorded at capture time."""
+    _launches[0] += n
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise with the library's message on failure."""
     lib = load()
     rc = getattr(lib, name)(*args)
+    _launches[0] += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.advgrpo_last_error().decode("utf-8", "replace")
         raise AdvGrpoError(f"{name} failed ({rc}): {msg}")

@@ -28,7 +28,8 @@ struct GCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStagingBytes = 2 * BM * 128;   // two [128 x 64] bf16 epilogue tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN;   // 512 or 256
   static constexpr int kThreads = 192;
 };
@@ -56,16 +57,19 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
+            const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
             const GParams p) {
   using G = GCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::kStages * G::kStageBytes);
+  uint8_t* stage = smem + G::kStages * G::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + G::kStagingBytes);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + G::kStages;
   uint64_t* bar_acc_full = bar_empty + G::kStages;   // 2
   uint64_t* bar_acc_empty = bar_acc_full + 2;        // 2
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_res = bar_acc_empty + 2;             // 2
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_res + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,6 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
       mbar_init(&bar_acc_empty[i], 128);
+      mbar_init(&bar_res[i], 1);
     }
     fence_barrier_init();
   }
@@ -145,34 +150,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
   } else {
     // ============================== epilogue ==============================
+    // TMEM -> registers -> (bias / GELU / gate * y + residual) -> bf16 -> 128B-swizzled smem tile
+    // [128 rows x 64 cols] -> TMA store (coalesced, clipped at the M / N edges).  Two staging tiles
+    // alternate; the residual tile is TMA-prefetched INTO the staging tile and updated in place.
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const int tid = threadIdx.x;                       // 0..127
+    const int lrow = warp * 32 + lane;                 // row inside the tile
+    const bool has_res = p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL;
+    constexpr int NG = BN / 64;
+    uint32_t res_phase[2] = {0u, 0u};
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const int m0 = (tile / p.tiles_n) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      const int row = m0 + warp * 32 + lane;
+      const int row = m0 + lrow;
       const bool row_ok = row < p.M;
       mbar_wait(&bar_acc_full[acc], (local >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + lane_addr;
-      __nv_bfloat16* crow = p.C + (int64_t)row * p.ldc + n0;
-      const __nv_bfloat16* rrow = p.residual ? p.residual + (int64_t)row * p.ldr + n0 : nullptr;
       const __nv_bfloat16* grow =
           (p.gate && row_ok) ? p.gate + (int64_t)(row / p.rows_per_gate) * p.gate_stride + n0 : nullptr;
+      if (has_res && tid == 0) {
+        tma_store_wait_read<0>();
+        mbar_expect_tx(&bar_res[0], BM * 128);
+        tma_load_2d(stage, &tm_r, &bar_res[0], n0, m0);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_acc + c * 32, r);
-        tmem_wait_ld();
-        if (row_ok) {
+      for (int g = 0; g < NG; ++g) {
+        const int buf = g & 1;
+        uint8_t* sbuf = stage + buf * (BM * 128);
+        if (tid == 0) {
+          if (has_res) {
+            if (g + 1 < NG && n0 + (g + 1) * 64 < p.N) {
+              tma_store_wait_read<0>();              // staging tile buf^1 (store g-1) has been read out
+              mbar_expect_tx(&bar_res[buf ^ 1], BM * 128);
+              tma_load_2d(stage + (buf ^ 1) * (BM * 128), &tm_r, &bar_res[buf ^ 1], n0 + (g + 1) * 64, m0);
+            }
+          } else {
+            tma_store_wait_read<1>();                // store g-2 (same staging tile) has been read out
+          }
+        }
+        named_bar_sync(1, 128);
+        if (n0 + g * 64 >= p.N) break;               // uniform: whole 64-column group beyond N
+        if (has_res) {
+          mbar_wait(&bar_res[buf], res_phase[buf]);
+          res_phase[buf] ^= 1u;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = g * 2 + cc;
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             const int col = n0 + c * 32 + i;
-            if (col < p.N) {
-              float f[8];
+            const int piece = cc * 4 + i / 8;
+            uint8_t* sp = sbuf + lrow * 128 + ((piece ^ (lrow & 7)) * 16);
+            float f[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i + j]);
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i + j]);
+            if (col < p.N) {
               if (p.bias) {
                 float bb[8];
                 unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), bb);
@@ -183,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 // the activation is applied to the bf16-rounded pre-activation so that the fused
                 // forward is bit-identical to "store z in bf16, then GELU(z)" (training replay)
                 const bf16x8 z = pack8(f);
-                if (p.preact) *reinterpret_cast<bf16x8*>(p.preact + (int64_t)row * p.ldc + n0 + c * 32 + i) = z;
+                if (p.preact && row_ok) *reinterpret_cast<bf16x8*>(p.preact + (int64_t)row * p.ldc + col) = z;
                 unpack8(z, f);
                 if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
 #pragma unroll
@@ -192,21 +231,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
                 }
-              } else if (p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
-                float gg[8], rr[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(grow + c * 32 + i), gg);
-                unpack8(*reinterpret_cast<const bf16x8*>(rrow + c * 32 + i), rr);
+              } else if (has_res) {
+                float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
+                if (row_ok) unpack8(*reinterpret_cast<const bf16x8*>(grow + c * 32 + i), gg);
+                unpack8(*reinterpret_cast<const bf16x8*>(sp), rr);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaf(gg[j], f[j], rr[j]);
               }
-              *reinterpret_cast<bf16x8*>(crow + c * 32 + i) = pack8(f);
             }
+            *reinterpret_cast<bf16x8*>(sp) = pack8(f);
           }
         }
+        if (g == NG - 1 || n0 + (g + 1) * 64 >= p.N) {
+          tc_fence_before();
+          mbar_arrive(&bar_acc_empty[acc]);           // accumulator fully read: next tile may overwrite
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (tid == 0) {
+          tma_store_2d(&tm_c, sbuf, n0 + g * 64, m0);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&bar_acc_empty[acc]);
     }
+    if (tid == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -219,7 +267,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
 template <int BN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ta2,
-                const CUtensorMap& tw2, GParams& p, cudaStream_t st) {
+                const CUtensorMap& tw2, const CUtensorMap& tc, const CUtensorMap& tr, GParams& p,
+                cudaStream_t st) {
   using G = GCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -231,7 +280,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
   int tiles = p.tiles_m * p.tiles_n;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  gemm_kernel<BN><<<grid, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, p);
+  gemm_kernel<BN><<<grid, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, tc, tr, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -265,7 +314,7 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                           aligned16(residual) && aligned16(gate),
                       "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
   }
-  CUtensorMap ta, tw, ta2, tw2;
+  CUtensorMap ta, tw, ta2, tw2, tc, tr;
   const int BN = (N >= 256 && N % 256 == 0) ? 256 : 128;
   {
     const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
@@ -291,6 +340,18 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
       ta2 = ta;
       tw2 = tw;
     }
+    const uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t sc[2] = {0, (uint64_t)ldc * 2};
+    const uint32_t bc[2] = {64, BM};
+    rc = make_tmap_bf16(&tc, C, 2, dc, sc, bc, true);
+    if (rc) return rc;
+    if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+      const uint64_t sr[2] = {0, (uint64_t)ldr * 2};
+      rc = make_tmap_bf16(&tr, residual, 2, dc, sr, bc, true);
+      if (rc) return rc;
+    } else {
+      tr = tc;
+    }
   }
   GParams p;
   p.C = (__nv_bfloat16*)C;
@@ -301,8 +362,8 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
   p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.M = (int)M; p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = has2 ? (int)(K2 / BK) : 0;
   p.epilogue = epilogue;
-  if (BN == 256) return launch_gemm<256>(ta, tw, ta2, tw2, p, (cudaStream_t)stream);
-  return launch_gemm<128>(ta, tw, ta2, tw2, p, (cudaStream_t)stream);
+  if (BN == 256) return launch_gemm<256>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  return launch_gemm<128>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -66,8 +66,11 @@ __device__ __forceinline__ int quantise_bf16(__nv_bfloat16 v) {
   return (int)p;
 }
 
-// horizontal pass: bf16 [P, H, W] -> u8 [P, H, out]      (P = B*3 planes)
-__global__ void pil_horizontal_kernel(const __nv_bfloat16* __restrict__ img, int H, int W, int out,
+__device__ __forceinline__ int quantise_bf16(uint8_t v) { return (int)v; }   // already 8-bit (PIL input)
+
+// horizontal pass: bf16 or u8 [P, H, W] -> u8 [P, H, out]      (P = B*3 planes)
+template <typename InT>
+__global__ void pil_horizontal_kernel(const InT* __restrict__ img, int H, int W, int out,
                                       int ksize, const int* __restrict__ bounds,
                                       const int* __restrict__ kk, uint8_t* __restrict__ tmp) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,7 +80,7 @@ __global__ void pil_horizontal_kernel(const __nv_bfloat16* __restrict__ img, int
   if (idx >= (int64_t)H * out) return;
   const int y = (int)(idx / out), xx = (int)(idx % out);
   const int xmin = bounds[xx * 2], xmax = bounds[xx * 2 + 1];
-  const __nv_bfloat16* row = img + ((int64_t)plane * H + y) * W;
+  const InT* row = img + ((int64_t)plane * H + y) * W;
   int ss0 = 1 << (kPrecisionBits - 1);
   for (int x = 0; x < xmax; ++x) ss0 += quantise_bf16(row[xmin + x]) * kk[xx * ksize + x];
   tmp[((int64_t)plane * H + y) * out + xx] = clip8(ss0);
@@ -178,12 +181,12 @@ size_t advgrpo_clip_preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, 
   return coeff + (size_t)B * 3 * H * out + 256;
 }
 
-int advgrpo_clip_preprocess(const void* images, int64_t B, int64_t H, int64_t W, int64_t out,
+int advgrpo_clip_preprocess(const void* images, int images_u8, int64_t B, int64_t H, int64_t W, int64_t out,
                             const float* mean3, const float* std3, void* pixels, int pixels_f32,
                             uint8_t* u8_out, void* workspace, size_t workspace_bytes,
                             advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(images && mean3 && std3 && pixels, "clip_preprocess: null pointer");
-  ADVGRPO_CHECK_ARG(B >= 1 && H == W && H >= out && out >= 1, "clip_preprocess: square images with H >= out required (H=%lld W=%lld out=%lld)",
+  ADVGRPO_CHECK_ARG(B >= 1 && H == W && H >= 1 && out >= 1, "clip_preprocess: square images required (H=%lld W=%lld out=%lld)",
                     (long long)H, (long long)W, (long long)out);
   const int ks = pil_ksize((int)H, (int)out);
   ADVGRPO_CHECK_ARG(ks <= 64, "clip_preprocess: downscale factor too large");
@@ -198,8 +201,12 @@ int advgrpo_clip_preprocess(const void* images, int64_t B, int64_t H, int64_t W,
   pil_coeffs_kernel<<<(unsigned)((out + 127) / 128), 128, 0, st>>>((int)H, (int)out, ks, bounds, kk);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   const unsigned planes = (unsigned)(B * 3);
-  pil_horizontal_kernel<<<dim3((unsigned)((H * out + 255) / 256), planes), 256, 0, st>>>(
-      (const __nv_bfloat16*)images, (int)H, (int)W, (int)out, ks, bounds, kk, tmp);
+  if (images_u8)
+    pil_horizontal_kernel<uint8_t><<<dim3((unsigned)((H * out + 255) / 256), planes), 256, 0, st>>>(
+        (const uint8_t*)images, (int)H, (int)W, (int)out, ks, bounds, kk, tmp);
+  else
+    pil_horizontal_kernel<__nv_bfloat16><<<dim3((unsigned)((H * out + 255) / 256), planes), 256, 0, st>>>(
+        (const __nv_bfloat16*)images, (int)H, (int)W, (int)out, ks, bounds, kk, tmp);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   dim3 g2((unsigned)((out * out + 255) / 256), planes);
   if (pixels_f32)

@@ -201,6 +201,7 @@ class SD3Transformer2DModel(torch.nn.Module):
                     self.lora_B[key] = torch.nn.Parameter(bb.to(self.device_, torch.float32))
                     self._lora_names.append(name)
         self._lora_cache = None
+        self._lora_dirty = False
         self._lora_enabled = True
 
     # ------------------------------------------------------------------ peft-like surface
@@ -217,7 +218,7 @@ class SD3Transformer2DModel(torch.nn.Module):
 
     def invalidate_lora_cache(self):
         """Call after an optimizer step / EMA swap changed the LoRA parameters."""
-        self._lora_cache = None
+        self._lora_dirty = True
 
     class _Disable:
         def __init__(self, m):
@@ -240,8 +241,23 @@ class SD3Transformer2DModel(torch.nn.Module):
         if not self.lora_rank or not self._lora_enabled:
             return [dict() for _ in self.blocks]
         grad = torch.is_grad_enabled() and any(q.requires_grad for q in self.lora_A.values())
-        if not grad and self._lora_cache is not None:
+        if grad:
+            return self._build_lora_packs()
+        if self._lora_cache is not None and not self._lora_dirty:
             return self._lora_cache
+        with torch.no_grad():
+            packs = self._build_lora_packs()
+        if self._lora_cache is None:
+            self._lora_cache = packs
+        else:                                   # in place: captured CUDA graphs keep pointing at these buffers
+            for old, new in zip(self._lora_cache, packs):
+                for k in old:
+                    old[k][0].copy_(new[k][0])
+                    old[k][1].copy_(new[k][1])
+        self._lora_dirty = False
+        return self._lora_cache
+
+    def _build_lora_packs(self):
         r, s, d = self.lora_rank, self.lora_scale, self.d
         packs = []
         for blk in self.blocks:
@@ -256,7 +272,6 @@ class SD3Transformer2DModel(torch.nn.Module):
                 ab = [get(n) for n in names]
                 rp = ((len(ab) * r + 63) // 64) * 64
                 a = torch.cat([x[0] for x in ab] + [torch.zeros(rp - len(ab) * r, d, device=self.device_)], 0)
-                w2 = torch.zeros(len(ab) * d, rp, device=self.device_)
                 cols = [F.pad(s * x[1], (j * r, rp - (j + 1) * r)) for j, x in enumerate(ab)]
                 w2 = torch.cat(cols, 0)
                 return a.to(torch.bfloat16), w2.to(torch.bfloat16)
@@ -267,8 +282,6 @@ class SD3Transformer2DModel(torch.nn.Module):
             if get("attn.to_add_out") is not None:
                 pk["cout"] = fused(("attn.to_add_out",))
             packs.append(pk)
-        if not grad:
-            self._lora_cache = packs
         return packs
 
     # ------------------------------------------------------------------ building blocks

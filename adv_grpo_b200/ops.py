@@ -371,7 +371,8 @@ def _const3(vals, device):
 def clip_preprocess(images, out_size=224, dtype=torch.bfloat16, want_u8=False):
     """bf16 [B,3,H,W] in [0,1] -> CLIPProcessor pixel_values [B,3,out,out] (PIL-exact 8-bit resize)."""
     _need_cuda(images)
-    images = _bf16c(images)
+    is_u8 = images.dtype == torch.uint8
+    images = images.contiguous() if is_u8 else _bf16c(images)
     B, C, H, W = images.shape
     assert C == 3
     dev = images.device
@@ -379,7 +380,7 @@ def clip_preprocess(images, out_size=224, dtype=torch.bfloat16, want_u8=False):
     u8 = torch.empty((B, 3, out_size, out_size), dtype=torch.uint8, device=dev) if want_u8 else None
     ws_bytes = _lib.query("advgrpo_clip_preprocess_workspace_bytes", B, H, W, out_size)
     ws = _workspace("clip_pre", ws_bytes, dev)
-    _lib.call("advgrpo_clip_preprocess", _ptr(images), B, H, W, out_size, _ptr(_const3(CLIP_MEAN, dev)),
+    _lib.call("advgrpo_clip_preprocess", _ptr(images), int(is_u8), B, H, W, out_size, _ptr(_const3(CLIP_MEAN, dev)),
               _ptr(_const3(CLIP_STD, dev)), _ptr(pix), int(dtype == torch.float32), _ptr(u8), _ptr(ws),
               ws.numel(), _stream())
     return (pix, u8) if want_u8 else pix

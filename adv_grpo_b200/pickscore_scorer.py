@@ -1,0 +1,98 @@
+"""Drop-in for `adv_grpo/pickscore_scorer.py`: `PickScoreScorer(device, dtype)` exposing `.processor`
+(with `.tokenizer`), `.model` and `__call__(prompt, images) -> scores` (cosine * exp(logit_scale) / 26).
+
+B200-native path: images that are already CUDA tensors in [0,1] (what the rollout produces) are
+quantised, PIL-exact bicubic-resized to 224 and normalised by one preprocessing kernel chain -- no
+device->host->PIL->device trip (`adv_grpo/rewards.py:581-584`); the text tower runs ONCE per distinct
+prompt (the reference recomputes it for each of the G identical prompts); the score is a fused
+row-dot instead of the diagonal of a [B,B] matmul (`pickscore_scorer.py:47-51`).
+
+No tokenizer files or pretrained weights exist on the box: `processor.tokenizer` is a deterministic
+synthetic CLIP-shaped tokenizer (BOS, hashed word ids, EOS) unless a real one is supplied, and the
+model is seeded-random CLIP-ViT-H/14 unless a state dict is supplied.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+from . import ops
+from .clip import CLIPModel
+from .weights import CLIP_H, init_clip
+
+
+class SyntheticCLIPTokenizer:
+    bos, eos, vocab = 49406, 49407, 49408
+
+    def __init__(self, vocab=49408):
+        self.vocab = vocab
+        self.bos, self.eos = vocab - 2, vocab - 1
+
+    def _ids(self, text, max_length):
+        words = text.lower().split()
+        ids = [self.bos] + [1 + zlib.crc32(w.encode()) % (self.vocab - 3) for w in words][: max_length - 2] + [self.eos]
+        return ids
+
+    def __call__(self, text, padding=True, truncation=True, max_length=77, return_tensors="pt", **_):
+        if isinstance(text, str):
+            text = [text]
+        rows = [self._ids(t, max_length) for t in text]
+        width = max_length if padding == "max_length" else max(len(r) for r in rows)
+        out = np.zeros((len(rows), width), dtype=np.int64)
+        for i, r in enumerate(rows):
+            out[i, :len(r)] = r
+        return {"input_ids": torch.from_numpy(out), "attention_mask": torch.from_numpy((out != 0).astype(np.int64))}
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [" ".join(str(int(t)) for t in row if int(t) not in (0, self.bos, self.eos)) for row in ids]
+
+
+class CLIPProcessorLike:
+    """`processor(images=...)` / `processor(text=...)` / `processor.tokenizer(...)`."""
+
+    def __init__(self, tokenizer, device, size=224):
+        self.tokenizer, self.device, self.size = tokenizer, device, size
+
+    def __call__(self, images=None, text=None, return_tensors="pt", **kw):
+        if text is not None:
+            return self.tokenizer(text, **kw)
+        return {"pixel_values": images_to_pixel_values(images, self.device, self.size)}
+
+
+def images_to_pixel_values(images, device, size=224, dtype=torch.bfloat16):
+    """CUDA float tensor in [0,1] (bf16 quantisation semantics of rewards.py:581), uint8 tensor, or a list
+    of PIL images / HWC uint8 arrays (the reference's inputs) -> CLIP pixel_values on the device."""
+    if torch.is_tensor(images):
+        t = images.to(device)
+        t = t if t.dtype == torch.uint8 else t.to(torch.bfloat16)
+    else:
+        arr = np.stack([np.asarray(im) for im in images])            # [B,H,W,3] uint8
+        t = torch.from_numpy(arr).to(device).permute(0, 3, 1, 2).contiguous()
+    return ops.clip_preprocess(t, size, dtype=dtype)
+
+
+class PickScoreScorer(torch.nn.Module):
+    def __init__(self, device="cuda", dtype=torch.float32, cfg=CLIP_H, state_dict=None, tokenizer=None, seed=3):
+        super().__init__()
+        self.device, self.dtype = device, dtype
+        if state_dict is None:
+            state_dict = init_clip(cfg, seed=seed, device=device, dtype=torch.bfloat16)
+        # the kernels compute in bf16 (fp32 accumulation); dtype is recorded for API parity
+        self.model = CLIPModel.from_params(state_dict, cfg, device=device, dtype=torch.bfloat16)
+        self.processor = CLIPProcessorLike(tokenizer or SyntheticCLIPTokenizer(cfg["vocab"]), device, cfg["image"])
+
+    @torch.no_grad()
+    def __call__(self, prompt, images):
+        model = self.model.module if hasattr(self.model, "module") else self.model   # quirk Q3 tolerated
+        pixel_values = images_to_pixel_values(images, self.device, self.processor.size)
+        if isinstance(prompt, str):
+            prompt = [prompt]
+        uniq = list(dict.fromkeys(prompt))
+        ids = self.processor.tokenizer(uniq, padding=True, truncation=True, max_length=77)["input_ids"].to(self.device)
+        image_embs = model.get_image_features(pixel_values=pixel_values).float()
+        image_embs = image_embs / image_embs.norm(p=2, dim=-1, keepdim=True)
+        text_embs = model.get_text_features(input_ids=ids).float()
+        text_embs = text_embs / text_embs.norm(p=2, dim=-1, keepdim=True)
+        index = torch.tensor([uniq.index(p) for p in prompt], device=self.device)
+        scores = model.logit_scale.exp().float() * (text_embs[index] * image_embs).sum(-1)
+        return scores / 26

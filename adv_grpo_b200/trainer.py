@@ -1,0 +1,299 @@
+"""The GRPO epoch of `scripts/train_sd3_fast_pickscore.py:709-1191` / `train_sd3_fast_dino_patch.py`
+on the B200 kernels: SAMPLING (rollout + reward) -> gather + group advantage -> (discriminator step |
+generator step with the clipped policy-gradient loss).  One process per GPU; prompts shard across
+ranks (each rank rolls out whole G-sample groups); NCCL is used only for
+  * the packed all-gather of rewards + prompt ids (`train_pick:926-938,966`),
+  * the flat LoRA-gradient all-reduce at each accumulation boundary (`:1165-1171`, ZeRO-2 there),
+  * the discriminator parameter sync after a D step (north_star; the reference leaves per-rank
+    discriminators un-synchronised, quirk Q3 -- `sync_discriminator=False` reproduces that).
+Everything between the collectives stays on the device: no `.cpu().numpy()` of rewards, no tokenizer
+decode of prompt ids, no float64 host advantages.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
+from .ema import EMAModuleWrapper
+from .pick_score_training import CLIPCriterion, CLIPCriterionConfig
+from .pickscore_scorer import images_to_pixel_values
+from .rewards import multi_score
+from .sampler import DistributedKRepeatSampler
+from .stat_tracking import PerPromptStatTracker
+
+
+class SyntheticTextEmbedder:
+    """Stand-in for `compute_text_embeddings` (`train_pick:186-193`; the CLIP-L/G + T5-XXL encoders are
+    outside the hot path and no weights exist here): deterministic N(0,1) embeddings per prompt index
+    (SURVEY.md section 8d)."""
+
+    def __init__(self, joint_dim=4096, pooled_dim=2048, n_tokens=205, device="cuda"):
+        self.joint_dim, self.pooled_dim, self.n_tokens, self.device = joint_dim, pooled_dim, n_tokens, device
+
+    def __call__(self, prompt_index):
+        g = torch.Generator().manual_seed(1000 + int(prompt_index))
+        e = torch.randn(1, self.n_tokens, self.joint_dim, generator=g).to(self.device, torch.bfloat16)
+        p = torch.randn(1, self.pooled_dim, generator=g).to(self.device, torch.bfloat16)
+        return e, p
+
+    def negative(self):
+        g = torch.Generator().manual_seed(999)
+        e = torch.randn(1, self.n_tokens, self.joint_dim, generator=g).to(self.device, torch.bfloat16)
+        p = torch.randn(1, self.pooled_dim, generator=g).to(self.device, torch.bfloat16)
+        return e, p
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def all_gather_cat(t):
+    rank, world = _world()
+    if world == 1:
+        return t
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out
+
+
+def compute_log_prob(transformer, pipeline, sample, j, embeds, pooled_embeds, config):
+    """`train_pick:233-267`: transformer forward on the CFG batch + fused CFG / Flow-CPS replay log-prob."""
+    lat = sample["latents"][:, j]
+    ts = sample["timesteps"][:, j]
+    cfg = bool(config.train.cfg)
+    if cfg:
+        noise_pred = transformer(hidden_states=torch.cat([lat, lat]), timestep=torch.cat([ts, ts]),
+                                 encoder_hidden_states=embeds, pooled_projections=pooled_embeds, return_dict=False)[0]
+    else:
+        noise_pred = transformer(hidden_states=lat, timestep=ts, encoder_hidden_states=embeds,
+                                 pooled_projections=pooled_embeds, return_dict=False)[0]
+    log_prob, mean, std = ops.sde_logprob_replay(noise_pred, lat, sample["next_latents"][:, j], ts,
+                                                 pipeline.scheduler.timesteps, pipeline.scheduler.sigmas,
+                                                 config.sample.guidance_scale, config.sample.noise_level, cfg=cfg)
+    return sample["next_latents"][:, j], log_prob, mean, std
+
+
+class GRPOTrainer:
+    def __init__(self, config, pipeline, prompts, scorer=None, head=None, embedder=None, device="cuda",
+                 reference_image_fn=None, sync_discriminator=True):
+        self.config, self.pipeline, self.prompts, self.device = config, pipeline, list(prompts), device
+        self.rank, self.world = _world()
+        self.transformer = pipeline.transformer
+        self.scorer, self.head = scorer, head
+        self.embedder = embedder or SyntheticTextEmbedder(self.transformer.cfg["joint_dim"],
+                                                          self.transformer.cfg["pooled_dim"], device=device)
+        self.reference_image_fn = reference_image_fn or self._synthetic_reference
+        self.sync_discriminator = sync_discriminator
+        s, t = config.sample, config.train
+        self.params = self.transformer.trainable_parameters()
+        self.optimizer = torch.optim.AdamW(self.params, lr=t.learning_rate, betas=(t.adam_beta1, t.adam_beta2),
+                                           weight_decay=t.adam_weight_decay, eps=t.adam_epsilon, fused=True)
+        self.ema = EMAModuleWrapper(self.params, decay=0.9, update_step_interval=8, device=device) if t.ema else None
+        self.reward_fn = multi_score(device, dict(config.reward_fn))
+        self.reward_key = next(iter(dict(config.reward_fn)))
+        self.sampler = DistributedKRepeatSampler(self.prompts, s.train_batch_size,
+                                                 s.num_image_per_prompt // s.mini_num_image_per_prompt
+                                                 if s.get("shard_groups_across_ranks", False) else 1,
+                                                 self.world, self.rank, seed=42)
+        self.stat_tracker = PerPromptStatTracker(s.global_std, device=device)
+        self.neg_embeds, self.neg_pooled = self.embedder.negative()
+        self.generator = torch.Generator(device=device).manual_seed(config.seed + self.rank)
+        self.global_step = 0
+        self.epoch = 0
+        self.optimizer_D = None
+        if config.get("train_d", False):
+            if self.reward_key == "pickscore_cotrain":
+                self.criterion = CLIPCriterion(CLIPCriterionConfig())
+                self.optimizer_D = torch.optim.Adam(scorer.model.parameters(), lr=config.d_lr, betas=(0.5, 0.999))
+            elif head is not None:
+                self.optimizer_D = torch.optim.Adam(head.parameters(), lr=config.d_lr, betas=(0.5, 0.999))
+        self.last_info = {}
+
+    # ------------------------------------------------------------------ sampling
+    def _synthetic_reference(self, prompt_index, n, size):
+        g = torch.Generator().manual_seed(11 + int(prompt_index))
+        return torch.rand(n, 3, size, size, generator=g).to(self.device)
+
+    def _prompt_ids(self, prompt, n):
+        ids = self.pipeline.tokenizer([prompt], padding="max_length", max_length=256, truncation=True)["input_ids"]
+        return ids.to(self.device).repeat(n, 1)
+
+    def _score(self, images, prompts):
+        kw = dict(scorer=self.scorer)
+        if self.head is not None:
+            kw["head"] = self.head
+        details, _ = self.reward_fn(images.to(torch.bfloat16), prompts, [{}] * len(prompts), **kw)
+        return {k: torch.as_tensor(v, device=self.device).float() for k, v in details.items()}
+
+    @torch.no_grad()
+    def sample_epoch(self):
+        c, s = self.config, self.config.sample
+        G = s.mini_num_image_per_prompt
+        samples = []
+        self.transformer.eval()
+        for i in range(s.num_batches_per_epoch):
+            idx = self.sampler.indices_for_epoch(self.epoch * s.num_batches_per_epoch + i)[self.rank][0]
+            prompt = self.prompts[idx]
+            pe, pp = self.embedder(idx)
+            images, latents, log_probs, timesteps = pipeline_with_logprob_random(
+                self.pipeline, prompt_embeds=pe, pooled_prompt_embeds=pp, negative_prompt_embeds=self.neg_embeds,
+                negative_pooled_prompt_embeds=self.neg_pooled, num_inference_steps=s.num_steps,
+                guidance_scale=s.guidance_scale, output_type="pt", height=c.resolution, width=c.resolution,
+                noise_level=s.noise_level, mini_num_image_per_prompt=G, train_num_steps=s.train_num_steps,
+                process_index=self.rank, sample_num_steps=s.num_steps, random_timestep=s.get("random_timestep", 0),
+                generator=self.generator)
+            ref_images = self.reference_image_fn(idx, G, c.resolution)
+            prompts = [prompt] * G
+            lat = torch.stack(latents, dim=1)                       # [G, T+1, 16, h, w]   train_pick:806-810
+            samples.append({
+                "prompt_ids": self._prompt_ids(prompt, G),
+                "prompt_embeds": pe.repeat(G, 1, 1), "pooled_prompt_embeds": pp.repeat(G, 1),
+                "timesteps": torch.stack(timesteps, dim=1), "latents": lat[:, :-1], "next_latents": lat[:, 1:],
+                "log_probs": torch.stack(log_probs, dim=1),
+                "rewards": self._score(images, prompts), "reference_rewards": self._score(ref_images, prompts),
+                "images": images, "ref_images": ref_images, "prompts": prompts,
+            })
+        return samples
+
+    # ------------------------------------------------------------------ advantages
+    def compute_advantages(self, samples):
+        T = self.config.sample.train_num_steps
+        avg = torch.cat([s["rewards"]["avg"] for s in samples])                 # [N_local]
+        rewards = avg[:, None].repeat(1, T)                                       # train_pick:928
+        ids = torch.cat([s["prompt_ids"] for s in samples])
+        g_rewards, g_ids = all_gather_cat(rewards), all_gather_cat(ids)           # train_pick:930,966
+        adv = self.stat_tracker.update_device(g_ids, g_rewards)                   # float64 [N_total, T]
+        zero_std_ratio, reward_std_mean = self.stat_tracker.zero_std_stats()
+        group_size, _ = self.stat_tracker.get_stats()
+        self.stat_tracker.clear()
+        n = rewards.shape[0]
+        local = adv.reshape(self.world, n, T)[self.rank]                          # train_pick:995-999
+        self.last_info.update(reward_mean=g_rewards[:, 0].mean(), zero_std_ratio=zero_std_ratio,
+                              reward_std_mean=reward_std_mean, group_size=group_size)
+        return local
+
+    # ------------------------------------------------------------------ discriminator step
+    def discriminator_step(self, samples):
+        c = self.config
+        real = torch.cat([s["ref_images"] for s in samples])
+        fake = torch.cat([s["images"] for s in samples])
+        prompts = [p for s in samples for p in s["prompts"]]
+        if self.reward_key == "pickscore_cotrain":
+            model = self.scorer.model
+            for p in model.parameters():
+                p.requires_grad = False
+            for p in model.vision_model.encoder.layers[c.tune_layer:].parameters():   # train_pick:1016-1020
+                p.requires_grad = True
+            ids = self.scorer.processor.tokenizer(prompts, padding="max_length", truncation=True, max_length=77)["input_ids"].to(self.device)
+            # tensor_to_pil_list (train_pick:133-148): (x*255).astype(uint8) truncation, then CLIPProcessor
+            to_u8 = lambda x: (x.float().clamp(0, 1) * 255).to(torch.uint8)
+            batch = {"input_ids": ids, "pixels_0": images_to_pixel_values(to_u8(real), self.device),
+                     "pixels_1": images_to_pixel_values(to_u8(fake), self.device),
+                     "label_0": torch.tensor(1.0, device=self.device), "label_1": torch.tensor(0.0, device=self.device),
+                     "num_examples_per_prompt": torch.tensor(1.0, device=self.device)}
+            loss = self.criterion(model, batch)
+            params = [p for p in model.parameters() if p.requires_grad]
+        else:
+            with torch.no_grad():
+                fr = self.scorer.forward_features(ops.dino_preprocess(real, 518))
+                ff = self.scorer.forward_features(ops.dino_preprocess(fake, 518))
+            hp = next(self.head.parameters())
+            fr, ff = fr.to(hp.dtype), ff.to(hp.dtype)
+            relu = torch.nn.functional.relu
+            lr_, lf_ = self.head(fr[:, 0]).squeeze(-1), self.head(ff[:, 0]).squeeze(-1)
+            image_loss = 0.5 * (relu(1.0 - lr_).mean() + relu(1.0 + lf_).mean())
+            B, N, D = fr[:, 1:].shape
+            n_sel = min(64, N)
+            ir = torch.randint(0, N, (B, n_sel), device=self.device)
+            if_ = torch.randint(0, N, (B, n_sel), device=self.device)
+            sr = torch.gather(fr[:, 1:], 1, ir.unsqueeze(-1).expand(-1, -1, D))
+            sf = torch.gather(ff[:, 1:], 1, if_.unsqueeze(-1).expand(-1, -1, D))
+            patch_loss = 0.5 * (relu(1.0 - self.head(sr).squeeze(-1)).mean() + relu(1.0 + self.head(sf).squeeze(-1)).mean())
+            loss = image_loss + 0.3 * patch_loss                                      # train_dino:186-219
+            params = list(self.head.parameters())
+        self.optimizer_D.zero_grad()
+        loss.backward()
+        if self.world > 1 and self.sync_discriminator:
+            flat = torch.cat([p.grad.reshape(-1).float() for p in params])
+            dist.all_reduce(flat)
+            flat /= self.world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        self.optimizer_D.step()
+        return loss.detach()
+
+    # ------------------------------------------------------------------ generator step
+    def _sync_grads(self):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= self.world
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def train_generator(self, samples, advantages):
+        c, t = self.config, self.config.train
+        T = c.sample.train_num_steps
+        gas = t.gradient_accumulation_steps * T                      # Accelerator(grad_accum = gas * T), train_pick:426
+        self.transformer.train()
+        stats_acc = []
+        micro = 0
+        n_local = samples[0]["latents"].shape[0]
+        for i, sample in enumerate(samples):
+            if t.cfg:
+                embeds = torch.cat([self.neg_embeds.repeat(n_local, 1, 1), sample["prompt_embeds"]])
+                pooled = torch.cat([self.neg_pooled.repeat(n_local, 1), sample["pooled_prompt_embeds"]])
+            else:
+                embeds, pooled = sample["prompt_embeds"], sample["pooled_prompt_embeds"]
+            adv_i = advantages[i * n_local:(i + 1) * n_local]
+            for j in range(T):
+                _, log_prob, _, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c)
+                loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
+                                                 t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
+                loss.backward()
+                stats_acc.append(stats)
+                micro += 1
+                if micro % gas == 0:
+                    self._sync_grads()
+                    torch.nn.utils.clip_grad_norm_(self.params, t.max_grad_norm)
+                    self.optimizer.step()
+                    self.optimizer.zero_grad(set_to_none=False)
+                    self.transformer.invalidate_lora_cache()
+                    self.global_step += 1
+            if self.ema is not None:
+                self.ema.step(self.params, self.global_step)
+        if stats_acc:
+            m = torch.stack(stats_acc).mean(0)
+            self.last_info.update(loss=m[0], approx_kl=m[1], clipfrac=m[2], clipfrac_gt_one=m[3], clipfrac_lt_one=m[4],
+                                  policy_loss=m[5])
+
+    # ------------------------------------------------------------------ one epoch
+    def run_epoch(self):
+        c = self.config
+        samples = self.sample_epoch()
+        advantages = self.compute_advantages(samples)
+        did_d = False
+        if c.get("train_d", False) and self.optimizer_D is not None:
+            if self.reward_key == "pickscore_cotrain":
+                gen = all_gather_cat(torch.cat([s["rewards"][self.reward_key] for s in samples])).mean()
+                ref = all_gather_cat(torch.cat([s["reference_rewards"][self.reward_key] for s in samples])).mean()
+                did_d = bool(ref < gen)                                        # train_pick:1025 (one host sync per epoch)
+            else:
+                did_d = (self.epoch + 1) % c.d_times != 0                      # train_dino:1097
+        if did_d:
+            self.last_info["d_loss"] = self.discriminator_step(samples)
+            self.global_step += 1                                              # quirk Q8: G step skipped this epoch
+        else:
+            self.train_generator(samples, advantages)
+        self.epoch += 1
+        return {"did_d_step": did_d, "n_samples": sum(s["latents"].shape[0] for s in samples), **self.last_info}

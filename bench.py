@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the Adv-GRPO hot path (BASELINE.json metric: GRPO samples/sec, rollout + score + update,
+SD3.5-medium, 512x512, 10 denoise steps, G = 8, PickScore reward, LoRA r=32).
+
+    python bench.py --gpus N --steps K --warmup W           # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU cores
+
+One "step" = one GRPO epoch slice per rank: NB = 2 prompt groups of G = 8 images are rolled out
+(10 MMDiT steps at CFG batch 16, fused CFG/SDE/log-prob, VAE decode), scored (PickScore on generated and
+reference images), turned into group-relative advantages, and trained on (2 SDE-window timesteps per
+group, forward + backward through the LoRA MMDiT, clipped GRPO loss, all-reduce, clip + AdamW + EMA):
+2 optimizer steps per step, like the reference epoch.  value = samples (images) through that whole
+slice per second, summed over ranks.  Synthetic prompts / seeded random weights at the true shapes (no
+datasets or checkpoints exist on the box).  `e2e` repeats the measurement with every step's inputs
+(prompt embeddings, reference images) copied from pinned host memory and the step's metrics read back.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRPO samples/sec (rollout+score+update) SD3.5-medium 512x512 G=8 10-step PickScore LoRA"
+UNIT = "samples/s"
+NB, G, T_STEPS, T_TRAIN, RES = 2, 8, 10, 2, 512
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(steps=1, warmup=0, verbose=False):
+    """Times the oracle (the CPU restatement of the reference algorithm, oracle/) on the host cores on a
+    bounded sample of the config-2 workload and extrapolates by the exact step counts:
+      per sample = 10 x MMDiT fwd (CFG pair, B=2) + 2 x (fwd + bwd, B=2) + 1 VAE decode + 2 PickScore image fwd
+    Returns (samples_per_s list per step, cores, description)."""
+    import torch
+    from adv_grpo_b200 import weights
+    from oracle import clip as clip_o
+    from oracle import vae as vae_o
+    from oracle.mmdit import MMDiTOracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cfg = weights.SD35_MEDIUM
+    t0 = time.perf_counter()
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    lora = weights.init_lora(cfg, rank=32, seed=1, perturb_b=0.01)
+    lora = {k: (a.requires_grad_(True), b.requires_grad_(True)) for k, (a, b) in lora.items()}
+    oracle = MMDiTOracle(params, dict(cfg, dual_layers=set(cfg["dual_layers"])), lora=lora, lora_scale=2.0)
+    del params
+    vparams = weights.init_vae_decoder(weights.VAE_SD3, seed=2, device="cpu")
+    cparams = {k: v.float() for k, v in weights.init_clip(weights.CLIP_H, seed=3, device="cpu").items()}
+    ccfg = dict(patch=14, v_layers=32, v_heads=16, t_layers=24, t_heads=16)
+    if verbose:
+        print(f"[cpu baseline] init {time.perf_counter() - t0:.1f}s, {cores} threads", file=sys.stderr)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, RES // 8, RES // 8, generator=g)
+    t = torch.full((2,), 500.0)
+    ctx = torch.randn(2, 205, 4096, generator=g)
+    pooled = torch.randn(2, 2048, generator=g)
+    results = []
+    for it in range(warmup + steps):
+        with torch.no_grad():
+            a = time.perf_counter()
+            oracle.forward(x, t, ctx, pooled)
+            t_fwd = time.perf_counter() - a
+        a = time.perf_counter()
+        out = oracle.forward(x, t, ctx, pooled)
+        out.square().mean().backward()
+        t_fb = time.perf_counter() - a
+        with torch.no_grad():
+            a = time.perf_counter()
+            vae_o.decode_latents_to_image(vparams, x[:1])
+            t_vae = time.perf_counter() - a
+            a = time.perf_counter()
+            clip_o.image_features(cparams, ccfg, torch.randn(1, 3, 224, 224, generator=g))
+            t_clip = time.perf_counter() - a
+        per_sample = T_STEPS * t_fwd + T_TRAIN * t_fb + t_vae + 2 * t_clip
+        if verbose:
+            print(f"[cpu baseline] fwd(B=2) {t_fwd:.2f}s  fwd+bwd(B=2) {t_fb:.2f}s  vae {t_vae:.2f}s  clip {t_clip:.2f}s "
+                  f"-> {per_sample:.1f}s/sample", file=sys.stderr)
+        if it >= warmup:
+            results.append(1.0 / per_sample)
+    desc = ("oracle (torch fp32 restatement of the reference path) on host cores: timed 1 MMDiT fwd at B=2 (one CFG "
+            "pair), 1 fwd+bwd at B=2, 1 VAE decode, 1 PickScore image fwd at SD3.5-M/512px shapes; per-sample time = "
+            "10*fwd + 2*(fwd+bwd) + vae + 2*clip (extrapolated by step counts)")
+    return results, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, cores, desc = cpu_reference_sample(steps=args.steps, warmup=min(args.warmup, 1), verbose=True)
+    v = statistics.mean(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SD3.5-medium LoRA 512x512, 10 steps, G=8, PickScore reward (config 2)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from adv_grpo_b200 import _lib, ops, weights
+    from adv_grpo_b200.config import load_config
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
+    from adv_grpo_b200.trainer import GRPOTrainer, SyntheticTextEmbedder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    _lib.call("advgrpo_device_check", local)
+    torch.backends.cuda.matmul.allow_tf32 = True        # reference: train_sd3_fast_pickscore.py:537-538
+    torch.backends.cudnn.allow_tf32 = True
+
+    pipe = StableDiffusion3Pipeline.from_seed(weights.SD35_MEDIUM, weights.VAE_SD3, device=dev, seed=0)
+    scorer = PickScoreScorer(device=dev, dtype=torch.bfloat16)
+    cfg = load_config("pickscore_cotrain_sd3_fast")
+    cfg.sample.num_batches_per_epoch = NB
+    cfg.train.gradient_accumulation_steps = 1
+    cfg.train_d = False
+    prompts = [f"synthetic prompt {i}" for i in range(99)]
+
+    class HostStagedEmbedder(SyntheticTextEmbedder):
+        """e2e leg: every call copies the prompt embeddings from pinned host memory."""
+
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.cache, self.h2d = {}, 0
+
+        def __call__(self, idx):
+            if idx not in self.cache:
+                g = torch.Generator().manual_seed(1000 + int(idx))
+                e = torch.randn(1, self.n_tokens, self.joint_dim, generator=g).bfloat16().pin_memory()
+                p = torch.randn(1, self.pooled_dim, generator=g).bfloat16().pin_memory()
+                self.cache[idx] = (e, p)
+            e, p = self.cache[idx]
+            self.h2d += e.numel() * 2 + p.numel() * 2
+            return e.to(self.device, non_blocking=True), p.to(self.device, non_blocking=True)
+
+    class DeviceEmbedder(SyntheticTextEmbedder):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.cache = {}
+
+        def __call__(self, idx):
+            if idx not in self.cache:
+                self.cache[idx] = super().__call__(idx)
+            return self.cache[idx]
+
+    host_refs, dev_refs = {}, {}
+    counters = {"h2d": 0}
+
+    def ref_host(idx, n, size):
+        if idx not in host_refs:
+            g = torch.Generator().manual_seed(11 + int(idx))
+            host_refs[idx] = torch.rand(n, 3, size, size, generator=g).pin_memory()
+        counters["h2d"] += host_refs[idx].numel() * 4
+        return host_refs[idx].to(dev, non_blocking=True)
+
+    def ref_dev(idx, n, size):
+        if idx not in dev_refs:
+            g = torch.Generator().manual_seed(11 + int(idx))
+            dev_refs[idx] = torch.rand(n, 3, size, size, generator=g).to(dev)
+        return dev_refs[idx]
+
+    emb_dev = DeviceEmbedder(device=dev)
+    emb_host = HostStagedEmbedder(device=dev)
+    trainer = GRPOTrainer(cfg, pipe, prompts, scorer=scorer, embedder=emb_dev, device=dev, reference_image_fn=ref_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, read_back):
+        d2h = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(k):
+            info = trainer.run_epoch()
+            if read_back:
+                vals = torch.stack([info["loss"].float(), info["reward_mean"].float(), info["approx_kl"].float()]).cpu()
+                d2h += vals.numel() * 4
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), _lib.launch_count() - n0, d2h
+
+    # ---- warm-up (also captures the CUDA graphs and pre-stages every prompt this run will touch) ----
+    trainer.embedder, trainer.reference_image_fn = emb_host, ref_host
+    timed(1, True)
+    trainer.embedder, trainer.reference_image_fn = emb_dev, ref_dev
+    timed(max(args.warmup, 3) - 1, False)
+    # pre-stage the device-resident inputs of the timed region (value leg: inputs already in HBM)
+    e_save, s_save = trainer.epoch, trainer.sampler
+    for ep in range(trainer.epoch, trainer.epoch + 2 * args.steps + 2):
+        for i in range(NB):
+            idx = trainer.sampler.indices_for_epoch(ep * NB + i)[rank][0]
+            emb_dev(idx), ref_dev(idx, G, RES), emb_host(idx), ref_host(idx, G, RES)
+    emb_host.h2d, counters["h2d"] = 0, 0
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches, _ = timed(args.steps, False)
+    trainer.embedder, trainer.reference_image_fn = emb_host, ref_host
+    ms_e2e, _, d2h = timed(args.steps, True)
+    clk = clocks.stop() if rank == 0 else None
+    samples = world * NB * G * args.steps
+    value = samples / (ms_dev / 1e3)
+    e2e_value = samples / (ms_e2e / 1e3)
+    h2d_per_step = (emb_host.h2d + counters["h2d"]) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM) and of the attention kernels, measured live ----
+    peak_burst, peak_sustained, hbm, src = _peaks()
+
+    def time_kernel(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    M, K, N, K2 = 2 * G * 1024, 1536, 4608, 128
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = torch.randn(N, K, device=dev).bfloat16()
+    A2 = torch.randn(M, K2, device=dev).bfloat16()
+    W2 = torch.randn(N, K2, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev).bfloat16()
+    ms_gemm = time_kernel(lambda: ops.gemm(A, W, bias=bias, a2=A2, w2=W2))
+    gemm_flops = 2.0 * M * N * (K + K2)
+    S = 1024 + 205
+    qkv = torch.randn(2 * G, S, 3, 24, 64, device=dev).bfloat16()
+    ms_attn = time_kernel(lambda: ops.attention_fwd(qkv, want_lse=False))
+    attn_flops = 4.0 * 2 * G * 24 * S * S * 64
+    out, lse = ops.attention_fwd(qkv)
+    dout = torch.randn_like(out)
+    ms_attn_bwd = time_kernel(lambda: ops.attention_bwd(qkv, out, dout, lse), iters=10)
+    achieved = gemm_flops / ms_gemm / 1e9
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (fused QKV projection + LoRA second product, "
+                f"M={M} N={N} K={K}+{K2})", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                "frac": achieved / peak_burst, "traffic": None, "peak_source": f"{src} burst bf16 (kernel timed alone)"}
+    kernels = {
+        "attn_fwd_tflops": attn_flops / ms_attn / 1e9, "attn_fwd_frac": attn_flops / ms_attn / 1e9 / peak_burst,
+        "attn_bwd_tflops": 2.5 * attn_flops / ms_attn_bwd / 1e9,
+        "attn_bwd_frac": 2.5 * attn_flops / ms_attn_bwd / 1e9 / peak_burst,
+        "attn_shape": f"B={2 * G} H=24 S={S} D=64",
+        "step_tflops": 71.2 * value / world, "step_frac_of_sustained": 71.2 * value / world / peak_sustained,
+    }
+    del A, W, A2, W2, qkv, out, dout
+    torch.cuda.empty_cache()
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        vals, cores, desc = cpu_reference_sample(steps=1, warmup=0)
+        cpu = {"value": vals[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "SD3.5-medium LoRA r32 512x512, 10 denoise steps (2 trained), G=8, CFG 4.5, PickScore "
+                                   f"(CLIP-ViT-H/14) reward on generated+reference images; {NB} groups + 2 optimizer "
+                                   "steps per rank per step (BASELINE config 2)",
+                       "l2": "per-step working set (4.4 GB weights + activations) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

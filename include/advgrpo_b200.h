@@ -208,12 +208,14 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
  *   u8 = clamp(round(bf16(img) * 255), 0, 255)           (bf16 arithmetic, quirk Q6)
  *   PIL-compatible antialiased bicubic resize to out_size x out_size (two passes, 8-bit
  *   intermediate, Pillow's 22-bit fixed-point coefficients) -> /255 -> (x - mean) / std.
- * images: bf16 [B, 3, H, W] in [0,1]; pixels: bf16 or f32 [B, 3, out, out];
+ * images: bf16 [B, 3, H, W] in [0,1], or (images_u8 != 0) uint8 [B, 3, H, W] already-quantised
+ * planes (the PIL inputs of train_pickscore, train_sd3_fast_pickscore.py:162-163);
+ * pixels: bf16 or f32 [B, 3, out, out];
  * u8_out (optional): uint8 [B, 3, out, out] resized bytes for bit-exact checks.
  * workspace: advgrpo_clip_preprocess_workspace_bytes(B, H, W, out) bytes.
  */
 size_t advgrpo_clip_preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, int64_t out);
-int advgrpo_clip_preprocess(const void* images, int64_t B, int64_t H, int64_t W, int64_t out,
+int advgrpo_clip_preprocess(const void* images, int images_u8, int64_t B, int64_t H, int64_t W, int64_t out,
                             const float* mean3, const float* std3, void* pixels, int pixels_f32,
                             uint8_t* u8_out, void* workspace, size_t workspace_bytes,
                             advgrpo_stream_t stream);

@@ -273,7 +273,7 @@ def test_qk_norm_concat_fwd_bwd(ops, S_txt):
 
 
 # ------------------------------------------------------------------ reward preprocessing
-@pytest.mark.parametrize("H", [512, 256])
+@pytest.mark.parametrize("H", [512, 256, 128])
 def test_clip_preprocess_bit_exact_with_pillow(ops, H):
     from PIL import Image
     g = torch.Generator().manual_seed(H)
