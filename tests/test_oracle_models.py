@@ -1,0 +1,86 @@
+"""Cross-check the oracle's restated model bodies against same-architecture implementations that ARE
+installed here (transformers CLIPModel / Dinov2Model, Pillow) -- SURVEY.md section 8c.  Tiny configs, CPU."""
+import numpy as np
+import torch
+
+from oracle import clip as clip_o
+from oracle import dinov2 as dino_o
+from oracle import preprocess as pre_o
+
+
+def test_clip_oracle_matches_transformers():
+    from transformers import CLIPConfig, CLIPModel
+    cfg = CLIPConfig(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                         vocab_size=300, max_position_embeddings=77, hidden_act="gelu", eos_token_id=2, bos_token_id=0,
+                         pad_token_id=1, projection_dim=32),
+        vision_config=dict(hidden_size=96, intermediate_size=192, num_hidden_layers=2, num_attention_heads=4,
+                           image_size=56, patch_size=14, hidden_act="gelu", projection_dim=32),
+        projection_dim=32)
+    torch.manual_seed(0)
+    m = CLIPModel(cfg).eval()
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ocfg = dict(patch=14, v_layers=2, v_heads=4, t_layers=2, t_heads=4)
+    pix = torch.randn(3, 3, 56, 56)
+    ids = torch.randint(3, 299, (3, 20))
+    ids[:, -1] = 299                                     # highest id last = EOS position for argmax pooling
+    with torch.no_grad():
+        ref_i = m.get_image_features(pixel_values=pix)
+        ref_t = m.get_text_features(input_ids=ids)
+        ref_i = getattr(ref_i, "pooler_output", ref_i)   # transformers 5.x returns an output object
+        ref_t = getattr(ref_t, "pooler_output", ref_t)
+        got_i = clip_o.image_features(p, ocfg, pix)
+        got_t = clip_o.text_features(p, ocfg, ids)
+    assert torch.allclose(got_i, ref_i, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(got_t, ref_t, atol=2e-5, rtol=1e-4)
+
+
+def test_dinov2_oracle_matches_transformers():
+    from transformers import Dinov2Config, Dinov2Model
+    cfg = Dinov2Config(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, mlp_ratio=2, image_size=56,
+                       patch_size=14, layerscale_value=0.3, hidden_act="gelu", qkv_bias=True, layer_norm_eps=1e-6)
+    torch.manual_seed(0)
+    m = Dinov2Model(cfg).eval()
+    sd = m.state_dict()
+    p = {"patch_embed.proj.weight": sd["embeddings.patch_embeddings.projection.weight"],
+         "patch_embed.proj.bias": sd["embeddings.patch_embeddings.projection.bias"],
+         "cls_token": sd["embeddings.cls_token"], "pos_embed": sd["embeddings.position_embeddings"],
+         "norm.weight": sd["layernorm.weight"], "norm.bias": sd["layernorm.bias"]}
+    for i in range(2):
+        h, b = f"encoder.layer.{i}", f"blocks.{i}"
+        p[b + ".norm1.weight"], p[b + ".norm1.bias"] = sd[h + ".norm1.weight"], sd[h + ".norm1.bias"]
+        p[b + ".norm2.weight"], p[b + ".norm2.bias"] = sd[h + ".norm2.weight"], sd[h + ".norm2.bias"]
+        p[b + ".attn.qkv.weight"] = torch.cat([sd[f"{h}.attention.attention.{n}.weight"] for n in ("query", "key", "value")])
+        p[b + ".attn.qkv.bias"] = torch.cat([sd[f"{h}.attention.attention.{n}.bias"] for n in ("query", "key", "value")])
+        p[b + ".attn.proj.weight"], p[b + ".attn.proj.bias"] = sd[h + ".attention.output.dense.weight"], sd[h + ".attention.output.dense.bias"]
+        p[b + ".ls1.gamma"], p[b + ".ls2.gamma"] = sd[h + ".layer_scale1.lambda1"], sd[h + ".layer_scale2.lambda1"]
+        p[b + ".mlp.fc1.weight"], p[b + ".mlp.fc1.bias"] = sd[h + ".mlp.fc1.weight"], sd[h + ".mlp.fc1.bias"]
+        p[b + ".mlp.fc2.weight"], p[b + ".mlp.fc2.bias"] = sd[h + ".mlp.fc2.weight"], sd[h + ".mlp.fc2.bias"]
+    x = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        ref = m(pixel_values=x).last_hidden_state
+        got = dino_o.forward_features(p, dict(patch=14, heads=4, layers=2), x)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_pil_resize_restatement_is_bit_exact_with_pillow():
+    from PIL import Image
+    rng = np.random.RandomState(0)
+    for H, out in ((512, 224), (300, 224), (128, 224)):
+        img = rng.randint(0, 256, size=(H, H, 3), dtype=np.uint8)
+        ref = np.array(Image.fromarray(img).resize((out, out), resample=Image.BICUBIC))
+        got = pre_o.pil_bicubic_resize_u8(img.transpose(2, 0, 1), out).transpose(1, 2, 0)
+        assert np.array_equal(ref, got), (H, out)
+
+
+def test_dino_head_reward_and_hinge_loss_shapes():
+    torch.manual_seed(0)
+    hp = {"layers.0.weight": torch.randn(16, 32) * 0.1, "layers.0.bias": torch.zeros(16),
+          "layers.2.weight": torch.randn(1, 16) * 0.1, "layers.2.bias": torch.zeros(1)}
+    feats = torch.randn(3, 10, 32)
+    idx = torch.randint(0, 9, (3, 4))
+    hybrid, cls_s, patch_s = dino_o.patch_reward(hp, feats, idx)
+    assert hybrid.shape == (3,) and patch_s.shape == (3, 4)
+    assert torch.allclose(hybrid, 0.7 * cls_s + 0.3 * patch_s.mean(1))
+    loss, acc = dino_o.hinge_d_loss(hp, feats, feats.flip(0), idx, idx)
+    assert loss.dim() == 0 and 0 <= acc <= 1
