@@ -84,7 +84,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const int b = blockIdx.z;
   const int S = p.S;
   const int nq_total = (S + T - 1) / T;
-  const int i_begin = p.causal ? (kv0 / T) : 0;      // query tiles strictly above the diagonal see nothing
+  const int i_begin = (p.causal & 1) ? (kv0 / T) : 0;      // query tiles strictly above the diagonal see nothing
   const int nq = nq_total - i_begin;
 
   if (threadIdx.x == 0) {
@@ -233,7 +233,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           float p0 = ex2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2[c * 32 + e]));
           float p1 = ex2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2[c * 32 + e + 1]));
           if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
-          if (p.causal) {
+          if (p.causal & 1) {
             if (q_a < kv_idx) p0 = 0.f;
             if (q_a + 1 < kv_idx) p1 = 0.f;
           }
@@ -317,7 +317,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
-      if (tid == 0) {
+      if (tid == 0 && !(p.causal & 2)) {   // bit 1: timing experiment only (skip the dQ reduce)
         const int grow = (int)(stat_row + (int64_t)i * T);
         tma_reduce_add_2d(&tm_dq, stage, 0, grow);
         tma_reduce_add_2d(&tm_dq, stage + 16384, 32, grow);

@@ -39,7 +39,11 @@ struct Cfg {
   static constexpr int kColsPerQ = 128 + 64 + D;
   static constexpr int kTmemCols = (NQ * kColsPerQ <= 256) ? 256 : 512;
   static constexpr int kSoftmaxWarps = 4 * NQ;
-  static constexpr int kThreads = (kSoftmaxWarps + 2) * 32;
+  static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;   // + one utility warpgroup (TMA, MMA, 2 idle)
+  // register re-balancing (setmaxnreg works per 4-warp group): utility warps shrink, softmax warps grow
+  static constexpr bool kRebalance = (D == 64);
+  static constexpr int kRegsUtility = 64;
+  static constexpr int kRegsSoftmax = (NQ == 2) ? 216 : 192;   // 256*216+128*64 <= 384*168; 128*192+128*64 <= 256*128
   static_assert(NQ * kColsPerQ <= 512, "TMEM budget");
 };
 
@@ -52,7 +56,26 @@ struct Params {
   int causal;
 };
 
-template <int D, int NQ>
+// 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, rel. err 7.5e-5): used for
+// EMU of every 4 element pairs so the 16/clk/SM MUFU unit is not the only exp engine (it would cap the
+// tensor pipe at 50% for head_dim 64).  Two elements at a time with the packed f32x2 FMA / ADD.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer
+  const float2 xr = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(xr, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));         // f in [-0.5, 0.5]
+  float2 pl = __ffma2_rn(f, make_float2(0.055171650f, 0.055171650f), make_float2(0.24261113f, 0.24261113f));
+  pl = __ffma2_rn(pl, f, make_float2(0.69326097f, 0.69326097f));
+  pl = __ffma2_rn(pl, f, make_float2(0.99992806f, 0.99992806f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(xr.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(xr.y) << 23));
+  return r;
+}
+
+template <int D, int NQ, int EMU>
 __global__ void __launch_bounds__(Cfg<D, NQ>::kThreads, (NQ == 1 && D == 64) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   using C = Cfg<D, NQ>;
@@ -69,7 +92,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* bar_s_full = bar_kv_empty + STAGES; // NQ
   uint64_t* bar_p_full = bar_s_full + NQ;       // NQ
   uint64_t* bar_pv_done = bar_p_full + NQ;      // NQ
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_pv_done + NQ);
+  uint64_t* bar_s_free = bar_pv_done + NQ;      // NQ   softmax has S in registers: QK(j+1) may overwrite it
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_s_free + NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       mbar_init(&bar_s_full[i], 1);
       mbar_init(&bar_p_full[i], 128);
       mbar_init(&bar_pv_done[i], 1);
+      mbar_init(&bar_s_free[i], 128);
     }
     fence_barrier_init();
   }
@@ -109,6 +134,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
+  if (warp >= C::kSoftmaxWarps) {
+  if constexpr (C::kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsUtility));
   if (warp == C::kSoftmaxWarps) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -166,30 +193,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       for (int j = 0; j < nkv; ++j) {
         const int st = j % STAGES;
-        for (int q = 0; q < NQ; ++q) {
-          mbar_wait(&bar_p_full[q], j & 1);
-          tc_fence_after();
-          if (j + 1 < nkv) {
-            const int st1 = (j + 1) % STAGES;
-            if (q == 0) {
-              mbar_wait(&bar_k_full[st1], ((j + 1) / STAGES) & 1);
-              tc_fence_after();
-            }
+        if (j + 1 < nkv) {
+          const int st1 = (j + 1) % STAGES;
+          for (int q = 0; q < NQ; ++q) {
+            mbar_wait(&bar_s_free[q], j & 1);           // S(j) is in the softmax warps' registers
+            if (q == 0) mbar_wait(&bar_k_full[st1], ((j + 1) / STAGES) & 1);
+            tc_fence_after();
             issue_qk(q, st1);
             mma_commit(&bar_s_full[q]);
           }
-          if (q == 0) {
-            mbar_wait(&bar_v_full[st], (j / STAGES) & 1);
-            tc_fence_after();
-          }
+        }
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&bar_p_full[q], j & 1);
+          if (q == 0) mbar_wait(&bar_v_full[st], (j / STAGES) & 1);
+          tc_fence_after();
           issue_pv(q, st, j > 0);
           mma_commit(&bar_pv_done[q]);
         }
         mma_commit(&bar_kv_empty[st]);
       }
     }
+  }
   } else {
     // ============================== softmax / epilogue ==============================
+    if constexpr (C::kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsSoftmax));
     const int q = warp / 4;                         // query tile handled by this warp
     const int row = (warp % 4) * 32 + lane;         // row inside the tile == TMEM lane
     const int q_idx = q0 + q * BQ + row;            // global query index
@@ -211,27 +238,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         lim = c < lim ? c : lim;
       }
       const bool need_mask = lim < BKV;
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
+      // ---- S row -> registers (single TMEM read), then release S for QK(j+1) ----
+      uint32_t sv[4][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(s_tmem + c * 32, r);
-        tmem_wait_ld();
-        if (need_mask) {
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bar_s_free[q]);
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+            if (c * 32 + i >= lim) sv[c][i] = 0xff800000u;   // -inf
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])));
       float m_new = fmaxf(m, mx * sl2);
       // lazy rescale: keep the stale max while it is within 2^8 of the true one
       if (m != -INFINITY && m_new - m <= kRescaleThreshold) m_new = m;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // fully masked row so far
-      const float alpha = (m == -INFINITY) ? 1.f : exp2f(m - m_use);
+      const float alpha = (m == -INFINITY) ? 1.f : ex2(m - m_use);
       if (j > 0) {
         mbar_wait(&bar_pv_done[q], (j - 1) & 1);
         tc_fence_after();
@@ -247,28 +277,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
         }
       }
-      // ---- pass 2: p = exp2(s * scale - m), row sum, bf16 P -> TMEM ----
-      float rowsum = 0.f;
-      const float neg_m = -m_use;
+      // ---- p = exp2(s * scale - m), row sum, bf16 P -> TMEM ----
+      float2 sum2 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(s_tmem + c * 32, r);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float e0 = exp2f(fmaf(__uint_as_float(r[i]), sl2, neg_m));
-          float e1 = exp2f(fmaf(__uint_as_float(r[i + 1]), sl2, neg_m));
-          if (need_mask) {
-            if (c * 32 + i >= lim) e0 = 0.f;
-            if (c * 32 + i + 1 >= lim) e1 = 0.f;
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+          float2 e;
+          if ((i / 2) % 4 < EMU) {
+            e = ex2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
           }
-          rowsum += e0 + e1;
-          pk[i / 2] = pack_bf16(e0, e1);
+          sum2 = __fadd2_rn(sum2, e);
+          pk[i / 2] = pack_bf16(e.x, e.y);
         }
         tmem_st16(p_tmem + c * 16, pk);
       }
+      const float rowsum = sum2.x + sum2.y;
       l = l * alpha + rowsum;
       m = m_new;
       tmem_wait_st();
@@ -315,7 +345,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   }
 }
 
-template <int D, int NQ>
+template <int D, int NQ, int EMU>
 int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H, float scale,
            int causal, cudaStream_t st) {
   using C = Cfg<D, NQ>;
@@ -327,7 +357,7 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   if (rc != ADVGRPO_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_kernel<D, NQ, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   Params p;
@@ -340,21 +370,29 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   dim3 grid((unsigned)((S + BQ * NQ - 1) / (BQ * NQ)), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<D, NQ><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
+  attn_fwd_kernel<D, NQ, EMU><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
 
 }  // namespace
 
-// variant: 0 = auto, 1 = one query tile per CTA (2 CTAs/SM), 2 = two query tiles per CTA
+// variant: 0 = auto; 1..6 = {1,2} query tiles per CTA x {0,1,2} of every 4 exp pairs emulated on the FMA pipe
 int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
                       int64_t D, float scale, int causal, int variant, cudaStream_t st) {
+#define ADVGRPO_ATTN_ARGS qkv, out, out2, S_split, lse, B, S, H, scale, causal, st
   if (D == 64) {
-    if (variant == 2) return launch<64, 2>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
-    return launch<64, 1>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
+    switch (variant) {
+      case 1: return launch<64, 1, 0>(ADVGRPO_ATTN_ARGS);
+      case 2: return launch<64, 2, 0>(ADVGRPO_ATTN_ARGS);
+      case 3: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS);
+      case 4: return launch<64, 2, 1>(ADVGRPO_ATTN_ARGS);
+      case 5: return launch<64, 1, 2>(ADVGRPO_ATTN_ARGS);
+      case 6: return launch<64, 2, 2>(ADVGRPO_ATTN_ARGS);
+      default: return launch<64, 1, 0>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
+    }
   }
-  if (D == 128) return launch<128, 1>(qkv, out, out2, S_split, lse, B, S, H, scale, causal, st);
+  if (D == 128) return launch<128, 1, 0>(ADVGRPO_ATTN_ARGS);
   return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_fwd: head_dim %lld not in {64, 128}", (long long)D);
 }
 

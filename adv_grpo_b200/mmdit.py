@@ -294,12 +294,11 @@ class SD3Transformer2DModel(torch.nn.Module):
 
     def _attention(self, joint, split):
         if torch.is_grad_enabled() and joint.requires_grad:
-            o = ops.attention(joint)                               # [B, S, H, D]
-            B, S = o.shape[:2]
-            o = o.reshape(B, S, self.d)
             if split:
-                return o[:, :split].contiguous(), o[:, split:].contiguous()
-            return o, None
+                oi, ot = ops.attention_split(joint, split)
+                return oi.reshape(oi.shape[0], -1, self.d), ot.reshape(ot.shape[0], -1, self.d)
+            o = ops.attention(joint)                               # [B, S, H, D]
+            return o.reshape(o.shape[0], o.shape[1], self.d), None
         o, _ = ops.attention_fwd(joint, want_lse=False, split=split)
         if split:
             return o[0].reshape(o[0].shape[0], -1, self.d), o[1].reshape(o[1].shape[0], -1, self.d)

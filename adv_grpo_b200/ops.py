@@ -314,6 +314,30 @@ class _Attention(torch.autograd.Function):
         return attention_bwd(qkv, out, dout, lse, scale, causal), None, None
 
 
+class _AttentionSplit(torch.autograd.Function):
+    """Joint attention whose output leaves as the (image rows, text rows) pair; the backward re-joins the
+    two incoming gradients with ONE concatenation instead of autograd's zero-fill + slice-copy + add."""
+
+    @staticmethod
+    def forward(ctx, qkv, scale, causal, split):
+        out, lse = attention_fwd(qkv, scale, causal, want_lse=True)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (scale, causal)
+        return out[:, :split].contiguous(), out[:, split:].contiguous()
+
+    @staticmethod
+    def backward(ctx, d_img, d_txt):
+        qkv, out, lse = ctx.saved_tensors
+        scale, causal = ctx.meta
+        dout = torch.cat([d_img, d_txt], dim=1)
+        return attention_bwd(qkv, out, dout, lse, scale, causal), None, None, None
+
+
+def attention_split(qkv, split, scale=None, causal=False):
+    """Differentiable joint attention returning (out[:, :split], out[:, split:]) as contiguous tensors."""
+    return _AttentionSplit.apply(qkv, scale, causal, split)
+
+
 def attention(qkv, scale=None, causal=False):
     """qkv bf16 [B,S,3,H,D] -> out bf16 [B,S,H,D]; differentiable."""
     if torch.is_grad_enabled() and qkv.requires_grad:

@@ -67,6 +67,12 @@ def probe_attn_v2():
     _attn(2, S=1229)
 
 
+def probe_attn_variants():
+    for v in (3, 4, 5, 6):
+        _attn(v, S=1229)
+        _attn(v, S=300, causal=True)
+
+
 def probe_attn_d128():
     _attn(1, D=128, S=257)
 
@@ -118,6 +124,16 @@ def probe_perf_bwd():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"attn bwd: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for _ in range(3):
+        ops.attention_bwd(qkv, out, dout, lse, causal=2)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        ops.attention_bwd(qkv, out, dout, lse, causal=2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"attn bwd WITHOUT dQ reduce (timing experiment): {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
     q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3))
     o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
     go = dout.permute(0, 2, 1, 3)
@@ -139,7 +155,7 @@ def probe_perf():
     B, S, H, D = 16, 1229, 24, 64
     qkv = torch.randn(B, S, 3, H, D, device="cuda").bfloat16()
     flops = 4 * B * H * S * S * D
-    for variant in (1, 2):
+    for variant in (1, 2, 3, 4, 5, 6):
         for _ in range(3):
             ops.attention_fwd(qkv, variant=variant, want_lse=False)
         torch.cuda.synchronize()

@@ -16,8 +16,9 @@ for r in csv.DictReader(lines):
         rows.append((r["Kernel Name"], v))
 agg = defaultdict(lambda: [0, 0.0])
 for name, us in rows:
-    key = re.sub(r"<.*", "", name)
-    key = re.sub(r"\(.*", "", key)[:70]
+    key = name.replace("(anonymous namespace)::", "").replace("void ", "")
+    key = re.sub(r"\(.*", "", key)
+    key = re.sub(r"<(unnamed)>::", "", key)[:70]
     agg[key][0] += 1
     agg[key][1] += us
 total = sum(v[1] for v in agg.values())
