@@ -163,25 +163,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+      // descriptors are built once; per MMA only the 16-byte-unit start address is advanced
+      const uint64_t q_d0 = make_smem_desc_sw128(smem_u32(q_smem), 16, 1024);
+      const uint64_t k_d0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);
+      const uint64_t v_d0 = make_smem_desc_sw128(smem_u32(v_smem), BKV * 128, 1024);
       auto issue_qk = [&](int q, int st) {
-        const uint32_t qa = smem_u32(q_smem + q * C::kTileBytes);
-        const uint32_t ka = smem_u32(k_smem + st * C::kTileBytes);
         const uint32_t s_tmem = tmem_base + q * C::kColsPerQ;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k / 4) * (BQ * 128) + (k % 4) * 32;
-          mma_ss(s_tmem, make_smem_desc_sw128(qa + off, 16, 1024),
-                 make_smem_desc_sw128(ka + off, 16, 1024), idesc_qk, k > 0);
+          const uint32_t off = ((k / 4) * (BQ * 128) + (k % 4) * 32) >> 4;
+          mma_ss(s_tmem, q_d0 + (uint64_t)(q * (C::kTileBytes >> 4) + off),
+                 k_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + off), idesc_qk, k > 0);
         }
       };
       auto issue_pv = [&](int q, int st, bool acc) {
-        const uint32_t va = smem_u32(v_smem + st * C::kTileBytes);
         const uint32_t p_tmem = tmem_base + q * C::kColsPerQ + 128;
         const uint32_t o_tmem = tmem_base + q * C::kColsPerQ + 192;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          mma_ts(o_tmem, p_tmem + k * 8, make_smem_desc_sw128(va + k * 2048, BKV * 128, 1024),
-                 idesc_pv, (acc || k > 0) ? 1u : 0u);
+          mma_ts(o_tmem, p_tmem + k * 8, v_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + k * 128), idesc_pv,
+                 (acc || k > 0) ? 1u : 0u);
         }
       };
       mbar_wait(bar_q_full, 0);

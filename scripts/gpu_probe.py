@@ -124,16 +124,6 @@ def probe_perf_bwd():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"attn bwd: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
-    for _ in range(3):
-        ops.attention_bwd(qkv, out, dout, lse, causal=2)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(10):
-        ops.attention_bwd(qkv, out, dout, lse, causal=2)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print(f"attn bwd WITHOUT dQ reduce (timing experiment): {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
     q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).detach().requires_grad_(True) for i in range(3))
     o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
     go = dout.permute(0, 2, 1, 3)

@@ -1,0 +1,97 @@
+"""Reward path (A7/A8a/A8b) and the stat-tracker mirror on the GPU vs the CPU oracle, tiny tower configs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_pickscore_scorer_matches_oracle():
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from oracle import clip as clip_o
+    from oracle import preprocess as pre_o
+    cfg = weights.CLIP_TINY
+    params = weights.init_clip(cfg, seed=3, device="cpu", dtype=torch.bfloat16)
+    scorer = PickScoreScorer(device=DEV, cfg=cfg, state_dict=params)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(4, 3, 256, 256, generator=g).bfloat16()
+    prompts = ["a red cube", "a red cube", "two green spheres on a table", "a red cube"]
+    scores = scorer(prompts, images.to(DEV)).float().cpu()
+    # oracle: bf16 quantisation -> PIL-exact resize -> CLIP towers in fp32 -> cosine * exp(logit_scale) / 26
+    u8 = pre_o.pil_bicubic_resize_u8(pre_o.quantise_bf16(images).numpy(), 224)
+    pix = torch.from_numpy(pre_o.clip_pixel_values(u8))
+    ids = scorer.processor.tokenizer(prompts, padding=True, max_length=77)["input_ids"]
+    p32 = {k: v.float() for k, v in params.items()}
+    ocfg = dict(patch=cfg["patch"], v_layers=cfg["v_layers"], v_heads=cfg["v_heads"], t_layers=cfg["t_layers"], t_heads=cfg["t_heads"])
+    ref = clip_o.pickscore(p32, ocfg, ids, pix)
+    # bf16 towers vs fp32 oracle: scores are O(1) cosines * 100 / 26
+    assert torch.allclose(scores, ref, atol=4e-2), (scores, ref)
+    # PIL-image entry (the reference's input type) gives the same pixels as the uint8 tensor entry
+    from PIL import Image
+    q = pre_o.quantise_bf16(images)
+    pil = [Image.fromarray(q[i].permute(1, 2, 0).numpy()) for i in range(4)]
+    s_pil = scorer(prompts, pil).float().cpu()
+    assert torch.allclose(s_pil, scores, atol=1e-6)
+
+
+def test_dino_patch_reward_matches_oracle():
+    from adv_grpo_b200 import rewards, weights
+    from adv_grpo_b200.dinov2 import DINOHead, DinoV2
+    from oracle import dinov2 as dino_o
+    cfg = weights.DINOV2_TINY
+    params = weights.init_dinov2(cfg, seed=4, device="cpu", dtype=torch.bfloat16)
+    scorer = DinoV2(params, cfg, device=DEV)
+    head = DINOHead(in_dim=cfg["width"], hidden_dim=64).to(DEV)
+    fn = rewards.multi_score(DEV, {"dino_patch_cotrain": 1.0})
+    images = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(123)
+    details, _ = fn(images.to(DEV), ["p"] * 3, [{}] * 3, scorer=scorer, head=head)
+    torch.manual_seed(123)
+    idx = torch.randint(0, 1369, (3, 64), device=DEV).cpu()             # same CUDA draw as rewards.py:406
+    feats = dino_o.forward_features({k: v.float() for k, v in params.items()},
+                                    dict(patch=14, heads=cfg["heads"], layers=cfg["layers"]), dino_o.preprocess(images))
+    hp = {k: v.detach().float().cpu() for k, v in head.state_dict().items()}
+    ref, cls_s, _ = dino_o.patch_reward(hp, feats, idx)
+    got = details["dino_patch_cotrain"].float().cpu()
+    assert torch.allclose(got, ref, atol=3e-2), (got, ref)
+    assert torch.equal(details["avg"].cpu(), got)
+
+
+def test_stat_tracker_mirror_golden(golden):
+    from adv_grpo_b200.stat_tracking import PerPromptStatTracker
+    for gs, key in ((False, "G1"), (True, "G2")):
+        t = PerPromptStatTracker(global_std=gs)
+        a = t.update(['a', 'b', 'a', 'c', 'b', 'a'], [1, 2, 3, 4, 5, 6])
+        assert isinstance(a, np.ndarray) and a.dtype == np.float64
+        np.testing.assert_allclose(a, golden[key], rtol=1e-12, atol=1e-12)
+        size, n_hist = t.get_stats()
+        assert abs(size - golden["G1_stats"][0]) < 1e-12 and n_hist == golden["G1_stats"][1]
+        t.clear()
+        assert t.stats == {}
+    t = PerPromptStatTracker(global_std=True)
+    a = t.update(['p', 'p', 'q', 'q'], [[1, 1], [2, 2], [3, 3], [4, 4]])
+    np.testing.assert_allclose(a, golden["G3"], rtol=1e-12, atol=1e-12)
+
+
+def test_sde_mirror_signature_and_grad(golden, golden_dir):
+    """adv_grpo.diffusers_patch.sd3_sde_with_logprob.sde_step_with_logprob_new drop-in on golden G8."""
+    import os
+    from adv_grpo_b200.diffusers_patch.sd3_sde_with_logprob import sde_step_with_logprob_new
+    from adv_grpo_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    sch = FlowMatchEulerDiscreteScheduler()
+    sch.set_timesteps(10, device=DEV)
+    t = torch.load(os.path.join(golden_dir, "g8_tensors.pt"))
+    mo = t["v"].bfloat16().to(DEV).requires_grad_(True)
+    ts = sch.timesteps[golden["G8_step_index"]]
+    prev, lp, mean, std = sde_step_with_logprob_new(sch, mo, ts, t["x"].bfloat16().to(DEV), noise_level=0.8,
+                                                    prev_sample=t["prev"].bfloat16().to(DEV))
+    np.testing.assert_allclose(lp.detach().cpu().numpy(), np.array(golden["G8_log_prob"], dtype=np.float32), rtol=2e-6)
+    assert torch.equal(mean.cpu(), t["mean"]) and std.shape == (4, 1, 1, 1)
+    lp.sum().backward()
+    assert mo.grad is not None and torch.isfinite(mo.grad.float()).all()
+    # rollout form: fresh noise, returns fp32 prev like the reference
+    prev2, lp2, _, _ = sde_step_with_logprob_new(sch, mo.detach(), ts[:1], t["x"].bfloat16().to(DEV), noise_level=0.8,
+                                                 generator=torch.Generator(device=DEV).manual_seed(1))
+    assert prev2.dtype == torch.float32 and lp2.shape == (4,)
