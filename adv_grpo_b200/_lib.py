@@ -38,6 +38,8 @@ SIGNATURES = {
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_clip_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "advgrpo_group_norm_workspace_bytes": (_SZ, [_I64, _I64]),
+    "advgrpo_group_norm_silu_nhwc": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P, _SZ, _P]),
 }
 # test/bench hooks that are exported but not part of include/advgrpo_b200.h
 _EXTRA = {
@@ -71,7 +73,7 @@ def load():
 
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2,
+_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2,
                      "advgrpo_device_check": 0}
 _launches = [0]
 

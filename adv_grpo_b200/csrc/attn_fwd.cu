@@ -42,8 +42,8 @@ struct Cfg {
   static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;   // + one utility warpgroup (TMA, MMA, 2 idle)
   // register re-balancing (setmaxnreg works per 4-warp group): utility warps shrink, softmax warps grow
   static constexpr bool kRebalance = (D == 64);
-  static constexpr int kRegsUtility = 64;
-  static constexpr int kRegsSoftmax = (NQ == 2) ? 216 : 192;   // 256*216+128*64 <= 384*168; 128*192+128*64 <= 256*128
+  static constexpr int kRegsUtility = 56;
+  static constexpr int kRegsSoftmax = (NQ == 2) ? 216 : 200;   // 256*216+128*56 <= 384*168; 128*200+128*56 <= 256*128
   static_assert(NQ * kColsPerQ <= 512, "TMEM budget");
 };
 
@@ -253,11 +253,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= lim) sv[c][i] = 0xff800000u;   // -inf
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent FMNMX3 chains
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])));
+        for (int i = 0; i < 32; i += 2)
+          mx4[(i / 2) & 3] = fmaxf(mx4[(i / 2) & 3], fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       float m_new = fmaxf(m, mx * sl2);
       // lazy rescale: keep the stale max while it is within 2^8 of the true one
       if (m != -INFINITY && m_new - m <= kRescaleThreshold) m_new = m;

@@ -1,0 +1,118 @@
+// GroupNorm(32 groups, affine) + optional SiLU for NHWC fp32 activations: the normalisation between the
+// cuDNN convolutions of the SD3 VAE decoder (fast.py:669 -> diffusers AutoencoderKL.decode, ResnetBlock2D /
+// mid-block attention / conv_norm_out).  PyTorch's group_norm on channels_last tensors round-trips through
+// NCHW copies and launches SiLU separately; this is two streaming passes (statistics, apply) at HBM speed.
+//   stats : per-thread channel-quad partial sums -> shared-memory double atomics per group -> global
+//   apply : y = (x - mean) * rstd * gamma[c] + beta[c]   (then x * sigmoid(x) if silu)
+#include "common.cuh"
+
+namespace advgrpo {
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int groups,
+                int pixels_per_block) {
+  __shared__ double s_sum[64], s_sq[64];
+  const int n = blockIdx.y;
+  const int quads = C / 4;                       // float4 per pixel
+  const int ppi = kThreads / quads;              // pixels per iteration
+  const int q = threadIdx.x % quads, pl = threadIdx.x / quads;
+  const int cpg = C / groups;
+  const int g = (q * 4) / cpg;
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int64_t p0 = (int64_t)blockIdx.x * pixels_per_block;
+  int64_t p1 = p0 + pixels_per_block;
+  if (p1 > HW) p1 = HW;
+  const float* base = x + (int64_t)n * HW * C;
+  float s = 0.f, ss = 0.f;
+  if (pl < ppi) {
+    for (int64_t p = p0 + pl; p < p1; p += ppi) {
+      const float4 v = *reinterpret_cast<const float4*>(base + p * C + q * 4);
+      s += (v.x + v.y) + (v.z + v.w);
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    }
+    atomicAdd(&s_sum[g], (double)s);
+    atomicAdd(&s_sq[g], (double)ss);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    atomicAdd(&sums[((int64_t)n * groups + threadIdx.x) * 2], s_sum[threadIdx.x]);
+    atomicAdd(&sums[((int64_t)n * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ y, int64_t HW, int C, int groups, float eps,
+                int silu) {
+  const int n = blockIdx.y;
+  const int quads = C / 4;
+  const int64_t total = HW * quads;
+  const int cpg = C / groups;
+  const double cnt = (double)HW * cpg;
+  const float* xb = x + (int64_t)n * HW * C;
+  float* yb = y + (int64_t)n * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int q = (int)(i % quads);
+    const int c = q * 4;
+    const int g = c / cpg;
+    const double m = sums[((int64_t)n * groups + g) * 2] / cnt;
+    double var = sums[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0) var = 0;
+    const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float4 v = *reinterpret_cast<const float4*>(xb + i * 4);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float o[4] = {(v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
+                  (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w};
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.0f + __expf(-o[j]));
+    }
+    *reinterpret_cast<float4*>(yb + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace
+}  // namespace advgrpo
+
+using namespace advgrpo;
+
+extern "C" {
+
+size_t advgrpo_group_norm_workspace_bytes(int64_t B, int64_t groups) { return (size_t)B * groups * 2 * sizeof(double); }
+
+int advgrpo_group_norm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, int64_t B,
+                                 int64_t HW, int64_t C, int64_t groups, float eps, int silu, void* workspace,
+                                 size_t workspace_bytes, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(x && gamma && beta && y, "group_norm_silu_nhwc: null pointer");
+  ADVGRPO_CHECK_ARG(B >= 1 && HW >= 1 && groups >= 1 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 &&
+                        C / 4 <= kThreads && kThreads % (C / 4) == 0,
+                    "group_norm_silu_nhwc: unsupported C=%lld groups=%lld", (long long)C, (long long)groups);
+  ADVGRPO_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "group_norm_silu_nhwc: alignment");
+  if (!workspace || workspace_bytes < advgrpo_group_norm_workspace_bytes(B, groups))
+    return set_error(ADVGRPO_ERR_WORKSPACE, "group_norm_silu_nhwc: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = (double*)workspace;
+  ADVGRPO_CUDA_CALL(cudaMemsetAsync(sums, 0, advgrpo_group_norm_workspace_bytes(B, groups), st));
+  const int ppi = kThreads / (int)(C / 4);
+  int64_t blocks = (int64_t)sm_count() * 8 / B;
+  if (blocks < 1) blocks = 1;
+  int64_t ppb = (HW + blocks - 1) / blocks;
+  ppb = (ppb + ppi - 1) / ppi * ppi;
+  blocks = (HW + ppb - 1) / ppb;
+  gn_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, st>>>(x, sums, HW, (int)C, (int)groups, (int)ppb);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  int64_t ablocks = (HW * (C / 4) + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 16 / B + 1;
+  if (ablocks > cap) ablocks = cap;
+  gn_apply_kernel<<<dim3((unsigned)ablocks, (unsigned)B), kThreads, 0, st>>>(x, sums, gamma, beta, y, HW, (int)C,
+                                                                            (int)groups, eps, silu);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+}  // extern "C"

@@ -422,3 +422,21 @@ def dino_preprocess(images, out_size=518):
     _lib.call("advgrpo_dino_preprocess", _ptr(images), int(images.dtype == torch.float32), B, H, W, out_size,
               _ptr(_const3(IMAGENET_MEAN, dev)), _ptr(_const3(IMAGENET_STD, dev)), _ptr(pix), _stream())
     return pix
+
+
+# --------------------------------------------------------------------------- VAE GroupNorm (+SiLU)
+def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True):
+    """x: f32 [B, C, H, W] stored channels_last (or [B, H, W, C] contiguous).  Returns the same logical shape,
+    channels_last."""
+    _need_cuda(x)
+    if x.dim() != 4 or x.dtype != torch.float32:
+        raise _lib.AdvGrpoError("group_norm_silu_nhwc expects a 4-D float32 tensor")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    ws_bytes = _lib.query("advgrpo_group_norm_workspace_bytes", B, groups)
+    ws = _workspace("gn", ws_bytes, x.device)
+    _lib.call("advgrpo_group_norm_silu_nhwc", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), B, H * W, C, groups,
+              float(eps), int(bool(silu)), _ptr(ws), ws.numel(), _stream())
+    return y

@@ -77,9 +77,57 @@ def compute_log_prob(transformer, pipeline, sample, j, embeds, pooled_embeds, co
     return sample["next_latents"][:, j], log_prob, mean, std
 
 
+class GraphedMicroStep:
+    """One replay micro-step (MMDiT forward on the CFG batch + fused CFG/SDE log-prob + clipped GRPO loss +
+    backward into the LoRA .grad buffers) captured as a CUDA graph: the eager version is CPU-bound (~3000
+    launches of Python/autograd/ctypes dispatch per micro-step).  First call per shape runs eagerly (warm-up),
+    the second captures, later ones replay.  Gradients accumulate in place into the existing .grad tensors."""
+
+    def __init__(self, trainer):
+        self.t, self.entries = trainer, {}
+
+    def _eager(self, lat, nxt, ts, embeds, pooled, old_lp, adv, sched_t, sigmas, grad_scale):
+        tr, c = self.t, self.t.config
+        noise_pred = tr.transformer(hidden_states=torch.cat([lat, lat]), timestep=torch.cat([ts, ts]),
+                                    encoder_hidden_states=embeds, pooled_projections=pooled, return_dict=False)[0]
+        # the scheduler tables are re-created by every rollout: they enter the graph through static copies
+        log_prob, _, _ = ops.sde_logprob_replay(noise_pred, lat, nxt, ts, sched_t, sigmas, c.sample.guidance_scale,
+                                                c.sample.noise_level, cfg=True)
+        loss, stats = ops.grpo_clip_loss(log_prob, old_lp, adv, c.train.clip_range, c.train.adv_clip_max,
+                                         grad_scale=grad_scale)
+        loss.backward()
+        return stats
+
+    def __call__(self, lat, nxt, ts, embeds, pooled, old_lp, adv, grad_scale):
+        from . import _lib
+        key = (tuple(lat.shape), tuple(embeds.shape), float(grad_scale))
+        ent = self.entries.get(key)
+        sch = self.t.pipeline.scheduler
+        args = (lat, nxt, ts, embeds, pooled, old_lp, adv, sch.timesteps.to(lat.device, torch.float32).contiguous(),
+                sch.sigmas.to(lat.device, torch.float32).contiguous())
+        if ent is None:                                   # warm-up (also creates the .grad tensors)
+            self.entries[key] = "warm"
+            return self._eager(*args, grad_scale).clone()
+        if ent == "warm":
+            static = [a.clone() for a in args]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                stats = self._eager(*static, grad_scale)
+            ent = (g, static, stats, _lib.launch_count() - n0)
+            self.entries[key] = ent
+        g, static, stats, n_kernels = ent
+        for dst, src in zip(static, args):
+            dst.copy_(src)
+        g.replay()
+        _lib.add_launches(n_kernels)
+        return stats.clone()
+
+
 class GRPOTrainer:
     def __init__(self, config, pipeline, prompts, scorer=None, head=None, embedder=None, device="cuda",
-                 reference_image_fn=None, sync_discriminator=True):
+                 reference_image_fn=None, sync_discriminator=True, graph_train=None):
         self.config, self.pipeline, self.prompts, self.device = config, pipeline, list(prompts), device
         self.rank, self.world = _world()
         self.transformer = pipeline.transformer
@@ -112,6 +160,9 @@ class GRPOTrainer:
             elif head is not None:
                 self.optimizer_D = torch.optim.Adam(head.parameters(), lr=config.d_lr, betas=(0.5, 0.999))
         self.last_info = {}
+        if graph_train is None:
+            graph_train = getattr(pipeline, "graphed_transformer", None) is not None
+        self.micro_step = GraphedMicroStep(self) if graph_train else None
 
     # ------------------------------------------------------------------ sampling
     def _synthetic_reference(self, prompt_index, n, size):
@@ -257,10 +308,15 @@ class GRPOTrainer:
                 embeds, pooled = sample["prompt_embeds"], sample["pooled_prompt_embeds"]
             adv_i = advantages[i * n_local:(i + 1) * n_local]
             for j in range(T):
-                _, log_prob, _, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c)
-                loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
-                                                 t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
-                loss.backward()
+                if self.micro_step is not None and t.cfg:
+                    stats = self.micro_step(sample["latents"][:, j].contiguous(), sample["next_latents"][:, j].contiguous(),
+                                            sample["timesteps"][:, j].contiguous(), embeds, pooled,
+                                            sample["log_probs"][:, j].contiguous(), adv_i[:, j].contiguous(), 1.0 / gas)
+                else:
+                    _, log_prob, _, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c)
+                    loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
+                                                     t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
+                    loss.backward()
                 stats_acc.append(stats)
                 micro += 1
                 if micro % gas == 0:

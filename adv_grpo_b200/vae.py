@@ -6,6 +6,7 @@ diffusers state-dict names."""
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .weights import VAE_SD3
 
 
@@ -24,15 +25,19 @@ class AutoencoderKL:
     def to(self, *a, **k):
         return self
 
-    def _gn(self, name, x):
-        return F.group_norm(x, 32, self.p[name + ".weight"], self.p[name + ".bias"], eps=1e-6)
+    def _gn(self, name, x, silu=False):
+        C = x.shape[1]
+        if x.is_cuda and x.dtype == torch.float32 and C % 128 == 0 and 256 % (C // 4) == 0:
+            return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu)
+        y = F.group_norm(x, 32, self.p[name + ".weight"], self.p[name + ".bias"], eps=1e-6)   # tiny test configs
+        return F.silu(y) if silu else y
 
     def _conv(self, name, x, pad=1):
         return F.conv2d(x, self.p[name + ".weight"], self.p[name + ".bias"], padding=pad)
 
     def _resnet(self, pre, x):
-        h = self._conv(pre + ".conv1", F.silu(self._gn(pre + ".norm1", x)))
-        h = self._conv(pre + ".conv2", F.silu(self._gn(pre + ".norm2", h)))
+        h = self._conv(pre + ".conv1", self._gn(pre + ".norm1", x, silu=True))
+        h = self._conv(pre + ".conv2", self._gn(pre + ".norm2", h, silu=True))
         if pre + ".conv_shortcut.weight" in self.p:
             x = self._conv(pre + ".conv_shortcut", x, pad=0)
         return x + h
@@ -60,7 +65,7 @@ class AutoencoderKL:
             if i < n_up - 1:
                 x = F.interpolate(x, scale_factor=2.0, mode="nearest")
                 x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
-        x = F.silu(self._gn("decoder.conv_norm_out", x))
+        x = self._gn("decoder.conv_norm_out", x, silu=True)
         return (self._conv("decoder.conv_out", x),)
 
 

@@ -225,6 +225,17 @@ int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64
                             int64_t out, const float* mean3, const float* std3, void* pixels,
                             advgrpo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * A6 glue: GroupNorm(groups, affine, eps) + optional SiLU on NHWC fp32 activations -- the normalisation
+ * between the convolutions of the SD3 VAE decoder (diffusers AutoencoderKL.decode, reference call site
+ * adv_grpo/diffusers_patch/sd3_pipeline_with_logprob_fast.py:669).  x, y: f32 [B, HW, C] (channels last);
+ * gamma, beta: f32 [C].  C / groups must be a multiple of 4.  In place (y == x) is allowed.
+ */
+size_t advgrpo_group_norm_workspace_bytes(int64_t B, int64_t groups);
+int advgrpo_group_norm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, int64_t B,
+                                 int64_t HW, int64_t C, int64_t groups, float eps, int silu, void* workspace,
+                                 size_t workspace_bytes, advgrpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

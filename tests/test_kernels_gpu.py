@@ -304,3 +304,37 @@ def test_dino_preprocess_matches_torch_bicubic(ops):
     got_bf = ops.dino_preprocess(img.bfloat16().to(DEV), 518).float().cpu()
     ref_bf = dino_o.preprocess(img.bfloat16().float())
     assert (got_bf - ref_bf).abs().max() < 0.05
+
+
+# ------------------------------------------------------------------ VAE GroupNorm + SiLU (A6 glue)
+@pytest.mark.parametrize("C,H,W,silu", [(128, 24, 20, True), (256, 16, 16, True), (512, 9, 7, False), (512, 32, 32, True)])
+def test_group_norm_silu_nhwc(ops, C, H, W, silu):
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(3, C, H, W, generator=g) * 2 + 0.7)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = torch.nn.functional.group_norm(x, 32, gamma, beta, eps=1e-6)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    got = ops.group_norm_silu_nhwc(xd, gamma.to(DEV), beta.to(DEV), 32, 1e-6, silu)
+    assert got.shape == x.shape and got.is_contiguous(memory_format=torch.channels_last)
+    # fp32 statistics accumulated in double; __expf in SiLU
+    assert torch.allclose(got.cpu(), ref, rtol=2e-5, atol=2e-5)
+
+
+def test_vae_decoder_matches_oracle_at_true_widths():
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.vae import AutoencoderKL, VaeImageProcessor
+    from oracle import vae as vae_o
+    vp = weights.init_vae_decoder(weights.VAE_SD3, seed=2, device="cpu")
+    vae = AutoencoderKL(vp, weights.VAE_SD3, device=DEV)
+    z = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(0))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        got = VaeImageProcessor().postprocess(vae.decode(z.to(DEV) / 1.5305 + 0.0609)[0], output_type="pt").cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    ref = vae_o.decode_latents_to_image(vp, z)
+    assert got.shape == (2, 3, 64, 64)
+    assert (got - ref).abs().max().item() < 2e-3
