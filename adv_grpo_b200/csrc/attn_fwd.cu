@@ -392,7 +392,7 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 4: return launch<64, 2, 1>(ADVGRPO_ATTN_ARGS);
       case 5: return launch<64, 1, 2>(ADVGRPO_ATTN_ARGS);
       case 6: return launch<64, 2, 2>(ADVGRPO_ATTN_ARGS);
-      default: return launch<64, 1, 0>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
+      default: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
     }
   }
   if (D == 128) return launch<128, 1, 0>(ADVGRPO_ATTN_ARGS);
