@@ -44,6 +44,7 @@ SIGNATURES = {
 # test/bench hooks that are exported but not part of include/advgrpo_b200.h
 _EXTRA = {
     "advgrpo_attn_fwd_variant": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _I, _P]),
+    "advgrpo_debug_set_gemm_variant": (None, [_I]),
 }
 
 _lib = None

@@ -22,11 +22,13 @@ using namespace sm100;
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-template <int BN>
+// TWO = CTA pair (cta_group::2): the pair owns a 256 x 256 tile, each CTA stages its own 128 A rows and
+// half (128 rows) of the B tile, which halves the per-CTA operand traffic and leaves room for 6 stages.
+template <int BN, bool TWO = false>
 struct GCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = TWO ? 6 : ((BN == 256) ? 4 : 6);
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 2 * BM * 128;   // two [128 x 64] bf16 epilogue tiles
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
@@ -53,13 +55,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 
-template <int BN>
+template <int BN, bool TWO>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
             const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
             const GParams p) {
-  using G = GCfg<BN>;
+  using G = GCfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage = smem + G::kStages * G::kStageBytes;
@@ -75,6 +77,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int kb_total = p.kb1 + p.kb2;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;          // 0 = leader CTA of the pair
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kTileM = TWO ? 2 * BM : BM;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G::kStages; ++i) {
@@ -83,17 +89,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], 128);
+      mbar_init(&bar_acc_empty[i], TWO ? 256 : 128);
       mbar_init(&bar_res[i], 1);
     }
     fence_barrier_init();
   }
+  if constexpr (TWO) cluster_sync_all();          // peer barriers exist before any remote arrive / multicast
   if (warp == 5) {
-    tmem_alloc(tmem_base_smem, G::kTmemCols);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc_2cta(tmem_base_smem, G::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_base_smem, G::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -103,31 +115,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       prefetch_tmap(&tm_a);
       prefetch_tmap(&tm_w);
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * BM;
-        const int n0 = (tile % p.tiles_n) * BN;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
+        const int n0 = (tile % p.tiles_n) * BN + (TWO ? (int)rank * (BN / 2) : 0);
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int st = it % G::kStages;
           mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
           uint8_t* sa = smem + st * G::kStageBytes;
           uint8_t* sb = sa + G::kABytes;
-          mbar_expect_tx(&bar_full[st], G::kStageBytes);
-          if (kb < p.kb1) {
-            tma_load_2d(sa, &tm_a, &bar_full[st], kb * BK, m0);
-            tma_load_2d(sb, &tm_w, &bar_full[st], kb * BK, n0);
+          const CUtensorMap* ma = kb < p.kb1 ? &tm_a : &tm_a2;
+          const CUtensorMap* mw = kb < p.kb1 ? &tm_w : &tm_w2;
+          const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BK;
+          if constexpr (TWO) {
+            // both CTAs' bytes land on the LEADER's full barrier (one expect_tx of the pair's total)
+            const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
+            if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
+            tma_load_2d_2sm(sa, ma, full_leader, kc, m0);
+            tma_load_2d_2sm(sb, mw, full_leader, kc, n0);
           } else {
-            tma_load_2d(sa, &tm_a2, &bar_full[st], (kb - p.kb1) * BK, m0);
-            tma_load_2d(sb, &tm_w2, &bar_full[st], (kb - p.kb1) * BK, n0);
+            mbar_expect_tx(&bar_full[st], G::kStageBytes);
+            tma_load_2d(sa, ma, &bar_full[st], kc, m0);
+            tma_load_2d(sb, mw, &bar_full[st], kc, n0);
           }
         }
       }
     }
   } else if (warp == 5) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
       int it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
         const int acc = local & 1;
         mbar_wait(&bar_acc_empty[acc], ((local >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -140,12 +158,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           const uint32_t sb = sa + G::kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            mma_ss(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
-                   make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO)
+              mma_ss_2cta(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                          make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              mma_ss(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                     make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(&bar_empty[st]);
+          if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
         }
-        mma_commit(&bar_acc_full[acc]);
+        if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
       }
     }
   } else {
@@ -160,9 +182,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     constexpr int NG = BN / 64;
     uint32_t res_phase[2] = {0u, 0u};
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int acc = local & 1;
-      const int m0 = (tile / p.tiles_n) * BM;
+      const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int row = m0 + lrow;
       const bool row_ok = row < p.M;
@@ -243,8 +265,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           }
         }
         if (g == NG - 1 || n0 + (g + 1) * 64 >= p.N) {
-          tc_fence_before();
-          mbar_arrive(&bar_acc_empty[acc]);           // accumulator fully read: next tile may overwrite
+          tc_fence_before();                          // accumulator fully read: next tile may overwrite
+          if constexpr (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
+          else mbar_arrive(&bar_acc_empty[acc]);
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -258,32 +281,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, G::kTmemCols);
+    if constexpr (TWO) tmem_dealloc_2cta(tmem_base, G::kTmemCols); else tmem_dealloc(tmem_base, G::kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, bool TWO>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ta2,
                 const CUtensorMap& tw2, const CUtensorMap& tc, const CUtensorMap& tr, GParams& p,
                 cudaStream_t st) {
-  using G = GCfg<BN>;
+  using G = GCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(gemm_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
     attr_set = true;
   }
-  p.tiles_m = (p.M + BM - 1) / BM;
+  constexpr int kTileM = TWO ? 2 * BM : BM;
+  p.tiles_m = (p.M + kTileM - 1) / kTileM;
   p.tiles_n = (p.N + BN - 1) / BN;
   int tiles = p.tiles_m * p.tiles_n;
-  int grid = sm_count();
-  if (grid > tiles) grid = tiles;
-  gemm_kernel<BN><<<grid, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, tc, tr, p);
+  int workers = TWO ? sm_count() / 2 : sm_count();
+  if (workers > tiles) workers = tiles;
+  if constexpr (TWO) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * workers);
+    cfg.blockDim = dim3(G::kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO>, ta, tw, ta2, tw2, tc, tr, p));
+  } else {
+    gemm_kernel<BN, TWO><<<workers, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, tc, tr, p);
+  }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
+
+int g_gemm_variant = 0;   // 0 = auto, 1 = single-CTA tiles only, 2 = CTA pairs whenever the shape allows
 
 }  // namespace
 }  // namespace advgrpo
@@ -324,7 +366,8 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
     if (rc) return rc;
     const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t sw[2] = {0, (uint64_t)ldw * 2};
-    const uint32_t bw[2] = {BK, (uint32_t)BN};
+    const bool two = g_gemm_variant != 1 && BN == 256 && M >= 256;
+    const uint32_t bw[2] = {BK, (uint32_t)(two ? BN / 2 : BN)};
     rc = make_tmap_bf16(&tw, W, 2, dw, sw, bw, true);
     if (rc) return rc;
     if (has2) {
@@ -362,8 +405,13 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
   p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.M = (int)M; p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = has2 ? (int)(K2 / BK) : 0;
   p.epilogue = epilogue;
-  if (BN == 256) return launch_gemm<256>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
-  return launch_gemm<128>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  if (g_gemm_variant != 1 && BN == 256 && M >= 256)
+    return launch_gemm<256, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  if (BN == 256) return launch_gemm<256, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  return launch_gemm<128, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
 }
+
+// Test/bench hook (not part of the reference-facing surface): force the GEMM CTA shape.
+void advgrpo_debug_set_gemm_variant(int v) { g_gemm_variant = v; }
 
 }  // extern "C"

@@ -346,6 +346,11 @@ def attention(qkv, scale=None, causal=False):
 
 
 # --------------------------------------------------------------------------- GEMM
+def set_gemm_variant(v):
+    """Test/bench hook: 0 = auto (CTA pairs when the shape allows), 1 = single-CTA tiles only."""
+    _lib.load().advgrpo_debug_set_gemm_variant(int(v))
+
+
 EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL = 0, 1, 2, 3
 
 

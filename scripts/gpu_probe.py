@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 def probe_gemm_small():
     import torch
     from adv_grpo_b200 import ops
-    for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 256, 128), (256, 512, 256), (1229, 1536, 1536)]:
+    for (M, N, K) in [(128, 128, 64), (256, 256, 64), (256, 256, 128), (512, 512, 256), (1229, 1536, 1536), (300, 256, 64)]:
         g = torch.Generator(device="cuda").manual_seed(1)
         a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
         w = torch.randn(N, K, device="cuda", generator=g).bfloat16() / 8
@@ -172,7 +172,9 @@ def probe_perf():
     for (M, N, K) in [(19664, 4608, 1536), (19664, 1536, 1536), (19664, 6144, 1536), (19664, 1536, 6144)]:
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = torch.randn(N, K, device="cuda").bfloat16()
-        for name, fn in (("ours", lambda: ops.gemm(a, w)), ("cublas", lambda: torch.nn.functional.linear(a, w))):
+        for name, fn in (("ours-1cta", lambda: ops.gemm(a, w)), ("ours-2cta", lambda: ops.gemm(a, w)),
+                         ("cublas", lambda: torch.nn.functional.linear(a, w))):
+            ops.set_gemm_variant(1 if name == "ours-1cta" else 0)
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
