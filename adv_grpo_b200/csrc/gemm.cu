@@ -26,13 +26,13 @@ constexpr int BK = 64;
 // half (128 rows) of the B tile, which halves the per-CTA operand traffic and leaves room for 6 stages.
 template <int BN, bool TWO = false>
 struct GCfg {
-  static constexpr int kStages = TWO ? 6 : ((BN == 256) ? 4 : 6);
+  static constexpr int kStages = TWO ? 6 : ((BN >= 192) ? 4 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 2 * BM * 128;   // two [128 x 64] bf16 epilogue tiles
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
-  static constexpr int kTmemCols = 2 * BN;   // 512 or 256
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;   // two accumulators, power-of-two allocation
   static constexpr int kThreads = 192;
 };
 
@@ -357,7 +357,30 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
   }
   CUtensorMap ta, tw, ta2, tw2, tc, tr;
-  const int BN = (N >= 256 && N % 256 == 0) ? 256 : 128;
+  // Tile shape: minimise (waves of the persistent schedule) x (tile area / measured relative tile efficiency).
+  // CTA pairs with 256x256 tiles are the most efficient per FLOP (profiles/: 1.37 vs 1.20 PFLOP/s for
+  // single-CTA 128x256 tiles at M = 16384), but small-M problems (the 205-token text stream) lose whole
+  // waves to quantisation and prefer finer tiles.
+  struct Cand { int bn; bool pair; double eff; };
+  const Cand cands[4] = {{256, true, 1.00}, {256, false, 0.87}, {192, true, 0.80}, {128, false, 0.70}};
+  int BN = 128;
+  bool pair_ok = false;
+  {
+    double best = -1;
+    for (int ci = 0; ci < 4; ++ci) {
+      const Cand& c = cands[ci];
+      if (c.pair && (g_gemm_variant == 1 || M < 256)) continue;
+      if (!c.pair && g_gemm_variant == 3 && M >= 256 && N >= 256) continue;   // test hook: force pairs
+      if (c.bn > 128 && N < c.bn) continue;
+      if (c.bn == 192 && N % 192 != 0) continue;
+      const int64_t workers = c.pair ? sm_count() / 2 : sm_count();
+      const int64_t tile_m = c.pair ? 256 : 128;
+      const int64_t tiles = ((M + tile_m - 1) / tile_m) * ((N + c.bn - 1) / c.bn);
+      // a pair tile (256 rows) is worked on by two SMs: per-SM time ~ 128 * bn in both cases
+      const double cost = (double)((tiles + workers - 1) / workers) * (double)(128 * c.bn) / c.eff;
+      if (best < 0 || cost < best) { best = cost; BN = c.bn; pair_ok = c.pair; }
+    }
+  }
   {
     const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t sa[2] = {0, (uint64_t)lda * 2};
@@ -366,7 +389,7 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
     if (rc) return rc;
     const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t sw[2] = {0, (uint64_t)ldw * 2};
-    const bool two = g_gemm_variant != 1 && BN == 256 && M >= 256;
+    const bool two = pair_ok;
     const uint32_t bw[2] = {BK, (uint32_t)(two ? BN / 2 : BN)};
     rc = make_tmap_bf16(&tw, W, 2, dw, sw, bw, true);
     if (rc) return rc;
@@ -405,9 +428,10 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
   p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.M = (int)M; p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = has2 ? (int)(K2 / BK) : 0;
   p.epilogue = epilogue;
-  if (g_gemm_variant != 1 && BN == 256 && M >= 256)
-    return launch_gemm<256, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  if (pair_ok && BN == 256) return launch_gemm<256, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  if (pair_ok && BN == 192) return launch_gemm<192, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
   if (BN == 256) return launch_gemm<256, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  if (BN == 192) return launch_gemm<192, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
   return launch_gemm<128, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
 }
 

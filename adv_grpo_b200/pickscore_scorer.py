@@ -71,15 +71,55 @@ def images_to_pixel_values(images, device, size=224, dtype=torch.bfloat16):
     return ops.clip_preprocess(t, size, dtype=dtype)
 
 
+class _GraphedImageTower:
+    """CUDA-graph replay of `model.get_image_features` for a fixed batch shape (the ViT-H forward is ~400
+    launches of a few microseconds each: launch-bound when issued eagerly).  Re-captured whenever a
+    parameter version changes (discriminator steps update the last vision blocks in place)."""
+
+    def __init__(self, model):
+        self.model, self.entries = model, {}
+
+    def _version(self):
+        return sum(p._version for p in self.model.vision_model.parameters()) + self.model.visual_projection.weight._version
+
+    def __call__(self, pixel_values):
+        from . import _lib
+        key = (tuple(pixel_values.shape), pixel_values.dtype)
+        ver = self._version()
+        ent = self.entries.get(key)
+        if ent is None or ent[0] != ver:
+            if ent is None or ent[1] is not None:            # first sight (or stale graph): run eagerly once to warm up
+                self.entries[key] = (ver, None, None, None, 0)
+                return self.model.get_image_features(pixel_values=pixel_values)
+        if ent[1] is None:
+            static_in = pixel_values.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                out = self.model.get_image_features(pixel_values=static_in)
+            ent = (ver, g, static_in, out, _lib.launch_count() - n0)
+            self.entries[key] = ent
+        _, g, static_in, out, n_kernels = ent
+        static_in.copy_(pixel_values)
+        g.replay()
+        _lib.add_launches(n_kernels)
+        return out.clone()
+
+
 class PickScoreScorer(torch.nn.Module):
-    def __init__(self, device="cuda", dtype=torch.float32, cfg=CLIP_H, state_dict=None, tokenizer=None, seed=3):
+    def __init__(self, device="cuda", dtype=torch.float32, cfg=CLIP_H, state_dict=None, tokenizer=None, seed=3,
+                 use_cuda_graph=True):
         super().__init__()
+        self.use_cuda_graph = use_cuda_graph
         self.device, self.dtype = device, dtype
         if state_dict is None:
             state_dict = init_clip(cfg, seed=seed, device=device, dtype=torch.bfloat16)
         # the kernels compute in bf16 (fp32 accumulation); dtype is recorded for API parity
         self.model = CLIPModel.from_params(state_dict, cfg, device=device, dtype=torch.bfloat16)
         self.processor = CLIPProcessorLike(tokenizer or SyntheticCLIPTokenizer(cfg["vocab"]), device, cfg["image"])
+        self._image_tower = None
+        self._text_cache = {}
 
     @torch.no_grad()
     def __call__(self, prompt, images):
@@ -88,11 +128,28 @@ class PickScoreScorer(torch.nn.Module):
         if isinstance(prompt, str):
             prompt = [prompt]
         uniq = list(dict.fromkeys(prompt))
-        ids = self.processor.tokenizer(uniq, padding=True, truncation=True, max_length=77)["input_ids"].to(self.device)
-        image_embs = model.get_image_features(pixel_values=pixel_values).float()
+        if self.use_cuda_graph and torch.device(self.device).type == "cuda":
+            if self._image_tower is None or self._image_tower.model is not model:
+                self._image_tower = _GraphedImageTower(model)
+            image_embs = self._image_tower(pixel_values).float()
+        else:
+            image_embs = model.get_image_features(pixel_values=pixel_values).float()
         image_embs = image_embs / image_embs.norm(p=2, dim=-1, keepdim=True)
-        text_embs = model.get_text_features(input_ids=ids).float()
-        text_embs = text_embs / text_embs.norm(p=2, dim=-1, keepdim=True)
+        # the text tower is frozen: one forward per distinct prompt, cached across calls (generated and
+        # reference images of a group share the prompt; the reference recomputes it for every image)
+        tver = sum(p._version for p in model.text_model.parameters())
+        feats = []
+        for pr in uniq:
+            hit = self._text_cache.get(pr)
+            if hit is None or hit[0] != tver:
+                ids = self.processor.tokenizer([pr], padding=True, truncation=True, max_length=77)["input_ids"].to(self.device)
+                t = model.get_text_features(input_ids=ids).float()
+                if len(self._text_cache) > 4096:
+                    self._text_cache.clear()
+                hit = (tver, t / t.norm(p=2, dim=-1, keepdim=True))
+                self._text_cache[pr] = hit
+            feats.append(hit[1])
+        text_embs = torch.cat(feats, 0)
         index = torch.tensor([uniq.index(p) for p in prompt], device=self.device)
         scores = model.logit_scale.exp().float() * (text_embs[index] * image_embs).sum(-1)
         return scores / 26

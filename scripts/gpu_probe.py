@@ -169,12 +169,12 @@ def probe_perf():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"torch SDPA (library baseline): {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
-    for (M, N, K) in [(19664, 4608, 1536), (19664, 1536, 1536), (19664, 6144, 1536), (19664, 1536, 6144)]:
+    for (M, N, K) in [(16384, 4608, 1536), (16384, 1536, 1536), (16384, 6144, 1536), (16384, 1536, 6144), (3280, 1536, 1536), (3280, 4608, 1536), (3280, 1536, 6144)]:
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = torch.randn(N, K, device="cuda").bfloat16()
-        for name, fn in (("ours-1cta", lambda: ops.gemm(a, w)), ("ours-2cta", lambda: ops.gemm(a, w)),
-                         ("cublas", lambda: torch.nn.functional.linear(a, w))):
-            ops.set_gemm_variant(1 if name == "ours-1cta" else 0)
+        for name, fn in (("ours-1cta", lambda: ops.gemm(a, w)), ("ours-2cta-bn256", lambda: ops.gemm(a, w)),
+                         ("ours-auto", lambda: ops.gemm(a, w)), ("cublas", lambda: torch.nn.functional.linear(a, w))):
+            ops.set_gemm_variant({"ours-1cta": 1, "ours-2cta-bn256": 3}.get(name, 0))
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()

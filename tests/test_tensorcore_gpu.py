@@ -159,3 +159,24 @@ def test_attention_autograd_function(ops):
     out = ops.attention(qkv)
     (out.float() * w).sum().backward()
     assert qkv.grad is not None and qkv.grad.shape == qkv.shape and torch.isfinite(qkv.grad.float()).all()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("M,N,K", [(1000, 1536, 256), (520, 192, 64), (3280, 1536, 1536), (256, 4608, 128), (700, 384, 192)])
+def test_gemm_tile_variants(ops, variant, M, N, K):
+    """CTA pairs / single CTA and 256- / 192- / 128-wide tiles must agree with fp32 matmul (incl. ragged M, N)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g).bfloat16()
+    res = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    gate = torch.randn(1, N, device=DEV, generator=g).bfloat16()
+    ops.set_gemm_variant(variant)
+    try:
+        got = ops.gemm(a, w, bias=bias)
+        got_r = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GATE_RESIDUAL, residual=res, gate=gate, rows_per_gate=M)
+    finally:
+        ops.set_gemm_variant(0)
+    ref = a.float() @ w.float().T + bias.float()
+    assert _rel_err(got, ref) < 6e-3
+    assert _rel_err(got_r, res.float() + gate.float() * ref) < 6e-3
