@@ -30,20 +30,24 @@ constexpr int BKV = 128;
 constexpr int STAGES = 2;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain: skip O rescale while max grows < 2^8
 
-template <int D, int NQ>
+template <int D, int NQ, int RS = 1>
 struct Cfg {
   static constexpr int kHalves = D / 64;                 // 64-column (128 B) swizzle atoms per row
   static constexpr int kTileBytes = BQ * D * 2;          // one Q/K/V tile
   static constexpr int kSmemTiles = NQ * kTileBytes + STAGES * 2 * kTileBytes;
-  static constexpr int kSmemBytes = kSmemTiles + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kXchBytes = 3 * NQ * RS * 128 * 4;   // row max (2 parities) + row sum exchange between row-split threads
+  static constexpr int kSmemBytes = kSmemTiles + 1024 /*align*/ + 256 /*barriers*/ + kXchBytes;
   static constexpr int kColsPerQ = 128 + 64 + D;
   static constexpr int kTmemCols = (NQ * kColsPerQ <= 256) ? 256 : 512;
-  static constexpr int kSoftmaxWarps = 4 * NQ;
+  static constexpr int kSoftmaxWarps = 4 * NQ * RS;   // RS threads share one query row (column slices)
   static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;   // + one utility warpgroup (TMA, MMA, 2 idle)
   // register re-balancing (setmaxnreg works per 4-warp group): utility warps shrink, softmax warps grow
   static constexpr bool kRebalance = (D == 64);
-  static constexpr int kRegsUtility = 56;
-  static constexpr int kRegsSoftmax = (NQ == 2) ? 216 : 200;   // 256*216+128*56 <= 384*168; 128*200+128*56 <= 256*128
+  static constexpr int kRegsUtility = (RS == 2) ? 40 : 56;
+  // budgets: (softmax threads) * kRegsSoftmax + 128 * kRegsUtility <= threads * (registers at launch)
+  //   RS=1: NQ=2 256*216+128*56 <= 384*168 ; NQ=1 128*200+128*56 <= 256*128
+  //   RS=2: NQ=2 512*104+128*40 <= 640*96  ; NQ=1 256*96+128*40 <= 384*80
+  static constexpr int kRegsSoftmax = (RS == 2) ? ((NQ == 2) ? 104 : 96) : ((NQ == 2) ? 216 : 200);
   static_assert(NQ * kColsPerQ <= 512, "TMEM budget");
 };
 
@@ -75,10 +79,10 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
-template <int D, int NQ, int EMU>
-__global__ void __launch_bounds__(Cfg<D, NQ>::kThreads, (NQ == 1 && D == 64) ? 2 : 1)
+template <int D, int NQ, int EMU, int RS>
+__global__ void __launch_bounds__(Cfg<D, NQ, RS>::kThreads, (NQ == 1 && D == 64) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  using C = Cfg<D, NQ>;
+  using C = Cfg<D, NQ, RS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                   // NQ tiles
@@ -94,6 +98,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* bar_pv_done = bar_p_full + NQ;      // NQ
   uint64_t* bar_s_free = bar_pv_done + NQ;      // NQ   softmax has S in registers: QK(j+1) may overwrite it
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_s_free + NQ);
+  float* xch = reinterpret_cast<float*>(smem + C::kSmemTiles + 256);   // [3][NQ][RS][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,9 +124,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(&bar_s_full[i], 1);
-      mbar_init(&bar_p_full[i], 128);
+      mbar_init(&bar_p_full[i], 128 * RS);
       mbar_init(&bar_pv_done[i], 1);
-      mbar_init(&bar_s_free[i], 128);
+      mbar_init(&bar_s_free[i], 128 * RS);
     }
     fence_barrier_init();
   }
@@ -218,48 +223,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   } else {
     // ============================== softmax / epilogue ==============================
     if constexpr (C::kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsSoftmax));
-    const int q = warp / 4;                         // query tile handled by this warp
+    constexpr int NCH = 4 / RS;                     // 32-column chunks of the S row owned by this thread
+    constexpr int CPT = 128 / RS;                   // S columns per thread
+    constexpr int OCH = (D / 32) / RS;              // 32-column chunks of the O row owned by this thread
+    const int wg = warp / 4;
+    const int q = wg / RS;                          // query tile handled by this warp
+    const int half = wg % RS;                       // column slice of the row (RS threads share a row)
     const int row = (warp % 4) * 32 + lane;         // row inside the tile == TMEM lane
     const int q_idx = q0 + q * BQ + row;            // global query index
     const uint32_t lane_addr = static_cast<uint32_t>((warp % 4) * 32) << 16;
-    const uint32_t s_tmem = tmem_base + q * C::kColsPerQ + lane_addr;
-    const uint32_t p_tmem = s_tmem + 128;
-    const uint32_t o_tmem = s_tmem + 192;
+    const uint32_t s_tmem = tmem_base + q * C::kColsPerQ + lane_addr + half * CPT;
+    const uint32_t p_tmem = tmem_base + q * C::kColsPerQ + 128 + lane_addr + half * (CPT / 2);
+    const uint32_t o_tmem = tmem_base + q * C::kColsPerQ + 192 + lane_addr + half * (OCH * 32);
+    float* xmax = xch + (q * RS) * 128 + row;       // + parity * NQ*RS*128 + slice * 128
+    float* xsum = xch + 2 * NQ * RS * 128 + (q * RS) * 128 + row;
     const float sl2 = p.scale_log2;
     float m = -INFINITY;   // running max (scaled, log2 domain)
-    float l = 0.f;         // running denominator
+    float l = 0.f;         // running denominator (this thread's column slice)
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&bar_s_full[q], j & 1);
       tc_fence_after();
-      const int kv0 = j * BKV;
-      // columns >= lim are masked out
+      const int kv0 = j * BKV + half * CPT;         // first kv index of my column slice
+      // columns >= lim (relative to my slice) are masked out
       int lim = S - kv0;
       if (p.causal) {
         int c = q_idx - kv0 + 1;
         lim = c < lim ? c : lim;
       }
-      const bool need_mask = lim < BKV;
-      // ---- S row -> registers (single TMEM read), then release S for QK(j+1) ----
-      uint32_t sv[4][32];
+      const bool need_mask = lim < CPT;
+      // ---- my slice of the S row -> registers (single TMEM read), then release S for QK(j+1) ----
+      uint32_t sv[NCH][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+      for (int c = 0; c < NCH; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&bar_s_free[q]);
       if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NCH; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= lim) sv[c][i] = 0xff800000u;   // -inf
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent FMNMX3 chains
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
           mx4[(i / 2) & 3] = fmaxf(mx4[(i / 2) & 3], fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if constexpr (RS == 2) {
+        // the two threads of a row agree on the row max through shared memory (double-buffered by tile parity)
+        float* slot = xmax + (j & 1) * (NQ * RS * 128);
+        slot[half * 128] = mx;
+        named_bar_sync(1 + q, 128 * RS);
+        mx = fmaxf(mx, slot[(half ^ 1) * 128]);
+      }
       float m_new = fmaxf(m, mx * sl2);
       // lazy rescale: keep the stale max while it is within 2^8 of the true one
       if (m != -INFINITY && m_new - m <= kRescaleThreshold) m_new = m;
@@ -270,7 +289,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < OCH; ++c) {
             uint32_t r[32];
             tmem_ld32(o_tmem + c * 32, r);
             tmem_wait_ld();
@@ -284,7 +303,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       float2 sum2 = make_float2(0.f, 0.f);
       const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -311,14 +330,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     // ---- epilogue: O / l -> bf16, token-major store ----
     mbar_wait(&bar_pv_done[q], (nkv - 1) & 1);
     tc_fence_after();
+    if constexpr (RS == 2) {
+      xsum[half * 128] = l;
+      named_bar_sync(1 + q, 128 * RS);
+      l += xsum[(half ^ 1) * 128];
+    }
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const bool valid = q_idx < S;
     __nv_bfloat16* orow;
     if (p.out2 == nullptr) orow = p.out + (((int64_t)b * S + q_idx) * p.H + h) * D;
     else if (q_idx < p.S_split) orow = p.out + (((int64_t)b * p.S_split + q_idx) * p.H + h) * D;
     else orow = p.out2 + (((int64_t)b * (S - p.S_split) + (q_idx - p.S_split)) * p.H + h) * D;
+    orow += half * (OCH * 32);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OCH; ++c) {
       uint32_t r[32];
       tmem_ld32(o_tmem + c * 32, r);
       tmem_wait_ld();
@@ -334,7 +359,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         }
       }
     }
-    if (valid && p.lse) {
+    if (valid && p.lse && half == 0) {
       const float mm = (m == -INFINITY) ? 0.f : m;
       p.lse[((int64_t)b * p.H + h) * S + q_idx] = (mm + log2f(l)) * 0.6931471805599453f;
     }
@@ -348,10 +373,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   }
 }
 
-template <int D, int NQ, int EMU>
+template <int D, int NQ, int EMU, int RS = 1>
 int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H, float scale,
            int causal, cudaStream_t st) {
-  using C = Cfg<D, NQ>;
+  using C = Cfg<D, NQ, RS>;
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)D, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
   const uint64_t strides[4] = {0, (uint64_t)D * 2, (uint64_t)(3 * H * D) * 2, (uint64_t)(S * 3 * H * D) * 2};
@@ -360,7 +385,7 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   if (rc != ADVGRPO_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_kernel<D, NQ, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_kernel<D, NQ, EMU, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   Params p;
@@ -373,14 +398,15 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   dim3 grid((unsigned)((S + BQ * NQ - 1) / (BQ * NQ)), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<D, NQ, EMU><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
+  attn_fwd_kernel<D, NQ, EMU, RS><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
 
 }  // namespace
 
-// variant: 0 = auto; 1..6 = {1,2} query tiles per CTA x {0,1,2} of every 4 exp pairs emulated on the FMA pipe
+// variant: 0 = auto; 1..6 = {1,2} query tiles per CTA x {0,1,2} of every 4 exp pairs emulated on the FMA pipe;
+// 7..10 = the same with two threads per query row (column-split softmax, 16 softmax warps per SM)
 int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
                       int64_t D, float scale, int causal, int variant, cudaStream_t st) {
 #define ADVGRPO_ATTN_ARGS qkv, out, out2, S_split, lse, B, S, H, scale, causal, st
@@ -392,6 +418,10 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 4: return launch<64, 2, 1>(ADVGRPO_ATTN_ARGS);
       case 5: return launch<64, 1, 2>(ADVGRPO_ATTN_ARGS);
       case 6: return launch<64, 2, 2>(ADVGRPO_ATTN_ARGS);
+      case 7: return launch<64, 1, 0, 2>(ADVGRPO_ATTN_ARGS);   // two threads per query row
+      case 8: return launch<64, 1, 1, 2>(ADVGRPO_ATTN_ARGS);
+      case 9: return launch<64, 2, 0, 2>(ADVGRPO_ATTN_ARGS);
+      case 10: return launch<64, 2, 1, 2>(ADVGRPO_ATTN_ARGS);
       default: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
     }
   }

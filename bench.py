@@ -319,7 +319,12 @@ def run_ours(args):
     achieved = gemm_flops / ms_gemm / 1e9
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (fused QKV projection + LoRA second product, "
                 f"M={M} N={N} K={K}+{K2})", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                "frac": achieved / peak_burst, "traffic": None, "peak_source": f"{src} burst bf16 (kernel timed alone)"}
+                "frac": achieved / peak_burst,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the same M, N, K (without the LoRA
+                # blocks) from the ncu --set full capture in profiles/r1_ncu_full_summary.md; algorithmic bytes
+                # (A + W + C in bf16) are 2 * (M*K + N*K + M*N) = 215 MB: no wasted re-reads
+                "traffic": 167.9e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * N),
+                "peak_source": f"{src} burst bf16 (kernel timed alone)"}
     kernels = {
         "attn_fwd_tflops": attn_flops / ms_attn / 1e9, "attn_fwd_frac": attn_flops / ms_attn / 1e9 / peak_burst,
         "attn_bwd_tflops": 2.5 * attn_flops / ms_attn_bwd / 1e9,
