@@ -12,8 +12,8 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads)
-gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int64_t HW, int C, int groups,
-                int pixels_per_block) {
+gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, double* __restrict__ sums, int64_t HW,
+                int C, int groups, int pixels_per_block) {
   __shared__ double s_sum[64], s_sq[64];
   const int n = blockIdx.y;
   const int quads = C / 4;                       // float4 per pixel
@@ -28,9 +28,11 @@ gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int64_t 
   if (p1 > HW) p1 = HW;
   const float* base = x + (int64_t)n * HW * C;
   float s = 0.f, ss = 0.f;
+  const float4 ib = in_bias ? *reinterpret_cast<const float4*>(in_bias + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   if (pl < ppi) {
     for (int64_t p = p0 + pl; p < p1; p += ppi) {
-      const float4 v = *reinterpret_cast<const float4*>(base + p * C + q * 4);
+      float4 v = *reinterpret_cast<const float4*>(base + p * C + q * 4);
+      v.x += ib.x; v.y += ib.y; v.z += ib.z; v.w += ib.w;
       s += (v.x + v.y) + (v.z + v.w);
       ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
     }
@@ -45,7 +47,7 @@ gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int64_t 
 }
 
 __global__ void __launch_bounds__(kThreads)
-gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
+gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, const double* __restrict__ sums, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ y, int64_t HW, int C, int groups, float eps,
                 int silu) {
   const int n = blockIdx.y;
@@ -63,7 +65,11 @@ gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, co
     double var = sums[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
     if (var < 0) var = 0;
     const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float4 v = *reinterpret_cast<const float4*>(xb + i * 4);
+    float4 v = *reinterpret_cast<const float4*>(xb + i * 4);
+    if (in_bias) {
+      const float4 ib = *reinterpret_cast<const float4*>(in_bias + c);
+      v.x += ib.x; v.y += ib.y; v.z += ib.z; v.w += ib.w;
+    }
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
     const float4 be = *reinterpret_cast<const float4*>(beta + c);
     float o[4] = {(v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
@@ -76,6 +82,42 @@ gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, co
   }
 }
 
+// out = a + b + bias[c]   (residual add of a ResnetBlock2D with the conv bias folded in)
+__global__ void __launch_bounds__(kThreads)
+add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
+                float* __restrict__ out, int64_t total4, int C) {
+  const int quads = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (int64_t)gridDim.x * kThreads) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bb = *reinterpret_cast<const float4*>(bias + (i % quads) * 4);
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x + bb.x, x.y + y.y + bb.y, x.z + y.z + bb.z, x.w + y.w + bb.w);
+  }
+}
+
+// nearest-neighbour 2x upsampling, NHWC fp32: one float4 read, four float4 writes per thread
+__global__ void __launch_bounds__(kThreads)
+upsample2x_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t B, int H, int W, int C) {
+  const int quads = C / 4;
+  const int64_t total = B * H * W * quads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int q = (int)(i % quads);
+    int64_t pix = i / quads;
+    const int xw = (int)(pix % W);
+    pix /= W;
+    const int yh = (int)(pix % H);
+    const int64_t n = pix / H;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float* base = y + (((n * 2 * H + 2 * yh) * 2 * W + 2 * xw) * (int64_t)C) + q * 4;
+    const int64_t row = (int64_t)2 * W * C;
+    *reinterpret_cast<float4*>(base) = v;
+    *reinterpret_cast<float4*>(base + C) = v;
+    *reinterpret_cast<float4*>(base + row) = v;
+    *reinterpret_cast<float4*>(base + row + C) = v;
+  }
+}
+
 }  // namespace
 }  // namespace advgrpo
 
@@ -85,7 +127,7 @@ extern "C" {
 
 size_t advgrpo_group_norm_workspace_bytes(int64_t B, int64_t groups) { return (size_t)B * groups * 2 * sizeof(double); }
 
-int advgrpo_group_norm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, int64_t B,
+int advgrpo_group_norm_silu_nhwc(const float* x, const float* in_bias, const float* gamma, const float* beta, float* y, int64_t B,
                                  int64_t HW, int64_t C, int64_t groups, float eps, int silu, void* workspace,
                                  size_t workspace_bytes, advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(x && gamma && beta && y, "group_norm_silu_nhwc: null pointer");
@@ -104,13 +146,41 @@ int advgrpo_group_norm_silu_nhwc(const float* x, const float* gamma, const float
   int64_t ppb = (HW + blocks - 1) / blocks;
   ppb = (ppb + ppi - 1) / ppi * ppi;
   blocks = (HW + ppb - 1) / ppb;
-  gn_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, st>>>(x, sums, HW, (int)C, (int)groups, (int)ppb);
+  gn_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, st>>>(x, in_bias, sums, HW, (int)C, (int)groups, (int)ppb);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   int64_t ablocks = (HW * (C / 4) + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)sm_count() * 16 / B + 1;
   if (ablocks > cap) ablocks = cap;
-  gn_apply_kernel<<<dim3((unsigned)ablocks, (unsigned)B), kThreads, 0, st>>>(x, sums, gamma, beta, y, HW, (int)C,
+  gn_apply_kernel<<<dim3((unsigned)ablocks, (unsigned)B), kThreads, 0, st>>>(x, in_bias, sums, gamma, beta, y, HW, (int)C,
                                                                             (int)groups, eps, silu);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+int advgrpo_add_bias_nhwc(const float* a, const float* b, const float* bias, float* out, int64_t rows, int64_t C,
+                          advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(a && b && out, "add_bias_nhwc: null pointer");
+  ADVGRPO_CHECK_ARG(rows >= 1 && C >= 4 && C % 4 == 0, "add_bias_nhwc: C must be a multiple of 4");
+  ADVGRPO_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(out) && (!bias || aligned16(bias)), "add_bias_nhwc: alignment");
+  const int64_t total4 = rows * (C / 4);
+  int64_t blocks = (total4 + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  add_bias_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(a, b, bias, out, total4, (int)C);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+int advgrpo_upsample_nearest2x_nhwc(const float* x, float* y, int64_t B, int64_t H, int64_t W, int64_t C,
+                                    advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(x && y, "upsample_nearest2x_nhwc: null pointer");
+  ADVGRPO_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0, "upsample_nearest2x_nhwc: bad shape");
+  ADVGRPO_CHECK_ARG(aligned16(x) && aligned16(y), "upsample_nearest2x_nhwc: alignment");
+  const int64_t total = B * H * W * (C / 4);
+  int64_t blocks = (total + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, y, B, (int)H, (int)W, (int)C);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

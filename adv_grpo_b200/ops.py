@@ -430,7 +430,7 @@ def dino_preprocess(images, out_size=518):
 
 
 # --------------------------------------------------------------------------- VAE GroupNorm (+SiLU)
-def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True):
+def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True, in_bias=None):
     """x: f32 [B, C, H, W] stored channels_last (or [B, H, W, C] contiguous).  Returns the same logical shape,
     channels_last."""
     _need_cuda(x)
@@ -442,6 +442,26 @@ def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True):
     y = torch.empty_like(x, memory_format=torch.channels_last)
     ws_bytes = _lib.query("advgrpo_group_norm_workspace_bytes", B, groups)
     ws = _workspace("gn", ws_bytes, x.device)
-    _lib.call("advgrpo_group_norm_silu_nhwc", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), B, H * W, C, groups,
+    _lib.call("advgrpo_group_norm_silu_nhwc", _ptr(x), _ptr(in_bias), _ptr(gamma), _ptr(beta), _ptr(y), B, H * W, C, groups,
               float(eps), int(bool(silu)), _ptr(ws), ws.numel(), _stream())
+    return y
+
+
+def add_bias_nhwc(a, b, bias=None):
+    """a + b + bias[c] for channels_last fp32 4-D tensors (fused residual add of the VAE resnet blocks)."""
+    _need_cuda(a, b)
+    a = a if a.is_contiguous(memory_format=torch.channels_last) else a.contiguous(memory_format=torch.channels_last)
+    b = b if b.is_contiguous(memory_format=torch.channels_last) else b.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = a.shape
+    out = torch.empty_like(a, memory_format=torch.channels_last)
+    _lib.call("advgrpo_add_bias_nhwc", _ptr(a), _ptr(b), _ptr(bias), _ptr(out), B * H * W, C, _stream())
+    return out
+
+
+def upsample_nearest2x_nhwc(x):
+    _need_cuda(x)
+    x = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    y = torch.empty((B, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    _lib.call("advgrpo_upsample_nearest2x_nhwc", _ptr(x), _ptr(y), B, H, W, C, _stream())
     return y

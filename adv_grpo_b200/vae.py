@@ -1,7 +1,14 @@
 """SD3 VAE decoder (`pipeline.vae` of the reference: `fast.py:667-669`, kept in fp32 like
 `train_sd3_fast_pickscore.py:481`) + the `VaeImageProcessor.postprocess(output_type='pt')` step.
-The convolutions are plain library calls (cuDNN, TF32 like the reference's allow_tf32) in
-channels_last; SURVEY.md section 8(f) ranks a tcgen05 implicit-GEMM decoder as "next".
+
+Channels-last fp32 end to end.  The convolutions are plain library calls (cuDNN implicit GEMM, TF32 like the
+reference's allow_tf32); SURVEY.md section 8(f) ranks a tcgen05 implicit-GEMM decoder as "next".  Everything
+between the convolutions is fused into our streaming kernels so that no tensor makes an extra HBM round trip:
+  * GroupNorm + SiLU in two passes, with the PRECEDING convolution's bias folded into the statistics/apply
+    (the convolutions run bias-free: no separate bias pass, no NCHW<->NHWC copies around group_norm);
+  * residual add + conv2 bias (+ shortcut bias) in one pass;
+  * nearest 2x upsampling as one vectorised pass;
+  * the single-head mid-block attention as two TF32 batched GEMMs + softmax instead of an fp32 SIMT fmha.
 diffusers state-dict names."""
 import torch
 import torch.nn.functional as F
@@ -21,35 +28,67 @@ class AutoencoderKL:
             if v.dim() == 4:
                 v = v.contiguous(memory_format=torch.channels_last)
             self.p[k] = v
+        self.fused = torch.device(device).type == "cuda" and dtype == torch.float32
 
     def to(self, *a, **k):
         return self
 
-    def _gn(self, name, x, silu=False):
+    # ---- building blocks -------------------------------------------------------------------------------
+    def _fusable(self, C):
+        return self.fused and C % 128 == 0 and 256 % (C // 4) == 0
+
+    def _gn(self, name, x, silu=False, in_bias=None):
         C = x.shape[1]
-        if x.is_cuda and x.dtype == torch.float32 and C % 128 == 0 and 256 % (C // 4) == 0:
-            return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu)
+        if self._fusable(C):
+            return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu,
+                                            in_bias=in_bias)
+        if in_bias is not None:
+            x = x + in_bias[None, :, None, None]
         y = F.group_norm(x, 32, self.p[name + ".weight"], self.p[name + ".bias"], eps=1e-6)   # tiny test configs
         return F.silu(y) if silu else y
 
-    def _conv(self, name, x, pad=1):
-        return F.conv2d(x, self.p[name + ".weight"], self.p[name + ".bias"], padding=pad)
+    def _conv(self, name, x, pad=1, bias=True):
+        return F.conv2d(x, self.p[name + ".weight"], self.p[name + ".bias"] if bias else None, padding=pad)
 
     def _resnet(self, pre, x):
-        h = self._conv(pre + ".conv1", self._gn(pre + ".norm1", x, silu=True))
-        h = self._conv(pre + ".conv2", self._gn(pre + ".norm2", h, silu=True))
-        if pre + ".conv_shortcut.weight" in self.p:
-            x = self._conv(pre + ".conv_shortcut", x, pad=0)
-        return x + h
+        p = self.p
+        C_out = p[pre + ".conv1.weight"].shape[0]
+        fuse = self._fusable(C_out)
+        h = self._conv(pre + ".conv1", self._gn(pre + ".norm1", x, silu=True), bias=not fuse)
+        h = self._gn(pre + ".norm2", h, silu=True, in_bias=p[pre + ".conv1.bias"] if fuse else None)
+        h = self._conv(pre + ".conv2", h, bias=not fuse)
+        has_sc = pre + ".conv_shortcut.weight" in p
+        if has_sc:
+            x = self._conv(pre + ".conv_shortcut", x, pad=0, bias=not fuse)
+        if not fuse:
+            return x + h
+        bias = p[pre + ".conv2.bias"]
+        if has_sc:
+            key = pre + ".fused_bias"
+            if key not in p:
+                p[key] = (p[pre + ".conv2.bias"] + p[pre + ".conv_shortcut.bias"]).contiguous()
+            bias = p[key]
+        return ops.add_bias_nhwc(x, h, bias)
 
     def _mid_attn(self, pre, x):
         p = self.p
         B, C, H, W = x.shape
-        h = self._gn(pre + ".group_norm", x).reshape(B, C, H * W).transpose(1, 2)
+        h = self._gn(pre + ".group_norm", x)
+        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)                       # NHWC storage: a view, no copy
         q, k, v = (F.linear(h, p[f"{pre}.to_{n}.weight"], p[f"{pre}.to_{n}.bias"]) for n in "qkv")
-        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        if self.fused:
+            s = torch.bmm(q * (C ** -0.5), k.transpose(1, 2))
+            o = torch.bmm(torch.softmax(s, dim=-1), v)
+        else:
+            o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         o = F.linear(o, p[pre + ".to_out.0.weight"], p[pre + ".to_out.0.bias"])
-        return x + o.transpose(1, 2).reshape(B, C, H, W)
+        o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                         # logical NCHW, channels_last strides
+        return ops.add_bias_nhwc(x, o, None) if self.fused else x + o
+
+    def _upsample(self, x):
+        if self.fused and x.shape[1] % 4 == 0:
+            return ops.upsample_nearest2x_nhwc(x)
+        return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
     @torch.no_grad()
     def decode(self, z, return_dict=False):
@@ -63,8 +102,7 @@ class AutoencoderKL:
             for j in range(self.cfg["layers_per_block"] + 1):
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x)
             if i < n_up - 1:
-                x = F.interpolate(x, scale_factor=2.0, mode="nearest")
-                x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
+                x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", self._upsample(x))
         x = self._gn("decoder.conv_norm_out", x, silu=True)
         return (self._conv("decoder.conv_out", x),)
 

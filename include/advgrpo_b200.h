@@ -230,11 +230,19 @@ int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64
  * between the convolutions of the SD3 VAE decoder (diffusers AutoencoderKL.decode, reference call site
  * adv_grpo/diffusers_patch/sd3_pipeline_with_logprob_fast.py:669).  x, y: f32 [B, HW, C] (channels last);
  * gamma, beta: f32 [C].  C / groups must be a multiple of 4.  In place (y == x) is allowed.
+ * in_bias (f32 [C], may be NULL) is added to x first: the bias of the preceding convolution, so the
+ * convolution itself runs bias-free and no separate bias pass exists.
  */
 size_t advgrpo_group_norm_workspace_bytes(int64_t B, int64_t groups);
-int advgrpo_group_norm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, int64_t B,
-                                 int64_t HW, int64_t C, int64_t groups, float eps, int silu, void* workspace,
-                                 size_t workspace_bytes, advgrpo_stream_t stream);
+int advgrpo_group_norm_silu_nhwc(const float* x, const float* in_bias, const float* gamma, const float* beta,
+                                 float* y, int64_t B, int64_t HW, int64_t C, int64_t groups, float eps, int silu,
+                                 void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
+/* out = a + b + bias[c] on NHWC fp32 [rows, C] (ResnetBlock2D residual add with the conv2 / shortcut biases
+ * folded in; bias may be NULL), and nearest-neighbour 2x upsampling x [B,H,W,C] -> y [B,2H,2W,C] (Upsample2D). */
+int advgrpo_add_bias_nhwc(const float* a, const float* b, const float* bias, float* out, int64_t rows, int64_t C,
+                          advgrpo_stream_t stream);
+int advgrpo_upsample_nearest2x_nhwc(const float* x, float* y, int64_t B, int64_t H, int64_t W, int64_t C,
+                                    advgrpo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,93 @@
+"""Reward towers at their TRUE sizes (CLIP-ViT-H/14, DINOv2-B/14) against the fp32 CPU oracle, and the two
+discriminator steps (configs 3 and 5) against the oracle losses."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_clip_h_pickscore_full_size_matches_oracle():
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from oracle import clip as clip_o
+    from oracle import preprocess as pre_o
+    cfg = weights.CLIP_H
+    params = weights.init_clip(cfg, seed=3, device="cpu", dtype=torch.bfloat16)
+    scorer = PickScoreScorer(device=DEV, cfg=cfg, state_dict=params)
+    images = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(0)).bfloat16()
+    prompts = ["a watercolor painting of a lighthouse at dawn", "a robot reading a newspaper"]
+    got = scorer(prompts, images.to(DEV)).float().cpu()
+    got2 = scorer(prompts, images.to(DEV)).float().cpu()              # second call: CUDA-graph replay + text cache
+    u8 = pre_o.pil_bicubic_resize_u8(pre_o.quantise_bf16(images).numpy(), 224)
+    pix = torch.from_numpy(pre_o.clip_pixel_values(u8))
+    ids = scorer.processor.tokenizer(prompts, padding=True, max_length=77)["input_ids"]
+    ocfg = dict(patch=14, v_layers=32, v_heads=16, t_layers=24, t_heads=16)
+    ref = clip_o.pickscore({k: v.float() for k, v in params.items()}, ocfg, ids, pix)
+    # 32 + 24 bf16 layers vs fp32: scores are 100/26 * cosine
+    assert torch.allclose(got, ref, atol=6e-2), (got, ref)
+    assert torch.allclose(got2, got, atol=1e-6)
+
+
+def test_dinov2_b_full_size_matches_oracle():
+    from adv_grpo_b200 import ops, weights
+    from adv_grpo_b200.dinov2 import DinoV2
+    from oracle import dinov2 as dino_o
+    cfg = weights.DINOV2_B
+    params = weights.init_dinov2(cfg, seed=4, device="cpu", dtype=torch.bfloat16)
+    scorer = DinoV2(params, cfg, device=DEV)
+    images = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(1))
+    feats = scorer.forward_features(ops.dino_preprocess(images.to(DEV), 518)).float().cpu()
+    ref = dino_o.forward_features({k: v.float() for k, v in params.items()}, dict(patch=14, heads=12, layers=12),
+                                  dino_o.preprocess(images))
+    assert feats.shape == ref.shape == (2, 1370, 768)
+    err = (feats - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 4e-2, err
+    cos = torch.nn.functional.cosine_similarity(feats.flatten(), ref.flatten(), dim=0).item()
+    assert cos > 0.999, cos
+
+
+def test_pickscore_discriminator_step_matches_oracle_loss():
+    """train_pickscore (train_sd3_fast_pickscore.py:151-183): loss value vs the oracle criterion on oracle features,
+    and only vision_model.encoder.layers[tune_layer:] move."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.pick_score_training import CLIPCriterion, CLIPCriterionConfig
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer, images_to_pixel_values
+    from oracle import clip as clip_o
+    from oracle import clip_criterion as crit_o
+    from oracle import preprocess as pre_o
+    cfg = weights.CLIP_TINY
+    params = weights.init_clip(cfg, seed=3, device="cpu", dtype=torch.bfloat16)
+    scorer = PickScoreScorer(device=DEV, cfg=cfg, state_dict=params)
+    model = scorer.model
+    for p in model.parameters():
+        p.requires_grad = False
+    for p in model.vision_model.encoder.layers[-1:].parameters():
+        p.requires_grad = True
+    g = torch.Generator().manual_seed(2)
+    real = (torch.rand(3, 3, 64, 64, generator=g) * 255).to(torch.uint8)
+    fake = (torch.rand(3, 3, 64, 64, generator=g) * 255).to(torch.uint8)
+    prompts = ["a", "b c", "d e f"]
+    ids = scorer.processor.tokenizer(prompts, padding="max_length", max_length=77)["input_ids"]
+    batch = {"input_ids": ids.to(DEV), "pixels_0": images_to_pixel_values(real, DEV), "pixels_1": images_to_pixel_values(fake, DEV),
+             "label_0": torch.tensor(1.0, device=DEV), "label_1": torch.tensor(0.0, device=DEV),
+             "num_examples_per_prompt": torch.tensor(1.0, device=DEV)}
+    loss = CLIPCriterion(CLIPCriterionConfig())(model, batch)
+    # oracle
+    p32 = {k: v.float() for k, v in params.items()}
+    ocfg = dict(patch=cfg["patch"], v_layers=cfg["v_layers"], v_heads=cfg["v_heads"], t_layers=cfg["t_layers"], t_heads=cfg["t_heads"])
+    pix = lambda u: torch.from_numpy(pre_o.clip_pixel_values(pre_o.pil_bicubic_resize_u8(u.numpy(), 224)))
+    norm = lambda t: t / t.norm(dim=-1, keepdim=True)
+    ref = crit_o.clip_pair_loss(norm(clip_o.text_features(p32, ocfg, ids)), norm(clip_o.image_features(p32, ocfg, pix(real))),
+                                norm(clip_o.image_features(p32, ocfg, pix(fake))), p32["logit_scale"].exp(),
+                                torch.tensor(1.0), torch.tensor(0.0))
+    assert abs(loss.item() - ref.item()) < 5e-2 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.5, 0.999))
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    loss.backward()
+    opt.step()
+    moved = [n for n, p in model.named_parameters() if not torch.equal(p, before[n])]
+    assert moved and all(".encoder.layers.1." in n and n.startswith("vision_model") for n in moved), moved
+    # the fast path picks up the updated weights (packed operands are rebuilt on the version change)
+    s1 = scorer(prompts, real.to(DEV))
+    assert torch.isfinite(s1).all()

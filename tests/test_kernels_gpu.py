@@ -338,3 +338,19 @@ def test_vae_decoder_matches_oracle_at_true_widths():
     ref = vae_o.decode_latents_to_image(vp, z)
     assert got.shape == (2, 3, 64, 64)
     assert (got - ref).abs().max().item() < 2e-3
+
+
+def test_vae_fused_helpers(ops):
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(2, 128, 6, 10, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(2, 128, 6, 10, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(128, generator=g).to(DEV)
+    assert torch.allclose(ops.add_bias_nhwc(a, b, bias), a + b + bias[None, :, None, None], atol=1e-6)
+    assert torch.equal(ops.add_bias_nhwc(a, b), a + b)
+    up = ops.upsample_nearest2x_nhwc(a)
+    assert torch.equal(up, torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"))
+    assert up.is_contiguous(memory_format=torch.channels_last)
+    gamma, beta = torch.randn(128, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV)
+    got = ops.group_norm_silu_nhwc(a, gamma, beta, 32, 1e-6, True, in_bias=bias)
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(a + bias[None, :, None, None], 32, gamma, beta, eps=1e-6))
+    assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5)
