@@ -91,3 +91,48 @@ def test_pickscore_discriminator_step_matches_oracle_loss():
     # the fast path picks up the updated weights (packed operands are rebuilt on the version change)
     s1 = scorer(prompts, real.to(DEV))
     assert torch.isfinite(s1).all()
+
+
+def test_config1_rollout_sd35_medium_true_size_matches_oracle():
+    """BASELINE config 1 (SD3.5-medium, 256x256, 4 denoise steps, G=2, CFG 4.5, noise 0.8, SDE window 2) at the
+    TRUE model size: GPU rollout (bf16 kernels) vs the CPU oracle in the reference's dtype regime, same seeded
+    weights, same injected noise."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
+    from adv_grpo_b200.mmdit import SD3Transformer2DModel
+    from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
+    from adv_grpo_b200.vae import AutoencoderKL
+    from oracle import pipeline as pipe_o
+    from oracle.mmdit import MMDiTOracle
+    cfg = weights.SD35_MEDIUM
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    lora = weights.init_lora(cfg, rank=32, seed=1, perturb_b=0.01)
+    lora = {k: (a.bfloat16().float(), b.bfloat16().float()) for k, (a, b) in lora.items()}
+    vp = weights.init_vae_decoder(weights.VAE_SD3, seed=2, device="cpu")
+    pipe = StableDiffusion3Pipeline(SD3Transformer2DModel(cfg, params, lora=lora, device=DEV),
+                                    AutoencoderKL(vp, weights.VAE_SD3, device=DEV), device=DEV, use_cuda_graph=False)
+    G, steps, T_train = 2, 4, 2
+    g = torch.Generator().manual_seed(7)
+    pe = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    pp = torch.randn(1, 2048, generator=g).bfloat16()
+    ne = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    npool = torch.randn(1, 2048, generator=g).bfloat16()
+    lat = torch.randn(G, 16, 32, 32, generator=g).bfloat16()
+    noises = [torch.randn(G, 16, 32, 32, generator=g) for _ in range(steps)]
+    img, lats, lps, tss = pipeline_with_logprob_random(
+        pipe, prompt_embeds=pe.to(DEV), pooled_prompt_embeds=pp.to(DEV), negative_prompt_embeds=ne.to(DEV),
+        negative_pooled_prompt_embeds=npool.to(DEV), num_inference_steps=steps, guidance_scale=4.5, output_type="pt",
+        height=256, width=256, noise_level=0.8, mini_num_image_per_prompt=G, train_num_steps=T_train, process_index=0,
+        sample_num_steps=steps, random_timestep=0, latents=lat.to(DEV), noise=[n.to(DEV) for n in noises])
+    oracle = MMDiTOracle(params, dict(cfg, dual_layers=set(cfg["dual_layers"])), lora=lora, lora_scale=2.0)
+    with torch.no_grad():
+        _, lats_o, lps_o, _, _ = pipe_o.rollout(oracle, vp, pe.repeat(G, 1, 1), pp.repeat(G, 1), ne.repeat(G, 1, 1),
+                                                npool.repeat(G, 1), lat, steps, 4.5, 0.8, T_train, 0, noises, decode=False)
+    assert img.shape == (G, 3, 256, 256) and torch.isfinite(img).all()
+    for a, b in zip(lats, lats_o):
+        d = (a.float().cpu() - b.float()).abs()
+        # 24 bf16 blocks vs fp32: within 1e-2 of the latent range per element (north_star), far less on average
+        assert d.max().item() <= 1e-2 * b.float().abs().max().item() + 2 ** -6, (d.max().item(), b.float().abs().max().item())
+        assert d.mean().item() < 6e-3
+    for a, b in zip(lps, lps_o):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-6)
