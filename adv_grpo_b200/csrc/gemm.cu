@@ -36,16 +36,22 @@ struct GCfg {
   static constexpr int kThreads = 192;
 };
 
-struct GParams {
-  __nv_bfloat16* C;
+// Per-problem fields.  A launch runs one or TWO problems that share N, K, K2 and the epilogue type (the image
+// and the text stream of an MMDiT block use different weights on differently sized row sets): the persistent
+// tile loop simply continues from the tiles of problem 0 into those of problem 1, so the short text problem
+// fills the tail wave of the image problem instead of paying its own launch + wave quantisation.
+struct GProb {
   __nv_bfloat16* preact;   // optional: bf16 pre-activation (acc + bias) for the GELU backward
   const __nv_bfloat16* bias;
-  const __nv_bfloat16* residual;
   const __nv_bfloat16* gate;
-  int64_t ldc, ldr, gate_stride, rows_per_gate;
-  int M, N, kb1, kb2;   // k blocks of the main and of the second product
+  int64_t ldc, gate_stride, rows_per_gate;
+  int M, tiles_m;
+};
+struct GParams {
+  GProb a, b;              // problem 0, problem 1 (b.M == 0 when absent)
+  int N, kb1, kb2;         // k blocks of the main and of the second product
   int epilogue;
-  int tiles_m, tiles_n;
+  int tiles_n, tiles0, num_tiles;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -60,6 +66,9 @@ __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
             const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
+            const __grid_constant__ CUtensorMap tn_a, const __grid_constant__ CUtensorMap tn_w,
+            const __grid_constant__ CUtensorMap tn_a2, const __grid_constant__ CUtensorMap tn_w2,
+            const __grid_constant__ CUtensorMap tn_c, const __grid_constant__ CUtensorMap tn_r,
             const GParams p) {
   using G = GCfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.num_tiles;
   const int kb_total = p.kb1 + p.kb2;
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;          // 0 = leader CTA of the pair
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -116,15 +125,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       prefetch_tmap(&tm_w);
       int it = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
-        const int n0 = (tile % p.tiles_n) * BN + (TWO ? (int)rank * (BN / 2) : 0);
+        const bool second = tile >= p.tiles0;
+        const int t = second ? tile - p.tiles0 : tile;
+        const int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM;
+        const int n0 = (t % p.tiles_n) * BN + (TWO ? (int)rank * (BN / 2) : 0);
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int st = it % G::kStages;
           mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
           uint8_t* sa = smem + st * G::kStageBytes;
           uint8_t* sb = sa + G::kABytes;
-          const CUtensorMap* ma = kb < p.kb1 ? &tm_a : &tm_a2;
-          const CUtensorMap* mw = kb < p.kb1 ? &tm_w : &tm_w2;
+          const CUtensorMap* ma = kb < p.kb1 ? (second ? &tn_a : &tm_a) : (second ? &tn_a2 : &tm_a2);
+          const CUtensorMap* mw = kb < p.kb1 ? (second ? &tn_w : &tm_w) : (second ? &tn_w2 : &tm_w2);
           const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BK;
           if constexpr (TWO) {
             // both CTAs' bytes land on the LEADER's full barrier (one expect_tx of the pair's total)
@@ -184,19 +195,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     int local = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
       const int acc = local & 1;
-      const int m0 = (tile / p.tiles_n) * kTileM + (int)rank * BM;
-      const int n0 = (tile % p.tiles_n) * BN;
+      const bool second = tile >= p.tiles0;
+      const int t = second ? tile - p.tiles0 : tile;
+      const int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM;
+      const int n0 = (t % p.tiles_n) * BN;
       const int row = m0 + lrow;
-      const bool row_ok = row < p.M;
+      const int prob_M = second ? p.b.M : p.a.M;
+      const bool row_ok = row < prob_M;
+      const __nv_bfloat16* p_bias = second ? p.b.bias : p.a.bias;
+      const __nv_bfloat16* p_gate = second ? p.b.gate : p.a.gate;
+      __nv_bfloat16* p_preact = second ? p.b.preact : p.a.preact;
+      const int64_t p_ldc = second ? p.b.ldc : p.a.ldc;
+      const int64_t p_gate_stride = second ? p.b.gate_stride : p.a.gate_stride;
+      const int64_t p_rows_per_gate = second ? p.b.rows_per_gate : p.a.rows_per_gate;
+      const CUtensorMap* m_c = second ? &tn_c : &tm_c;
+      const CUtensorMap* m_r = second ? &tn_r : &tm_r;
       mbar_wait(&bar_acc_full[acc], (local >> 1) & 1);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * BN + lane_addr;
       const __nv_bfloat16* grow =
-          (p.gate && row_ok) ? p.gate + (int64_t)(row / p.rows_per_gate) * p.gate_stride + n0 : nullptr;
+          (p_gate && row_ok) ? p_gate + (int64_t)(row / p_rows_per_gate) * p_gate_stride + n0 : nullptr;
       if (has_res && tid == 0) {
         tma_store_wait_read<0>();
         mbar_expect_tx(&bar_res[0], BM * 128);
-        tma_load_2d(stage, &tm_r, &bar_res[0], n0, m0);
+        tma_load_2d(stage, m_r, &bar_res[0], n0, m0);
       }
 #pragma unroll 1
       for (int g = 0; g < NG; ++g) {
@@ -207,7 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             if (g + 1 < NG && n0 + (g + 1) * 64 < p.N) {
               tma_store_wait_read<0>();              // staging tile buf^1 (store g-1) has been read out
               mbar_expect_tx(&bar_res[buf ^ 1], BM * 128);
-              tma_load_2d(stage + (buf ^ 1) * (BM * 128), &tm_r, &bar_res[buf ^ 1], n0 + (g + 1) * 64, m0);
+              tma_load_2d(stage + (buf ^ 1) * (BM * 128), m_r, &bar_res[buf ^ 1], n0 + (g + 1) * 64, m0);
             }
           } else {
             tma_store_wait_read<1>();                // store g-2 (same staging tile) has been read out
@@ -234,9 +256,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i + j]);
             if (col < p.N) {
-              if (p.bias) {
+              if (p_bias) {
                 float bb[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.bias + col), bb);
+                unpack8(*reinterpret_cast<const bf16x8*>(p_bias + col), bb);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += bb[j];
               }
@@ -244,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 // the activation is applied to the bf16-rounded pre-activation so that the fused
                 // forward is bit-identical to "store z in bf16, then GELU(z)" (training replay)
                 const bf16x8 z = pack8(f);
-                if (p.preact && row_ok) *reinterpret_cast<bf16x8*>(p.preact + (int64_t)row * p.ldc + col) = z;
+                if (p_preact && row_ok) *reinterpret_cast<bf16x8*>(p_preact + (int64_t)row * p_ldc + col) = z;
                 unpack8(z, f);
                 if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
 #pragma unroll
@@ -272,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (tid == 0) {
-          tma_store_2d(&tm_c, sbuf, n0 + g * 64, m0);
+          tma_store_2d(m_c, sbuf, n0 + g * 64, m0);
           tma_store_commit();
         }
       }
@@ -288,10 +310,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   }
 }
 
+struct Maps {
+  CUtensorMap a, w, a2, w2, c, r;
+};
+
 template <int BN, bool TWO>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ta2,
-                const CUtensorMap& tw2, const CUtensorMap& tc, const CUtensorMap& tr, GParams& p,
-                cudaStream_t st) {
+int launch_gemm(const Maps& m0, const Maps& m1, GParams& p, cudaStream_t st) {
   using G = GCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -299,11 +323,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     attr_set = true;
   }
   constexpr int kTileM = TWO ? 2 * BM : BM;
-  p.tiles_m = (p.M + kTileM - 1) / kTileM;
+  p.a.tiles_m = (p.a.M + kTileM - 1) / kTileM;
+  p.b.tiles_m = (p.b.M + kTileM - 1) / kTileM;
   p.tiles_n = (p.N + BN - 1) / BN;
-  int tiles = p.tiles_m * p.tiles_n;
+  p.tiles0 = p.a.tiles_m * p.tiles_n;
+  p.num_tiles = p.tiles0 + p.b.tiles_m * p.tiles_n;
   int workers = TWO ? sm_count() / 2 : sm_count();
-  if (workers > tiles) workers = tiles;
+  if (workers > p.num_tiles) workers = p.num_tiles;
   if constexpr (TWO) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * workers);
@@ -317,15 +343,154 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO>, ta, tw, ta2, tw2, tc, tr, p));
+    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO>, m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
+                                         m1.a2, m1.w2, m1.c, m1.r, p));
   } else {
-    gemm_kernel<BN, TWO><<<workers, G::kThreads, G::kSmemBytes, st>>>(ta, tw, ta2, tw2, tc, tr, p);
+    gemm_kernel<BN, TWO><<<workers, G::kThreads, G::kSmemBytes, st>>>(m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
+                                                                      m1.a2, m1.w2, m1.c, m1.r, p);
   }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
 
-int g_gemm_variant = 0;   // 0 = auto, 1 = single-CTA tiles only, 2 = CTA pairs whenever the shape allows
+int g_gemm_variant = 0;   // 0 = auto, 1 = single-CTA tiles only, 3 = CTA pairs whenever the shape allows
+
+// One problem of a (possibly dual) launch, as the C ABI passes it.
+struct ProbArgs {
+  const void *A, *W, *A2, *W2, *bias, *residual, *gate;
+  void *C, *preact;
+  int64_t lda, ldw, lda2, ldw2, ldc, ldr, gate_stride, rows_per_gate, M;
+};
+
+int check_prob(const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int epilogue) {
+  ADVGRPO_CHECK_ARG(q.A && q.W && q.C, "gemm_bf16: null pointer");
+  ADVGRPO_CHECK_ARG(q.M >= 1, "gemm_bf16: M must be >= 1 (got %lld)", (long long)q.M);
+  ADVGRPO_CHECK_ARG(q.lda % 8 == 0 && q.ldw % 8 == 0 && q.ldc % 8 == 0, "gemm_bf16: leading dimensions must be multiples of 8");
+  ADVGRPO_CHECK_ARG(aligned16(q.A) && aligned16(q.W) && aligned16(q.C) && (!q.bias || aligned16(q.bias)) &&
+                        (!q.preact || aligned16(q.preact)),
+                    "gemm_bf16: 16-byte alignment");
+  if (K2 > 0) {
+    ADVGRPO_CHECK_ARG(q.A2 && q.W2 && q.lda2 % 8 == 0 && q.ldw2 % 8 == 0 && aligned16(q.A2) && aligned16(q.W2),
+                      "gemm_bf16: second product needs A2, W2, aligned operands");
+  }
+  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+    ADVGRPO_CHECK_ARG(q.residual && q.gate && q.rows_per_gate >= 1 && q.ldr % 8 == 0 && q.gate_stride % 8 == 0 &&
+                          aligned16(q.residual) && aligned16(q.gate),
+                      "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
+  }
+  (void)N; (void)K;
+  return ADVGRPO_OK;
+}
+
+int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int BN, bool two, int epilogue) {
+  const uint64_t da[2] = {(uint64_t)K, (uint64_t)q.M};
+  const uint64_t sa[2] = {0, (uint64_t)q.lda * 2};
+  const uint32_t ba[2] = {BK, BM};
+  int rc = make_tmap_bf16(&m.a, q.A, 2, da, sa, ba, true);
+  if (rc) return rc;
+  const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t sw[2] = {0, (uint64_t)q.ldw * 2};
+  const uint32_t bw[2] = {BK, (uint32_t)(two ? BN / 2 : BN)};
+  rc = make_tmap_bf16(&m.w, q.W, 2, dw, sw, bw, true);
+  if (rc) return rc;
+  if (K2 > 0) {
+    const uint64_t da2[2] = {(uint64_t)K2, (uint64_t)q.M};
+    const uint64_t sa2[2] = {0, (uint64_t)q.lda2 * 2};
+    rc = make_tmap_bf16(&m.a2, q.A2, 2, da2, sa2, ba, true);
+    if (rc) return rc;
+    const uint64_t dw2[2] = {(uint64_t)K2, (uint64_t)N};
+    const uint64_t sw2[2] = {0, (uint64_t)q.ldw2 * 2};
+    rc = make_tmap_bf16(&m.w2, q.W2, 2, dw2, sw2, bw, true);
+    if (rc) return rc;
+  } else {
+    m.a2 = m.a;
+    m.w2 = m.w;
+  }
+  const uint64_t dc[2] = {(uint64_t)N, (uint64_t)q.M};
+  const uint64_t sc[2] = {0, (uint64_t)q.ldc * 2};
+  const uint32_t bc[2] = {64, BM};
+  rc = make_tmap_bf16(&m.c, q.C, 2, dc, sc, bc, true);
+  if (rc) return rc;
+  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+    const uint64_t sr[2] = {0, (uint64_t)q.ldr * 2};
+    rc = make_tmap_bf16(&m.r, q.residual, 2, dc, sr, bc, true);
+    if (rc) return rc;
+  } else {
+    m.r = m.c;
+  }
+  return ADVGRPO_OK;
+}
+
+void fill_prob(GProb& g, const ProbArgs& q) {
+  g.preact = (__nv_bfloat16*)q.preact;
+  g.bias = (const __nv_bfloat16*)q.bias;
+  g.gate = (const __nv_bfloat16*)q.gate;
+  g.ldc = q.ldc;
+  g.gate_stride = q.gate_stride;
+  g.rows_per_gate = q.rows_per_gate > 0 ? q.rows_per_gate : 1;
+  g.M = (int)q.M;
+  g.tiles_m = 0;
+}
+
+// nprob = 1 or 2 problems sharing N, K, K2 and the epilogue type
+int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2, int epilogue, cudaStream_t st) {
+  ADVGRPO_CHECK_ARG(N >= 8 && K >= 64, "gemm_bf16: bad sizes N=%lld K=%lld", (long long)N, (long long)K);
+  ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && K2 % 64 == 0,
+                    "gemm_bf16: K and K2 must be multiples of 64 and N of 8 (K=%lld K2=%lld N=%lld)", (long long)K,
+                    (long long)K2, (long long)N);
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_bf16: unknown epilogue %d", epilogue);
+  for (int i = 0; i < nprob; ++i) {
+    int rc = check_prob(probs[i], N, K, K2, epilogue);
+    if (rc) return rc;
+  }
+  // Tile shape: minimise (waves of the persistent schedule) x (tile area / measured relative tile efficiency).
+  // CTA pairs with 256x256 tiles are the most efficient per FLOP (profiles/: 1.37 vs 1.20 PFLOP/s for
+  // single-CTA 128x256 tiles at M = 16384), but small-M problems (the 205-token text stream) lose whole
+  // waves to quantisation and prefer finer tiles.
+  struct Cand { int bn; bool pair; double eff; };
+  const Cand cands[4] = {{256, true, 1.00}, {256, false, 0.87}, {192, true, 0.80}, {128, false, 0.70}};
+  int64_t min_m = probs[0].M;
+  for (int i = 1; i < nprob; ++i) min_m = probs[i].M < min_m ? probs[i].M : min_m;
+  int BN = 128;
+  bool pair_ok = false;
+  {
+    double best = -1;
+    for (int ci = 0; ci < 4; ++ci) {
+      const Cand& c = cands[ci];
+      if (c.pair && (g_gemm_variant == 1 || min_m < 256)) continue;
+      if (!c.pair && g_gemm_variant == 3 && min_m >= 256 && N >= 256) continue;   // test hook: force pairs
+      if (c.bn > 128 && N < c.bn) continue;
+      if (c.bn == 192 && N % 192 != 0) continue;
+      const int64_t workers = c.pair ? sm_count() / 2 : sm_count();
+      const int64_t tile_m = c.pair ? 256 : 128;
+      int64_t tiles = 0;
+      for (int i = 0; i < nprob; ++i) tiles += ((probs[i].M + tile_m - 1) / tile_m) * ((N + c.bn - 1) / c.bn);
+      // a pair tile (256 rows) is worked on by two SMs: per-SM time ~ 128 * bn in both cases
+      const double cost = (double)((tiles + workers - 1) / workers) * (double)(128 * c.bn) / c.eff;
+      if (best < 0 || cost < best) { best = cost; BN = c.bn; pair_ok = c.pair; }
+    }
+  }
+  Maps m0, m1;
+  int rc = make_maps(m0, probs[0], N, K, K2, BN, pair_ok, epilogue);
+  if (rc) return rc;
+  if (nprob == 2) {
+    rc = make_maps(m1, probs[1], N, K, K2, BN, pair_ok, epilogue);
+    if (rc) return rc;
+  } else {
+    m1 = m0;
+  }
+  GParams p;
+  fill_prob(p.a, probs[0]);
+  if (nprob == 2) fill_prob(p.b, probs[1]);
+  else { fill_prob(p.b, probs[0]); p.b.M = 0; }
+  p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = (int)(K2 / BK);
+  p.epilogue = epilogue;
+  if (pair_ok && BN == 256) return launch_gemm<256, true>(m0, m1, p, st);
+  if (pair_ok && BN == 192) return launch_gemm<192, true>(m0, m1, p, st);
+  if (BN == 256) return launch_gemm<256, false>(m0, m1, p, st);
+  if (BN == 192) return launch_gemm<192, false>(m0, m1, p, st);
+  return launch_gemm<128, false>(m0, m1, p, st);
+}
 
 }  // namespace
 }  // namespace advgrpo
@@ -339,100 +504,27 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
                       const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
                       int64_t rows_per_gate, void* preact_out, advgrpo_stream_t stream) {
-  ADVGRPO_CHECK_ARG(A && W && C, "gemm_bf16: null pointer");
-  ADVGRPO_CHECK_ARG(!preact_out || aligned16(preact_out), "gemm_bf16: preact_out alignment");
-  ADVGRPO_CHECK_ARG(M >= 1 && N >= 8 && K >= 64, "gemm_bf16: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
-  ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0, "gemm_bf16: K must be a multiple of 64 and N of 8 (K=%lld N=%lld)", (long long)K, (long long)N);
-  ADVGRPO_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_bf16: leading dimensions must be multiples of 8");
-  ADVGRPO_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(C) && (!bias || aligned16(bias)), "gemm_bf16: 16-byte alignment");
-  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_bf16: unknown epilogue %d", epilogue);
-  const bool has2 = A2 != nullptr;
-  if (has2) {
-    ADVGRPO_CHECK_ARG(W2 && K2 >= 64 && K2 % 64 == 0 && lda2 % 8 == 0 && ldw2 % 8 == 0 && aligned16(A2) && aligned16(W2),
-                      "gemm_bf16: second product needs W2, K2 %% 64 == 0, aligned operands");
+  ProbArgs q = {A, W, A2, W2, bias, residual, gate, C, preact_out, lda, ldw, lda2, ldw2, ldc, ldr, gate_stride,
+                rows_per_gate, M};
+  return gemm_run(&q, 1, N, K, A2 ? K2 : 0, epilogue, (cudaStream_t)stream);
+}
+
+int advgrpo_gemm_bf16_dual(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                           const void* const* A2, const int64_t* lda2, const void* const* W2, const int64_t* ldw2,
+                           int64_t K2, const void* const* bias, void* const* C, const int64_t* ldc, const int64_t* M,
+                           int64_t N, int64_t K, int epilogue, const void* const* residual, const int64_t* ldr,
+                           const void* const* gate, const int64_t* gate_stride, const int64_t* rows_per_gate,
+                           void* const* preact_out, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(A && W && C && M && lda && ldw && ldc, "gemm_bf16_dual: null argument array");
+  ProbArgs q[2];
+  for (int i = 0; i < 2; ++i) {
+    q[i] = {A[i], W[i], A2 ? A2[i] : nullptr, W2 ? W2[i] : nullptr, bias ? bias[i] : nullptr,
+            residual ? residual[i] : nullptr, gate ? gate[i] : nullptr, C[i], preact_out ? preact_out[i] : nullptr,
+            lda[i], ldw[i], lda2 ? lda2[i] : 0, ldw2 ? ldw2[i] : 0, ldc[i], ldr ? ldr[i] : 0,
+            gate_stride ? gate_stride[i] : 0, rows_per_gate ? rows_per_gate[i] : 1, M[i]};
   }
-  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
-    ADVGRPO_CHECK_ARG(residual && gate && rows_per_gate >= 1 && ldr % 8 == 0 && gate_stride % 8 == 0 &&
-                          aligned16(residual) && aligned16(gate),
-                      "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
-  }
-  CUtensorMap ta, tw, ta2, tw2, tc, tr;
-  // Tile shape: minimise (waves of the persistent schedule) x (tile area / measured relative tile efficiency).
-  // CTA pairs with 256x256 tiles are the most efficient per FLOP (profiles/: 1.37 vs 1.20 PFLOP/s for
-  // single-CTA 128x256 tiles at M = 16384), but small-M problems (the 205-token text stream) lose whole
-  // waves to quantisation and prefer finer tiles.
-  struct Cand { int bn; bool pair; double eff; };
-  const Cand cands[4] = {{256, true, 1.00}, {256, false, 0.87}, {192, true, 0.80}, {128, false, 0.70}};
-  int BN = 128;
-  bool pair_ok = false;
-  {
-    double best = -1;
-    for (int ci = 0; ci < 4; ++ci) {
-      const Cand& c = cands[ci];
-      if (c.pair && (g_gemm_variant == 1 || M < 256)) continue;
-      if (!c.pair && g_gemm_variant == 3 && M >= 256 && N >= 256) continue;   // test hook: force pairs
-      if (c.bn > 128 && N < c.bn) continue;
-      if (c.bn == 192 && N % 192 != 0) continue;
-      const int64_t workers = c.pair ? sm_count() / 2 : sm_count();
-      const int64_t tile_m = c.pair ? 256 : 128;
-      const int64_t tiles = ((M + tile_m - 1) / tile_m) * ((N + c.bn - 1) / c.bn);
-      // a pair tile (256 rows) is worked on by two SMs: per-SM time ~ 128 * bn in both cases
-      const double cost = (double)((tiles + workers - 1) / workers) * (double)(128 * c.bn) / c.eff;
-      if (best < 0 || cost < best) { best = cost; BN = c.bn; pair_ok = c.pair; }
-    }
-  }
-  {
-    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t sa[2] = {0, (uint64_t)lda * 2};
-    const uint32_t ba[2] = {BK, BM};
-    int rc = make_tmap_bf16(&ta, A, 2, da, sa, ba, true);
-    if (rc) return rc;
-    const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
-    const uint64_t sw[2] = {0, (uint64_t)ldw * 2};
-    const bool two = pair_ok;
-    const uint32_t bw[2] = {BK, (uint32_t)(two ? BN / 2 : BN)};
-    rc = make_tmap_bf16(&tw, W, 2, dw, sw, bw, true);
-    if (rc) return rc;
-    if (has2) {
-      const uint64_t da2[2] = {(uint64_t)K2, (uint64_t)M};
-      const uint64_t sa2[2] = {0, (uint64_t)lda2 * 2};
-      rc = make_tmap_bf16(&ta2, A2, 2, da2, sa2, ba, true);
-      if (rc) return rc;
-      const uint64_t dw2[2] = {(uint64_t)K2, (uint64_t)N};
-      const uint64_t sw2[2] = {0, (uint64_t)ldw2 * 2};
-      rc = make_tmap_bf16(&tw2, W2, 2, dw2, sw2, bw, true);
-      if (rc) return rc;
-    } else {
-      ta2 = ta;
-      tw2 = tw;
-    }
-    const uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
-    const uint64_t sc[2] = {0, (uint64_t)ldc * 2};
-    const uint32_t bc[2] = {64, BM};
-    rc = make_tmap_bf16(&tc, C, 2, dc, sc, bc, true);
-    if (rc) return rc;
-    if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
-      const uint64_t sr[2] = {0, (uint64_t)ldr * 2};
-      rc = make_tmap_bf16(&tr, residual, 2, dc, sr, bc, true);
-      if (rc) return rc;
-    } else {
-      tr = tc;
-    }
-  }
-  GParams p;
-  p.C = (__nv_bfloat16*)C;
-  p.preact = (__nv_bfloat16*)preact_out;
-  p.bias = (const __nv_bfloat16*)bias;
-  p.residual = (const __nv_bfloat16*)residual;
-  p.gate = (const __nv_bfloat16*)gate;
-  p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
-  p.M = (int)M; p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = has2 ? (int)(K2 / BK) : 0;
-  p.epilogue = epilogue;
-  if (pair_ok && BN == 256) return launch_gemm<256, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
-  if (pair_ok && BN == 192) return launch_gemm<192, true>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
-  if (BN == 256) return launch_gemm<256, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
-  if (BN == 192) return launch_gemm<192, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
-  return launch_gemm<128, false>(ta, tw, ta2, tw2, tc, tr, p, (cudaStream_t)stream);
+  const bool has2 = A2 && A2[0];
+  return gemm_run(q, 2, N, K, has2 ? K2 : 0, epilogue, (cudaStream_t)stream);
 }
 
 // Test/bench hook (not part of the reference-facing surface): force the GEMM CTA shape.

@@ -111,6 +111,81 @@ class _LinearFn(torch.autograd.Function):
         return dx, None, None, None, da, dw2, None, d_res, None, None
 
 
+class _DualLinearFn(torch.autograd.Function):
+    """The image-stream and text-stream versions of one projection (different weights, same N / K / epilogue) as
+    ONE persistent dual-problem GEMM launch, forward and backward.  Argument layout: the two problems' tensors
+    interleaved (x0, x1, w0, w1, wt0, wt1, b0, b1, a0, a1, w2_0, w2_1, epilogue, r0, r1, g0, g1, rows0, rows1)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, w0, w1, wt0, wt1, b0, b1, la0, la1, lw0, lw1, epilogue, r0, r1, g0, g1, rows0, rows1):
+        has_lora = la0 is not None
+        t0 = t1 = None
+        if has_lora:
+            t0, t1 = ops.gemm_dual((x0, x1), (la0, la1))
+        pre = (None, None)
+        if epilogue in (ops.EPI_GELU_TANH, ops.EPI_GELU_ERF) and any(ctx.needs_input_grad):
+            pre = tuple(torch.empty((x.numel() // x.shape[-1], w0.shape[0]), dtype=torch.bfloat16, device=x.device)
+                        for x in (x0, x1))
+        y0, y1 = ops.gemm_dual((x0, x1), (w0, w1), bias=(b0, b1), a2=(t0, t1), w2=(lw0, lw1), epilogue=epilogue,
+                               residual=(r0, r1), gate=(g0, g1), rows_per_gate=(rows0, rows1), preact_out=pre)
+        ctx.save_for_backward(x0, x1, t0, t1, la0, la1, lw0, lw1, g0, g1, pre[0], pre[1])
+        ctx.meta = (wt0, wt1, epilogue, rows0, rows1)
+        return y0, y1
+
+    @staticmethod
+    def backward(ctx, dy0, dy1):
+        x0, x1, t0, t1, la0, la1, lw0, lw1, g0, g1, pre0, pre1 = ctx.saved_tensors
+        wt0, wt1, epilogue, rows0, rows1 = ctx.meta
+        xs, ts, las, lws, gs, pres, rows = (x0, x1), (t0, t1), (la0, la1), (lw0, lw1), (g0, g1), (pre0, pre1), (rows0, rows1)
+        dys, d_res, dy2 = [dy0.contiguous(), dy1.contiguous()], [None, None], [None, None]
+        for i in range(2):
+            N = dys[i].shape[-1]
+            d = dys[i].reshape(-1, N)
+            if epilogue == ops.EPI_GATE_RESIDUAL:
+                d_res[i] = dys[i]
+                d = (d.reshape(gs[i].shape[0], rows[i], N) * gs[i].reshape(gs[i].shape[0], 1, N)).reshape(-1, N)
+            elif epilogue == ops.EPI_GELU_TANH:
+                d = torch.ops.aten.gelu_backward(d, pres[i], approximate="tanh")
+            elif epilogue == ops.EPI_GELU_ERF:
+                d = torch.ops.aten.gelu_backward(d, pres[i], approximate="none")
+            dy2[i] = d
+        das, dws, dts = [None, None], [None, None], (None, None)
+        has_lora = la0 is not None
+        if has_lora:
+            dts = ops.gemm_dual(tuple(dy2), (lw0.t().contiguous(), lw1.t().contiguous()))
+            for i in range(2):
+                x2 = xs[i].reshape(-1, xs[i].shape[-1])
+                if ctx.needs_input_grad[8 + i]:
+                    das[i] = dts[i].t() @ x2
+                if ctx.needs_input_grad[10 + i]:
+                    dws[i] = dy2[i].t() @ ts[i].reshape(-1, ts[i].shape[-1])
+        dx0 = dx1 = None
+        need0, need1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need0 and need1:
+            if has_lora:
+                dx0, dx1 = ops.gemm_dual(tuple(dy2), (wt0(), wt1()), a2=dts, w2=(la0.t().contiguous(), la1.t().contiguous()))
+            else:
+                dx0, dx1 = ops.gemm_dual(tuple(dy2), (wt0(), wt1()))
+            dx0 = dx0.reshape(*dys[0].shape[:-1], dx0.shape[-1])
+            dx1 = dx1.reshape(*dys[1].shape[:-1], dx1.shape[-1])
+        else:
+            for i, need in enumerate((need0, need1)):
+                if not need:
+                    continue
+                wt = (wt0, wt1)[i]()
+                if has_lora:
+                    dx = ops.gemm(dy2[i], wt, a2=dts[i], w2=las[i].t().contiguous())
+                else:
+                    dx = ops.gemm(dy2[i], wt)
+                dx = dx.reshape(*dys[i].shape[:-1], wt.shape[0])
+                if i == 0:
+                    dx0 = dx
+                else:
+                    dx1 = dx
+        return (dx0, dx1, None, None, None, None, None, None, das[0], das[1], dws[0], dws[1], None, d_res[0], d_res[1],
+                None, None, None, None)
+
+
 class _WT:
     """Lazily materialised transposed copy of a frozen weight (only layers that back-propagate
     to their input ever build one)."""
@@ -200,6 +275,7 @@ class SD3Transformer2DModel(torch.nn.Module):
                     self.lora_A[key] = torch.nn.Parameter(a.to(self.device_, torch.float32))
                     self.lora_B[key] = torch.nn.Parameter(bb.to(self.device_, torch.float32))
                     self._lora_names.append(name)
+        self.dual_gemm = True            # image + text projections of a block as one dual-problem GEMM launch
         self._lora_cache = None
         self._lora_dirty = False
         self._lora_enabled = True
@@ -292,6 +368,16 @@ class SD3Transformer2DModel(torch.nn.Module):
         return _LinearFn.apply(x, blk["w_" + key], blk["wt_" + key], blk["b_" + key], a, w2, epilogue, residual,
                                gate, rows)
 
+    def _lin2(self, x, c, blk, key, ckey, lora_pack=None, epilogue=ops.EPI_NONE, res=(None, None), gate=(None, None),
+              rows=(1, 1)):
+        """Image-stream and text-stream projection `key` / `ckey` of one block in a single dual-problem launch."""
+        a0 = w20 = a1 = w21 = None
+        if lora_pack is not None and key in lora_pack and ckey in lora_pack:
+            (a0, w20), (a1, w21) = lora_pack[key], lora_pack[ckey]
+        return _DualLinearFn.apply(x, c, blk["w_" + key], blk["w_" + ckey], blk["wt_" + key], blk["wt_" + ckey],
+                                   blk["b_" + key], blk["b_" + ckey], a0, a1, w20, w21, epilogue, res[0], res[1],
+                                   gate[0], gate[1], rows[0], rows[1])
+
     def _attention(self, joint, split):
         if torch.is_grad_enabled() and joint.requires_grad:
             if split:
@@ -321,25 +407,39 @@ class SD3Transformer2DModel(torch.nn.Module):
             c1 = ops.ln_modulate(c, ch(ec, 1), ch(ec, 0))           # AdaLayerNormContinuous: (scale, shift)
         else:
             c1 = ops.ln_modulate(c, ch(ec, 0), ch(ec, 1))
-        qkv_x = self._lin(x1, blk, "qkv", pk)
-        qkv_c = self._lin(c1, blk, "cqkv", pk)
+        if self.dual_gemm:
+            qkv_x, qkv_c = self._lin2(x1, c1, blk, "qkv", "cqkv", pk)
+        else:
+            qkv_x = self._lin(x1, blk, "qkv", pk)
+            qkv_c = self._lin(c1, blk, "cqkv", pk)
         joint = ops.qk_norm_concat(qkv_x, qkv_c, blk.get("nq"), blk.get("nk"), blk.get("ncq"), blk.get("nck"), H, D)
         ox, oc = self._attention(joint, N)
-        x = self._lin(ox, blk, "out", pk, ops.EPI_GATE_RESIDUAL, x, ch(ex, 2), N)
+        fused_out = self.dual_gemm and not blk["last"]
+        if fused_out:
+            x, c = self._lin2(ox, oc, blk, "out", "cout", pk, ops.EPI_GATE_RESIDUAL, (x, c), (ch(ex, 2), ch(ec, 2)), (N, Nc))
+        else:
+            x = self._lin(ox, blk, "out", pk, ops.EPI_GATE_RESIDUAL, x, ch(ex, 2), N)
         if blk["dual"]:
             qkv2 = self._lin(x2, blk, "qkv2")
             j2 = ops.qk_norm_concat(qkv2, None, blk.get("nq2"), blk.get("nk2"), None, None, H, D)
             o2, _ = self._attention(j2, 0)
             x = self._lin(o2, blk, "out2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 8), N)
         xm = ops.ln_modulate(x, ch(ex, 3), ch(ex, 4))
-        hmid = self._lin(xm, blk, "ff1", None, ops.EPI_GELU_TANH)
-        x = self._lin(hmid, blk, "ff2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 5), N)
         if blk["last"]:
+            hmid = self._lin(xm, blk, "ff1", None, ops.EPI_GELU_TANH)
+            x = self._lin(hmid, blk, "ff2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 5), N)
             return x, None
-        c = self._lin(oc, blk, "cout", pk, ops.EPI_GATE_RESIDUAL, c, ch(ec, 2), Nc)
+        if not fused_out:
+            c = self._lin(oc, blk, "cout", pk, ops.EPI_GATE_RESIDUAL, c, ch(ec, 2), Nc)
         cm = ops.ln_modulate(c, ch(ec, 3), ch(ec, 4))
-        hmid = self._lin(cm, blk, "cff1", None, ops.EPI_GELU_TANH)
-        c = self._lin(hmid, blk, "cff2", None, ops.EPI_GATE_RESIDUAL, c, ch(ec, 5), Nc)
+        if self.dual_gemm:
+            hx, hc = self._lin2(xm, cm, blk, "ff1", "cff1", None, ops.EPI_GELU_TANH)
+            x, c = self._lin2(hx, hc, blk, "ff2", "cff2", None, ops.EPI_GATE_RESIDUAL, (x, c), (ch(ex, 5), ch(ec, 5)), (N, Nc))
+        else:
+            hmid = self._lin(xm, blk, "ff1", None, ops.EPI_GELU_TANH)
+            x = self._lin(hmid, blk, "ff2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 5), N)
+            hmid = self._lin(cm, blk, "cff1", None, ops.EPI_GELU_TANH)
+            c = self._lin(hmid, blk, "cff2", None, ops.EPI_GATE_RESIDUAL, c, ch(ec, 5), Nc)
         return x, c
 
     # ------------------------------------------------------------------ forward

@@ -380,6 +380,46 @@ def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, ga
     return c2d.reshape(*lead, N)
 
 
+def _arr_p(vals):
+    import ctypes
+    return (ctypes.c_void_p * 2)(*[None if v is None else v for v in vals])
+
+
+def _arr_i(vals):
+    import ctypes
+    return (ctypes.c_int64 * 2)(*[int(v) for v in vals])
+
+
+def gemm_dual(a, w, bias=(None, None), a2=(None, None), w2=(None, None), epilogue=EPI_NONE, residual=(None, None),
+              gate=(None, None), rows_per_gate=(1, 1), preact_out=(None, None)):
+    """Two problems (same N, K, K2, epilogue; different operands / row counts) in one persistent launch.
+    Every argument is a pair; returns the pair of outputs."""
+    _need_cuda(a[0], a[1], w[0], w[1])
+    a2d, lead, cs = [], [], []
+    for i in range(2):
+        lead.append(a[i].shape[:-1])
+        t = a[i].reshape(-1, a[i].shape[-1])
+        a2d.append(t if t.stride(-1) == 1 else t.contiguous())
+    K, N = a2d[0].shape[1], w[0].shape[0]
+    assert a2d[1].shape[1] == K and w[1].shape[0] == N and w[0].shape[1] == K and w[1].shape[1] == K
+    w = [x if x.stride(-1) == 1 else x.contiguous() for x in w]
+    M = [t.shape[0] for t in a2d]
+    for i in range(2):
+        cs.append(torch.empty((M[i], N), dtype=torch.bfloat16, device=a2d[i].device))
+    has2 = a2[0] is not None
+    a2r = [None if x is None else x.reshape(M[i], -1) for i, x in enumerate(a2)]
+    K2 = a2r[0].shape[1] if has2 else 0
+    r2d = [None if x is None else x.reshape(M[i], N) for i, x in enumerate(residual)]
+    st = lambda xs: [0 if x is None else x.stride(0) for x in xs]
+    _lib.call("advgrpo_gemm_bf16_dual", _arr_p([_ptr(t) for t in a2d]), _arr_i(st(a2d)), _arr_p([_ptr(t) for t in w]),
+              _arr_i(st(w)), _arr_p([_ptr(t) for t in a2r]), _arr_i(st(a2r)), _arr_p([_ptr(t) for t in w2]),
+              _arr_i(st(w2)), K2, _arr_p([_ptr(t) for t in bias]), _arr_p([_ptr(t) for t in cs]), _arr_i(st(cs)),
+              _arr_i(M), N, K, int(epilogue), _arr_p([_ptr(t) for t in r2d]), _arr_i(st(r2d)),
+              _arr_p([_ptr(t) for t in gate]), _arr_i(st(gate)), _arr_i(rows_per_gate),
+              _arr_p([_ptr(t) for t in preact_out]), _stream())
+    return cs[0].reshape(*lead[0], N), cs[1].reshape(*lead[1], N)
+
+
 # --------------------------------------------------------------------------- reward preprocessing
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)

@@ -202,6 +202,17 @@ int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       const void* residual, int64_t ldr, const void* gate, int64_t gate_stride,
                       int64_t rows_per_gate, void* preact_out, advgrpo_stream_t stream);
 
+/* Two problems in ONE persistent launch: same N, K, K2 and epilogue, different operands and row counts
+ * (every argument array has 2 entries; optional arrays may be NULL).  The MMDiT block runs its image-stream
+ * and text-stream projections (different weights, 1024 vs 205 tokens per sample) this way: the short text
+ * problem fills the tail wave of the image problem instead of paying its own launch and wave quantisation. */
+int advgrpo_gemm_bf16_dual(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                           const void* const* A2, const int64_t* lda2, const void* const* W2, const int64_t* ldw2,
+                           int64_t K2, const void* const* bias, void* const* C, const int64_t* ldc, const int64_t* M,
+                           int64_t N, int64_t K, int epilogue, const void* const* residual, const int64_t* ldr,
+                           const void* const* gate, const int64_t* gate_stride, const int64_t* rows_per_gate,
+                           void* const* preact_out, advgrpo_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * A8a preprocessing: the reward image path of adv_grpo/rewards.py:581-584 +
  * adv_grpo/pickscore_scorer.py:21-28 (CLIPProcessor) without the host round trip:

@@ -86,3 +86,15 @@ def test_mmdit_backward_matches_oracle_autograd():
             assert cos > 0.99, (name, cos)
             rel = (got.float().cpu() - refg).norm().item() / refg.norm().item()
             assert rel < 0.1, (name, rel)
+
+
+def test_mmdit_dual_gemm_matches_separate_launches():
+    model, oracle, x, t, ctx, pooled = _setup()
+    args = (x.to(DEV), t.to(DEV), ctx.to(DEV), pooled.to(DEV))
+    with torch.no_grad():
+        model.dual_gemm = True
+        a = model(*args)[0]
+        model.dual_gemm = False
+        b = model(*args)[0]
+        model.dual_gemm = True
+    assert torch.allclose(a.float(), b.float(), atol=2e-2, rtol=2e-2)

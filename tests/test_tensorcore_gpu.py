@@ -180,3 +180,31 @@ def test_gemm_tile_variants(ops, variant, M, N, K):
     ref = a.float() @ w.float().T + bias.float()
     assert _rel_err(got, ref) < 6e-3
     assert _rel_err(got_r, res.float() + gate.float() * ref) < 6e-3
+
+
+def test_gemm_dual_problem_launch(ops):
+    """Image-stream + text-stream projection in one persistent launch == two separate launches."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, N_img, N_txt, K, N, R = 2, 1024, 205, 1536, 1536, 64
+    a = [torch.randn(B * n, K, device=DEV, generator=g).bfloat16() for n in (N_img, N_txt)]
+    w = [(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16() for _ in range(2)]
+    bias = [torch.randn(N, device=DEV, generator=g).bfloat16() for _ in range(2)]
+    res = [torch.randn(B * n, N, device=DEV, generator=g).bfloat16() for n in (N_img, N_txt)]
+    gate = [torch.randn(B, N, device=DEV, generator=g).bfloat16() for _ in range(2)]
+    a2 = [torch.randn(B * n, R, device=DEV, generator=g).bfloat16() for n in (N_img, N_txt)]
+    w2 = [(0.1 * torch.randn(N, R, device=DEV, generator=g)).bfloat16() for _ in range(2)]
+    y = ops.gemm_dual(a, w, bias=bias, a2=a2, w2=w2, epilogue=ops.EPI_GATE_RESIDUAL, residual=res, gate=gate,
+                      rows_per_gate=(N_img, N_txt))
+    for i, n in enumerate((N_img, N_txt)):
+        single = ops.gemm(a[i], w[i], bias=bias[i], a2=a2[i], w2=w2[i], epilogue=ops.EPI_GATE_RESIDUAL, residual=res[i],
+                          gate=gate[i], rows_per_gate=n)
+        ref = res[i].float() + gate[i].float().repeat_interleave(n, 0) * (a[i].float() @ w[i].float().T + bias[i].float()
+                                                                         + a2[i].float() @ w2[i].float().T)
+        assert _rel_err(y[i], ref) < 6e-3
+        assert torch.allclose(y[i].float(), single.float(), atol=1e-2, rtol=1e-2)
+    pre = [torch.empty(B * n, N, device=DEV, dtype=torch.bfloat16) for n in (N_img, N_txt)]
+    h = ops.gemm_dual(a, w, bias=bias, epilogue=ops.EPI_GELU_TANH, preact_out=pre)
+    for i in range(2):
+        z = a[i].float() @ w[i].float().T + bias[i].float()
+        assert _rel_err(pre[i], z) < 6e-3
+        assert _rel_err(h[i], torch.nn.functional.gelu(z, approximate="tanh")) < 6e-3
