@@ -2,11 +2,13 @@
 //   C[M,N] = epi( A[M,K] W[N,K]^T (+ A2[M,K2] W2[N,K2]^T) + bias )
 // Both operands are K-major (activations row-major, nn.Linear weights [out, in]) so one
 // 128B-swizzled TMA box per operand per 64-wide K block feeds tcgen05.mma directly.
-//   warp 4 : TMA producer (STAGES-deep smem ring)          warp 5 : MMA issuer (one thread)
-//   warps 0-3 : epilogue (TMEM -> registers -> bias / GELU / gate*x + residual -> bf16 stores)
-// Tile 128 x BN (BN = 256 or 128), K block 64.  Two TMEM accumulators (2 x BN columns) so the
-// epilogue of tile i overlaps the main loop of tile i+1.  One CTA per SM, static round-robin
-// tile schedule with N fastest (neighbouring CTAs share the A row block in L2).
+//   warp 8 : TMA producer (STAGES-deep smem ring)          warp 9 : MMA issuer (one thread)
+//   warps 0-3 / 4-7 : two epilogue teams (TMEM -> registers -> bias / GELU / gate*x + residual -> bf16 ->
+//   swizzled smem -> TMA store).  Team k drains TMEM accumulator k, i.e. every other tile of the CTA, so an
+//   epilogue may take up to two main loops before it stalls the tensor pipe, and each SM sub-partition holds
+//   two epilogue warps that hide each other's TMEM / barrier / MUFU latencies.
+// Tile 128 x BN (BN = 256 or 128), K block 64.  Two TMEM accumulators (2 x BN columns).  One CTA per SM,
+// static round-robin tile schedule with N fastest (neighbouring CTAs share the A row block in L2).
 // The optional second product accumulates the LoRA update into the same accumulator.
 //
 // Replaces the nn.Linear / peft lora.Linear layers under SD3Transformer2DModel
@@ -26,14 +28,17 @@ constexpr int BK = 64;
 // half (128 rows) of the B tile, which halves the per-CTA operand traffic and leaves room for 6 stages.
 template <int BN, bool TWO = false>
 struct GCfg {
-  static constexpr int kStages = TWO ? 6 : ((BN >= 192) ? 4 : 6);
+  // epilogue staging ring: 4 [128 x 64] bf16 tiles where shared memory allows (residual prefetch two column
+  // groups ahead; pre-activation + activation tile per group), 2 for the single-CTA 128 x 256 tile
+  static constexpr int kNBuf = 4;                      // 2 per epilogue team
+  static constexpr int kStages = TWO ? 5 : ((BN >= 256) ? 3 : (BN >= 192 ? 4 : 5));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 2 * BM * 128;   // two [128 x 64] bf16 epilogue tiles
+  static constexpr int kStagingBytes = kNBuf * BM * 128;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;   // two accumulators, power-of-two allocation
-  static constexpr int kThreads = 192;
+  static constexpr int kThreads = 320;
 };
 
 // Per-problem fields.  A launch runs one or TWO problems that share N, K, K2 and the epilogue type (the image
@@ -54,15 +59,34 @@ struct GParams {
   int tiles_n, tiles0, num_tiles;
 };
 
+// Activations on the MUFU fast paths (1 tanh.approx, or 1 rcp + 1 ex2): the accurate libdevice tanhf / erff
+// cost ~30 instructions per element and made the FF1 epilogue twice as long as its main loop.  The result
+// is rounded to bf16 (2^-8 relative), far above either approximation's error.
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)
+  const float z = fabsf(x) * 0.7071067811865476f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);              // 0.5 x (1 + sign(x) erf|x|) = hx + |hx| erf|x|
+}
 
 template <int BN, bool TWO>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
             const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
@@ -79,8 +103,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   uint64_t* bar_empty = bars + G::kStages;
   uint64_t* bar_acc_full = bar_empty + G::kStages;   // 2
   uint64_t* bar_acc_empty = bar_acc_full + 2;        // 2
-  uint64_t* bar_res = bar_acc_empty + 2;             // 2
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_res + 2);
+  uint64_t* bar_res = bar_acc_empty + 2;             // 4
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_res + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,12 +123,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
       mbar_init(&bar_acc_empty[i], TWO ? 256 : 128);
-      mbar_init(&bar_res[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_res[i], 1);
     fence_barrier_init();
   }
   if constexpr (TWO) cluster_sync_all();          // peer barriers exist before any remote arrive / multicast
-  if (warp == 5) {
+  if (warp == 9) {
     if constexpr (TWO) {
       tmem_alloc_2cta(tmem_base_smem, G::kTmemCols);
       tmem_relinquish_2cta();
@@ -118,7 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       prefetch_tmap(&tm_a);
@@ -151,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================== MMA issuer ==============================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
@@ -183,18 +207,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
   } else {
     // ============================== epilogue ==============================
-    // TMEM -> registers -> (bias / GELU / gate * y + residual) -> bf16 -> 128B-swizzled smem tile
-    // [128 rows x 64 cols] -> TMA store (coalesced, clipped at the M / N edges).  Two staging tiles
-    // alternate; the residual tile is TMA-prefetched INTO the staging tile and updated in place.
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const int tid = threadIdx.x;                       // 0..127
-    const int lrow = warp * 32 + lane;                 // row inside the tile
+    // Team k (warps 4k .. 4k+3) owns accumulator k = the CTA's tiles k, k+2, k+4, ... and two [128 x 64] bf16
+    // staging tiles.  Per 64-column group: TMEM -> registers -> (bias / GELU / gate * y + residual) -> bf16 ->
+    // 128B-swizzled staging tile -> TMA store (coalesced, clipped at the M / N edges).
+    //   plain / GELU       : the two tiles alternate; a tile is rewritten once its store of two groups ago drained
+    //   GATE_RESIDUAL      : the residual tile is TMA-prefetched INTO the staging tile one group ahead, updated in place
+    //   GELU + preact out  : each group fills both tiles (z, act) and issues two stores
+    const int team = warp >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int tid = threadIdx.x & 127;                 // thread inside the team
+    const int lrow = (warp & 3) * 32 + lane;           // row inside the tile
+    const uint32_t bar_a = 1 + 2 * team, bar_b = 2 + 2 * team;
+    uint8_t* tstage = stage + team * (2 * BM * 128);
+    uint64_t* tbar_res = bar_res + 2 * team;
     const bool has_res = p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL;
+    const bool is_gelu = p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF;
     constexpr int NG = BN / 64;
-    uint32_t res_phase[2] = {0u, 0u};
-    int local = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
-      const int acc = local & 1;
+    uint32_t gc = 0;                                   // running column-group counter of this team (ring position)
+    int round = 0;
+    for (int tile = worker + team * num_workers; tile < num_tiles; tile += 2 * num_workers, ++round) {
+      const int acc = team;
       const bool second = tile >= p.tiles0;
       const int t = second ? tile - p.tiles0 : tile;
       const int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM;
@@ -204,97 +236,119 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const bool row_ok = row < prob_M;
       const __nv_bfloat16* p_bias = second ? p.b.bias : p.a.bias;
       const __nv_bfloat16* p_gate = second ? p.b.gate : p.a.gate;
-      __nv_bfloat16* p_preact = second ? p.b.preact : p.a.preact;
-      const int64_t p_ldc = second ? p.b.ldc : p.a.ldc;
+      const bool has_preact = is_gelu && (second ? p.b.preact : p.a.preact) != nullptr;
       const int64_t p_gate_stride = second ? p.b.gate_stride : p.a.gate_stride;
       const int64_t p_rows_per_gate = second ? p.b.rows_per_gate : p.a.rows_per_gate;
       const CUtensorMap* m_c = second ? &tn_c : &tm_c;
-      const CUtensorMap* m_r = second ? &tn_r : &tm_r;
-      mbar_wait(&bar_acc_full[acc], (local >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + acc * BN + lane_addr;
+      const CUtensorMap* m_r = second ? &tn_r : &tm_r;   // residual (GATE_RESIDUAL) or pre-activation (GELU) map
+      int ng = (p.N - n0 + 63) / 64;                      // column groups of this tile inside N
+      ng = ng < NG ? ng : NG;
       const __nv_bfloat16* grow =
           (p_gate && row_ok) ? p_gate + (int64_t)(row / p_rows_per_gate) * p_gate_stride + n0 : nullptr;
       if (has_res && tid == 0) {
-        tma_store_wait_read<0>();
-        mbar_expect_tx(&bar_res[0], BM * 128);
-        tma_load_2d(stage, m_r, &bar_res[0], n0, m0);
+        tma_store_wait_read<1>();                      // tile gc&1 was last stored two groups ago
+        const uint32_t b = gc & 1;
+        mbar_expect_tx(&tbar_res[b], BM * 128);
+        tma_load_2d(tstage + b * (BM * 128), m_r, &tbar_res[b], n0, m0);
       }
+      mbar_wait(&bar_acc_full[acc], round & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * BN + lane_addr;
 #pragma unroll 1
-      for (int g = 0; g < NG; ++g) {
-        const int buf = g & 1;
-        uint8_t* sbuf = stage + buf * (BM * 128);
-        if (tid == 0) {
-          if (has_res) {
-            if (g + 1 < NG && n0 + (g + 1) * 64 < p.N) {
-              tma_store_wait_read<0>();              // staging tile buf^1 (store g-1) has been read out
-              mbar_expect_tx(&bar_res[buf ^ 1], BM * 128);
-              tma_load_2d(stage + (buf ^ 1) * (BM * 128), m_r, &bar_res[buf ^ 1], n0 + (g + 1) * 64, m0);
-            }
-          } else {
-            tma_store_wait_read<1>();                // store g-2 (same staging tile) has been read out
-          }
-        }
-        named_bar_sync(1, 128);
-        if (n0 + g * 64 >= p.N) break;               // uniform: whole 64-column group beyond N
+      for (int g = 0; g < ng; ++g, ++gc) {
+        // ---- issue the accumulator loads first; everything below up to the wait overlaps their latency
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_acc + g * 64, r0);
+        tmem_ld32(t_acc + g * 64 + 32, r1);
+        uint32_t buf;
         if (has_res) {
-          mbar_wait(&bar_res[buf], res_phase[buf]);
-          res_phase[buf] ^= 1u;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = g * 2 + cc;
-          uint32_t r[32];
-          tmem_ld32(t_acc + c * 32, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const int col = n0 + c * 32 + i;
-            const int piece = cc * 4 + i / 8;
-            uint8_t* sp = sbuf + lrow * 128 + ((piece ^ (lrow & 7)) * 16);
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i + j]);
-            if (col < p.N) {
-              if (p_bias) {
-                float bb[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p_bias + col), bb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += bb[j];
-              }
-              if (p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF) {
-                // the activation is applied to the bf16-rounded pre-activation so that the fused
-                // forward is bit-identical to "store z in bf16, then GELU(z)" (training replay)
-                const bf16x8 z = pack8(f);
-                if (p_preact && row_ok) *reinterpret_cast<bf16x8*>(p_preact + (int64_t)row * p_ldc + col) = z;
-                unpack8(z, f);
-                if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-                }
-              } else if (has_res) {
-                float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
-                if (row_ok) unpack8(*reinterpret_cast<const bf16x8*>(grow + c * 32 + i), gg);
-                unpack8(*reinterpret_cast<const bf16x8*>(sp), rr);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaf(gg[j], f[j], rr[j]);
-              }
-            }
-            *reinterpret_cast<bf16x8*>(sp) = pack8(f);
+          buf = gc & 1;
+          if (tid == 0 && g + 1 < ng) {
+            tma_store_wait_read<0>();                  // the other tile (store of group g-1) is drained
+            const uint32_t b = buf ^ 1;
+            mbar_expect_tx(&tbar_res[b], BM * 128);
+            tma_load_2d(tstage + b * (BM * 128), m_r, &tbar_res[b], n0 + (g + 1) * 64, m0);
           }
+        } else if (has_preact) {
+          buf = 0;
+          if (tid == 0) tma_store_wait_read<0>();
+          named_bar_sync(bar_a, 128);
+        } else {
+          buf = gc & 1;
+          if (tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(bar_a, 128);
         }
-        if (g == NG - 1 || n0 + (g + 1) * 64 >= p.N) {
-          tc_fence_before();                          // accumulator fully read: next tile may overwrite
+        uint8_t* sbuf = tstage + buf * (BM * 128);
+        const int colg = n0 + g * 64;
+        bf16x8 bv[8], gv[8];
+        if (p_bias) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (colg + q * 8 < p.N) bv[q] = *reinterpret_cast<const bf16x8*>(p_bias + colg + q * 8);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (grow && colg + q * 8 < p.N) gv[q] = *reinterpret_cast<const bf16x8*>(grow + g * 64 + q * 8);
+          mbar_wait(&tbar_res[buf], (gc >> 1) & 1);
+        }
+        tmem_wait_ld();
+        if (g == ng - 1) {
+          tc_fence_before();                          // accumulator fully read: the MMA warp may overwrite it
           if constexpr (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
           else mbar_arrive(&bar_acc_empty[acc]);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = colg + q * 8;
+          uint8_t* sp = sbuf + lrow * 128 + ((q ^ (lrow & 7)) * 16);
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(q < 4 ? r0[(q & 3) * 8 + j] : r1[(q & 3) * 8 + j]);
+          if (col < p.N) {
+            if (p_bias) {
+              float bb[8];
+              unpack8(bv[q], bb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += bb[j];
+            }
+            if (is_gelu) {
+              // the activation is applied to the bf16-rounded pre-activation so that the fused
+              // forward is bit-identical to "store z in bf16, then GELU(z)" (training replay)
+              const bf16x8 z = pack8(f);
+              unpack8(z, f);
+              if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+              }
+              if (has_preact) {
+                *reinterpret_cast<bf16x8*>(sp) = z;
+                sp += BM * 128;
+              }
+            } else if (has_res) {
+              float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
+              if (grow) unpack8(gv[q], gg);
+              unpack8(*reinterpret_cast<const bf16x8*>(sp), rr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(gg[j], f[j], rr[j]);
+            }
+          } else if (has_preact) {
+            sp += BM * 128;
+          }
+          *reinterpret_cast<bf16x8*>(sp) = pack8(f);
+        }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(bar_b, 128);
         if (tid == 0) {
-          tma_store_2d(m_c, sbuf, n0 + g * 64, m0);
+          if (has_preact) {
+            tma_store_2d(m_r, sbuf, colg, m0);
+            tma_store_2d(m_c, sbuf + BM * 128, colg, m0);
+          } else {
+            tma_store_2d(m_c, sbuf, colg, m0);
+          }
           tma_store_commit();
         }
       }
@@ -304,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
   tc_fence_before();
   if constexpr (TWO) cluster_sync_all(); else __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     if constexpr (TWO) tmem_dealloc_2cta(tmem_base, G::kTmemCols); else tmem_dealloc(tmem_base, G::kTmemCols);
   }
@@ -414,6 +468,9 @@ int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int 
   if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
     const uint64_t sr[2] = {0, (uint64_t)q.ldr * 2};
     rc = make_tmap_bf16(&m.r, q.residual, 2, dc, sr, bc, true);
+    if (rc) return rc;
+  } else if (q.preact) {
+    rc = make_tmap_bf16(&m.r, q.preact, 2, dc, sc, bc, true);   // pre-activation output: same shape / ld as C
     if (rc) return rc;
   } else {
     m.r = m.c;

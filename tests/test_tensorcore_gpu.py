@@ -208,3 +208,34 @@ def test_gemm_dual_problem_launch(ops):
         z = a[i].float() @ w[i].float().T + bias[i].float()
         assert _rel_err(pre[i], z) < 6e-3
         assert _rel_err(h[i], torch.nn.functional.gelu(z, approximate="tanh")) < 6e-3
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("M,N,K", [(777, 1544, 128), (300, 200, 64), (2600, 6144, 256)])
+def test_gemm_epilogue_staging_ring_ragged(ops, variant, M, N, K):
+    """The epilogue staging ring (residual prefetch two column groups ahead, pre-activation + activation tiles)
+    at ragged M / N (N not a multiple of the 64-column group, last tile partially outside) for every tile shape."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g).bfloat16()
+    z = a.float() @ w.float().T + bias.float()
+    ops.set_gemm_variant(variant)
+    try:
+        pre = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        h = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU_TANH, preact_out=pre)
+        assert torch.equal(pre, z.bfloat16()) or _rel_err(pre, z) < 6e-3
+        # the activation is evaluated on the bf16-rounded pre-activation (training replay == rollout)
+        assert _rel_err(h, torch.nn.functional.gelu(pre.float(), approximate="tanh")) < 6e-3
+        h2 = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU_TANH)
+        assert torch.equal(h, h2)
+        he = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GELU_ERF)
+        assert _rel_err(he, torch.nn.functional.gelu(pre.float())) < 6e-3
+        rpg = 100
+        res = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+        gate = torch.randn((M + rpg - 1) // rpg, N, device=DEV, generator=g).bfloat16()
+        y = ops.gemm(a, w, bias=bias, epilogue=ops.EPI_GATE_RESIDUAL, residual=res, gate=gate, rows_per_gate=rpg)
+        ref = res.float() + gate.float().repeat_interleave(rpg, 0)[:M] * z
+        assert _rel_err(y, ref) < 6e-3
+    finally:
+        ops.set_gemm_variant(0)
