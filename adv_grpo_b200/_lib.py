@@ -37,6 +37,8 @@ SIGNATURES = {
                                   _I64, _I, _P, _I64, _P, _I64, _I64, _P, _P]),
     "advgrpo_gemm_bf16_dual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P,
                                        _P, _P, _P, _P]),
+    "advgrpo_gemm_qkv_norm": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64,
+                                      _F, _P]),
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_clip_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),

@@ -284,6 +284,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if (m != -INFINITY && m_new - m <= kRescaleThreshold) m_new = m;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // fully masked row so far
       const float alpha = (m == -INFINITY) ? 1.f : ex2(m - m_use);
+      // ---- p = exp2(s * scale - m) and the row sum, bf16 P kept in registers: the exponentials do not depend
+      //      on PV(j-1), so they run while the tensor pipe is still busy with it ----
+      float2 sum2 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_use, -m_use);
+      uint32_t pk[NCH][16];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+          float2 e;
+          if ((i / 2) % 4 < EMU) {
+            e = ex2_poly2(x);
+          } else {
+            e.x = ex2(x.x);
+            e.y = ex2(x.y);
+          }
+          sum2 = __fadd2_rn(sum2, e);
+          pk[c][i / 2] = pack_bf16(e.x, e.y);
+        }
+      }
+      // ---- only now wait for PV(j-1): it reads P(j-1) from the TMEM columns P(j) is about to overwrite, and O
+      //      may only be rescaled between PV(j-1) and PV(j) ----
       if (j > 0) {
         mbar_wait(&bar_pv_done[q], (j - 1) & 1);
         tc_fence_after();
@@ -299,27 +322,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
         }
       }
-      // ---- p = exp2(s * scale - m), row sum, bf16 P -> TMEM ----
-      float2 sum2 = make_float2(0.f, 0.f);
-      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
-          float2 e;
-          if ((i / 2) % 4 < EMU) {
-            e = ex2_poly2(x);
-          } else {
-            e.x = ex2(x.x);
-            e.y = ex2(x.y);
-          }
-          sum2 = __fadd2_rn(sum2, e);
-          pk[i / 2] = pack_bf16(e.x, e.y);
-        }
-        tmem_st16(p_tmem + c * 16, pk);
-      }
+      for (int c = 0; c < NCH; ++c) tmem_st16(p_tmem + c * 16, pk[c]);
       const float rowsum = sum2.x + sum2.y;
       l = l * alpha + rowsum;
       m = m_new;

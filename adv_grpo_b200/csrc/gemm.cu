@@ -51,12 +51,20 @@ struct GProb {
   const __nv_bfloat16* gate;
   int64_t ldc, gate_stride, rows_per_gate;
   int M, tiles_m;
+  const __nv_bfloat16* norm_q;   // QKNORM: per-head RMSNorm weights [64] of the q / k sections (NULL = no norm)
+  const __nv_bfloat16* norm_k;
+  // QKNORM tiles never cross a sample: row blocks are enumerated per sample (tps blocks for each of the S_x-token
+  // samples), A / A2 / C / pre-norm go through 3-D maps {column, token, sample} whose token bound zero-fills the
+  // loads and clips the stores of the ragged last block
+  int S_x, tps;
 };
 struct GParams {
   GProb a, b;              // problem 0, problem 1 (b.M == 0 when absent)
   int N, kb1, kb2;         // k blocks of the main and of the second product
   int epilogue;
   int tiles_n, tiles0, num_tiles;
+  int HD;                  // QKNORM: width of one q / k / v section (heads * 64)
+  float eps;
 };
 
 // Activations on the MUFU fast paths (1 tanh.approx, or 1 rcp + 1 ex2): the accurate libdevice tanhf / erff
@@ -114,6 +122,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int kTileM = TWO ? 2 * BM : BM;
+  const bool per_sample = p.epilogue == ADVGRPO_EPI_QKNORM;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G::kStages; ++i) {
@@ -151,13 +160,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const bool second = tile >= p.tiles0;
         const int t = second ? tile - p.tiles0 : tile;
-        const int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM;
+        int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM, sb = 0;
+        if (per_sample) {
+          const int tps = second ? p.b.tps : p.a.tps;
+          sb = (t / p.tiles_n) / tps;
+          m0 = ((t / p.tiles_n) % tps) * kTileM + (int)rank * BM;
+        }
         const int n0 = (t % p.tiles_n) * BN + (TWO ? (int)rank * (BN / 2) : 0);
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int st = it % G::kStages;
           mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
           uint8_t* sa = smem + st * G::kStageBytes;
-          uint8_t* sb = sa + G::kABytes;
+          uint8_t* sw = sa + G::kABytes;
           const CUtensorMap* ma = kb < p.kb1 ? (second ? &tn_a : &tm_a) : (second ? &tn_a2 : &tm_a2);
           const CUtensorMap* mw = kb < p.kb1 ? (second ? &tn_w : &tm_w) : (second ? &tn_w2 : &tm_w2);
           const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BK;
@@ -165,12 +179,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             // both CTAs' bytes land on the LEADER's full barrier (one expect_tx of the pair's total)
             const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
             if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
-            tma_load_2d_2sm(sa, ma, full_leader, kc, m0);
-            tma_load_2d_2sm(sb, mw, full_leader, kc, n0);
+            if (per_sample) tma_load_3d_2sm(sa, ma, full_leader, kc, m0, sb);
+            else tma_load_2d_2sm(sa, ma, full_leader, kc, m0);
+            tma_load_2d_2sm(sw, mw, full_leader, kc, n0);
           } else {
             mbar_expect_tx(&bar_full[st], G::kStageBytes);
-            tma_load_2d(sa, ma, &bar_full[st], kc, m0);
-            tma_load_2d(sb, mw, &bar_full[st], kc, n0);
+            if (per_sample) tma_load_3d(sa, ma, &bar_full[st], kc, m0, sb);
+            else tma_load_2d(sa, ma, &bar_full[st], kc, m0);
+            tma_load_2d(sw, mw, &bar_full[st], kc, n0);
           }
         }
       }
@@ -222,6 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint64_t* tbar_res = bar_res + 2 * team;
     const bool has_res = p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL;
     const bool is_gelu = p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF;
+    const bool is_qkn = p.epilogue == ADVGRPO_EPI_QKNORM;
     constexpr int NG = BN / 64;
     uint32_t gc = 0;                                   // running column-group counter of this team (ring position)
     int round = 0;
@@ -229,14 +246,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const int acc = team;
       const bool second = tile >= p.tiles0;
       const int t = second ? tile - p.tiles0 : tile;
-      const int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM;
+      int m0 = (t / p.tiles_n) * kTileM + (int)rank * BM, sb = 0;
+      if (per_sample) {
+        const int tps = second ? p.b.tps : p.a.tps;
+        sb = (t / p.tiles_n) / tps;
+        m0 = ((t / p.tiles_n) % tps) * kTileM + (int)rank * BM;
+      }
       const int n0 = (t % p.tiles_n) * BN;
       const int row = m0 + lrow;
-      const int prob_M = second ? p.b.M : p.a.M;
+      const int prob_M = per_sample ? (second ? p.b.S_x : p.a.S_x) : (second ? p.b.M : p.a.M);
       const bool row_ok = row < prob_M;
       const __nv_bfloat16* p_bias = second ? p.b.bias : p.a.bias;
       const __nv_bfloat16* p_gate = second ? p.b.gate : p.a.gate;
-      const bool has_preact = is_gelu && (second ? p.b.preact : p.a.preact) != nullptr;
+      const bool has_preact = (is_gelu || is_qkn) && (second ? p.b.preact : p.a.preact) != nullptr;
+      const __nv_bfloat16* p_nq = second ? p.b.norm_q : p.a.norm_q;
+      const __nv_bfloat16* p_nk = second ? p.b.norm_k : p.a.norm_k;
       const int64_t p_gate_stride = second ? p.b.gate_stride : p.a.gate_stride;
       const int64_t p_rows_per_gate = second ? p.b.rows_per_gate : p.a.rows_per_gate;
       const CUtensorMap* m_c = second ? &tn_c : &tm_c;
@@ -292,12 +316,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             if (grow && colg + q * 8 < p.N) gv[q] = *reinterpret_cast<const bf16x8*>(grow + g * 64 + q * 8);
           mbar_wait(&tbar_res[buf], (gc >> 1) & 1);
         }
+        // QKNORM: this 64-column group is exactly one head of the q (sec 0), k (sec 1) or v (sec 2) section
+        const __nv_bfloat16* nw = nullptr;
+        if (is_qkn) {
+          const int sec = colg / p.HD;
+          nw = sec == 0 ? p_nq : (sec == 1 ? p_nk : nullptr);
+          if (nw) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gv[q] = *reinterpret_cast<const bf16x8*>(nw + q * 8);
+          }
+        }
         tmem_wait_ld();
         if (g == ng - 1) {
           tc_fence_before();                          // accumulator fully read: the MMA warp may overwrite it
           if constexpr (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
           else mbar_arrive(&bar_acc_empty[acc]);
         }
+        if (is_qkn) {
+          // z = bf16(acc + bias); per-head RMSNorm of z in the summation order of qk_norm_concat_fwd_kernel
+          // (8-element fmaf chains, then a pairwise tree), so the fused and the two-kernel paths are bit-identical
+          float cs[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(q < 4 ? r0[(q & 3) * 8 + j] : r1[(q & 3) * 8 + j]);
+            if (p_bias) {
+              float bb[8];
+              unpack8(bv[q], bb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += bb[j];
+            }
+            const bf16x8 z = pack8(f);
+            unpack8(z, f);
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+            cs[q] = ss;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (q < 4) r0[(q & 3) * 8 + j] = __float_as_uint(f[j]);
+              else r1[(q & 3) * 8 + j] = __float_as_uint(f[j]);
+            }
+            if (has_preact) *reinterpret_cast<bf16x8*>(sbuf + lrow * 128 + ((q ^ (lrow & 7)) * 16)) = z;
+          }
+          const float ssum = ((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]));
+          const float rn = rsqrtf(ssum * (1.0f / 64.0f) + p.eps);
+          uint8_t* obuf = has_preact ? sbuf + BM * 128 : sbuf;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(q < 4 ? r0[(q & 3) * 8 + j] : r1[(q & 3) * 8 + j]);
+            if (nw) {
+              float fw[8];
+              unpack8(gv[q], fw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = f[j] * rn * fw[j];
+            }
+            *reinterpret_cast<bf16x8*>(obuf + lrow * 128 + ((q ^ (lrow & 7)) * 16)) = pack8(f);
+          }
+        } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int col = colg + q * 8;
@@ -340,10 +419,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           }
           *reinterpret_cast<bf16x8*>(sp) = pack8(f);
         }
+        }
         fence_proxy_async_smem();
         named_bar_sync(bar_b, 128);
         if (tid == 0) {
-          if (has_preact) {
+          if (is_qkn) {
+            // C is the joint [sample, token, 3 HD] buffer seen as {column, token of this stream, sample}
+            if (has_preact) tma_store_3d(m_r, sbuf, colg, m0, sb);
+            tma_store_3d(m_c, has_preact ? sbuf + BM * 128 : sbuf, colg, m0, sb);
+          } else if (has_preact) {
             tma_store_2d(m_r, sbuf, colg, m0);
             tma_store_2d(m_c, sbuf + BM * 128, colg, m0);
           } else {
@@ -379,6 +463,12 @@ int launch_gemm(const Maps& m0, const Maps& m1, GParams& p, cudaStream_t st) {
   constexpr int kTileM = TWO ? 2 * BM : BM;
   p.a.tiles_m = (p.a.M + kTileM - 1) / kTileM;
   p.b.tiles_m = (p.b.M + kTileM - 1) / kTileM;
+  if (p.epilogue == ADVGRPO_EPI_QKNORM) {
+    p.a.tps = (p.a.S_x + kTileM - 1) / kTileM;
+    p.b.tps = (p.b.S_x + kTileM - 1) / kTileM;
+    p.a.tiles_m = (p.a.M / p.a.S_x) * p.a.tps;
+    p.b.tiles_m = (p.b.M / p.b.S_x) * p.b.tps;
+  }
   p.tiles_n = (p.N + BN - 1) / BN;
   p.tiles0 = p.a.tiles_m * p.tiles_n;
   p.num_tiles = p.tiles0 + p.b.tiles_m * p.tiles_n;
@@ -414,6 +504,10 @@ struct ProbArgs {
   const void *A, *W, *A2, *W2, *bias, *residual, *gate;
   void *C, *preact;
   int64_t lda, ldw, lda2, ldw2, ldc, ldr, gate_stride, rows_per_gate, M;
+  // QKNORM only: C = first row of this stream inside the joint buffer, ldc = joint row stride,
+  // S_x tokens per sample in this stream, c_batch_stride = elements between samples of the joint buffer
+  const void *norm_q = nullptr, *norm_k = nullptr;
+  int64_t S_x = 0, c_batch_stride = 0;
 };
 
 int check_prob(const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int epilogue) {
@@ -437,10 +531,20 @@ int check_prob(const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int epilogue
 }
 
 int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int BN, bool two, int epilogue) {
+  const bool per_sample = epilogue == ADVGRPO_EPI_QKNORM;
+  const uint64_t nb = per_sample ? (uint64_t)(q.M / q.S_x) : 1;
+  const uint32_t b3[3] = {BK, BM, 1};
   const uint64_t da[2] = {(uint64_t)K, (uint64_t)q.M};
   const uint64_t sa[2] = {0, (uint64_t)q.lda * 2};
   const uint32_t ba[2] = {BK, BM};
-  int rc = make_tmap_bf16(&m.a, q.A, 2, da, sa, ba, true);
+  int rc;
+  if (per_sample) {
+    const uint64_t d3[3] = {(uint64_t)K, (uint64_t)q.S_x, nb};
+    const uint64_t s3[3] = {0, (uint64_t)q.lda * 2, (uint64_t)(q.S_x * q.lda) * 2};
+    rc = make_tmap_bf16(&m.a, q.A, 3, d3, s3, b3, true);
+  } else {
+    rc = make_tmap_bf16(&m.a, q.A, 2, da, sa, ba, true);
+  }
   if (rc) return rc;
   const uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t sw[2] = {0, (uint64_t)q.ldw * 2};
@@ -450,7 +554,13 @@ int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int 
   if (K2 > 0) {
     const uint64_t da2[2] = {(uint64_t)K2, (uint64_t)q.M};
     const uint64_t sa2[2] = {0, (uint64_t)q.lda2 * 2};
-    rc = make_tmap_bf16(&m.a2, q.A2, 2, da2, sa2, ba, true);
+    if (per_sample) {
+      const uint64_t d3[3] = {(uint64_t)K2, (uint64_t)q.S_x, nb};
+      const uint64_t s3[3] = {0, (uint64_t)q.lda2 * 2, (uint64_t)(q.S_x * q.lda2) * 2};
+      rc = make_tmap_bf16(&m.a2, q.A2, 3, d3, s3, b3, true);
+    } else {
+      rc = make_tmap_bf16(&m.a2, q.A2, 2, da2, sa2, ba, true);
+    }
     if (rc) return rc;
     const uint64_t dw2[2] = {(uint64_t)K2, (uint64_t)N};
     const uint64_t sw2[2] = {0, (uint64_t)q.ldw2 * 2};
@@ -463,6 +573,21 @@ int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int 
   const uint64_t dc[2] = {(uint64_t)N, (uint64_t)q.M};
   const uint64_t sc[2] = {0, (uint64_t)q.ldc * 2};
   const uint32_t bc[2] = {64, BM};
+  if (epilogue == ADVGRPO_EPI_QKNORM) {
+    // joint buffer seen from this stream: {column, token of the stream, sample}
+    const uint64_t d3[3] = {(uint64_t)N, (uint64_t)q.S_x, nb};
+    const uint64_t s3[3] = {0, (uint64_t)q.ldc * 2, (uint64_t)q.c_batch_stride * 2};
+    rc = make_tmap_bf16(&m.c, q.C, 3, d3, s3, b3, true);
+    if (rc) return rc;
+    if (q.preact) {
+      const uint64_t sp[3] = {0, (uint64_t)N * 2, (uint64_t)(q.S_x * N) * 2};
+      rc = make_tmap_bf16(&m.r, q.preact, 3, d3, sp, b3, true);   // flat [M, N] pre-norm copy, same tiling
+      if (rc) return rc;
+    } else {
+      m.r = m.c;
+    }
+    return ADVGRPO_OK;
+  }
   rc = make_tmap_bf16(&m.c, q.C, 2, dc, sc, bc, true);
   if (rc) return rc;
   if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
@@ -487,15 +612,20 @@ void fill_prob(GProb& g, const ProbArgs& q) {
   g.rows_per_gate = q.rows_per_gate > 0 ? q.rows_per_gate : 1;
   g.M = (int)q.M;
   g.tiles_m = 0;
+  g.norm_q = (const __nv_bfloat16*)q.norm_q;
+  g.norm_k = (const __nv_bfloat16*)q.norm_k;
+  g.S_x = q.S_x > 0 ? (int)q.S_x : 1;
+  g.tps = 1;
 }
 
 // nprob = 1 or 2 problems sharing N, K, K2 and the epilogue type
-int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2, int epilogue, cudaStream_t st) {
+int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2, int epilogue, cudaStream_t st,
+             int64_t HD = 0, float eps = 0.f) {
   ADVGRPO_CHECK_ARG(N >= 8 && K >= 64, "gemm_bf16: bad sizes N=%lld K=%lld", (long long)N, (long long)K);
   ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && K2 % 64 == 0,
                     "gemm_bf16: K and K2 must be multiples of 64 and N of 8 (K=%lld K2=%lld N=%lld)", (long long)K,
                     (long long)K2, (long long)N);
-  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_bf16: unknown epilogue %d", epilogue);
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm_bf16: unknown epilogue %d", epilogue);
   for (int i = 0; i < nprob; ++i) {
     int rc = check_prob(probs[i], N, K, K2, epilogue);
     if (rc) return rc;
@@ -521,7 +651,12 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
       const int64_t workers = c.pair ? sm_count() / 2 : sm_count();
       const int64_t tile_m = c.pair ? 256 : 128;
       int64_t tiles = 0;
-      for (int i = 0; i < nprob; ++i) tiles += ((probs[i].M + tile_m - 1) / tile_m) * ((N + c.bn - 1) / c.bn);
+      for (int i = 0; i < nprob; ++i) {
+        const int64_t rows_tiles = epilogue == ADVGRPO_EPI_QKNORM
+                                       ? (probs[i].M / probs[i].S_x) * ((probs[i].S_x + tile_m - 1) / tile_m)
+                                       : (probs[i].M + tile_m - 1) / tile_m;
+        tiles += rows_tiles * ((N + c.bn - 1) / c.bn);
+      }
       // a pair tile (256 rows) is worked on by two SMs: per-SM time ~ 128 * bn in both cases
       const double cost = (double)((tiles + workers - 1) / workers) * (double)(128 * c.bn) / c.eff;
       if (best < 0 || cost < best) { best = cost; BN = c.bn; pair_ok = c.pair; }
@@ -542,6 +677,8 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   else { fill_prob(p.b, probs[0]); p.b.M = 0; }
   p.N = (int)N; p.kb1 = (int)(K / BK); p.kb2 = (int)(K2 / BK);
   p.epilogue = epilogue;
+  p.HD = (int)HD;
+  p.eps = eps;
   if (pair_ok && BN == 256) return launch_gemm<256, true>(m0, m1, p, st);
   if (pair_ok && BN == 192) return launch_gemm<192, true>(m0, m1, p, st);
   if (BN == 256) return launch_gemm<256, false>(m0, m1, p, st);
@@ -582,6 +719,34 @@ int advgrpo_gemm_bf16_dual(const void* const* A, const int64_t* lda, const void*
   }
   const bool has2 = A2 && A2[0];
   return gemm_run(q, 2, N, K, has2 ? K2 : 0, epilogue, (cudaStream_t)stream);
+}
+
+int advgrpo_gemm_qkv_norm(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                          const void* const* A2, const int64_t* lda2, const void* const* W2, const int64_t* ldw2,
+                          int64_t K2, const void* const* bias, const void* const* norm_q, const void* const* norm_k,
+                          void* qkv_joint, void* const* prenorm_out, int64_t B, const int64_t* S, int64_t H,
+                          int64_t D, int64_t K, float eps, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(A && W && lda && ldw && S && qkv_joint, "gemm_qkv_norm: null argument");
+  ADVGRPO_CHECK_ARG(D == 64, "gemm_qkv_norm: head_dim must be 64 (got %lld)", (long long)D);
+  ADVGRPO_CHECK_ARG(B >= 1 && H >= 1 && S[0] >= 1 && S[1] >= 0, "gemm_qkv_norm: bad sizes B=%lld H=%lld S=(%lld,%lld)",
+                    (long long)B, (long long)H, (long long)S[0], (long long)S[1]);
+  ADVGRPO_CHECK_ARG(aligned16(qkv_joint), "gemm_qkv_norm: 16-byte alignment");
+  const int64_t HD = H * D, N = 3 * HD, S_joint = S[0] + S[1];
+  const int nprob = S[1] > 0 ? 2 : 1;
+  ProbArgs q[2];
+  for (int i = 0; i < nprob; ++i) {
+    ADVGRPO_CHECK_ARG((norm_q && norm_q[i]) == (norm_k && norm_k[i]), "gemm_qkv_norm: norm_q / norm_k must both be set or both NULL");
+    void* c = (__nv_bfloat16*)qkv_joint + (i == 0 ? 0 : S[0] * N);
+    q[i] = {A[i], W[i], A2 ? A2[i] : nullptr, W2 ? W2[i] : nullptr, bias ? bias[i] : nullptr, nullptr, nullptr, c,
+            prenorm_out ? prenorm_out[i] : nullptr, lda[i], ldw[i], lda2 ? lda2[i] : 0, ldw2 ? ldw2[i] : 0, N, 0, 0, 1,
+            B * S[i]};
+    q[i].norm_q = norm_q ? norm_q[i] : nullptr;
+    q[i].norm_k = norm_k ? norm_k[i] : nullptr;
+    q[i].S_x = S[i];
+    q[i].c_batch_stride = S_joint * N;
+  }
+  const bool has2 = A2 && A2[0];
+  return gemm_run(q, nprob, N, K, has2 ? K2 : 0, ADVGRPO_EPI_QKNORM, (cudaStream_t)stream, HD, eps);
 }
 
 // Test/bench hook (not part of the reference-facing surface): force the GEMM CTA shape.

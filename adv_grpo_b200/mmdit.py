@@ -276,6 +276,7 @@ class SD3Transformer2DModel(torch.nn.Module):
                     self.lora_B[key] = torch.nn.Parameter(bb.to(self.device_, torch.float32))
                     self._lora_names.append(name)
         self.dual_gemm = True            # image + text projections of a block as one dual-problem GEMM launch
+        self.fused_qkv_norm = True       # no-grad forward: q/k RMSNorm + concat inside the QKV GEMM epilogue
         self._lora_cache = None
         self._lora_dirty = False
         self._lora_enabled = True
@@ -378,6 +379,16 @@ class SD3Transformer2DModel(torch.nn.Module):
                                    blk["b_" + key], blk["b_" + ckey], a0, a1, w20, w21, epilogue, res[0], res[1],
                                    gate[0], gate[1], rows[0], rows[1])
 
+    def _qkv_norm(self, blk, x1, c1, pk):
+        """no-grad path: fused QKV projection (+LoRA) + q/k RMSNorm + concat, one launch for both streams."""
+        H, D = self.cfg["heads"], self.cfg["head_dim"]
+        a2 = w2 = (None, None)
+        if pk is not None and "qkv" in pk and "cqkv" in pk:
+            (a0, w20), (a1, w21) = pk["qkv"], pk["cqkv"]
+            a2, w2 = ops.gemm_dual((x1, c1), (a0, a1)), (w20, w21)
+        return ops.gemm_qkv_norm(x1, c1, (blk["w_qkv"], blk["w_cqkv"]), (blk["b_qkv"], blk["b_cqkv"]),
+                                 (blk.get("nq"), blk.get("ncq")), (blk.get("nk"), blk.get("nck")), H, D, a2=a2, w2=w2)
+
     def _attention(self, joint, split):
         if torch.is_grad_enabled() and joint.requires_grad:
             if split:
@@ -407,19 +418,27 @@ class SD3Transformer2DModel(torch.nn.Module):
             c1 = ops.ln_modulate(c, ch(ec, 1), ch(ec, 0))           # AdaLayerNormContinuous: (scale, shift)
         else:
             c1 = ops.ln_modulate(c, ch(ec, 0), ch(ec, 1))
-        if self.dual_gemm:
-            qkv_x, qkv_c = self._lin2(x1, c1, blk, "qkv", "cqkv", pk)
+        fused_qkv = self.fused_qkv_norm and not torch.is_grad_enabled() and D == 64
+        if fused_qkv:
+            joint = self._qkv_norm(blk, x1, c1, pk)
         else:
-            qkv_x = self._lin(x1, blk, "qkv", pk)
-            qkv_c = self._lin(c1, blk, "cqkv", pk)
-        joint = ops.qk_norm_concat(qkv_x, qkv_c, blk.get("nq"), blk.get("nk"), blk.get("ncq"), blk.get("nck"), H, D)
+            if self.dual_gemm:
+                qkv_x, qkv_c = self._lin2(x1, c1, blk, "qkv", "cqkv", pk)
+            else:
+                qkv_x = self._lin(x1, blk, "qkv", pk)
+                qkv_c = self._lin(c1, blk, "cqkv", pk)
+            joint = ops.qk_norm_concat(qkv_x, qkv_c, blk.get("nq"), blk.get("nk"), blk.get("ncq"), blk.get("nck"), H, D)
         ox, oc = self._attention(joint, N)
         fused_out = self.dual_gemm and not blk["last"]
         if fused_out:
             x, c = self._lin2(ox, oc, blk, "out", "cout", pk, ops.EPI_GATE_RESIDUAL, (x, c), (ch(ex, 2), ch(ec, 2)), (N, Nc))
         else:
             x = self._lin(ox, blk, "out", pk, ops.EPI_GATE_RESIDUAL, x, ch(ex, 2), N)
-        if blk["dual"]:
+        if blk["dual"] and fused_qkv:
+            j2 = ops.gemm_qkv_norm(x2, None, (blk["w_qkv2"],), (blk["b_qkv2"],), (blk.get("nq2"),), (blk.get("nk2"),), H, D)
+            o2, _ = self._attention(j2, 0)
+            x = self._lin(o2, blk, "out2", None, ops.EPI_GATE_RESIDUAL, x, ch(ex, 8), N)
+        elif blk["dual"]:
             qkv2 = self._lin(x2, blk, "qkv2")
             j2 = ops.qk_norm_concat(qkv2, None, blk.get("nq2"), blk.get("nk2"), None, None, H, D)
             o2, _ = self._attention(j2, 0)

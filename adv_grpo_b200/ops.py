@@ -420,6 +420,33 @@ def gemm_dual(a, w, bias=(None, None), a2=(None, None), w2=(None, None), epilogu
     return cs[0].reshape(*lead[0], N), cs[1].reshape(*lead[1], N)
 
 
+def gemm_qkv_norm(x, c, w, bias, norm_q, norm_k, H, D=64, a2=(None, None), w2=(None, None), eps=1e-6,
+                  prenorm_out=(None, None)):
+    """Fused QKV projection + per-head q/k RMSNorm + [image, text] concat in one persistent dual-problem launch
+    (`advgrpo_gemm_qkv_norm`): x [B,S_img,K], c [B,S_txt,K] or None -> joint [B,S_img+S_txt,3,H,D].
+    w / bias / norm_q / norm_k / a2 / w2 are (image, text) pairs.  No autograd (rollout path); bit-identical to
+    gemm_dual + qk_norm_concat."""
+    _need_cuda(x, w[0])
+    B, S_img, K = x.shape
+    S_txt = 0 if c is None else c.shape[1]
+    n = 2 if c is not None else 1
+    xs = [x.reshape(-1, K)] + ([c.reshape(-1, K)] if c is not None else [])
+    xs = [t if t.stride(-1) == 1 else t.contiguous() for t in xs]
+    ws = [t if t.stride(-1) == 1 else t.contiguous() for t in w[:n]]
+    pad = lambda seq: list(seq[:n]) + [None] * (2 - n)
+    xs2, ws2 = pad(xs), pad(ws)
+    a2r = [None if t is None else t.reshape(xs[i].shape[0], -1) for i, t in enumerate(pad(a2)) ]
+    K2 = a2r[0].shape[1] if a2r[0] is not None else 0
+    joint = torch.empty((B, S_img + S_txt, 3, H, D), dtype=torch.bfloat16, device=x.device)
+    st = lambda ts: [0 if t is None else t.stride(0) for t in ts]
+    _lib.call("advgrpo_gemm_qkv_norm", _arr_p([_ptr(t) for t in xs2]), _arr_i(st(xs2)), _arr_p([_ptr(t) for t in ws2]),
+              _arr_i(st(ws2)), _arr_p([_ptr(t) for t in a2r]), _arr_i(st(a2r)), _arr_p([_ptr(t) for t in pad(w2)]),
+              _arr_i(st(pad(w2))), K2, _arr_p([_ptr(t) for t in pad(bias)]), _arr_p([_ptr(t) for t in pad(norm_q)]),
+              _arr_p([_ptr(t) for t in pad(norm_k)]), _ptr(joint), _arr_p([_ptr(t) for t in pad(prenorm_out)]), B,
+              _arr_i([S_img, S_txt]), H, D, K, float(eps), _stream())
+    return joint
+
+
 # --------------------------------------------------------------------------- reward preprocessing
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)

@@ -196,6 +196,7 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
 #define ADVGRPO_EPI_GELU_TANH 1
 #define ADVGRPO_EPI_GELU_ERF 2
 #define ADVGRPO_EPI_GATE_RESIDUAL 3
+#define ADVGRPO_EPI_QKNORM 4 /* only through advgrpo_gemm_qkv_norm */
 int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
@@ -212,6 +213,21 @@ int advgrpo_gemm_bf16_dual(const void* const* A, const int64_t* lda, const void*
                            int64_t N, int64_t K, int epilogue, const void* const* residual, const int64_t* ldr,
                            const void* const* gate, const int64_t* gate_stride, const int64_t* rows_per_gate,
                            void* const* preact_out, advgrpo_stream_t stream);
+
+/* Fused QKV projection of one MMDiT attention (JointAttnProcessor2_0: to_q/to_k/to_v and add_q/k/v_proj, per-head
+ * RMSNorm norm_q / norm_k / norm_added_q / norm_added_k, torch.cat([image, text], dim=1); reference call site
+ * sd3_pipeline_with_logprob_fast.py:630-637) as ONE persistent launch: problem 0 = image stream, problem 1 = text
+ * stream (S[1] == 0: image-only attention, the attn2 of the SD3.5 dual blocks).  A[i]: bf16 [B * S[i], K];
+ * W[i]: bf16 [3 * H * D, K] (q | k | v rows); optional LoRA second product as in advgrpo_gemm_bf16; bias[i] bf16 [3HD].
+ * Epilogue: z = bf16(acc + bias); q and k heads are RMS-normalised over D = 64 with norm_q[i] / norm_k[i] (bf16 [64],
+ * both NULL = no normalisation) exactly as advgrpo_qk_norm_concat_fwd does; the result is TMA-stored straight into
+ * qkv_joint bf16 [B, S[0] + S[1], 3, H, D] (image tokens first).  prenorm_out[i] (optional): z as flat [B * S[i], 3HD]
+ * for the backward pass. */
+int advgrpo_gemm_qkv_norm(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                          const void* const* A2, const int64_t* lda2, const void* const* W2, const int64_t* ldw2,
+                          int64_t K2, const void* const* bias, const void* const* norm_q, const void* const* norm_k,
+                          void* qkv_joint, void* const* prenorm_out, int64_t B, const int64_t* S, int64_t H,
+                          int64_t D, int64_t K, float eps, advgrpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * A8a preprocessing: the reward image path of adv_grpo/rewards.py:581-584 +

@@ -84,3 +84,51 @@ def test_dino_head_reward_and_hinge_loss_shapes():
     assert torch.allclose(hybrid, 0.7 * cls_s + 0.3 * patch_s.mean(1))
     loss, acc = dino_o.hinge_d_loss(hp, feats, feats.flip(0), idx, idx)
     assert loss.dim() == 0 and 0 <= acc <= 1
+
+
+def test_vae_decoder_oracle_matches_flux_autoencoder():
+    """torchtitan's FLUX autoencoder (installed here) is the same LDM decoder family as
+    the SD3 VAE (GroupNorm(32, eps 1e-6) + swish resnets, single-head mid attention, nearest-2x upsample).
+    Map the oracle's diffusers-named weights onto it (the standard LDM <-> diffusers key conversion) and
+    compare the decoder outputs."""
+    import pytest
+    ae = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    from adv_grpo_b200 import weights
+    from oracle import vae as vae_o
+    cfg = dict(latent_channels=16, block_out=(32, 64, 128, 128), layers_per_block=2)
+    p = weights.init_vae_decoder(cfg, seed=3, device="cpu")
+    dec = ae.Decoder(ch=32, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, in_channels=3, resolution=64,
+                     z_channels=16).eval()
+    sd = {}
+
+    def put(dst, src, conv1x1=False):
+        for s in ("weight", "bias"):
+            v = p[f"decoder.{src}.{s}"]
+            sd[f"{dst}.{s}"] = v[:, :, None, None] if (conv1x1 and s == "weight" and v.dim() == 2) else v
+
+    def resnet(dst, src):
+        for n in ("norm1", "conv1", "norm2", "conv2"):
+            put(f"{dst}.{n}", f"{src}.{n}")
+        if f"decoder.{src}.conv_shortcut.weight" in p:
+            put(f"{dst}.nin_shortcut", f"{src}.conv_shortcut")
+
+    put("conv_in", "conv_in")
+    resnet("mid.block_1", "mid_block.resnets.0")
+    resnet("mid.block_2", "mid_block.resnets.1")
+    put("mid.attn_1.norm", "mid_block.attentions.0.group_norm")
+    for a, b in (("q", "to_q"), ("k", "to_k"), ("v", "to_v"), ("proj_out", "to_out.0")):
+        put(f"mid.attn_1.{a}", f"mid_block.attentions.0.{b}", conv1x1=True)
+    for i in range(4):                       # diffusers up_blocks.i (coarse -> fine) = LDM up[3 - i]
+        for j in range(3):
+            resnet(f"up.{3 - i}.block.{j}", f"up_blocks.{i}.resnets.{j}")
+        if i < 3:
+            put(f"up.{3 - i}.upsample.conv", f"up_blocks.{i}.upsamplers.0.conv")
+    put("norm_out", "conv_norm_out")
+    put("conv_out", "conv_out")
+    missing, unexpected = dec.load_state_dict(sd, strict=True)
+    z = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = dec(z)
+        got = vae_o.vae_decode(p, z)
+    assert got.shape == ref.shape == (2, 3, 64, 64)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), (got - ref).abs().max()

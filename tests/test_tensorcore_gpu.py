@@ -239,3 +239,54 @@ def test_gemm_epilogue_staging_ring_ragged(ops, variant, M, N, K):
         assert _rel_err(y, ref) < 6e-3
     finally:
         ops.set_gemm_variant(0)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("B,S_img,S_txt,H", [(2, 1024, 205, 24), (3, 64, 13, 4), (16, 256, 205, 24), (2, 300, 0, 4),
+                                             (5, 100, 77, 4)])
+def test_gemm_qkv_norm_fused_epilogue_bit_exact(ops, variant, B, S_img, S_txt, H):
+    """Fused QKV projection + per-head q/k RMSNorm + [image, text] concat (one launch, clipped 3-D TMA stores into
+    the joint buffer) == dual GEMM followed by qk_norm_concat, bit for bit; also vs an fp32 torch reference."""
+    g = torch.Generator(device=DEV).manual_seed(B + S_img + S_txt)
+    K, D, R = 256, 64, 64
+    N = 3 * H * D
+    x = torch.randn(B, S_img, K, device=DEV, generator=g).bfloat16()
+    c = torch.randn(B, S_txt, K, device=DEV, generator=g).bfloat16() if S_txt else None
+    w = [(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16() for _ in range(2)]
+    bias = [torch.randn(N, device=DEV, generator=g).bfloat16() for _ in range(2)]
+    nq = [(1 + 0.2 * torch.randn(D, device=DEV, generator=g)).bfloat16() for _ in range(2)]
+    nk = [(1 + 0.2 * torch.randn(D, device=DEV, generator=g)).bfloat16() for _ in range(2)]
+    a2 = [torch.randn(B, s, R, device=DEV, generator=g).bfloat16() for s in (S_img, S_txt)]
+    w2 = [(0.1 * torch.randn(N, R, device=DEV, generator=g)).bfloat16() for _ in range(2)]
+    ops.set_gemm_variant(variant)
+    try:
+        for lora in (False, True):
+            kw = dict(a2=tuple(a2), w2=tuple(w2)) if lora else {}
+            pre = [torch.full((B * s, N), float("nan"), device=DEV, dtype=torch.bfloat16) for s in (S_img, S_txt)]
+            if S_txt:
+                joint = ops.gemm_qkv_norm(x, c, w, bias, nq, nk, H, D, prenorm_out=tuple(pre), **kw)
+                joint_np = ops.gemm_qkv_norm(x, c, w, bias, nq, nk, H, D, **kw)
+                qx, qc = ops.gemm_dual((x, c), w, bias=bias, **kw)
+                ref = ops.qk_norm_concat(qx, qc, nq[0], nk[0], nq[1], nk[1], H, D)
+            else:
+                kw1 = dict(a2=(a2[0],), w2=(w2[0],)) if lora else {}
+                joint = ops.gemm_qkv_norm(x, None, w[:1], bias[:1], nq[:1], nk[:1], H, D, prenorm_out=(pre[0],), **kw1)
+                joint_np = ops.gemm_qkv_norm(x, None, w[:1], bias[:1], nq[:1], nk[:1], H, D, **kw1)
+                qx, qc = ops.gemm(x, w[0], bias=bias[0], **({"a2": a2[0], "w2": w2[0]} if lora else {})), None
+                ref = ops.qk_norm_concat(qx, None, nq[0], nk[0], None, None, H, D)
+            assert joint.shape == (B, S_img + S_txt, 3, H, D)
+            assert torch.equal(joint, ref) and torch.equal(joint_np, ref)
+            assert torch.equal(pre[0].reshape(qx.shape), qx)
+            if S_txt:
+                assert torch.equal(pre[1].reshape(qc.shape), qc)
+            # fp32 reference of the same op on the image stream
+            z = x.float().reshape(-1, K) @ w[0].float().T + bias[0].float()
+            if lora:
+                z = z + a2[0].float().reshape(-1, R) @ w2[0].float().T
+            z = z.reshape(B, S_img, 3, H, D)
+            rn = torch.rsqrt(z[:, :, :2].pow(2).mean(-1, keepdim=True) + 1e-6)
+            wn = torch.stack([nq[0].float(), nk[0].float()])[None, None, :, None, :]
+            zr = torch.cat([z[:, :, :2] * rn * wn, z[:, :, 2:]], 2)
+            assert _rel_err(joint[:, :S_img], zr) < 1.2e-2
+    finally:
+        ops.set_gemm_variant(0)
