@@ -58,6 +58,7 @@ struct Params {
   int S, H, S_split;
   float scale_log2;     // softmax scale * log2(e)
   int causal;
+  int park;             // bit 0: MMA warp waits parked, bit 1: softmax S waits parked (experiment switches)
 };
 
 // 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, rel. err 7.5e-5): used for
@@ -92,8 +93,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* bar_q_full = bars;                  // 1
   uint64_t* bar_k_full = bars + 1;              // STAGES
   uint64_t* bar_v_full = bar_k_full + STAGES;   // STAGES
-  uint64_t* bar_kv_empty = bar_v_full + STAGES; // STAGES
-  uint64_t* bar_s_full = bar_kv_empty + STAGES; // NQ
+  uint64_t* bar_k_empty = bar_v_full + STAGES;  // STAGES   K(j) is free once QK(j) completed (long before PV(j))
+  uint64_t* bar_v_empty = bar_k_empty + STAGES; // STAGES   V(j) is free once PV(j) completed
+  uint64_t* bar_s_full = bar_v_empty + STAGES;  // NQ
   uint64_t* bar_p_full = bar_s_full + NQ;       // NQ
   uint64_t* bar_pv_done = bar_p_full + NQ;      // NQ
   uint64_t* bar_s_free = bar_pv_done + NQ;      // NQ   softmax has S in registers: QK(j+1) may overwrite it
@@ -120,7 +122,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&bar_k_full[i], 1);
       mbar_init(&bar_v_full[i], 1);
-      mbar_init(&bar_kv_empty[i], 1);
+      mbar_init(&bar_k_empty[i], 1);
+      mbar_init(&bar_v_empty[i], 1);
     }
     for (int i = 0; i < NQ; ++i) {
       mbar_init(&bar_s_full[i], 1);
@@ -150,17 +153,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         for (int hf = 0; hf < C::kHalves; ++hf)
           tma_load_4d(q_smem + q * C::kTileBytes + hf * (BQ * 128), &tmap, bar_q_full, hf * 64,
                       0 * p.H + h, q0 + q * BQ, b);
-      for (int j = 0; j < nkv; ++j) {
+      // K runs STAGES tiles ahead of the QK MMAs: its stage is released by QK(j) itself, so K(j + STAGES) is
+      // already in flight while the softmax of tile j is still running (a K stage released only after PV(j)
+      // left one softmax period for the whole L2 / HBM round trip and stalled S(j+1)); V follows one tile behind.
+      auto load_k = [&](int j) {
         const int st = j % STAGES;
-        mbar_wait(&bar_kv_empty[st], ((j / STAGES) & 1) ^ 1);
         mbar_expect_tx(&bar_k_full[st], C::kTileBytes);
         for (int hf = 0; hf < C::kHalves; ++hf)
           tma_load_4d(k_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_k_full[st],
                       hf * 64, 1 * p.H + h, j * BKV, b);
+      };
+      for (int j = 0; j < STAGES && j < nkv; ++j) load_k(j);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % STAGES;
+        mbar_wait_parked(&bar_v_empty[st], ((j / STAGES) & 1) ^ 1);
         mbar_expect_tx(&bar_v_full[st], C::kTileBytes);
         for (int hf = 0; hf < C::kHalves; ++hf)
           tma_load_4d(v_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_v_full[st],
                       hf * 64, 2 * p.H + h, j * BKV, b);
+        if (j + STAGES < nkv) {
+          mbar_wait_parked(&bar_k_empty[st], (j / STAGES) & 1);        // QK(j) done
+          load_k(j + STAGES);
+        }
       }
     }
   } else if (warp == C::kSoftmaxWarps + 1) {
@@ -190,33 +204,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                  (acc || k > 0) ? 1u : 0u);
         }
       };
-      mbar_wait(bar_q_full, 0);
-      mbar_wait(&bar_k_full[0], 0);
+      const bool pk = p.park & 1;
+      auto wait = [&](uint64_t* bar, uint32_t par) { if (pk) mbar_wait_parked(bar, par); else mbar_wait(bar, par); };
+      wait(bar_q_full, 0);
+      wait(&bar_k_full[0], 0);
       tc_fence_after();
       for (int q = 0; q < NQ; ++q) {
         issue_qk(q, 0);
         mma_commit(&bar_s_full[q]);
       }
+      mma_commit(&bar_k_empty[0]);
       for (int j = 0; j < nkv; ++j) {
         const int st = j % STAGES;
         if (j + 1 < nkv) {
           const int st1 = (j + 1) % STAGES;
           for (int q = 0; q < NQ; ++q) {
-            mbar_wait(&bar_s_free[q], j & 1);           // S(j) is in the softmax warps' registers
-            if (q == 0) mbar_wait(&bar_k_full[st1], ((j + 1) / STAGES) & 1);
+            wait(&bar_s_free[q], j & 1);           // S(j) is in the softmax warps' registers
+            if (q == 0) wait(&bar_k_full[st1], ((j + 1) / STAGES) & 1);
             tc_fence_after();
             issue_qk(q, st1);
             mma_commit(&bar_s_full[q]);
           }
+          mma_commit(&bar_k_empty[st1]);
         }
         for (int q = 0; q < NQ; ++q) {
-          mbar_wait(&bar_p_full[q], j & 1);
-          if (q == 0) mbar_wait(&bar_v_full[st], (j / STAGES) & 1);
+          wait(&bar_p_full[q], j & 1);
+          if (q == 0) wait(&bar_v_full[st], (j / STAGES) & 1);
           tc_fence_after();
           issue_pv(q, st, j > 0);
           mma_commit(&bar_pv_done[q]);
         }
-        mma_commit(&bar_kv_empty[st]);
+        mma_commit(&bar_v_empty[st]);
       }
     }
   }
@@ -241,7 +259,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     float m = -INFINITY;   // running max (scaled, log2 domain)
     float l = 0.f;         // running denominator (this thread's column slice)
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&bar_s_full[q], j & 1);
+      if (p.park & 2) mbar_wait_parked(&bar_s_full[q], j & 1); else mbar_wait(&bar_s_full[q], j & 1);
       tc_fence_after();
       const int kv0 = j * BKV + half * CPT;         // first kv index of my column slice
       // columns >= lim (relative to my slice) are masked out
@@ -377,9 +395,375 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant (default): one CTA per SM slot walks a static round-robin list of (query tile, head, sample)
+// work items.  All pipelines (Q double buffer, K / V rings, S / P / O in TMEM) run on global tile counters, so the
+// Q + first K loads and the first QK MMA of item n+1 are issued while the softmax warps are still finishing and
+// writing out item n: the per-CTA prologue (tensor-map fetch, TMEM allocation, Q/K round trip) and the epilogue
+// no longer idle the SM between 10-tile work items.
+template <int D>
+struct PCfg {
+  static constexpr int kHalves = D / 64;
+  static constexpr int kTileBytes = BQ * D * 2;
+  static constexpr int kSmemTiles = 2 * kTileBytes + STAGES * 2 * kTileBytes;   // 2 Q buffers + K ring + V ring
+  static constexpr int kSmemBytes = kSmemTiles + 1024 + 256;
+  static constexpr int kColsPerQ = 128 + 64 + D;
+  static constexpr int kTmemCols = (kColsPerQ <= 256) ? 256 : 512;
+  static constexpr int kThreads = 256;
+  static constexpr bool kRebalance = (D == 64);
+};
+
+template <int D, int EMU>
+__global__ void __launch_bounds__(256, (D == 64) ? 2 : 1)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p, const int n_items, const int nqt) {
+  using C = PCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                                   // 2 tiles
+  uint8_t* k_smem = smem + 2 * C::kTileBytes;               // STAGES tiles
+  uint8_t* v_smem = k_smem + STAGES * C::kTileBytes;        // STAGES tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemTiles);
+  uint64_t* bar_q_full = bars;                   // 2
+  uint64_t* bar_q_empty = bars + 2;              // 2
+  uint64_t* bar_k_full = bars + 4;               // STAGES
+  uint64_t* bar_v_full = bar_k_full + STAGES;    // STAGES
+  uint64_t* bar_k_empty = bar_v_full + STAGES;   // STAGES
+  uint64_t* bar_v_empty = bar_k_empty + STAGES;  // STAGES
+  uint64_t* bar_s_full = bar_v_empty + STAGES;   // 1
+  uint64_t* bar_p_full = bar_s_full + 1;         // 1
+  uint64_t* bar_pv_done = bar_p_full + 1;        // 1
+  uint64_t* bar_s_free = bar_pv_done + 1;        // 1
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_s_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.S;
+  const int H = p.H;
+
+  // item -> (query tile, head, sample) and its number of K/V tiles
+  auto item_q0 = [&](int it) { return (it % nqt) * BQ; };
+  auto item_h = [&](int it) { return (it / nqt) % H; };
+  auto item_b = [&](int it) { return it / (nqt * H); };
+  auto item_nkv = [&](int it) {
+    int kv_len = S;
+    if (p.causal) {
+      const int qend = item_q0(it) + BQ;
+      kv_len = qend < S ? qend : S;
+    }
+    return (kv_len + BKV - 1) / BKV;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q_full[i], 1);
+      mbar_init(&bar_q_empty[i], 1);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&bar_k_full[i], 1);
+      mbar_init(&bar_v_full[i], 1);
+      mbar_init(&bar_k_empty[i], 1);
+      mbar_init(&bar_v_empty[i], 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_p_full, 128);
+    mbar_init(bar_pv_done, 1);
+    mbar_init(bar_s_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_base_smem, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp >= 4) {
+    if constexpr (C::kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+    if (warp == 4) {
+      // ============================== TMA producer ==============================
+      if (lane == 0) {
+        prefetch_tmap(&tmap);
+        // K cursor (runs STAGES tiles ahead, loads the Q tile when it enters a new item) and V cursor
+        int k_item = blockIdx.x, k_j = 0, k_n = 0, k_g = 0;          // item, tile in item, local item index, global tile
+        int k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+        auto advance_k = [&]() {
+          if (k_item >= n_items) return;
+          if (k_j == 0) {
+            const int qb = k_n & 1;
+            mbar_wait_parked(&bar_q_empty[qb], ((k_n >> 1) & 1) ^ 1);
+            mbar_expect_tx(&bar_q_full[qb], C::kTileBytes);
+            for (int hf = 0; hf < C::kHalves; ++hf)
+              tma_load_4d(q_smem + qb * C::kTileBytes + hf * (BQ * 128), &tmap, &bar_q_full[qb], hf * 64,
+                          0 * H + item_h(k_item), item_q0(k_item), item_b(k_item));
+          }
+          const int st = k_g % STAGES;
+          mbar_wait_parked(&bar_k_empty[st], ((k_g / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&bar_k_full[st], C::kTileBytes);
+          for (int hf = 0; hf < C::kHalves; ++hf)
+            tma_load_4d(k_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_k_full[st], hf * 64,
+                        1 * H + item_h(k_item), k_j * BKV, item_b(k_item));
+          ++k_g;
+          if (++k_j == k_nkv) {
+            k_j = 0;
+            ++k_n;
+            k_item += gridDim.x;
+            k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+          }
+        };
+        for (int i = 0; i < STAGES; ++i) advance_k();
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
+          for (int j = 0; j < nkv; ++j, ++g) {
+            const int st = g % STAGES;
+            mbar_wait_parked(&bar_v_empty[st], ((g / STAGES) & 1) ^ 1);
+            mbar_expect_tx(&bar_v_full[st], C::kTileBytes);
+            for (int hf = 0; hf < C::kHalves; ++hf)
+              tma_load_4d(v_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_v_full[st], hf * 64,
+                          2 * H + h, j * BKV, b);
+            advance_k();
+          }
+        }
+      }
+    } else if (warp == 5) {
+      // ============================== MMA issuer ==============================
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+        const uint64_t q_d0 = make_smem_desc_sw128(smem_u32(q_smem), 16, 1024);
+        const uint64_t k_d0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);
+        const uint64_t v_d0 = make_smem_desc_sw128(smem_u32(v_smem), BKV * 128, 1024);
+        const uint32_t s_tmem = tmem_base, p_tmem = tmem_base + 128, o_tmem = tmem_base + 192;
+        auto issue_qk = [&](int qb, int st) {
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = ((k / 4) * (BQ * 128) + (k % 4) * 32) >> 4;
+            mma_ss(s_tmem, q_d0 + (uint64_t)(qb * (C::kTileBytes >> 4) + off),
+                   k_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + off), idesc_qk, k > 0);
+          }
+        };
+        auto issue_pv = [&](int st, bool acc) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            mma_ts(o_tmem, p_tmem + k * 8, v_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + k * 128), idesc_pv,
+                   (acc || k > 0) ? 1u : 0u);
+        };
+        // QK cursor: one tile ahead of the PV cursor
+        int q_item = blockIdx.x, q_j = 0, q_n = 0, q_g = 0;
+        int q_nkv = q_item < n_items ? item_nkv(q_item) : 0;
+        auto advance_qk = [&]() {
+          if (q_item >= n_items) return;
+          const int qb = q_n & 1;
+          if (q_g > 0) mbar_wait(bar_s_free, (q_g - 1) & 1);          // S(g-1) is in the softmax warps' registers
+          if (q_j == 0) mbar_wait(&bar_q_full[qb], (q_n >> 1) & 1);
+          const int st = q_g % STAGES;
+          mbar_wait(&bar_k_full[st], (q_g / STAGES) & 1);
+          tc_fence_after();
+          issue_qk(qb, st);
+          mma_commit(bar_s_full);
+          mma_commit(&bar_k_empty[st]);
+          ++q_g;
+          if (++q_j == q_nkv) {
+            mma_commit(&bar_q_empty[qb]);                              // last QK of the item read the Q tile
+            q_j = 0;
+            ++q_n;
+            q_item += gridDim.x;
+            q_nkv = q_item < n_items ? item_nkv(q_item) : 0;
+          }
+        };
+        advance_qk();
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int nkv = item_nkv(item);
+          for (int j = 0; j < nkv; ++j, ++g) {
+            advance_qk();                                              // S(g+1), possibly of the next item
+            const int st = g % STAGES;
+            mbar_wait(bar_p_full, g & 1);
+            mbar_wait(&bar_v_full[st], (g / STAGES) & 1);
+            tc_fence_after();
+            issue_pv(st, j > 0);
+            mma_commit(bar_pv_done);
+            mma_commit(&bar_v_empty[st]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== softmax / epilogue ==============================
+    if constexpr (C::kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
+    const int row = warp * 32 + lane;               // row inside the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_addr;
+    const uint32_t p_tmem = tmem_base + 128 + lane_addr;
+    const uint32_t o_tmem = tmem_base + 192 + lane_addr;
+    const float sl2 = p.scale_log2;
+    int g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
+      const int q_idx = item_q0(item) + row;
+      float m = -INFINITY;   // running max (scaled, log2 domain)
+      float l = 0.f;         // running denominator
+      for (int j = 0; j < nkv; ++j, ++g) {
+        mbar_wait(bar_s_full, g & 1);
+        tc_fence_after();
+        const int kv0 = j * BKV;
+        int lim = S - kv0;
+        if (p.causal) {
+          const int c = q_idx - kv0 + 1;
+          lim = c < lim ? c : lim;
+        }
+        const bool need_mask = lim < 128;
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(bar_s_free);
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= lim) sv[c][i] = 0xff800000u;   // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            mx4[(i / 2) & 3] = fmaxf(mx4[(i / 2) & 3], fmaxf(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float m_new = fmaxf(m, mx * sl2);
+        if (m != -INFINITY && m_new - m <= kRescaleThreshold) m_new = m;   // lazy rescale
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = (m == -INFINITY) ? 1.f : ex2(m - m_use);
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_use, -m_use);
+        uint32_t pk[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+            float2 e;
+            if ((i / 2) % 4 < EMU) {
+              e = ex2_poly2(x);
+            } else {
+              e.x = ex2(x.x);
+              e.y = ex2(x.y);
+            }
+            sum2 = __fadd2_rn(sum2, e);
+            pk[c][i / 2] = pack_bf16(e.x, e.y);
+          }
+        }
+        // PV(g-1) reads P(g-1) from the columns P(g) overwrites; O may only be rescaled between PV(g-1) and PV(g).
+        // For the first tile of an item the epilogue of the previous item already consumed that phase.
+        if (j > 0) {
+          mbar_wait(bar_pv_done, (g - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t r[32];
+              tmem_ld32(o_tmem + c * 32, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st32(o_tmem + c * 32, r);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st16(p_tmem + c * 16, pk[c]);
+        l = l * alpha + (sum2.x + sum2.y);
+        m = m_new;
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_full);
+      }
+      // ---- epilogue: O / l -> bf16, token-major store (the MMA warp is already computing S of the next item) ----
+      mbar_wait(bar_pv_done, (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+      const bool valid = q_idx < S;
+      __nv_bfloat16* orow;
+      if (p.out2 == nullptr) orow = p.out + (((int64_t)b * S + q_idx) * H + h) * D;
+      else if (q_idx < p.S_split) orow = p.out + (((int64_t)b * p.S_split + q_idx) * H + h) * D;
+      else orow = p.out2 + (((int64_t)b * (S - p.S_split) + (q_idx - p.S_split)) * H + h) * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(o_tmem + c * 32, r);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(r[i + 0]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
+            v.y = pack_bf16(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+            v.z = pack_bf16(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
+            v.w = pack_bf16(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + i) = v;
+          }
+        }
+      }
+      tc_fence_before();      // O is in registers: orders the TMEM reads before the next item's PV(0) (after p_full)
+      if (valid && p.lse) {
+        const float mm = (m == -INFINITY) ? 0.f : m;
+        p.lse[((int64_t)b * H + h) * S + q_idx] = (mm + log2f(l)) * 0.6931471805599453f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int D, int EMU>
+int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
+                   float scale, int causal, cudaStream_t st) {
+  using C = PCfg<D>;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {(uint64_t)D, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+  const uint64_t strides[4] = {0, (uint64_t)D * 2, (uint64_t)(3 * H * D) * 2, (uint64_t)(S * 3 * H * D) * 2};
+  const uint32_t box[4] = {64, 1, BQ, 1};
+  int rc = make_tmap_bf16(&tmap, qkv, 4, dims, strides, box, true);
+  if (rc != ADVGRPO_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_persist_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  Params p;
+  p.out = (__nv_bfloat16*)out;
+  p.out2 = (__nv_bfloat16*)out2;
+  p.S_split = (int)S_split;
+  p.lse = lse;
+  p.S = (int)S;
+  p.H = (int)H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  p.park = 0;
+  const int nqt = (int)((S + BQ - 1) / BQ);
+  const int64_t items = (int64_t)nqt * H * B;
+  ADVGRPO_CHECK_ARG(items < (int64_t)1 << 30, "attn_fwd: too many work items");
+  const int per_sm = (D == 64) ? 2 : 1;
+  int grid = sm_count() * per_sm;
+  if (grid > items) grid = (int)items;
+  attn_fwd_persist_kernel<D, EMU><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p, (int)items, nqt);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
 template <int D, int NQ, int EMU, int RS = 1>
 int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H, float scale,
-           int causal, cudaStream_t st) {
+           int causal, cudaStream_t st, int park = 0) {
   using C = Cfg<D, NQ, RS>;
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)D, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
@@ -401,6 +785,7 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   p.H = (int)H;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  p.park = park;
   dim3 grid((unsigned)((S + BQ * NQ - 1) / (BQ * NQ)), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<D, NQ, EMU, RS><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
@@ -426,10 +811,15 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 8: return launch<64, 1, 1, 2>(ADVGRPO_ATTN_ARGS);
       case 9: return launch<64, 2, 0, 2>(ADVGRPO_ATTN_ARGS);
       case 10: return launch<64, 2, 1, 2>(ADVGRPO_ATTN_ARGS);
-      default: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
+      case 11: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS, 1);
+      case 12: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS, 2);
+      case 13: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS, 3);
+      case 14: return launch_persist<64, 0>(ADVGRPO_ATTN_ARGS);
+      case 15: return launch_persist<64, 2>(ADVGRPO_ATTN_ARGS);
+      default: return launch_persist<64, 1>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
     }
   }
-  if (D == 128) return launch<128, 1, 0>(ADVGRPO_ATTN_ARGS);
+  if (D == 128) return variant == 1 ? launch<128, 1, 0>(ADVGRPO_ATTN_ARGS) : launch_persist<128, 0>(ADVGRPO_ATTN_ARGS);
   return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_fwd: head_dim %lld not in {64, 128}", (long long)D);
 }
 

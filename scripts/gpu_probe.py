@@ -145,7 +145,7 @@ def probe_perf():
     B, S, H, D = 16, 1229, 24, 64
     qkv = torch.randn(B, S, 3, H, D, device="cuda").bfloat16()
     flops = 4 * B * H * S * S * D
-    for variant in (1, 3, 4, 7, 8, 9, 10):
+    for variant in (3, 0, 14, 15):
         for _ in range(3):
             ops.attention_fwd(qkv, variant=variant, want_lse=False)
         torch.cuda.synchronize()
