@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kThreads) sde_fwd_kernel(FwdArgs a) {
 struct BwdArgs {
   const __nv_bfloat16 *vu, *vt, *x, *prev_in;
   const float *timesteps, *sched_t, *sigmas, *grad_lp;
+  const float *grad_kl, *mean_ref;     // KL term of train_sd3_fast_pickscore.py:1124-1128 (both NULL when beta == 0)
   int64_t t_count;
   int T;
   __nv_bfloat16 *gvu, *gvt;
@@ -195,6 +196,8 @@ __global__ void __launch_bounds__(kThreads) sde_bwd_kernel(BwdArgs a) {
   // d mu / d v = (1 - sigma) c - sigma (1 - sigma')
   const float dmu_dv = k.one_m_sigma * k.c - k.sigma * k.one_m_sigma_prev;
   const float coef = a.grad_lp[b] * (2.0f / (float)a.n) * dmu_dv;
+  // kl[b] = mean((mu - mu_ref)^2):  d kl[b] / d v = (2/n) (mu - mu_ref) d mu / d v
+  const float coef_kl = a.mean_ref ? a.grad_kl[b] * (2.0f / (float)a.n) * dmu_dv : 0.f;
   const int64_t base = (int64_t)b * a.n;
   const int64_t nvec = a.n / kVec;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec;
@@ -209,10 +212,19 @@ __global__ void __launch_bounds__(kThreads) sde_bwd_kernel(BwdArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) vt[j] = cfg_bf16(vu[j], vt[j], a.guidance);
     }
+    float mr[8];
+    if (a.mean_ref) {
+      const float4 m0 = *reinterpret_cast<const float4*>(a.mean_ref + e);
+      const float4 m1 = *reinterpret_cast<const float4*>(a.mean_ref + e + 4);
+      mr[0] = m0.x; mr[1] = m0.y; mr[2] = m0.z; mr[3] = m0.w;
+      mr[4] = m1.x; mr[5] = m1.y; mr[6] = m1.z; mr[7] = m1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float mu = mean_of(x[j], vt[j], k);
-      float g = bf16_round(coef * (pv[j] - mu));   // grad at noise_pred (bf16 tensor)
+      float gf = coef * (pv[j] - mu);
+      if (a.mean_ref) gf = fmaf(coef_kl, mu - mr[j], gf);
+      float g = bf16_round(gf);                     // grad at noise_pred (bf16 tensor)
       if (a.vu) {
         float gd = bf16_round(a.guidance * g);      // through e = g * d
         gt[j] = gd;                                 // d = t - u
@@ -293,6 +305,19 @@ int advgrpo_cfg_sde_logprob_bwd(const void* v_uncond, const void* v_text, const 
                                 const float* grad_log_prob, void* grad_v_uncond, void* grad_v_text,
                                 int64_t B, int64_t n, float guidance, float noise_level,
                                 advgrpo_stream_t stream) {
+  return advgrpo_cfg_sde_logprob_kl_bwd(v_uncond, v_text, x, prev_in, timesteps, t_count, sched_timesteps, sigmas, T,
+                                        grad_log_prob, nullptr, nullptr, grad_v_uncond, grad_v_text, B, n, guidance,
+                                        noise_level, stream);
+}
+
+int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, const void* x,
+                                   const void* prev_in, const float* timesteps, int64_t t_count,
+                                   const float* sched_timesteps, const float* sigmas, int64_t T,
+                                   const float* grad_log_prob, const float* grad_kl, const float* mean_ref,
+                                   void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
+                                   float noise_level, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG((grad_kl == nullptr) == (mean_ref == nullptr), "cfg_sde_logprob_kl_bwd: grad_kl and mean_ref go together");
+  ADVGRPO_CHECK_ARG(!mean_ref || aligned16(mean_ref), "cfg_sde_logprob_kl_bwd: mean_ref must be 16-byte aligned");
   ADVGRPO_CHECK_ARG(v_text && x && prev_in && timesteps && sched_timesteps && sigmas &&
                         grad_log_prob && grad_v_text,
                     "cfg_sde_logprob_bwd: null required pointer");
@@ -306,6 +331,7 @@ int advgrpo_cfg_sde_logprob_bwd(const void* v_uncond, const void* v_text, const 
   a.vu = (const __nv_bfloat16*)v_uncond; a.vt = (const __nv_bfloat16*)v_text;
   a.x = (const __nv_bfloat16*)x; a.prev_in = (const __nv_bfloat16*)prev_in;
   a.timesteps = timesteps; a.sched_t = sched_timesteps; a.sigmas = sigmas; a.grad_lp = grad_log_prob;
+  a.grad_kl = grad_kl; a.mean_ref = mean_ref;
   a.t_count = t_count; a.T = (int)T; a.gvu = (__nv_bfloat16*)grad_v_uncond;
   a.gvt = (__nv_bfloat16*)grad_v_text; a.n = n; a.guidance = guidance;
   a.sin_level = (float)sin((double)noise_level * M_PI / 2.0);

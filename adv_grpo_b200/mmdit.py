@@ -293,6 +293,17 @@ class SD3Transformer2DModel(torch.nn.Module):
             out[f"base_model.model.{name}.lora_B.weight"] = self.lora_B[key].detach()
         return out
 
+    def save_pretrained(self, path):
+        """peft adapter directory (`adapter_config.json` + `adapter_model.safetensors`), as `save_ckpt` of
+        `train_sd3_fast_pickscore.py:389-398` writes it."""
+        from .checkpoint import save_lora
+        save_lora(self, path)
+
+    def load_adapter(self, path, strict=True):
+        """`PeftModel.from_pretrained(transformer, config.train.lora_path)` (`train_pick:506-509`)."""
+        from .checkpoint import load_lora
+        return load_lora(self, path, strict=strict)
+
     def invalidate_lora_cache(self):
         """Call after an optimizer step / EMA swap changed the LoRA parameters."""
         self._lora_dirty = True

@@ -83,11 +83,13 @@ def cfg_sde_step_logprob(v_uncond, v_text, x, timesteps, sched_timesteps, sigmas
 
 class _SdeLogProbReplay(torch.autograd.Function):
     """log_prob of a stored transition under the current model output; differentiable w.r.t.
-    the (CFG-batched) transformer output (train_sd3_fast_pickscore.py:233-267)."""
+    the (CFG-batched) transformer output (train_sd3_fast_pickscore.py:233-267).  With `mean_ref`
+    (prev_sample_mean of the adapter-disabled forward) it also returns the per-sample KL regulariser
+    kl[b] = mean((mu - mu_ref)^2) of train_sd3_fast_pickscore.py:1124-1128, differentiable as well."""
 
     @staticmethod
     def forward(ctx, noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
-                noise_level, cfg, want_mean):
+                noise_level, cfg, want_mean, mean_ref):
         noise_pred = _bf16c(noise_pred)
         if cfg:
             vu, vt = noise_pred.chunk(2)
@@ -95,18 +97,22 @@ class _SdeLogProbReplay(torch.autograd.Function):
             vu, vt = None, noise_pred
         _, logp, mean, std = cfg_sde_step_logprob(vu, vt, x, timesteps, sched_timesteps, sigmas,
                                                   guidance_scale, noise_level, prev_sample=prev_sample,
-                                                  want_mean=want_mean)
-        ctx.save_for_backward(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas)
+                                                  want_mean=want_mean or mean_ref is not None)
+        kl = torch.empty(0, device=x.device)
+        if mean_ref is not None:
+            mean_ref = mean_ref.to(torch.float32).contiguous()
+            kl = ((mean - mean_ref) ** 2).reshape(x.shape[0], -1).mean(1)
+        ctx.save_for_backward(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, mean_ref)
         ctx.meta = (float(guidance_scale), float(noise_level), bool(cfg))
         ctx.mark_non_differentiable(std)
         if mean is None:
             mean = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(mean)
-        return logp, mean, std
+        return logp, mean, std, kl
 
     @staticmethod
-    def backward(ctx, g_logp, _gm, _gs):
-        noise_pred, x, prev, timesteps, sched_t, sigmas = ctx.saved_tensors
+    def backward(ctx, g_logp, _gm, _gs, g_kl):
+        noise_pred, x, prev, timesteps, sched_t, sigmas, mean_ref = ctx.saved_tensors
         gs, nl, cfg = ctx.meta
         B = x.shape[0]
         n = x.numel() // B
@@ -119,21 +125,28 @@ class _SdeLogProbReplay(torch.autograd.Function):
             vu, vt, gvu, gvt = None, noise_pred, None, grad
         x, prev = _bf16c(x), _bf16c(prev)
         timesteps = timesteps.to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
-        g_logp = g_logp.to(torch.float32).contiguous()
-        _lib.call("advgrpo_cfg_sde_logprob_bwd", _ptr(vu), _ptr(vt), _ptr(x), _ptr(prev), _ptr(timesteps),
-                  timesteps.numel(), _ptr(sched_t), _ptr(sigmas), sched_t.numel(), _ptr(g_logp), _ptr(gvu),
-                  _ptr(gvt), B, n, gs, nl, _stream())
-        return grad, None, None, None, None, None, None, None, None, None
+        g_logp = (torch.zeros(B, device=dev) if g_logp is None else g_logp).to(torch.float32).contiguous()
+        if mean_ref is not None:
+            g_kl = (torch.zeros(B, device=dev) if g_kl is None else g_kl).to(torch.float32).contiguous()
+        else:
+            g_kl = None
+        _lib.call("advgrpo_cfg_sde_logprob_kl_bwd", _ptr(vu), _ptr(vt), _ptr(x), _ptr(prev), _ptr(timesteps),
+                  timesteps.numel(), _ptr(sched_t), _ptr(sigmas), sched_t.numel(), _ptr(g_logp), _ptr(g_kl),
+                  _ptr(mean_ref), _ptr(gvu), _ptr(gvt), B, n, gs, nl, _stream())
+        return grad, None, None, None, None, None, None, None, None, None, None
 
 
 def sde_logprob_replay(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
-                       noise_level, cfg=True, want_mean=False):
+                       noise_level, cfg=True, want_mean=False, mean_ref=None):
+    """Returns (log_prob, prev_sample_mean or None, std_dev_t), plus the per-sample KL term when `mean_ref` is given."""
     dev = x.device
     sched_timesteps = sched_timesteps.to(device=dev, dtype=torch.float32).contiguous()
     sigmas = sigmas.to(device=dev, dtype=torch.float32).contiguous()
-    logp, mean, std = _SdeLogProbReplay.apply(noise_pred, _bf16c(x), _bf16c(prev_sample), timesteps,
-                                              sched_timesteps, sigmas, guidance_scale, noise_level, cfg,
-                                              want_mean)
+    logp, mean, std, kl = _SdeLogProbReplay.apply(noise_pred, _bf16c(x), _bf16c(prev_sample), timesteps,
+                                                  sched_timesteps, sigmas, guidance_scale, noise_level, cfg,
+                                                  want_mean, mean_ref)
+    if mean_ref is not None:
+        return logp, (mean if want_mean else None), std, kl
     return logp, (mean if want_mean else None), std
 
 

@@ -60,8 +60,10 @@ def all_gather_cat(t):
     return out
 
 
-def compute_log_prob(transformer, pipeline, sample, j, embeds, pooled_embeds, config):
-    """`train_pick:233-267`: transformer forward on the CFG batch + fused CFG / Flow-CPS replay log-prob."""
+def compute_log_prob(transformer, pipeline, sample, j, embeds, pooled_embeds, config, mean_ref=None, want_mean=False):
+    """`train_pick:233-267`: transformer forward on the CFG batch + fused CFG / Flow-CPS replay log-prob.
+    With `mean_ref` (the adapter-disabled prev_sample_mean, `train_pick:1105-1108`) the last element of the
+    returned tuple is the per-sample KL term instead of std_dev_t's successor (5-tuple)."""
     lat = sample["latents"][:, j]
     ts = sample["timesteps"][:, j]
     cfg = bool(config.train.cfg)
@@ -71,9 +73,14 @@ def compute_log_prob(transformer, pipeline, sample, j, embeds, pooled_embeds, co
     else:
         noise_pred = transformer(hidden_states=lat, timestep=ts, encoder_hidden_states=embeds,
                                  pooled_projections=pooled_embeds, return_dict=False)[0]
-    log_prob, mean, std = ops.sde_logprob_replay(noise_pred, lat, sample["next_latents"][:, j], ts,
-                                                 pipeline.scheduler.timesteps, pipeline.scheduler.sigmas,
-                                                 config.sample.guidance_scale, config.sample.noise_level, cfg=cfg)
+    out = ops.sde_logprob_replay(noise_pred, lat, sample["next_latents"][:, j], ts,
+                                 pipeline.scheduler.timesteps, pipeline.scheduler.sigmas,
+                                 config.sample.guidance_scale, config.sample.noise_level, cfg=cfg,
+                                 want_mean=want_mean, mean_ref=mean_ref)
+    if mean_ref is not None:
+        log_prob, mean, std, kl = out
+        return sample["next_latents"][:, j], log_prob, mean, std, kl
+    log_prob, mean, std = out
     return sample["next_latents"][:, j], log_prob, mean, std
 
 
@@ -137,6 +144,8 @@ class GRPOTrainer:
         self.reference_image_fn = reference_image_fn or self._synthetic_reference
         self.sync_discriminator = sync_discriminator
         s, t = config.sample, config.train
+        if t.get("lora_path", None):                                       # resume, train_pick:506-509
+            self.transformer.load_adapter(t.lora_path)
         self.params = self.transformer.trainable_parameters()
         self.optimizer = torch.optim.AdamW(self.params, lr=t.learning_rate, betas=(t.adam_beta1, t.adam_beta2),
                                            weight_decay=t.adam_weight_decay, eps=t.adam_epsilon, fused=True)
@@ -308,7 +317,20 @@ class GRPOTrainer:
                 embeds, pooled = sample["prompt_embeds"], sample["pooled_prompt_embeds"]
             adv_i = advantages[i * n_local:(i + 1) * n_local]
             for j in range(T):
-                if self.micro_step is not None and t.cfg:
+                if t.beta > 0:
+                    # KL-regularised step (train_pick:1105-1108,1124-1128): reference mean from the adapter-disabled
+                    # forward, loss = policy_loss + beta * mean_b(mean_chw((mu - mu_ref)^2))
+                    with torch.no_grad(), self.transformer.disable_adapter():
+                        _, _, mean_ref, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c,
+                                                             want_mean=True)
+                    _, log_prob, _, _, kl = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c,
+                                                             mean_ref=mean_ref)
+                    loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
+                                                     t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
+                    kl_loss = kl.mean()
+                    (loss + (t.beta / gas) * kl_loss.to(loss.dtype)).backward()
+                    self.last_info["kl_loss"] = kl_loss.detach()
+                elif self.micro_step is not None and t.cfg:
                     stats = self.micro_step(sample["latents"][:, j].contiguous(), sample["next_latents"][:, j].contiguous(),
                                             sample["timesteps"][:, j].contiguous(), embeds, pooled,
                                             sample["log_probs"][:, j].contiguous(), adv_i[:, j].contiguous(), 1.0 / gas)
@@ -332,6 +354,13 @@ class GRPOTrainer:
             m = torch.stack(stats_acc).mean(0)
             self.last_info.update(loss=m[0], approx_kl=m[1], clipfrac=m[2], clipfrac_gt_one=m[3], clipfrac_lt_one=m[4],
                                   policy_loss=m[5])
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_ckpt(self, save_dir):
+        """`save_ckpt` (`train_pick:389-398`): peft adapter directory with the EMA weights swapped in, rank 0 only."""
+        from .checkpoint import save_ckpt
+        return save_ckpt(save_dir, self.transformer, self.global_step, ema=self.ema, trainable_parameters=self.params,
+                         use_ema=bool(self.config.train.ema), is_main_process=self.rank == 0)
 
     # ------------------------------------------------------------------ one epoch
     def run_epoch(self):

@@ -87,6 +87,17 @@ int advgrpo_cfg_sde_logprob_bwd(const void* v_uncond, const void* v_text, const 
                                 int64_t B, int64_t n, float guidance, float noise_level,
                                 advgrpo_stream_t stream);
 
+/* The same backward with the KL regulariser of train_sd3_fast_pickscore.py:1105-1108,1124-1128 (train.beta > 0):
+ *   kl[b] = mean_{CHW}((mu - mu_ref)^2), mu_ref = prev_sample_mean of the adapter-disabled forward (f32 [B, n]);
+ *   d kl[b] / d v = (2/n) (mu - mu_ref) d mu / d v is added with weight grad_kl[b] (f32 [B]).
+ * grad_kl == mean_ref == NULL reduces to advgrpo_cfg_sde_logprob_bwd. */
+int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, const void* x,
+                                   const void* prev_in, const float* timesteps, int64_t t_count,
+                                   const float* sched_timesteps, const float* sigmas, int64_t T,
+                                   const float* grad_log_prob, const float* grad_kl, const float* mean_ref,
+                                   void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
+                                   float noise_level, advgrpo_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * A9: group-relative advantage.  Replaces adv_grpo/stat_tracking.py:18-47
  * (PerPromptStatTracker.update, type='grpo') together with the prompt-identity

@@ -20,3 +20,11 @@ def grpo_clip_loss(log_prob, old_log_prob, advantages, clip_range, adv_clip_max)
         "policy_loss": policy_loss,
     }
     return policy_loss, info
+
+
+def kl_loss(prev_sample_mean, prev_sample_mean_ref):
+    """KL regulariser of the beta > 0 branch (`train_sd3_fast_pickscore.py:1124-1128`; the 1 / (2 std^2) factor is
+    commented out in the reference): mean over the batch of the per-sample mean squared distance between the
+    prev_sample_mean of the LoRA model and of the adapter-disabled model."""
+    kl = ((prev_sample_mean - prev_sample_mean_ref) ** 2).mean(dim=(1, 2, 3), keepdim=True)
+    return torch.mean(kl)

@@ -173,3 +173,66 @@ def test_two_rank_gloo_plumbing():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_lora_adapter_dir_roundtrip_peft_layout(tmp_path):
+    """§8f on-disk format: the peft adapter directory of `save_ckpt` (`train_pick:389-398`) / `lora_path` resume
+    (`:506-509`): key names, config fields, EMA swap, strictness.  CPU only (no kernels involved)."""
+    import json
+    from adv_grpo_b200 import checkpoint, weights
+    from adv_grpo_b200.ema import EMAModuleWrapper
+    from adv_grpo_b200.mmdit import SD3Transformer2DModel
+    cfg = weights.MMDIT_TINY
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    lora = weights.init_lora(cfg, rank=32, seed=1, perturb_b=0.02)
+    m = SD3Transformer2DModel(cfg, params, lora=lora, device="cpu")
+    d = tmp_path / "ckpt"
+    m.save_pretrained(str(d))
+    conf = json.load(open(d / "adapter_config.json"))
+    assert conf["peft_type"] == "LORA" and conf["r"] == 32 and conf["lora_alpha"] == 64
+    assert conf["target_modules"] == sorted(weights.LORA_TARGETS) and conf["init_lora_weights"] == "gaussian"
+    from safetensors.torch import load_file
+    sd = load_file(str(d / "adapter_model.safetensors"))
+    assert "base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight" in sd
+    assert sd["base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight"].shape == (32, cfg["heads"] * cfg["head_dim"])
+    assert sd["base_model.model.transformer_blocks.0.attn.to_out.0.lora_B.weight"].shape == (cfg["heads"] * cfg["head_dim"], 32)
+    assert all(k.startswith("base_model.model.transformer_blocks.") and ".default." not in k for k in sd)
+    # the context-pre-only last block has no to_add_out adapter
+    last = cfg["num_layers"] - 1
+    assert f"base_model.model.transformer_blocks.{last}.attn.to_add_out.lora_A.weight" not in sd
+    # load into a fresh model (different LoRA init) -> identical factors; in place (parameter objects survive)
+    m2 = SD3Transformer2DModel(cfg, params, lora=weights.init_lora(cfg, rank=32, seed=9, perturb_b=0.5), device="cpu")
+    ids = [id(p) for p in m2.trainable_parameters()]
+    missing, unexpected = m2.load_adapter(str(d))
+    assert not missing and not unexpected and ids == [id(p) for p in m2.trainable_parameters()]
+    for k, v in m.lora_state_dict().items():
+        assert torch.equal(v, m2.lora_state_dict()[k])
+    # keys carrying the adapter name (in-memory peft state dicts) are accepted too
+    from safetensors.torch import save_file
+    save_file({k.replace(".weight", ".default.weight"): v for k, v in sd.items()}, str(d / "adapter_model.safetensors"))
+    assert checkpoint.load_adapter_dir(str(d))[0].keys() == sd.keys()
+    # strictness and rank check
+    bad = dict(sd)
+    bad.pop("base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight")
+    checkpoint.save_adapter_dir(str(tmp_path / "bad"), bad, conf)
+    with pytest.raises(KeyError):
+        m2.load_adapter(str(tmp_path / "bad"))
+    checkpoint.save_adapter_dir(str(tmp_path / "r16"), sd, dict(conf, r=16))
+    with pytest.raises(ValueError):
+        m2.load_adapter(str(tmp_path / "r16"))
+    # save_ckpt: EMA weights are what lands on disk, the live weights come back afterwards
+    ps = m.trainable_parameters()
+    ema = EMAModuleWrapper(ps, decay=0.9, update_step_interval=1, device="cpu")
+    live = [p.detach().clone() for p in ps]
+    with torch.no_grad():
+        for p in ps:
+            p.add_(1.0)
+    moved = [p.detach().clone() for p in ps]
+    root = checkpoint.save_ckpt(str(tmp_path / "run"), m, 7, ema=ema, trainable_parameters=ps, use_ema=True)
+    assert root.endswith("checkpoints/checkpoint-7/lora")
+    on_disk, _ = checkpoint.load_adapter_dir(root)
+    k0 = "base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight"
+    assert torch.equal(on_disk[k0], live[0])                      # EMA shadow == the weights at wrapper creation
+    assert all(torch.equal(a, b) for a, b in zip(moved, ps))      # live weights restored
+    assert checkpoint.save_ckpt(str(tmp_path / "run2"), m, 1, is_main_process=False).endswith("lora")
+    assert not (tmp_path / "run2" / "checkpoints" / "checkpoint-1" / "lora" / "adapter_config.json").exists()

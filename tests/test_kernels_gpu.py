@@ -123,6 +123,47 @@ def test_sde_replay_backward_matches_autograd_of_oracle(ops, sched):
     assert cos > 0.9995
 
 
+def test_sde_replay_kl_term_matches_autograd_of_oracle(ops, sched):
+    """beta > 0 branch (train_pick:1105-1108,1124-1128): loss = sum_b w_b logp_b + beta * kl, kl from the oracle
+    restatement; value and gradient w.r.t. the CFG-batched transformer output."""
+    from oracle import grpo_loss as loss_o
+    B, shape = 4, (16, 16, 16)
+    g = torch.Generator().manual_seed(12)
+    npred = torch.randn(2 * B, *shape, generator=g).bfloat16()
+    x = torch.randn(B, *shape, generator=g).bfloat16()
+    prev = (x.float() + 0.3 * torch.randn(B, *shape, generator=g)).bfloat16()
+    mean_ref = x.float() + 0.2 * torch.randn(B, *shape, generator=g)
+    idx = [0, 3, 1, 5]
+    w = torch.randn(B, generator=g)
+    beta = 0.7
+    npo = npred.float().requires_grad_(True)
+    vu, vt = npo.chunk(2)
+    v = vu + 4.5 * (vt - vu)
+    _, lp_o, mean_o, _ = sde_o.sde_step_with_logprob_new(sched.sigmas, idx, v, x, 0.8, prev_sample=prev)
+    kl_o = loss_o.kl_loss(mean_o, mean_ref)
+    ((lp_o * w).sum() + beta * kl_o).backward()
+    npd = npred.to(DEV).requires_grad_(True)
+    lp, _, _, kl = ops.sde_logprob_replay(npd, x.to(DEV), prev.to(DEV), sched.timesteps[idx], sched.timesteps,
+                                          sched.sigmas, 4.5, 0.8, cfg=True, mean_ref=mean_ref.to(DEV))
+    assert kl.shape == (B,)
+    # forward value: mu carries the bf16 rounding of the CFG combine (the oracle's v is fp32 here)
+    assert torch.allclose(kl.mean().cpu(), kl_o.detach(), rtol=2e-2)
+    ((lp * w.to(DEV)).sum() + beta * kl.mean()).backward()
+    got, ref = npd.grad.float().cpu(), npo.grad
+    assert (got - ref).abs().max() <= 0.02 * ref.abs().max()
+    assert torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0) > 0.9995
+    # the KL gradient alone (no policy term)
+    npd2 = npred.to(DEV).requires_grad_(True)
+    _, _, _, kl2 = ops.sde_logprob_replay(npd2, x.to(DEV), prev.to(DEV), sched.timesteps[idx], sched.timesteps,
+                                          sched.sigmas, 4.5, 0.8, cfg=True, mean_ref=mean_ref.to(DEV))
+    kl2.mean().backward()
+    npo2 = npred.float().requires_grad_(True)
+    vu, vt = npo2.chunk(2)
+    _, _, mean_o2, _ = sde_o.sde_step_with_logprob_new(sched.sigmas, idx, vu + 4.5 * (vt - vu), x, 0.8, prev_sample=prev)
+    loss_o.kl_loss(mean_o2, mean_ref).backward()
+    assert torch.nn.functional.cosine_similarity(npd2.grad.float().cpu().flatten(), npo2.grad.flatten(), dim=0) > 0.9995
+
+
 # ------------------------------------------------------------------ A9 advantage
 def _keys_from_prompts(prompts, L=8):
     table = {}

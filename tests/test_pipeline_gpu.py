@@ -132,3 +132,29 @@ def test_grpo_epoch_smoke_pickscore_and_dino():
         assert seen_g or seen_d
         if seen_g:
             assert any(not torch.equal(a, b) for a, b in zip(before, tr.params))
+
+
+def test_grpo_epoch_with_kl_regulariser():
+    """train.beta > 0 (`train_pick:1105-1108,1124-1128`): the adapter-disabled reference forward + KL term run
+    through the eager micro-step; with the LoRA B matrices at zero the model equals its reference, so kl == 0,
+    and after perturbing B the KL is positive and changes the gradients."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.config import load_config
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from adv_grpo_b200.trainer import GRPOTrainer
+    pipe, cfg, *_ = _tiny_pipeline(True)
+    c = load_config("pickscore_cotrain_sd3_fast")
+    c.resolution, c.sample.num_steps, c.sample.mini_num_image_per_prompt = 128, 4, 2
+    c.sample.num_batches_per_epoch, c.train.gradient_accumulation_steps, c.train_d = 1, 1, False
+    c.train.beta = 0.5
+    tr = GRPOTrainer(c, pipe, [f"prompt {i}" for i in range(5)], scorer=PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY),
+                     device=DEV)
+    info = tr.run_epoch()
+    assert torch.isfinite(info["loss"]) and torch.isfinite(info["kl_loss"])
+    assert float(info["kl_loss"]) > 0.0           # _tiny_pipeline perturbs lora_B, so the adapter changes the mean
+    with torch.no_grad():
+        for p in tr.transformer.lora_B.values():
+            p.zero_()
+    tr.transformer.invalidate_lora_cache()
+    info = tr.run_epoch()
+    assert float(info["kl_loss"]) == 0.0          # adapter == identity -> mu == mu_ref exactly (same fused forward)
