@@ -4,7 +4,7 @@ advantage -> update hot path behind the reference's own Python surface.
 `install_as_adv_grpo()` registers this package's modules under the reference's import names
 (`adv_grpo.rewards`, `adv_grpo.stat_tracking`, `adv_grpo.ema`, `adv_grpo.pickscore_scorer`,
 `adv_grpo.pick_score_training`, `adv_grpo.diffusers_patch.sd3_sde_with_logprob`,
-`adv_grpo.diffusers_patch.sd3_pipeline_with_logprob_fast`) so that
+`adv_grpo.diffusers_patch.sd3_pipeline_with_logprob_fast`, `adv_grpo.diffusers_patch.train_dreambooth_lora_sd3`) so that
 `scripts/train_sd3_fast_{pickscore,dino_patch}.py` import the B200 path unchanged.
 """
 import importlib
@@ -23,6 +23,7 @@ _ALIASES = {
     "adv_grpo.diffusers_patch.sd3_sde_with_logprob": "adv_grpo_b200.diffusers_patch.sd3_sde_with_logprob",
     "adv_grpo.diffusers_patch.sd3_pipeline_with_logprob_fast":
         "adv_grpo_b200.diffusers_patch.sd3_pipeline_with_logprob_fast",
+    "adv_grpo.diffusers_patch.train_dreambooth_lora_sd3": "adv_grpo_b200.diffusers_patch.train_dreambooth_lora_sd3",
 }
 
 

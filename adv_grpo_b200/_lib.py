@@ -33,6 +33,7 @@ SIGNATURES = {
     "advgrpo_qk_norm_concat_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64,
                                            _I64, _F, _P]),
     "advgrpo_attn_fwd": (c_int, [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, _F, _I, _P]),
+    "advgrpo_attn_fwd_bias": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _P]),
     "advgrpo_attn_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P, _SZ, _P]),
     "advgrpo_gemm_bf16": (c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _I64,

@@ -59,6 +59,7 @@ struct Params {
   float scale_log2;     // softmax scale * log2(e)
   int causal;
   int park;             // bit 0: MMA warp waits parked, bit 1: softmax S waits parked (experiment switches)
+  const float* bias;    // optional additive score bias [H, S, S] (T5 relative positions); persistent kernel only
 };
 
 // 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, rel. err 7.5e-5): used for
@@ -598,7 +599,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
     const uint32_t s_tmem = tmem_base + lane_addr;
     const uint32_t p_tmem = tmem_base + 128 + lane_addr;
     const uint32_t o_tmem = tmem_base + 192 + lane_addr;
-    const float sl2 = p.scale_log2;
+    const float sl2 = p.bias ? 1.0f : p.scale_log2;   // with a bias the scores are moved to the log2 domain first
     int g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
@@ -621,6 +622,16 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(bar_s_free);
+        if (p.bias) {
+          // t = s * scale * log2(e) + bias * log2(e): this thread's row of the [S, S] bias plane of head h
+          const float* brow = p.bias + ((int64_t)h * S + (q_idx < S ? q_idx : S - 1)) * S + kv0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < lim)
+                sv[c][i] = __float_as_uint(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, brow[c * 32 + i] * 1.4426950408889634f));
+        }
         if (need_mask) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -727,7 +738,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
 
 template <int D, int EMU>
 int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
-                   float scale, int causal, cudaStream_t st) {
+                   float scale, int causal, cudaStream_t st, const float* bias = nullptr) {
   using C = PCfg<D>;
   CUtensorMap tmap;
   const uint64_t dims[4] = {(uint64_t)D, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
@@ -750,6 +761,7 @@ int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, floa
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.park = 0;
+  p.bias = bias;
   const int nqt = (int)((S + BQ - 1) / BQ);
   const int64_t items = (int64_t)nqt * H * B;
   ADVGRPO_CHECK_ARG(items < (int64_t)1 << 30, "attn_fwd: too many work items");
@@ -786,6 +798,7 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.park = park;
+  p.bias = nullptr;
   dim3 grid((unsigned)((S + BQ * NQ - 1) / (BQ * NQ)), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<D, NQ, EMU, RS><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
@@ -838,6 +851,16 @@ int advgrpo_attn_fwd(const void* qkv, void* out, void* out2, int64_t S_split, fl
                     (long long)B, (long long)S, (long long)H);
   ADVGRPO_CHECK_ARG(aligned16(qkv) && aligned16(out), "attn_fwd: tensors must be 16-byte aligned");
   return attn_fwd_dispatch(qkv, out, out2, S_split, lse, B, S, H, D, scale, causal, 0, (cudaStream_t)stream);
+}
+
+int advgrpo_attn_fwd_bias(const void* qkv, const float* bias, void* out, float* lse, int64_t B, int64_t S, int64_t H,
+                          int64_t D, float scale, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(qkv && out && bias, "attn_fwd_bias: null pointer");
+  ADVGRPO_CHECK_ARG(B >= 1 && S >= 1 && H >= 1, "attn_fwd_bias: bad sizes B=%lld S=%lld H=%lld", (long long)B, (long long)S,
+                    (long long)H);
+  ADVGRPO_CHECK_ARG(D == 64, "attn_fwd_bias: head_dim must be 64 (got %lld)", (long long)D);
+  ADVGRPO_CHECK_ARG(aligned16(qkv) && aligned16(out), "attn_fwd_bias: tensors must be 16-byte aligned");
+  return launch_persist<64, 1>(qkv, out, nullptr, 0, lse, B, S, H, scale, 0, (cudaStream_t)stream, bias);
 }
 
 // Test/bench hook (not part of the reference-facing surface): pick the CTA shape explicitly.

@@ -237,7 +237,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint8_t* tstage = stage + team * (2 * BM * 128);
     uint64_t* tbar_res = bar_res + 2 * team;
     const bool has_res = p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL;
-    const bool is_gelu = p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF;
+    const bool is_gelu = p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF ||
+                         p.epilogue == ADVGRPO_EPI_QUICK_GELU;
     const bool is_qkn = p.epilogue == ADVGRPO_EPI_QKNORM;
     constexpr int NG = BN / 64;
     uint32_t gc = 0;                                   // running column-group counter of this team (ring position)
@@ -399,9 +400,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               if (p.epilogue == ADVGRPO_EPI_GELU_TANH) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
-              } else {
+              } else if (p.epilogue == ADVGRPO_EPI_GELU_ERF) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+              } else {
+                // quick_gelu (CLIP-L text encoder): x sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x))
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + ex2(-2.4554669595930156f * f[j]));
               }
               if (has_preact) {
                 *reinterpret_cast<bf16x8*>(sp) = z;
@@ -625,7 +630,7 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && K2 % 64 == 0,
                     "gemm_bf16: K and K2 must be multiples of 64 and N of 8 (K=%lld K2=%lld N=%lld)", (long long)K,
                     (long long)K2, (long long)N);
-  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm_bf16: unknown epilogue %d", epilogue);
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 5, "gemm_bf16: unknown epilogue %d", epilogue);
   for (int i = 0; i < nprob; ++i) {
     int rc = check_prob(probs[i], N, K, K2, epilogue);
     if (rc) return rc;

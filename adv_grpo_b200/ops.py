@@ -300,6 +300,19 @@ def attention_fwd(qkv, scale=None, causal=False, want_lse=True, variant=0, split
     return ((out, out2) if split else out), lse
 
 
+def attention_fwd_bias(qkv, bias, scale=1.0, want_lse=False):
+    """softmax(scale * Q K^T + bias[h]) V with bias f32 [H, S, S] (T5 relative-position attention)."""
+    _need_cuda(qkv, bias)
+    qkv = _bf16c(qkv)
+    B, S, three, H, D = qkv.shape
+    bias = bias.to(torch.float32).contiguous()
+    assert three == 3 and tuple(bias.shape) == (H, S, S)
+    out = torch.empty((B, S, H, D), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device) if want_lse else None
+    _lib.call("advgrpo_attn_fwd_bias", _ptr(qkv), _ptr(bias), _ptr(out), _ptr(lse), B, S, H, D, float(scale), _stream())
+    return out, lse
+
+
 def attention_bwd(qkv, out, dout, lse, scale=None, causal=False):
     qkv, out, dout = _bf16c(qkv), _bf16c(out), _bf16c(dout)
     B, S, _, H, D = qkv.shape
@@ -364,7 +377,7 @@ def set_gemm_variant(v):
     _lib.load().advgrpo_debug_set_gemm_variant(int(v))
 
 
-EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL = 0, 1, 2, 3
+EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL, EPI_QUICK_GELU = 0, 1, 2, 3, 5
 
 
 def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, gate=None,

@@ -37,7 +37,7 @@ def _pad_heads_cols(w, heads, hd, hd_pad):
 
 class ViTBlock:
     def __init__(self, width, heads, wq, bq, wk, bk, wv, bv, wo, bo, ln1, ln2, fc1, fc2, eps, gamma1=None,
-                 gamma2=None):
+                 gamma2=None, act_epilogue=ops.EPI_GELU_ERF):
         hd = width // heads
         hd_pad = 64 if hd <= 64 else 128
         assert hd <= 128
@@ -54,6 +54,7 @@ class ViTBlock:
         self.g1 = ones if gamma1 is None else gamma1.reshape(1, width).to(torch.bfloat16)
         self.g2 = ones if gamma2 is None else gamma2.reshape(1, width).to(torch.bfloat16)
         self.scale = hd ** -0.5
+        self.act_epilogue = act_epilogue
 
     def __call__(self, x, causal=False):
         B, S, W = x.shape
@@ -64,7 +65,7 @@ class ViTBlock:
         x = ops.gemm(o.view(B, S, self.heads * self.hd_pad), self.w_o, bias=self.b_o,
                      epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=self.g1, rows_per_gate=M)
         h = F.layer_norm(x, (W,), self.ln2[0], self.ln2[1], self.eps)
-        m = ops.gemm(h, self.w_fc1, bias=self.b_fc1, epilogue=ops.EPI_GELU_ERF)
+        m = ops.gemm(h, self.w_fc1, bias=self.b_fc1, epilogue=self.act_epilogue)
         x = ops.gemm(m, self.w_fc2, bias=self.b_fc2, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=self.g2,
                      rows_per_gate=M)
         return x

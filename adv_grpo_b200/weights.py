@@ -26,6 +26,14 @@ DINOV2_TINY = dict(patch=14, image=518, width=256, layers=2, heads=4, mlp=512)
 VAE_SD3 = dict(latent_channels=16, block_out=(128, 256, 512, 512), layers_per_block=2)
 VAE_TINY = dict(latent_channels=16, block_out=(32, 32, 64, 64), layers_per_block=2)
 
+# text encoders of stabilityai/stable-diffusion-3.5-medium (text_encoder / text_encoder_2 / text_encoder_3)
+CLIP_L_TEXT = dict(width=768, layers=12, heads=12, mlp=3072, act="quick_gelu", vocab=49408, ctx=77, proj=768, eos_id=2)
+CLIP_G_TEXT = dict(width=1280, layers=32, heads=20, mlp=5120, act="gelu", vocab=49408, ctx=77, proj=1280, eos_id=2)
+T5_XXL = dict(d_model=4096, layers=24, heads=64, d_kv=64, d_ff=10240, vocab=32128, num_buckets=32, max_distance=128)
+CLIP_L_TEXT_TINY = dict(width=128, layers=3, heads=2, mlp=256, act="quick_gelu", vocab=1000, ctx=77, proj=128, eos_id=2)
+CLIP_G_TEXT_TINY = dict(width=192, layers=3, heads=3, mlp=384, act="gelu", vocab=1000, ctx=77, proj=192, eos_id=2)
+T5_TINY = dict(d_model=512, layers=2, heads=4, d_kv=64, d_ff=640, vocab=500, num_buckets=32, max_distance=128)
+
 LORA_TARGETS = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0",
                 "attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj", "attn.to_add_out")
 
@@ -207,4 +215,46 @@ def init_dino_head(in_dim=768, hidden=512, seed=5, device="cpu", dtype=torch.flo
     it = _Init(seed, device, dtype)
     it.linear("layers.0", hidden, in_dim, std=in_dim ** -0.5)
     it.linear("layers.2", 1, hidden, std=hidden ** -0.5)
+    return it.p
+
+
+def init_clip_text(cfg, seed=5, device="cpu", dtype=torch.bfloat16):
+    """transformers `CLIPTextModelWithProjection` state dict (random init at the given sizes)."""
+    it = _Init(seed, device, dtype)
+    w = cfg["width"]
+    it.normal("text_model.embeddings.token_embedding.weight", (cfg["vocab"], w), 0.02)
+    it.normal("text_model.embeddings.position_embedding.weight", (cfg["ctx"], w), 0.01)
+    for i in range(cfg["layers"]):
+        l = f"text_model.encoder.layers.{i}"
+        for n in ("layer_norm1", "layer_norm2"):
+            it.normal(f"{l}.{n}.weight", (w,), 0.05, 1.0)
+            it.normal(f"{l}.{n}.bias", (w,), 0.02)
+        for n in "qkv":
+            it.linear(f"{l}.self_attn.{n}_proj", w, w, std=w ** -0.5)
+        it.linear(f"{l}.self_attn.out_proj", w, w, std=w ** -0.5)
+        it.linear(f"{l}.mlp.fc1", cfg["mlp"], w, std=w ** -0.5)
+        it.linear(f"{l}.mlp.fc2", w, cfg["mlp"], std=cfg["mlp"] ** -0.5)
+    it.normal("text_model.final_layer_norm.weight", (w,), 0.05, 1.0)
+    it.normal("text_model.final_layer_norm.bias", (w,), 0.02)
+    it.normal("text_projection.weight", (cfg["proj"], w), w ** -0.5)
+    return it.p
+
+
+def init_t5_encoder(cfg, seed=6, device="cpu", dtype=torch.bfloat16):
+    """transformers `T5EncoderModel` (v1.1, gated-gelu) state dict (random init at the given sizes)."""
+    it = _Init(seed, device, dtype)
+    d, inner = cfg["d_model"], cfg["heads"] * cfg["d_kv"]
+    it.normal("shared.weight", (cfg["vocab"], d), 1.0)
+    it.normal("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", (cfg["num_buckets"], cfg["heads"]), 0.5)
+    for i in range(cfg["layers"]):
+        b = f"encoder.block.{i}"
+        for n in "qkv":
+            it.normal(f"{b}.layer.0.SelfAttention.{n}.weight", (inner, d), (d ** -0.5) * (cfg["d_kv"] ** -0.25))
+        it.normal(f"{b}.layer.0.SelfAttention.o.weight", (d, inner), inner ** -0.5)
+        it.normal(f"{b}.layer.0.layer_norm.weight", (d,), 0.05, 1.0)
+        it.normal(f"{b}.layer.1.layer_norm.weight", (d,), 0.05, 1.0)
+        it.normal(f"{b}.layer.1.DenseReluDense.wi_0.weight", (cfg["d_ff"], d), d ** -0.5)
+        it.normal(f"{b}.layer.1.DenseReluDense.wi_1.weight", (cfg["d_ff"], d), d ** -0.5)
+        it.normal(f"{b}.layer.1.DenseReluDense.wo.weight", (d, cfg["d_ff"]), cfg["d_ff"] ** -0.5)
+    it.normal("encoder.final_layer_norm.weight", (d,), 0.05, 1.0)
     return it.p

@@ -183,6 +183,12 @@ int advgrpo_qk_norm_concat_bwd(const void* qkv_img, const void* qkv_txt, const v
 int advgrpo_attn_fwd(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B,
                      int64_t S, int64_t H, int64_t D, float scale, int causal,
                      advgrpo_stream_t stream);
+/* The same forward with an additive score bias shared by all samples: P = softmax(scale * Q K^T + bias[h]),
+ * bias f32 [H, S, S] (query-major).  This is T5's relative-position attention (scale = 1) in the text-encoding step
+ * compute_text_embeddings / encode_prompt (train_sd3_fast_pickscore.py:186-193,
+ * diffusers_patch/train_dreambooth_lora_sd3.py:98-144). */
+int advgrpo_attn_fwd_bias(const void* qkv, const float* bias, void* out, float* lse, int64_t B, int64_t S, int64_t H,
+                          int64_t D, float scale, advgrpo_stream_t stream);
 /* dqkv: bf16 [B, S, 3, H, D].  workspace: advgrpo_attn_bwd_workspace_bytes(...) bytes. */
 size_t advgrpo_attn_bwd_workspace_bytes(int64_t B, int64_t S, int64_t H, int64_t D);
 int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
@@ -208,6 +214,7 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
 #define ADVGRPO_EPI_GELU_ERF 2
 #define ADVGRPO_EPI_GATE_RESIDUAL 3
 #define ADVGRPO_EPI_QKNORM 4 /* only through advgrpo_gemm_qkv_norm */
+#define ADVGRPO_EPI_QUICK_GELU 5 /* x * sigmoid(1.702 x): the CLIP-L text encoder of encode_prompt */
 int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,

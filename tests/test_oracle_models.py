@@ -132,3 +132,51 @@ def test_vae_decoder_oracle_matches_flux_autoencoder():
         got = vae_o.vae_decode(p, z)
     assert got.shape == ref.shape == (2, 3, 64, 64)
     assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), (got - ref).abs().max()
+
+
+def test_clip_text_with_projection_oracle_matches_transformers():
+    """encode_prompt's CLIP branch (train_dreambooth_lora_sd3.py:57-93): hidden_states[-2] and text_embeds, for both
+    activation flavours (CLIP-L quick_gelu, CLIP-G gelu)."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+    from oracle import text_encoders as te_o
+    for act in ("quick_gelu", "gelu"):
+        cfg = CLIPTextConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
+                             vocab_size=300, max_position_embeddings=77, hidden_act=act, eos_token_id=2, bos_token_id=0,
+                             pad_token_id=1, projection_dim=48)
+        torch.manual_seed(0)
+        m = CLIPTextModelWithProjection(cfg).eval()
+        p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        ids = torch.randint(3, 298, (2, 77))
+        ids[0, 10:] = 299                                   # EOS (highest id) then EOS padding, as the CLIP tokenizers pad
+        ids[1, 30:] = 299
+        with torch.no_grad():
+            ref = m(ids, output_hidden_states=True)
+            got_te, got_h = te_o.clip_text_with_projection(p, dict(layers=3, heads=4, act=act, eos_id=2), ids)
+        assert len(got_h) == len(ref.hidden_states) == 4
+        assert torch.allclose(got_te, ref[0], atol=2e-5, rtol=1e-4)
+        assert torch.allclose(got_te, ref.text_embeds, atol=2e-5, rtol=1e-4)
+        assert torch.allclose(got_h[-2], ref.hidden_states[-2], atol=2e-5, rtol=1e-4)
+
+
+def test_t5_encoder_oracle_matches_transformers():
+    """encode_prompt's T5 branch (train_dreambooth_lora_sd3.py:13-55): T5 v1.1 encoder (gated-gelu, RMS norm,
+    relative-position bias, no mask) incl. the bucket function."""
+    from transformers import T5Config, T5EncoderModel
+    from oracle import text_encoders as te_o
+    cfg = T5Config(vocab_size=200, d_model=64, d_kv=16, d_ff=96, num_layers=3, num_heads=4,
+                   relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                   feed_forward_proj="gated-gelu", dropout_rate=0.0, is_encoder_decoder=False, use_cache=False)
+    torch.manual_seed(0)
+    m = T5EncoderModel(cfg).eval()
+    with torch.no_grad():
+        m.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight.normal_(0, 0.5)
+        for blk in m.encoder.block:                      # non-trivial norm weights
+            blk.layer[0].layer_norm.weight.normal_(1, 0.1)
+            blk.layer[1].layer_norm.weight.normal_(1, 0.1)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ids = torch.randint(2, 199, (2, 200))                # S = 200 > max_distance: exercises the log buckets + clamp
+    ids[:, 150:] = 0
+    with torch.no_grad():
+        ref = m(ids)[0]
+        got = te_o.t5_encoder(p, dict(layers=3, heads=4, d_kv=16), ids)
+    assert torch.allclose(got, ref, atol=3e-5, rtol=1e-4), (got - ref).abs().max()
