@@ -40,6 +40,7 @@ SIGNATURES = {
                                   _I64, _I, _P, _I64, _P, _I64, _I64, _P, _P]),
     "advgrpo_gemm_bf16_dual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P,
                                        _P, _P, _P, _P]),
+    "advgrpo_row_gate_mul": (c_int, [_P, _P, _I64, _I64, _P, _I64, _I64, _P]),
     "advgrpo_gemm_qkv_norm": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64,
                                       _F, _P]),
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),

@@ -93,7 +93,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);              // 0.5 x (1 + sign(x) erf|x|) = hx + |hx| erf|x|
 }
 
-template <int BN, bool TWO>
+// d/dz of the tanh GELU: 0.5 (1 + t) + 0.5 z (1 - t^2) k (1 + 3 c z^2), t = tanh(k (z + c z^3))
+__device__ __forceinline__ float gelu_tanh_grad(float z) {
+  const float z2 = z * z;
+  const float u = z * fmaf(0.0356774081f, z2, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = fmaf(0.1070322243f, z2, 0.7978845608f);      // k (1 + 3 c z^2)
+  return fmaf(0.5f * z * fmaf(-t, t, 1.0f), du, fmaf(0.5f, t, 0.5f));
+}
+
+// EC = epilogue class (compile time, so each instantiation only carries the registers its epilogues need):
+//   0 = plain / bias / GELU variants (+ optional pre-activation store), 1 = epilogues with a prefetched auxiliary
+//   tile (GATE_RESIDUAL, GELU_TANH_GRAD), 2 = QKNORM (per-sample tiling, 3-D maps)
+template <int BN, bool TWO, int EC>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
@@ -122,7 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int kTileM = TWO ? 2 * BM : BM;
-  const bool per_sample = p.epilogue == ADVGRPO_EPI_QKNORM;
+  constexpr bool per_sample = EC == 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G::kStages; ++i) {
@@ -236,10 +249,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     const uint32_t bar_a = 1 + 2 * team, bar_b = 2 + 2 * team;
     uint8_t* tstage = stage + team * (2 * BM * 128);
     uint64_t* tbar_res = bar_res + 2 * team;
-    const bool has_res = p.epilogue == ADVGRPO_EPI_GATE_RESIDUAL;
-    const bool is_gelu = p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF ||
-                         p.epilogue == ADVGRPO_EPI_QUICK_GELU;
-    const bool is_qkn = p.epilogue == ADVGRPO_EPI_QKNORM;
+    constexpr bool has_res = EC == 1;                                         // auxiliary tile prefetched like the residual
+    const bool is_ggrad = has_res && p.epilogue == ADVGRPO_EPI_GELU_TANH_GRAD;   // C = acc * gelu'(z)
+    const bool is_gelu = EC == 0 && (p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF ||
+                                     p.epilogue == ADVGRPO_EPI_QUICK_GELU);
+    constexpr bool is_qkn = EC == 2;
     constexpr int NG = BN / 64;
     uint32_t gc = 0;                                   // running column-group counter of this team (ring position)
     int round = 0;
@@ -412,6 +426,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 *reinterpret_cast<bf16x8*>(sp) = z;
                 sp += BM * 128;
               }
+            } else if (is_ggrad) {
+              float zz[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(sp), zz);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] *= gelu_tanh_grad(zz[j]);
             } else if (has_res) {
               float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
               if (grow) unpack8(gv[q], gg);
@@ -457,12 +476,12 @@ struct Maps {
   CUtensorMap a, w, a2, w2, c, r;
 };
 
-template <int BN, bool TWO>
+template <int BN, bool TWO, int EC>
 int launch_gemm(const Maps& m0, const Maps& m1, GParams& p, cudaStream_t st) {
   using G = GCfg<BN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(gemm_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(gemm_kernel<BN, TWO, EC>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
     attr_set = true;
   }
   constexpr int kTileM = TWO ? 2 * BM : BM;
@@ -492,10 +511,10 @@ int launch_gemm(const Maps& m0, const Maps& m1, GParams& p, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO>, m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
+    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO, EC>, m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
                                          m1.a2, m1.w2, m1.c, m1.r, p));
   } else {
-    gemm_kernel<BN, TWO><<<workers, G::kThreads, G::kSmemBytes, st>>>(m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
+    gemm_kernel<BN, TWO, EC><<<workers, G::kThreads, G::kSmemBytes, st>>>(m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
                                                                       m1.a2, m1.w2, m1.c, m1.r, p);
   }
   ADVGRPO_CUDA_LAUNCH_CHECK();
@@ -530,6 +549,10 @@ int check_prob(const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int epilogue
     ADVGRPO_CHECK_ARG(q.residual && q.gate && q.rows_per_gate >= 1 && q.ldr % 8 == 0 && q.gate_stride % 8 == 0 &&
                           aligned16(q.residual) && aligned16(q.gate),
                       "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
+  }
+  if (epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) {
+    ADVGRPO_CHECK_ARG(q.residual && q.ldr % 8 == 0 && aligned16(q.residual),
+                      "gemm_bf16: GELU_TANH_GRAD needs the pre-activation in `residual`");
   }
   (void)N; (void)K;
   return ADVGRPO_OK;
@@ -595,7 +618,7 @@ int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int 
   }
   rc = make_tmap_bf16(&m.c, q.C, 2, dc, sc, bc, true);
   if (rc) return rc;
-  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL) {
+  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) {
     const uint64_t sr[2] = {0, (uint64_t)q.ldr * 2};
     rc = make_tmap_bf16(&m.r, q.residual, 2, dc, sr, bc, true);
     if (rc) return rc;
@@ -630,7 +653,7 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && K2 % 64 == 0,
                     "gemm_bf16: K and K2 must be multiples of 64 and N of 8 (K=%lld K2=%lld N=%lld)", (long long)K,
                     (long long)K2, (long long)N);
-  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 5, "gemm_bf16: unknown epilogue %d", epilogue);
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 6, "gemm_bf16: unknown epilogue %d", epilogue);
   for (int i = 0; i < nprob; ++i) {
     int rc = check_prob(probs[i], N, K, K2, epilogue);
     if (rc) return rc;
@@ -684,11 +707,20 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   p.epilogue = epilogue;
   p.HD = (int)HD;
   p.eps = eps;
-  if (pair_ok && BN == 256) return launch_gemm<256, true>(m0, m1, p, st);
-  if (pair_ok && BN == 192) return launch_gemm<192, true>(m0, m1, p, st);
-  if (BN == 256) return launch_gemm<256, false>(m0, m1, p, st);
-  if (BN == 192) return launch_gemm<192, false>(m0, m1, p, st);
-  return launch_gemm<128, false>(m0, m1, p, st);
+  const int ec = (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) ? 1
+                 : (epilogue == ADVGRPO_EPI_QKNORM ? 2 : 0);
+#define ADVGRPO_GEMM_DISPATCH(BNV, TWOV)                                   \
+  switch (ec) {                                                            \
+    case 0: return launch_gemm<BNV, TWOV, 0>(m0, m1, p, st);               \
+    case 1: return launch_gemm<BNV, TWOV, 1>(m0, m1, p, st);               \
+    default: return launch_gemm<BNV, TWOV, 2>(m0, m1, p, st);              \
+  }
+  if (pair_ok && BN == 256) { ADVGRPO_GEMM_DISPATCH(256, true) }
+  if (pair_ok && BN == 192) { ADVGRPO_GEMM_DISPATCH(192, true) }
+  if (BN == 256) { ADVGRPO_GEMM_DISPATCH(256, false) }
+  if (BN == 192) { ADVGRPO_GEMM_DISPATCH(192, false) }
+  ADVGRPO_GEMM_DISPATCH(128, false)
+#undef ADVGRPO_GEMM_DISPATCH
 }
 
 }  // namespace

@@ -226,6 +226,22 @@ __global__ void qk_norm_concat_bwd_kernel(const __nv_bfloat16* __restrict__ qkv_
   }
 }
 
+__global__ void __launch_bounds__(256)
+row_gate_mul_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gate, int64_t gate_stride,
+                    int64_t rows_per_gate, __nv_bfloat16* __restrict__ out, int64_t M, int nvec) {
+  const int64_t total = M * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / nvec;
+    const int c = (int)(i - m * nvec) * 8;
+    float a[8], g[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + i * 8), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(gate + (m / rows_per_gate) * gate_stride + c), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= g[j];
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(a);
+  }
+}
+
 }  // namespace
 }  // namespace advgrpo
 
@@ -281,6 +297,22 @@ int advgrpo_ln_modulate_bwd(const void* x, const void* scale, const void* scale2
   DISPATCH_NV((int)(D / 256), ln_modulate_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)scale2, mod_stride,
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (__nv_bfloat16*)dx, accumulate, rows, S, eps));
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+int advgrpo_row_gate_mul(const void* x, const void* gate, int64_t gate_stride, int64_t rows_per_gate, void* out,
+                         int64_t M, int64_t N, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(x && gate && out, "row_gate_mul: null pointer");
+  ADVGRPO_CHECK_ARG(N % 8 == 0 && gate_stride % 8 == 0 && rows_per_gate >= 1, "row_gate_mul: N and gate_stride must be multiples of 8");
+  ADVGRPO_CHECK_ARG(aligned16(x) && aligned16(gate) && aligned16(out), "row_gate_mul: 16-byte alignment");
+  if (M == 0 || N == 0) return ADVGRPO_OK;
+  const int64_t total = M * (N / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  row_gate_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate, gate_stride, rows_per_gate, (__nv_bfloat16*)out, M, (int)(N / 8));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

@@ -86,8 +86,7 @@ class _LinearFn(torch.autograd.Function):
         d_res = None
         if epilogue == ops.EPI_GATE_RESIDUAL:
             d_res = dy
-            g = gate.reshape(gate.shape[0], 1, N)
-            dy2 = (dy2.reshape(gate.shape[0], rows_per_gate, N) * g).reshape(-1, N)
+            dy2 = ops.row_gate_mul(dy2, gate, rows_per_gate)
         elif epilogue == ops.EPI_GELU_TANH:
             dy2 = torch.ops.aten.gelu_backward(dy2, preact, approximate="tanh")
         elif epilogue == ops.EPI_GELU_ERF:
@@ -143,7 +142,7 @@ class _DualLinearFn(torch.autograd.Function):
             d = dys[i].reshape(-1, N)
             if epilogue == ops.EPI_GATE_RESIDUAL:
                 d_res[i] = dys[i]
-                d = (d.reshape(gs[i].shape[0], rows[i], N) * gs[i].reshape(gs[i].shape[0], 1, N)).reshape(-1, N)
+                d = ops.row_gate_mul(d, gs[i], rows[i])
             elif epilogue == ops.EPI_GELU_TANH:
                 d = torch.ops.aten.gelu_backward(d, pres[i], approximate="tanh")
             elif epilogue == ops.EPI_GELU_ERF:
@@ -184,6 +183,40 @@ class _DualLinearFn(torch.autograd.Function):
                     dx1 = dx
         return (dx0, dx1, None, None, None, None, None, None, das[0], das[1], dws[0], dws[1], None, d_res[0], d_res[1],
                 None, None, None, None)
+
+
+class _DualFeedForwardFn(torch.autograd.Function):
+    """Both streams' feed-forward of one MMDiT block, x + gate * (GELU_tanh(x_mod W1^T + b1) W2^T + b2), as two
+    dual-problem GEMM launches forward and two backward (the weights are frozen: no LoRA on the FF layers,
+    train_sd3_fast_pickscore.py:490-499).  Backward: dz = ((dy * gate) W2) * gelu'(z) in the epilogue of the first
+    GEMM (z = stored bf16 pre-activation), dx_mod = dz W1; the hidden activation itself is never stored."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, w1_0, w1_1, w1t_0, w1t_1, b1_0, b1_1, w2_0, w2_1, w2t_0, w2t_1, b2_0, b2_1, r0, r1, g0, g1,
+                rows0, rows1):
+        pre = (None, None)
+        if any(ctx.needs_input_grad):
+            pre = tuple(torch.empty((x.numel() // x.shape[-1], w1_0.shape[0]), dtype=torch.bfloat16, device=x.device)
+                        for x in (x0, x1))
+        h0, h1 = ops.gemm_dual((x0, x1), (w1_0, w1_1), bias=(b1_0, b1_1), epilogue=ops.EPI_GELU_TANH, preact_out=pre)
+        y0, y1 = ops.gemm_dual((h0, h1), (w2_0, w2_1), bias=(b2_0, b2_1), epilogue=ops.EPI_GATE_RESIDUAL,
+                               residual=(r0, r1), gate=(g0, g1), rows_per_gate=(rows0, rows1))
+        ctx.save_for_backward(g0, g1, pre[0], pre[1])
+        ctx.meta = (w1t_0, w1t_1, w2t_0, w2t_1, rows0, rows1)
+        return y0, y1
+
+    @staticmethod
+    def backward(ctx, dy0, dy1):
+        g0, g1, pre0, pre1 = ctx.saved_tensors
+        w1t_0, w1t_1, w2t_0, w2t_1, rows0, rows1 = ctx.meta
+        dy0, dy1 = dy0.contiguous(), dy1.contiguous()
+        d0 = ops.row_gate_mul(dy0.reshape(-1, dy0.shape[-1]), g0, rows0)
+        d1 = ops.row_gate_mul(dy1.reshape(-1, dy1.shape[-1]), g1, rows1)
+        dz0, dz1 = ops.gemm_dual((d0, d1), (w2t_0(), w2t_1()), epilogue=ops.EPI_GELU_TANH_GRAD, residual=(pre0, pre1))
+        dx0, dx1 = ops.gemm_dual((dz0, dz1), (w1t_0(), w1t_1()))
+        dx0 = dx0.reshape(*dy0.shape[:-1], dx0.shape[-1])
+        dx1 = dx1.reshape(*dy1.shape[:-1], dx1.shape[-1])
+        return (dx0, dx1) + (None,) * 12 + (dy0, dy1, None, None, None, None)
 
 
 class _WT:
@@ -277,6 +310,7 @@ class SD3Transformer2DModel(torch.nn.Module):
                     self._lora_names.append(name)
         self.dual_gemm = True            # image + text projections of a block as one dual-problem GEMM launch
         self.fused_qkv_norm = True       # no-grad forward: q/k RMSNorm + concat inside the QKV GEMM epilogue
+        self.fused_ff = True             # feed-forward pair as one autograd node (GELU backward in a GEMM epilogue)
         self._lora_cache = None
         self._lora_dirty = False
         self._lora_enabled = True
@@ -462,7 +496,11 @@ class SD3Transformer2DModel(torch.nn.Module):
         if not fused_out:
             c = self._lin(oc, blk, "cout", pk, ops.EPI_GATE_RESIDUAL, c, ch(ec, 2), Nc)
         cm = ops.ln_modulate(c, ch(ec, 3), ch(ec, 4))
-        if self.dual_gemm:
+        if self.dual_gemm and self.fused_ff:
+            x, c = _DualFeedForwardFn.apply(xm, cm, blk["w_ff1"], blk["w_cff1"], blk["wt_ff1"], blk["wt_cff1"], blk["b_ff1"],
+                                            blk["b_cff1"], blk["w_ff2"], blk["w_cff2"], blk["wt_ff2"], blk["wt_cff2"],
+                                            blk["b_ff2"], blk["b_cff2"], x, c, ch(ex, 5), ch(ec, 5), N, Nc)
+        elif self.dual_gemm:
             hx, hc = self._lin2(xm, cm, blk, "ff1", "cff1", None, ops.EPI_GELU_TANH)
             x, c = self._lin2(hx, hc, blk, "ff2", "cff2", None, ops.EPI_GATE_RESIDUAL, (x, c), (ch(ex, 5), ch(ec, 5)), (N, Nc))
         else:

@@ -377,7 +377,7 @@ def set_gemm_variant(v):
     _lib.load().advgrpo_debug_set_gemm_variant(int(v))
 
 
-EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL, EPI_QUICK_GELU = 0, 1, 2, 3, 5
+EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL, EPI_QUICK_GELU, EPI_GELU_TANH_GRAD = 0, 1, 2, 3, 5, 6
 
 
 def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, gate=None,
@@ -404,6 +404,17 @@ def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, ga
               _ptr(c2d), c2d.stride(0), M, N, K, int(epilogue), _ptr(r2d), 0 if r2d is None else r2d.stride(0),
               _ptr(gate), 0 if gate is None else gate.stride(0), int(rows_per_gate), _ptr(preact_out), _stream())
     return c2d.reshape(*lead, N)
+
+
+def row_gate_mul(x, gate, rows_per_gate):
+    """x [M, N] bf16 (any leading shape) * gate[m // rows_per_gate] (gate [G, N], row-strided) in one pass."""
+    _need_cuda(x, gate)
+    x = _bf16c(x)
+    N = x.shape[-1]
+    M = x.numel() // N
+    out = torch.empty_like(x)
+    _lib.call("advgrpo_row_gate_mul", _ptr(x), _ptr(gate), gate.stride(0), int(rows_per_gate), _ptr(out), M, N, _stream())
+    return out
 
 
 def _arr_p(vals):

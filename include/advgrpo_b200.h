@@ -196,6 +196,11 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
                      int causal, void* workspace, size_t workspace_bytes,
                      advgrpo_stream_t stream);
 
+/* out[m, :] = x[m, :] * gate[m / rows_per_gate, :] (bf16; gate rows of stride gate_stride): the backward of the adaLN
+ * gate in `x + gate * f(.)` (d f = dy * gate) as one HBM pass.  N multiple of 8. */
+int advgrpo_row_gate_mul(const void* x, const void* gate, int64_t gate_stride, int64_t rows_per_gate, void* out,
+                         int64_t M, int64_t N, advgrpo_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Dense contraction with fused epilogue (tcgen05 + TMA), the nn.Linear / peft
  * lora.Linear layers of SD3Transformer2DModel and of the reward ViTs:
@@ -215,6 +220,8 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
 #define ADVGRPO_EPI_GATE_RESIDUAL 3
 #define ADVGRPO_EPI_QKNORM 4 /* only through advgrpo_gemm_qkv_norm */
 #define ADVGRPO_EPI_QUICK_GELU 5 /* x * sigmoid(1.702 x): the CLIP-L text encoder of encode_prompt */
+#define ADVGRPO_EPI_GELU_TANH_GRAD 6 /* C = acc * gelu_tanh'(z), z = bf16 [M, N] passed as `residual` (ld ldr): the backward
+                                        of a GELU feed-forward, dz = (dy W2) * gelu'(z), without a separate elementwise pass */
 int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,

@@ -290,3 +290,29 @@ def test_gemm_qkv_norm_fused_epilogue_bit_exact(ops, variant, B, S_img, S_txt, H
             assert _rel_err(joint[:, :S_img], zr) < 1.2e-2
     finally:
         ops.set_gemm_variant(0)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_gemm_gelu_grad_epilogue_and_row_gate_mul(ops, variant):
+    """Backward of a GELU feed-forward without elementwise passes: dz = ((dy * gate) W) * gelu_tanh'(z) with z
+    prefetched like the residual tile; and the adaLN-gate multiply as one HBM pass."""
+    g = torch.Generator(device=DEV).manual_seed(21 + variant)
+    B, S, K, N = 3, 333, 256, 1544
+    dy = torch.randn(B * S, K, device=DEV, generator=g).bfloat16()
+    gate = torch.randn(B, 4 * K, device=DEV, generator=g).bfloat16()[:, K:2 * K]          # strided rows, like an adaLN chunk
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    z = (1.5 * torch.randn(B * S, N, device=DEV, generator=g)).bfloat16()
+    d = ops.row_gate_mul(dy, gate, S)
+    ref_d = (dy.float().view(B, S, K) * gate.float()[:, None]).view(B * S, K)
+    assert torch.equal(d, ref_d.bfloat16())
+    ops.set_gemm_variant(variant)
+    try:
+        got = ops.gemm(d, w, epilogue=ops.EPI_GELU_TANH_GRAD, residual=z)
+        got2 = ops.gemm_dual((d, d[:100]), (w, w), epilogue=ops.EPI_GELU_TANH_GRAD, residual=(z, z[:100]))
+    finally:
+        ops.set_gemm_variant(0)
+    acc = d.float() @ w.float().T
+    zz = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zz, approximate="tanh").backward(acc)
+    assert _rel_err(got, zz.grad) < 6e-3
+    assert _rel_err(got2[0], zz.grad) < 6e-3 and _rel_err(got2[1], zz.grad[:100]) < 6e-3
