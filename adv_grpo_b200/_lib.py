@@ -48,6 +48,7 @@ SIGNATURES = {
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
     "advgrpo_group_norm_workspace_bytes": (_SZ, [_I64, _I64]),
     "advgrpo_group_norm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P, _SZ, _P]),
+    "advgrpo_conv2d_nhwc_tf32": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
     "advgrpo_add_bias_nhwc": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "advgrpo_upsample_nearest2x_nhwc": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _P]),
 }

@@ -46,6 +46,15 @@ gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, 
   }
 }
 
+// Round to the nearest TF32 value (10-bit mantissa, ties away): what cuDNN / cuBLAS do to fp32 operands of a TF32
+// tensor-core product.  The tcgen05 TF32 convolution reads its operands straight from TMA-filled shared memory, where
+// the tensor core would TRUNCATE the low 13 mantissa bits, so the producer of every convolution input rounds here.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(kThreads)
 gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, const double* __restrict__ sums, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ y, int64_t HW, int C, int groups, float eps,
@@ -74,9 +83,13 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, 
     const float4 be = *reinterpret_cast<const float4*>(beta + c);
     float o[4] = {(v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
                   (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w};
-    if (silu) {
+    if (silu & 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.0f + __expf(-o[j]));
+    }
+    if (silu & 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
     }
     *reinterpret_cast<float4*>(yb + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -108,7 +121,9 @@ upsample2x_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t B,
     pix /= W;
     const int yh = (int)(pix % H);
     const int64_t n = pix / H;
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    // the upsampled map is only ever the input of the upsampler's convolution: hand it over as TF32 values
+    v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
     float* base = y + (((n * 2 * H + 2 * yh) * 2 * W + 2 * xw) * (int64_t)C) + q * 4;
     const int64_t row = (int64_t)2 * W * C;
     *reinterpret_cast<float4*>(base) = v;

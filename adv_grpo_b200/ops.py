@@ -534,7 +534,7 @@ def dino_preprocess(images, out_size=518):
 
 
 # --------------------------------------------------------------------------- VAE GroupNorm (+SiLU)
-def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True, in_bias=None):
+def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True, in_bias=None, round_tf32=False):
     """x: f32 [B, C, H, W] stored channels_last (or [B, H, W, C] contiguous).  Returns the same logical shape,
     channels_last."""
     _need_cuda(x)
@@ -547,7 +547,31 @@ def group_norm_silu_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=True, in_bias
     ws_bytes = _lib.query("advgrpo_group_norm_workspace_bytes", B, groups)
     ws = _workspace("gn", ws_bytes, x.device)
     _lib.call("advgrpo_group_norm_silu_nhwc", _ptr(x), _ptr(in_bias), _ptr(gamma), _ptr(beta), _ptr(y), B, H * W, C, groups,
-              float(eps), int(bool(silu)), _ptr(ws), ws.numel(), _stream())
+              float(eps), int(bool(silu)) | (2 if round_tf32 else 0), _ptr(ws), ws.numel(), _stream())
+    return y
+
+
+def pack_conv_weight_tf32(w):
+    """torch conv weight [Cout, Cin, kh, kw] -> tap-major [Cout, kh*kw*Cin] fp32, rounded to the nearest TF32 value
+    (10-bit mantissa) so the tensor core's truncation of the low 13 mantissa bits is exact for the weights."""
+    w = w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+    bits = w.view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32).contiguous()
+
+
+def conv2d_nhwc_tf32(x, w_packed, bias, ksize):
+    """x: f32 [B, Cin, H, W] stored channels_last; w_packed from `pack_conv_weight_tf32`.  3x3 / pad 1 or 1x1
+    convolution on the tcgen05 TF32 implicit-GEMM kernel.  Returns f32 [B, Cout, H, W], channels_last."""
+    _need_cuda(x, w_packed)
+    if x.dim() != 4 or x.dtype != torch.float32:
+        raise _lib.AdvGrpoError("conv2d_nhwc_tf32 expects a 4-D float32 tensor")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    B, Cin, H, W = x.shape
+    Cout = w_packed.shape[0]
+    assert w_packed.shape[1] == ksize * ksize * Cin
+    y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    _lib.call("advgrpo_conv2d_nhwc_tf32", _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(y), B, H, W, Cin, Cout, int(ksize), _stream())
     return y
 
 

@@ -29,6 +29,7 @@ class AutoencoderKL:
                 v = v.contiguous(memory_format=torch.channels_last)
             self.p[k] = v
         self.fused = torch.device(device).type == "cuda" and dtype == torch.float32
+        self.native_conv = True       # 3x3 / 1x1 convolutions on the tcgen05 TF32 implicit-GEMM kernel (csrc/conv.cu)
 
     def to(self, *a, **k):
         return self
@@ -41,14 +42,22 @@ class AutoencoderKL:
         C = x.shape[1]
         if self._fusable(C):
             return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu,
-                                            in_bias=in_bias)
+                                            in_bias=in_bias, round_tf32=self.native_conv)
         if in_bias is not None:
             x = x + in_bias[None, :, None, None]
         y = F.group_norm(x, 32, self.p[name + ".weight"], self.p[name + ".bias"], eps=1e-6)   # tiny test configs
         return F.silu(y) if silu else y
 
     def _conv(self, name, x, pad=1, bias=True):
-        return F.conv2d(x, self.p[name + ".weight"], self.p[name + ".bias"] if bias else None, padding=pad)
+        w = self.p[name + ".weight"]
+        Cout, Cin, k, _ = w.shape
+        if self.native_conv and self.fused and Cin % 32 == 0 and Cout % 32 == 0 and k in (1, 3) and pad == k // 2:
+            key = name + ".packed_tf32"
+            if key not in self.p:
+                self.p[key] = ops.pack_conv_weight_tf32(w)
+            return ops.conv2d_nhwc_tf32(x, self.p[key], self.p[name + ".bias"] if bias else None, k)
+        # conv_in (16 input channels) and conv_out (3 output channels) stay library calls: 0.3 % of the decoder FLOPs
+        return F.conv2d(x, w, self.p[name + ".bias"] if bias else None, padding=pad)
 
     def _resnet(self, pre, x):
         p = self.p

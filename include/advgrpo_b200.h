@@ -284,17 +284,32 @@ int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64
  * gamma, beta: f32 [C].  C / groups must be a multiple of 4.  In place (y == x) is allowed.
  * in_bias (f32 [C], may be NULL) is added to x first: the bias of the preceding convolution, so the
  * convolution itself runs bias-free and no separate bias pass exists.
+ * silu: bit 0 = apply SiLU; bit 1 = round the output to the nearest TF32 value (the output feeds
+ * advgrpo_conv2d_nhwc_tf32, whose tensor-core operands would otherwise be truncated).
  */
 size_t advgrpo_group_norm_workspace_bytes(int64_t B, int64_t groups);
 int advgrpo_group_norm_silu_nhwc(const float* x, const float* in_bias, const float* gamma, const float* beta,
                                  float* y, int64_t B, int64_t HW, int64_t C, int64_t groups, float eps, int silu,
                                  void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
 /* out = a + b + bias[c] on NHWC fp32 [rows, C] (ResnetBlock2D residual add with the conv2 / shortcut biases
- * folded in; bias may be NULL), and nearest-neighbour 2x upsampling x [B,H,W,C] -> y [B,2H,2W,C] (Upsample2D). */
+ * folded in; bias may be NULL), and nearest-neighbour 2x upsampling x [B,H,W,C] -> y [B,2H,2W,C] (Upsample2D; the
+ * values are rounded to TF32: the result is the input of the upsampler's convolution). */
 int advgrpo_add_bias_nhwc(const float* a, const float* b, const float* bias, float* out, int64_t rows, int64_t C,
                           advgrpo_stream_t stream);
 int advgrpo_upsample_nearest2x_nhwc(const float* x, float* y, int64_t B, int64_t H, int64_t W, int64_t C,
                                     advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A6: the decoder's convolutions as an implicit GEMM on tcgen05 in TF32 with fp32 accumulation (the reference runs
+ * `pipeline.vae.decode` in fp32, i.e. TF32 tensor-core convolutions under PyTorch's default cudnn.allow_tf32;
+ * adv_grpo/diffusers_patch/sd3_pipeline_with_logprob_fast.py:667-670, train_sd3_fast_pickscore.py:481).
+ * x: f32 [B, H, W, Cin] (channels last); w: f32 [Cout, ksize*ksize, Cin] (tap-major, i.e. the torch weight
+ * [Cout, Cin, kh, kw] permuted to [Cout, kh, kw, Cin]); bias: f32 [Cout] or NULL; y: f32 [B, H, W, Cout].
+ * ksize 3 (stride 1, zero padding 1) or 1.  Cin, Cout multiples of 32.  No workspace: the zero padding comes
+ * from the TMA unit's out-of-bounds fill, there is no im2col buffer.
+ */
+int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t H, int64_t W,
+                             int64_t Cin, int64_t Cout, int ksize, advgrpo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -378,7 +378,20 @@ def test_vae_decoder_matches_oracle_at_true_widths():
         torch.backends.cudnn.allow_tf32 = prev
     ref = vae_o.decode_latents_to_image(vp, z)
     assert got.shape == (2, 3, 64, 64)
-    assert (got - ref).abs().max().item() < 2e-3
+    # the convolutions run in TF32 (tcgen05 kind::tf32 here, cuDNN TF32 in the reference's fp32 VAE under PyTorch's
+    # default cudnn.allow_tf32): bound our deviation from the fp32 oracle by that of the library TF32 path on the
+    # same decoder, and report both
+    vae.native_conv = False
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        lib = VaeImageProcessor().postprocess(vae.decode(z.to(DEV) / 1.5305 + 0.0609)[0], output_type="pt").cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+        vae.native_conv = True
+    err, err_lib = (got - ref).abs().max().item(), (lib - ref).abs().max().item()
+    print(f"VAE decode max |err| vs fp32 oracle: tcgen05 TF32 {err:.2e}, cuDNN TF32 {err_lib:.2e}")
+    assert err < max(2e-3, 2.0 * err_lib), (err, err_lib)
+    assert (got - ref).abs().mean().item() < 5e-4
 
 
 def test_vae_fused_helpers(ops):
@@ -389,9 +402,45 @@ def test_vae_fused_helpers(ops):
     assert torch.allclose(ops.add_bias_nhwc(a, b, bias), a + b + bias[None, :, None, None], atol=1e-6)
     assert torch.equal(ops.add_bias_nhwc(a, b), a + b)
     up = ops.upsample_nearest2x_nhwc(a)
-    assert torch.equal(up, torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"))
+    # nearest-2x, handed to the upsampler's TF32 convolution as TF32 values (round to nearest, ties away: the low 13
+    # mantissa bits are zero)
+    a_tf32 = ((a.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(up, torch.nn.functional.interpolate(a_tf32, scale_factor=2.0, mode="nearest"))
     assert up.is_contiguous(memory_format=torch.channels_last)
     gamma, beta = torch.randn(128, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV)
     got = ops.group_norm_silu_nhwc(a, gamma, beta, 32, 1e-6, True, in_bias=bias)
     ref = torch.nn.functional.silu(torch.nn.functional.group_norm(a + bias[None, :, None, None], 32, gamma, beta, eps=1e-6))
     assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5)
+    got_r = ops.group_norm_silu_nhwc(a, gamma, beta, 32, 1e-6, True, in_bias=bias, round_tf32=True)
+    assert torch.equal(got_r, ((got.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
+
+
+# ------------------------------------------------------------------ A6 convolution (tcgen05 TF32 implicit GEMM)
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 64, 128, 3), (1, 64, 64, 512, 512, 3), (2, 5, 20, 32, 96, 3),
+                                              (1, 128, 128, 256, 128, 3), (2, 32, 32, 512, 256, 1), (1, 7, 9, 64, 32, 1),
+                                              (3, 8, 256, 128, 128, 3)])
+def test_conv2d_nhwc_tf32_matches_torch_fp32(ops, B, H, W, Cin, Cout, k):
+    """3x3 (zero padding from the TMA out-of-bounds fill, incl. negative start coordinates) and 1x1 convolutions,
+    ragged patches (W, H not multiples of the patch), vs an fp32 torch convolution.  TF32 inputs (10-bit mantissa),
+    fp32 accumulation: error bound ~2^-10 per operand relative to the accumulated magnitude."""
+    g = torch.Generator(device=DEV).manual_seed(B + H + W + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), padding=k // 2).float()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    wp = ops.pack_conv_weight_tf32(w)
+    got = ops.conv2d_nhwc_tf32(x, wp, bias, k)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    err = (got - ref).abs().max().item()
+    assert err <= 4e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+    got_nb = ops.conv2d_nhwc_tf32(x, wp, None, k)
+    assert torch.allclose(got_nb + bias[None, :, None, None], got, atol=1e-5)
+    # borders are where the out-of-bounds fill matters: check them separately
+    for sl in ((slice(None), slice(None), 0), (slice(None), slice(None), H - 1), (slice(None), slice(None), slice(None), 0),
+               (slice(None), slice(None), slice(None), W - 1)):
+        assert (got[sl] - ref[sl]).abs().max().item() <= 4e-3 * ref.abs().max().item()
