@@ -25,11 +25,13 @@ constexpr int CBK = 32;    // fp32 channels per K block (128 bytes)
 
 // MT = 128-pixel sub-tiles per CTA tile (two vertically adjacent patches share one B tile): with 128 output
 // channels a 128 x 128 tile needs 32 KB of operands per 256 tensor clocks, which starves the pipe; 256 x 128 halves it.
-template <int BN, int MT>
+// TWO = CTA pair (cta_group::2): the pair owns 256 pixels (two stacked patches, one per CTA) x 256 channels; each CTA
+// stages its own patch and HALF of the weight tile, which halves the per-CTA operand traffic and allows 5 stages.
+template <int BN, int MT, bool TWO = false>
 struct CCfg {
-  static constexpr int kStages = (BN * MT >= 256) ? 3 : 5;
+  static constexpr int kStages = TWO ? 5 : ((BN * MT >= 256) ? 3 : 5);
   static constexpr int kABytes = MT * CBM * 128;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kNBuf = 4;                            // 2 staging tiles [128 x 32 fp32] per epilogue team
   static constexpr int kStagingBytes = kNBuf * CBM * 128;
@@ -59,6 +61,15 @@ __device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+__device__ __forceinline__ void mma_ss_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -66,11 +77,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool TWO>
 __global__ void __launch_bounds__(320, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                  const __grid_constant__ CUtensorMap tm_y, const CParams p) {
-  using G = CCfg<BN, MT>;
+  using G = CCfg<BN, MT, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage = smem + G::kStages * G::kStageBytes;
@@ -85,7 +96,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_tiles;
   const int kb_total = p.taps * p.kb_per_tap;
-  const int worker = (int)blockIdx.x, num_workers = (int)gridDim.x;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;          // 0 = leader CTA of the pair
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kRowMul = TWO ? 2 : MT;                       // patches stacked per tile
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G::kStages; ++i) {
@@ -94,16 +108,22 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], 128);
+      mbar_init(&bar_acc_empty[i], TWO ? 256 : 128);
     }
     fence_barrier_init();
   }
+  if constexpr (TWO) cluster_sync_all();
   if (warp == 9) {
-    tmem_alloc(tmem_base_smem, G::kTmemCols);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc_2cta(tmem_base_smem, G::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_base_smem, G::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -112,7 +132,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     n0 = (tile % p.tiles_n) * BN;
     const int m = tile / p.tiles_n;
     x0 = (m % p.tiles_x) * p.bw;
-    y0 = ((m / p.tiles_x) % p.tiles_y) * (p.bh * MT);
+    y0 = ((m / p.tiles_x) % p.tiles_y) * (p.bh * kRowMul) + (TWO ? (int)rank * p.bh : 0);
     b = m / (p.tiles_x * p.tiles_y);
   };
 
@@ -131,18 +151,25 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const int st = it % G::kStages;
             mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
             uint8_t* sa = smem + st * G::kStageBytes;
-            mbar_expect_tx(&bar_full[st], G::kStageBytes);
             // rows outside the image (negative or >= W / H coordinates) arrive as zeros: the conv's zero padding
-            tma_load_4d(sa, &tm_x, &bar_full[st], cb * CBK, x0 + dx, y0 + dy, b);
-            tma_load_2d(sa + G::kABytes, &tm_w, &bar_full[st], tap * p.Cin + cb * CBK, n0);
+            if constexpr (TWO) {
+              const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
+              if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
+              tma_load_4d_2sm(sa, &tm_x, full_leader, cb * CBK, x0 + dx, y0 + dy, b);
+              tma_load_2d_2sm(sa + G::kABytes, &tm_w, full_leader, tap * p.Cin + cb * CBK, n0 + (int)rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&bar_full[st], G::kStageBytes);
+              tma_load_4d(sa, &tm_x, &bar_full[st], cb * CBK, x0 + dx, y0 + dy, b);
+              tma_load_2d(sa + G::kABytes, &tm_w, &bar_full[st], tap * p.Cin + cb * CBK, n0);
+            }
           }
         }
       }
     }
   } else if (warp == 9) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(CBM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TWO ? 2 * CBM : CBM, BN);
       int it = 0, local = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
         const int acc = local & 1;
@@ -158,12 +185,17 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
           for (int k = 0; k < CBK / 8; ++k)   // K = 8 tf32 (32 bytes) per instruction
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              mma_ss_tf32(d_tmem + mt * BN, make_smem_desc_sw128(sa + mt * (CBM * 128) + k * 32, 16, 1024),
-                          make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          mma_commit(&bar_empty[st]);
+            for (int mt = 0; mt < MT; ++mt) {
+              if constexpr (TWO)
+                mma_ss_tf32_2cta(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                                 make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                mma_ss_tf32(d_tmem + mt * BN, make_smem_desc_sw128(sa + mt * (CBM * 128) + k * 32, 16, 1024),
+                            make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
         }
-        mma_commit(&bar_acc_full[acc]);
+        if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
       }
     }
   } else {
@@ -203,7 +235,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tmem_wait_ld();
         if (gg == ng * MT - 1) {
           tc_fence_before();
-          mbar_arrive(&bar_acc_empty[team]);
+          if constexpr (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[team]), 0));
+          else mbar_arrive(&bar_acc_empty[team]);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -226,27 +259,45 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, G::kTmemCols);
+    if constexpr (TWO) tmem_dealloc_2cta(tmem_base, G::kTmemCols); else tmem_dealloc(tmem_base, G::kTmemCols);
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool TWO>
 int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CParams& p, cudaStream_t st) {
-  using G = CCfg<BN, MT>;
+  using G = CCfg<BN, MT, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(conv_tf32_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(conv_tf32_kernel<BN, MT, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
     attr_set = true;
   }
-  int workers = sm_count();
+  int workers = TWO ? sm_count() / 2 : sm_count();
   if (workers > p.num_tiles) workers = p.num_tiles;
-  conv_tf32_kernel<BN, MT><<<workers, G::kThreads, G::kSmemBytes, st>>>(mx, mw, my, p);
+  if constexpr (TWO) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * workers);
+    cfg.blockDim = dim3(G::kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, conv_tf32_kernel<BN, MT, TWO>, mx, mw, my, p));
+  } else {
+    conv_tf32_kernel<BN, MT, TWO><<<workers, G::kThreads, G::kSmemBytes, st>>>(mx, mw, my, p);
+  }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
+
+int g_conv_variant = 0;   // 0 = auto, 1 = single-CTA tiles only (test hook)
 
 }  // namespace
 }  // namespace advgrpo
@@ -254,6 +305,9 @@ int launch_conv(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap&
 using namespace advgrpo;
 
 extern "C" {
+
+// Test/bench hook (not part of the reference-facing surface): force the convolution CTA shape.
+void advgrpo_debug_set_conv_variant(int v) { g_conv_variant = v; }
 
 int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t H, int64_t W,
                              int64_t Cin, int64_t Cout, int ksize, advgrpo_stream_t stream) {
@@ -275,8 +329,10 @@ int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, 
   p.tiles_x = (int)((W + bw - 1) / bw);
   p.tiles_y = (int)((H + bh - 1) / bh);
   const int BN = Cout >= 256 ? 256 : 128;
+  const bool pair = BN == 256 && H >= 2 * bh && g_conv_variant != 1;
   const int MT = (BN == 128 && H >= 2 * bh) ? 2 : 1;
-  p.tiles_y = (int)((H + bh * MT - 1) / (bh * MT));
+  const int rows = pair ? 2 : MT;                                          // patches stacked per tile
+  p.tiles_y = (int)((H + bh * rows - 1) / (bh * rows));
   p.tiles_n = (int)((Cout + BN - 1) / BN);
   const int64_t tiles = (int64_t)p.tiles_n * p.tiles_x * p.tiles_y * B;
   ADVGRPO_CHECK_ARG(tiles < ((int64_t)1 << 30), "conv2d_nhwc_tf32: too many tiles");
@@ -290,16 +346,17 @@ int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, 
   if (rc) return rc;
   const uint64_t dw[2] = {(uint64_t)(taps * Cin), (uint64_t)Cout};
   const uint64_t sw[2] = {0, (uint64_t)(taps * Cin) * 4};
-  const uint32_t bwt[2] = {CBK, (uint32_t)BN};
+  const uint32_t bwt[2] = {CBK, (uint32_t)(pair ? BN / 2 : BN)};
   rc = make_tmap(&mw, w, 2, dw, sw, bwt, true, true);
   if (rc) return rc;
   const uint64_t dy[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t sy[4] = {0, (uint64_t)Cout * 4, (uint64_t)(W * Cout) * 4, (uint64_t)(H * W * Cout) * 4};
   rc = make_tmap(&my, y, 4, dy, sy, by, true, true);
   if (rc) return rc;
-  if (BN == 256) return launch_conv<256, 1>(mx, mw, my, p, (cudaStream_t)stream);
-  if (MT == 2) return launch_conv<128, 2>(mx, mw, my, p, (cudaStream_t)stream);
-  return launch_conv<128, 1>(mx, mw, my, p, (cudaStream_t)stream);
+  if (pair) return launch_conv<256, 1, true>(mx, mw, my, p, (cudaStream_t)stream);
+  if (BN == 256) return launch_conv<256, 1, false>(mx, mw, my, p, (cudaStream_t)stream);
+  if (MT == 2) return launch_conv<128, 2, false>(mx, mw, my, p, (cudaStream_t)stream);
+  return launch_conv<128, 1, false>(mx, mw, my, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -418,8 +418,9 @@ def test_vae_fused_helpers(ops):
 # ------------------------------------------------------------------ A6 convolution (tcgen05 TF32 implicit GEMM)
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 64, 128, 3), (1, 64, 64, 512, 512, 3), (2, 5, 20, 32, 96, 3),
                                               (1, 128, 128, 256, 128, 3), (2, 32, 32, 512, 256, 1), (1, 7, 9, 64, 32, 1),
-                                              (3, 8, 256, 128, 128, 3)])
-def test_conv2d_nhwc_tf32_matches_torch_fp32(ops, B, H, W, Cin, Cout, k):
+                                              (3, 8, 256, 128, 128, 3), (2, 17, 40, 64, 320, 3)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_conv2d_nhwc_tf32_matches_torch_fp32(ops, B, H, W, Cin, Cout, k, variant):
     """3x3 (zero padding from the TMA out-of-bounds fill, incl. negative start coordinates) and 1x1 convolutions,
     ragged patches (W, H not multiples of the patch), vs an fp32 torch convolution.  TF32 inputs (10-bit mantissa),
     fp32 accumulation: error bound ~2^-10 per operand relative to the accumulated magnitude."""
@@ -434,11 +435,16 @@ def test_conv2d_nhwc_tf32_matches_torch_fp32(ops, B, H, W, Cin, Cout, k):
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     wp = ops.pack_conv_weight_tf32(w)
-    got = ops.conv2d_nhwc_tf32(x, wp, bias, k)
+    from adv_grpo_b200 import _lib
+    _lib.load().advgrpo_debug_set_conv_variant(variant)      # 0 = auto (CTA pairs for >= 256 output channels), 1 = single CTA
+    try:
+        got = ops.conv2d_nhwc_tf32(x, wp, bias, k)
+        got_nb = ops.conv2d_nhwc_tf32(x, wp, None, k)
+    finally:
+        _lib.load().advgrpo_debug_set_conv_variant(0)
     assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
     err = (got - ref).abs().max().item()
     assert err <= 4e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
-    got_nb = ops.conv2d_nhwc_tf32(x, wp, None, k)
     assert torch.allclose(got_nb + bias[None, :, None, None], got, atol=1e-5)
     # borders are where the out-of-bounds fill matters: check them separately
     for sl in ((slice(None), slice(None), 0), (slice(None), slice(None), H - 1), (slice(None), slice(None), slice(None), 0),
