@@ -9,7 +9,7 @@
 //   dV_j += P^T dO_i            (A = P^T from TMEM,   B = dO_i  MN-major)
 //   dK_j += dS^T Q_i            (A = dS^T K-major,    B = Q_i   MN-major)
 //   dQ_i  = dS K_j              (A = dS^T read MN-major, B = K_j MN-major) -> fp32 TMA reduce-add
-// Warp roles (448 threads): warps 0-7 compute (thread = kv row; two warpgroups split the 128
+// Warp roles (512 threads, the last two warps idle): warps 0-7 compute (thread = kv row; two warpgroups split the 128
 // query columns), warps 8-11 drain dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk.tensor add into
 // the fp32 dQ accumulator), warp 12 TMA producer, warp 13 MMA issuer.
 // TMEM columns: S^T 0-127 | dP^T 128-255 | P^T 256-319 | dV 320-383 | dK 384-447 | dQ 448-511.
@@ -45,7 +45,7 @@ constexpr int OFF_DQ = OFF_DS + 2 * kDsBytes;             // 1
 constexpr int OFF_STAT = OFF_DQ + kDqBytes;               // QSTAGES
 constexpr int OFF_BAR = OFF_STAT + QSTAGES * kStatBytes;
 constexpr int kSmemBytes = OFF_BAR + 256 + 1024;
-constexpr int kThreads = 448;
+constexpr int kThreads = 512;   // 14 working warps + 2 idle ones so that every setmaxnreg warpgroup is complete
 constexpr int COL_S = 0, COL_DP = 128, COL_P = 256, COL_DV = 320, COL_DK = 384, COL_DQ = 448;
 
 struct BParams {
@@ -116,6 +116,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
   const int64_t stat_row = ((int64_t)b * p.H + h) * p.S_pad;
 
+  // register re-balancing (setmaxnreg is per 4-warp group): 256 compute threads x 184 + 128 drain x 88 + 128 utility x 56
+  // = 512 x 128, the registers at launch
+  if (warp >= 12) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 12) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -197,8 +201,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (nq > 0) back_half(nq - 1);
       mma_commit(bar_dkv_full);
     }
+  }
   } else if (warp < 8) {
     // ============================== compute: P^T and dS^T ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     const int wg = warp / 4;                          // which half of the query columns
     const int row = (warp % 4) * 32 + lane;           // kv row inside the tile == TMEM lane
     const int kv_idx = kv0 + row;
@@ -211,48 +217,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int i = i_begin + it;
       const int st = it % QSTAGES, bb = it & 1;
       const float* lse2 = reinterpret_cast<const float*>(smem + OFF_STAT + st * kStatBytes);
-      const float* delta = lse2 + T;
-      uint8_t* ds_row = smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128;   // 64-col block = wg
+      const uint32_t ds_row = smem_u32(smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128);   // 64-col block = wg
+      const uint32_t stat_s = smem_u32(lse2);          // lse2[128] then delta[128] (explicit shared-space loads)
       mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);     // lse2 / delta visible
       mbar_wait(bar_s_full, it & 1);
       tc_fence_after();
+      // my 64 query columns of S^T and dP^T -> registers in one go, then release both TMEM regions at once: the MMA
+      // warp issues S^T / dP^T of the NEXT query tile while this tile's exponentials are still running (they were
+      // serialised behind the whole tile before: ncu showed 12 % of the compute warps' time waiting on s_full)
+      uint32_t rs[2][32], rp[2][32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld32(t_s + (wg * 2 + cc) * 32, rs[cc]);
+        tmem_ld32(t_dp + (wg * 2 + cc) * 32, rp[cc]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_s_free);
       if (it > 0) mbar_wait(bar_pv_done, (it - 1) & 1);   // P^T region free
       if (it >= 2) mbar_wait(&bar_ds_empty[bb], ((it - 2) >> 1) & 1);   // dS buffer free
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = wg * 2 + cc;                    // 32-column chunk of the query axis
-        uint32_t rs[32], rp[32];
-        tmem_ld32(t_s + c * 32, rs);
-        tmem_ld32(t_dp + c * 32, rp);
-        tmem_wait_ld();
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int q_a = i * T + c * 32 + e;
-          float p0 = ex2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2[c * 32 + e]));
-          float p1 = ex2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2[c * 32 + e + 1]));
+        for (int e = 0; e < 32; e += 4) {
+          const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
+          const float4 d4 = lds_f4(stat_s + T * 4 + (c * 32 + e) * 4);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int u = 0; u < 4; u += 2) {
+          const int ee = e + u;
+          const int q_a = i * T + c * 32 + ee;
+          float p0 = ex2(fmaf(__uint_as_float(rs[cc][ee]), p.scale_log2, -ls[u]));
+          float p1 = ex2(fmaf(__uint_as_float(rs[cc][ee + 1]), p.scale_log2, -ls[u + 1]));
           if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
           if (p.causal & 1) {
             if (q_a < kv_idx) p0 = 0.f;
             if (q_a + 1 < kv_idx) p1 = 0.f;
           }
-          const float d0 = p0 * (__uint_as_float(rp[e]) - delta[c * 32 + e]);
-          const float d1 = p1 * (__uint_as_float(rp[e + 1]) - delta[c * 32 + e + 1]);
-          pk[e / 2] = pack_bf16(p0, p1);
-          dk[e / 2] = pack_bf16(d0, d1);
+          const float d0 = p0 * (__uint_as_float(rp[cc][ee]) - dl[u]);
+          const float d1 = p1 * (__uint_as_float(rp[cc][ee + 1]) - dl[u + 1]);
+          pk[ee / 2] = pack_bf16(p0, p1);
+          dk[ee / 2] = pack_bf16(d0, d1);
+          }
         }
         tmem_st16(t_p + c * 16, pk);
         // dS^T row: 64 bytes of this chunk = four 16-byte pieces, hand swizzled (128B pattern)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int piece = cc * 4 + k;
-          *reinterpret_cast<uint4*>(ds_row + ((piece ^ (row & 7)) * 16)) =
-              make_uint4(dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+          sts_u4(ds_row + ((piece ^ (row & 7)) * 16), make_uint4(dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]));
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_s_free);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_full);
@@ -290,6 +308,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
   } else {
     // ============================== dQ drain (warps 8-11) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int row = (warp % 4) * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t t_dq = tmem_base + COL_DQ + (static_cast<uint32_t>((warp % 4) * 32) << 16);
     uint8_t* stage = smem + OFF_DQ;
@@ -310,10 +329,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       // two [128 rows x 32 fp32] boxes, 128B-swizzled rows
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        *reinterpret_cast<uint4*>(stage + row * 128 + ((k ^ (row & 7)) * 16)) =
-            make_uint4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
-        *reinterpret_cast<uint4*>(stage + 16384 + row * 128 + ((k ^ (row & 7)) * 16)) =
-            make_uint4(r1[4 * k], r1[4 * k + 1], r1[4 * k + 2], r1[4 * k + 3]);
+        sts_u4(smem_u32(stage) + row * 128 + ((k ^ (row & 7)) * 16),
+               make_uint4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]));
+        sts_u4(smem_u32(stage) + 16384 + row * 128 + ((k ^ (row & 7)) * 16),
+               make_uint4(r1[4 * k], r1[4 * k + 1], r1[4 * k + 2], r1[4 * k + 3]));
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);

@@ -245,7 +245,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (p.bias) {
             v.x += bv[q].x; v.y += bv[q].y; v.z += bv[q].z; v.w += bv[q].w;
           }
-          *reinterpret_cast<float4*>(sbuf + lrow * 128 + ((q ^ (lrow & 7)) * 16)) = v;
+          sts_u4(smem_u32(sbuf) + lrow * 128 + ((q ^ (lrow & 7)) * 16),
+                 make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_b, 128);

@@ -93,6 +93,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);              // 0.5 x (1 + sign(x) erf|x|) = hx + |hx| erf|x|
 }
 
+// staging-tile accesses as explicit LDS / STS (a pointer derived from the aligned dynamic-smem base is generic)
+__device__ __forceinline__ void sts_bf16x8(const uint8_t* p, const bf16x8& v) {
+  sts_u4(smem_u32(p), *reinterpret_cast<const uint4*>(&v));
+}
+__device__ __forceinline__ bf16x8 lds_bf16x8(const uint8_t* p) {
+  const uint4 u = lds_u4(smem_u32(p));
+  return *reinterpret_cast<const bf16x8*>(&u);
+}
+
 // d/dz of the tanh GELU: 0.5 (1 + t) + 0.5 z (1 - t^2) k (1 + 3 c z^2), t = tanh(k (z + c z^3))
 __device__ __forceinline__ float gelu_tanh_grad(float z) {
   const float z2 = z * z;
@@ -373,7 +382,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               if (q < 4) r0[(q & 3) * 8 + j] = __float_as_uint(f[j]);
               else r1[(q & 3) * 8 + j] = __float_as_uint(f[j]);
             }
-            if (has_preact) *reinterpret_cast<bf16x8*>(sbuf + lrow * 128 + ((q ^ (lrow & 7)) * 16)) = z;
+            if (has_preact) sts_bf16x8(sbuf + lrow * 128 + ((q ^ (lrow & 7)) * 16), z);
           }
           const float ssum = ((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]));
           const float rn = rsqrtf(ssum * (1.0f / 64.0f) + p.eps);
@@ -389,7 +398,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = f[j] * rn * fw[j];
             }
-            *reinterpret_cast<bf16x8*>(obuf + lrow * 128 + ((q ^ (lrow & 7)) * 16)) = pack8(f);
+            sts_bf16x8(obuf + lrow * 128 + ((q ^ (lrow & 7)) * 16), pack8(f));
           }
         } else {
 #pragma unroll
@@ -423,25 +432,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + ex2(-2.4554669595930156f * f[j]));
               }
               if (has_preact) {
-                *reinterpret_cast<bf16x8*>(sp) = z;
+                sts_bf16x8(sp, z);
                 sp += BM * 128;
               }
             } else if (is_ggrad) {
               float zz[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(sp), zz);
+              unpack8(lds_bf16x8(sp), zz);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] *= gelu_tanh_grad(zz[j]);
             } else if (has_res) {
               float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
               if (grow) unpack8(gv[q], gg);
-              unpack8(*reinterpret_cast<const bf16x8*>(sp), rr);
+              unpack8(lds_bf16x8(sp), rr);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaf(gg[j], f[j], rr[j]);
             }
           } else if (has_preact) {
             sp += BM * 128;
           }
-          *reinterpret_cast<bf16x8*>(sp) = pack8(f);
+          sts_bf16x8(sp, pack8(f));
         }
         }
         fence_proxy_async_smem();

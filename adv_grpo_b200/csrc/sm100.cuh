@@ -149,6 +149,16 @@ __device__ __forceinline__ float4 lds_f4(uint32_t smem_addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
   return v;
 }
+// Explicit shared-space accesses: pointers derived from the aligned dynamic-smem base lose their address space and
+// would compile to generic LD / ST (long-scoreboard latency) instead of LDS / STS.
+__device__ __forceinline__ void sts_u4(uint32_t smem_addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+  return v;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

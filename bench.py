@@ -320,10 +320,11 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (fused QKV projection + LoRA second product, "
                 f"M={M} N={N} K={K}+{K2})", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
                 "frac": achieved / peak_burst,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the same M, N, K (without the LoRA
-                # blocks) from the ncu --set full capture in profiles/r1_ncu_full_summary.md; algorithmic bytes
-                # (A + W + C in bf16) are 2 * (M*K + N*K + M*N) = 215 MB: no wasted re-reads
-                "traffic": 167.9e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * N),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the same M, N, K, K2 from the ncu
+                # --set full capture in profiles/r1_ncu_full_summary_final.md (70.0 MB read + 108.5 MB written; the
+                # 151 MB output is partly still in L2 when the capture ends); algorithmic bytes (A + W + A2 + W2 + C
+                # in bf16) are 221 MB: no wasted re-reads
+                "traffic": 178.5e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * K2 + N * K2 + M * N),
                 "peak_source": f"{src} burst bf16 (kernel timed alone)"}
     kernels = {
         "attn_fwd_tflops": attn_flops / ms_attn / 1e9, "attn_fwd_frac": attn_flops / ms_attn / 1e9 / peak_burst,
