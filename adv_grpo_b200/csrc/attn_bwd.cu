@@ -31,7 +31,8 @@ using namespace sm100;
 
 constexpr int T = 128;          // tile rows (both q and kv)
 constexpr int D = 64;
-constexpr int QSTAGES = 2;
+constexpr int QSTAGES = 3;   // Q / dO / stats ring: a stage is only released by the back-half MMAs of its tile, so two
+                             // stages left S^T / dP^T of tile it+1 waiting for a load issued one tile too late (ncu: 27 %)
 constexpr int kTile = T * D * 2;            // 16 KB  bf16 [128 x 64]
 constexpr int kDsBytes = T * T * 2;         // 32 KB  bf16 [128 x 128]
 constexpr int kStatBytes = 2 * T * 4;       // lse2 + delta
@@ -40,8 +41,8 @@ constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + kTile;
 constexpr int OFF_Q = OFF_V + kTile;                      // QSTAGES
 constexpr int OFF_DO = OFF_Q + QSTAGES * kTile;           // QSTAGES
-constexpr int OFF_DS = OFF_DO + QSTAGES * kTile;          // 2
-constexpr int OFF_DQ = OFF_DS + 2 * kDsBytes;             // 1
+constexpr int OFF_DS = OFF_DO + QSTAGES * kTile;          // 1 (written at the very end of a tile's math: no double buffer)
+constexpr int OFF_DQ = OFF_DS + kDsBytes;                 // 1
 constexpr int OFF_STAT = OFF_DQ + kDqBytes;               // QSTAGES
 constexpr int OFF_BAR = OFF_STAT + QSTAGES * kStatBytes;
 constexpr int kSmemBytes = OFF_BAR + 256 + 1024;
@@ -116,10 +117,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
   const int64_t stat_row = ((int64_t)b * p.H + h) * p.S_pad;
 
-  // register re-balancing (setmaxnreg is per 4-warp group): 256 compute threads x 184 + 128 drain x 88 + 128 utility x 56
+  // register re-balancing (setmaxnreg is per 4-warp group): 256 compute threads x 176 + 128 drain x 88 + 128 utility x 72
   // = 512 x 128, the registers at launch
   if (warp >= 12) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 12) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -147,7 +148,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
       const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
       auto back_half = [&](int it) {
-        const int st = it % QSTAGES, bb = it & 1;
+        const int st = it % QSTAGES, bb = 0;
         const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
         const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
         const uint32_t ds_s = smem_u32(smem + OFF_DS + bb * kDsBytes);
@@ -160,7 +161,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                  make_smem_desc_sw128(do_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
         mma_commit(bar_pv_done);
         // dK += dS^T Q
-        mbar_wait(&bar_ds_full[bb], (it >> 1) & 1);
+        mbar_wait(&bar_ds_full[bb], it & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < T / 16; ++k)
@@ -204,18 +205,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
   } else if (warp < 8) {
     // ============================== compute: P^T and dS^T ==============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     const int wg = warp / 4;                          // which half of the query columns
     const int row = (warp % 4) * 32 + lane;           // kv row inside the tile == TMEM lane
     const int kv_idx = kv0 + row;
     const bool kv_ok = kv_idx < S;
+    const bool kv_ok_tile = kv0 + T <= S;             // every kv row of this CTA's tile is a real token
     const uint32_t lane_addr = static_cast<uint32_t>((warp % 4) * 32) << 16;
     const uint32_t t_s = tmem_base + COL_S + lane_addr;
     const uint32_t t_dp = tmem_base + COL_DP + lane_addr;
     const uint32_t t_p = tmem_base + COL_P + lane_addr;
     for (int it = 0; it < nq; ++it) {
       const int i = i_begin + it;
-      const int st = it % QSTAGES, bb = it & 1;
+      const int st = it % QSTAGES, bb = 0;
       const float* lse2 = reinterpret_cast<const float*>(smem + OFF_STAT + st * kStatBytes);
       const uint32_t ds_row = smem_u32(smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128);   // 64-col block = wg
       const uint32_t stat_s = smem_u32(lse2);          // lse2[128] then delta[128] (explicit shared-space loads)
@@ -234,41 +236,73 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(bar_s_free);
+      // P^T and dS^T of both chunks into registers first: the exponentials do not depend on the dV MMA of the previous
+      // tile, which is still reading P^T(it-1) from the TMEM columns the stores below overwrite
+      uint32_t pk[2][16], dk[2][16];
+      // element-wise masking (causal diagonal tile, kv rows beyond S) only where a tile needs it: the common tile
+      // runs 5 instructions per element (FFMA, MUFU.EX2, FADD, FMUL, half a pack pair) instead of ~19
+      const bool masked = !kv_ok_tile || ((p.causal & 1) && i * T < kv0 + T);
+      if (masked) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = wg * 2 + cc;                    // 32-column chunk of the query axis
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
+            const float4 d4 = lds_f4(stat_s + T * 4 + (c * 32 + e) * 4);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const int ee = e + u;
+              const int q_a = i * T + c * 32 + ee;
+              float p0 = ex2(fmaf(__uint_as_float(rs[cc][ee]), p.scale_log2, -ls[u]));
+              float p1 = ex2(fmaf(__uint_as_float(rs[cc][ee + 1]), p.scale_log2, -ls[u + 1]));
+              if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
+              if (p.causal & 1) {
+                if (q_a < kv_idx) p0 = 0.f;
+                if (q_a + 1 < kv_idx) p1 = 0.f;
+              }
+              const float d0 = p0 * (__uint_as_float(rp[cc][ee]) - dl[u]);
+              const float d1 = p1 * (__uint_as_float(rp[cc][ee + 1]) - dl[u + 1]);
+              pk[cc][ee / 2] = pack_bf16(p0, p1);
+              dk[cc][ee / 2] = pack_bf16(d0, d1);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = wg * 2 + cc;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
+            const float4 d4 = lds_f4(stat_s + T * 4 + (c * 32 + e) * 4);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const int ee = e + u;
+              const float p0 = ex2(fmaf(__uint_as_float(rs[cc][ee]), p.scale_log2, -ls[u]));
+              const float p1 = ex2(fmaf(__uint_as_float(rs[cc][ee + 1]), p.scale_log2, -ls[u + 1]));
+              const float d0 = p0 * (__uint_as_float(rp[cc][ee]) - dl[u]);
+              const float d1 = p1 * (__uint_as_float(rp[cc][ee + 1]) - dl[u + 1]);
+              pk[cc][ee / 2] = pack_bf16(p0, p1);
+              dk[cc][ee / 2] = pack_bf16(d0, d1);
+            }
+          }
+        }
+      }
       if (it > 0) mbar_wait(bar_pv_done, (it - 1) & 1);   // P^T region free
-      if (it >= 2) mbar_wait(&bar_ds_empty[bb], ((it - 2) >> 1) & 1);   // dS buffer free
+      if (it >= 1) mbar_wait(&bar_ds_empty[bb], (it - 1) & 1);   // dK / dQ MMAs of the previous tile read the dS buffer
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int c = wg * 2 + cc;                    // 32-column chunk of the query axis
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
-          const float4 d4 = lds_f4(stat_s + T * 4 + (c * 32 + e) * 4);
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-          const int ee = e + u;
-          const int q_a = i * T + c * 32 + ee;
-          float p0 = ex2(fmaf(__uint_as_float(rs[cc][ee]), p.scale_log2, -ls[u]));
-          float p1 = ex2(fmaf(__uint_as_float(rs[cc][ee + 1]), p.scale_log2, -ls[u + 1]));
-          if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
-          if (p.causal & 1) {
-            if (q_a < kv_idx) p0 = 0.f;
-            if (q_a + 1 < kv_idx) p1 = 0.f;
-          }
-          const float d0 = p0 * (__uint_as_float(rp[cc][ee]) - dl[u]);
-          const float d1 = p1 * (__uint_as_float(rp[cc][ee + 1]) - dl[u + 1]);
-          pk[ee / 2] = pack_bf16(p0, p1);
-          dk[ee / 2] = pack_bf16(d0, d1);
-          }
-        }
-        tmem_st16(t_p + c * 16, pk);
+        tmem_st16(t_p + (wg * 2 + cc) * 16, pk[cc]);
         // dS^T row: 64 bytes of this chunk = four 16-byte pieces, hand swizzled (128B pattern)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int piece = cc * 4 + k;
-          sts_u4(ds_row + ((piece ^ (row & 7)) * 16), make_uint4(dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]));
+          sts_u4(ds_row + ((piece ^ (row & 7)) * 16),
+                 make_uint4(dk[cc][4 * k], dk[cc][4 * k + 1], dk[cc][4 * k + 2], dk[cc][4 * k + 3]));
         }
       }
       tmem_wait_st();
@@ -277,33 +311,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       fence_proxy_async_smem();
       mbar_arrive(&bar_ds_full[bb]);
     }
-    // ---- epilogue: dK, dV -> bf16 ----
-    if (wg == 0) {
+    // ---- epilogue: dV (warpgroup 0) and dK (warpgroup 1) -> bf16 ----
+    {
       mbar_wait(bar_dkv_full, 0);
       tc_fence_after();
       __nv_bfloat16* base = p.dqkv + ((int64_t)b * S + kv_idx) * 3 * p.H * D;
+      const int which = wg;                           // 0: dV, 1: dK
+      const uint32_t t_acc = tmem_base + (which == 0 ? COL_DV : COL_DK) + lane_addr;
+      const float sc = which == 0 ? 1.0f : p.scale;
+      __nv_bfloat16* dst = base + ((which == 0 ? 2 : 1) * p.H + h) * D;
+      uint32_t r[2][32];
+      tmem_ld32(t_acc, r[0]);
+      tmem_ld32(t_acc + 32, r[1]);
+      tmem_wait_ld();
+      if (kv_ok) {
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {       // 0: dV, 1: dK
-        const uint32_t t_acc = tmem_base + (which == 0 ? COL_DV : COL_DK) + lane_addr;
-        const float sc = which == 0 ? 1.0f : p.scale;
-        __nv_bfloat16* dst = base + ((which == 0 ? 2 : 1) * p.H + h) * D;
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_acc + c * 32, r);
-          tmem_wait_ld();
-          if (kv_ok) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              uint4 v;
-              v.x = pack_bf16(__uint_as_float(r[e + 0]) * sc, __uint_as_float(r[e + 1]) * sc);
-              v.y = pack_bf16(__uint_as_float(r[e + 2]) * sc, __uint_as_float(r[e + 3]) * sc);
-              v.z = pack_bf16(__uint_as_float(r[e + 4]) * sc, __uint_as_float(r[e + 5]) * sc);
-              v.w = pack_bf16(__uint_as_float(r[e + 6]) * sc, __uint_as_float(r[e + 7]) * sc);
-              *reinterpret_cast<uint4*>(dst + c * 32 + e) = v;
-            }
+          for (int e = 0; e < 32; e += 8) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(r[c][e + 0]) * sc, __uint_as_float(r[c][e + 1]) * sc);
+            v.y = pack_bf16(__uint_as_float(r[c][e + 2]) * sc, __uint_as_float(r[c][e + 3]) * sc);
+            v.z = pack_bf16(__uint_as_float(r[c][e + 4]) * sc, __uint_as_float(r[c][e + 5]) * sc);
+            v.w = pack_bf16(__uint_as_float(r[c][e + 6]) * sc, __uint_as_float(r[c][e + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c * 32 + e) = v;
           }
-        }
       }
     }
   } else {
