@@ -219,6 +219,29 @@ class _DualFeedForwardFn(torch.autograd.Function):
         return (dx0, dx1) + (None,) * 12 + (dy0, dy1, None, None, None, None)
 
 
+class _LoraPackFn(torch.autograd.Function):
+    """All LoRA GEMM operands of the model from the ONE flat fp32 master buffer in three kernels: scale (alpha / r on
+    the B factors), gather through a precomputed index (zero padding = index of an appended zero), cast to bf16.
+    Outputs are the per-linear (A_pad, sB_pad) views of the packed buffer; backward concatenates their gradients and
+    gathers them back through the inverse index.  Replaces ~800 cat / pad / mul launches per forward (and as many in
+    the backward and after every optimizer step)."""
+
+    @staticmethod
+    def forward(ctx, flat, layout):
+        ext = torch.cat([flat.detach() * layout["scale"], layout["zero"]])
+        packed = ext.index_select(0, layout["idx"]).to(torch.bfloat16)
+        ctx.layout = layout
+        return tuple(packed[o:o + n].view(shape) for o, n, shape in layout["views"])
+
+    @staticmethod
+    def backward(ctx, *grads):
+        layout = ctx.layout
+        parts = [(g.reshape(-1).to(torch.bfloat16) if g is not None else torch.zeros(n, dtype=torch.bfloat16, device=layout["idx"].device))
+                 for g, (o, n, shape) in zip(grads, layout["views"])]
+        gp = torch.cat(parts)
+        return gp.index_select(0, layout["inv"]).float() * layout["scale"], None
+
+
 class _WT:
     """Lazily materialised transposed copy of a frozen weight (only layers that back-propagate
     to their input ever build one)."""
@@ -288,26 +311,38 @@ class SD3Transformer2DModel(torch.nn.Module):
         self.ada_b = torch.cat(ada_b, 0).contiguous()
         self.w_patch = p["pos_embed.proj.weight"].reshape(d, -1).contiguous()
         self._pos_cache = {}
-        # ---- LoRA (fp32 master parameters, peft layout) ----
+        # ---- LoRA: ONE flat fp32 master parameter (peft-layout A [r, in] / B [out, r] factors are views of it) ----
         self.lora_rank, self.lora_scale = lora_rank, lora_alpha / lora_rank
-        self.lora_A = torch.nn.ParameterDict()
-        self.lora_B = torch.nn.ParameterDict()
+        self.lora_A, self.lora_B = {}, {}            # name -> view of the flat buffer (shares storage; .grad = view of flat.grad)
         self._lora_names = []
+        init, sizes = [], []
         if lora_rank:
             for i in range(L):
                 for t in LORA_TARGETS:
                     name = f"transformer_blocks.{i}.{t}"
                     if name + ".weight" not in p:
                         continue
-                    key = name.replace(".", "_")
                     if lora is not None:
                         a, bb = lora[name]
                     else:
                         a = torch.randn(lora_rank, d) / lora_rank
                         bb = torch.zeros(d, lora_rank)
-                    self.lora_A[key] = torch.nn.Parameter(a.to(self.device_, torch.float32))
-                    self.lora_B[key] = torch.nn.Parameter(bb.to(self.device_, torch.float32))
+                    init.append((name, a.to(torch.float32), bb.to(torch.float32)))
                     self._lora_names.append(name)
+        flat = torch.cat([t.reshape(-1) for _, a, bb in init for t in (a, bb)]) if init else torch.zeros(0)
+        self.lora_flat = torch.nn.Parameter(flat.to(self.device_, torch.float32).contiguous())
+        self.lora_flat.grad = torch.zeros_like(self.lora_flat)
+        off = 0
+        self._lora_off = {}
+        for name, a, bb in init:
+            key = name.replace(".", "_")
+            for dct, t in ((self.lora_A, a), (self.lora_B, bb)):
+                v = self.lora_flat.data[off:off + t.numel()].view(t.shape)
+                v.grad = self.lora_flat.grad[off:off + t.numel()].view(t.shape)
+                dct[key] = v
+                self._lora_off[(key, "A" if dct is self.lora_A else "B")] = off
+                off += t.numel()
+        self._lora_layout = self._make_lora_layout() if init else None
         self.dual_gemm = True            # image + text projections of a block as one dual-problem GEMM launch
         self.fused_qkv_norm = True       # no-grad forward: q/k RMSNorm + concat inside the QKV GEMM epilogue
         self.fused_ff = True             # feed-forward pair as one autograd node (GELU backward in a GEMM epilogue)
@@ -317,14 +352,16 @@ class SD3Transformer2DModel(torch.nn.Module):
 
     # ------------------------------------------------------------------ peft-like surface
     def trainable_parameters(self):
-        return list(self.lora_A.values()) + list(self.lora_B.values())
+        """The single flat LoRA parameter (optimizer / clipping / EMA / all-reduce work on one tensor); the per-layer
+        factors are `lora_A[key]` / `lora_B[key]` views of it."""
+        return [self.lora_flat]
 
     def lora_state_dict(self):
         out = {}
         for name in self._lora_names:
             key = name.replace(".", "_")
-            out[f"base_model.model.{name}.lora_A.weight"] = self.lora_A[key].detach()
-            out[f"base_model.model.{name}.lora_B.weight"] = self.lora_B[key].detach()
+            out[f"base_model.model.{name}.lora_A.weight"] = self.lora_A[key]
+            out[f"base_model.model.{name}.lora_B.weight"] = self.lora_B[key]
         return out
 
     def save_pretrained(self, path):
@@ -357,54 +394,64 @@ class SD3Transformer2DModel(torch.nn.Module):
         return SD3Transformer2DModel._Disable(self)
 
     # ------------------------------------------------------------------ LoRA operand packing
+    def _make_lora_layout(self):
+        """Index maps between the flat master buffer and the packed bf16 GEMM operands: per fused linear
+        (A_pad [r_pad, K], sB_pad [N, r_pad]) with r_pad a multiple of 64 (zero padded; block-diagonal for fused QKV)."""
+        r, d, dev = self.lora_rank, self.d, self.device_
+        n_flat = self.lora_flat.numel()
+        idx_parts, views, keys = [], [], []
+        scale = torch.ones(n_flat, dtype=torch.float32)
+        pos = 0
+        for blk in self.blocks:
+            i = blk["idx"]
+            entry = {}
+            for pk_key, names in (("qkv", ("attn.to_q", "attn.to_k", "attn.to_v")),
+                                  ("cqkv", ("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj")),
+                                  ("out", ("attn.to_out.0",)), ("cout", ("attn.to_add_out",))):
+                ks = [f"transformer_blocks.{i}.{t}".replace(".", "_") for t in names]
+                if ks[0] not in self.lora_A:
+                    continue
+                n = len(ks)
+                rp = ((n * r + 63) // 64) * 64
+                ia = torch.full((rp, d), n_flat, dtype=torch.int64)
+                iw = torch.full((n * d, rp), n_flat, dtype=torch.int64)
+                for j, k in enumerate(ks):
+                    oa, ob = self._lora_off[(k, "A")], self._lora_off[(k, "B")]
+                    ia[j * r:(j + 1) * r] = oa + torch.arange(r * d).view(r, d)
+                    iw[j * d:(j + 1) * d, j * r:(j + 1) * r] = ob + torch.arange(d * r).view(d, r)
+                    scale[ob:ob + d * r] = self.lora_scale
+                for t in (ia, iw):
+                    idx_parts.append(t.reshape(-1))
+                    views.append((pos, t.numel(), tuple(t.shape)))
+                    pos += t.numel()
+                entry[pk_key] = (len(views) - 2, len(views) - 1)
+            keys.append(entry)
+        idx = torch.cat(idx_parts)
+        inv = torch.empty(n_flat, dtype=torch.int64)
+        valid = idx < n_flat
+        inv[idx[valid]] = torch.arange(idx.numel())[valid]
+        return dict(idx=idx.to(dev, torch.int32), inv=inv.to(dev, torch.int32), scale=scale.to(dev),
+                    zero=torch.zeros(1, device=dev), views=views, keys=keys)
+
+    def _packs_from(self, tensors):
+        return [{k: (tensors[ia], tensors[iw]) for k, (ia, iw) in entry.items()} for entry in self._lora_layout["keys"]]
+
     def _pack_lora(self):
-        """bf16 GEMM operands of the LoRA second product per fused linear: (A_pad [r_pad, K], sB_pad
-        [N, r_pad]) with r_pad a multiple of 64 (zero padded; block-diagonal for fused QKV)."""
-        if not self.lora_rank or not self._lora_enabled:
+        if not self.lora_rank or not self._lora_enabled or self._lora_layout is None:
             return [dict() for _ in self.blocks]
-        grad = torch.is_grad_enabled() and any(q.requires_grad for q in self.lora_A.values())
-        if grad:
-            return self._build_lora_packs()
+        if torch.is_grad_enabled() and self.lora_flat.requires_grad:
+            return self._packs_from(_LoraPackFn.apply(self.lora_flat, self._lora_layout))
         if self._lora_cache is not None and not self._lora_dirty:
             return self._lora_cache
         with torch.no_grad():
-            packs = self._build_lora_packs()
-        if self._lora_cache is None:
-            self._lora_cache = packs
-        else:                                   # in place: captured CUDA graphs keep pointing at these buffers
-            for old, new in zip(self._lora_cache, packs):
-                for k in old:
-                    old[k][0].copy_(new[k][0])
-                    old[k][1].copy_(new[k][1])
+            tensors = _LoraPackFn.apply(self.lora_flat, self._lora_layout)
+            if self._lora_cache is None:
+                self._lora_cache_tensors = [t.clone() for t in tensors]
+                self._lora_cache = self._packs_from(self._lora_cache_tensors)
+            else:                               # in place: captured CUDA graphs keep pointing at these buffers
+                torch._foreach_copy_(self._lora_cache_tensors, list(tensors))
         self._lora_dirty = False
         return self._lora_cache
-
-    def _build_lora_packs(self):
-        r, s, d = self.lora_rank, self.lora_scale, self.d
-        packs = []
-        for blk in self.blocks:
-            i = blk["idx"]
-            pk = {}
-
-            def get(t):
-                key = f"transformer_blocks.{i}.{t}".replace(".", "_")
-                return (self.lora_A[key], self.lora_B[key]) if key in self.lora_A else None
-
-            def fused(names):
-                ab = [get(n) for n in names]
-                rp = ((len(ab) * r + 63) // 64) * 64
-                a = torch.cat([x[0] for x in ab] + [torch.zeros(rp - len(ab) * r, d, device=self.device_)], 0)
-                cols = [F.pad(s * x[1], (j * r, rp - (j + 1) * r)) for j, x in enumerate(ab)]
-                w2 = torch.cat(cols, 0)
-                return a.to(torch.bfloat16), w2.to(torch.bfloat16)
-
-            pk["qkv"] = fused(("attn.to_q", "attn.to_k", "attn.to_v"))
-            pk["cqkv"] = fused(("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj"))
-            pk["out"] = fused(("attn.to_out.0",))
-            if get("attn.to_add_out") is not None:
-                pk["cout"] = fused(("attn.to_add_out",))
-            packs.append(pk)
-        return packs
 
     # ------------------------------------------------------------------ building blocks
     def _lin(self, x, blk, key, lora_pack=None, epilogue=ops.EPI_NONE, residual=None, gate=None, rows=1):

@@ -222,17 +222,20 @@ def test_lora_adapter_dir_roundtrip_peft_layout(tmp_path):
         m2.load_adapter(str(tmp_path / "r16"))
     # save_ckpt: EMA weights are what lands on disk, the live weights come back afterwards
     ps = m.trainable_parameters()
+    assert len(ps) == 1 and ps[0] is m.lora_flat                  # one flat master parameter; per-layer factors are views
     ema = EMAModuleWrapper(ps, decay=0.9, update_step_interval=1, device="cpu")
+    k0 = "base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight"
     live = [p.detach().clone() for p in ps]
+    live_k0 = m.lora_state_dict()[k0].clone()
     with torch.no_grad():
         for p in ps:
             p.add_(1.0)
+    assert torch.equal(m.lora_state_dict()[k0], live_k0 + 1.0)    # the views see the update of the flat buffer
     moved = [p.detach().clone() for p in ps]
     root = checkpoint.save_ckpt(str(tmp_path / "run"), m, 7, ema=ema, trainable_parameters=ps, use_ema=True)
     assert root.endswith("checkpoints/checkpoint-7/lora")
     on_disk, _ = checkpoint.load_adapter_dir(root)
-    k0 = "base_model.model.transformer_blocks.0.attn.to_q.lora_A.weight"
-    assert torch.equal(on_disk[k0], live[0])                      # EMA shadow == the weights at wrapper creation
+    assert torch.equal(on_disk[k0], live_k0)                      # EMA shadow == the weights at wrapper creation
     assert all(torch.equal(a, b) for a, b in zip(moved, ps))      # live weights restored
     assert checkpoint.save_ckpt(str(tmp_path / "run2"), m, 1, is_main_process=False).endswith("lora")
     assert not (tmp_path / "run2" / "checkpoints" / "checkpoint-1" / "lora" / "adapter_config.json").exists()
