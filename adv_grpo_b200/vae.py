@@ -1,13 +1,15 @@
 """SD3 VAE decoder (`pipeline.vae` of the reference: `fast.py:667-669`, kept in fp32 like
 `train_sd3_fast_pickscore.py:481`) + the `VaeImageProcessor.postprocess(output_type='pt')` step.
 
-Channels-last fp32 end to end.  The convolutions are plain library calls (cuDNN implicit GEMM, TF32 like the
-reference's allow_tf32); SURVEY.md section 8(f) ranks a tcgen05 implicit-GEMM decoder as "next".  Everything
-between the convolutions is fused into our streaming kernels so that no tensor makes an extra HBM round trip:
+Channels-last fp32 end to end.  Every 3x3 / 1x1 convolution with >= 32 channels on both sides (33 of the 35) runs on
+the tcgen05 TF32 implicit-GEMM kernel of csrc/conv.cu (TF32 tensor cores with fp32 accumulation, like the reference's
+fp32 VAE under cudnn.allow_tf32); conv_in (16 input channels) and conv_out (3 output channels) are library calls.
+Everything between the convolutions is fused into our streaming kernels so that no tensor makes an extra HBM round trip:
   * GroupNorm + SiLU in two passes, with the PRECEDING convolution's bias folded into the statistics/apply
     (the convolutions run bias-free: no separate bias pass, no NCHW<->NHWC copies around group_norm);
   * residual add + conv2 bias (+ shortcut bias) in one pass;
-  * nearest 2x upsampling as one vectorised pass;
+  * nearest 2x upsampling as one vectorised pass; GroupNorm-apply and upsample hand their outputs over as TF32 values
+    (round to nearest) so the tensor core's operand truncation is exact;
   * the single-head mid-block attention as two TF32 batched GEMMs + softmax instead of an fp32 SIMT fmha.
 diffusers state-dict names."""
 import torch

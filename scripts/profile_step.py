@@ -13,6 +13,8 @@ from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
 from adv_grpo_b200.trainer import GRPOTrainer
 
 dev = "cuda:0"
+torch.backends.cuda.matmul.allow_tf32 = True        # as bench.py / train_sd3_fast_pickscore.py:537-538
+torch.backends.cudnn.allow_tf32 = True
 graph = os.environ.get("GRAPH", "0") == "1"
 pipe = StableDiffusion3Pipeline.from_seed(weights.SD35_MEDIUM, weights.VAE_SD3, device=dev, seed=0, use_cuda_graph=graph)
 scorer = PickScoreScorer(device=dev, dtype=torch.bfloat16)
