@@ -31,7 +31,7 @@ struct GCfg {
   // epilogue staging ring: 4 [128 x 64] bf16 tiles where shared memory allows (residual prefetch two column
   // groups ahead; pre-activation + activation tile per group), 2 for the single-CTA 128 x 256 tile
   static constexpr int kNBuf = 4;                      // 2 per epilogue team
-  static constexpr int kStages = TWO ? 5 : ((BN >= 256) ? 3 : (BN >= 192 ? 4 : 5));
+  static constexpr int kStages = TWO ? 5 : ((BN >= 256) ? 3 : (BN >= 192 ? 4 : (BN >= 128 ? 5 : 6)));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -671,16 +671,19 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   // CTA pairs with 256x256 tiles are the most efficient per FLOP (profiles/: 1.37 vs 1.20 PFLOP/s for
   // single-CTA 128x256 tiles at M = 16384), but small-M problems (the 205-token text stream) lose whole
   // waves to quantisation and prefer finer tiles.
+  // 128 x 64 tiles exist for the weight-streaming GEMMs with M <= 128 (one prompt through the text encoders): there
+  // the time is set by how many SMs pull weights concurrently, so N is cut finer to occupy more of them.
   struct Cand { int bn; bool pair; double eff; };
-  const Cand cands[4] = {{256, true, 1.00}, {256, false, 0.87}, {192, true, 0.80}, {128, false, 0.70}};
+  const Cand cands[5] = {{256, true, 1.00}, {256, false, 0.87}, {192, true, 0.80}, {128, false, 0.70}, {64, false, 0.45}};
   int64_t min_m = probs[0].M;
   for (int i = 1; i < nprob; ++i) min_m = probs[i].M < min_m ? probs[i].M : min_m;
   int BN = 128;
   bool pair_ok = false;
   {
     double best = -1;
-    for (int ci = 0; ci < 4; ++ci) {
+    for (int ci = 0; ci < 5; ++ci) {
       const Cand& c = cands[ci];
+      if (c.bn == 64 && (min_m > 128 || nprob != 1 || epilogue == ADVGRPO_EPI_QKNORM)) continue;
       if (c.pair && (g_gemm_variant == 1 || min_m < 256)) continue;
       if (!c.pair && g_gemm_variant == 3 && min_m >= 256 && N >= 256) continue;   // test hook: force pairs
       if (c.bn > 128 && N < c.bn) continue;
@@ -728,6 +731,7 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   if (pair_ok && BN == 192) { ADVGRPO_GEMM_DISPATCH(192, true) }
   if (BN == 256) { ADVGRPO_GEMM_DISPATCH(256, false) }
   if (BN == 192) { ADVGRPO_GEMM_DISPATCH(192, false) }
+  if (BN == 64) { ADVGRPO_GEMM_DISPATCH(64, false) }
   ADVGRPO_GEMM_DISPATCH(128, false)
 #undef ADVGRPO_GEMM_DISPATCH
 }

@@ -27,9 +27,12 @@ def _to_unit_tensor(images, device):
     return images
 
 
+PICKSCORE_KWARGS = {}      # extra PickScoreScorer kwargs of the frozen `pickscore` reward (state_dict=..., cfg=...)
+
+
 def pickscore_score(device):
     from .pickscore_scorer import PickScoreScorer
-    scorer = PickScoreScorer(dtype=torch.float32, device=device)     # own frozen model (rewards.py:564)
+    scorer = PickScoreScorer(dtype=torch.float32, device=device, **PICKSCORE_KWARGS)   # own frozen model (rewards.py:564)
 
     def _fn(images, prompts, metadata):
         return scorer(prompts, _to_unit_tensor(images, device)), {}

@@ -95,3 +95,41 @@ def test_sde_mirror_signature_and_grad(golden, golden_dir):
     prev2, lp2, _, _ = sde_step_with_logprob_new(sch, mo.detach(), ts[:1], t["x"].bfloat16().to(DEV), noise_level=0.8,
                                                  generator=torch.Generator(device=DEV).manual_seed(1))
     assert prev2.dtype == torch.float32 and lp2.shape == (4,)
+
+
+def test_multi_reward_pickscore_plus_host_plugin_config4():
+    """BASELINE config 4's reward_fn {"pickscore": 0.5, "ocr": 0.5} (`rewards.py:1043-1093`): the frozen PickScore
+    reward on the B200 kernels combined with a HOST plugin that returns a Python list (the reference's OcrScorer is a
+    CPU PaddleOCR + Levenshtein plugin, `ocr.py:22-65`; PaddleOCR is not installable here, so a deterministic host
+    function with the same call convention stands in).  score_details carries both rewards and their weighted sum."""
+    from adv_grpo_b200 import rewards, weights
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(4, 3, 96, 96, generator=g).to(DEV)
+    prompts = ["a red cube", "a red cube", "two green spheres", "a sign that says hello"]
+
+    def ocr_factory(device):
+        def _fn(imgs, prm, metadata):
+            assert torch.is_tensor(imgs) and len(prm) == imgs.shape[0]
+            return [float(len(p) % 7) / 7.0 for p in prm], {}            # list[float], like OcrScorer.__call__
+        return _fn
+
+    orig, orig_kw = rewards.score_functions["ocr"], dict(rewards.PICKSCORE_KWARGS)
+    rewards.score_functions["ocr"] = ocr_factory
+    rewards.PICKSCORE_KWARGS.update(cfg=weights.CLIP_TINY, seed=3)
+    try:
+        fn = rewards.multi_score(DEV, {"pickscore": 0.5, "ocr": 0.5})
+        details, extra = fn(images.to(torch.bfloat16), prompts, [{}] * 4, only_strict=True)
+    finally:
+        rewards.score_functions["ocr"] = orig
+        rewards.PICKSCORE_KWARGS.clear()
+        rewards.PICKSCORE_KWARGS.update(orig_kw)
+    assert extra == {} and set(details) == {"pickscore", "ocr", "avg"}
+    ocr = torch.tensor([float(len(p) % 7) / 7.0 for p in prompts], device=DEV)
+    pick = torch.as_tensor(details["pickscore"]).float()
+    assert torch.allclose(details["avg"], 0.5 * pick + 0.5 * ocr, atol=1e-6)
+    # the frozen reward equals an identically initialised co-trained scorer (same kernels, same weights)
+    ref = PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY, seed=3)(prompts, images.to(torch.bfloat16)).float()
+    assert torch.allclose(pick, ref, atol=1e-6)
+    # consumed as in train_sd3_fast_pickscore.py:849-856
+    assert all(torch.as_tensor(v).float().shape == (4,) for v in details.values())
