@@ -24,6 +24,10 @@ SIGNATURES = {
                                             _I64, _F, _F, _P]),
     "advgrpo_cfg_sde_logprob_kl_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64,
                                                _I64, _F, _F, _P]),
+    "advgrpo_cfg_sde_step_logprob_variant": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P,
+                                                     _I64, _I64, _F, _F, _U64, _U64, _P, _SZ, _I, _P]),
+    "advgrpo_cfg_sde_logprob_bwd_variant": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _I64,
+                                                    _I64, _F, _F, _I, _P]),
     "advgrpo_group_advantage_workspace_bytes": (_SZ, [_I64, _I64]),
     "advgrpo_group_advantage": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _SZ, _P]),
     "advgrpo_grpo_clip_loss": (c_int, [_P, _P, _P, _I64, _I64, _D, _D, _D, _P, _P, _P]),

@@ -19,13 +19,16 @@ constexpr int kVec = 8;  // bf16 elements per 16-byte load
 
 struct StepCoef {
   float sigma, sigma_prev, std, c, one_m_sigma, one_m_sigma_prev;
+  // Flow-SDE variant (sde.py:13-73): mu = x * ax + (v * cv) * dt, noise scale s_noise = std * sqrt(-dt)
+  float ax, cv, dt, s_noise;
+  int mode;                 // 0 = Flow-CPS (sde_step_with_logprob_new), 1 = Flow-SDE (sde_step_with_logprob)
   bool valid;
 };
 
 // sde.py:106-122 scalar part; index_for_timestep done on the device (no .item()).
 __device__ __forceinline__ StepCoef step_coef(const float* timesteps, int64_t t_count, int b,
                                               const float* sched_t, const float* sigmas, int T,
-                                              float sin_level) {
+                                              float sin_level, int mode = 0, float noise_level = 0.f) {
   const float t = timesteps[t_count == 1 ? 0 : b];
   // diffusers index_for_timestep: the 2nd match if the timestep occurs more than once
   int first = -1, second = -1;
@@ -45,6 +48,21 @@ __device__ __forceinline__ StepCoef step_coef(const float* timesteps, int64_t t_
   k.c = __fsqrt_rn(__fsub_rn(__fmul_rn(k.sigma_prev, k.sigma_prev), __fmul_rn(k.std, k.std)));
   k.one_m_sigma = __fsub_rn(1.0f, k.sigma);
   k.one_m_sigma_prev = __fsub_rn(1.0f, k.sigma_prev);
+  k.mode = mode;
+  k.s_noise = k.std;
+  k.ax = k.cv = k.dt = 0.f;
+  if (mode == 1) {
+    // sde.py:46-53 in torch's fp32 op order (every scalar below is a [B,1,1,1] fp32 tensor in the reference)
+    const float sigma_max = sigmas[1];
+    const float den = __fsub_rn(1.0f, k.sigma == 1.0f ? sigma_max : k.sigma);
+    k.std = __fmul_rn(__fsqrt_rn(__fdiv_rn(k.sigma, den)), noise_level);
+    k.dt = __fsub_rn(k.sigma_prev, k.sigma);
+    const float std2 = __fmul_rn(k.std, k.std);
+    const float two_sigma = __fmul_rn(2.0f, k.sigma);
+    k.ax = __fadd_rn(1.0f, __fmul_rn(__fdiv_rn(std2, two_sigma), k.dt));
+    k.cv = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(std2, k.one_m_sigma), two_sigma));
+    k.s_noise = __fmul_rn(k.std, __fsqrt_rn(__fmul_rn(-1.0f, k.dt)));
+  }
   return k;
 }
 
@@ -56,6 +74,7 @@ __device__ __forceinline__ float cfg_bf16(float u, float t, float g) {
 }
 
 __device__ __forceinline__ float mean_of(float x, float v, const StepCoef& k) {
+  if (k.mode == 1) return __fadd_rn(__fmul_rn(x, k.ax), __fmul_rn(__fmul_rn(v, k.cv), k.dt));   // sde.py:53
   float x0 = __fsub_rn(x, __fmul_rn(k.sigma, v));                 // sde.py:120
   float x1 = __fadd_rn(x, __fmul_rn(v, k.one_m_sigma));           // sde.py:121
   return __fadd_rn(__fmul_rn(x0, k.one_m_sigma_prev), __fmul_rn(x1, k.c));  // sde.py:122
@@ -103,13 +122,15 @@ struct FwdArgs {
   uint64_t seed, offset;
   double* partial;
   unsigned int* tickets;
+  int mode;
+  float noise_level;
 };
 
 __global__ void __launch_bounds__(kThreads) sde_fwd_kernel(FwdArgs a) {
   __shared__ float scratch[32];
   __shared__ bool is_last;
   const int b = blockIdx.y;
-  const StepCoef k = step_coef(a.timesteps, a.t_count, b, a.sched_t, a.sigmas, a.T, a.sin_level);
+  const StepCoef k = step_coef(a.timesteps, a.t_count, b, a.sched_t, a.sigmas, a.T, a.sin_level, a.mode, a.noise_level);
   const int64_t base = (int64_t)b * a.n;
   const int64_t nvec = a.n / kVec;
   float acc = 0.f;
@@ -143,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) sde_fwd_kernel(FwdArgs a) {
         z[4] = z4[0]; z[5] = z4[1]; z[6] = z4[2]; z[7] = z4[3];
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pv[j] = __fadd_rn(mu[j], __fmul_rn(k.std, z[j]));  // sde.py:131
+      for (int j = 0; j < 8; ++j) pv[j] = __fadd_rn(mu[j], __fmul_rn(k.s_noise, z[j]));  // sde.py:131 / :62
       if (a.prev_out) *reinterpret_cast<bf16x8*>(a.prev_out + e) = pack8(pv);        // fast.py:654-655
     }
 #pragma unroll
@@ -172,6 +193,10 @@ __global__ void __launch_bounds__(kThreads) sde_fwd_kernel(FwdArgs a) {
     s = warp_sum(s);
     if (threadIdx.x == 0) {
       float lp = (float)(-(s / (double)a.n));                      // sde.py:134-137
+      if (k.mode == 1) {                                           // sde.py:64-71 (Gaussian log-density, mean over CHW)
+        const double sn = (double)k.s_noise;
+        lp = (float)(-(s / (double)a.n) / (2.0 * sn * sn) - log(sn) - 0.91893853320467274178);   // log(sqrt(2 pi))
+      }
       a.log_prob[b] = k.valid ? lp : __int_as_float(0x7fc00000);
       if (a.std_out) a.std_out[b] = k.std;
       a.tickets[b] = 0u;  // leave the workspace clean for the next call
@@ -188,14 +213,18 @@ struct BwdArgs {
   __nv_bfloat16 *gvu, *gvt;
   int64_t n;
   float guidance, sin_level;
+  int mode;
+  float noise_level;
 };
 
 __global__ void __launch_bounds__(kThreads) sde_bwd_kernel(BwdArgs a) {
   const int b = blockIdx.y;
-  const StepCoef k = step_coef(a.timesteps, a.t_count, b, a.sched_t, a.sigmas, a.T, a.sin_level);
-  // d mu / d v = (1 - sigma) c - sigma (1 - sigma')
-  const float dmu_dv = k.one_m_sigma * k.c - k.sigma * k.one_m_sigma_prev;
-  const float coef = a.grad_lp[b] * (2.0f / (float)a.n) * dmu_dv;
+  const StepCoef k = step_coef(a.timesteps, a.t_count, b, a.sched_t, a.sigmas, a.T, a.sin_level, a.mode, a.noise_level);
+  // Flow-CPS: d mu / d v = (1 - sigma) c - sigma (1 - sigma'), d logp / d mu = (2/n) (prev - mu)
+  // Flow-SDE: d mu / d v = cv dt,                              d logp / d mu = (prev - mu) / (n s^2)
+  const float dmu_dv = k.mode == 1 ? k.cv * k.dt : k.one_m_sigma * k.c - k.sigma * k.one_m_sigma_prev;
+  const float dlp = k.mode == 1 ? 1.0f / ((float)a.n * k.s_noise * k.s_noise) : 2.0f / (float)a.n;
+  const float coef = a.grad_lp[b] * dlp * dmu_dv;
   // kl[b] = mean((mu - mu_ref)^2):  d kl[b] / d v = (2/n) (mu - mu_ref) d mu / d v
   const float coef_kl = a.mean_ref ? a.grad_kl[b] * (2.0f / (float)a.n) * dmu_dv : 0.f;
   const int64_t base = (int64_t)b * a.n;
@@ -266,6 +295,20 @@ int advgrpo_cfg_sde_step_logprob(const void* v_uncond, const void* v_text, const
                                  float* std_out, int64_t B, int64_t n, float guidance,
                                  float noise_level, uint64_t seed, uint64_t offset, void* workspace,
                                  size_t workspace_bytes, advgrpo_stream_t stream) {
+  return advgrpo_cfg_sde_step_logprob_variant(v_uncond, v_text, x, prev_in, noise, timesteps, t_count, sched_timesteps,
+                                              sigmas, T, prev_out, prev_mean_out, log_prob, std_out, B, n, guidance,
+                                              noise_level, seed, offset, workspace, workspace_bytes, 0, stream);
+}
+
+int advgrpo_cfg_sde_step_logprob_variant(const void* v_uncond, const void* v_text, const void* x,
+                                         const void* prev_in, const float* noise, const float* timesteps,
+                                         int64_t t_count, const float* sched_timesteps, const float* sigmas,
+                                         int64_t T, void* prev_out, float* prev_mean_out, float* log_prob,
+                                         float* std_out, int64_t B, int64_t n, float guidance,
+                                         float noise_level, uint64_t seed, uint64_t offset, void* workspace,
+                                         size_t workspace_bytes, int variant, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(variant == 0 || variant == 1, "cfg_sde_step_logprob: variant must be 0 (Flow-CPS) or 1 (Flow-SDE)");
+  ADVGRPO_CHECK_ARG(variant == 0 || T >= 2, "cfg_sde_step_logprob: Flow-SDE needs at least two schedule steps (sigma_max = sigmas[1])");
   ADVGRPO_CHECK_ARG(v_text && x && timesteps && sched_timesteps && sigmas && log_prob,
                     "cfg_sde_step_logprob: null required pointer");
   ADVGRPO_CHECK_ARG(B > 0 && n > 0 && n % kVec == 0, "cfg_sde_step_logprob: n=%lld must be a positive multiple of 8",
@@ -291,6 +334,7 @@ int advgrpo_cfg_sde_step_logprob(const void* v_uncond, const void* v_text, const
   a.guidance = guidance;
   a.sin_level = (float)sin((double)noise_level * M_PI / 2.0);   // sde.py:119 (python double -> f32 scalar)
   a.seed = seed; a.offset = offset;
+  a.mode = variant; a.noise_level = noise_level;
   a.partial = (double*)workspace;
   a.tickets = (unsigned int*)((char*)workspace + (size_t)B * 2048 * sizeof(double));
   ADVGRPO_CUDA_CALL(cudaMemsetAsync(a.tickets, 0, (size_t)B * sizeof(unsigned int), st));
@@ -305,9 +349,9 @@ int advgrpo_cfg_sde_logprob_bwd(const void* v_uncond, const void* v_text, const 
                                 const float* grad_log_prob, void* grad_v_uncond, void* grad_v_text,
                                 int64_t B, int64_t n, float guidance, float noise_level,
                                 advgrpo_stream_t stream) {
-  return advgrpo_cfg_sde_logprob_kl_bwd(v_uncond, v_text, x, prev_in, timesteps, t_count, sched_timesteps, sigmas, T,
-                                        grad_log_prob, nullptr, nullptr, grad_v_uncond, grad_v_text, B, n, guidance,
-                                        noise_level, stream);
+  return advgrpo_cfg_sde_logprob_bwd_variant(v_uncond, v_text, x, prev_in, timesteps, t_count, sched_timesteps, sigmas, T,
+                                             grad_log_prob, nullptr, nullptr, grad_v_uncond, grad_v_text, B, n, guidance,
+                                             noise_level, 0, stream);
 }
 
 int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, const void* x,
@@ -316,6 +360,18 @@ int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, con
                                    const float* grad_log_prob, const float* grad_kl, const float* mean_ref,
                                    void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
                                    float noise_level, advgrpo_stream_t stream) {
+  return advgrpo_cfg_sde_logprob_bwd_variant(v_uncond, v_text, x, prev_in, timesteps, t_count, sched_timesteps, sigmas, T,
+                                             grad_log_prob, grad_kl, mean_ref, grad_v_uncond, grad_v_text, B, n, guidance,
+                                             noise_level, 0, stream);
+}
+
+int advgrpo_cfg_sde_logprob_bwd_variant(const void* v_uncond, const void* v_text, const void* x,
+                                        const void* prev_in, const float* timesteps, int64_t t_count,
+                                        const float* sched_timesteps, const float* sigmas, int64_t T,
+                                        const float* grad_log_prob, const float* grad_kl, const float* mean_ref,
+                                        void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
+                                        float noise_level, int variant, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(variant == 0 || variant == 1, "cfg_sde_logprob_bwd: variant must be 0 (Flow-CPS) or 1 (Flow-SDE)");
   ADVGRPO_CHECK_ARG((grad_kl == nullptr) == (mean_ref == nullptr), "cfg_sde_logprob_kl_bwd: grad_kl and mean_ref go together");
   ADVGRPO_CHECK_ARG(!mean_ref || aligned16(mean_ref), "cfg_sde_logprob_kl_bwd: mean_ref must be 16-byte aligned");
   ADVGRPO_CHECK_ARG(v_text && x && prev_in && timesteps && sched_timesteps && sigmas &&
@@ -335,6 +391,7 @@ int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, con
   a.t_count = t_count; a.T = (int)T; a.gvu = (__nv_bfloat16*)grad_v_uncond;
   a.gvt = (__nv_bfloat16*)grad_v_text; a.n = n; a.guidance = guidance;
   a.sin_level = (float)sin((double)noise_level * M_PI / 2.0);
+  a.mode = variant; a.noise_level = noise_level;
   int gx = blocks_per_sample(B, n);
   sde_bwd_kernel<<<dim3(gx, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(a);
   ADVGRPO_CUDA_LAUNCH_CHECK();

@@ -26,7 +26,7 @@ def _as_bf16_pair(model_output, sample):
 
 
 def sde_step_with_logprob_new(self, model_output, timestep, sample, noise_level=0.7, prev_sample=None,
-                              generator=None, noise=None):
+                              generator=None, noise=None, _variant=ops.SDE_FLOW_CPS):
     """Flow-CPS reverse step.  Returns (prev_sample, log_prob, prev_sample_mean, std_dev_t) like
     sde.py:139.  `log_prob` is differentiable w.r.t. `model_output` when `prev_sample` is given
     (the replay of train_sd3_fast_pickscore.py:258-267).  Extra keyword `noise` injects the Gaussian
@@ -44,7 +44,7 @@ def sde_step_with_logprob_new(self, model_output, timestep, sample, noise_level=
     sigmas = self.sigmas
     if prev_sample is not None:
         logp, mean, std = ops.sde_logprob_replay(mo, x, prev_sample.to(torch.bfloat16), t, sched_t, sigmas, 1.0,
-                                                 noise_level, cfg=False, want_mean=True)
+                                                 noise_level, cfg=False, want_mean=True, variant=_variant)
         return prev_sample.float(), logp, mean, std.view(*shape)
     seed = 0
     if generator is not None:
@@ -55,9 +55,15 @@ def sde_step_with_logprob_new(self, model_output, timestep, sample, noise_level=
         seed = torch.initial_seed()
     prev, logp, mean, std = ops.cfg_sde_step_logprob(None, mo, x, t, sched_t, sigmas, 1.0, noise_level,
                                                      noise=noise, seed=seed, offset=_next_offset(x.numel()),
-                                                     want_mean=True)
+                                                     want_mean=True, variant=_variant)
     return prev.float(), logp, mean, std.view(*shape)
 
 
-# the scripts import it under this alias (train_sd3_fast_pickscore.py:21)
-sde_step_with_logprob = sde_step_with_logprob_new
+def sde_step_with_logprob(self, model_output, timestep, sample, noise_level=0.7, prev_sample=None, generator=None,
+                          noise=None):
+    """Flow-SDE reverse step with the Gaussian log-density (sde.py:13-73): same signature and return convention; the
+    same fused kernel in its second variant.  (Both training scripts import `sde_step_with_logprob_new` under this
+    name, train_sd3_fast_pickscore.py:21; a module-level import of `sde_step_with_logprob` gets this function, as
+    in the reference file.)"""
+    return sde_step_with_logprob_new(self, model_output, timestep, sample, noise_level, prev_sample, generator, noise,
+                                     _variant=ops.SDE_FLOW_SDE)

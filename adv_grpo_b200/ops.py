@@ -47,10 +47,13 @@ def _bf16c(t):
 
 
 # --------------------------------------------------------------------------- A4 + A5
+SDE_FLOW_CPS, SDE_FLOW_SDE = 0, 1      # sde_step_with_logprob_new (sde.py:77-139) / sde_step_with_logprob (sde.py:13-73)
+
+
 def cfg_sde_step_logprob(v_uncond, v_text, x, timesteps, sched_timesteps, sigmas, guidance_scale,
                          noise_level, prev_sample=None, noise=None, seed=0, offset=0,
-                         want_mean=False, want_prev=True):
-    """Fused CFG + Flow-CPS step + log-prob. Returns (prev_sample_bf16|None, log_prob f32[B],
+                         want_mean=False, want_prev=True, variant=SDE_FLOW_CPS):
+    """Fused CFG + Flow-CPS (or Flow-SDE) step + log-prob. Returns (prev_sample_bf16|None, log_prob f32[B],
     prev_sample_mean f32|None, std_dev_t f32[B])."""
     _need_cuda(v_text, x)
     v_text, x = _bf16c(v_text), _bf16c(x)
@@ -73,11 +76,11 @@ def cfg_sde_step_logprob(v_uncond, v_text, x, timesteps, sched_timesteps, sigmas
     std = torch.empty(B, dtype=torch.float32, device=dev)
     ws_bytes = _lib.query("advgrpo_sde_step_workspace_bytes", B, n)
     ws = _workspace("sde", ws_bytes, dev)
-    _lib.call("advgrpo_cfg_sde_step_logprob", _ptr(v_uncond), _ptr(v_text), _ptr(x), _ptr(prev_in),
+    _lib.call("advgrpo_cfg_sde_step_logprob_variant", _ptr(v_uncond), _ptr(v_text), _ptr(x), _ptr(prev_in),
               _ptr(noise), _ptr(timesteps), timesteps.numel(), _ptr(sched_timesteps), _ptr(sigmas), T,
               _ptr(prev_out), _ptr(mean_out), _ptr(logp), _ptr(std), B, n, float(guidance_scale),
               float(noise_level), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _ptr(ws),
-              ws.numel(), _stream())
+              ws.numel(), int(variant), _stream())
     return prev_out, logp, mean_out, std
 
 
@@ -89,7 +92,7 @@ class _SdeLogProbReplay(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
-                noise_level, cfg, want_mean, mean_ref):
+                noise_level, cfg, want_mean, mean_ref, variant=SDE_FLOW_CPS):
         noise_pred = _bf16c(noise_pred)
         if cfg:
             vu, vt = noise_pred.chunk(2)
@@ -97,13 +100,13 @@ class _SdeLogProbReplay(torch.autograd.Function):
             vu, vt = None, noise_pred
         _, logp, mean, std = cfg_sde_step_logprob(vu, vt, x, timesteps, sched_timesteps, sigmas,
                                                   guidance_scale, noise_level, prev_sample=prev_sample,
-                                                  want_mean=want_mean or mean_ref is not None)
+                                                  want_mean=want_mean or mean_ref is not None, variant=variant)
         kl = torch.empty(0, device=x.device)
         if mean_ref is not None:
             mean_ref = mean_ref.to(torch.float32).contiguous()
             kl = ((mean - mean_ref) ** 2).reshape(x.shape[0], -1).mean(1)
         ctx.save_for_backward(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, mean_ref)
-        ctx.meta = (float(guidance_scale), float(noise_level), bool(cfg))
+        ctx.meta = (float(guidance_scale), float(noise_level), bool(cfg), int(variant))
         ctx.mark_non_differentiable(std)
         if mean is None:
             mean = torch.empty(0, device=x.device)
@@ -113,7 +116,7 @@ class _SdeLogProbReplay(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_logp, _gm, _gs, g_kl):
         noise_pred, x, prev, timesteps, sched_t, sigmas, mean_ref = ctx.saved_tensors
-        gs, nl, cfg = ctx.meta
+        gs, nl, cfg, variant = ctx.meta
         B = x.shape[0]
         n = x.numel() // B
         dev = x.device
@@ -130,21 +133,21 @@ class _SdeLogProbReplay(torch.autograd.Function):
             g_kl = (torch.zeros(B, device=dev) if g_kl is None else g_kl).to(torch.float32).contiguous()
         else:
             g_kl = None
-        _lib.call("advgrpo_cfg_sde_logprob_kl_bwd", _ptr(vu), _ptr(vt), _ptr(x), _ptr(prev), _ptr(timesteps),
+        _lib.call("advgrpo_cfg_sde_logprob_bwd_variant", _ptr(vu), _ptr(vt), _ptr(x), _ptr(prev), _ptr(timesteps),
                   timesteps.numel(), _ptr(sched_t), _ptr(sigmas), sched_t.numel(), _ptr(g_logp), _ptr(g_kl),
-                  _ptr(mean_ref), _ptr(gvu), _ptr(gvt), B, n, gs, nl, _stream())
-        return grad, None, None, None, None, None, None, None, None, None, None
+                  _ptr(mean_ref), _ptr(gvu), _ptr(gvt), B, n, gs, nl, variant, _stream())
+        return grad, None, None, None, None, None, None, None, None, None, None, None
 
 
 def sde_logprob_replay(noise_pred, x, prev_sample, timesteps, sched_timesteps, sigmas, guidance_scale,
-                       noise_level, cfg=True, want_mean=False, mean_ref=None):
+                       noise_level, cfg=True, want_mean=False, mean_ref=None, variant=SDE_FLOW_CPS):
     """Returns (log_prob, prev_sample_mean or None, std_dev_t), plus the per-sample KL term when `mean_ref` is given."""
     dev = x.device
     sched_timesteps = sched_timesteps.to(device=dev, dtype=torch.float32).contiguous()
     sigmas = sigmas.to(device=dev, dtype=torch.float32).contiguous()
     logp, mean, std, kl = _SdeLogProbReplay.apply(noise_pred, _bf16c(x), _bf16c(prev_sample), timesteps,
                                                   sched_timesteps, sigmas, guidance_scale, noise_level, cfg,
-                                                  want_mean, mean_ref)
+                                                  want_mean, mean_ref, variant)
     if mean_ref is not None:
         return logp, (mean if want_mean else None), std, kl
     return logp, (mean if want_mean else None), std

@@ -98,6 +98,25 @@ int advgrpo_cfg_sde_logprob_kl_bwd(const void* v_uncond, const void* v_text, con
                                    void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
                                    float noise_level, advgrpo_stream_t stream);
 
+/* The same two entry points with the step variant selectable: 0 = Flow-CPS (`sde_step_with_logprob_new`, sde.py:77-139,
+ * the one both training scripts import), 1 = Flow-SDE (`sde_step_with_logprob`, sde.py:13-73):
+ *   std = sqrt(sigma / (1 - (sigma == 1 ? sigmas[1] : sigma))) * noise_level, dt = sigma' - sigma,
+ *   mu = x (1 + std^2 / (2 sigma) dt) + v (1 + std^2 (1 - sigma) / (2 sigma)) dt, prev = mu + std sqrt(-dt) eps,
+ *   log_prob = mean_{CHW}( -(prev - mu)^2 / (2 (std sqrt(-dt))^2) - log(std sqrt(-dt)) - log sqrt(2 pi) ). */
+int advgrpo_cfg_sde_step_logprob_variant(const void* v_uncond, const void* v_text, const void* x,
+                                         const void* prev_in, const float* noise, const float* timesteps,
+                                         int64_t t_count, const float* sched_timesteps, const float* sigmas,
+                                         int64_t T, void* prev_out, float* prev_mean_out, float* log_prob,
+                                         float* std_out, int64_t B, int64_t n, float guidance,
+                                         float noise_level, uint64_t seed, uint64_t offset, void* workspace,
+                                         size_t workspace_bytes, int variant, advgrpo_stream_t stream);
+int advgrpo_cfg_sde_logprob_bwd_variant(const void* v_uncond, const void* v_text, const void* x,
+                                        const void* prev_in, const float* timesteps, int64_t t_count,
+                                        const float* sched_timesteps, const float* sigmas, int64_t T,
+                                        const float* grad_log_prob, const float* grad_kl, const float* mean_ref,
+                                        void* grad_v_uncond, void* grad_v_text, int64_t B, int64_t n, float guidance,
+                                        float noise_level, int variant, advgrpo_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * A9: group-relative advantage.  Replaces adv_grpo/stat_tracking.py:18-47
  * (PerPromptStatTracker.update, type='grpo') together with the prompt-identity

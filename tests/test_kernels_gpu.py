@@ -164,6 +164,51 @@ def test_sde_replay_kl_term_matches_autograd_of_oracle(ops, sched):
     assert torch.nn.functional.cosine_similarity(npd2.grad.float().cpu().flatten(), npo2.grad.flatten(), dim=0) > 0.9995
 
 
+def test_flow_sde_variant_golden_g11_and_backward(ops, sched, golden, golden_dir):
+    """The Flow-SDE step (`sde_step_with_logprob`, sde.py:13-73) through the same fused kernel: replay and rollout
+    against the verbatim reference outputs (golden G11: mean bit-exact, log-prob to fp32 summation order), and the
+    backward against autograd of the oracle restatement."""
+    t = torch.load(os.path.join(golden_dir, "g11_tensors.pt"))
+    idx = golden["G11_step_index"]
+    ts = sched.timesteps[idx]
+    _, lp, mean, std = ops.cfg_sde_step_logprob(None, t["v"].bfloat16().to(DEV), t["x"].bfloat16().to(DEV), ts,
+                                                sched.timesteps, sched.sigmas, 1.0, 0.7,
+                                                prev_sample=t["prev"].bfloat16().to(DEV), want_mean=True,
+                                                variant=ops.SDE_FLOW_SDE)
+    assert torch.equal(mean.cpu(), t["mean"])
+    np.testing.assert_allclose(lp.cpu().numpy(), np.array(golden["G11_log_prob"], dtype=np.float32), rtol=3e-6)
+    np.testing.assert_array_equal(std.cpu().numpy(), np.array(golden["G11_std"], dtype=np.float32))
+    prev, lp_r, mean_r, std_r = ops.cfg_sde_step_logprob(None, t["v"][:2].bfloat16().to(DEV), t["x"][:2].bfloat16().to(DEV),
+                                                         sched.timesteps[2:3], sched.timesteps, sched.sigmas, 1.0, 0.7,
+                                                         noise=t["noise"].to(DEV), want_mean=True, variant=ops.SDE_FLOW_SDE)
+    assert torch.equal(mean_r.cpu(), t["mean_rollout"])
+    assert torch.equal(prev.cpu(), t["prev_rollout"].bfloat16())             # stored latents are bf16 (fast.py:654-655)
+    np.testing.assert_allclose(lp_r.cpu().numpy(), np.array(golden["G11_rollout_log_prob"], dtype=np.float32), rtol=3e-6)
+    np.testing.assert_array_equal(std_r.cpu().numpy(), np.full(2, golden["G11_rollout_std"][0], dtype=np.float32))
+    # the reference-surface mirror
+    from adv_grpo_b200.diffusers_patch.sd3_sde_with_logprob import sde_step_with_logprob
+    _, lp_m, mean_m, std_m = sde_step_with_logprob(sched, t["v"].to(DEV), ts, t["x"].to(DEV), noise_level=0.7,
+                                                   prev_sample=t["prev"].to(DEV))
+    assert torch.equal(mean_m.cpu(), t["mean"]) and std_m.shape == (4, 1, 1, 1)
+    # backward (CFG batch) vs autograd of the oracle
+    g = torch.Generator().manual_seed(13)
+    B, shape = 4, (16, 16, 16)
+    npred = torch.randn(2 * B, *shape, generator=g).bfloat16()
+    x, prev_s = t["x"].bfloat16(), t["prev"].bfloat16()
+    w = torch.randn(B, generator=g)
+    npo = npred.float().requires_grad_(True)
+    vu, vt = npo.chunk(2)
+    _, lp_o, _, _ = sde_o.sde_step_with_logprob(sched.sigmas, idx, vu + 4.5 * (vt - vu), x, 0.7, prev_sample=prev_s)
+    (lp_o * w).sum().backward()
+    npd = npred.to(DEV).requires_grad_(True)
+    lp_d, _, _ = ops.sde_logprob_replay(npd, x.to(DEV), prev_s.to(DEV), ts, sched.timesteps, sched.sigmas, 4.5, 0.7,
+                                        cfg=True, variant=ops.SDE_FLOW_SDE)
+    (lp_d * w.to(DEV)).sum().backward()
+    got, ref = npd.grad.float().cpu(), npo.grad
+    assert (got - ref).abs().max() <= 0.02 * ref.abs().max()
+    assert torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0) > 0.9995
+
+
 # ------------------------------------------------------------------ A9 advantage
 def _keys_from_prompts(prompts, L=8):
     table = {}

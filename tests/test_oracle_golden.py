@@ -85,3 +85,20 @@ def test_ema_g10(golden):
         ema_o.ema_step(ema, params, 0.9, 8, step)
         got = [e.sum().item() for e in ema]
         np.testing.assert_allclose(got, golden["G10_ema_sums"][step], rtol=1e-5, atol=1e-5)
+
+
+def test_flow_sde_step_g11(golden, golden_dir):
+    """Flow-SDE variant (sde.py:13-73) against the verbatim reference output: replay with per-sample timesteps
+    (incl. sigma == 1 -> sigma_max) and the rollout form with injected noise, bit for bit."""
+    t = torch.load(os.path.join(golden_dir, "g11_tensors.pt"))
+    s = FlowMatchEulerOracle()
+    s.set_timesteps(10)
+    _, lp, mean, std = sde_o.sde_step_with_logprob(s.sigmas, golden["G11_step_index"], t["v"], t["x"], 0.7,
+                                                   prev_sample=t["prev"])
+    assert torch.equal(mean, t["mean"])
+    np.testing.assert_array_equal(lp.numpy(), np.array(golden["G11_log_prob"], dtype=np.float32))
+    np.testing.assert_array_equal(std.flatten().numpy(), np.array(golden["G11_std"], dtype=np.float32))
+    prev, lp_r, mean_r, std_r = sde_o.sde_step_with_logprob(s.sigmas, [2], t["v"][:2], t["x"][:2], 0.7, noise=t["noise"])
+    assert torch.equal(prev, t["prev_rollout"]) and torch.equal(mean_r, t["mean_rollout"])
+    np.testing.assert_array_equal(lp_r.numpy(), np.array(golden["G11_rollout_log_prob"], dtype=np.float32))
+    np.testing.assert_array_equal(std_r.flatten().numpy(), np.array(golden["G11_rollout_std"], dtype=np.float32))
