@@ -239,3 +239,39 @@ def test_lora_adapter_dir_roundtrip_peft_layout(tmp_path):
     assert all(torch.equal(a, b) for a, b in zip(moved, ps))      # live weights restored
     assert checkpoint.save_ckpt(str(tmp_path / "run2"), m, 1, is_main_process=False).endswith("lora")
     assert not (tmp_path / "run2" / "checkpoints" / "checkpoint-1" / "lora" / "adapter_config.json").exists()
+
+
+def test_reference_image_index_matches_reference_preprocessing(tmp_path):
+    """§8f on-disk format: the {prompt: [files]} index + Image.open -> Resize((S,S)) -> ToTensor of
+    `train_pick:705-707,773-799` (PIL bilinear with antialiasing, [0,1] float32 CHW), fallback image, caching, hook."""
+    import json
+    from PIL import Image
+    from adv_grpo_b200.reference_images import ReferenceImageIndex
+    rng = np.random.RandomState(0)
+    root = tmp_path / "imgs"
+    root.mkdir()
+    names = []
+    for i, (h, w) in enumerate([(40, 64), (100, 30), (16, 16)]):
+        arr = rng.randint(0, 256, size=(h, w, 3), dtype=np.uint8)
+        Image.fromarray(arr).save(root / f"r{i}.png")
+        names.append(f"r{i}.png")
+    Image.fromarray(np.full((8, 8, 3), 7, dtype=np.uint8)).save(tmp_path / "default.png")
+    idx_path = tmp_path / "index.json"
+    json.dump({"a cat": names[:2], "a dog": [names[2], "missing.png"]}, open(idx_path, "w"))
+    idx = ReferenceImageIndex(str(idx_path), str(root), size=32, device="cpu", default_image=str(tmp_path / "default.png"))
+    got = idx("a cat")
+    assert got.shape == (2, 3, 32, 32) and got.dtype == torch.float32 and 0.0 <= got.min() and got.max() <= 1.0
+    for k, name in enumerate(names[:2]):                               # the reference's own expression
+        ref = np.asarray(Image.open(root / name).convert("RGB").resize((32, 32), Image.BILINEAR), dtype=np.float32) / 255.0
+        assert np.array_equal(got[k].permute(1, 2, 0).numpy(), ref)
+    dog = idx("a dog")
+    assert dog.shape == (2, 3, 32, 32) and torch.allclose(dog[1], torch.full((3, 32, 32), 7 / 255.0))   # fallback image
+    assert idx("a cat") is got                                         # cached
+    assert idx("a cat", n=5).shape == (5, 3, 32, 32) and torch.equal(idx("a cat", n=5)[2], got[0])
+    with pytest.raises(KeyError):
+        idx("a bird")
+    fn = idx.as_trainer_fn(["a dog", "a cat"])
+    assert torch.equal(fn(1, 2, 32), got)
+    strict = ReferenceImageIndex(str(idx_path), str(root), size=32, device="cpu")
+    with pytest.raises(FileNotFoundError):
+        strict("a dog")
