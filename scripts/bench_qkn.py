@@ -37,6 +37,8 @@ cases = {
     "single GELU (img)": lambda: ops.gemm(x, w[0], bias=bias[0], epilogue=ops.EPI_GELU_TANH),
     "single NONE (txt)": lambda: ops.gemm(c, w[1], bias=bias[1]),
 }
+la = [(torch.randn(128, K, device=DEV, generator=g) / 32).bfloat16() for _ in range(2)]
+cases["LoRA down-projection dual (N=128)"] = lambda: ops.gemm_dual((x, c), la)
 with torch.no_grad():
     for name, fn in cases.items():
         print(f"{name:40s} {timeit(fn):8.1f} us", flush=True)
