@@ -209,12 +209,16 @@ class GRPOTrainer:
             ref_images = self.reference_image_fn(idx, G, c.resolution)
             prompts = [prompt] * G
             lat = torch.stack(latents, dim=1)                       # [G, T+1, 16, h, w]   train_pick:806-810
+            # generated and reference images through the reward model as ONE batch of 2G (the reference submits two
+            # reward_fn calls, train_pick:816-817; scores are per image, so the split halves are the same values)
+            both = self._score(torch.cat([images.to(torch.float32), ref_images.to(images.device, torch.float32)]),
+                               prompts + prompts)
             samples.append({
                 "prompt_ids": self._prompt_ids(prompt, G),
                 "prompt_embeds": pe.repeat(G, 1, 1), "pooled_prompt_embeds": pp.repeat(G, 1),
                 "timesteps": torch.stack(timesteps, dim=1), "latents": lat[:, :-1], "next_latents": lat[:, 1:],
                 "log_probs": torch.stack(log_probs, dim=1),
-                "rewards": self._score(images, prompts), "reference_rewards": self._score(ref_images, prompts),
+                "rewards": {k: v[:G] for k, v in both.items()}, "reference_rewards": {k: v[G:] for k, v in both.items()},
                 "images": images, "ref_images": ref_images, "prompts": prompts,
             })
         return samples
