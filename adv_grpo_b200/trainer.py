@@ -359,6 +359,51 @@ class GRPOTrainer:
             self.last_info.update(loss=m[0], approx_kl=m[1], clipfrac=m[2], clipfrac_gt_one=m[3], clipfrac_lt_one=m[4],
                                   policy_loss=m[5])
 
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def evaluate(self, prompt_indices=None, batch_size=None):
+        """`eval` of `train_pick:269-382` (every `config.eval_freq` epochs): EMA weights swapped in, the test prompts in
+        batches of `sample.test_batch_size` through the SAME rollout function as a deterministic ODE (`noise_level=0`,
+        `sample.eval_num_steps` steps, one image per prompt, generator seeded with 0 per batch), rewards gathered over
+        ranks, `eval_reward_<key>` = mean over the values != -10.  Returns (metrics, last_batch_images); the wandb image
+        logging of the reference is not part of this path."""
+        c, s = self.config, self.config.sample
+        idxs = list(range(len(self.prompts))) if prompt_indices is None else list(prompt_indices)
+        idxs = idxs[self.rank::self.world]                                    # test DataLoader sharded by accelerate
+        bs = int(batch_size or s.test_batch_size)
+        if c.train.ema and self.ema is not None:
+            self.ema.copy_ema_to(self.params, store_temp=True)
+            self.transformer.invalidate_lora_cache()
+        self.transformer.eval()
+        all_rewards, images = {}, None
+        try:
+            for b0 in range(0, len(idxs), bs):
+                batch = idxs[b0:b0 + bs]
+                prompts = [self.prompts[i] for i in batch]
+                emb = [self.embedder(i) for i in batch]
+                pe, pp = torch.cat([e[0] for e in emb]), torch.cat([e[1] for e in emb])
+                generator = torch.Generator(device=self.device).manual_seed(0)
+                images, _, _, _ = pipeline_with_logprob_random(
+                    self.pipeline, prompt_embeds=pe, pooled_prompt_embeds=pp,
+                    negative_prompt_embeds=self.neg_embeds.repeat(len(batch), 1, 1),
+                    negative_pooled_prompt_embeds=self.neg_pooled.repeat(len(batch), 1),
+                    num_inference_steps=s.eval_num_steps, guidance_scale=s.guidance_scale, output_type="pt",
+                    height=c.resolution, width=c.resolution, noise_level=0, mini_num_image_per_prompt=1,
+                    process_index=self.rank, sample_num_steps=s.num_steps, random_timestep=s.get("random_timestep", 0),
+                    generator=generator)
+                for k, v in self._score(images, prompts).items():
+                    all_rewards.setdefault(k, []).append(all_gather_cat(v))
+        finally:
+            if c.train.ema and self.ema is not None:
+                self.ema.copy_temp_to(self.params)
+                self.transformer.invalidate_lora_cache()
+        metrics = {}
+        for k, vals in all_rewards.items():
+            v = torch.cat(vals)
+            keep = v != -10
+            metrics[f"eval_reward_{k}"] = v[keep].mean() if keep.any() else v.new_tensor(float("nan"))
+        return metrics, images
+
     # ------------------------------------------------------------------ checkpoint
     def save_ckpt(self, save_dir):
         """`save_ckpt` (`train_pick:389-398`): peft adapter directory with the EMA weights swapped in, rank 0 only."""

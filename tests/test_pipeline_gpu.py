@@ -158,3 +158,28 @@ def test_grpo_epoch_with_kl_regulariser():
     tr.transformer.invalidate_lora_cache()
     info = tr.run_epoch()
     assert float(info["kl_loss"]) == 0.0          # adapter == identity -> mu == mu_ref exactly (same fused forward)
+
+
+def test_trainer_evaluate_is_deterministic_ode_and_restores_weights():
+    """`eval` of `train_pick:269-382`: noise_level = 0 rollout (eval_num_steps, one image per prompt, seed 0 per batch),
+    rewards averaged per key; with EMA the shadow weights are swapped in and the live weights restored afterwards."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.config import load_config
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from adv_grpo_b200.trainer import GRPOTrainer
+    pipe, cfg, *_ = _tiny_pipeline(True)
+    c = load_config("pickscore_cotrain_sd3_fast")
+    c.resolution, c.sample.num_steps, c.sample.eval_num_steps, c.sample.test_batch_size = 128, 4, 6, 2
+    c.sample.mini_num_image_per_prompt, c.sample.num_batches_per_epoch, c.train_d = 2, 1, False
+    c.train.gradient_accumulation_steps, c.train.ema = 1, True
+    tr = GRPOTrainer(c, pipe, [f"prompt {i}" for i in range(5)], scorer=PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY),
+                     device=DEV)
+    tr.run_epoch()                                                     # moves the live weights away from the EMA shadow
+    live = [p.detach().clone() for p in tr.params]
+    m1, img1 = tr.evaluate()
+    m2, img2 = tr.evaluate(prompt_indices=range(5), batch_size=2)
+    assert set(m1) == {"eval_reward_pickscore_cotrain", "eval_reward_avg"}
+    assert all(torch.isfinite(v) for v in m1.values())
+    assert all(torch.equal(m1[k], m2[k]) for k in m1) and torch.equal(img1, img2)      # deterministic ODE, seed 0
+    assert img1.shape == (1, 3, 128, 128)                               # 5 prompts in batches of 2: the last batch has one
+    assert all(torch.equal(a, b) for a, b in zip(live, tr.params))      # EMA swapped out again
