@@ -36,13 +36,13 @@ constexpr int QSTAGES = 3;   // Q / dO / stats ring: a stage is only released by
 constexpr int kTile = T * D * 2;            // 16 KB  bf16 [128 x 64]
 constexpr int kDsBytes = T * T * 2;         // 32 KB  bf16 [128 x 128]
 constexpr int kStatBytes = 2 * T * 4;       // lse2 + delta
-constexpr int kDqBytes = T * D * 4;         // 32 KB  fp32 [128 x 64]
+constexpr int kDqBytes = T * 32 * 4;        // 16 KB  fp32 [128 x 32]: the dQ tile is drained as two half-width boxes
 constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + kTile;
 constexpr int OFF_Q = OFF_V + kTile;                      // QSTAGES
 constexpr int OFF_DO = OFF_Q + QSTAGES * kTile;           // QSTAGES
-constexpr int OFF_DS = OFF_DO + QSTAGES * kTile;          // 1 (written at the very end of a tile's math: no double buffer)
-constexpr int OFF_DQ = OFF_DS + kDsBytes;                 // 1
+constexpr int OFF_DS = OFF_DO + QSTAGES * kTile;          // 2 (dK / dQ MMAs of tile it-1 still read one while tile it writes the other)
+constexpr int OFF_DQ = OFF_DS + 2 * kDsBytes;             // 1
 constexpr int OFF_STAT = OFF_DQ + kDqBytes;               // QSTAGES
 constexpr int OFF_BAR = OFF_STAT + QSTAGES * kStatBytes;
 constexpr int kSmemBytes = OFF_BAR + 256 + 1024;
@@ -148,7 +148,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
       const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
       auto back_half = [&](int it) {
-        const int st = it % QSTAGES, bb = 0;
+        const int st = it % QSTAGES, bb = it & 1;
         const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
         const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
         const uint32_t ds_s = smem_u32(smem + OFF_DS + bb * kDsBytes);
@@ -161,7 +161,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                  make_smem_desc_sw128(do_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
         mma_commit(bar_pv_done);
         // dK += dS^T Q
-        mbar_wait(&bar_ds_full[bb], it & 1);
+        mbar_wait(&bar_ds_full[bb], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < T / 16; ++k)
@@ -217,7 +217,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t t_p = tmem_base + COL_P + lane_addr;
     for (int it = 0; it < nq; ++it) {
       const int i = i_begin + it;
-      const int st = it % QSTAGES, bb = 0;
+      const int st = it % QSTAGES, bb = it & 1;
       const float* lse2 = reinterpret_cast<const float*>(smem + OFF_STAT + st * kStatBytes);
       const uint32_t ds_row = smem_u32(smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128);   // 64-col block = wg
       const uint32_t stat_s = smem_u32(lse2);          // lse2[128] then delta[128] (explicit shared-space loads)
@@ -292,7 +292,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }
       if (it > 0) mbar_wait(bar_pv_done, (it - 1) & 1);   // P^T region free
-      if (it >= 1) mbar_wait(&bar_ds_empty[bb], (it - 1) & 1);   // dK / dQ MMAs of the previous tile read the dS buffer
+      if (it >= 2) mbar_wait(&bar_ds_empty[bb], ((it - 2) >> 1) & 1);   // dS buffer free (dK / dQ MMAs of tile it-2 done)
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -355,24 +355,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(bar_dq_free);
-      // previous reduce must have finished reading the staging tile
-      if (tid == 0) tma_store_wait_read();
-      named_bar_sync(1, 128);
-      // two [128 rows x 32 fp32] boxes, 128B-swizzled rows
+      // two [128 rows x 32 fp32] boxes through ONE 16 KB staging tile (128B-swizzled rows), one after the other
+      const int grow = (int)(stat_row + (int64_t)i * T);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        sts_u4(smem_u32(stage) + row * 128 + ((k ^ (row & 7)) * 16),
-               make_uint4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]));
-        sts_u4(smem_u32(stage) + 16384 + row * 128 + ((k ^ (row & 7)) * 16),
-               make_uint4(r1[4 * k], r1[4 * k + 1], r1[4 * k + 2], r1[4 * k + 3]));
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (tid == 0 && !(p.causal & 2)) {   // bit 1: timing experiment only (skip the dQ reduce)
-        const int grow = (int)(stat_row + (int64_t)i * T);
-        tma_reduce_add_2d(&tm_dq, stage, 0, grow);
-        tma_reduce_add_2d(&tm_dq, stage + 16384, 32, grow);
-        tma_store_commit();
+      for (int hf = 0; hf < 2; ++hf) {
+        if (tid == 0) tma_store_wait_read();          // the previous reduce finished reading the staging tile
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t* r = hf == 0 ? r0 : r1;
+          sts_u4(smem_u32(stage) + row * 128 + ((k ^ (row & 7)) * 16),
+                 make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (tid == 0 && !(p.causal & 2)) {   // bit 1: timing experiment only (skip the dQ reduce)
+          tma_reduce_add_2d(&tm_dq, stage, hf * 32, grow);
+          tma_store_commit();
+        }
       }
     }
     if (tid == 0) tma_store_wait_all();
