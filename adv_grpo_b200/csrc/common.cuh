@@ -76,21 +76,29 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return warp_sum(t);
 }
 
+// Eight bf16 values as ONE 16-byte vector.  The payload is a built-in uint4 so that `*reinterpret_cast<const bf16x8*>(p)`
+// compiles to a single LDG.128 / STG.128 (an array of four __nv_bfloat162 members was split into four 32-bit accesses,
+// which quadrupled the L1 wavefronts of every streaming kernel).
 struct alignas(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
 };
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+  const uint32_t w[4] = {p.u.x, p.u.y, p.u.z, p.u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
+    f[2 * i] = __uint_as_float(w[i] << 16);               // low half = element 2i
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);   // high half = element 2i + 1
   }
 }
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
-  bf16x8 p;
+  uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  bf16x8 p;
+  p.u = make_uint4(w[0], w[1], w[2], w[3]);
   return p;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
