@@ -10,6 +10,7 @@ namespace advgrpo {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxGroups = 64;     // checked in the entry point
 
 __global__ void __launch_bounds__(kThreads)
 gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, double* __restrict__ sums, int64_t HW,
@@ -64,16 +65,28 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ in_bias, 
   const int64_t total = HW * quads;
   const int cpg = C / groups;
   const double cnt = (double)HW * cpg;
-  const float* xb = x + (int64_t)n * HW * C;
-  float* yb = y + (int64_t)n * HW * C;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
-    const int q = (int)(i % quads);
-    const int c = q * 4;
-    const int g = c / cpg;
+  // per-group mean / rstd once per CTA (double arithmetic on the f64 sums), then float lookups in the streaming loop:
+  // recomputing them per float4 put an FP64 divide + sqrt on every element quad (FP64 runs at 1/64 rate on this part)
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  for (int g = threadIdx.x; g < groups; g += kThreads) {
     const double m = sums[((int64_t)n * groups + g) * 2] / cnt;
     double var = sums[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
     if (var < 0) var = 0;
-    const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[g] = (float)m;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float* xb = x + (int64_t)n * HW * C;
+  float* yb = y + (int64_t)n * HW * C;
+  // channel-quad index carried incrementally (no 64-bit modulo per element); group index by shift when cpg is 2^k
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int dq = (int)(stride % quads);
+  const int cpg_shift = (cpg & (cpg - 1)) == 0 ? __ffs(cpg) - 1 : -1;
+  int q = (int)(((int64_t)blockIdx.x * kThreads + threadIdx.x) % quads);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride, q = (q + dq >= quads ? q + dq - quads : q + dq)) {
+    const int c = q * 4;
+    const int g = cpg_shift >= 0 ? (c >> cpg_shift) : c / cpg;
+    const float mean = s_mean[g], rstd = s_rstd[g];
     float4 v = *reinterpret_cast<const float4*>(xb + i * 4);
     if (in_bias) {
       const float4 ib = *reinterpret_cast<const float4*>(in_bias + c);
@@ -100,11 +113,14 @@ __global__ void __launch_bounds__(kThreads)
 add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias,
                 float* __restrict__ out, int64_t total4, int C) {
   const int quads = C / 4;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (int64_t)gridDim.x * kThreads) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int dq = (int)(stride % quads);
+  int q = (int)(((int64_t)blockIdx.x * kThreads + threadIdx.x) % quads);
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += stride, q = (q + dq >= quads ? q + dq - quads : q + dq)) {
     const float4 x = reinterpret_cast<const float4*>(a)[i];
     const float4 y = reinterpret_cast<const float4*>(b)[i];
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) bb = *reinterpret_cast<const float4*>(bias + (i % quads) * 4);
+    if (bias) bb = *reinterpret_cast<const float4*>(bias + q * 4);
     reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x + bb.x, x.y + y.y + bb.y, x.z + y.z + bb.z, x.w + y.w + bb.w);
   }
 }
