@@ -297,6 +297,10 @@ class GRPOTrainer:
         if self.world == 1:
             return
         grads = [p.grad for p in self.params]
+        if len(grads) == 1:                          # the flat LoRA master parameter: reduce its gradient in place
+            dist.all_reduce(grads[0])
+            grads[0] /= self.world
+            return
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat)
         flat /= self.world
