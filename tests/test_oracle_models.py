@@ -180,3 +180,57 @@ def test_t5_encoder_oracle_matches_transformers():
         ref = m(ids)[0]
         got = te_o.t5_encoder(p, dict(layers=3, heads=4, d_kv=16), ids)
     assert torch.allclose(got, ref, atol=3e-5, rtol=1e-4), (got - ref).abs().max()
+
+
+def test_mmdit_joint_block_oracle_matches_flux_double_stream_block():
+    """torchtitan's FLUX `DoubleStreamBlock` (installed here) is structurally the MMDiT
+    joint block (adaLN-Zero with 6 chunks in the order shift/scale/gate x2 from `Linear(SiLU(vec))`, affine-free
+    LayerNorm eps 1e-6, per-head RMS q/k norm, ONE softmax over the concatenated text+image tokens, gated
+    residuals, GELU(tanh) feed-forward).  Differences: FLUX concatenates [text, image] (attention without a mask
+    is invariant to the key order, so the per-stream outputs are the same) and applies RoPE (identity at
+    position 0).  Map the oracle's diffusers-named weights of a non-dual, non-last block onto it."""
+    import pytest
+    layers = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    from adv_grpo_b200 import weights
+    from oracle.mmdit import MMDiTOracle, timestep_embedding
+
+    cfg = dict(weights.MMDIT_TINY, num_layers=3, dual_layers=())
+    p = weights.init_mmdit(cfg, seed=11, device="cpu", dtype=torch.float32)
+    H, D = cfg["heads"], cfg["head_dim"]
+    d = H * D
+    blk = layers.DoubleStreamBlock(d, H, mlp_ratio=4.0, qkv_bias=True).eval()
+    for n in (blk.img_attn.norm, blk.txt_attn.norm):
+        n.query_norm.eps = n.key_norm.eps = 1e-6          # diffusers RMSNorm(eps=1e-6); nn.RMSNorm defaults to finfo.eps
+    i = 1
+    pre = f"transformer_blocks.{i}"
+    sd = {}
+    for s in ("weight", "bias"):
+        sd[f"img_mod.lin.{s}"] = p[f"{pre}.norm1.linear.{s}"]
+        sd[f"txt_mod.lin.{s}"] = p[f"{pre}.norm1_context.linear.{s}"]
+        sd[f"img_attn.qkv.{s}"] = torch.cat([p[f"{pre}.attn.to_{n}.{s}"] for n in "qkv"])
+        sd[f"txt_attn.qkv.{s}"] = torch.cat([p[f"{pre}.attn.add_{n}_proj.{s}"] for n in "qkv"])
+        sd[f"img_attn.proj.{s}"] = p[f"{pre}.attn.to_out.0.{s}"]
+        sd[f"txt_attn.proj.{s}"] = p[f"{pre}.attn.to_add_out.{s}"]
+        sd[f"img_mlp.0.{s}"] = p[f"{pre}.ff.net.0.proj.{s}"]
+        sd[f"img_mlp.2.{s}"] = p[f"{pre}.ff.net.2.{s}"]
+        sd[f"txt_mlp.0.{s}"] = p[f"{pre}.ff_context.net.0.proj.{s}"]
+        sd[f"txt_mlp.2.{s}"] = p[f"{pre}.ff_context.net.2.{s}"]
+    sd["img_attn.norm.query_norm.weight"] = p[f"{pre}.attn.norm_q.weight"]
+    sd["img_attn.norm.key_norm.weight"] = p[f"{pre}.attn.norm_k.weight"]
+    sd["txt_attn.norm.query_norm.weight"] = p[f"{pre}.attn.norm_added_q.weight"]
+    sd["txt_attn.norm.key_norm.weight"] = p[f"{pre}.attn.norm_added_k.weight"]
+    blk.load_state_dict(sd, strict=True)
+
+    g = torch.Generator().manual_seed(12)
+    B, N, T = 2, 36, 13
+    x, c, temb = torch.randn(B, N, d, generator=g), torch.randn(B, T, d, generator=g), torch.randn(B, d, generator=g)
+    pe = torch.eye(2).expand(1, 1, T + N, D // 2, 2, 2)   # RoPE at position 0
+    oracle = MMDiTOracle(p, dict(cfg, dual_layers=set()))
+    with torch.no_grad():
+        ref_x, ref_c = blk(x, c, temb, pe)
+        got_x, got_c = oracle.block(i, x, c, temb)
+    assert torch.allclose(got_x, ref_x, atol=2e-5, rtol=1e-4), (got_x - ref_x).abs().max()
+    assert torch.allclose(got_c, ref_c, atol=2e-5, rtol=1e-4), (got_c - ref_c).abs().max()
+    # the sinusoidal timestep features (diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0))
+    t = torch.tensor([1000.0, 464.876, 8.9286])
+    assert torch.allclose(timestep_embedding(t), layers.timestep_embedding(t, 256, time_factor=1.0), atol=1e-6)
