@@ -83,7 +83,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_sample(steps=1, warmup=0, verbose=False):
+def cpu_reference_sample(steps=1, warmup=0, verbose=False, budget_s=None):
     """Times the oracle (the CPU restatement of the reference algorithm, oracle/) on the host cores on a
     bounded sample of the config-2 workload and extrapolates by the exact step counts:
       per sample = 10 x MMDiT fwd (CFG pair, B=2) + 2 x (fwd + bwd, B=2) + 1 VAE decode + 2 PickScore image fwd
@@ -113,7 +113,12 @@ def cpu_reference_sample(steps=1, warmup=0, verbose=False):
     ctx = torch.randn(2, 205, 4096, generator=g)
     pooled = torch.randn(2, 2048, generator=g)
     results = []
+    t_start = time.perf_counter()
     for it in range(warmup + steps):
+        # bounded run: the CPU timings repeat to ~2 %, so once the wall budget is spent the remaining steps
+        # would only repeat the same sample; the executed count is reported in the description
+        if budget_s is not None and results and time.perf_counter() - t_start > budget_s:
+            break
         with torch.no_grad():
             a = time.perf_counter()
             oracle.forward(x, t, ctx, pooled)
@@ -138,6 +143,8 @@ def cpu_reference_sample(steps=1, warmup=0, verbose=False):
     desc = ("oracle (torch fp32 restatement of the reference path) on host cores: timed 1 MMDiT fwd at B=2 (one CFG "
             "pair), 1 fwd+bwd at B=2, 1 VAE decode, 1 PickScore image fwd at SD3.5-M/512px shapes; per-sample time = "
             "10*fwd + 2*(fwd+bwd) + vae + 2*clip (extrapolated by step counts)")
+    if len(results) < steps:
+        desc += f"; {len(results)} of {steps} requested steps executed within the {budget_s:.0f} s wall budget"
     return results, cores, desc
 
 
@@ -145,9 +152,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, cores, desc = cpu_reference_sample(steps=args.steps, warmup=min(args.warmup, 1), verbose=True)
+    vals, cores, desc = cpu_reference_sample(steps=args.steps, warmup=min(args.warmup, 1), verbose=True,
+                                             budget_s=args.cpu_budget)
     v = statistics.mean(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "steps_executed": len(vals),
             "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SD3.5-medium LoRA 512x512, 10 steps, G=8, PickScore reward (config 2)"},
@@ -367,6 +376,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=150.0,
+                    help="--impl reference: wall-clock bound (s) of the timed CPU samples (init excluded)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
