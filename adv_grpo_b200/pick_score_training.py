@@ -38,7 +38,7 @@ class CLIPCriterion(_Loss):
         return i0, i1, text
 
     def calc_loss(self, text_features, image_0_features, image_1_features, logit_scale, label_0, label_1,
-                  num_examples_per_prompt=None, *args, **kwargs):
+                  num_examples_per_prompt, *args, **kwargs):
         if self.cfg.in_batch_negatives or self.cfg.is_distributed:
             raise NotImplementedError("the training scripts use in_batch_negatives=False, is_distributed=False")
         # per prompt: softmax over {real_i, fake_i} of s * <t_i, .>  (row-wise dots; no [B,2B] matmul)
@@ -57,4 +57,4 @@ class CLIPCriterion(_Loss):
         i0, i1, t = self.get_features(model, batch[c.input_ids_column_name], batch[c.pixels_0_column_name],
                                       batch[c.pixels_1_column_name])
         return self.calc_loss(t, i0, i1, model.logit_scale.exp(), batch[c.label_0_column_name],
-                              batch[c.label_1_column_name], batch.get(c.num_examples_per_prompt_column_name))
+                              batch[c.label_1_column_name], batch[c.num_examples_per_prompt_column_name])

@@ -275,3 +275,73 @@ def test_reference_image_index_matches_reference_preprocessing(tmp_path):
     strict = ReferenceImageIndex(str(idx_path), str(root), size=32, device="cpu")
     with pytest.raises(FileNotFoundError):
         strict("a dog")
+
+
+def _mirror(key):
+    """Resolves 'adv_grpo/<file>.py::A.b' to the callable of the same dotted name in adv_grpo_b200.
+    Inner `_fn` closures are obtained by calling the factory (device='cpu' never touches CUDA at build time)."""
+    import importlib
+    rel, dotted = key.split("::")
+    mod = importlib.import_module("adv_grpo_b200." + rel[len("adv_grpo/"):-3].replace("/", "."))
+    parts = dotted.split(".")
+    obj = getattr(mod, parts[0])
+    for p in parts[1:]:
+        if p == "_fn":
+            obj = obj("cpu", {"pickscore_cotrain": 1.0}) if parts[0] == "multi_score" else obj("cpu")
+        else:
+            obj = getattr(obj, p)
+    return obj
+
+
+def test_boundary_signatures_match_reference(golden_dir):
+    """every boundary symbol keeps the reference's parameter names, order and defaults
+    (tests/golden/signatures.json is extracted from the reference sources by tests/golden/make_signatures.py).
+    A mirror may append optional parameters, and may accept **kwargs for reference parameters it ignores."""
+    import inspect
+    import json
+    with open(os.path.join(golden_dir, "signatures.json")) as f:
+        ref = json.load(f)
+    checked = 0
+    for key, spec in sorted(ref.items()):
+        if "keys" in spec:
+            continue
+        factory_name = key.split("::")[1].split(".")[0]
+        if key.endswith("._fn") and factory_name in ("pickscore_score", "ocr_score"):
+            # these factories build a model / need PaddleOCR: read the closure's parameters off its code object
+            from adv_grpo_b200 import rewards
+            code = next(c for c in getattr(rewards, factory_name).__code__.co_consts
+                        if hasattr(c, "co_name") and c.co_name == "_fn")
+            assert list(code.co_varnames[:code.co_argcount]) == [p["name"] for p in spec["params"]], key
+            checked += 1
+            continue
+        fn = _mirror(key)
+        sig = inspect.signature(fn)
+        ours = list(sig.parameters.values())
+        has_varkw = any(p.kind is p.VAR_KEYWORD for p in ours)
+        names = [p.name for p in ours]
+        ref_params = [p for p in spec["params"]]
+        if ref_params and ref_params[0]["name"] == "self" and (not names or names[0] != "self"):
+            # bound-method view / the reference's `self` is the pipeline or scheduler passed positionally
+            if inspect.ismethod(fn) or key.endswith(("__init__", "__call__")) or "." in key.split("::")[1]:
+                ref_params = ref_params[1:]
+        pos = 0
+        for rp in ref_params:
+            if rp["name"] not in sig.parameters:
+                assert has_varkw and rp["default"] is not None, f"{key}: parameter {rp['name']!r} is missing"
+                continue
+            op = sig.parameters[rp["name"]]
+            if rp["default"] is None:
+                assert op.default is inspect.Parameter.empty, f"{key}: {rp['name']} must stay required"
+                if rp["kind"] == "positional":
+                    assert names.index(rp["name"]) == pos, f"{key}: positional order of {rp['name']}"
+            else:
+                assert op.default is not inspect.Parameter.empty, f"{key}: {rp['name']} lost its default"
+                want = eval(rp["default"], {"torch": torch})
+                got = list(op.default) if isinstance(want, list) else op.default   # immutable tuple for a list default
+                assert got == want, f"{key}: default of {rp['name']} is {op.default!r}, reference {want!r}"
+            pos += 1
+        checked += 1
+    assert checked >= 29
+    # the registry exposes every reward key of the reference (rewards.py:1014-1038)
+    from adv_grpo_b200 import rewards
+    assert set(ref["adv_grpo/rewards.py::multi_score.score_functions"]["keys"]) <= set(rewards.score_functions)
