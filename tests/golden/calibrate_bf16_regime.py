@@ -13,7 +13,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from adv_grpo_b200 import weights                      # noqa: E402
 from oracle import pipeline as pipe_o                  # noqa: E402
 from oracle.mmdit import MMDiTOracle                   # noqa: E402

@@ -130,7 +130,7 @@ def test_config1_rollout_sd35_medium_true_size_matches_oracle():
                                                 npool.repeat(G, 1), lat, steps, 4.5, 0.8, T_train, 0, noises, decode=False)
     assert img.shape == (G, 3, 256, 256) and torch.isfinite(img).all()
     # Tolerance = the deviation of the reference's OWN dtype regime (the oracle evaluated in bf16) from the fp32
-    # oracle on these exact inputs, measured by scripts/calibrate_bf16_regime.py and committed as a fixture: the
+    # oracle on these exact inputs, measured by tests/golden/calibrate_bf16_regime.py and committed as a fixture: the
     # seeded random weights amplify bf16 rounding far more than trained ones, so a fixed 1e-2 of range is not
     # reachable by ANY bf16 implementation here (the bf16 oracle itself is off by 2.3e-2 of range at step 2).
     import json
