@@ -48,7 +48,7 @@ def main():
     for a, b in zip(out["bf16"][1], out["fp32"][1]):
         res["log_probs"].append(dict(max_abs=(a - b).abs().max().item(), ref=b.abs().max().item()))
     print(json.dumps(res, indent=1))
-    with open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "bf16_regime_calibration.json"), "w") as f:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bf16_regime_calibration.json"), "w") as f:
         json.dump(res, f, indent=1)
 
 
