@@ -171,6 +171,25 @@ def group_advantage(rewards, group_keys, global_std=True, want_stats=True):
     return (adv[:, 0] if squeeze else adv), stats
 
 
+# --------------------------------------------------------------------------- A12
+def clip_adamw(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+               max_grad_norm=1.0, zero_grad=True, want_norm=True):
+    """In-place global-norm clip + AdamW step (+ gradient clear) on one flat fp32 CUDA tensor
+    (train_sd3_fast_pickscore.py:1165-1171).  Returns the pre-clip gradient norm (f32 [1], device) or None."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("clip_adamw: param / grad / exp_avg / exp_avg_sq must be contiguous fp32 of one size")
+    norm = torch.zeros(1, dtype=torch.float32, device=param.device) if (want_norm and max_grad_norm > 0) else None
+    ws_bytes = _lib.query("advgrpo_clip_adamw_workspace_bytes", n)
+    ws = _workspace("adamw", ws_bytes, param.device)
+    _lib.call("advgrpo_clip_adamw", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr),
+              float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(max_grad_norm),
+              int(bool(zero_grad)), _ptr(norm), _ptr(ws), ws.numel(), _stream())
+    return norm
+
+
 # --------------------------------------------------------------------------- A11
 class _GrpoClipLoss(torch.autograd.Function):
     @staticmethod

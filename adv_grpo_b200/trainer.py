@@ -17,6 +17,7 @@ import torch.distributed as dist
 from . import ops
 from .diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
 from .ema import EMAModuleWrapper
+from .optim import FlatClipAdamW
 from .pick_score_training import CLIPCriterion, CLIPCriterionConfig
 from .pickscore_scorer import images_to_pixel_values
 from .rewards import multi_score
@@ -147,8 +148,10 @@ class GRPOTrainer:
         if t.get("lora_path", None):                                       # resume, train_pick:506-509
             self.transformer.load_adapter(t.lora_path)
         self.params = self.transformer.trainable_parameters()
-        self.optimizer = torch.optim.AdamW(self.params, lr=t.learning_rate, betas=(t.adam_beta1, t.adam_beta2),
-                                           weight_decay=t.adam_weight_decay, eps=t.adam_epsilon, fused=True)
+        # clip_grad_norm_ + AdamW.step + zero_grad of train_pick:1165-1171 as one native call on the flat parameter
+        self.optimizer = FlatClipAdamW(self.params, lr=t.learning_rate, betas=(t.adam_beta1, t.adam_beta2),
+                                       weight_decay=t.adam_weight_decay, eps=t.adam_epsilon,
+                                       max_grad_norm=t.max_grad_norm)
         self.ema = EMAModuleWrapper(self.params, decay=0.9, update_step_interval=8, device=device) if t.ema else None
         self.reward_fn = multi_score(device, dict(config.reward_fn))
         self.reward_key = next(iter(dict(config.reward_fn)))
@@ -351,9 +354,7 @@ class GRPOTrainer:
                 micro += 1
                 if micro % gas == 0:
                     self._sync_grads()
-                    torch.nn.utils.clip_grad_norm_(self.params, t.max_grad_norm)
-                    self.optimizer.step()
-                    self.optimizer.zero_grad(set_to_none=False)
+                    self.optimizer.step()                       # clip + AdamW + gradient clear (csrc/optim.cu)
                     self.transformer.invalidate_lora_cache()
                     self.global_step += 1
             if self.ema is not None:

@@ -152,6 +152,25 @@ int advgrpo_grpo_clip_loss(const float* log_prob, const float* old_log_prob,
                            float* grad_log_prob, advgrpo_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * A12: global-norm gradient clipping + AdamW + gradient clear on the flat fp32 LoRA master
+ * parameter.  Replaces scripts/train_sd3_fast_pickscore.py:1165-1171
+ * (accelerator.clip_grad_norm_(params, max_grad_norm); optimizer.step(); optimizer.zero_grad(),
+ * optimizer = torch.optim.AdamW, :515-521).  The all-reduce of the gradient (NCCL) runs before
+ * this call.  Two kernels, no host read of the norm:
+ *   norm = ||g||_2;  g <- g * min(max_grad_norm / (norm + 1e-6), 1)      (skipped if max_grad_norm <= 0)
+ *   p <- p - lr wd p;  m <- m + (1 - b1)(g - m);  v <- b2 v + (1 - b2) g^2;
+ *   p <- p - lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+ * param, grad, exp_avg, exp_avg_sq: f32 [n], 16-byte aligned.  step >= 1 is the 1-based count of
+ * this update.  zero_grad != 0 clears grad in the same pass (else it is left clipped, as torch
+ * does in place).  grad_norm_out (optional, f32 [1]) receives the pre-clip norm.
+ */
+size_t advgrpo_clip_adamw_workspace_bytes(int64_t n);
+int advgrpo_clip_adamw(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       double lr, double beta1, double beta2, double eps, double weight_decay,
+                       int64_t step, double max_grad_norm, int zero_grad, float* grad_norm_out,
+                       void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * A3 glue (MMDiT block, diffusers AdaLayerNormZero / SD35AdaLayerNormZeroX /
  * AdaLayerNormContinuous as called from SD3Transformer2DModel, reference call site
  * fast.py:630-637): y = LayerNorm(x; no affine, eps) * (1 + scale[b]) + shift[b].

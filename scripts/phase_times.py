@@ -48,7 +48,7 @@ with torch.no_grad():
     _, t_fe = timed(lambda: pipe.transformer(x, t, e, po))
 print(f"rollout(10 steps + vae) {t_r:.1f} ms | vae decode {t_v:.1f} ms | pickscore(8 imgs) {t_sc:.1f} ms | mmdit fwd graph {t_f:.1f} ms eager {t_fe:.1f} ms")
 def opt():
-    torch.nn.utils.clip_grad_norm_(tr.params, 1.0); tr.optimizer.step(); tr.optimizer.zero_grad(set_to_none=False); tr.transformer.invalidate_lora_cache()
+    tr.optimizer.step(); tr.transformer.invalidate_lora_cache()
     with torch.no_grad():
         tr.transformer._pack_lora()
 _, t_o = timed(opt)

@@ -44,6 +44,11 @@ def test_bad_arguments_return_error_codes_not_crashes():
     with pytest.raises(_lib.AdvGrpoError, match="head_dim"):
         _lib.call("advgrpo_attn_fwd", 16, 16, None, 0, None, 1, 128, 4, 80, 0.1, 0, None)
     assert _lib.query("advgrpo_sde_step_workspace_bytes", 8, 65536) > 0
+    with pytest.raises(_lib.AdvGrpoError, match="null"):
+        _lib.call("advgrpo_clip_adamw", None, None, None, None, 16, 3e-4, 0.9, 0.999, 1e-8, 1e-4, 1, 1.0, 1, None, None, 0, None)
+    with pytest.raises(_lib.AdvGrpoError, match="step"):
+        _lib.call("advgrpo_clip_adamw", 16, 16, 16, 16, 16, 3e-4, 0.9, 0.999, 1e-8, 1e-4, 0, 1.0, 1, None, None, 0, None)
+    assert _lib.query("advgrpo_clip_adamw_workspace_bytes", 1 << 20) >= 8
 
 
 def test_ops_refuse_cpu_tensors():
@@ -51,3 +56,6 @@ def test_ops_refuse_cpu_tensors():
     from adv_grpo_b200 import ops
     with pytest.raises(_lib.AdvGrpoError, match="CUDA"):
         ops.group_advantage(torch.zeros(4), torch.zeros(4, dtype=torch.int64))
+    from adv_grpo_b200.optim import FlatClipAdamW
+    with pytest.raises(ValueError, match="CUDA"):
+        FlatClipAdamW([torch.nn.Parameter(torch.zeros(8))])

@@ -495,3 +495,46 @@ def test_conv2d_nhwc_tf32_matches_torch_fp32(ops, B, H, W, Cin, Cout, k, variant
     for sl in ((slice(None), slice(None), 0), (slice(None), slice(None), H - 1), (slice(None), slice(None), slice(None), 0),
                (slice(None), slice(None), slice(None), W - 1)):
         assert (got[sl] - ref[sl]).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------ A12 clip + AdamW
+@pytest.mark.parametrize("n", [5, 1_000_003, 18_776_064])
+def test_clip_adamw_matches_torch_adamw(ops, n):
+    """train_sd3_fast_pickscore.py:1165-1171 with the optimizer of :515-521: clip_grad_norm_(max_norm) ->
+    torch.optim.AdamW.step() -> zero_grad().  The reference's own optimizer (torch.optim.AdamW, CPU fp32,
+    single-tensor path) is the checker.  Three steps: clipped (norm >> 1), clipped, not clipped (tiny gradient).
+    Tolerance: 1e-5 relative on p / m / v (fp32; FMA contraction differs by an ulp), 2e-6 on the norm (vs float64)."""
+    from adv_grpo_b200.optim import FlatClipAdamW
+    g = torch.Generator().manual_seed(n % 1000)
+    p0 = torch.randn(n, generator=g) * 0.18
+    hp = dict(lr=3e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-8)
+    ref_p = torch.nn.Parameter(p0.clone())
+    ref_opt = torch.optim.AdamW([ref_p], foreach=False, fused=False, **hp)
+    our_p = torch.nn.Parameter(p0.clone().to(DEV))
+    our_opt = FlatClipAdamW([our_p], max_grad_norm=1.0, **hp)
+    for step, scale in enumerate((1.0, 0.05, 1e-6)):
+        grad = torch.randn(n, generator=g) * scale
+        # clip_grad_norm_ with the norm taken in float64 (torch's own fp32 CPU reduction is ~1e-5 off at 1e6
+        # elements, the kernel accumulates block partials in f64); checked against torch's value at 3e-5 below
+        ref_norm = grad.double().norm().float()
+        ref_p.grad = grad * torch.clamp(1.0 / (ref_norm + 1e-6), max=1.0)
+        torch.testing.assert_close(ref_norm, grad.norm(), rtol=3e-5, atol=0)
+        ref_opt.step()
+        our_p.grad = grad.clone().to(DEV)
+        norm = our_opt.step()
+        assert torch.count_nonzero(our_p.grad).item() == 0            # cleared in the same pass
+        torch.testing.assert_close(norm.cpu()[0], ref_norm, rtol=2e-6, atol=0)
+        st = ref_opt.state[ref_p]
+        torch.testing.assert_close(our_p.detach().cpu(), ref_p.detach(), rtol=1e-5, atol=1e-7)
+        for name in ("exp_avg", "exp_avg_sq"):           # atol scaled to the tensor: sums that cancel keep ulp-level errors
+            torch.testing.assert_close(our_opt.state[our_p][name].cpu(), st[name], rtol=1e-5,
+                                       atol=1e-6 * st[name].abs().max().item())
+    # zero_grad=False leaves the clipped gradient in place, like clip_grad_norm_
+    grad = torch.randn(n, generator=g)
+    our_p.grad = grad.clone().to(DEV)
+    norm = our_opt.step(zero_grad=False)
+    want = grad * min(1.0 / (grad.double().norm().item() + 1e-6), 1.0)
+    torch.testing.assert_close(our_p.grad.cpu(), want, rtol=1e-5, atol=1e-9)
+    # state dict round trip keeps the torch AdamW names
+    sd = our_opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 4
