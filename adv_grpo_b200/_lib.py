@@ -35,6 +35,7 @@ SIGNATURES = {
     "advgrpo_clip_adamw": (c_int, [_P, _P, _P, _P, _I64, _D, _D, _D, _D, _D, _I64, _D, _I, _P, _P, _SZ, _P]),
     "advgrpo_ln_modulate_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _F, _P]),
     "advgrpo_ln_modulate_bwd": (c_int, [_P, _P, _P, _I64, _P, _P, _P, _I, _I64, _I64, _I64, _F, _P]),
+    "advgrpo_layer_norm_affine": (c_int, [_P, _P, _P, _P, _I64, _I64, _F, _P]),
     "advgrpo_qk_norm_concat_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P]),
     "advgrpo_qk_norm_concat_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64,
                                            _I64, _F, _P]),

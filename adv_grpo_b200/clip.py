@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import vit
+from . import ops, vit
 from .weights import CLIP_H
 
 
@@ -101,7 +101,7 @@ class _VisionModel(nn.Module):
             x = vit.patch_embed(pixel_values, self._w_patch, None, self.cfg["patch"])
             cls = e.class_embedding.detach().to(x.dtype).expand(x.shape[0], 1, -1)
             x = torch.cat([cls, x], 1) + e.position_embedding.weight.detach().to(x.dtype)[None]
-            x = F.layer_norm(x, (x.shape[-1],), self.pre_layrnorm.weight, self.pre_layrnorm.bias, 1e-5).contiguous()
+            x = ops.layer_norm(x, self.pre_layrnorm.weight.detach(), self.pre_layrnorm.bias.detach(), 1e-5).contiguous()
         for layer in self.encoder.layers:
             x = layer(x, causal=False)
         return self.post_layernorm(x[:, 0])

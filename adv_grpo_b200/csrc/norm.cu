@@ -15,7 +15,9 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
-template <int NV>  // D = NV * 256
+// AFFINE: plain LayerNorm with per-channel weight / bias (`scale` = weight, `shift` = bias, mod_stride 0):
+// y = n * weight + bias instead of n * (1 + scale) + shift.
+template <int NV, bool AFFINE = false>  // D = NV * 256
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ shift,
                        const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift2,
@@ -55,9 +57,9 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     unpack8(*reinterpret_cast<const bf16x8*>(sh + off), fsh);
     unpack8(*reinterpret_cast<const bf16x8*>(sc + off), fsc);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, 1.0f + fsc[j], fsh[j]);
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, AFFINE ? fsc[j] : 1.0f + fsc[j], fsh[j]);
     *reinterpret_cast<bf16x8*>(y + row * D + off) = pack8(o);
-    if (y2) {
+    if (!AFFINE && y2) {
       unpack8(*reinterpret_cast<const bf16x8*>(shift2 + b * mod_stride + off), fsh);
       unpack8(*reinterpret_cast<const bf16x8*>(scale2 + b * mod_stride + off), fsc);
 #pragma unroll
@@ -277,6 +279,21 @@ int advgrpo_ln_modulate_fwd(const void* x, const void* shift, const void* scale,
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
       (const __nv_bfloat16*)shift2, (const __nv_bfloat16*)scale2, mod_stride, (__nv_bfloat16*)y,
       (__nv_bfloat16*)y2, rows, S, eps));
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+int advgrpo_layer_norm_affine(const void* x, const void* weight, const void* bias, void* y, int64_t rows,
+                              int64_t D, float eps, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(x && weight && bias && y, "layer_norm_affine: null pointer");
+  ADVGRPO_CHECK_ARG(D % 256 == 0 && D <= 2048, "layer_norm_affine: D=%lld must be a multiple of 256 (<= 2048)", (long long)D);
+  ADVGRPO_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(bias) && aligned16(y),
+                    "layer_norm_affine: tensors must be 16-byte aligned");
+  if (rows <= 0) return ADVGRPO_OK;
+  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  DISPATCH_NV((int)(D / 256), ln_modulate_fwd_kernel<NV, true><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)weight, nullptr, nullptr, 0,
+      (__nv_bfloat16*)y, nullptr, rows, rows, eps));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

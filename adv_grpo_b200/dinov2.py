@@ -2,7 +2,6 @@
 the reference's DINO adversarial reward (`scripts/train_sd3_fast_dino_patch.py:589-603`,
 `adv_grpo/rewards.py:375-434`).  timm state-dict names (`vit_base_patch14_dinov2.lvd142m`)."""
 import torch
-import torch.nn.functional as F
 
 from . import ops, vit
 from .weights import DINOV2_B
@@ -43,7 +42,7 @@ class DinoV2:
         x = x.contiguous()
         for blk in self.blocks:
             x = blk(x)
-        return F.layer_norm(x, (x.shape[-1],), p["norm.weight"], p["norm.bias"], 1e-6)
+        return ops.layer_norm(x, p["norm.weight"], p["norm.bias"], 1e-6)
 
 
 class DINOHead(torch.nn.Module):

@@ -261,6 +261,22 @@ def ln_modulate(x, shift, scale, shift2=None, scale2=None, eps=1e-6):
     return _LnModulate.apply(x, shift, scale, shift2, scale2, eps)
 
 
+def layer_norm(x, weight, bias, eps):
+    """Affine LayerNorm over the last dim of the reward towers' blocks (bf16, width a multiple of 256) on the
+    `ln_modulate` kernel.  Inference only: when a gradient is needed (the discriminator step trains the last CLIP
+    blocks, train_sd3_fast_pickscore.py:151-183) autograd's own LayerNorm node is used."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad)
+    D = x.shape[-1]
+    if needs_grad or x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or D % 256 or D > 2048:
+        return torch.nn.functional.layer_norm(x, (D,), weight, bias, eps)
+    _need_cuda(x, weight, bias)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.call("advgrpo_layer_norm_affine", _ptr(x), _ptr(weight.contiguous()), _ptr(bias.contiguous()), _ptr(y),
+              x.numel() // D, D, float(eps), _stream())
+    return y
+
+
 # --------------------------------------------------------------------------- q/k RMSNorm + concat
 class _QkNormConcat(torch.autograd.Function):
     @staticmethod

@@ -1,7 +1,7 @@
 """Pre-LN ViT encoder blocks on the libadvgrpo_b200 kernels, shared by the PickScore CLIP-ViT-H/14
 towers (`adv_grpo/pickscore_scorer.py:40-43`) and DINOv2-B/14 (`adv_grpo/rewards.py:397`).
 
-Per block: LayerNorm (torch) -> fused QKV tcgen05 GEMM writing the token-major [B,S,3,H,Dp] buffer
+Per block: LayerNorm (`ops.layer_norm`, the ln_modulate kernel in affine mode) -> fused QKV tcgen05 GEMM writing the token-major [B,S,3,H,Dp] buffer
 the attention kernel reads through TMA -> flash attention -> out-projection GEMM with the residual
 add (and DINOv2's LayerScale) fused as `x + gamma * (W o + b)` -> LayerNorm -> fc1 GEMM + GELU(erf)
 epilogue -> fc2 GEMM + fused residual.  Heads narrower than the 64/128 the attention kernel supports
@@ -59,12 +59,12 @@ class ViTBlock:
     def __call__(self, x, causal=False):
         B, S, W = x.shape
         M = B * S
-        h = F.layer_norm(x, (W,), self.ln1[0], self.ln1[1], self.eps)
+        h = ops.layer_norm(x, self.ln1[0], self.ln1[1], self.eps)
         qkv = ops.gemm(h, self.w_qkv, bias=self.b_qkv).view(B, S, 3, self.heads, self.hd_pad)
         o, _ = ops.attention_fwd(qkv, scale=self.scale, causal=causal, want_lse=False)
         x = ops.gemm(o.view(B, S, self.heads * self.hd_pad), self.w_o, bias=self.b_o,
                      epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=self.g1, rows_per_gate=M)
-        h = F.layer_norm(x, (W,), self.ln2[0], self.ln2[1], self.eps)
+        h = ops.layer_norm(x, self.ln2[0], self.ln2[1], self.eps)
         m = ops.gemm(h, self.w_fc1, bias=self.b_fc1, epilogue=self.act_epilogue)
         x = ops.gemm(m, self.w_fc2, bias=self.b_fc2, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=self.g2,
                      rows_per_gate=M)

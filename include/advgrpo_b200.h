@@ -188,6 +188,14 @@ int advgrpo_ln_modulate_bwd(const void* x, const void* scale, const void* scale2
                             int accumulate, int64_t B, int64_t S, int64_t D, float eps,
                             advgrpo_stream_t stream);
 
+/* A8a/A8b glue: affine LayerNorm of the reward towers' pre-LN blocks (transformers CLIPEncoderLayer
+ * layer_norm1/2 behind adv_grpo/pickscore_scorer.py:40-43; timm Block norm1/2 behind
+ * adv_grpo/rewards.py:397-399): y = (x - mean) * rstd * weight + bias, fp32 statistics, bf16 in/out.
+ * x, y: bf16 [rows, D]; weight, bias: bf16 [D].  D must be a multiple of 256 and <= 2048.
+ */
+int advgrpo_layer_norm_affine(const void* x, const void* weight, const void* bias, void* y, int64_t rows,
+                              int64_t D, float eps, advgrpo_stream_t stream);
+
 /* Per-head RMSNorm of q and k (diffusers RMSNorm(head_dim, eps) inside
  * JointAttnProcessor2_0) fused with the [image, text] sequence concat: builds the joint
  * token-major buffer qkv_joint bf16 [B, S_img + S_txt, 3, H, D] that the attention

@@ -538,3 +538,26 @@ def test_clip_adamw_matches_torch_adamw(ops, n):
     # state dict round trip keeps the torch AdamW names
     sd = our_opt.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and int(sd["state"][0]["step"]) == 4
+
+
+# ------------------------------------------------------------------ A8 glue: affine LayerNorm of the reward towers
+@pytest.mark.parametrize("rows,D,eps", [(2 * 257, 1280, 1e-5), (3 * 1370, 768, 1e-6), (77, 1024, 1e-5), (1, 256, 1e-5)])
+def test_layer_norm_affine_matches_torch_fp32(ops, rows, D, eps):
+    """CLIPEncoderLayer.layer_norm1/2 (transformers, pickscore_scorer.py:40-43) / timm Block.norm1/2
+    (rewards.py:397-399): fp32 statistics over the bf16 row, bf16 output.  Checked against torch's fp32
+    LayerNorm of the same bf16 values: at most one bf16 rounding step apart (2^-8 relative) per element."""
+    g = torch.Generator().manual_seed(rows + D)
+    x = (torch.randn(rows, D, generator=g) * 3 + 0.5).bfloat16()
+    w = (1 + 0.2 * torch.randn(D, generator=g)).bfloat16()
+    b = (0.1 * torch.randn(D, generator=g)).bfloat16()
+    y = ops.layer_norm(x.to(DEV), w.to(DEV), b.to(DEV), eps)
+    assert y.dtype == torch.bfloat16 and y.shape == x.shape
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), eps)
+    err = (y.float().cpu() - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 1e-6).all(), err.max()
+    # 3-D input keeps its shape; a tensor that needs a gradient goes through autograd's LayerNorm
+    x3 = x.to(DEV).view(1, rows, D)
+    assert ops.layer_norm(x3, w.to(DEV), b.to(DEV), eps).shape == x3.shape
+    xg = x.to(DEV).float().requires_grad_()
+    ops.layer_norm(xg, w.to(DEV).float(), b.to(DEV).float(), eps).sum().backward()
+    assert xg.grad is not None
