@@ -514,11 +514,11 @@ def test_clip_adamw_matches_torch_adamw(ops, n):
     our_opt = FlatClipAdamW([our_p], max_grad_norm=1.0, **hp)
     for step, scale in enumerate((1.0, 0.05, 1e-6)):
         grad = torch.randn(n, generator=g) * scale
-        # clip_grad_norm_ with the norm taken in float64 (torch's own fp32 CPU reduction is ~1e-5 off at 1e6
-        # elements, the kernel accumulates block partials in f64); checked against torch's value at 3e-5 below
+        # clip_grad_norm_ with the norm taken in float64: torch's own fp32 CPU reduction is 1e-5 off at 1e6 elements
+        # and 9e-4 off at 1.9e7 (measured), the kernel accumulates its block partials in f64
         ref_norm = grad.double().norm().float()
         ref_p.grad = grad * torch.clamp(1.0 / (ref_norm + 1e-6), max=1.0)
-        torch.testing.assert_close(ref_norm, grad.norm(), rtol=3e-5, atol=0)
+        torch.testing.assert_close(ref_norm, grad.norm(), rtol=2e-3, atol=0)
         ref_opt.step()
         our_p.grad = grad.clone().to(DEV)
         norm = our_opt.step()
