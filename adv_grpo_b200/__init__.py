@@ -2,7 +2,7 @@
 advantage -> update hot path behind the reference's own Python surface.
 
 `install_as_adv_grpo()` registers this package's modules under the reference's import names
-(`adv_grpo.rewards`, `adv_grpo.stat_tracking`, `adv_grpo.ema`, `adv_grpo.pickscore_scorer`,
+(`adv_grpo.rewards`, `adv_grpo.stat_tracking`, `adv_grpo.ema`, `adv_grpo.ocr`, `adv_grpo.pickscore_scorer`,
 `adv_grpo.pick_score_training`, `adv_grpo.diffusers_patch.sd3_sde_with_logprob`,
 `adv_grpo.diffusers_patch.sd3_pipeline_with_logprob_fast`, `adv_grpo.diffusers_patch.train_dreambooth_lora_sd3`) so that
 `scripts/train_sd3_fast_{pickscore,dino_patch}.py` import the B200 path unchanged.
@@ -17,6 +17,7 @@ _ALIASES = {
     "adv_grpo.rewards": "adv_grpo_b200.rewards",
     "adv_grpo.stat_tracking": "adv_grpo_b200.stat_tracking",
     "adv_grpo.ema": "adv_grpo_b200.ema",
+    "adv_grpo.ocr": "adv_grpo_b200.ocr",
     "adv_grpo.pickscore_scorer": "adv_grpo_b200.pickscore_scorer",
     "adv_grpo.pick_score_training": "adv_grpo_b200.pick_score_training",
     "adv_grpo.diffusers_patch": "adv_grpo_b200.diffusers_patch",

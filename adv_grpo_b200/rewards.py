@@ -6,7 +6,8 @@ the weighted sum in `score_details['avg']` (`rewards.py:1012-1095`).  Factory pr
 
 On the hot path (B200 kernels, device-resident, no host round trip):
   pickscore_cotrain, pickscore, dino_patch_cotrain
-Host plugin kept as in the reference:  ocr (PaddleOCR on CPU; unavailable here -> clear error).
+Host plugin kept as in the reference:  ocr (`ocr.OcrScorer`: PaddleOCR or an injected recogniser on the CPU +
+Levenshtein reward; a missing recogniser raises at construction).
 All other registry keys of the reference exist so configs do not KeyError; they raise
 NotImplementedError when instantiated (remote HTTP / sglang / SigLIP / aesthetic ... scorers are
 outside the hot path).
@@ -72,13 +73,12 @@ def dino_patch_cotrain_score(device, n_patches=64):
     return _fn
 
 
+OCR_KWARGS = {}            # extra OcrScorer kwargs (recognizer=callable replaces PaddleOCR)
+
+
 def ocr_score(device):
-    try:
-        from adv_grpo.ocr import OcrScorer                     # the reference's CPU PaddleOCR plugin
-    except Exception as e:  # paddleocr / Levenshtein are not installed in this image
-        raise NotImplementedError("the 'ocr' reward is the reference's host plugin (adv_grpo/ocr.py, PaddleOCR on "
-                                  f"CPU); it is not available here: {e}")
-    scorer = OcrScorer()
+    from .ocr import OcrScorer                                 # host plugin: PaddleOCR (or OCR_KWARGS["recognizer"]) on CPU
+    scorer = OcrScorer(**OCR_KWARGS)
 
     def _fn(images, prompts, metadata):
         if torch.is_tensor(images):

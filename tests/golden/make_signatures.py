@@ -34,6 +34,8 @@ SYMBOLS = [
     ("adv_grpo/diffusers_patch/sd3_sde_with_logprob.py", "sde_step_with_logprob_new"),
     ("adv_grpo/diffusers_patch/sd3_pipeline_with_logprob_fast.py", "pipeline_with_logprob_random"),
     ("adv_grpo/diffusers_patch/train_dreambooth_lora_sd3.py", "encode_prompt"),
+    ("adv_grpo/ocr.py", "OcrScorer.__init__"),
+    ("adv_grpo/ocr.py", "OcrScorer.__call__"),
     ("adv_grpo/rewards.py", "multi_score"),
     ("adv_grpo/rewards.py", "multi_score._fn"),
     ("adv_grpo/rewards.py", "pickscore_score"),

@@ -341,7 +341,44 @@ def test_boundary_signatures_match_reference(golden_dir):
                 assert got == want, f"{key}: default of {rp['name']} is {op.default!r}, reference {want!r}"
             pos += 1
         checked += 1
-    assert checked >= 29
+    assert checked >= 31
     # the registry exposes every reward key of the reference (rewards.py:1014-1038)
     from adv_grpo_b200 import rewards
     assert set(ref["adv_grpo/rewards.py::multi_score.score_functions"]["keys"]) <= set(rewards.score_functions)
+
+
+def test_ocr_host_plugin_reward_arithmetic():
+    """adv_grpo/ocr.py:31-65 with an injected recogniser (PaddleOCR is not installable here): quoted target text,
+    blank stripping + lower-casing, containment shortcut, Levenshtein distance capped at len(target), failure =
+    maximum penalty, list[float] return; and the registry path `multi_score(device, {"ocr": w})`."""
+    import numpy as np
+    from adv_grpo_b200 import rewards
+    from adv_grpo_b200.ocr import OcrScorer, levenshtein
+    assert [levenshtein(*p) for p in (("kitten", "sitting"), ("flaw", "lawn"), ("", "abc"), ("abc", "abc"), ("abc", "abd"))] \
+        == [3, 2, 3, 0, 1]
+    texts = {0: [("Hello W", 0.9), ("orld", 0.8)], 1: [("HELLO", 0.9), ("junk", 0.0)], 2: [], 3: None,
+             4: [("completely unrelated long text", 0.9)]}
+
+    def recognizer(img):
+        r = texts[int(img[0, 0, 0])]
+        if r is None:
+            raise RuntimeError("recogniser failure")
+        return r
+
+    imgs = [np.full((8, 8, 3), i, dtype=np.uint8) for i in range(5)]
+    prompts = ['a sign that says "Hello World" in neon'] * 5
+    got = OcrScorer(recognizer=recognizer)(imgs, prompts)
+    # 0: exact after normalisation -> 1; 1: "hello" vs "helloworld": distance 5 of 10 -> 0.5 (zero-confidence line dropped);
+    # 2: nothing recognised -> distance 10 -> 0; 3: failure -> 0; 4: distance > len(target) capped -> 0
+    assert got == [1.0, 0.5, 0.0, 0.0, 0.0] and isinstance(got, list)
+    rewards.OCR_KWARGS["recognizer"] = recognizer
+    try:
+        fn = rewards.multi_score("cpu", {"ocr": 2.0})
+        images = torch.stack([torch.full((3, 8, 8), i / 255.0) for i in range(5)])      # NCHW in [0, 1], rewards.py:680-683
+        details, extra = fn(images, prompts, [{}] * 5)
+    finally:
+        rewards.OCR_KWARGS.clear()
+    assert details["ocr"] == got and extra == {}
+    assert torch.allclose(details["avg"], 2.0 * torch.tensor(got))
+    with pytest.raises(ImportError, match="paddleocr"):
+        OcrScorer()
