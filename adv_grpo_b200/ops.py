@@ -30,8 +30,9 @@ def _need_cuda(*ts):
 
 
 def _workspace(tag, nbytes, device):
-    """Per (op, device, stream) scratch buffer so concurrent streams never share one."""
-    key = (tag, device.index, _stream())
+    """Per (op, device, stream, thread) scratch buffer: concurrent streams never share one, and neither do two host
+    threads enqueueing multi-kernel entry points on the same stream (ctypes releases the GIL during the call)."""
+    key = (tag, device.index, _stream(), threading.get_ident())
     with _ws_lock:
         buf = _ws_cache.get(key)
         if buf is None or buf.numel() < nbytes:

@@ -11,6 +11,7 @@ No tokenizer files or pretrained weights exist on the box: `processor.tokenizer`
 synthetic CLIP-shaped tokenizer (BOS, hashed word ids, EOS) unless a real one is supplied, and the
 model is seeded-random CLIP-ViT-H/14 unless a state dict is supplied.
 """
+import threading
 import zlib
 
 import numpy as np
@@ -96,7 +97,9 @@ class _GraphedImageTower:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: a capture started from a reward worker thread must not turn the sampling thread's
+            # allocations / event queries into capture errors (the default "global" mode does)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 out = self.model.get_image_features(pixel_values=static_in)
             ent = (ver, g, static_in, out, _lib.launch_count() - n0)
             self.entries[key] = ent
@@ -120,9 +123,17 @@ class PickScoreScorer(torch.nn.Module):
         self.processor = CLIPProcessorLike(tokenizer or SyntheticCLIPTokenizer(cfg["vocab"]), device, cfg["image"])
         self._image_tower = None
         self._text_cache = {}
+        self._lock = threading.RLock()
 
     @torch.no_grad()
     def __call__(self, prompt, images):
+        # The training scripts call the reward function from an 8-worker thread pool while the main thread keeps
+        # sampling (train_sd3_fast_pickscore.py:668,816-817).  The graphed image tower owns static buffers and the
+        # text cache is shared, so calls on one scorer are serialised (their GPU work is stream-ordered anyway).
+        with self._lock:
+            return self._score(prompt, images)
+
+    def _score(self, prompt, images):
         model = self.model.module if hasattr(self.model, "module") else self.model   # quirk Q3 tolerated
         pixel_values = images_to_pixel_values(images, self.device, self.processor.size)
         if isinstance(prompt, str):

@@ -133,3 +133,34 @@ def test_multi_reward_pickscore_plus_host_plugin_config4():
     assert torch.allclose(pick, ref, atol=1e-6)
     # consumed as in train_sd3_fast_pickscore.py:849-856
     assert all(torch.as_tensor(v).float().shape == (4,) for v in details.values())
+
+
+def test_reward_fn_from_thread_pool_while_main_thread_works():
+    """SURVEY.md section 8b threading contract: the scripts call `reward_fn` from an 8-worker ThreadPoolExecutor while
+    the main thread keeps sampling (train_sd3_fast_pickscore.py:668,816-817).  Scores computed concurrently (graph
+    capture, replay and the text cache included) must equal the serial ones, and the main thread's own kernels and
+    allocations must not be disturbed by a capture started in a worker."""
+    from concurrent.futures import ThreadPoolExecutor
+    from adv_grpo_b200 import ops, rewards, weights
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    scorer = PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY, seed=3)
+    fn = rewards.multi_score(DEV, {"pickscore_cotrain": 1.0})
+    g = torch.Generator().manual_seed(2)
+    batches = [torch.rand(4, 3, 96, 96, generator=g).to(DEV).bfloat16() for _ in range(12)]
+    prompts = [[f"prompt {i % 3}"] * 4 for i in range(12)]
+    serial = [fn(b, p, [{}] * 4, scorer=scorer)[0]["avg"].clone() for b, p in zip(batches, prompts)]
+    fresh = PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY, seed=3)       # nothing captured / cached yet
+    a = torch.randn(512, 256, device=DEV).bfloat16()
+    w = torch.randn(384, 256, device=DEV).bfloat16()
+    want = ops.gemm(a, w).clone()
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        futs = [ex.submit(lambda b, p: fn(b, p, [{}] * 4, scorer=fresh)[0]["avg"].clone(), b, p)
+                for b, p in zip(batches, prompts)]
+        outs = []
+        while not all(f.done() for f in futs):                                # the "sampling" thread: kernels + allocations
+            outs.append(ops.gemm(a, w) + torch.zeros(512, 384, device=DEV, dtype=torch.bfloat16))
+        got = [f.result() for f in futs]
+    torch.cuda.synchronize()
+    for s, c in zip(serial, got):
+        assert torch.equal(s, c)
+    assert all(torch.equal(o, want) for o in outs[:: max(1, len(outs) // 16)])
