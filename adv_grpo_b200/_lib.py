@@ -64,6 +64,7 @@ _EXTRA = {
     "advgrpo_attn_fwd_variant": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _I, _P]),
     "advgrpo_debug_set_gemm_variant": (None, [_I]),
     "advgrpo_debug_set_conv_variant": (None, [_I]),
+    "advgrpo_debug_set_pdl": (None, [_I]),
 }
 
 _lib = None

@@ -115,6 +115,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int64_t stat_row = ((int64_t)b * p.H + h) * p.S_pad;
 
   // register re-balancing (setmaxnreg is per 4-warp group): 256 compute threads x 176 + 128 drain x 88 + 128 utility x 72
@@ -391,6 +393,8 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, cons
                                      const float* __restrict__ lse, float* __restrict__ lse2,
                                      float* __restrict__ delta, float* __restrict__ dq_acc, int B, int S,
                                      int S_pad, int H) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   // one 8-lane group per (b, h, s_pad) row
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
   const int sub = threadIdx.x & 7;
@@ -422,6 +426,8 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, cons
 
 __global__ void attn_bwd_dq_finish_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
                                           int B, int S, int S_pad, int H, float scale) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;
   const int sub = threadIdx.x & 7;
   const int64_t total = (int64_t)B * H * S;
@@ -469,8 +475,9 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
     const int64_t groups = B * H * sp;
     const int threads = 256;
     const int64_t blocks = (groups * 8 + threads - 1) / threads;
-    attn_bwd_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
-                                                               lse, lse2, delta, dq_acc, (int)B, (int)S, (int)sp, (int)H);
+    ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_prep_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, 1,
+                                   (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, (const float*)lse, lse2, delta,
+                                   dq_acc, (int)B, (int)S, (int)sp, (int)H));
     ADVGRPO_CUDA_LAUNCH_CHECK();
   }
   CUtensorMap tm_qkv, tm_do, tm_dq;
@@ -504,14 +511,14 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   dim3 grid((unsigned)(sp / T), (unsigned)H, (unsigned)B);
-  attn_bwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_qkv, tm_do, tm_dq, p);
+  ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tm_qkv, tm_do, tm_dq, p));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   {
     const int64_t groups = B * H * S;
     const int threads = 256;
     const int64_t blocks = (groups * 8 + threads - 1) / threads;
-    attn_bwd_dq_finish_kernel<<<(unsigned)blocks, threads, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (int)B, (int)S, (int)sp,
-                                                                    (int)H, scale);
+    ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_dq_finish_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, 1,
+                                   (const float*)dq_acc, (__nv_bfloat16*)dqkv, (int)B, (int)S, (int)sp, (int)H, scale));
     ADVGRPO_CUDA_LAUNCH_CHECK();
   }
   return ADVGRPO_OK;

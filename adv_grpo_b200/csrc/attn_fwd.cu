@@ -479,6 +479,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
 
   if (warp >= 4) {
     if constexpr (C::kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
@@ -768,7 +770,8 @@ int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, floa
   const int per_sm = (D == 64) ? 2 : 1;
   int grid = sm_count() * per_sm;
   if (grid > items) grid = (int)items;
-  attn_fwd_persist_kernel<D, EMU><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p, (int)items, nqt);
+  ADVGRPO_CUDA_CALL(launch_chain(attn_fwd_persist_kernel<D, EMU>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmap, p,
+                                 (int)items, nqt));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

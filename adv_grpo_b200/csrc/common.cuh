@@ -41,6 +41,42 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();
 
+// ---- programmatic dependent launch (experimental, off by default: env ADVGRPO_PDL=1 or advgrpo_debug_set_pdl) ----
+// Kernels of the MMDiT forward / backward chain call pdl_trigger() + pdl_wait() once their prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) is done and before their first global-memory access.  When the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, the next kernel's CTAs are scheduled as soon as every CTA of
+// this one has started, run their own prologue, and block in griddepcontrol.wait until this grid has completed and
+// flushed: the launch latency and the prologue move off the critical path.  Without the attribute both instructions
+// are no-ops, so the default (plain <<<>>>) behaviour is unchanged.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda) ----
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1. bf16 elements.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
@@ -50,6 +86,8 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

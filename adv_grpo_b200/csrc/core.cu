@@ -2,6 +2,8 @@
 // the host-side TMA tensor-map encoder shared by the tensor-core kernels.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace advgrpo {
@@ -27,6 +29,16 @@ int sm_count() {
   }
   return cached[dev];
 }
+
+static int g_pdl = -1;   // -1: read ADVGRPO_PDL on first use
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ADVGRPO_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
+}
+void set_pdl(int v) { g_pdl = v ? 1 : 0; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -80,6 +92,9 @@ extern "C" {
 int advgrpo_abi_version(void) { return ADVGRPO_ABI_VERSION; }
 
 const char* advgrpo_last_error(void) { return advgrpo::g_last_error; }
+
+// Test/bench hook: programmatic dependent launch for the MMDiT kernel chain (see common.cuh).
+void advgrpo_debug_set_pdl(int v) { advgrpo::set_pdl(v); }
 
 int advgrpo_device_check(int dev) {
   cudaDeviceProp p;

@@ -172,6 +172,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();   // prologue done (TMEM held): the next kernel may be scheduled behind this one
+  pdl_wait();      // no global-memory access before the previous kernel's results are visible
 
   if (warp == 8) {
     // ============================== TMA producer ==============================
@@ -507,25 +509,9 @@ int launch_gemm(const Maps& m0, const Maps& m1, GParams& p, cudaStream_t st) {
   p.num_tiles = p.tiles0 + p.b.tiles_m * p.tiles_n;
   int workers = TWO ? sm_count() / 2 : sm_count();
   if (workers > p.num_tiles) workers = p.num_tiles;
-  if constexpr (TWO) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * workers);
-    cfg.blockDim = dim3(G::kThreads);
-    cfg.dynamicSmemBytes = G::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    ADVGRPO_CUDA_CALL(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, TWO, EC>, m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
-                                         m1.a2, m1.w2, m1.c, m1.r, p));
-  } else {
-    gemm_kernel<BN, TWO, EC><<<workers, G::kThreads, G::kSmemBytes, st>>>(m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w,
-                                                                      m1.a2, m1.w2, m1.c, m1.r, p);
-  }
+  ADVGRPO_CUDA_CALL(launch_chain(gemm_kernel<BN, TWO, EC>, dim3(TWO ? 2 * workers : workers), dim3(G::kThreads),
+                                 G::kSmemBytes, st, TWO ? 2 : 1, m0.a, m0.w, m0.a2, m0.w2, m0.c, m0.r, m1.a, m1.w, m1.a2,
+                                 m1.w2, m1.c, m1.r, p));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

@@ -24,6 +24,8 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
                        const __nv_bfloat16* __restrict__ scale2, int64_t mod_stride,
                        __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2, int64_t rows,
                        int64_t S, float eps) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   constexpr int D = NV * 256;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -76,6 +78,8 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
                        const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                        __nv_bfloat16* __restrict__ dx, int accumulate, int64_t rows, int64_t S,
                        float eps) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   constexpr int D = NV * 256;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -149,6 +153,8 @@ __global__ void qk_norm_concat_fwd_kernel(const __nv_bfloat16* __restrict__ qkv_
                                           const __nv_bfloat16* __restrict__ wk_txt,
                                           __nv_bfloat16* __restrict__ out, int64_t S_img,
                                           int64_t S_txt, int HD, float eps) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int64_t S = S_img + S_txt;
   const int64_t b = blockIdx.x / S, s = blockIdx.x % S;
   const bool is_img = s < S_img;
@@ -189,6 +195,8 @@ __global__ void qk_norm_concat_bwd_kernel(const __nv_bfloat16* __restrict__ qkv_
                                           __nv_bfloat16* __restrict__ dq_img,
                                           __nv_bfloat16* __restrict__ dq_txt, int64_t S_img,
                                           int64_t S_txt, int HD, float eps) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int64_t S = S_img + S_txt;
   const int64_t b = blockIdx.x / S, s = blockIdx.x % S;
   const bool is_img = s < S_img;
@@ -231,6 +239,8 @@ __global__ void qk_norm_concat_bwd_kernel(const __nv_bfloat16* __restrict__ qkv_
 __global__ void __launch_bounds__(256)
 row_gate_mul_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gate, int64_t gate_stride,
                     int64_t rows_per_gate, __nv_bfloat16* __restrict__ out, int64_t M, int nvec) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int64_t total = M * nvec;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t m = i / nvec;
@@ -275,10 +285,12 @@ int advgrpo_ln_modulate_fwd(const void* x, const void* shift, const void* scale,
   const int64_t rows = B * S;
   if (rows == 0) return ADVGRPO_OK;
   const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  DISPATCH_NV((int)(D / 256), ln_modulate_fwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
+  cudaError_t le = cudaSuccess;
+  DISPATCH_NV((int)(D / 256), le = launch_chain(ln_modulate_fwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0,
+      (cudaStream_t)stream, 1, (const __nv_bfloat16*)x, (const __nv_bfloat16*)shift, (const __nv_bfloat16*)scale,
       (const __nv_bfloat16*)shift2, (const __nv_bfloat16*)scale2, mod_stride, (__nv_bfloat16*)y,
       (__nv_bfloat16*)y2, rows, S, eps));
+  ADVGRPO_CUDA_CALL(le);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -311,9 +323,11 @@ int advgrpo_ln_modulate_bwd(const void* x, const void* scale, const void* scale2
   const int64_t rows = B * S;
   if (rows == 0) return ADVGRPO_OK;
   const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  DISPATCH_NV((int)(D / 256), ln_modulate_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)scale2, mod_stride,
+  cudaError_t le = cudaSuccess;
+  DISPATCH_NV((int)(D / 256), le = launch_chain(ln_modulate_bwd_kernel<NV>, dim3(grid), dim3(kWarpsPerBlock * 32), 0,
+      (cudaStream_t)stream, 1, (const __nv_bfloat16*)x, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)scale2, mod_stride,
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2, (__nv_bfloat16*)dx, accumulate, rows, S, eps));
+  ADVGRPO_CUDA_CALL(le);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -328,8 +342,8 @@ int advgrpo_row_gate_mul(const void* x, const void* gate, int64_t gate_stride, i
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  row_gate_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate, gate_stride, rows_per_gate, (__nv_bfloat16*)out, M, (int)(N / 8));
+  ADVGRPO_CUDA_CALL(launch_chain(row_gate_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, 1,
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate, gate_stride, rows_per_gate, (__nv_bfloat16*)out, M, (int)(N / 8)));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -346,10 +360,10 @@ int advgrpo_qk_norm_concat_fwd(const void* qkv_img, const void* qkv_txt, const v
   ADVGRPO_CHECK_ARG(aligned16(qkv_img) && aligned16(qkv_joint) && (!qkv_txt || aligned16(qkv_txt)), "qk_norm_concat_fwd: 16-byte alignment");
   const int64_t tokens = B * (S_img + S_txt);
   if (tokens == 0) return ADVGRPO_OK;
-  qk_norm_concat_fwd_kernel<<<(unsigned)tokens, (unsigned)(H * D / 8), 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv_img, (const __nv_bfloat16*)qkv_txt, (const __nv_bfloat16*)wq_img,
+  ADVGRPO_CUDA_CALL(launch_chain(qk_norm_concat_fwd_kernel, dim3((unsigned)tokens), dim3((unsigned)(H * D / 8)), 0,
+      (cudaStream_t)stream, 1, (const __nv_bfloat16*)qkv_img, (const __nv_bfloat16*)qkv_txt, (const __nv_bfloat16*)wq_img,
       (const __nv_bfloat16*)wk_img, (const __nv_bfloat16*)wq_txt, (const __nv_bfloat16*)wk_txt,
-      (__nv_bfloat16*)qkv_joint, S_img, S_txt, (int)(H * D), eps);
+      (__nv_bfloat16*)qkv_joint, S_img, S_txt, (int)(H * D), eps));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -365,11 +379,11 @@ int advgrpo_qk_norm_concat_bwd(const void* qkv_img, const void* qkv_txt, const v
   ADVGRPO_CHECK_ARG((S_txt == 0) == (qkv_txt == nullptr) && (S_txt == 0) == (dqkv_txt == nullptr), "qk_norm_concat_bwd: text tensors must be given iff S_txt > 0");
   const int64_t tokens = B * (S_img + S_txt);
   if (tokens == 0) return ADVGRPO_OK;
-  qk_norm_concat_bwd_kernel<<<(unsigned)tokens, (unsigned)(H * D / 8), 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv_img, (const __nv_bfloat16*)qkv_txt, (const __nv_bfloat16*)wq_img,
+  ADVGRPO_CUDA_CALL(launch_chain(qk_norm_concat_bwd_kernel, dim3((unsigned)tokens), dim3((unsigned)(H * D / 8)), 0,
+      (cudaStream_t)stream, 1, (const __nv_bfloat16*)qkv_img, (const __nv_bfloat16*)qkv_txt, (const __nv_bfloat16*)wq_img,
       (const __nv_bfloat16*)wk_img, (const __nv_bfloat16*)wq_txt, (const __nv_bfloat16*)wk_txt,
       (const __nv_bfloat16*)dqkv_joint, (__nv_bfloat16*)dqkv_img, (__nv_bfloat16*)dqkv_txt, S_img, S_txt,
-      (int)(H * D), eps);
+      (int)(H * D), eps));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

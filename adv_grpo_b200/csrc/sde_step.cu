@@ -127,6 +127,8 @@ struct FwdArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) sde_fwd_kernel(FwdArgs a) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   __shared__ float scratch[32];
   __shared__ bool is_last;
   const int b = blockIdx.y;
@@ -218,6 +220,8 @@ struct BwdArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) sde_bwd_kernel(BwdArgs a) {
+  pdl_trigger();   // programmatic dependent launch (common.cuh): no-ops unless the launch carries the attribute
+  pdl_wait();
   const int b = blockIdx.y;
   const StepCoef k = step_coef(a.timesteps, a.t_count, b, a.sched_t, a.sigmas, a.T, a.sin_level, a.mode, a.noise_level);
   // Flow-CPS: d mu / d v = (1 - sigma) c - sigma (1 - sigma'), d logp / d mu = (2/n) (prev - mu)
@@ -338,7 +342,7 @@ int advgrpo_cfg_sde_step_logprob_variant(const void* v_uncond, const void* v_tex
   a.partial = (double*)workspace;
   a.tickets = (unsigned int*)((char*)workspace + (size_t)B * 2048 * sizeof(double));
   ADVGRPO_CUDA_CALL(cudaMemsetAsync(a.tickets, 0, (size_t)B * sizeof(unsigned int), st));
-  sde_fwd_kernel<<<dim3(gx, (unsigned)B), kThreads, 0, st>>>(a);
+  ADVGRPO_CUDA_CALL(launch_chain(sde_fwd_kernel, dim3(gx, (unsigned)B), dim3(kThreads), 0, st, 1, a));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -393,7 +397,7 @@ int advgrpo_cfg_sde_logprob_bwd_variant(const void* v_uncond, const void* v_text
   a.sin_level = (float)sin((double)noise_level * M_PI / 2.0);
   a.mode = variant; a.noise_level = noise_level;
   int gx = blocks_per_sample(B, n);
-  sde_bwd_kernel<<<dim3(gx, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(a);
+  ADVGRPO_CUDA_CALL(launch_chain(sde_bwd_kernel, dim3(gx, (unsigned)B), dim3(kThreads), 0, (cudaStream_t)stream, 1, a));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
