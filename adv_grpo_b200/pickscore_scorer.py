@@ -11,6 +11,7 @@ No tokenizer files or pretrained weights exist on the box: `processor.tokenizer`
 synthetic CLIP-shaped tokenizer (BOS, hashed word ids, EOS) unless a real one is supplied, and the
 model is seeded-random CLIP-ViT-H/14 unless a state dict is supplied.
 """
+import os
 import threading
 import zlib
 
@@ -72,6 +73,11 @@ def images_to_pixel_values(images, device, size=224, dtype=torch.bfloat16):
     return ops.clip_preprocess(t, size, dtype=dtype)
 
 
+# Reward worker threads (train_sd3_fast_pickscore.py:668) may capture the image-tower graph; set to False to let only
+# the main thread capture (workers then run the tower eagerly until the main thread has captured it).
+CAPTURE_FROM_ANY_THREAD = os.environ.get("ADVGRPO_SCORER_CAPTURE_MAIN_ONLY", "0") != "1"
+
+
 class _GraphedImageTower:
     """CUDA-graph replay of `model.get_image_features` for a fixed batch shape (the ViT-H forward is ~400
     launches of a few microseconds each: launch-bound when issued eagerly).  Re-captured whenever a
@@ -93,7 +99,12 @@ class _GraphedImageTower:
                 self.entries[key] = (ver, None, None, None, 0)
                 return self.model.get_image_features(pixel_values=pixel_values)
         if ent[1] is None:
+            if not CAPTURE_FROM_ANY_THREAD and threading.current_thread() is not threading.main_thread():
+                return self.model.get_image_features(pixel_values=pixel_values)
             static_in = pixel_values.clone()
+            # warm up in THIS thread right before capturing: per-thread lazily created state (cuBLAS handle of the
+            # projection, per-thread workspaces) must exist, creating it inside a capture invalidates the capture
+            self.model.get_image_features(pixel_values=static_in)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
