@@ -284,6 +284,23 @@ def run_ours(args):
     trainer.embedder, trainer.reference_image_fn = emb_host, ref_host
     ms_e2e, _, d2h = timed(args.steps, True)
     clk = clocks.stop() if rank == 0 else None
+    # phase split of ONE further step (device-resident inputs, CUDA events between the phases; explains `value`,
+    # is not part of it)
+    trainer.embedder, trainer.reference_image_fn = emb_dev, ref_dev
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier()
+    ev[0].record()
+    smp = trainer.sample_epoch()
+    ev[1].record()
+    adv = trainer.compute_advantages(smp)
+    ev[2].record()
+    trainer.train_generator(smp, adv)
+    ev[3].record()
+    trainer.epoch += 1
+    barrier()
+    phases = {"rollout_decode_score": ev[0].elapsed_time(ev[1]), "advantages": ev[1].elapsed_time(ev[2]),
+              "update": ev[2].elapsed_time(ev[3])}
+    del smp, adv
     samples = world * NB * G * args.steps
     value = samples / (ms_dev / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
@@ -360,7 +377,8 @@ def run_ours(args):
                        "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h / args.steps},
-            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels}
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
+            "phases_ms": phases}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
