@@ -156,11 +156,14 @@ def test_reward_fn_from_thread_pool_while_main_thread_works():
     with ThreadPoolExecutor(max_workers=8) as ex:
         futs = [ex.submit(lambda b, p: fn(b, p, [{}] * 4, scorer=fresh)[0]["avg"].clone(), b, p)
                 for b, p in zip(batches, prompts)]
-        outs = []
+        outs, n_iter = [], 0
         while not all(f.done() for f in futs):                                # the "sampling" thread: kernels + allocations
-            outs.append(ops.gemm(a, w) + torch.zeros(512, 384, device=DEV, dtype=torch.bfloat16))
+            o = ops.gemm(a, w) + torch.zeros(512, 384, device=DEV, dtype=torch.bfloat16)
+            if n_iter % 64 == 0 and len(outs) < 64:                           # keep a bounded sample of the results
+                outs.append(o)
+            n_iter += 1
         got = [f.result() for f in futs]
     torch.cuda.synchronize()
     for s, c in zip(serial, got):
         assert torch.equal(s, c)
-    assert all(torch.equal(o, want) for o in outs[:: max(1, len(outs) // 16)])
+    assert all(torch.equal(o, want) for o in outs)
