@@ -30,6 +30,7 @@ SIGNATURES = {
                                                     _I64, _F, _F, _I, _P]),
     "advgrpo_group_advantage_workspace_bytes": (_SZ, [_I64, _I64]),
     "advgrpo_group_advantage": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _SZ, _P]),
+    "advgrpo_group_advantage_mode": (c_int, [_P, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P, _SZ, _P]),
     "advgrpo_grpo_clip_loss": (c_int, [_P, _P, _P, _I64, _I64, _D, _D, _D, _P, _P, _P]),
     "advgrpo_clip_adamw_workspace_bytes": (_SZ, [_I64]),
     "advgrpo_clip_adamw": (c_int, [_P, _P, _P, _P, _I64, _D, _D, _D, _D, _D, _I64, _D, _I, _P, _P, _SZ, _P]),
@@ -94,7 +95,7 @@ def load():
 
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_clip_adamw": 2,
+_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
                      "advgrpo_device_check": 0}
 _launches = [0]
 

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(1024) group_advantage_kernel(const float* __re
                                                                const uint64_t* __restrict__ h1,
                                                                const uint64_t* __restrict__ h2,
                                                                int64_t N, int64_t T, int global_std,
-                                                               double* __restrict__ adv,
+                                                               int mode, double* __restrict__ adv,
                                                                double* __restrict__ stats) {
   __shared__ double scratch[32];
   __shared__ double col_std[16];
@@ -74,7 +74,33 @@ __global__ void __launch_bounds__(1024) group_advantage_kernel(const float* __re
   for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
     const uint64_t a = h1[i], b = h2[i];
     bool leader = true;
-    for (int64_t t = 0; t < T; ++t) {
+    if (mode != 0) {
+      // the other `type`s of PerPromptStatTracker.update (stat_tracking.py:48-70); group members in array order
+      for (int64_t j = 0; j < i; ++j)
+        if (h1[j] == a && h2[j] == b) leader = false;
+      if (mode == 1) {                                   // 'rwr': the rewards themselves
+        for (int64_t t = 0; t < T; ++t) adv[i * T + t] = (double)r[i * T + t];
+      } else if (mode == 2) {                            // 'sft': 1 where the reward equals the maximum of the group's
+        float mx = -INFINITY;                            //        WHOLE [n, T] block (torch.max over all elements)
+        for (int64_t j = 0; j < N; ++j)
+          if (h1[j] == a && h2[j] == b)
+            for (int64_t t = 0; t < T; ++t) mx = fmaxf(mx, r[j * T + t]);
+        for (int64_t t = 0; t < T; ++t) adv[i * T + t] = r[i * T + t] == mx ? 1.0 : 0.0;
+      } else {                                           // 'dpo' (T == 1): +1 at the first arg-max, -1 at the first arg-min
+        float mx = -INFINITY, mn = INFINITY;
+        int64_t jmax = -1, jmin = -1, first = -1, second = -1;
+        for (int64_t j = 0; j < N; ++j)
+          if (h1[j] == a && h2[j] == b) {
+            const float v = r[j];
+            if (v > mx) { mx = v; jmax = j; }
+            if (v < mn) { mn = v; jmin = j; }
+            if (first < 0) first = j; else if (second < 0) second = j;
+          }
+        if (jmax == jmin) { jmin = first; jmax = second; }   // all equal: min_idx = 0, max_idx = 1 (stat_tracking.py:60-62)
+        adv[i] = i == jmax ? 1.0 : (i == jmin ? -1.0 : 0.0);
+      }
+    }
+    for (int64_t t = 0; mode == 0 && t < T; ++t) {
       double s = 0.0;
       int64_t cnt = 0;
       for (int64_t j = 0; j < N; ++j) {
@@ -185,11 +211,13 @@ size_t advgrpo_group_advantage_workspace_bytes(int64_t N, int64_t T) {
   return (size_t)N * 2 * sizeof(uint64_t) + 16;
 }
 
-int advgrpo_group_advantage(const float* rewards, const int64_t* group_keys, int64_t key_len,
-                            int64_t N, int64_t T, int global_std, double* advantages,
-                            double* stats, void* workspace, size_t workspace_bytes,
-                            advgrpo_stream_t stream) {
+int advgrpo_group_advantage_mode(const float* rewards, const int64_t* group_keys, int64_t key_len,
+                                 int64_t N, int64_t T, int global_std, int mode, double* advantages,
+                                 double* stats, void* workspace, size_t workspace_bytes,
+                                 advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(rewards && group_keys && advantages, "group_advantage: null pointer");
+  ADVGRPO_CHECK_ARG(mode >= ADVGRPO_ADV_GRPO && mode <= ADVGRPO_ADV_DPO, "group_advantage: unknown mode %d", mode);
+  ADVGRPO_CHECK_ARG(mode != ADVGRPO_ADV_DPO || T == 1, "group_advantage: mode 'dpo' needs 1-D rewards (T = 1)");
   ADVGRPO_CHECK_ARG(N >= 0 && T >= 1 && T <= 16 && key_len >= 1,
                     "group_advantage: need N >= 0, 1 <= T <= 16, key_len >= 1 (got N=%lld T=%lld key_len=%lld)",
                     (long long)N, (long long)T, (long long)key_len);
@@ -203,9 +231,17 @@ int advgrpo_group_advantage(const float* rewards, const int64_t* group_keys, int
   hash_rows_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(group_keys, key_len, N, h1, h2);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   int threads = N >= 1024 ? 1024 : (int)(((N + 31) / 32) * 32);
-  group_advantage_kernel<<<1, threads, 0, st>>>(rewards, h1, h2, N, T, global_std, advantages, stats);
+  group_advantage_kernel<<<1, threads, 0, st>>>(rewards, h1, h2, N, T, global_std, mode, advantages, stats);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
+}
+
+int advgrpo_group_advantage(const float* rewards, const int64_t* group_keys, int64_t key_len,
+                            int64_t N, int64_t T, int global_std, double* advantages,
+                            double* stats, void* workspace, size_t workspace_bytes,
+                            advgrpo_stream_t stream) {
+  return advgrpo_group_advantage_mode(rewards, group_keys, key_len, N, T, global_std, ADVGRPO_ADV_GRPO, advantages, stats,
+                                      workspace, workspace_bytes, stream);
 }
 
 int advgrpo_grpo_clip_loss(const float* log_prob, const float* old_log_prob,

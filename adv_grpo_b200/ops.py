@@ -155,9 +155,12 @@ def sde_logprob_replay(noise_pred, x, prev_sample, timesteps, sched_timesteps, s
 
 
 # --------------------------------------------------------------------------- A9
-def group_advantage(rewards, group_keys, global_std=True, want_stats=True):
-    """rewards f32 [N] or [N,T] (CUDA); group_keys int64 [N] or [N,L] (CUDA).
-    Returns (advantages f64 same shape as rewards, stats f64[4] or None)."""
+ADV_MODES = {"grpo": 0, "rwr": 1, "sft": 2, "dpo": 3}
+
+
+def group_advantage(rewards, group_keys, global_std=True, want_stats=True, mode="grpo"):
+    """rewards f32 [N] or [N,T] (CUDA); group_keys int64 [N] or [N,L] (CUDA); mode = the `type` of
+    PerPromptStatTracker.update.  Returns (advantages f64 same shape as rewards, stats f64[4] or None)."""
     _need_cuda(rewards, group_keys)
     squeeze = rewards.dim() == 1
     r = rewards.to(torch.float32).reshape(rewards.shape[0], -1).contiguous()
@@ -167,8 +170,8 @@ def group_advantage(rewards, group_keys, global_std=True, want_stats=True):
     stats = torch.zeros(4, dtype=torch.float64, device=r.device) if want_stats else None
     ws_bytes = _lib.query("advgrpo_group_advantage_workspace_bytes", N, T)
     ws = _workspace("adv", ws_bytes, r.device)
-    _lib.call("advgrpo_group_advantage", _ptr(r), _ptr(keys), keys.shape[1], N, T, int(bool(global_std)),
-              _ptr(adv), _ptr(stats), _ptr(ws), ws.numel(), _stream())
+    _lib.call("advgrpo_group_advantage_mode", _ptr(r), _ptr(keys), keys.shape[1], N, T, int(bool(global_std)),
+              ADV_MODES[mode], _ptr(adv), _ptr(stats), _ptr(ws), ws.numel(), _stream())
     return (adv[:, 0] if squeeze else adv), stats
 
 

@@ -1,11 +1,11 @@
-"""Drop-in for `adv_grpo/stat_tracking.py` (`PerPromptStatTracker`, type='grpo').  Same constructor,
+"""Drop-in for `adv_grpo/stat_tracking.py` (`PerPromptStatTracker`).  Same constructor,
 `update(prompts, rewards) -> float64 ndarray`, `get_stats()`, `clear()`; the arithmetic is the
 group-advantage kernel.  `update_device` is the B200-native entry: it takes the gathered reward
 tensor and the gathered prompt-id rows ON THE DEVICE and returns device tensors, skipping the
 tokenizer decode and both host round trips of `train_sd3_fast_pickscore.py:931,962-970,995-999`.
 History semantics: the scripts clear the tracker every epoch (`:989`), so an update only ever sees
 the current epoch's rewards; carrying statistics across un-cleared updates is not supported
-(raises), the 'rwr' / 'sft' / 'dpo' modes are unused by the scripts and not provided."""
+(raises).  The 'rwr' / 'sft' / 'dpo' modes (unused by the scripts) are modes of the same kernel."""
 import zlib
 
 import numpy as np
@@ -22,23 +22,23 @@ class PerPromptStatTracker:
         self.history_prompts = set()
         self._last = None
 
-    def update_device(self, prompt_keys, rewards):
+    def update_device(self, prompt_keys, rewards, type="grpo"):
         """prompt_keys int64 [N] or [N, L] (e.g. gathered `prompt_ids`), rewards f32 [N] or [N, T], both CUDA.
         Returns advantages f64 (same shape as rewards) on the device."""
-        adv, stats = ops.group_advantage(rewards, prompt_keys, self.global_std, want_stats=True)
+        adv, stats = ops.group_advantage(rewards, prompt_keys, self.global_std, want_stats=True, mode=type)
         self._last = stats
         return adv
 
     def update(self, prompts, rewards, type="grpo"):
-        if type != "grpo":
-            raise NotImplementedError("only type='grpo' is used by the training scripts")
+        if type not in ops.ADV_MODES:
+            raise ValueError(f"unknown type {type!r}; the reference knows 'grpo', 'rwr', 'sft', 'dpo'")
         if self.stats:
             raise NotImplementedError("call clear() between updates (the scripts do, train_sd3_fast_pickscore.py:989)")
         prompts = list(prompts)
         keys = torch.tensor([[zlib.crc32(p.encode()), zlib.adler32(p.encode()), len(p)] for p in prompts],
                             dtype=torch.int64, device=self.device)
         r = torch.as_tensor(np.asarray(rewards, dtype=np.float64), dtype=torch.float32, device=self.device)
-        adv = self.update_device(keys, r)
+        adv = self.update_device(keys, r, type)
         uniq = set(prompts)
         for p in uniq:
             self.stats[p] = prompts.count(p)

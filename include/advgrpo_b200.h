@@ -130,7 +130,21 @@ int advgrpo_cfg_sde_logprob_bwd_variant(const void* v_uncond, const void* v_text
  * float64, quirk Q5).  stats (optional, f64 [4]): {n_groups, mean group size,
  * zero_std_ratio, mean per-group std of column 0}.
  */
+/* `type` of PerPromptStatTracker.update (stat_tracking.py:46-70).  GRPO is the only one the training scripts
+ * use; the others are per-group selections of the same [N, T] rewards:
+ *   RWR: the rewards themselves;  SFT: 1.0 where the reward equals the maximum over the group's whole [n, T]
+ *   block;  DPO (T = 1 only): +1 at the group's first arg-max, -1 at its first arg-min, members in array order,
+ *   an all-equal group gets -1 / +1 on its first / second member. */
+#define ADVGRPO_ADV_GRPO 0
+#define ADVGRPO_ADV_RWR 1
+#define ADVGRPO_ADV_SFT 2
+#define ADVGRPO_ADV_DPO 3
 size_t advgrpo_group_advantage_workspace_bytes(int64_t N, int64_t T);
+int advgrpo_group_advantage_mode(const float* rewards, const int64_t* group_keys, int64_t key_len,
+                                 int64_t N, int64_t T, int global_std, int mode, double* advantages,
+                                 double* stats, void* workspace, size_t workspace_bytes,
+                                 advgrpo_stream_t stream);
+/* mode = ADVGRPO_ADV_GRPO */
 int advgrpo_group_advantage(const float* rewards, const int64_t* group_keys, int64_t key_len,
                             int64_t N, int64_t T, int global_std, double* advantages,
                             double* stats, void* workspace, size_t workspace_bytes,

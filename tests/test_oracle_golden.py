@@ -102,3 +102,18 @@ def test_flow_sde_step_g11(golden, golden_dir):
     assert torch.equal(prev, t["prev_rollout"]) and torch.equal(mean_r, t["mean_rollout"])
     np.testing.assert_array_equal(lp_r.numpy(), np.array(golden["G11_rollout_log_prob"], dtype=np.float32))
     np.testing.assert_array_equal(std_r.flatten().numpy(), np.array(golden["G11_rollout_std"], dtype=np.float32))
+
+
+def test_advantage_modes_g12(golden_dir):
+    """'rwr' / 'sft' / 'dpo' of PerPromptStatTracker.update: oracle restatement vs the verbatim reference file
+    (tests/golden/make_golden_adv_modes.py)."""
+    import json
+    import os
+    with open(os.path.join(golden_dir, "golden_adv_modes.json")) as f:
+        g = json.load(f)
+    for mode in ("rwr", "sft", "dpo"):
+        got = st_o.mode_advantages(g["prompts"], g["rewards"], mode)
+        for gs in (0, 1):                                   # global_std does not enter these modes
+            np.testing.assert_array_equal(got, np.array(g[f"{mode}_global{gs}"]))
+    for mode in ("rwr", "sft"):
+        np.testing.assert_array_equal(st_o.mode_advantages(g["prompts"], g["rewards_2d"], mode), np.array(g[f"{mode}_2d"]))

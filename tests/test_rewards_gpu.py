@@ -167,3 +167,29 @@ def test_reward_fn_from_thread_pool_while_main_thread_works():
     for s, c in zip(serial, got):
         assert torch.equal(s, c)
     assert all(torch.equal(o, want) for o in outs)
+
+
+def test_stat_tracker_other_types_match_reference_golden(golden_dir):
+    """PerPromptStatTracker.update(type='rwr' | 'sft' | 'dpo') (stat_tracking.py:48-70) as modes of the group-advantage
+    kernel, bit-exact against the outputs of the verbatim reference file (golden G12), ties and an all-equal group
+    included; 2-D rewards for 'rwr' / 'sft'; 'dpo' refuses 2-D rewards (the reference's flat index is only meaningful
+    for 1-D)."""
+    import json
+    import os
+    from adv_grpo_b200 import _lib
+    from adv_grpo_b200.stat_tracking import PerPromptStatTracker
+    with open(os.path.join(golden_dir, "golden_adv_modes.json")) as f:
+        g = json.load(f)
+    for mode in ("rwr", "sft", "dpo"):
+        for gs in (False, True):
+            t = PerPromptStatTracker(global_std=gs)
+            a = t.update(g["prompts"], g["rewards"], type=mode)
+            assert a.dtype == np.float64
+            np.testing.assert_array_equal(a, np.array(g[f"{mode}_global{int(gs)}"]))
+    for mode in ("rwr", "sft"):
+        a = PerPromptStatTracker(global_std=True).update(g["prompts"], g["rewards_2d"], type=mode)
+        np.testing.assert_array_equal(a, np.array(g[f"{mode}_2d"]))
+    with pytest.raises(_lib.AdvGrpoError, match="dpo"):
+        PerPromptStatTracker().update(g["prompts"], g["rewards_2d"], type="dpo")
+    with pytest.raises(ValueError):
+        PerPromptStatTracker().update(g["prompts"], g["rewards"], type="ppo")
