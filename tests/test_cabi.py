@@ -59,3 +59,33 @@ def test_ops_refuse_cpu_tensors():
     from adv_grpo_b200.optim import FlatClipAdamW
     with pytest.raises(ValueError, match="CUDA"):
         FlatClipAdamW([torch.nn.Parameter(torch.zeros(8))])
+
+
+def test_empty_inputs_are_noops_or_clean_errors():
+    """Edge of every size range, checked without a device (the entry points decide before any CUDA call): the
+    streaming ops accept an empty batch as a no-op returning 0; the tensor-core / image ops refuse empty shapes with
+    ADVGRPO_ERR_BAD_ARG and a message instead of launching a zero-sized grid."""
+    buf = 4096                     # a non-null, 16-byte aligned address that is never dereferenced for empty inputs
+    ok = [
+        ("advgrpo_group_advantage", (buf, buf, 1, 0, 2, 1, buf, None, None, 0, None)),
+        ("advgrpo_group_advantage_mode", (buf, buf, 1, 0, 1, 0, 3, buf, None, None, 0, None)),
+        ("advgrpo_ln_modulate_fwd", (buf, buf, buf, None, None, 1536, buf, None, 0, 77, 1536, 1e-6, None)),
+        ("advgrpo_ln_modulate_bwd", (buf, buf, None, 1536, buf, None, buf, 0, 0, 77, 1536, 1e-6, None)),
+        ("advgrpo_layer_norm_affine", (buf, buf, buf, buf, 0, 1280, 1e-5, None)),
+        ("advgrpo_row_gate_mul", (buf, buf, 1536, 1, buf, 0, 1536, None)),
+        ("advgrpo_qk_norm_concat_fwd", (buf, None, buf, buf, None, None, buf, 0, 16, 0, 24, 64, 1e-6, None)),
+        ("advgrpo_clip_adamw", (buf, buf, buf, buf, 0, 3e-4, 0.9, 0.999, 1e-8, 1e-4, 1, 1.0, 1, None, None, 0, None)),
+    ]
+    for name, args in ok:
+        assert _lib.call(name, *args) == 0, name
+    bad = [
+        ("advgrpo_attn_fwd", (buf, buf, None, 0, None, 0, 128, 4, 64, 0.125, 0, None)),
+        ("advgrpo_attn_bwd", (buf, buf, buf, buf, buf, 0, 128, 4, 64, 0.125, 0, buf, 1 << 20, None)),
+        ("advgrpo_conv2d_nhwc_tf32", (buf, buf, None, buf, 0, 8, 8, 64, 64, 3, None)),
+        ("advgrpo_dino_preprocess", (buf, 0, 0, 64, 64, 518, buf, buf, buf, None)),
+        ("advgrpo_upsample_nearest2x_nhwc", (buf, buf, 0, 8, 8, 64, None)),
+    ]
+    for name, args in bad:
+        with pytest.raises(_lib.AdvGrpoError):
+            _lib.call(name, *args)
+        assert len(_lib.load().advgrpo_last_error()) > 0
