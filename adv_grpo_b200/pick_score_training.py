@@ -37,19 +37,47 @@ class CLIPCriterion(_Loss):
         i0, i1 = img.chunk(2, dim=0)
         return i0, i1, text
 
+    @staticmethod
+    def gather_features(features):
+        """Autograd-aware all-gather over the ranks (pick_score_training.py:108-111)."""
+        import torch.distributed.nn
+        return torch.cat(torch.distributed.nn.all_gather(features), dim=0)
+
     def calc_loss(self, text_features, image_0_features, image_1_features, logit_scale, label_0, label_1,
                   num_examples_per_prompt, *args, **kwargs):
-        if self.cfg.in_batch_negatives or self.cfg.is_distributed:
-            raise NotImplementedError("the training scripts use in_batch_negatives=False, is_distributed=False")
-        # per prompt: softmax over {real_i, fake_i} of s * <t_i, .>  (row-wise dots; no [B,2B] matmul)
+        device = image_0_features.device
+        if self.cfg.is_distributed:                                   # pick_score_training.py:135-141
+            image_0_features = self.gather_features(image_0_features)
+            image_1_features = self.gather_features(image_1_features)
+            text_features = self.gather_features(text_features)
+            label_0 = self.gather_features(label_0)
+            label_1 = self.gather_features(label_1)
+        label_0, label_1 = torch.as_tensor(label_0, device=device), torch.as_tensor(label_1, device=device)
+        zeros = torch.zeros(text_features.shape[0], dtype=torch.long, device=device)
+        # text loss of the pair {image_0_i, image_1_i}: softmax over s * <t_i, .> (row-wise dots; the reference takes
+        # the diagonals of a [B, 2B] matmul, :172-181)
         l0 = logit_scale * (text_features * image_0_features).sum(-1)
         l1 = logit_scale * (text_features * image_1_features).sum(-1)
-        pair = torch.stack([l0, l1], dim=-1)
-        zeros = torch.zeros(pair.shape[0], dtype=torch.long, device=pair.device)
-        loss = label_0 * F.cross_entropy(pair, zeros, reduction="none") + \
-            label_1 * F.cross_entropy(pair, zeros + 1, reduction="none")
-        is_tie = (torch.as_tensor(label_0) == torch.as_tensor(label_1)).float()
-        loss = loss + is_tie * torch.log(torch.tensor(0.5, device=pair.device))
+        if self.cfg.in_batch_negatives:                               # :150-170: every other example is a negative
+            all_images = torch.cat([image_0_features, image_1_features], dim=0)
+            logits_per_image = logit_scale * all_images @ text_features.T
+            image_0_logits, image_1_logits = logits_per_image.chunk(2, dim=0)
+            text_logits = logit_scale * text_features @ all_images.T
+            labels = torch.arange(all_images.shape[0], device=device, dtype=torch.long)
+            image_0_labels, image_1_labels = labels.chunk(2, dim=0)
+            text_labels = torch.arange(text_features.shape[0], device=device, dtype=torch.long)
+            image_loss = label_0 * F.cross_entropy(image_0_logits, text_labels, reduction="none") + \
+                label_1 * F.cross_entropy(image_1_logits, text_labels, reduction="none")
+            text_0_loss = F.cross_entropy(text_logits, image_0_labels, reduction="none")
+            text_1_loss = F.cross_entropy(text_logits, image_1_labels, reduction="none")
+        else:
+            pair = torch.stack([l0, l1], dim=-1)
+            text_0_loss = F.cross_entropy(pair, zeros, reduction="none")
+            text_1_loss = F.cross_entropy(pair, zeros + 1, reduction="none")
+        text_loss = label_0 * text_0_loss + label_1 * text_1_loss
+        is_tie = (label_0 == label_1).float()                         # a tie's ideal loss is log 2: shift it to 0 (:186-190)
+        text_loss = text_loss + is_tie * torch.log(torch.tensor(0.5, device=device))
+        loss = (image_loss + text_loss) / 2 if self.cfg.in_batch_negatives else text_loss
         return loss.mean()
 
     def forward(self, model, batch):

@@ -382,3 +382,50 @@ def test_ocr_host_plugin_reward_arithmetic():
     assert torch.allclose(details["avg"], 2.0 * torch.tensor(got))
     with pytest.raises(ImportError, match="paddleocr"):
         OcrScorer()
+
+
+def _criterion_rank(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adv_grpo_b200.pick_score_training import CLIPCriterion, CLIPCriterionConfig
+    t = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g13_tensors.pt"))
+    n = t["t"].shape[0] // world
+    sl = slice(rank * n, (rank + 1) * n)
+    res = {}
+    for ibn in (False, True):
+        cfg = CLIPCriterionConfig(is_distributed=True, in_batch_negatives=ibn)
+        tt = t["t"][sl].clone().requires_grad_(True)
+        loss = CLIPCriterion(cfg).calc_loss(tt, t["i0"][sl], t["i1"][sl], torch.tensor(100.0), t["label_0"][sl],
+                                            t["label_1"][sl], torch.ones(n))
+        loss.backward()
+        res[f"loss_ibn{int(ibn)}"] = loss.item()
+        res[f"grad_t_sum_ibn{int(ibn)}"] = tt.grad.double().abs().sum().item()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_clip_criterion_in_batch_negatives_ties_and_distributed_g13(golden_dir):
+    """The branches of CLIPCriterion.calc_loss the presets leave off (pick_score_training.py:135-170: in-batch
+    negatives, per-example labels with ties, features gathered over the ranks) against golden G13 produced by the
+    verbatim reference class (tests/golden/make_golden_criterion.py); the distributed case on 2 gloo ranks."""
+    import json
+    import torch.multiprocessing as mp
+    from adv_grpo_b200.pick_score_training import CLIPCriterion, CLIPCriterionConfig
+    with open(os.path.join(golden_dir, "golden_criterion.json")) as f:
+        g = json.load(f)
+    t = torch.load(os.path.join(golden_dir, "g13_tensors.pt"))
+    for ibn in (False, True):
+        tt = t["t"].clone().requires_grad_(True)
+        loss = CLIPCriterion(CLIPCriterionConfig(in_batch_negatives=ibn)).calc_loss(
+            tt, t["i0"], t["i1"], torch.tensor(100.0), t["label_0"], t["label_1"], torch.ones(6))
+        loss.backward()
+        assert abs(loss.item() - g[f"local_loss_ibn{int(ibn)}"]) < 1e-5
+        assert abs(tt.grad.double().abs().sum().item() - g[f"local_grad_t_abs_sum_ibn{int(ibn)}"]) < 1e-3
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_criterion_rank, args=(2, 29541, out), nprocs=2, join=True)
+        got = {str(k): dict(v) for k, v in out.items()}
+    for r in ("0", "1"):
+        for k, v in g["distributed_world2"][r].items():
+            assert abs(got[r][k] - v) < 1e-3 * max(1.0, abs(v)), (r, k, got[r][k], v)
