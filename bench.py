@@ -26,7 +26,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "GRPO samples/sec (rollout+score+update) SD3.5-medium 512x512 G=8 10-step PickScore LoRA"
+# `metric` is BASELINE.json's own string (the workload detail -- SD3.5-medium LoRA r32, 512x512, G = 8, 10 steps,
+# PickScore -- is spelled out in `config.workload`)
+METRIC = "GRPO samples/sec (rollout+score+update) SD3-m G=8 10-step @1/2/4/8 B200"
+try:
+    with open(os.path.join(ROOT, "BASELINE.json")) as _f:
+        METRIC = json.load(_f).get("metric", METRIC)
+except (OSError, ValueError):
+    pass
 UNIT = "samples/s"
 NB, G, T_STEPS, T_TRAIN, RES = 2, 8, 10, 2, 512
 
