@@ -234,3 +234,27 @@ def test_mmdit_joint_block_oracle_matches_flux_double_stream_block():
     # the sinusoidal timestep features (diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0))
     t = torch.tensor([1000.0, 464.876, 8.9286])
     assert torch.allclose(timestep_embedding(t), layers.timestep_embedding(t, 256, time_factor=1.0), atol=1e-6)
+
+
+def test_mmdit_pos_embed_matches_mae_sincos_tables():
+    """diffusers `get_2d_sincos_pos_embed` (behind PatchEmbed.cropped_pos_embed, the MMDiT's additive position table)
+    is the MAE table with the grid divided by `grid_size / base_size`; transformers ships the MAE original.  Pins the
+    axis order (w first), the [sin, cos] halves and the half-h / half-w split of the oracle; the centre crop is then
+    the same table evaluated on the cropped, scaled coordinates."""
+    import pytest
+    mae = pytest.importorskip("transformers.models.vit_mae.modeling_vit_mae")
+    from oracle.mmdit import cropped_pos_embed
+    dim, n = 64, 12
+    full = cropped_pos_embed(dim, n, n, max_size=n, base_size=n)[0].numpy()          # no crop, scale 1
+    np.testing.assert_allclose(full, mae.get_2d_sincos_pos_embed(dim, n), atol=1e-6)
+    h, w, max_size, base = 6, 10, 24, 8                                                # SD3.5: 384 / 64, crop to the latent grid
+    top, left = (max_size - h) // 2, (max_size - w) // 2
+    gh = np.arange(top, top + h, dtype=np.float64) / (max_size / base)
+    gw = np.arange(left, left + w, dtype=np.float64) / (max_size / base)
+    grid = np.stack(np.meshgrid(gw, gh), axis=0).reshape(2, 1, h, w)
+    want = mae.get_2d_sincos_pos_embed_from_grid(dim, grid)
+    got = cropped_pos_embed(dim, h, w, max_size=max_size, base_size=base)[0].numpy()
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    # and it IS a crop of the full max_size table
+    table = cropped_pos_embed(dim, max_size, max_size, max_size=max_size, base_size=base)[0].reshape(max_size, max_size, dim)
+    np.testing.assert_allclose(got.reshape(h, w, dim), table[top:top + h, left:left + w].numpy(), atol=1e-6)
