@@ -258,3 +258,33 @@ def test_mmdit_pos_embed_matches_mae_sincos_tables():
     # and it IS a crop of the full max_size table
     table = cropped_pos_embed(dim, max_size, max_size, max_size=max_size, base_size=base)[0].reshape(max_size, max_size, dim)
     np.testing.assert_allclose(got.reshape(h, w, dim), table[top:top + h, left:left + w].numpy(), atol=1e-6)
+
+
+def test_mmdit_dual_attention_branch_matches_flux_self_attention():
+    """The image-only `attn2` of the SD3.5 dual-attention blocks (JointAttnProcessor2_0 without a context: to_q/k/v,
+    per-head RMS q/k norm, SDPA, to_out) against torchtitan's FLUX `SelfAttention` (fused qkv + QKNorm + attention +
+    proj; RoPE at position 0 = identity) with the oracle's diffusers-named weights mapped onto it."""
+    import pytest
+    layers = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    from adv_grpo_b200 import weights
+    from oracle.mmdit import MMDiTOracle
+    cfg = dict(weights.MMDIT_TINY)
+    p = weights.init_mmdit(cfg, seed=21, device="cpu", dtype=torch.float32)
+    H, D = cfg["heads"], cfg["head_dim"]
+    d = H * D
+    pre = "transformer_blocks.0.attn2"
+    sa = layers.SelfAttention(d, num_heads=H, qkv_bias=True).eval()
+    sa.norm.query_norm.eps = sa.norm.key_norm.eps = 1e-6
+    sd = {"norm.query_norm.weight": p[f"{pre}.norm_q.weight"], "norm.key_norm.weight": p[f"{pre}.norm_k.weight"]}
+    for s in ("weight", "bias"):
+        sd[f"qkv.{s}"] = torch.cat([p[f"{pre}.to_{n}.{s}"] for n in "qkv"])
+        sd[f"proj.{s}"] = p[f"{pre}.to_out.0.{s}"]
+    sa.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 36, d, generator=torch.Generator().manual_seed(22))
+    pe = torch.eye(2).expand(1, 1, 36, D // 2, 2, 2)
+    oracle = MMDiTOracle(p, dict(cfg, dual_layers=set(cfg["dual_layers"])))
+    with torch.no_grad():
+        ref = sa(x, pe)
+        got, none = oracle._attn(pre, x)
+    assert none is None
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), (got - ref).abs().max()
