@@ -288,3 +288,20 @@ def test_mmdit_dual_attention_branch_matches_flux_self_attention():
         got, none = oracle._attn(pre, x)
     assert none is None
     assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), (got - ref).abs().max()
+
+
+def test_scheduler_shift_is_the_flux_time_shift():
+    """The static shift of FlowMatchEulerDiscreteScheduler, sigma = shift * s / (1 + (shift - 1) * s), is FLUX's
+    `time_shift(mu = log(shift), sigma = 1, s)` (torchtitan ships the FLUX sampler).  Pins the functional form of the
+    oracle's schedule; the diffusers-specific parts (the shift applied to the training table AND again in
+    set_timesteps, the linspace end points) are restated from diffusers 0.33.1 and stay unpinned."""
+    import math
+    import pytest
+    sampling = pytest.importorskip("torchtitan.experiments.flux.sampling")
+    from oracle.scheduler import FlowMatchEulerOracle
+    sch = FlowMatchEulerOracle(shift=3.0)
+    sch.set_timesteps(10)
+    s = torch.linspace(sch.sigma_max, sch.sigma_min, 10, dtype=torch.float64)          # "t / 1000" space
+    want = sampling.time_shift(math.log(3.0), 1.0, s)
+    assert torch.allclose(sch.sigmas[:-1].double(), want, atol=1e-6)
+    assert sch.sigmas[-1] == 0 and torch.allclose(sch.timesteps, sch.sigmas[:-1] * 1000)
