@@ -5,6 +5,7 @@ numerical result on the hot path comes from the sm_100a kernels; there is no
 PyTorch/CPU fallback -- non-CUDA tensors raise.
 """
 import math
+import os
 import threading
 
 import torch
@@ -469,6 +470,30 @@ def _arr_i(vals):
     return (ctypes.c_int64 * 2)(*[int(v) for v in vals])
 
 
+# Experimental (off by default, ADVGRPO_GEMM_TAIL_SPLIT=1): when the 256x256 pair tiles of a
+# dual launch fill k full waves plus a small remainder, run the rows behind the remainder as a second launch (which
+# picks 128x128 tiles: one partial wave of quarter-cost tiles instead of a whole extra wave of pair tiles).
+GEMM_TAIL_SPLIT = os.environ.get("ADVGRPO_GEMM_TAIL_SPLIT", "0") == "1"
+
+
+def _tail_split_rows(M0, M1, N, rows_per_gate1, sms):
+    """Rows of problem 1 to keep in the dual launch (the rest goes to the tail launch), or None."""
+    pairs, tn = sms // 2, (N + 255) // 256
+    rt0, rt1 = (M0 + 255) // 256, (M1 + 255) // 256
+    tiles = (rt0 + rt1) * tn
+    full, rem = divmod(tiles, pairs)
+    if full < 2 or rem == 0 or 2 * rem > pairs or (full * pairs) % tn:
+        return None
+    keep_tiles = full * pairs // tn - rt0            # row tiles of problem 1 that complete the last full wave
+    if keep_tiles <= 0:
+        return None
+    split = (keep_tiles * 256 // rows_per_gate1) * rows_per_gate1      # whole gate groups only
+    if split <= 0 or split >= M1 or (split + 255) // 256 != keep_tiles:
+        return None
+    tail_tiles = ((M1 - split + 127) // 128) * ((N + 127) // 128)
+    return split if tail_tiles <= sms else None
+
+
 def gemm_dual(a, w, bias=(None, None), a2=(None, None), w2=(None, None), epilogue=EPI_NONE, residual=(None, None),
               gate=(None, None), rows_per_gate=(1, 1), preact_out=(None, None)):
     """Two problems (same N, K, K2, epilogue; different operands / row counts) in one persistent launch.
@@ -490,12 +515,23 @@ def gemm_dual(a, w, bias=(None, None), a2=(None, None), w2=(None, None), epilogu
     K2 = a2r[0].shape[1] if has2 else 0
     r2d = [None if x is None else x.reshape(M[i], N) for i, x in enumerate(residual)]
     st = lambda xs: [0 if x is None else x.stride(0) for x in xs]
+    split = None
+    if GEMM_TAIL_SPLIT:
+        split = _tail_split_rows(M[0], M[1], N, int(rows_per_gate[1]) if gate[1] is not None else 1,
+                                 torch.cuda.get_device_properties(a2d[0].device).multi_processor_count)
+    M_main = M if split is None else [M[0], split]
     _lib.call("advgrpo_gemm_bf16_dual", _arr_p([_ptr(t) for t in a2d]), _arr_i(st(a2d)), _arr_p([_ptr(t) for t in w]),
               _arr_i(st(w)), _arr_p([_ptr(t) for t in a2r]), _arr_i(st(a2r)), _arr_p([_ptr(t) for t in w2]),
               _arr_i(st(w2)), K2, _arr_p([_ptr(t) for t in bias]), _arr_p([_ptr(t) for t in cs]), _arr_i(st(cs)),
-              _arr_i(M), N, K, int(epilogue), _arr_p([_ptr(t) for t in r2d]), _arr_i(st(r2d)),
+              _arr_i(M_main), N, K, int(epilogue), _arr_p([_ptr(t) for t in r2d]), _arr_i(st(r2d)),
               _arr_p([_ptr(t) for t in gate]), _arr_i(st(gate)), _arr_i(rows_per_gate),
               _arr_p([_ptr(t) for t in preact_out]), _stream())
+    if split is not None:                                  # the rows behind the last full wave, as their own launch
+        rows = slice(split, None)
+        cut = lambda t: None if t is None else t.reshape(M[1], -1)[rows]
+        gemm(a2d[1][rows], w[1], bias=bias[1], a2=cut(a2r[1]), w2=w2[1], epilogue=epilogue, residual=cut(r2d[1]),
+             gate=None if gate[1] is None else gate[1][split // int(rows_per_gate[1]):],
+             rows_per_gate=int(rows_per_gate[1]), out=cs[1][rows], preact_out=cut(preact_out[1]))
     return cs[0].reshape(*lead[0], N), cs[1].reshape(*lead[1], N)
 
 

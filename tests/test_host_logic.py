@@ -429,3 +429,22 @@ def test_clip_criterion_in_batch_negatives_ties_and_distributed_g13(golden_dir):
     for r in ("0", "1"):
         for k, v in g["distributed_world2"][r].items():
             assert abs(got[r][k] - v) < 1e-3 * max(1.0, abs(v)), (r, k, got[r][k], v)
+
+
+def test_gemm_tail_split_host_logic():
+    """`ops._tail_split_rows` (experimental, off by default): the config-2 dual launch at N = 1536 is 462 pair tiles on
+    74 CTA pairs = six full waves + 18 tiles; the split keeps exactly the six full waves in the dual launch, cuts the text
+    rows at a whole number of 205-token samples, and leaves a tail that fits one wave of 128x128 tiles.  Shapes whose last
+    wave is more than half full, or that have fewer than two full waves, are left alone."""
+    from adv_grpo_b200 import ops
+    assert ops.GEMM_TAIL_SPLIT is False or os.environ.get("ADVGRPO_GEMM_TAIL_SPLIT") == "1"
+    f = ops._tail_split_rows
+    s = f(16384, 3280, 1536, 205, 148)
+    assert s == 2460 and s % 205 == 0
+    main_tiles = ((16384 + 255) // 256 + (s + 255) // 256) * 6
+    assert main_tiles == 6 * 74                                            # exactly six full waves
+    assert ((3280 - s + 127) // 128) * 12 <= 148                           # the tail is one wave of 128x128 tiles
+    assert f(16384, 3280, 1536, 1, 148) == 2560
+    assert f(16384, 3280, 4608, 1, 148) is None                            # 18.7 waves: last wave 73 % full
+    assert f(16384, 3280, 6144, 1, 148) is None                            # 24.97 waves
+    assert f(2048, 410, 1536, 205, 148) is None                            # fewer than two full waves
