@@ -31,6 +31,7 @@ def _encoder(p, pre, x, n_layers, heads, causal):
 
 
 def image_features(p, cfg, pixel_values, return_tokens=False):
+    """PickScoreScorer: `model.get_image_features(pixel_values=)` (pickscore_scorer.py:40-41; transformers CLIPModel vision tower + visual_projection)."""
     pre = "vision_model"
     x = F.conv2d(pixel_values, p[pre + ".embeddings.patch_embedding.weight"], stride=cfg["patch"])
     x = x.flatten(2).transpose(1, 2)
@@ -44,6 +45,7 @@ def image_features(p, cfg, pixel_values, return_tokens=False):
 
 
 def text_features(p, cfg, input_ids):
+    """PickScoreScorer: `model.get_text_features(input_ids=)` (pickscore_scorer.py:42-43; causal text tower, EOS pooling, text_projection)."""
     pre = "text_model"
     S = input_ids.shape[1]
     x = p[pre + ".embeddings.token_embedding.weight"][input_ids] + \

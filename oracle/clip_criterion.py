@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 
 def clip_pair_loss(text_features, image_0_features, image_1_features, logit_scale, label_0, label_1):
+    """CLIPCriterion.calc_loss, in_batch_negatives=False branch (pick_score_training.py:117-203)."""
     all_img = torch.cat([image_0_features, image_1_features], dim=0)
     text_logits = logit_scale * text_features @ all_img.T                   # :139
     t0, t1 = text_logits.chunk(2, dim=-1)                                    # :162

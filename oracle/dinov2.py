@@ -18,6 +18,7 @@ def _ln(p, name, x):
 
 
 def forward_features(p, cfg, images):
+    """timm `vit_base_patch14_dinov2.lvd142m` forward_features as called at rewards.py:397-399 / train_sd3_fast_dino_patch.py:589."""
     x = F.conv2d(images, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], stride=cfg["patch"])
     x = x.flatten(2).transpose(1, 2)
     x = torch.cat([p["cls_token"].expand(x.shape[0], -1, -1), x], 1) + p["pos_embed"]

@@ -7,6 +7,7 @@ import torch
 
 
 def grpo_clip_loss(log_prob, old_log_prob, advantages, clip_range, adv_clip_max):
+    """Clipped GRPO loss and its logged statistics (train_sd3_fast_pickscore.py:1111-1162)."""
     adv = torch.clamp(advantages, -adv_clip_max, adv_clip_max)          # :1111-1115
     ratio = torch.exp(log_prob - old_log_prob)                          # :1116
     unclipped = -adv * ratio                                            # :1117

@@ -22,6 +22,7 @@ LORA_TARGETS = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0",
 
 
 def sincos_1d(dim, pos):
+    """diffusers get_1d_sincos_pos_embed_from_grid ([sin, cos] halves) behind PatchEmbed (call site fast.py:630-637)."""
     omega = torch.arange(dim // 2, dtype=torch.float64) / (dim / 2.0)
     omega = 1.0 / 10000 ** omega
     out = pos.reshape(-1).to(torch.float64)[:, None] * omega[None]
@@ -42,6 +43,7 @@ def cropped_pos_embed(dim, h, w, max_size=384, base_size=64):
 
 
 def timestep_embedding(t, dim=256, max_period=10000):
+    """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) of CombinedTimestepTextProjEmbeddings (call site fast.py:630-637)."""
     half = dim // 2
     exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32) / half
     emb = t.float()[:, None] * exponent.exp()[None]
@@ -49,10 +51,12 @@ def timestep_embedding(t, dim=256, max_period=10000):
 
 
 def layer_norm(x, eps=1e-6):
+    """nn.LayerNorm(elementwise_affine=False, eps=1e-6) of AdaLayerNormZero / AdaLayerNormContinuous (call site fast.py:630-637)."""
     return F.layer_norm(x, (x.shape[-1],), eps=eps)
 
 
 def rms_norm(x, w, eps=1e-6):
+    """diffusers RMSNorm(head_dim, eps=1e-6) on q / k inside JointAttnProcessor2_0 (call site fast.py:630-637)."""
     var = x.float().pow(2).mean(-1, keepdim=True)
     return (x * torch.rsqrt(var + eps)).to(w.dtype) * w
 
@@ -69,6 +73,7 @@ class MMDiTOracle:
         self.dtype = dtype
 
     def lin(self, name, x):
+        """nn.Linear, or peft lora.Linear on the 8 targets of train_sd3_fast_pickscore.py:488-505: y + scale * B(A x)."""
         y = F.linear(x, self.p[name + ".weight"], self.p.get(name + ".bias"))
         if name in self.lora:                                   # peft lora.Linear: y + scale * B(A x)
             a, b = self.lora[name]
@@ -104,6 +109,7 @@ class MMDiTOracle:
         return self.lin(f"{pre}.net.2", F.gelu(self.lin(f"{pre}.net.0.proj", x), approximate="tanh"))
 
     def block(self, i, x, c, temb):
+        """diffusers JointTransformerBlock.forward (incl. the SD3.5 dual-attention and the context_pre_only last block), call site fast.py:630-637."""
         pre = f"transformer_blocks.{i}"
         last = i == self.cfg["num_layers"] - 1
         dual = i in self.cfg["dual_layers"]
@@ -136,6 +142,7 @@ class MMDiTOracle:
         return x, c
 
     def forward(self, hidden_states, timestep, encoder_hidden_states, pooled_projections, upto=None):
+        """diffusers SD3Transformer2DModel.forward as called at fast.py:630-637 and train_sd3_fast_pickscore.py:235-255."""
         cfg, dt = self.cfg, self.dtype
         ps = cfg["patch_size"]
         B, C, H, W = hidden_states.shape

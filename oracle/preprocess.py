@@ -21,6 +21,7 @@ CLIP_STD = np.array([0.26862954, 0.26130258, 0.27577711], dtype=np.float32)
 
 
 def quantise_bf16(images_bf16):
+    """`(images * 255).round().clamp(0, 255).to(torch.uint8)` on the bf16 images (rewards.py:581)."""
     return (images_bf16 * 255).round().clamp(0, 255).to(torch.uint8)
 
 
@@ -34,6 +35,7 @@ def _bicubic(x, a=-0.5):
 
 
 def precompute_coeffs(in_size, out_size):
+    """Pillow ImagingResample precompute_coeffs (bicubic, antialiased), the resize CLIPProcessor applies at pickscore_scorer.py:21-28."""
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
     support = 2.0 * filterscale
@@ -77,6 +79,7 @@ def pil_bicubic_resize_u8(img_u8, out_size):
 
 
 def clip_pixel_values(u8_chw):
-    """[B,3,h,w] uint8 -> float32 normalised (rescale in float64, cast f32, normalise in f32)."""
+    """CLIPProcessor rescale (1/255) + normalise after the resize / centre crop (pickscore_scorer.py:21-28).
+    [B,3,h,w] uint8 -> float32 normalised (rescale in float64, cast f32, normalise in f32)."""
     f = (u8_chw.astype(np.float64) * (1 / 255)).astype(np.float32)
     return (f - CLIP_MEAN[None, :, None, None]) / CLIP_STD[None, :, None, None]

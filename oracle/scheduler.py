@@ -28,6 +28,7 @@ class FlowMatchEulerOracle:
     def set_timesteps(self, num_inference_steps, device=None):
         # diffusers: timesteps = linspace(sigma_to_t(sigma_max), sigma_to_t(sigma_min), n);
         # sigmas = timesteps / N; sigmas = shift*s/(1+(shift-1)*s)   (shift applied a 2nd time)
+        """FlowMatchEulerDiscreteScheduler.set_timesteps via retrieve_timesteps (fast.py:574-580)."""
         ts = np.linspace(self._sigma_to_t(self.sigma_max), self._sigma_to_t(self.sigma_min),
                          num_inference_steps)
         sig = ts / self.num_train_timesteps
@@ -39,6 +40,7 @@ class FlowMatchEulerOracle:
         return self.timesteps
 
     def index_for_timestep(self, timestep, schedule_timesteps=None):
+        """FlowMatchEulerDiscreteScheduler.index_for_timestep as used at sd3_sde_with_logprob.py:106."""
         st = self.timesteps if schedule_timesteps is None else schedule_timesteps
         idx = (st == timestep).nonzero()
         pos = 1 if len(idx) > 1 else 0

@@ -11,6 +11,7 @@ import torch
 
 
 def cfg_combine(noise_pred_uncond, noise_pred_text, guidance_scale):
+    """Classifier-free guidance in the dtype of the model output (fast.py:640-642; train_sd3_fast_pickscore.py:242-247)."""
     # fast.py:641-642 -- evaluated in the dtype of the transformer output (bf16 in
     # the reference run: every elementwise op rounds to bf16).
     return noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)

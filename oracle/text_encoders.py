@@ -18,6 +18,7 @@ def _ln(p, name, x, eps=1e-5):
 
 
 def quick_gelu(x):
+    """transformers QuickGELUActivation of the CLIP-L text encoder (encode_prompt, train_dreambooth_lora_sd3.py:59-95)."""
     return x * torch.sigmoid(1.702 * x)
 
 
@@ -51,7 +52,8 @@ def clip_text_with_projection(p, cfg, input_ids):
 
 
 def t5_relative_position_bucket(relative_position, num_buckets=32, max_distance=128):
-    """transformers T5Attention._relative_position_bucket, bidirectional=True."""
+    """transformers T5Attention._relative_position_bucket (bidirectional) behind _encode_prompt_with_t5 (train_dreambooth_lora_sd3.py:19-56).
+    transformers T5Attention._relative_position_bucket, bidirectional=True."""
     num_buckets //= 2
     ret = (relative_position > 0).long() * num_buckets
     n = relative_position.abs()
@@ -64,7 +66,8 @@ def t5_relative_position_bucket(relative_position, num_buckets=32, max_distance=
 
 
 def t5_position_bias(p, S, num_buckets=32, max_distance=128):
-    """[H, S, S] additive score bias shared by every layer (block 0 owns the embedding)."""
+    """transformers T5Attention.compute_bias of block 0, shared by all blocks (train_dreambooth_lora_sd3.py:19-56).
+    [H, S, S] additive score bias shared by every layer (block 0 owns the embedding)."""
     ctx = torch.arange(S)[:, None]
     mem = torch.arange(S)[None, :]
     bucket = t5_relative_position_bucket(mem - ctx, num_buckets, max_distance)

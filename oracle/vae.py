@@ -58,6 +58,7 @@ def vae_decode(p, z):
 
 
 def decode_latents_to_image(p, latents):
+    """`latents / scaling_factor + shift_factor` -> vae.decode -> postprocess('pt') (fast.py:667-670)."""
     z = latents.float() / SCALING_FACTOR + SHIFT_FACTOR          # fast.py:667
     img = vae_decode(p, z)                                       # fast.py:669
     return (img / 2 + 0.5).clamp(0, 1)                           # postprocess('pt') -> denormalize
