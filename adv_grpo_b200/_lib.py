@@ -66,6 +66,7 @@ _EXTRA = {
     "advgrpo_debug_set_gemm_variant": (None, [_I]),
     "advgrpo_debug_set_conv_variant": (None, [_I]),
     "advgrpo_debug_set_pdl": (None, [_I]),
+    "advgrpo_debug_set_attn_trace": (None, [_P]),
 }
 
 _lib = None

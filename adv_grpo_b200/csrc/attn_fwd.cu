@@ -16,6 +16,7 @@
 // Replaces F.scaled_dot_product_attention in diffusers JointAttnProcessor2_0 / CLIPAttention /
 // timm Attention (see include/advgrpo_b200.h for the reference call sites).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -60,6 +61,7 @@ struct Params {
   int causal;
   int park;             // bit 0: MMA warp waits parked, bit 1: softmax S waits parked (experiment switches)
   const float* bias;    // optional additive score bias [H, S, S] (T5 relative positions); persistent kernel only
+  long long* trace;     // debug timeline (quad kernel, TRACE instantiation only): [cta < 4][role 2][tile < 128][8] clock64 stamps
 };
 
 // 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, rel. err 7.5e-5): used for
@@ -738,6 +740,500 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Quad-layout persistent variant (head_dim 64, the MMDiT / DINOv2 shape): the TMA and MMA pipelines are those of
+// attn_fwd_persist_kernel, but the softmax of a 128-row query tile runs on EIGHT warps instead of four.  S is read
+// with the 16-lane tcgen05.ld shape (16x256b: a row is spread over the 4 threads of a quad, like an mma.sync
+// accumulator), so a warp owns 16 rows x 128 columns and a thread 2 rows x 32 columns = 64 scores per tile: ~100
+// registers instead of ~200, which lets 16 softmax warps (4 per SM sub-partition, two CTAs per SM) hide the MUFU /
+// FMA latencies the 8-warp version exposed (ncu: 0.21 IPC per softmax warp, XU pipe 49 %, tensor pipe 30 %).  The row
+// max needs two quad shuffles per tile, the row sum is reduced over the quad once per work item, and P goes back to
+// TMEM with the matching 16x128b store (bf16 pairs of adjacent columns are already in one thread).
+struct QCfg {
+  static constexpr int kTileBytes = BQ * 64 * 2;
+  static constexpr int kSmemTiles = 2 * kTileBytes + STAGES * 2 * kTileBytes;
+  static constexpr int kSmemBytes = kSmemTiles + 1024 + 256;
+  static constexpr int kTmemCols = 256;                  // S 128 | P 64 | O 64
+  static constexpr int kSoftmaxWarps = 8;
+  static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;
+  // 2 CTAs / SM: 384 threads x 80 registers at launch = 256 x kRegsSoftmax + 128 x kRegsUtility
+  static constexpr int kRegsSoftmax = 104;
+  static constexpr int kRegsUtility = 32;
+};
+
+template <int EMU, bool TRACE = false>
+__global__ void __launch_bounds__(QCfg::kThreads, 2)
+attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_o,
+                     const __grid_constant__ CUtensorMap tmap_o2, const Params p, const int n_items, const int nqt,
+                     const int tma_out) {
+  using C = QCfg;
+  constexpr int D = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                                   // 2 tiles
+  uint8_t* k_smem = smem + 2 * C::kTileBytes;               // STAGES tiles
+  uint8_t* v_smem = k_smem + STAGES * C::kTileBytes;        // STAGES tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemTiles);
+  uint64_t* bar_q_full = bars;                   // 2
+  uint64_t* bar_q_empty = bars + 2;              // 2
+  uint64_t* bar_k_full = bars + 4;               // STAGES
+  uint64_t* bar_v_full = bar_k_full + STAGES;    // STAGES
+  uint64_t* bar_k_empty = bar_v_full + STAGES;   // STAGES
+  uint64_t* bar_v_empty = bar_k_empty + STAGES;  // STAGES
+  uint64_t* bar_s_full = bar_v_empty + STAGES;   // 1
+  uint64_t* bar_p_full = bar_s_full + 1;         // 1
+  uint64_t* bar_pv_done = bar_p_full + 1;        // 1
+  uint64_t* bar_s_free = bar_pv_done + 1;        // 1
+  uint64_t* bar_o_ready = bar_s_free + 1;        // 1   normalised O tile of the finished item is staged in its Q buffer
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bar_o_ready + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.S;
+  const int H = p.H;
+
+  auto item_q0 = [&](int it) { return (it % nqt) * BQ; };
+  auto item_h = [&](int it) { return (it / nqt) % H; };
+  auto item_b = [&](int it) { return it / (nqt * H); };
+  auto item_nkv = [&](int it) {
+    int kv_len = S;
+    if (p.causal) {
+      const int qend = item_q0(it) + BQ;
+      kv_len = qend < S ? qend : S;
+    }
+    return (kv_len + BKV - 1) / BKV;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q_full[i], 1);
+      mbar_init(&bar_q_empty[i], 1);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&bar_k_full[i], 1);
+      mbar_init(&bar_v_full[i], 1);
+      mbar_init(&bar_k_empty[i], 1);
+      mbar_init(&bar_v_empty[i], 1);
+    }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_p_full, C::kSoftmaxWarps * 32);
+    mbar_init(bar_pv_done, 1);
+    mbar_init(bar_s_free, C::kSoftmaxWarps * 32);
+    mbar_init(bar_o_ready, C::kSoftmaxWarps * 32);
+    fence_barrier_init();
+  }
+  if (warp == C::kSoftmaxWarps + 1) {
+    tmem_alloc(tmem_base_smem, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp >= C::kSoftmaxWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsUtility));
+    // Utility warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers) and only the TMA / tcgen05
+    // instructions themselves sit under elect_one(): under a divergent `lane == 0` branch ptxas wraps every UTCHMMA /
+    // UTCBAR / UTMALDG in an ELECT + BRA.U.ANY loop (~7 extra instructions each), which made the single issuing
+    // thread -- not the softmax -- the critical path of the tile loop (clock64 timeline: ~2200 clocks per tile).
+    // The QK and the PV MMAs are issued by two different warps, so each pays only two barrier waits per tile.
+    auto pin = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+    const uint32_t bar0 = pin(smem_u32(bars));
+    const uint32_t a_q_full = bar0, a_q_empty = bar0 + 16, a_k_full = bar0 + 32, a_v_full = a_k_full + 8 * STAGES,
+                   a_k_empty = a_v_full + 8 * STAGES, a_v_empty = a_k_empty + 8 * STAGES, a_s_full = a_v_empty + 8 * STAGES,
+                   a_p_full = a_s_full + 8, a_pv_done = a_s_full + 16, a_s_free = a_s_full + 24;
+    const uint32_t q_sm = pin(smem_u32(q_smem)), k_sm = q_sm + 2 * C::kTileBytes, v_sm = k_sm + STAGES * C::kTileBytes;
+    if (warp == C::kSoftmaxWarps) {
+      // ============================== TMA producer ==============================
+      if (elect_one()) prefetch_tmap(&tmap);
+      int k_item = blockIdx.x, k_j = 0, k_n = 0, k_g = 0;          // item, tile in item, local item index, global tile
+      int k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+      auto advance_k = [&]() {
+        if (k_item >= n_items) return;
+        if (k_j == 0) {
+          const int qb = k_n & 1;
+          mbar_wait_a(a_q_empty + 8 * qb, ((k_n >> 1) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(a_q_full + 8 * qb, C::kTileBytes);
+            tma_load_4d_a(q_sm + qb * C::kTileBytes, &tmap, a_q_full + 8 * qb, 0, 0 * H + item_h(k_item), item_q0(k_item),
+                          item_b(k_item));
+          }
+        }
+        const int st = k_g % STAGES;
+        mbar_wait_a(a_k_empty + 8 * st, ((k_g / STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(a_k_full + 8 * st, C::kTileBytes);
+          tma_load_4d_a(k_sm + st * C::kTileBytes, &tmap, a_k_full + 8 * st, 0, 1 * H + item_h(k_item), k_j * BKV,
+                        item_b(k_item));
+        }
+        ++k_g;
+        if (++k_j == k_nkv) {
+          k_j = 0;
+          ++k_n;
+          k_item += gridDim.x;
+          k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+        }
+      };
+      for (int i = 0; i < STAGES; ++i) advance_k();
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          mbar_wait_a(a_v_empty + 8 * st, ((g / STAGES) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(a_v_full + 8 * st, C::kTileBytes);
+            tma_load_4d_a(v_sm + st * C::kTileBytes, &tmap, a_v_full + 8 * st, 0, 2 * H + h, j * BKV, b);
+          }
+          advance_k();
+        }
+      }
+    } else if (warp == C::kSoftmaxWarps + 1) {
+      // ============================== QK issuer: S(g) = Q K_g^T ==============================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
+      const uint64_t q_d0 = make_smem_desc_sw128(q_sm, 16, 1024);
+      const uint64_t k_d0 = make_smem_desc_sw128(k_sm, 16, 1024);
+      const uint32_t s_tmem = tmem_base;
+      const bool tracer = TRACE && blockIdx.x < 4 && lane == 0;
+      long long* tr = TRACE ? p.trace + ((int64_t)blockIdx.x * 2 + 1) * 128 * 8 : nullptr;
+      int g = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int nkv = item_nkv(item);
+        const int qb = n & 1;
+        const uint64_t q_d = q_d0 + (uint64_t)(qb * (C::kTileBytes >> 4));
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          if (tracer && g < 128) tr[g * 8 + 0] = clock64();
+          if (g > 0) mbar_wait_a(a_s_free, (g - 1) & 1);          // S(g-1) is in the softmax warps' registers
+          if (j == 0) mbar_wait_a(a_q_full + 8 * qb, (n >> 1) & 1);
+          mbar_wait_a(a_k_full + 8 * st, (g / STAGES) & 1);
+          tc_fence_after();
+          if (tracer && g < 128) tr[g * 8 + 1] = clock64();
+          if (elect_one()) {
+            const uint64_t k_d = k_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+            mma_ss_c<false>(s_tmem, q_d, k_d, idesc_qk);
+            mma_ss_c<true>(s_tmem, q_d + 2, k_d + 2, idesc_qk);
+            mma_ss_c<true>(s_tmem, q_d + 4, k_d + 4, idesc_qk);
+            mma_ss_c<true>(s_tmem, q_d + 6, k_d + 6, idesc_qk);
+            mma_commit_a(a_s_full);
+            mma_commit_a(a_k_empty + 8 * st);
+            // last QK of the item read the Q tile; with the TMA-store epilogue the Q buffer doubles as the O staging
+            // tile and is released by the store warp instead
+            if (j == nkv - 1 && !tma_out) mma_commit_a(a_q_empty + 8 * qb);
+          }
+          __syncwarp();
+          if (tracer && g < 128) tr[g * 8 + 2] = clock64();
+        }
+      }
+    } else if (warp == C::kSoftmaxWarps + 2) {
+      // ============================== PV issuer: O += P_g V_g (P read from TMEM) ==============================
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+      const uint64_t v_d0 = make_smem_desc_sw128(v_sm, BKV * 128, 1024);
+      const uint32_t p_tmem = tmem_base + 128, o_tmem = tmem_base + 192;
+      const bool tracer = TRACE && blockIdx.x < 4 && lane == 0;
+      long long* tr = TRACE ? p.trace + ((int64_t)blockIdx.x * 2 + 1) * 128 * 8 : nullptr;
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nkv = item_nkv(item);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          if (tracer && g < 128) tr[g * 8 + 4] = clock64();
+          mbar_wait_a(a_p_full, g & 1);
+          if (tracer && g < 128) tr[g * 8 + 5] = clock64();
+          mbar_wait_a(a_v_full + 8 * st, (g / STAGES) & 1);
+          tc_fence_after();
+          if (tracer && g < 128) tr[g * 8 + 6] = clock64();
+          if (elect_one()) {
+            const uint64_t v_d = v_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+            if (j > 0) mma_ts_c<true>(o_tmem, p_tmem, v_d, idesc_pv);
+            else mma_ts_c<false>(o_tmem, p_tmem, v_d, idesc_pv);
+#pragma unroll
+            for (int k = 1; k < BKV / 16; ++k) mma_ts_c<true>(o_tmem, p_tmem + k * 8, v_d + (uint64_t)(k * 128), idesc_pv);
+            mma_commit_a(a_pv_done);
+            mma_commit_a(a_v_empty + 8 * st);
+          }
+          __syncwarp();
+          if (tracer && g < 128) tr[g * 8 + 7] = clock64();
+        }
+      }
+    } else if (tma_out) {
+      // ============================== O store: staged tile (Q buffer of the finished item) -> global by TMA ==============
+      const uint32_t a_o_ready = a_s_free + 8;
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int qb = n & 1;
+        mbar_wait_a(a_o_ready, n & 1);
+        if (elect_one()) {
+          const int q0 = item_q0(item), h = item_h(item), b = item_b(item);
+          if (p.out2 == nullptr || q0 < p.S_split) tma_store_4d_a(&tmap_o, q_sm + qb * C::kTileBytes, 0, h, q0, b);
+          else tma_store_4d_a(&tmap_o2, q_sm + qb * C::kTileBytes, 0, h, q0 - p.S_split, b);
+          tma_store_commit();
+          tma_store_wait_read();                      // the staged tile has been read: the Q buffer may be reloaded
+          mbar_arrive_a(a_q_empty + 8 * qb);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== softmax / epilogue (8 warps, quad layout) ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsSoftmax));
+    const int lane0 = (warp & 3) * 32 + (warp >> 2) * 16;     // first TMEM lane (= tile row) of this warp's 16 rows
+    const int row0 = lane0 + (lane >> 2);                      // this thread: rows row0 and row0 + 8
+    const int cq = lane & 3;                                   // columns 8k + 2 cq + {0, 1}
+    // pin(): an opaque move, so that ptxas keeps the value in a register instead of re-deriving it (shared-window
+    // conversion, thread-id arithmetic: ~10 instructions each) at every use inside the tile loop
+    auto pin = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+    const uint32_t s_tmem = pin(tmem_base + (static_cast<uint32_t>(lane0) << 16));
+    const uint32_t p_tmem = s_tmem + 128;
+    const uint32_t o_tmem = s_tmem + 192;
+    const uint32_t bar0 = pin(smem_u32(bars));                 // 32-bit shared addresses of the barriers, computed once
+    const uint32_t a_s_full = bar0 + 8 * (4 + 4 * STAGES), a_p_full = a_s_full + 8, a_pv_done = a_s_full + 16,
+                   a_s_free = a_s_full + 24;
+    const float sl2 = p.scale_log2;
+    const float2 sc2 = make_float2(sl2, sl2);
+    constexpr float kNegBig = -1.0e30f;                        // finite "-inf" for the running max: no special cases
+    const bool tracer = TRACE && blockIdx.x < 4 && threadIdx.x == 0;
+    long long* tr = TRACE ? p.trace + (int64_t)blockIdx.x * 2 * 128 * 8 : nullptr;
+    const uint32_t a_o_ready = a_s_free + 8;
+    const uint32_t q_sm = pin(smem_u32(q_smem));
+    // Epilogue of a finished item: O / l -> bf16.  TMA mode: the tile is staged (128B-swizzled, conflict-free 4-byte
+    // stores) in the item's Q buffer and written out by the store warp; otherwise token-major 4-byte global stores.
+    auto finish_item = [&](int item, int n, const float2 (&l2)[2], const float (&m)[2]) {
+      const int h = item_h(item), b = item_b(item);
+      const int q_idx0 = item_q0(item) + row0;
+      float inv_l[2], lse2[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float l = l2[r].x + l2[r].y;
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        inv_l[r] = l > 0.f ? __frcp_rn(l) : 0.f;
+        lse2[r] = (m[r] + __log2f(l)) * 0.6931471805599453f;
+      }
+      const uint32_t stage = q_sm + (n & 1) * C::kTileBytes;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[16];                                        // o[4k + 2r + c] = O[row0 + 8r][32 hh + 8k + 2cq + c]
+        tmem_ld_16x256b_x4(o_tmem + 32 * hh, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = row0 + 8 * r;
+          if (tma_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sts_u32(stage + row * 128 + (((4 * hh + k) ^ (row & 7)) << 4) + 4 * cq,
+                      pack_bf16(__uint_as_float(o[4 * k + 2 * r]) * inv_l[r], __uint_as_float(o[4 * k + 2 * r + 1]) * inv_l[r]));
+          } else {
+            const int q_idx = q_idx0 + 8 * r;
+            if (q_idx < S) {
+              __nv_bfloat16* orow;
+              if (p.out2 == nullptr) orow = p.out + (((int64_t)b * S + q_idx) * H + h) * D;
+              else if (q_idx < p.S_split) orow = p.out + (((int64_t)b * p.S_split + q_idx) * H + h) * D;
+              else orow = p.out2 + (((int64_t)b * (S - p.S_split) + (q_idx - p.S_split)) * H + h) * D;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint32_t*>(orow + 32 * hh + 8 * k + 2 * cq) =
+                    pack_bf16(__uint_as_float(o[4 * k + 2 * r]) * inv_l[r], __uint_as_float(o[4 * k + 2 * r + 1]) * inv_l[r]);
+            }
+          }
+        }
+      }
+      tc_fence_before();      // O is in registers: orders the TMEM reads before the next PV(0) (issued after p_full)
+      if (tma_out) {
+        fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA store
+        mbar_arrive_a(a_o_ready);
+      }
+      if (p.lse && cq == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          if (q_idx0 + 8 * r < S) p.lse[((int64_t)b * H + h) * S + q_idx0 + 8 * r] = lse2[r];
+      }
+    };
+    int g = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const int nkv = item_nkv(item);
+      const int q_idx0 = item_q0(item) + row0;                 // second row: q_idx0 + 8
+      float m[2] = {kNegBig, kNegBig};                         // running max (scaled, log2 domain)
+      float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // running denominators (this thread's columns)
+      for (int j = 0; j < nkv; ++j, ++g) {
+        if (tracer && g < 128) tr[g * 8 + 0] = clock64();
+        mbar_wait_a(a_s_full, g & 1);
+        tc_fence_after();
+        if (tracer && g < 128) tr[g * 8 + 1] = clock64();
+        uint32_t sa[32], sb[32];                               // s?[4k + 2r + c] = S[row0 + 8r][(64 if B) + 8k + 2cq + c]
+        tmem_ld_16x256b_x8(s_tmem, sa);
+        tmem_ld_16x256b_x8(s_tmem + 64, sb);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_a(a_s_free);
+        if (tracer && g < 128) tr[g * 8 + 2] = clock64();
+        const int kv0 = j * BKV;
+        int lim0 = S - kv0, lim1 = S - kv0;
+        if (p.causal) {
+          const int c0 = q_idx0 - kv0 + 1, c1 = c0 + 8;
+          lim0 = c0 < lim0 ? c0 : lim0;
+          lim1 = c1 < lim1 ? c1 : lim1;
+        }
+        if (lim0 < BKV || lim1 < BKV) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int col = 8 * k + 2 * cq + c;
+              if (col >= lim0) sa[4 * k + c] = 0xff800000u;          // -inf
+              if (col >= lim1) sa[4 * k + 2 + c] = 0xff800000u;
+              if (col + 64 >= lim0) sb[4 * k + c] = 0xff800000u;
+              if (col + 64 >= lim1) sb[4 * k + 2 + c] = 0xff800000u;
+            }
+        }
+        float alpha[2];
+        float2 nm2[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float mx0 = kNegBig, mx1 = kNegBig;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[4 * k + 2 * r]), __uint_as_float(sa[4 * k + 2 * r + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sb[4 * k + 2 * r]), __uint_as_float(sb[4 * k + 2 * r + 1])));
+          }
+          float mx = fmaxf(mx0, mx1);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float mn = fmaxf(m[r], mx * sl2);
+          if (mn - m[r] <= kRescaleThreshold) mn = m[r];       // lazy rescale (never taken on the first tile: m = -1e30)
+          alpha[r] = ex2(m[r] - mn);                           // 1 when the max is kept, 0 on the first tile
+          nm2[r] = make_float2(-mn, -mn);
+          m[r] = mn;
+        }
+        if (tracer && g < 128) tr[g * 8 + 3] = clock64();
+        // ---- p = exp2(s * scale - m), bf16 pairs; does not depend on PV(g-1) ----
+        uint32_t pk[32];                                       // pk[2k + r] = P[row0 + 8r][cols 8k + 2cq, +1], k < 16
+        float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const uint32_t(&sv)[32] = hb ? sb : sa;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[4 * k + 2 * r]), __uint_as_float(sv[4 * k + 2 * r + 1])),
+                                          sc2, nm2[r]);
+              float2 e;
+              if ((2 * k + r) % 4 < EMU) {
+                e = ex2_poly2(x);
+              } else {
+                e.x = ex2(x.x);
+                e.y = ex2(x.y);
+              }
+              sum2[r] = __fadd2_rn(sum2[r], e);
+              pk[16 * hb + 2 * k + r] = pack_bf16(e.x, e.y);
+            }
+        }
+        if (tracer && g < 128) tr[g * 8 + 4] = clock64();
+        // PV(g-1) reads P(g-1) from the columns P(g) overwrites; O may only be rescaled between PV(g-1) and PV(g).
+        // For the first tile of an item the epilogue of the previous item already consumed that phase.
+        if (j > 0) {
+          mbar_wait_a(a_pv_done, (g - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[16];                                  // o[4k + 2r + c] = O[row0 + 8r][32 hh + 8k + 2cq + c]
+              tmem_ld_16x256b_x4(o_tmem + 32 * hh, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha[(i >> 1) & 1]);
+              tmem_st_16x256b_x4(o_tmem + 32 * hh, o);
+            }
+          }
+        }
+        if (tracer && g < 128) tr[g * 8 + 5] = clock64();
+        tmem_st_16x128b_x16(p_tmem, pk);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l2[r] = __ffma2_rn(l2[r], make_float2(alpha[r], alpha[r]), sum2[r]);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_a(a_p_full);
+        if (tracer && g < 128) tr[g * 8 + 6] = clock64();
+      }
+      // ---- epilogue (the QK warp is already computing S of the next item).  Deferring it into the first tile of the
+      //      next item was measured slower: the extra live state costs more in the tile loop than the hidden wait ----
+      mbar_wait_a(a_pv_done, (g - 1) & 1);
+      tc_fence_after();
+      finish_item(item, n, l2, m);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::kSoftmaxWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+long long* g_attn_trace = nullptr;   // debug: set by advgrpo_debug_set_attn_trace; consumed by dispatch variant 19
+
+template <int EMU, bool TRACE = false>
+int launch_quad(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
+                float scale, int causal, cudaStream_t st) {
+  using C = QCfg;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {64, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+  const uint64_t strides[4] = {0, 64 * 2, (uint64_t)(3 * H * 64) * 2, (uint64_t)(S * 3 * H * 64) * 2};
+  const uint32_t box[4] = {64, 1, BQ, 1};
+  int rc = make_tmap_bf16(&tmap, qkv, 4, dims, strides, box, true);
+  if (rc != ADVGRPO_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_quad_kernel<EMU, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  Params p;
+  p.out = (__nv_bfloat16*)out;
+  p.out2 = (__nv_bfloat16*)out2;
+  p.S_split = (int)S_split;
+  p.lse = lse;
+  p.S = (int)S;
+  p.H = (int)H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  p.park = 0;
+  p.bias = nullptr;
+  p.trace = TRACE ? g_attn_trace : nullptr;
+  ADVGRPO_CHECK_ARG(!TRACE || p.trace, "attn_fwd: trace variant needs advgrpo_debug_set_attn_trace");
+  const int nqt = (int)((S + BQ - 1) / BQ);
+  const int64_t items = (int64_t)nqt * H * B;
+  ADVGRPO_CHECK_ARG(items < (int64_t)1 << 30, "attn_fwd: too many work items");
+  int grid = sm_count() * 2;
+  if (grid > items) grid = (int)items;
+  // O goes out by TMA (tile staged in the finished item's Q buffer) unless the image / text split cuts a 128-row tile
+  static const int tma_env = getenv("ADVGRPO_ATTN_TMA_OUT") ? atoi(getenv("ADVGRPO_ATTN_TMA_OUT")) : 1;
+  const int tma_out = (tma_env && (out2 == nullptr || S_split % BQ == 0)) ? 1 : 0;
+  CUtensorMap tmap_o = tmap, tmap_o2 = tmap;
+  if (tma_out) {
+    const int64_t S1 = out2 ? S_split : S;
+    const uint64_t od[4] = {64, (uint64_t)H, (uint64_t)S1, (uint64_t)B};
+    const uint64_t os[4] = {0, 64 * 2, (uint64_t)(H * 64) * 2, (uint64_t)(S1 * H * 64) * 2};
+    rc = make_tmap_bf16(&tmap_o, out, 4, od, os, box, true);
+    if (rc != ADVGRPO_OK) return rc;
+    if (out2) {
+      const uint64_t od2[4] = {64, (uint64_t)H, (uint64_t)(S - S_split), (uint64_t)B};
+      const uint64_t os2[4] = {0, 64 * 2, (uint64_t)(H * 64) * 2, (uint64_t)((S - S_split) * H * 64) * 2};
+      rc = make_tmap_bf16(&tmap_o2, out2, 4, od2, os2, box, true);
+      if (rc != ADVGRPO_OK) return rc;
+    }
+  }
+  ADVGRPO_CUDA_CALL(launch_chain(attn_fwd_quad_kernel<EMU, TRACE>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmap,
+                                 tmap_o, tmap_o2, p, (int)items, nqt, tma_out));
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
 template <int D, int EMU>
 int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
                    float scale, int causal, cudaStream_t st, const float* bias = nullptr) {
@@ -764,6 +1260,7 @@ int launch_persist(const void* qkv, void* out, void* out2, int64_t S_split, floa
   p.causal = causal;
   p.park = 0;
   p.bias = bias;
+  p.trace = nullptr;
   const int nqt = (int)((S + BQ - 1) / BQ);
   const int64_t items = (int64_t)nqt * H * B;
   ADVGRPO_CHECK_ARG(items < (int64_t)1 << 30, "attn_fwd: too many work items");
@@ -802,6 +1299,7 @@ int launch(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, 
   p.causal = causal;
   p.park = park;
   p.bias = nullptr;
+  p.trace = nullptr;
   dim3 grid((unsigned)((S + BQ * NQ - 1) / (BQ * NQ)), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<D, NQ, EMU, RS><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmap, p);
   ADVGRPO_CUDA_LAUNCH_CHECK();
@@ -832,7 +1330,12 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 13: return launch<64, 1, 1>(ADVGRPO_ATTN_ARGS, 3);
       case 14: return launch_persist<64, 0>(ADVGRPO_ATTN_ARGS);
       case 15: return launch_persist<64, 2>(ADVGRPO_ATTN_ARGS);
-      default: return launch_persist<64, 1>(ADVGRPO_ATTN_ARGS);   // fastest measured (profiles/)
+      case 16: return launch_quad<0>(ADVGRPO_ATTN_ARGS);      // 8 softmax warps per query tile (quad layout)
+      case 17: return launch_quad<1>(ADVGRPO_ATTN_ARGS);
+      case 18: return launch_quad<2>(ADVGRPO_ATTN_ARGS);
+      case 19: return launch_quad<1, true>(ADVGRPO_ATTN_ARGS);   // timeline trace (debug)
+      case 20: return launch_persist<64, 1>(ADVGRPO_ATTN_ARGS);   // round-1 default (thread-per-row persistent kernel)
+      default: return launch_quad<1>(ADVGRPO_ATTN_ARGS);          // fastest measured (profiles/r2_*)
     }
   }
   if (D == 128) return variant == 1 ? launch<128, 1, 0>(ADVGRPO_ATTN_ARGS) : launch_persist<128, 0>(ADVGRPO_ATTN_ARGS);
@@ -865,6 +1368,9 @@ int advgrpo_attn_fwd_bias(const void* qkv, const float* bias, void* out, float* 
   ADVGRPO_CHECK_ARG(aligned16(qkv) && aligned16(out), "attn_fwd_bias: tensors must be 16-byte aligned");
   return launch_persist<64, 1>(qkv, out, nullptr, 0, lse, B, S, H, scale, 0, (cudaStream_t)stream, bias);
 }
+
+// Debug: device buffer of 4 * 2 * 128 * 8 int64 clock stamps filled by dispatch variant 19.
+void advgrpo_debug_set_attn_trace(void* buf) { g_attn_trace = (long long*)buf; }
 
 // Test/bench hook (not part of the reference-facing surface): pick the CTA shape explicitly.
 int advgrpo_attn_fwd_variant(const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,

@@ -176,10 +176,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   pdl_wait();      // no global-memory access before the previous kernel's results are visible
 
   if (warp == 8) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      prefetch_tmap(&tm_a);
-      prefetch_tmap(&tm_w);
+    // ============================== TMA producer (warp-uniform loop, elect_one() around the TMA issue) ============
+    {
+      if (elect_one()) {
+        prefetch_tmap(&tm_a);
+        prefetch_tmap(&tm_w);
+      }
       int it = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const bool second = tile >= p.tiles0;
@@ -194,31 +196,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int st = it % G::kStages;
           mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
-          uint8_t* sa = smem + st * G::kStageBytes;
-          uint8_t* sw = sa + G::kABytes;
-          const CUtensorMap* ma = kb < p.kb1 ? (second ? &tn_a : &tm_a) : (second ? &tn_a2 : &tm_a2);
-          const CUtensorMap* mw = kb < p.kb1 ? (second ? &tn_w : &tm_w) : (second ? &tn_w2 : &tm_w2);
-          const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BK;
-          if constexpr (TWO) {
-            // both CTAs' bytes land on the LEADER's full barrier (one expect_tx of the pair's total)
-            const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
-            if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
-            if (per_sample) tma_load_3d_2sm(sa, ma, full_leader, kc, m0, sb);
-            else tma_load_2d_2sm(sa, ma, full_leader, kc, m0);
-            tma_load_2d_2sm(sw, mw, full_leader, kc, n0);
-          } else {
-            mbar_expect_tx(&bar_full[st], G::kStageBytes);
-            if (per_sample) tma_load_3d(sa, ma, &bar_full[st], kc, m0, sb);
-            else tma_load_2d(sa, ma, &bar_full[st], kc, m0);
-            tma_load_2d(sw, mw, &bar_full[st], kc, n0);
+          if (elect_one()) {
+            uint8_t* sa = smem + st * G::kStageBytes;
+            uint8_t* sw = sa + G::kABytes;
+            const CUtensorMap* ma = kb < p.kb1 ? (second ? &tn_a : &tm_a) : (second ? &tn_a2 : &tm_a2);
+            const CUtensorMap* mw = kb < p.kb1 ? (second ? &tn_w : &tm_w) : (second ? &tn_w2 : &tm_w2);
+            const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BK;
+            if constexpr (TWO) {
+              // both CTAs' bytes land on the LEADER's full barrier (one expect_tx of the pair's total)
+              const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
+              if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
+              if (per_sample) tma_load_3d_2sm(sa, ma, full_leader, kc, m0, sb);
+              else tma_load_2d_2sm(sa, ma, full_leader, kc, m0);
+              tma_load_2d_2sm(sw, mw, full_leader, kc, n0);
+            } else {
+              mbar_expect_tx(&bar_full[st], G::kStageBytes);
+              if (per_sample) tma_load_3d(sa, ma, &bar_full[st], kc, m0, sb);
+              else tma_load_2d(sa, ma, &bar_full[st], kc, m0);
+              tma_load_2d(sw, mw, &bar_full[st], kc, n0);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 9) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && rank == 0) {
+    // The warp runs the loop uniformly (all lanes wait on the barriers) and only the tcgen05 instructions sit under
+    // elect_one(): under a divergent `lane == 0` branch ptxas wraps every UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY
+    // loop (~7 extra instructions each; found with the clock64 timeline of the attention kernel, round 2).
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+      const uint32_t smem_base = smem_u32(smem);
       int it = 0, local = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
         const int acc = local & 1;
@@ -229,20 +238,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           const int st = it % G::kStages;
           mbar_wait(&bar_full[st], (it / G::kStages) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * G::kStageBytes);
-          const uint32_t sb = sa + G::kABytes;
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc_sw128(smem_base + st * G::kStageBytes, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(smem_base + st * G::kStageBytes + G::kABytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (TWO)
-              mma_ss_2cta(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
-                          make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              mma_ss(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
-                     make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // + k * 32 bytes inside the 128-byte swizzle row = + 2 in the descriptor's 16-byte address units
+              if constexpr (TWO) mma_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else mma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
+            if (kb == kb_total - 1) {
+              if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
+            }
           }
-          if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
+          __syncwarp();
         }
-        if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
       }
     }
   } else {

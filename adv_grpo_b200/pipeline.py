@@ -11,8 +11,10 @@ from .vae import AutoencoderKL, VaeImageProcessor
 
 
 class GraphedForward:
-    """Replays one captured MMDiT forward per input-shape key (no_grad rollout only).  The LoRA operand
-    buffers are updated in place by the model, so a graph stays valid across optimizer steps."""
+    """Replays one captured MMDiT forward per input-shape key (no_grad rollout only).  The captured kernels read the
+    model's persistent bf16 LoRA operand buffers; those are refreshed IN PLACE (eagerly, before the replay) whenever
+    `invalidate_lora_cache()` marked them dirty (optimizer step, EMA swap, `load_adapter`), so a graph stays valid
+    across parameter updates and never replays stale weights."""
 
     def __init__(self, model, warmup=2):
         self.model, self.warmup, self.graphs = model, warmup, {}
@@ -36,6 +38,8 @@ class GraphedForward:
             ent = (g, static_in, out, _lib.launch_count() - n0)
             self.graphs[key] = ent
         g, static_in, out, n_kernels = ent
+        with torch.no_grad():
+            self.model._pack_lora()          # no-op unless dirty; the repack writes into the buffers the graph reads
         static_in[0].copy_(hidden_states)
         static_in[1].copy_(timestep)
         static_in[2].copy_(encoder_hidden_states)

@@ -188,6 +188,69 @@ def probe_perf():
             print(f"gemm {M}x{N}x{K} {name}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def probe_attn_split():
+    """Default D=64 path with the image / text output split (TMA-store epilogue) against the unsplit output."""
+    import torch
+    from adv_grpo_b200 import ops
+    for (B, S, H, split) in ((2, 1229, 3, 1024), (1, 461, 2, 256), (2, 1229, 2, 1000), (1, 4301, 2, 4096)):
+        qkv = torch.randn(B, S, 3, H, 64, device="cuda").bfloat16()
+        ref, lse_ref = ops.attention_fwd(qkv, variant=3)
+        (o1, o2), lse = ops.attention_fwd(qkv, split=split)
+        full, _ = ops.attention_fwd(qkv)
+        torch.cuda.synchronize()
+        got = torch.cat([o1, o2], 1)
+        e1 = (got.float() - ref.float()).abs().max().item()
+        e2 = (full.float() - ref.float()).abs().max().item()
+        print(f"split B={B} S={S} H={H} split={split}: |split - v3| {e1:.3e}  |default - v3| {e2:.3e}  lse {(lse - lse_ref).abs().max().item():.3e}", flush=True)
+
+
+def probe_attn_quad():
+    """Correctness of the 8-softmax-warp (quad TMEM layout) forward, variants 16-18."""
+    for v in (16, 17, 18):
+        for S in (128, 77, 461, 1229, 1370):
+            _attn(v, S=S)
+        _attn(v, S=300, causal=True)
+        _attn(v, S=1024, causal=True)
+
+
+def _time_attn(B, S, H, D, variant, iters=10):
+    import torch
+    from adv_grpo_b200 import ops
+    qkv = torch.randn(B, S, 3, H, D, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.attention_fwd(qkv, variant=variant, want_lse=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.attention_fwd(qkv, variant=variant, want_lse=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return ms, 4 * B * H * S * S * D / ms / 1e9
+
+
+def probe_perf_attn():
+    import torch
+    for (B, S, H) in ((16, 1229, 24), (16, 1024, 24), (4, 4301, 24), (32, 1370, 12)):
+        for variant in (3, 0, 16, 17, 18):
+            ms, tf = _time_attn(B, S, H, 64, variant)
+            print(f"attn fwd B={B} S={S} H={H} variant {variant}: {ms:.3f} ms  {tf:.1f} TFLOP/s", flush=True)
+        qkv = torch.randn(B, S, 3, H, 64, device="cuda").bfloat16()
+        q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        for _ in range(3):
+            torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"torch SDPA B={B} S={S} H={H} (library baseline): {ms:.3f} ms  {4 * B * H * S * S * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 PROBES = {k[6:]: v for k, v in globals().items() if k.startswith("probe_")}
 
 if __name__ == "__main__":

@@ -78,7 +78,7 @@ def _ref_attention(qkv, scale, causal):
     return o.permute(0, 2, 1, 3), torch.logsumexp(s, dim=-1)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 16, 17, 18])
 @pytest.mark.parametrize("B,S,H", [(1, 128, 1), (2, 461, 4), (1, 1024, 2), (2, 1229, 3), (1, 1370, 2), (1, 77, 2),
                                    (1, 4301, 1)])
 def test_attention_fwd_d64(ops, variant, B, S, H):
