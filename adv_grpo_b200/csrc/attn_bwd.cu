@@ -125,62 +125,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 12) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // (utility warps run their loops warp-uniformly; only the TMA / tcgen05 instructions sit under elect_one(): under
+    //  a divergent `lane == 0` branch ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop)
+    if (elect_one()) {
       prefetch_tmap(&tm_qkv);
       prefetch_tmap(&tm_do);
       mbar_expect_tx(bar_kv_full, 2 * kTile);
       tma_load_4d(smem + OFF_K, &tm_qkv, bar_kv_full, 0, 1 * p.H + h, kv0, b);
       tma_load_4d(smem + OFF_V, &tm_qkv, bar_kv_full, 0, 2 * p.H + h, kv0, b);
-      for (int it = 0; it < nq; ++it) {
-        const int i = i_begin + it;
-        const int st = it % QSTAGES;
-        mbar_wait(&bar_q_empty[st], ((it / QSTAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < nq; ++it) {
+      const int i = i_begin + it;
+      const int st = it % QSTAGES;
+      mbar_wait(&bar_q_empty[st], ((it / QSTAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bar_q_full[st], 2 * kTile + kStatBytes);
         tma_load_4d(smem + OFF_Q + st * kTile, &tm_qkv, &bar_q_full[st], 0, 0 * p.H + h, i * T, b);
         tma_load_4d(smem + OFF_DO + st * kTile, &tm_do, &bar_q_full[st], 0, h, i * T, b);
         bulk_load_1d(smem + OFF_STAT + st * kStatBytes, p.lse2 + stat_row + i * T, T * 4, &bar_q_full[st]);
         bulk_load_1d(smem + OFF_STAT + st * kStatBytes + T * 4, p.delta + stat_row + i * T, T * 4, &bar_q_full[st]);
       }
+      __syncwarp();
     }
   } else if (warp == 13) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(T, T, 0, 0);     // A K-major, B K-major, N = 128
       constexpr uint32_t idesc_kn = make_idesc_bf16(T, D, 0, 1);    // A K-major (smem or TMEM), B MN-major
       constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
       const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
+      const uint32_t q_s0 = smem_u32(smem + OFF_Q), do_s0 = smem_u32(smem + OFF_DO), ds_s0 = smem_u32(smem + OFF_DS);
+      // descriptors built once; per MMA only the 16-byte-unit start address is advanced (2048 B -> 128, 32 B -> 2)
+      const uint64_t k_kmaj = make_smem_desc_sw128(k_s, 16, 1024), v_kmaj = make_smem_desc_sw128(v_s, 16, 1024);
+      const uint64_t k_mn = make_smem_desc_sw128(k_s, 16384, 1024);
       auto back_half = [&](int it) {
         const int st = it % QSTAGES, bb = it & 1;
-        const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
-        const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
-        const uint32_t ds_s = smem_u32(smem + OFF_DS + bb * kDsBytes);
+        const uint64_t q_mn = make_smem_desc_sw128(q_s0 + st * kTile, 16384, 1024);
+        const uint64_t do_mn = make_smem_desc_sw128(do_s0 + st * kTile, 16384, 1024);
+        const uint64_t ds_k = make_smem_desc_sw128(ds_s0 + bb * kDsBytes, 16, 1024);
+        const uint64_t ds_mn = make_smem_desc_sw128(ds_s0 + bb * kDsBytes, 16384, 1024);
         // dV += P^T dO
         mbar_wait(bar_p_full, it & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < T / 16; ++k)
-          mma_ts(tmem_base + COL_DV, tmem_base + COL_P + k * 8,
-                 make_smem_desc_sw128(do_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-        mma_commit(bar_pv_done);
+          for (int k = 0; k < T / 16; ++k)
+            mma_ts(tmem_base + COL_DV, tmem_base + COL_P + k * 8, do_mn + (uint64_t)(k * 128), idesc_kn,
+                   (it > 0 || k > 0) ? 1u : 0u);
+          mma_commit(bar_pv_done);
+        }
+        __syncwarp();
         // dK += dS^T Q
         mbar_wait(&bar_ds_full[bb], (it >> 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < T / 16; ++k)
-          mma_ss(tmem_base + COL_DK, make_smem_desc_sw128(ds_s + (k / 4) * 16384 + (k % 4) * 32, 16, 1024),
-                 make_smem_desc_sw128(q_s + k * 2048, 16384, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < T / 16; ++k)
+            mma_ss(tmem_base + COL_DK, ds_k + (uint64_t)((k / 4) * 1024 + (k % 4) * 2), q_mn + (uint64_t)(k * 128), idesc_kn,
+                   (it > 0 || k > 0) ? 1u : 0u);
+        }
+        __syncwarp();
         // dQ = dS K   (fresh accumulator every query tile)
         if (it > 0) {
           mbar_wait(bar_dq_free, (it - 1) & 1);
           tc_fence_after();
         }
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < T / 16; ++k)
-          mma_ss(tmem_base + COL_DQ, make_smem_desc_sw128(ds_s + k * 2048, 16384, 1024),
-                 make_smem_desc_sw128(k_s + k * 2048, 16384, 1024), idesc_mn, k > 0 ? 1u : 0u);
-        mma_commit(&bar_ds_empty[bb]);
-        mma_commit(bar_dq_full);
-        mma_commit(&bar_q_empty[st]);
+          for (int k = 0; k < T / 16; ++k)
+            mma_ss(tmem_base + COL_DQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mn, k > 0 ? 1u : 0u);
+          mma_commit(&bar_ds_empty[bb]);
+          mma_commit(bar_dq_full);
+          mma_commit(&bar_q_empty[st]);
+        }
+        __syncwarp();
       };
       mbar_wait(bar_kv_full, 0);
       for (int it = 0; it < nq; ++it) {
@@ -188,21 +207,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);
         if (it > 0) mbar_wait(bar_s_free, (it - 1) & 1);
         tc_fence_after();
-        const uint32_t q_s = smem_u32(smem + OFF_Q + st * kTile);
-        const uint32_t do_s = smem_u32(smem + OFF_DO + st * kTile);
+        if (elect_one()) {
+          const uint64_t q_k = make_smem_desc_sw128(q_s0 + st * kTile, 16, 1024);
+          const uint64_t do_k = make_smem_desc_sw128(do_s0 + st * kTile, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_ss(tmem_base + COL_S, make_smem_desc_sw128(k_s + k * 32, 16, 1024),
-                 make_smem_desc_sw128(q_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tmem_base + COL_S, k_kmaj + (uint64_t)(k * 2), q_k + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_ss(tmem_base + COL_DP, make_smem_desc_sw128(v_s + k * 32, 16, 1024),
-                 make_smem_desc_sw128(do_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        mma_commit(bar_s_full);
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tmem_base + COL_DP, v_kmaj + (uint64_t)(k * 2), do_k + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+          mma_commit(bar_s_full);
+        }
+        __syncwarp();
         if (it > 0) back_half(it - 1);
       }
       if (nq > 0) back_half(nq - 1);
-      mma_commit(bar_dkv_full);
+      if (elect_one()) mma_commit(bar_dkv_full);
+      __syncwarp();
     }
   }
   } else if (warp < 8) {

@@ -486,112 +486,116 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const Params p
 
   if (warp >= 4) {
     if constexpr (C::kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+    // Utility warps run their loops warp-uniformly and only the TMA / tcgen05 instructions sit under elect_one() (a
+    // divergent `lane == 0` branch makes ptxas wrap each of them in an ELECT + BRA.U.ANY loop); QK and PV are issued
+    // by two different warps.  See attn_fwd_quad_kernel.
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t a_q_full = bar0, a_q_empty = bar0 + 16, a_k_full = bar0 + 32, a_v_full = a_k_full + 8 * STAGES,
+                   a_k_empty = a_v_full + 8 * STAGES, a_v_empty = a_k_empty + 8 * STAGES, a_s_full = a_v_empty + 8 * STAGES,
+                   a_p_full = a_s_full + 8, a_pv_done = a_s_full + 16, a_s_free = a_s_full + 24;
+    const uint32_t q_sm = smem_u32(q_smem), k_sm = q_sm + 2 * C::kTileBytes, v_sm = k_sm + STAGES * C::kTileBytes;
     if (warp == 4) {
       // ============================== TMA producer ==============================
-      if (lane == 0) {
-        prefetch_tmap(&tmap);
-        // K cursor (runs STAGES tiles ahead, loads the Q tile when it enters a new item) and V cursor
-        int k_item = blockIdx.x, k_j = 0, k_n = 0, k_g = 0;          // item, tile in item, local item index, global tile
-        int k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
-        auto advance_k = [&]() {
-          if (k_item >= n_items) return;
-          if (k_j == 0) {
-            const int qb = k_n & 1;
-            mbar_wait_parked(&bar_q_empty[qb], ((k_n >> 1) & 1) ^ 1);
-            mbar_expect_tx(&bar_q_full[qb], C::kTileBytes);
+      if (elect_one()) prefetch_tmap(&tmap);
+      // K cursor (runs STAGES tiles ahead, loads the Q tile when it enters a new item) and V cursor
+      int k_item = blockIdx.x, k_j = 0, k_n = 0, k_g = 0;          // item, tile in item, local item index, global tile
+      int k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+      auto advance_k = [&]() {
+        if (k_item >= n_items) return;
+        if (k_j == 0) {
+          const int qb = k_n & 1;
+          mbar_wait_a(a_q_empty + 8 * qb, ((k_n >> 1) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(a_q_full + 8 * qb, C::kTileBytes);
             for (int hf = 0; hf < C::kHalves; ++hf)
-              tma_load_4d(q_smem + qb * C::kTileBytes + hf * (BQ * 128), &tmap, &bar_q_full[qb], hf * 64,
-                          0 * H + item_h(k_item), item_q0(k_item), item_b(k_item));
+              tma_load_4d_a(q_sm + qb * C::kTileBytes + hf * (BQ * 128), &tmap, a_q_full + 8 * qb, hf * 64,
+                            0 * H + item_h(k_item), item_q0(k_item), item_b(k_item));
           }
-          const int st = k_g % STAGES;
-          mbar_wait_parked(&bar_k_empty[st], ((k_g / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&bar_k_full[st], C::kTileBytes);
+        }
+        const int st = k_g % STAGES;
+        mbar_wait_a(a_k_empty + 8 * st, ((k_g / STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(a_k_full + 8 * st, C::kTileBytes);
           for (int hf = 0; hf < C::kHalves; ++hf)
-            tma_load_4d(k_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_k_full[st], hf * 64,
-                        1 * H + item_h(k_item), k_j * BKV, item_b(k_item));
-          ++k_g;
-          if (++k_j == k_nkv) {
-            k_j = 0;
-            ++k_n;
-            k_item += gridDim.x;
-            k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
-          }
-        };
-        for (int i = 0; i < STAGES; ++i) advance_k();
-        int g = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-          const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
-          for (int j = 0; j < nkv; ++j, ++g) {
-            const int st = g % STAGES;
-            mbar_wait_parked(&bar_v_empty[st], ((g / STAGES) & 1) ^ 1);
-            mbar_expect_tx(&bar_v_full[st], C::kTileBytes);
+            tma_load_4d_a(k_sm + st * C::kTileBytes + hf * (BKV * 128), &tmap, a_k_full + 8 * st, hf * 64,
+                          1 * H + item_h(k_item), k_j * BKV, item_b(k_item));
+        }
+        ++k_g;
+        if (++k_j == k_nkv) {
+          k_j = 0;
+          ++k_n;
+          k_item += gridDim.x;
+          k_nkv = k_item < n_items ? item_nkv(k_item) : 0;
+        }
+      };
+      for (int i = 0; i < STAGES; ++i) advance_k();
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nkv = item_nkv(item), h = item_h(item), b = item_b(item);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          mbar_wait_a(a_v_empty + 8 * st, ((g / STAGES) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(a_v_full + 8 * st, C::kTileBytes);
             for (int hf = 0; hf < C::kHalves; ++hf)
-              tma_load_4d(v_smem + st * C::kTileBytes + hf * (BKV * 128), &tmap, &bar_v_full[st], hf * 64,
-                          2 * H + h, j * BKV, b);
-            advance_k();
+              tma_load_4d_a(v_sm + st * C::kTileBytes + hf * (BKV * 128), &tmap, a_v_full + 8 * st, hf * 64, 2 * H + h,
+                            j * BKV, b);
           }
+          advance_k();
         }
       }
     } else if (warp == 5) {
-      // ============================== MMA issuer ==============================
-      if (lane == 0) {
-        constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
-        constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
-        const uint64_t q_d0 = make_smem_desc_sw128(smem_u32(q_smem), 16, 1024);
-        const uint64_t k_d0 = make_smem_desc_sw128(smem_u32(k_smem), 16, 1024);
-        const uint64_t v_d0 = make_smem_desc_sw128(smem_u32(v_smem), BKV * 128, 1024);
-        const uint32_t s_tmem = tmem_base, p_tmem = tmem_base + 128, o_tmem = tmem_base + 192;
-        auto issue_qk = [&](int qb, int st) {
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint32_t off = ((k / 4) * (BQ * 128) + (k % 4) * 32) >> 4;
-            mma_ss(s_tmem, q_d0 + (uint64_t)(qb * (C::kTileBytes >> 4) + off),
-                   k_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + off), idesc_qk, k > 0);
-          }
-        };
-        auto issue_pv = [&](int st, bool acc) {
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            mma_ts(o_tmem, p_tmem + k * 8, v_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + k * 128), idesc_pv,
-                   (acc || k > 0) ? 1u : 0u);
-        };
-        // QK cursor: one tile ahead of the PV cursor
-        int q_item = blockIdx.x, q_j = 0, q_n = 0, q_g = 0;
-        int q_nkv = q_item < n_items ? item_nkv(q_item) : 0;
-        auto advance_qk = [&]() {
-          if (q_item >= n_items) return;
-          const int qb = q_n & 1;
-          if (q_g > 0) mbar_wait(bar_s_free, (q_g - 1) & 1);          // S(g-1) is in the softmax warps' registers
-          if (q_j == 0) mbar_wait(&bar_q_full[qb], (q_n >> 1) & 1);
-          const int st = q_g % STAGES;
-          mbar_wait(&bar_k_full[st], (q_g / STAGES) & 1);
+      // ============================== QK issuer: S(g) = Q K_g^T ==============================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
+      const uint64_t q_d0 = make_smem_desc_sw128(q_sm, 16, 1024);
+      const uint64_t k_d0 = make_smem_desc_sw128(k_sm, 16, 1024);
+      const uint32_t s_tmem = tmem_base;
+      int g = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int nkv = item_nkv(item);
+        const int qb = n & 1;
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          if (g > 0) mbar_wait_a(a_s_free, (g - 1) & 1);          // S(g-1) is in the softmax warps' registers
+          if (j == 0) mbar_wait_a(a_q_full + 8 * qb, (n >> 1) & 1);
+          mbar_wait_a(a_k_full + 8 * st, (g / STAGES) & 1);
           tc_fence_after();
-          issue_qk(qb, st);
-          mma_commit(bar_s_full);
-          mma_commit(&bar_k_empty[st]);
-          ++q_g;
-          if (++q_j == q_nkv) {
-            mma_commit(&bar_q_empty[qb]);                              // last QK of the item read the Q tile
-            q_j = 0;
-            ++q_n;
-            q_item += gridDim.x;
-            q_nkv = q_item < n_items ? item_nkv(q_item) : 0;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+              const uint32_t off = ((k / 4) * (BQ * 128) + (k % 4) * 32) >> 4;
+              mma_ss(s_tmem, q_d0 + (uint64_t)(qb * (C::kTileBytes >> 4) + off),
+                     k_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + off), idesc_qk, k > 0);
+            }
+            mma_commit_a(a_s_full);
+            mma_commit_a(a_k_empty + 8 * st);
+            if (j == nkv - 1) mma_commit_a(a_q_empty + 8 * qb);   // last QK of the item read the Q tile
           }
-        };
-        advance_qk();
-        int g = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-          const int nkv = item_nkv(item);
-          for (int j = 0; j < nkv; ++j, ++g) {
-            advance_qk();                                              // S(g+1), possibly of the next item
-            const int st = g % STAGES;
-            mbar_wait(bar_p_full, g & 1);
-            mbar_wait(&bar_v_full[st], (g / STAGES) & 1);
-            tc_fence_after();
-            issue_pv(st, j > 0);
-            mma_commit(bar_pv_done);
-            mma_commit(&bar_v_empty[st]);
+          __syncwarp();
+        }
+      }
+    } else if (warp == 6) {
+      // ============================== PV issuer: O += P_g V_g (P read from TMEM) ==============================
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+      const uint64_t v_d0 = make_smem_desc_sw128(v_sm, BKV * 128, 1024);
+      const uint32_t p_tmem = tmem_base + 128, o_tmem = tmem_base + 192;
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nkv = item_nkv(item);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % STAGES;
+          mbar_wait_a(a_p_full, g & 1);
+          mbar_wait_a(a_v_full + 8 * st, (g / STAGES) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              mma_ts(o_tmem, p_tmem + k * 8, v_d0 + (uint64_t)(st * (C::kTileBytes >> 4) + k * 128), idesc_pv,
+                     (j > 0 || k > 0) ? 1u : 0u);
+            mma_commit_a(a_pv_done);
+            mma_commit_a(a_v_empty + 8 * st);
           }
+          __syncwarp();
         }
       }
     }

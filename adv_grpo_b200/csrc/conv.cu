@@ -137,10 +137,12 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   };
 
   if (warp == 8) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      prefetch_tmap(&tm_x);
-      prefetch_tmap(&tm_w);
+    // ============================== TMA producer (warp-uniform loop; elect_one() around the TMA issue) ==========
+    {
+      if (elect_one()) {
+        prefetch_tmap(&tm_x);
+        prefetch_tmap(&tm_w);
+      }
       int it = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int n0, x0, y0, b;
@@ -150,26 +152,30 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           for (int cb = 0; cb < p.kb_per_tap; ++cb, ++it) {
             const int st = it % G::kStages;
             mbar_wait(&bar_empty[st], ((it / G::kStages) & 1) ^ 1);
-            uint8_t* sa = smem + st * G::kStageBytes;
-            // rows outside the image (negative or >= W / H coordinates) arrive as zeros: the conv's zero padding
-            if constexpr (TWO) {
-              const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
-              if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
-              tma_load_4d_2sm(sa, &tm_x, full_leader, cb * CBK, x0 + dx, y0 + dy, b);
-              tma_load_2d_2sm(sa + G::kABytes, &tm_w, full_leader, tap * p.Cin + cb * CBK, n0 + (int)rank * (BN / 2));
-            } else {
-              mbar_expect_tx(&bar_full[st], G::kStageBytes);
-              tma_load_4d(sa, &tm_x, &bar_full[st], cb * CBK, x0 + dx, y0 + dy, b);
-              tma_load_2d(sa + G::kABytes, &tm_w, &bar_full[st], tap * p.Cin + cb * CBK, n0);
+            if (elect_one()) {
+              uint8_t* sa = smem + st * G::kStageBytes;
+              // rows outside the image (negative or >= W / H coordinates) arrive as zeros: the conv's zero padding
+              if constexpr (TWO) {
+                const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[st]), 0);
+                if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * G::kStageBytes);
+                tma_load_4d_2sm(sa, &tm_x, full_leader, cb * CBK, x0 + dx, y0 + dy, b);
+                tma_load_2d_2sm(sa + G::kABytes, &tm_w, full_leader, tap * p.Cin + cb * CBK, n0 + (int)rank * (BN / 2));
+              } else {
+                mbar_expect_tx(&bar_full[st], G::kStageBytes);
+                tma_load_4d(sa, &tm_x, &bar_full[st], cb * CBK, x0 + dx, y0 + dy, b);
+                tma_load_2d(sa + G::kABytes, &tm_w, &bar_full[st], tap * p.Cin + cb * CBK, n0);
+              }
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 9) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0 && rank == 0) {
+    // ============================== MMA issuer (warp-uniform loop; elect_one() around the tcgen05 issue) =========
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TWO ? 2 * CBM : CBM, BN);
+      const uint32_t smem_base = smem_u32(smem);
       int it = 0, local = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers, ++local) {
         const int acc = local & 1;
@@ -180,22 +186,27 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const int st = it % G::kStages;
           mbar_wait(&bar_full[st], (it / G::kStages) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * G::kStageBytes);
-          const uint32_t sb = sa + G::kABytes;
+          if (elect_one()) {
+            // descriptors built once per stage; + k * 32 bytes = + 2, + mt * CBM * 128 bytes in 16-byte address units
+            const uint64_t da = make_smem_desc_sw128(smem_base + st * G::kStageBytes, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(smem_base + st * G::kStageBytes + G::kABytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < CBK / 8; ++k)   // K = 8 tf32 (32 bytes) per instruction
+            for (int k = 0; k < CBK / 8; ++k)   // K = 8 tf32 (32 bytes) per instruction
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              if constexpr (TWO)
-                mma_ss_tf32_2cta(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024),
-                                 make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else
-                mma_ss_tf32(d_tmem + mt * BN, make_smem_desc_sw128(sa + mt * (CBM * 128) + k * 32, 16, 1024),
-                            make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int mt = 0; mt < MT; ++mt) {
+                if constexpr (TWO)
+                  mma_ss_tf32_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                else
+                  mma_ss_tf32(d_tmem + mt * BN, da + (uint64_t)(mt * (CBM * 128 / 16) + 2 * k), db + 2 * k, idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
+            if (kb == kb_total - 1) {
+              if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
             }
-          if constexpr (TWO) mma_commit_2cta_mc(&bar_empty[st], 3); else mma_commit(&bar_empty[st]);
+          }
+          __syncwarp();
         }
-        if constexpr (TWO) mma_commit_2cta_mc(&bar_acc_full[acc], 3); else mma_commit(&bar_acc_full[acc]);
       }
     }
   } else {
