@@ -28,7 +28,21 @@ _ALIASES = {
 }
 
 
-def install_as_adv_grpo():
+def from_diffusers(pipeline, **kw):
+    """diffusers `StableDiffusion3Pipeline` (transformer optionally peft-wrapped) -> the B200 pipeline with the same
+    weights (`adapters.from_diffusers`)."""
+    from .adapters import from_diffusers as _f
+    return _f(pipeline, **kw)
+
+
+def install_as_adv_grpo(shim_third_party=False, force_shims=False):
+    """Alias this package's modules as `adv_grpo.*`.  With `shim_third_party=True`, `diffusers` / `peft` / `accelerate` /
+    `ml_collections` modules are additionally provided (`adv_grpo_b200.shims`) for every one of those libraries that is
+    NOT installed, so `StableDiffusion3Pipeline.from_pretrained`, `get_peft_model` and `accelerator.prepare` of the
+    unmodified scripts (train_sd3_fast_pickscore.py:447-449,500-511,663) build and return this package's objects."""
+    if shim_third_party:
+        from . import shims
+        shims.install(force=force_shims)
     root = sys.modules.get("adv_grpo")
     if root is None:
         root = types.ModuleType("adv_grpo")

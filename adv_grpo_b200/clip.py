@@ -67,6 +67,20 @@ class CLIPEncoderLayer(nn.Module):
         return x + self.mlp.fc2(F.gelu(self.mlp.fc1(self.layer_norm2(x))))
 
 
+def _ln(mod, x):
+    """Affine LayerNorm on the native kernel; autograd's node only while the discriminator trains this module (A14)."""
+    if torch.is_grad_enabled() and (x.requires_grad or mod.weight.requires_grad):
+        return mod(x)
+    return ops.layer_norm(x.contiguous(), mod.weight.detach(), mod.bias.detach(), mod.eps)
+
+
+def _proj(lin, x):
+    """Bias-free projection of the pooled token on the tcgen05 GEMM; nn.Linear only under autograd."""
+    if torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad):
+        return lin(x)
+    return ops.gemm(x.contiguous(), lin.weight.detach())
+
+
 class _Encoder(nn.Module):
     def __init__(self, width, heads, mlp, layers):
         super().__init__()
@@ -104,7 +118,7 @@ class _VisionModel(nn.Module):
             x = ops.layer_norm(x, self.pre_layrnorm.weight.detach(), self.pre_layrnorm.bias.detach(), 1e-5).contiguous()
         for layer in self.encoder.layers:
             x = layer(x, causal=False)
-        return self.post_layernorm(x[:, 0])
+        return _ln(self.post_layernorm, x[:, 0])
 
 
 class _TextEmbeddings(nn.Module):
@@ -128,7 +142,7 @@ class _TextModel(nn.Module):
         x = (e.token_embedding(input_ids) + e.position_embedding.weight[:S][None]).contiguous()
         for layer in self.encoder.layers:
             x = layer(x, causal=True)
-        x = self.final_layer_norm(x)
+        x = _ln(self.final_layer_norm, x)
         return x[torch.arange(x.shape[0], device=x.device), input_ids.argmax(-1)]   # EOS (highest id) pooling
 
 
@@ -149,7 +163,7 @@ class CLIPModel(nn.Module):
         return m.to(device=device, dtype=dtype).eval()
 
     def get_image_features(self, pixel_values=None, **_):
-        return self.visual_projection(self.vision_model(pixel_values))
+        return _proj(self.visual_projection, self.vision_model(pixel_values))
 
     def get_text_features(self, input_ids=None, attention_mask=None, **_):
-        return self.text_projection(self.text_model(input_ids))
+        return _proj(self.text_projection, self.text_model(input_ids))

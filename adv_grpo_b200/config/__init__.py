@@ -43,6 +43,7 @@ def install_shims():
     if "ml_collections" not in sys.modules:
         m = types.ModuleType("ml_collections")
         m.ConfigDict = ConfigDict
+        m.__advgrpo_shim__ = True
         sys.modules["ml_collections"] = m
     if "imp" not in sys.modules:
         imp = types.ModuleType("imp")

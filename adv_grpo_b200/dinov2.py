@@ -55,3 +55,20 @@ class DINOHead(torch.nn.Module):
 
     def forward(self, x):
         return self.layers(x)
+
+
+def dino_hinge_d_loss(head, feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight=0.3):
+    """Discriminator (head) loss of `train_sd3_fast_dino_patch.py:186-219`: hinge loss on the CLS token of real / fake
+    images plus `patch_loss_weight` x the hinge loss on the sampled patch tokens (`idx_*` [B, n] = the torch.randint
+    draws of :199-200; NO L2 normalisation in the D step, unlike the reward path).  Returns (loss, accuracy)."""
+    relu = torch.nn.functional.relu
+    hp = next(head.parameters())
+    fr, ff = feats_real.to(hp.dtype), feats_fake.to(hp.dtype)
+    lr_, lf_ = head(fr[:, 0]).squeeze(-1), head(ff[:, 0]).squeeze(-1)
+    image_loss = 0.5 * (relu(1.0 - lr_).mean() + relu(1.0 + lf_).mean())
+    D = fr.shape[-1]
+    sr = torch.gather(fr[:, 1:], 1, idx_real.unsqueeze(-1).expand(-1, -1, D))
+    sf = torch.gather(ff[:, 1:], 1, idx_fake.unsqueeze(-1).expand(-1, -1, D))
+    patch_loss = 0.5 * (relu(1.0 - head(sr).squeeze(-1)).mean() + relu(1.0 + head(sf).squeeze(-1)).mean())
+    acc = 0.5 * ((lr_ > 0).float().mean() + (lf_ < 0).float().mean())
+    return image_loss + patch_loss_weight * patch_loss, acc

@@ -312,7 +312,7 @@ class SD3Transformer2DModel(torch.nn.Module):
         self.w_patch = p["pos_embed.proj.weight"].reshape(d, -1).contiguous()
         self._pos_cache = {}
         # ---- LoRA: ONE flat fp32 master parameter (peft-layout A [r, in] / B [out, r] factors are views of it) ----
-        self.lora_rank, self.lora_scale = lora_rank, lora_alpha / lora_rank
+        self.lora_rank, self.lora_scale = lora_rank, (lora_alpha / lora_rank if lora_rank else 0.0)
         self.lora_A, self.lora_B = {}, {}            # name -> view of the flat buffer (shares storage; .grad = view of flat.grad)
         self._lora_names = []
         init, sizes = [], []
@@ -351,6 +351,15 @@ class SD3Transformer2DModel(torch.nn.Module):
         self._lora_enabled = True
 
     # ------------------------------------------------------------------ peft-like surface
+    def to(self, *args, **kwargs):
+        """The weights live on the device given at construction (packed bf16 operands); `.to(accelerator.device)` /
+        `.to(dtype)` of the scripts is accepted and ignored."""
+        return self
+
+    def set_adapter(self, name="default"):
+        self.lora_flat.requires_grad_(True)
+        return self
+
     def trainable_parameters(self):
         """The single flat LoRA parameter (optimizer / clipping / EMA / all-reduce work on one tensor); the per-layer
         factors are `lora_A[key]` / `lora_B[key]` views of it."""

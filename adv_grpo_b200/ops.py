@@ -272,9 +272,13 @@ def layer_norm(x, weight, bias, eps):
     blocks, train_sd3_fast_pickscore.py:151-183) autograd's own LayerNorm node is used."""
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad)
     D = x.shape[-1]
-    if needs_grad or x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or D % 256 or D > 2048:
+    if needs_grad:                     # discriminator training of the last CLIP block only (A14): autograd's LayerNorm
         return torch.nn.functional.layer_norm(x, (D,), weight, bias, eps)
     _need_cuda(x, weight, bias)
+    if D % 256 or D > 2048:
+        raise ValueError(f"layer_norm: width {D} is not supported by the native kernel (multiple of 256, <= 2048); "
+                         "there is no PyTorch fallback")
+    x, weight, bias = _bf16c(x), _bf16c(weight), _bf16c(bias)
     x = x.contiguous()
     y = torch.empty_like(x)
     _lib.call("advgrpo_layer_norm_affine", _ptr(x), _ptr(weight.contiguous()), _ptr(bias.contiguous()), _ptr(y),

@@ -23,6 +23,16 @@ from .clip import CLIPModel
 from .weights import CLIP_H, init_clip
 
 
+class _Encoding(dict):
+    """`tokenizer(...)` result with both item and attribute access (`.input_ids`), like transformers' BatchEncoding."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
 class SyntheticCLIPTokenizer:
     bos, eos, vocab = 49406, 49407, 49408
 
@@ -43,7 +53,7 @@ class SyntheticCLIPTokenizer:
         out = np.zeros((len(rows), width), dtype=np.int64)
         for i, r in enumerate(rows):
             out[i, :len(r)] = r
-        return {"input_ids": torch.from_numpy(out), "attention_mask": torch.from_numpy((out != 0).astype(np.int64))}
+        return _Encoding({"input_ids": torch.from_numpy(out), "attention_mask": torch.from_numpy((out != 0).astype(np.int64))})
 
     def batch_decode(self, ids, skip_special_tokens=True):
         return [" ".join(str(int(t)) for t in row if int(t) not in (0, self.bos, self.eos)) for row in ids]
@@ -123,9 +133,15 @@ class _GraphedImageTower:
 
 class PickScoreScorer(torch.nn.Module):
     def __init__(self, device="cuda", dtype=torch.float32, cfg=CLIP_H, state_dict=None, tokenizer=None, seed=3,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, reference_score_arithmetic=False):
         super().__init__()
         self.use_cuda_graph = use_cuda_graph
+        # Quirk Q10: the reference scorer, instantiated in bf16 by the training script (train_pick:657 passes
+        # inference_dtype), L2-normalises the features, takes the text-image dot product and applies logit_scale / 26
+        # IN bf16 (adv_grpo/pickscore_scorer.py:40-51) and returns bf16 scores (3 significant digits).  The default here
+        # does that tail in fp32 on the same bf16 features (scores differ by <= 1 bf16 ulp of the reference's);
+        # reference_score_arithmetic=True reproduces the bf16 rounding sequence and dtype.
+        self.reference_score_arithmetic = reference_score_arithmetic
         self.device, self.dtype = device, dtype
         if state_dict is None:
             state_dict = init_clip(cfg, seed=seed, device=device, dtype=torch.bfloat16)
@@ -153,9 +169,11 @@ class PickScoreScorer(torch.nn.Module):
         if self.use_cuda_graph and torch.device(self.device).type == "cuda":
             if self._image_tower is None or self._image_tower.model is not model:
                 self._image_tower = _GraphedImageTower(model)
-            image_embs = self._image_tower(pixel_values).float()
+            image_embs = self._image_tower(pixel_values)
         else:
-            image_embs = model.get_image_features(pixel_values=pixel_values).float()
+            image_embs = model.get_image_features(pixel_values=pixel_values)
+        self._last_image_feats_bf16 = image_embs.to(torch.bfloat16)
+        image_embs = image_embs.float()
         image_embs = image_embs / image_embs.norm(p=2, dim=-1, keepdim=True)
         # the text tower is frozen: one forward per distinct prompt, cached across calls (generated and
         # reference images of a group share the prompt; the reference recomputes it for every image)
@@ -165,13 +183,23 @@ class PickScoreScorer(torch.nn.Module):
             hit = self._text_cache.get(pr)
             if hit is None or hit[0] != tver:
                 ids = self.processor.tokenizer([pr], padding=True, truncation=True, max_length=77)["input_ids"].to(self.device)
-                t = model.get_text_features(input_ids=ids).float()
+                t16 = model.get_text_features(input_ids=ids).to(torch.bfloat16)
+                t = t16.float()
                 if len(self._text_cache) > 4096:
                     self._text_cache.clear()
-                hit = (tver, t / t.norm(p=2, dim=-1, keepdim=True))
+                hit = (tver, t / t.norm(p=2, dim=-1, keepdim=True), t16 / t16.norm(p=2, dim=-1, keepdim=True))
                 self._text_cache[pr] = hit
             feats.append(hit[1])
         text_embs = torch.cat(feats, 0)
         index = torch.tensor([uniq.index(p) for p in prompt], device=self.device)
+        if self.reference_score_arithmetic:
+            bf = torch.bfloat16
+            # bf16 features were divided by their bf16 norms in the reference; redo that tail from the bf16 tower outputs
+            ie = self._last_image_feats_bf16
+            ie = ie / ie.norm(p=2, dim=-1, keepdim=True)
+            te = torch.cat([self._text_cache[pr][2] for pr in uniq], 0)[index]
+            # diag of `text_embs @ image_embs.T`: a bf16 matmul (fp32 products and accumulation, ONE rounding to bf16)
+            s_bf = model.logit_scale.exp().to(bf) * torch.bmm(te[:, None, :], ie[:, :, None]).reshape(-1)
+            return s_bf / 26
         scores = model.logit_scale.exp().float() * (text_embs[index] * image_embs).sum(-1)
         return scores / 26

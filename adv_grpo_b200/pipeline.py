@@ -53,6 +53,7 @@ class StableDiffusion3Pipeline:
     vae_scale_factor = 8
 
     def __init__(self, transformer, vae, scheduler=None, tokenizer=None, device="cuda", use_cuda_graph=True):
+        self._use_cuda_graph = use_cuda_graph
         self.transformer = transformer
         self.vae = vae
         self.scheduler = scheduler or FlowMatchEulerDiscreteScheduler()
@@ -60,7 +61,24 @@ class StableDiffusion3Pipeline:
         self.tokenizer = tokenizer or SyntheticCLIPTokenizer()
         self._execution_device = torch.device(device)
         self.default_sample_size = transformer.config.sample_size
-        self.graphed_transformer = GraphedForward(transformer) if use_cuda_graph else None
+        self._use_cuda_graph = use_cuda_graph
+        self.text_encoder = self.text_encoder_2 = self.text_encoder_3 = None
+        self.tokenizer_2 = self.tokenizer_3 = None
+        self.safety_checker = None
+
+    def set_progress_bar_config(self, **kw):
+        pass
+
+    @property
+    def transformer(self):
+        return self._transformer
+
+    @transformer.setter
+    def transformer(self, model):
+        """`pipeline.transformer = get_peft_model(pipeline.transformer, ...)` (train_pick:506-511): the rollout graph
+        runner follows the new object."""
+        self._transformer = model
+        self.graphed_transformer = GraphedForward(model) if getattr(self, "_use_cuda_graph", False) else None
 
     @classmethod
     def from_seed(cls, mmdit_cfg=weights.SD35_MEDIUM, vae_cfg=weights.VAE_SD3, device="cuda", lora_rank=32,
@@ -71,3 +89,16 @@ class StableDiffusion3Pipeline:
                                             device=device)
         vae = AutoencoderKL(weights.init_vae_decoder(vae_cfg, seed=seed + 2, device=device), vae_cfg, device=device)
         return cls(transformer, vae, device=device, use_cuda_graph=use_cuda_graph)
+
+    def add_seeded_text_encoders(self, clip_l=weights.CLIP_L_TEXT, clip_g=weights.CLIP_G_TEXT, t5=weights.T5_XXL, seed=5):
+        """CLIP-L / CLIP-G / T5 encoders with seeded weights at the given sizes + synthetic tokenizers (no checkpoints on
+        the box), so `pipeline.text_encoder{,_2,_3}` / `pipeline.tokenizer{,_2,_3}` of train_pick:456-457 exist."""
+        from . import text_encoders as te
+        dev = self._execution_device
+        self.text_encoder = te.CLIPTextModelWithProjection(weights.init_clip_text(clip_l, seed=seed, device=dev), clip_l, device=dev)
+        self.text_encoder_2 = te.CLIPTextModelWithProjection(weights.init_clip_text(clip_g, seed=seed + 1, device=dev), clip_g, device=dev)
+        self.text_encoder_3 = te.T5EncoderModel(weights.init_t5_encoder(t5, seed=seed + 2, device=dev), t5, device=dev)
+        self.tokenizer = SyntheticCLIPTokenizer(clip_l["vocab"])
+        self.tokenizer_2 = SyntheticCLIPTokenizer(clip_g["vocab"])
+        self.tokenizer_3 = SyntheticCLIPTokenizer(t5["vocab"])
+        return self

@@ -28,6 +28,15 @@ class _ClipTextOutput(tuple):
 
 
 class CLIPTextModelWithProjection:
+    def requires_grad_(self, flag=True):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
     def __init__(self, params, cfg, device="cuda", dtype=torch.bfloat16):
         self.cfg, self.device, self.dtype = dict(cfg), torch.device(device), dtype
         p = {k: v.to(device=self.device, dtype=dtype) for k, v in params.items()}
@@ -56,8 +65,8 @@ class CLIPTextModelWithProjection:
         for blk in self.blocks:
             x = blk(x, causal=True)
             hidden.append(x)
-        last = F.layer_norm(x, (x.shape[-1],), p["text_model.final_layer_norm.weight"],
-                            p["text_model.final_layer_norm.bias"], 1e-5)
+        last = ops.layer_norm(x.contiguous(), p["text_model.final_layer_norm.weight"],
+                              p["text_model.final_layer_norm.bias"], 1e-5)
         if cfg.get("eos_id", 2) == 2:
             pos = input_ids.argmax(-1)
         else:
@@ -86,6 +95,15 @@ def _t5_layer_norm(x, w, eps=1e-6):
 
 
 class T5EncoderModel:
+    def requires_grad_(self, flag=True):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
     def __init__(self, params, cfg, device="cuda", dtype=torch.bfloat16):
         self.cfg, self.device, self.dtype = dict(cfg), torch.device(device), dtype
         p = {k: v.to(device=self.device, dtype=dtype) for k, v in params.items()}

@@ -11,11 +11,14 @@ decode of prompt ids, no float64 host advantages.
 """
 import math
 
+import warnings
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
+from .dinov2 import dino_hinge_d_loss
 from .ema import EMAModuleWrapper
 from .optim import FlatClipAdamW
 from .pick_score_training import CLIPCriterion, CLIPCriterionConfig
@@ -155,15 +158,27 @@ class GRPOTrainer:
         self.ema = EMAModuleWrapper(self.params, decay=0.9, update_step_interval=8, device=device) if t.ema else None
         self.reward_fn = multi_score(device, dict(config.reward_fn))
         self.reward_key = next(iter(dict(config.reward_fn)))
-        self.sampler = DistributedKRepeatSampler(self.prompts, s.train_batch_size,
-                                                 s.num_image_per_prompt // s.mini_num_image_per_prompt
-                                                 if s.get("shard_groups_across_ranks", False) else 1,
-                                                 self.world, self.rank, seed=42)
+        # k = num_image_per_prompt // mini_num_image_per_prompt as in the reference (train_pick:577): a prompt is rolled
+        # out on k ranks and its advantage group has k * mini images.  Only when world * train_batch_size is not divisible
+        # by k (single-GPU runs of the 8-GPU presets) does the group collapse to one rank-call, with a warning.
+        # `sample.shard_groups_across_ranks = False` forces k = 1 (north_star bench: every rank owns whole groups).
+        k_ref = max(1, s.num_image_per_prompt // s.mini_num_image_per_prompt)
+        k = k_ref
+        if s.get("shard_groups_across_ranks", None) is False:
+            k = 1
+        elif (self.world * s.train_batch_size) % k_ref != 0:
+            k = 1
+            warnings.warn(f"world_size * train_batch_size = {self.world * s.train_batch_size} is not divisible by "
+                          f"k = num_image_per_prompt // mini_num_image_per_prompt = {k_ref}: every prompt is rolled out "
+                          f"by one rank-call only (group size {s.mini_num_image_per_prompt}, not {s.num_image_per_prompt})")
+        self.sampler = DistributedKRepeatSampler(self.prompts, s.train_batch_size, k, self.world, self.rank, seed=42)
         self.stat_tracker = PerPromptStatTracker(s.global_std, device=device)
         self.neg_embeds, self.neg_pooled = self.embedder.negative()
         self.generator = torch.Generator(device=device).manual_seed(config.seed + self.rank)
         self.global_step = 0
         self.epoch = 0
+        self._micro = 0                      # replay micro-steps so far (accumulation counter, persists across epochs)
+        self.d_schedule = None               # optional epoch -> bool override of the D / G gate (bench: alternate)
         self.optimizer_D = None
         if config.get("train_d", False):
             if self.reward_key == "pickscore_cotrain":
@@ -268,19 +283,12 @@ class GRPOTrainer:
             with torch.no_grad():
                 fr = self.scorer.forward_features(ops.dino_preprocess(real, 518))
                 ff = self.scorer.forward_features(ops.dino_preprocess(fake, 518))
-            hp = next(self.head.parameters())
-            fr, ff = fr.to(hp.dtype), ff.to(hp.dtype)
-            relu = torch.nn.functional.relu
-            lr_, lf_ = self.head(fr[:, 0]).squeeze(-1), self.head(ff[:, 0]).squeeze(-1)
-            image_loss = 0.5 * (relu(1.0 - lr_).mean() + relu(1.0 + lf_).mean())
-            B, N, D = fr[:, 1:].shape
+            N = fr.shape[1] - 1
             n_sel = min(64, N)
-            ir = torch.randint(0, N, (B, n_sel), device=self.device)
-            if_ = torch.randint(0, N, (B, n_sel), device=self.device)
-            sr = torch.gather(fr[:, 1:], 1, ir.unsqueeze(-1).expand(-1, -1, D))
-            sf = torch.gather(ff[:, 1:], 1, if_.unsqueeze(-1).expand(-1, -1, D))
-            patch_loss = 0.5 * (relu(1.0 - self.head(sr).squeeze(-1)).mean() + relu(1.0 + self.head(sf).squeeze(-1)).mean())
-            loss = image_loss + 0.3 * patch_loss                                      # train_dino:186-219
+            ir = torch.randint(0, N, (fr.shape[0], n_sel), device=self.device)
+            if_ = torch.randint(0, N, (ff.shape[0], n_sel), device=self.device)
+            loss, acc = dino_hinge_d_loss(self.head, fr, ff, ir, if_, 0.3)               # train_dino:186-219
+            self.last_info["d_acc"] = acc.detach()
             params = list(self.head.parameters())
         self.optimizer_D.zero_grad()
         loss.backward()
@@ -313,52 +321,70 @@ class GRPOTrainer:
             off += g.numel()
 
     def train_generator(self, samples, advantages):
+        """`train_pick:1050-1180`: per sample batch and SDE-window step one replay micro-step (forward + loss +
+        backward), an optimizer step every `gradient_accumulation_steps * T` micro-steps (the accelerate accumulation
+        counter persists across epochs), `train.num_inner_epochs` passes over the epoch's samples.  `train.micro_batch`
+        (not in the reference) replays a group in chunks of that many samples (same gradient: the loss is a batch mean,
+        each chunk is scaled by its share) to bound activation memory at 1024x1024 / G = 16."""
         c, t = self.config, self.config.train
         T = c.sample.train_num_steps
         gas = t.gradient_accumulation_steps * T                      # Accelerator(grad_accum = gas * T), train_pick:426
         self.transformer.train()
         stats_acc = []
-        micro = 0
         n_local = samples[0]["latents"].shape[0]
-        for i, sample in enumerate(samples):
-            if t.cfg:
-                embeds = torch.cat([self.neg_embeds.repeat(n_local, 1, 1), sample["prompt_embeds"]])
-                pooled = torch.cat([self.neg_pooled.repeat(n_local, 1), sample["pooled_prompt_embeds"]])
-            else:
-                embeds, pooled = sample["prompt_embeds"], sample["pooled_prompt_embeds"]
-            adv_i = advantages[i * n_local:(i + 1) * n_local]
-            for j in range(T):
-                if t.beta > 0:
-                    # KL-regularised step (train_pick:1105-1108,1124-1128): reference mean from the adapter-disabled
-                    # forward, loss = policy_loss + beta * mean_b(mean_chw((mu - mu_ref)^2))
-                    with torch.no_grad(), self.transformer.disable_adapter():
-                        _, _, mean_ref, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c,
-                                                             want_mean=True)
-                    _, log_prob, _, _, kl = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c,
-                                                             mean_ref=mean_ref)
-                    loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
-                                                     t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
-                    kl_loss = kl.mean()
-                    (loss + (t.beta / gas) * kl_loss.to(loss.dtype)).backward()
-                    self.last_info["kl_loss"] = kl_loss.detach()
-                elif self.micro_step is not None and t.cfg:
-                    stats = self.micro_step(sample["latents"][:, j].contiguous(), sample["next_latents"][:, j].contiguous(),
-                                            sample["timesteps"][:, j].contiguous(), embeds, pooled,
-                                            sample["log_probs"][:, j].contiguous(), adv_i[:, j].contiguous(), 1.0 / gas)
-                else:
-                    _, log_prob, _, _ = compute_log_prob(self.transformer, self.pipeline, sample, j, embeds, pooled, c)
-                    loss, stats = ops.grpo_clip_loss(log_prob, sample["log_probs"][:, j], adv_i[:, j].contiguous(),
-                                                     t.clip_range, t.adv_clip_max, grad_scale=1.0 / gas)
-                    loss.backward()
-                stats_acc.append(stats)
-                micro += 1
-                if micro % gas == 0:
-                    self._sync_grads()
-                    self.optimizer.step()                       # clip + AdamW + gradient clear (csrc/optim.cu)
-                    self.transformer.invalidate_lora_cache()
-                    self.global_step += 1
-            if self.ema is not None:
-                self.ema.step(self.params, self.global_step)
+        mb = int(t.get("micro_batch", 0) or 0)
+        mb = mb if 0 < mb < n_local and n_local % mb == 0 else n_local
+        for _inner in range(int(t.get("num_inner_epochs", 1) or 1)):
+            for i, sample in enumerate(samples):
+                adv_i = advantages[i * n_local:(i + 1) * n_local]
+                for j in range(T):
+                    stats_j = None
+                    for c0 in range(0, n_local, mb):
+                        sl = slice(c0, c0 + mb)
+                        sub = sample if mb == n_local else {k: sample[k][sl] for k in ("latents", "next_latents", "timesteps",
+                                                                                       "log_probs", "prompt_embeds",
+                                                                                       "pooled_prompt_embeds")}
+                        if t.cfg:
+                            embeds = torch.cat([self.neg_embeds.repeat(mb, 1, 1), sub["prompt_embeds"]])
+                            pooled = torch.cat([self.neg_pooled.repeat(mb, 1), sub["pooled_prompt_embeds"]])
+                        else:
+                            embeds, pooled = sub["prompt_embeds"], sub["pooled_prompt_embeds"]
+                        adv_c = adv_i[sl, j].contiguous()
+                        share = mb / n_local
+                        if t.beta > 0:
+                            # KL-regularised step (train_pick:1105-1108,1124-1128): reference mean from the adapter-disabled
+                            # forward, loss = policy_loss + beta * mean_b(mean_chw((mu - mu_ref)^2))
+                            with torch.no_grad(), self.transformer.disable_adapter():
+                                _, _, mean_ref, _ = compute_log_prob(self.transformer, self.pipeline, sub, j, embeds, pooled, c,
+                                                                     want_mean=True)
+                            _, log_prob, _, _, kl = compute_log_prob(self.transformer, self.pipeline, sub, j, embeds, pooled, c,
+                                                                     mean_ref=mean_ref)
+                            loss, stats = ops.grpo_clip_loss(log_prob, sub["log_probs"][:, j], adv_c,
+                                                             t.clip_range, t.adv_clip_max, grad_scale=share / gas)
+                            kl_loss = kl.mean()
+                            (loss + (t.beta * share / gas) * kl_loss.to(loss.dtype)).backward()
+                            self.last_info["kl_loss"] = kl_loss.detach()
+                            stats = stats.clone()
+                            stats[0] = stats[5] + t.beta * kl_loss.to(stats.dtype)       # logged loss = policy + beta * kl
+                        elif self.micro_step is not None and t.cfg:
+                            stats = self.micro_step(sub["latents"][:, j].contiguous(), sub["next_latents"][:, j].contiguous(),
+                                                    sub["timesteps"][:, j].contiguous(), embeds, pooled,
+                                                    sub["log_probs"][:, j].contiguous(), adv_c, share / gas)
+                        else:
+                            _, log_prob, _, _ = compute_log_prob(self.transformer, self.pipeline, sub, j, embeds, pooled, c)
+                            loss, stats = ops.grpo_clip_loss(log_prob, sub["log_probs"][:, j], adv_c,
+                                                             t.clip_range, t.adv_clip_max, grad_scale=share / gas)
+                            loss.backward()
+                        stats_j = stats * share if stats_j is None else stats_j + stats * share
+                    stats_acc.append(stats_j)
+                    self._micro += 1
+                    if self._micro % gas == 0:
+                        self._sync_grads()
+                        self.optimizer.step()                       # clip + AdamW + gradient clear (csrc/optim.cu)
+                        self.transformer.invalidate_lora_cache()
+                        self.global_step += 1
+                if self.ema is not None:
+                    self.ema.step(self.params, self.global_step)
         if stats_acc:
             m = torch.stack(stats_acc).mean(0)
             self.last_info.update(loss=m[0], approx_kl=m[1], clipfrac=m[2], clipfrac_gt_one=m[3], clipfrac_lt_one=m[4],
@@ -374,8 +400,14 @@ class GRPOTrainer:
         logging of the reference is not part of this path."""
         c, s = self.config, self.config.sample
         idxs = list(range(len(self.prompts))) if prompt_indices is None else list(prompt_indices)
-        idxs = idxs[self.rank::self.world]                                    # test DataLoader sharded by accelerate
         bs = int(batch_size or s.test_batch_size)
+        # test DataLoader sharded by accelerate, which pads the last batches so that every rank runs the same number of
+        # equally sized batches (the per-batch gathers below would otherwise mismatch): pad with repeats, mask them out
+        n_valid = len(idxs)
+        per_rank = -(-max(n_valid, 1) // (self.world * bs)) * bs
+        padded = idxs + [idxs[i % n_valid] for i in range(per_rank * self.world - n_valid)] if n_valid else []
+        valid_flags = [1.0] * n_valid + [0.0] * (len(padded) - n_valid)
+        idxs, flags = padded[self.rank::self.world], valid_flags[self.rank::self.world]
         if c.train.ema and self.ema is not None:
             self.ema.copy_ema_to(self.params, store_temp=True)
             self.transformer.invalidate_lora_cache()
@@ -396,8 +428,9 @@ class GRPOTrainer:
                     height=c.resolution, width=c.resolution, noise_level=0, mini_num_image_per_prompt=1,
                     process_index=self.rank, sample_num_steps=s.num_steps, random_timestep=s.get("random_timestep", 0),
                     generator=generator)
+                keep_b = all_gather_cat(torch.tensor(flags[b0:b0 + bs], device=self.device)) > 0
                 for k, v in self._score(images, prompts).items():
-                    all_rewards.setdefault(k, []).append(all_gather_cat(v))
+                    all_rewards.setdefault(k, []).append(all_gather_cat(v)[keep_b])
         finally:
             if c.train.ema and self.ema is not None:
                 self.ema.copy_temp_to(self.params)
@@ -423,7 +456,9 @@ class GRPOTrainer:
         advantages = self.compute_advantages(samples)
         did_d = False
         if c.get("train_d", False) and self.optimizer_D is not None:
-            if self.reward_key == "pickscore_cotrain":
+            if self.d_schedule is not None:
+                did_d = bool(self.d_schedule(self.epoch))
+            elif self.reward_key == "pickscore_cotrain":
                 gen = all_gather_cat(torch.cat([s["rewards"][self.reward_key] for s in samples])).mean()
                 ref = all_gather_cat(torch.cat([s["reference_rewards"][self.reward_key] for s in samples])).mean()
                 did_d = bool(ref < gen)                                        # train_pick:1025 (one host sync per epoch)

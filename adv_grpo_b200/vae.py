@@ -30,11 +30,23 @@ class AutoencoderKL:
             if v.dim() == 4:
                 v = v.contiguous(memory_format=torch.channels_last)
             self.p[k] = v
-        self.fused = torch.device(device).type == "cuda" and dtype == torch.float32
+        if dtype != torch.float32:
+            raise ValueError(f"AutoencoderKL is an fp32 model (train_pick:481 keeps the VAE in float32), got {dtype}")
+        self.fused = True            # every op below is a native kernel; decode() on a non-CUDA tensor raises (ops._need_cuda)
         self.native_conv = True       # 3x3 / 1x1 convolutions on the tcgen05 TF32 implicit-GEMM kernel (csrc/conv.cu)
+        self.max_latent_pixels = 8 * 64 * 64    # decode() splits larger batches (8 images at 512 px, 2 at 1024 px per call)
 
     def to(self, *a, **k):
         return self
+
+    def requires_grad_(self, flag=True):
+        return self
+
+    def eval(self):
+        return self
+
+    def state_dict(self):
+        return {k: v for k, v in self.p.items() if not k.endswith((".packed_tf32", ".fused_bias"))}
 
     # ---- building blocks -------------------------------------------------------------------------------
     def _fusable(self, C):
@@ -42,13 +54,11 @@ class AutoencoderKL:
 
     def _gn(self, name, x, silu=False, in_bias=None):
         C = x.shape[1]
-        if self._fusable(C):
-            return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu,
-                                            in_bias=in_bias, round_tf32=self.native_conv)
-        if in_bias is not None:
-            x = x + in_bias[None, :, None, None]
-        y = F.group_norm(x, 32, self.p[name + ".weight"], self.p[name + ".bias"], eps=1e-6)   # tiny test configs
-        return F.silu(y) if silu else y
+        if not self._fusable(C):
+            raise ValueError(f"GroupNorm over {C} channels is not supported by gn_stats / gn_apply (channels must be a "
+                             "multiple of 128 with 256 % (C / 4) == 0: 128, 256, 512, 1024); no PyTorch fallback")
+        return ops.group_norm_silu_nhwc(x, self.p[name + ".weight"], self.p[name + ".bias"], 32, 1e-6, silu,
+                                        in_bias=in_bias, round_tf32=self.native_conv)
 
     def _conv(self, name, x, pad=1, bias=True):
         w = self.p[name + ".weight"]
@@ -58,7 +68,11 @@ class AutoencoderKL:
             if key not in self.p:
                 self.p[key] = ops.pack_conv_weight_tf32(w)
             return ops.conv2d_nhwc_tf32(x, self.p[key], self.p[name + ".bias"] if bias else None, k)
-        # conv_in (16 input channels) and conv_out (3 output channels) stay library calls: 0.3 % of the decoder FLOPs
+        # conv_in (16 input channels) and conv_out (3 output channels) are the two documented library calls (cuDNN,
+        # 0.3 % of the decoder FLOPs); any other shape the native kernel cannot take is an error, not a silent fallback
+        if name not in ("decoder.conv_in", "decoder.conv_out") and self.native_conv:
+            raise ValueError(f"convolution {name} ({Cin} -> {Cout}, k={k}, pad={pad}) is not supported by conv_tf32_kernel "
+                             "(channels must be multiples of 32, k in {1, 3}, pad = k // 2)")
         return F.conv2d(x, w, self.p[name + ".bias"] if bias else None, padding=pad)
 
     def _resnet(self, pre, x):
@@ -87,22 +101,27 @@ class AutoencoderKL:
         h = self._gn(pre + ".group_norm", x)
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)                       # NHWC storage: a view, no copy
         q, k, v = (F.linear(h, p[f"{pre}.to_{n}.weight"], p[f"{pre}.to_{n}.bias"]) for n in "qkv")
-        if self.fused:
-            s = torch.bmm(q * (C ** -0.5), k.transpose(1, 2))
-            o = torch.bmm(torch.softmax(s, dim=-1), v)
-        else:
-            o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        # single-head attention over the 64 x 64 latent grid (1 % of the decoder FLOPs): two TF32 cuBLAS batched GEMMs
+        # + softmax, the third documented library call of the decoder
+        s = torch.bmm(q * (C ** -0.5), k.transpose(1, 2))
+        o = torch.bmm(torch.softmax(s, dim=-1), v)
         o = F.linear(o, p[pre + ".to_out.0.weight"], p[pre + ".to_out.0.bias"])
         o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                         # logical NCHW, channels_last strides
-        return ops.add_bias_nhwc(x, o, None) if self.fused else x + o
+        return ops.add_bias_nhwc(x, o, None)
 
     def _upsample(self, x):
-        if self.fused and x.shape[1] % 4 == 0:
-            return ops.upsample_nearest2x_nhwc(x)
-        return F.interpolate(x, scale_factor=2.0, mode="nearest")
+        return ops.upsample_nearest2x_nhwc(x)
 
     @torch.no_grad()
     def decode(self, z, return_dict=False):
+        B, _, h, w = z.shape
+        per_call = max(1, self.max_latent_pixels // (h * w))
+        if B > per_call:                               # bound the activation footprint (fp32 NHWC maps) of large batches
+            return (torch.cat([self._decode(z[i:i + per_call]) for i in range(0, B, per_call)]),)
+        return (self._decode(z),)
+
+    def _decode(self, z):
+        ops._need_cuda(z)
         x = z.to(self.dtype).contiguous(memory_format=torch.channels_last)
         x = self._conv("decoder.conv_in", x)
         x = self._resnet("decoder.mid_block.resnets.0", x)
@@ -115,7 +134,7 @@ class AutoencoderKL:
             if i < n_up - 1:
                 x = self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", self._upsample(x))
         x = self._gn("decoder.conv_norm_out", x, silu=True)
-        return (self._conv("decoder.conv_out", x),)
+        return self._conv("decoder.conv_out", x)
 
 
 class VaeImageProcessor:

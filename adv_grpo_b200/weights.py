@@ -19,19 +19,21 @@ MMDIT_TINY = dict(num_layers=3, heads=4, head_dim=64, dual_layers=(0, 1), qk_nor
 
 CLIP_H = dict(patch=14, image=224, v_width=1280, v_layers=32, v_heads=16, v_mlp=5120, t_width=1024,
               t_layers=24, t_heads=16, t_mlp=4096, vocab=49408, ctx=77, proj=1024)
-CLIP_TINY = dict(patch=14, image=224, v_width=128, v_layers=2, v_heads=2, v_mlp=256, t_width=128,
-                 t_layers=2, t_heads=2, t_mlp=256, vocab=1000, ctx=77, proj=64)
+# (tiny test configs keep every width a multiple of 256 and every VAE channel count a multiple of 128: the shapes the
+#  native LayerNorm / GroupNorm kernels accept -- there is no PyTorch fallback for other shapes)
+CLIP_TINY = dict(patch=14, image=224, v_width=256, v_layers=2, v_heads=4, v_mlp=512, t_width=256,
+                 t_layers=2, t_heads=4, t_mlp=512, vocab=1000, ctx=77, proj=64)
 DINOV2_B = dict(patch=14, image=518, width=768, layers=12, heads=12, mlp=3072)
 DINOV2_TINY = dict(patch=14, image=518, width=256, layers=2, heads=4, mlp=512)
 VAE_SD3 = dict(latent_channels=16, block_out=(128, 256, 512, 512), layers_per_block=2)
-VAE_TINY = dict(latent_channels=16, block_out=(32, 32, 64, 64), layers_per_block=2)
+VAE_TINY = dict(latent_channels=16, block_out=(128, 128, 256, 256), layers_per_block=2)
 
 # text encoders of stabilityai/stable-diffusion-3.5-medium (text_encoder / text_encoder_2 / text_encoder_3)
 CLIP_L_TEXT = dict(width=768, layers=12, heads=12, mlp=3072, act="quick_gelu", vocab=49408, ctx=77, proj=768, eos_id=2)
 CLIP_G_TEXT = dict(width=1280, layers=32, heads=20, mlp=5120, act="gelu", vocab=49408, ctx=77, proj=1280, eos_id=2)
 T5_XXL = dict(d_model=4096, layers=24, heads=64, d_kv=64, d_ff=10240, vocab=32128, num_buckets=32, max_distance=128)
-CLIP_L_TEXT_TINY = dict(width=128, layers=3, heads=2, mlp=256, act="quick_gelu", vocab=1000, ctx=77, proj=128, eos_id=2)
-CLIP_G_TEXT_TINY = dict(width=192, layers=3, heads=3, mlp=384, act="gelu", vocab=1000, ctx=77, proj=192, eos_id=2)
+CLIP_L_TEXT_TINY = dict(width=256, layers=3, heads=4, mlp=512, act="quick_gelu", vocab=1000, ctx=77, proj=256, eos_id=2)
+CLIP_G_TEXT_TINY = dict(width=512, layers=3, heads=8, mlp=768, act="gelu", vocab=1000, ctx=77, proj=512, eos_id=2)
 T5_TINY = dict(d_model=512, layers=2, heads=4, d_kv=64, d_ff=640, vocab=500, num_buckets=32, max_distance=128)
 
 LORA_TARGETS = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0",
@@ -40,11 +42,15 @@ LORA_TARGETS = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0",
 
 class _Init:
     def __init__(self, seed, device, dtype):
-        self.g = torch.Generator(device=device).manual_seed(seed)
+        self.meta = str(device) == "meta"                 # shape-only inventory (parameter-count tests), no storage
+        self.g = None if self.meta else torch.Generator(device=device).manual_seed(seed)
         self.device, self.dtype = device, dtype
         self.p = {}
 
     def normal(self, name, shape, std=0.02, mean=0.0):
+        if self.meta:
+            self.p[name] = torch.empty(shape, device="meta", dtype=self.dtype)
+            return
         t = torch.randn(shape, generator=self.g, device=self.device, dtype=torch.float32) * std + mean
         self.p[name] = t.to(self.dtype)
 

@@ -35,7 +35,31 @@ try:
 except (OSError, ValueError):
     pass
 UNIT = "samples/s"
-NB, G, T_STEPS, T_TRAIN, RES = 2, 8, 10, 2, 512
+NB, G, T_STEPS, T_TRAIN, RES = 2, 8, 10, 2, 512          # BASELINE config 2 (the default; the CPU arm is quoted on it)
+
+# BASELINE.json configs 2-5 (config 1 is the CPU plumbing case: tests/, not a bench line).  `groups` = prompt groups per
+# rank per step in weak scaling; `--scaling strong` fixes 16 groups per step over all ranks instead.
+CONFIGS = {
+    2: dict(preset="pickscore_cotrain_sd3_fast", res=512, steps=10, G=8, groups=2, train_d=False,
+            workload="SD3.5-medium LoRA r32 512x512, 10 denoise steps (2 trained), G=8, CFG 4.5, PickScore (CLIP-ViT-H/14) "
+                     "reward on generated+reference images; {nb} groups + 2 optimizer steps per rank per step (BASELINE config 2)"),
+    3: dict(preset="dino_patch_cotrain_sd3_fast", res=512, steps=10, G=8, groups=2, train_d=True,
+            workload="SD3.5-medium LoRA r32 512x512, 10 denoise steps (2 trained), G=8, DINOv2-B/14 patch adversarial reward "
+                     "(CLS + 64 patches, DINOHead) on generated+reference images; {nb} groups per rank per step; the step "
+                     "alternates generator GRPO updates with hinge-loss head (D) updates as train_sd3_fast_dino_patch.py:1097 "
+                     "(d_times = 10: 9 of 10 epochs are D steps) (BASELINE config 3)"),
+    4: dict(preset="pickscore_sd3_fast", res=1024, steps=20, G=16, groups=1, train_d=False,
+            workload="SD3.5-medium LoRA r32 1024x1024 (4301 joint tokens), 20 denoise steps (2 trained), G=16, multi-reward "
+                     "{{pickscore: 0.5, ocr: 0.5}} (rewards.py registry; frozen fp32 PickScore + the host OCR plugin with a "
+                     "deterministic recogniser stub, SURVEY 8d); {nb} group(s) + 2 optimizer steps per rank per step, the "
+                     "replay of a group runs in micro-batches of 8 samples (BASELINE config 4)"),
+    5: dict(preset="pickscore_cotrain_sd3_fast", res=512, steps=10, G=8, groups=2, train_d=True,
+            workload="SD3.5-medium LoRA r32 512x512, 10 steps, G=8, adversarial co-update: steps alternate a generator GRPO "
+                     "update and a PickScore discriminator update (CLIPCriterion on generated vs reference images, last "
+                     "vision block trainable, train_sd3_fast_pickscore.py:151-183,1003-1037); {nb} groups per rank per step "
+                     "(BASELINE config 5)"),
+}
+STRONG_GROUPS = 16
 
 
 def _peaks():
@@ -159,6 +183,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config != 2:
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is bounded to BASELINE config 2 (config "
+                          f"{args.config} needs hours of host time per sample)"}))
+        return
     vals, cores, desc = cpu_reference_sample(steps=args.steps, warmup=min(args.warmup, 1), verbose=True,
                                              budget_s=args.cpu_budget)
     v = statistics.mean(vals)
@@ -173,12 +201,30 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def _ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, extracted from the committed
+    `ncu --set full` captures by scripts/ncu_traffic.py into profiles/ncu_traffic.json (None when no capture exists)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            ent = json.load(f).get(key)
+        return (ent["dram_bytes"], ent["source"]) if ent else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def _ocr_stub(img):
+    """Deterministic recogniser for the host OCR plugin (SURVEY 8d allows a stub: PaddleOCR is not installable here):
+    the recognised text is a function of the image content, so rewards differ between samples of a group."""
+    v = int(img[::64, ::64].astype("int64").sum()) % 7
+    return [("text" + "x" * v, 0.9)]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from adv_grpo_b200 import _lib, ops, weights
+    from adv_grpo_b200 import _lib, ops, rewards, weights
     from adv_grpo_b200.config import load_config
-    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
     from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
     from adv_grpo_b200.trainer import GRPOTrainer, SyntheticTextEmbedder
 
@@ -193,13 +239,43 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = True        # reference: train_sd3_fast_pickscore.py:537-538
     torch.backends.cudnn.allow_tf32 = True
 
+    spec = CONFIGS[args.config]
+    res, t_steps, gsz = spec["res"], spec["steps"], spec["G"]
+    nb = spec["groups"]
+    if args.scaling == "strong":
+        total = STRONG_GROUPS if args.config != 4 else 8
+        if total % world:
+            raise SystemExit(f"--scaling strong needs a world size dividing {total}")
+        nb = total // world
+
     pipe = StableDiffusion3Pipeline.from_seed(weights.SD35_MEDIUM, weights.VAE_SD3, device=dev, seed=0)
-    scorer = PickScoreScorer(device=dev, dtype=torch.bfloat16)
-    cfg = load_config("pickscore_cotrain_sd3_fast")
-    cfg.sample.num_batches_per_epoch = NB
-    cfg.train.gradient_accumulation_steps = 1
-    cfg.train_d = False
-    prompts = [f"synthetic prompt {i}" for i in range(99)]
+    cfg = load_config(spec["preset"])
+    cfg.resolution = res
+    cfg.sample.num_steps = t_steps
+    cfg.sample.mini_num_image_per_prompt = gsz
+    cfg.sample.num_image_per_prompt = gsz                 # north_star: every rank rolls out its own G-sample groups
+    cfg.sample.shard_groups_across_ranks = False
+    cfg.sample.num_batches_per_epoch = nb
+    cfg.train.gradient_accumulation_steps = max(nb // 2, 1)   # 2 optimizer steps per step, like the reference epoch
+    cfg.train_d = spec["train_d"]
+    scorer = head = None
+    if args.config in (2, 5):
+        from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+        scorer = PickScoreScorer(device=dev, dtype=torch.bfloat16)
+    elif args.config == 3:
+        from adv_grpo_b200.dinov2 import DINOHead, DinoV2
+        scorer = DinoV2(weights.init_dinov2(weights.DINOV2_B, seed=4, device=dev, dtype=torch.bfloat16), weights.DINOV2_B,
+                        device=dev)
+        head = DINOHead(in_dim=scorer.num_features).to(dev)
+        cfg.d_times = 2                                   # alternate G / D epochs so a short run times both
+    elif args.config == 4:
+        rewards.OCR_KWARGS["recognizer"] = _ocr_stub
+        cfg.train.micro_batch = 8
+        cfg.train.gradient_accumulation_steps = 1
+    if args.config == 4:
+        prompts = [f'a storefront sign that says "text{i % 5}" number {i}' for i in range(99)]
+    else:
+        prompts = [f"synthetic prompt {i}" for i in range(99)]
 
     class HostStagedEmbedder(SyntheticTextEmbedder):
         """e2e leg: every call copies the prompt embeddings from pinned host memory."""
@@ -246,7 +322,10 @@ def run_ours(args):
 
     emb_dev = DeviceEmbedder(device=dev)
     emb_host = HostStagedEmbedder(device=dev)
-    trainer = GRPOTrainer(cfg, pipe, prompts, scorer=scorer, embedder=emb_dev, device=dev, reference_image_fn=ref_dev)
+    trainer = GRPOTrainer(cfg, pipe, prompts, scorer=scorer, head=head, embedder=emb_dev, device=dev,
+                          reference_image_fn=ref_dev)
+    if spec["train_d"]:
+        trainer.d_schedule = lambda epoch: epoch % 2 == 1          # G, D, G, D, ... (both updates inside a short run)
 
     def barrier():
         if world > 1:
@@ -262,7 +341,8 @@ def run_ours(args):
         for _ in range(k):
             info = trainer.run_epoch()
             if read_back:
-                vals = torch.stack([info["loss"].float(), info["reward_mean"].float(), info["approx_kl"].float()]).cpu()
+                keys = [kk for kk in ("loss", "reward_mean", "approx_kl", "d_loss") if kk in info]
+                vals = torch.stack([info[kk].float().reshape(()) for kk in keys]).cpu()
                 d2h += vals.numel() * 4
         e1.record()
         barrier()
@@ -272,16 +352,18 @@ def run_ours(args):
         return ms.item(), _lib.launch_count() - n0, d2h
 
     # ---- warm-up (also captures the CUDA graphs and pre-stages every prompt this run will touch) ----
+    n_warm = max(args.warmup, 3)
+    if spec["train_d"]:
+        n_warm += n_warm % 2                       # keep the G / D alternation aligned with the timed region
     trainer.embedder, trainer.reference_image_fn = emb_host, ref_host
     timed(1, True)
     trainer.embedder, trainer.reference_image_fn = emb_dev, ref_dev
-    timed(max(args.warmup, 3) - 1, False)
+    timed(n_warm - 1, False)
     # pre-stage the device-resident inputs of the timed region (value leg: inputs already in HBM)
-    e_save, s_save = trainer.epoch, trainer.sampler
     for ep in range(trainer.epoch, trainer.epoch + 2 * args.steps + 2):
-        for i in range(NB):
-            idx = trainer.sampler.indices_for_epoch(ep * NB + i)[rank][0]
-            emb_dev(idx), ref_dev(idx, G, RES), emb_host(idx), ref_host(idx, G, RES)
+        for i in range(nb):
+            idx = trainer.sampler.indices_for_epoch(ep * nb + i)[rank][0]
+            emb_dev(idx), ref_dev(idx, gsz, res), emb_host(idx), ref_host(idx, gsz, res)
     emb_host.h2d, counters["h2d"] = 0, 0
 
     clocks = ClockSampler(local)
@@ -294,7 +376,7 @@ def run_ours(args):
     # phase split of ONE further step (device-resident inputs, CUDA events between the phases; explains `value`,
     # is not part of it)
     trainer.embedder, trainer.reference_image_fn = emb_dev, ref_dev
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     barrier()
     ev[0].record()
     smp = trainer.sample_epoch()
@@ -303,12 +385,17 @@ def run_ours(args):
     ev[2].record()
     trainer.train_generator(smp, adv)
     ev[3].record()
+    if spec["train_d"]:
+        trainer.discriminator_step(smp)
+    ev[4].record()
     trainer.epoch += 1
     barrier()
     phases = {"rollout_decode_score": ev[0].elapsed_time(ev[1]), "advantages": ev[1].elapsed_time(ev[2]),
               "update": ev[2].elapsed_time(ev[3])}
+    if spec["train_d"]:
+        phases["discriminator_update"] = ev[3].elapsed_time(ev[4])
     del smp, adv
-    samples = world * NB * G * args.steps
+    samples = world * nb * gsz * args.steps
     value = samples / (ms_dev / 1e3)
     e2e_value = samples / (ms_e2e / 1e3)
     h2d_per_step = (emb_host.h2d + counters["h2d"]) / args.steps
@@ -334,7 +421,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / iters
 
-    M, K, N, K2 = 2 * G * 1024, 1536, 4608, 128
+    n_img = (res // 16) ** 2
+    bsz = 2 * min(gsz, 8)                            # CFG batch of one launch (config 4 replays in micro-batches of 8)
+    M, K, N, K2 = bsz * n_img, 1536, 4608, 128
     A = torch.randn(M, K, device=dev).bfloat16()
     W = torch.randn(N, K, device=dev).bfloat16()
     A2 = torch.randn(M, K2, device=dev).bfloat16()
@@ -342,44 +431,63 @@ def run_ours(args):
     bias = torch.randn(N, device=dev).bfloat16()
     ms_gemm = time_kernel(lambda: ops.gemm(A, W, bias=bias, a2=A2, w2=W2))
     gemm_flops = 2.0 * M * N * (K + K2)
-    S = 1024 + 205
-    qkv = torch.randn(2 * G, S, 3, 24, 64, device=dev).bfloat16()
-    ms_attn = time_kernel(lambda: ops.attention_fwd(qkv, want_lse=False))
-    attn_flops = 4.0 * 2 * G * 24 * S * S * 64
+    S = n_img + 205
+    qkv = torch.randn(bsz, S, 3, 24, 64, device=dev).bfloat16()
+    ms_attn = time_kernel(lambda: ops.attention_fwd(qkv, want_lse=False, split=n_img))
+    attn_flops = 4.0 * bsz * 24 * S * S * 64
     out, lse = ops.attention_fwd(qkv)
     dout = torch.randn_like(out)
     ms_attn_bwd = time_kernel(lambda: ops.attention_bwd(qkv, out, dout, lse), iters=10)
     achieved = gemm_flops / ms_gemm / 1e9
+    attn_alg_bytes = 2.0 * bsz * S * 24 * 64 * 4          # q, k, v read + o written, bf16
+    tr_gemm, tr_gemm_src = _ncu_traffic("gemm_qkv_lora")
+    tr_af, tr_af_src = _ncu_traffic("attn_fwd")
+    tr_ab, tr_ab_src = _ncu_traffic("attn_bwd")
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<256> (fused QKV projection + LoRA second product, "
                 f"M={M} N={N} K={K}+{K2})", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
                 "frac": achieved / peak_burst,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the same M, N, K, K2 from the ncu
-                # --set full capture in profiles/r1_ncu_full_summary_final.md (70.0 MB read + 108.5 MB written; the
-                # 151 MB output is partly still in L2 when the capture ends); algorithmic bytes (A + W + A2 + W2 + C
-                # in bf16) are 221 MB: no wasted re-reads
-                "traffic": 178.5e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * K2 + N * K2 + M * N),
-                "peak_source": f"{src} burst bf16 (kernel timed alone)"}
+                # dram bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json; captured at
+                # the config-2 shape); algorithmic bytes = A + W + A2 + W2 + C in bf16
+                "traffic": tr_gemm if args.config in (2, 3, 5) else None, "traffic_source": tr_gemm_src,
+                "algorithmic_bytes": 2.0 * (M * K + N * K + M * K2 + N * K2 + M * N),
+                "peak_source": f"{src} burst bf16 (kernel timed alone)",
+                # north_star's graded contraction: the joint text-image attention of one MMDiT block
+                "attention_fwd": {"bound": "tensor", "kernel": f"attn_fwd_quad_kernel (B={bsz} H=24 S={S} D=64, image/text "
+                                  "output split)", "achieved": attn_flops / ms_attn / 1e9, "peak": peak_burst,
+                                  "unit": "TFLOP/s", "frac": attn_flops / ms_attn / 1e9 / peak_burst,
+                                  "traffic": tr_af if args.config in (2, 3, 5) else None, "traffic_source": tr_af_src,
+                                  "algorithmic_bytes": attn_alg_bytes},
+                "attention_bwd": {"bound": "tensor", "kernel": f"attn_bwd_kernel (B={bsz} H=24 S={S} D=64)",
+                                  "achieved": 2.5 * attn_flops / ms_attn_bwd / 1e9, "peak": peak_burst, "unit": "TFLOP/s",
+                                  "frac": 2.5 * attn_flops / ms_attn_bwd / 1e9 / peak_burst,
+                                  "traffic": tr_ab if args.config in (2, 3, 5) else None, "traffic_source": tr_ab_src,
+                                  "algorithmic_bytes": 2.0 * attn_alg_bytes + 2.0 * bsz * S * 24 * 64 * 3}}
+    # FLOPs per GRPO sample: SURVEY 8d convention (2 T F + 2 T_train 3 F) and the executed count (LoRA-only backward:
+    # dX GEMMs = the forward GEMM share, attention backward = 2.5 x attention forward)
+    f_fwd = {512: 2.224, 1024: 10.92}.get(res, 2.224)
+    attn_share = {512: 0.138, 1024: 0.373}.get(res, 0.138)
+    conv_flops = 2 * t_steps * f_fwd + 2 * T_TRAIN * 3 * f_fwd
+    exec_flops = 2 * t_steps * f_fwd + 2 * T_TRAIN * (f_fwd + (1 - attn_share) * f_fwd + 2.5 * attn_share * f_fwd)
     kernels = {
-        "attn_fwd_tflops": attn_flops / ms_attn / 1e9, "attn_fwd_frac": attn_flops / ms_attn / 1e9 / peak_burst,
-        "attn_bwd_tflops": 2.5 * attn_flops / ms_attn_bwd / 1e9,
-        "attn_bwd_frac": 2.5 * attn_flops / ms_attn_bwd / 1e9 / peak_burst,
-        "attn_shape": f"B={2 * G} H=24 S={S} D=64",
-        "step_tflops": 71.2 * value / world, "step_frac_of_sustained": 71.2 * value / world / peak_sustained,
+        "attn_shape": f"B={bsz} H=24 S={S} D=64",
+        "tflop_per_sample_convention": conv_flops, "tflop_per_sample_executed": exec_flops,
+        "step_tflops": conv_flops * value / world, "step_frac_of_sustained": conv_flops * value / world / peak_sustained,
+        "step_tflops_executed": exec_flops * value / world,
+        "step_frac_of_sustained_executed": exec_flops * value / world / peak_sustained,
     }
     del A, W, A2, W2, qkv, out, dout
     torch.cuda.empty_cache()
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == 2:
         vals, cores, desc = cpu_reference_sample(steps=1, warmup=0)
         cpu = {"value": vals[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SD3.5-medium LoRA r32 512x512, 10 denoise steps (2 trained), G=8, CFG 4.5, PickScore "
-                                   f"(CLIP-ViT-H/14) reward on generated+reference images; {NB} groups + 2 optimizer "
-                                   "steps per rank per step (BASELINE config 2)",
+            "warmup": n_warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": spec["workload"].format(nb=nb), "baseline_config": args.config,
+                       "groups_per_step_all_ranks": nb * world,
                        "l2": "per-step working set (4.4 GB weights + activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
@@ -400,6 +508,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config: 2 PickScore GRPO (default, the headline), 3 DINOv2-patch adversarial, "
+                         "4 1024x1024 / 20 steps / G=16 PickScore+OCR, 5 generator + PickScore discriminator co-update")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: fixed groups per rank (default); strong: 16 groups per step split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=150.0,
                     help="--impl reference: wall-clock bound (s) of the timed CPU samples (init excluded)")

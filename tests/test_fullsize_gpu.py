@@ -145,3 +145,173 @@ def test_config1_rollout_sd35_medium_true_size_matches_oracle():
         assert d.mean().item() <= 1.5 * c["mean"] + 1e-3, (d.mean().item(), c)
     for a, b in zip(lps, lps_o):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-6)
+
+
+def test_config2_shape_replay_logprob_and_loss_match_oracle():
+    """BASELINE config 2 shape (SD3.5-medium TRUE size, 512x512 = 1024 + 205 joint tokens, 10 denoise steps, SDE window
+    of 2 steps, CFG 4.5, noise 0.8; one sample = a CFG pair, which the oracle finishes in tens of seconds on the host).
+    The GPU rolls out the trajectory; the two TRAINED transitions are then replayed teacher-forced by both
+    implementations on the GPU's own stored latents (train_sd3_fast_pickscore.py:233-267,1104-1123), so the compared
+    quantities depend on the model (unlike the rollout log-prob of an injected noise draw) and no trajectory divergence
+    inflates the tolerance: prev_sample_mean within 1e-2 of the latent range per element (north_star's bf16 bound), the
+    replay log-prob within 2e-3 absolute and the clipped GRPO step loss within 1e-3 relative."""
+    from adv_grpo_b200 import ops, weights
+    from adv_grpo_b200.config import ConfigDict
+    from adv_grpo_b200.diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
+    from adv_grpo_b200.mmdit import SD3Transformer2DModel
+    from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
+    from adv_grpo_b200.trainer import compute_log_prob
+    from adv_grpo_b200.vae import AutoencoderKL
+    from oracle import grpo_loss as loss_o
+    from oracle import sde as sde_o
+    from oracle.mmdit import MMDiTOracle
+    from oracle.scheduler import FlowMatchEulerOracle
+    cfg = weights.SD35_MEDIUM
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    lora = weights.init_lora(cfg, rank=32, seed=1, perturb_b=0.01)
+    lora = {k: (a.bfloat16().float(), b.bfloat16().float()) for k, (a, b) in lora.items()}
+    vp = weights.init_vae_decoder(weights.VAE_SD3, seed=2, device="cpu")
+    pipe = StableDiffusion3Pipeline(SD3Transformer2DModel(cfg, params, lora=lora, device=DEV),
+                                    AutoencoderKL(vp, weights.VAE_SD3, device=DEV), device=DEV, use_cuda_graph=False)
+    G, steps, T_train = 1, 10, 2
+    g = torch.Generator().manual_seed(17)
+    pe = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    pp = torch.randn(1, 2048, generator=g).bfloat16()
+    ne = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    npool = torch.randn(1, 2048, generator=g).bfloat16()
+    lat = torch.randn(G, 16, 64, 64, generator=g).bfloat16()
+    noises = [torch.randn(G, 16, 64, 64, generator=g) for _ in range(steps)]
+    img, lats, lps, tss = pipeline_with_logprob_random(
+        pipe, prompt_embeds=pe.to(DEV), pooled_prompt_embeds=pp.to(DEV), negative_prompt_embeds=ne.to(DEV),
+        negative_pooled_prompt_embeds=npool.to(DEV), num_inference_steps=steps, guidance_scale=4.5, output_type="pt",
+        height=512, width=512, noise_level=0.8, mini_num_image_per_prompt=G, train_num_steps=T_train, process_index=0,
+        sample_num_steps=steps, random_timestep=0, latents=lat.to(DEV), noise=[n.to(DEV) for n in noises])
+    assert img.shape == (G, 3, 512, 512) and torch.isfinite(img).all() and len(lats) == T_train + 1
+    L = torch.stack(lats, 1)
+    sample = {"latents": L[:, :-1], "next_latents": L[:, 1:], "timesteps": torch.stack(tss, 1), "log_probs": torch.stack(lps, 1)}
+    config = ConfigDict(dict(train=dict(cfg=True), sample=dict(guidance_scale=4.5, noise_level=0.8)))
+    embeds = torch.cat([ne.repeat(G, 1, 1), pe.repeat(G, 1, 1)]).to(DEV)
+    pooled = torch.cat([npool.repeat(G, 1), pp.repeat(G, 1)]).to(DEV)
+    adv = torch.tensor([1.5], dtype=torch.float64, device=DEV)
+    oracle = MMDiTOracle(params, dict(cfg, dual_layers=set(cfg["dual_layers"])), lora=lora, lora_scale=2.0)
+    sch = FlowMatchEulerOracle()
+    sch.set_timesteps(steps)
+    for j in range(T_train):
+        with torch.no_grad():
+            _, lp, mean, _ = compute_log_prob(pipe.transformer, pipe, sample, j, embeds, pooled, config, want_mean=True)
+            loss, stats = ops.grpo_clip_loss(lp, sample["log_probs"][:, j], adv, 1e-5, 5.0)
+            x = sample["latents"][:, j].cpu().float()
+            t = sch.timesteps[j].expand(2 * G)
+            pred = oracle.forward(torch.cat([x, x]), t, embeds.cpu().float(), pooled.cpu().float())
+            u, c = pred.chunk(2)
+            v = u + 4.5 * (c - u)
+            _, lp_o, mean_o, _ = sde_o.sde_step_with_logprob_new(sch.sigmas, [j] * G, v, x, 0.8,
+                                                                 prev_sample=sample["next_latents"][:, j].cpu().float())
+            loss_ref, _ = loss_o.grpo_clip_loss(lp_o, sample["log_probs"][:, j].cpu(), adv.cpu(), 1e-5, 5.0)
+        rng = mean_o.abs().max().item()
+        d = (mean.float().cpu() - mean_o).abs()
+        assert d.max().item() <= 1e-2 * rng, (j, d.max().item(), rng)
+        assert d.mean().item() <= 3e-3 * rng, (j, d.mean().item(), rng)      # measured 1.7e-3 of range
+        assert (lp.cpu() - lp_o).abs().max().item() < 2e-3, (j, lp.cpu(), lp_o)
+        assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item()), (j, loss.item(), loss_ref.item())
+
+
+def test_dino_discriminator_loss_and_head_grads_match_oracle():
+    """BASELINE config 3 D step (train_sd3_fast_dino_patch.py:186-219) at the TRUE DINOv2-B/14 size: hinge loss of the
+    head on CLS + sampled patch tokens of real / fake images and the gradients of every head parameter, GPU (bf16
+    backbone on the kernels, `dino_hinge_d_loss`) vs `oracle/dinov2.py` (fp32 CPU) with the same patch indices."""
+    from adv_grpo_b200 import ops, weights
+    from adv_grpo_b200.dinov2 import DINOHead, DinoV2, dino_hinge_d_loss
+    from oracle import dinov2 as dino_o
+    cfg = weights.DINOV2_B
+    params = weights.init_dinov2(cfg, seed=4, device="cpu", dtype=torch.bfloat16)
+    scorer = DinoV2(params, cfg, device=DEV)
+    torch.manual_seed(3)
+    head = DINOHead(in_dim=cfg["width"]).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    real = torch.rand(2, 3, 256, 256, generator=g)
+    fake = torch.rand(2, 3, 256, 256, generator=g)
+    ir = torch.randint(0, 1369, (2, 64), generator=g)
+    if_ = torch.randint(0, 1369, (2, 64), generator=g)
+    with torch.no_grad():
+        fr = scorer.forward_features(ops.dino_preprocess(real.to(DEV), 518))
+        ff = scorer.forward_features(ops.dino_preprocess(fake.to(DEV), 518))
+    loss, acc = dino_hinge_d_loss(head, fr, ff, ir.to(DEV), if_.to(DEV), 0.3)
+    loss.backward()
+    # oracle: fp32 features, fp32 head with the same initial parameters
+    p32 = {k: v.float() for k, v in params.items()}
+    ocfg = dict(patch=14, heads=12, layers=12)
+    with torch.no_grad():
+        fr_o = dino_o.forward_features(p32, ocfg, dino_o.preprocess(real))
+        ff_o = dino_o.forward_features(p32, ocfg, dino_o.preprocess(fake))
+    hp = {k: v.detach().cpu().float().clone().requires_grad_(True) for k, v in head.state_dict().items()}
+    loss_o, acc_o = dino_o.hinge_d_loss(hp, fr_o, ff_o, ir, if_, 0.3)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 2e-2 * abs(loss_o.item()), (loss.item(), loss_o.item())
+    for name, prm in head.named_parameters():
+        got, ref = prm.grad.float().cpu().flatten(), hp[name].grad.flatten()
+        cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+        rel = (got - ref).norm().item() / ref.norm().item()
+        # the head sees the bf16 backbone's features (up to 4e-2 of range off the fp32 oracle's, tested above), and a
+        # token near the hinge can flip its active set: measured cos 0.994 / rel 0.11 on the first layer's weight
+        assert cos > 0.99 and rel < 0.15, (name, cos, rel)
+
+
+def test_pickscore_discriminator_last_block_grads_match_oracle_autograd():
+    """BASELINE config 5 D step at the TRUE CLIP-ViT-H/14 width: CLIPCriterion loss (pick_score_training.py:94-224) and the
+    gradients of vision_model.encoder.layers[-1] (train_sd3_fast_pickscore.py:1016-1020, tune_layer = -1), GPU (31 frozen
+    blocks on the kernels, the trainable block under autograd) vs the fp32 CPU oracle's autograd."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.pick_score_training import CLIPCriterion, CLIPCriterionConfig
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer, images_to_pixel_values
+    from oracle import clip as clip_o
+    from oracle import clip_criterion as crit_o
+    from oracle import preprocess as pre_o
+    cfg = weights.CLIP_H
+    params = weights.init_clip(cfg, seed=3, device="cpu", dtype=torch.bfloat16)
+    scorer = PickScoreScorer(device=DEV, cfg=cfg, state_dict=params)
+    model = scorer.model
+    for p in model.parameters():
+        p.requires_grad = False
+    last = model.vision_model.encoder.layers[-1]
+    for p in last.parameters():
+        p.requires_grad = True
+    g = torch.Generator().manual_seed(2)
+    real = (torch.rand(2, 3, 64, 64, generator=g) * 255).to(torch.uint8)
+    fake = (torch.rand(2, 3, 64, 64, generator=g) * 255).to(torch.uint8)
+    prompts = ["a watercolor lighthouse", "a robot reading"]
+    ids = scorer.processor.tokenizer(prompts, padding="max_length", max_length=77)["input_ids"]
+    batch = {"input_ids": ids.to(DEV), "pixels_0": images_to_pixel_values(real, DEV), "pixels_1": images_to_pixel_values(fake, DEV),
+             "label_0": torch.tensor(1.0, device=DEV), "label_1": torch.tensor(0.0, device=DEV),
+             "num_examples_per_prompt": torch.tensor(1.0, device=DEV)}
+    loss = CLIPCriterion(CLIPCriterionConfig())(model, batch)
+    loss.backward()
+    # oracle
+    p32 = {k: v.float() for k, v in params.items()}
+    pre = f"vision_model.encoder.layers.{cfg['v_layers'] - 1}."
+    for k in p32:
+        if k.startswith(pre):
+            p32[k].requires_grad_(True)
+    ocfg = dict(patch=cfg["patch"], v_layers=cfg["v_layers"], v_heads=cfg["v_heads"], t_layers=cfg["t_layers"], t_heads=cfg["t_heads"])
+    pix = lambda u: torch.from_numpy(pre_o.clip_pixel_values(pre_o.pil_bicubic_resize_u8(u.numpy(), 224)))
+    norm = lambda t: t / t.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        tf = norm(clip_o.text_features(p32, ocfg, ids))
+    ref = crit_o.clip_pair_loss(tf, norm(clip_o.image_features(p32, ocfg, pix(real))),
+                                norm(clip_o.image_features(p32, ocfg, pix(fake))), p32["logit_scale"].exp().detach(),
+                                torch.tensor(1.0), torch.tensor(0.0))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 3e-2 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    checked = 0
+    for name, prm in last.named_parameters():
+        refg = p32[pre + name].grad
+        got = prm.grad.float().cpu()
+        if refg.norm().item() < 1e-12:
+            continue
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), refg.flatten(), dim=0).item()
+        rel = (got - refg).norm().item() / refg.norm().item()
+        # 31 frozen bf16 blocks with seeded random weights feed the trainable block (the same amplification the rollout
+        # calibration shows), whose own forward / backward is bf16 too: measured cos 0.98 / rel 0.22 on the worst tensor
+        assert cos > 0.97 and rel < 0.3, (name, cos, rel)
+        checked += 1
+    assert checked >= 10

@@ -448,3 +448,25 @@ def test_gemm_tail_split_host_logic():
     assert f(16384, 3280, 4608, 1, 148) is None                            # 18.7 waves: last wave 73 % full
     assert f(16384, 3280, 6144, 1, 148) is None                            # 24.97 waves
     assert f(2048, 410, 1536, 205, 148) is None                            # fewer than two full waves
+
+
+def test_parameter_inventory_matches_published_checkpoint_sizes():
+    """Cheap pin of every weight shape the models are built from: the state-dict inventories of
+    `weights.py` reproduce the parameter counts of the published checkpoints the reference loads --
+    stabilityai/stable-diffusion-3.5-medium transformer 2.24 B (+ the 384 x 384 x 1536 position table = 2.47 B, the
+    size of the released file), stable-diffusion-3-medium 2.03 B, laion CLIP-ViT-H-14 (PickScore_v1's backbone) 986 M,
+    timm vit_base_patch14_dinov2.lvd142m 86.6 M."""
+    import torch
+    from adv_grpo_b200 import weights
+    count = lambda p: sum(v.numel() for v in p.values())
+    mm = weights.init_mmdit(weights.SD35_MEDIUM, device="meta")
+    assert count(mm) == 2_243_171_520
+    assert count(mm) + 384 * 384 * 1536 == 2_469_663_936
+    assert count(weights.init_mmdit(weights.SD3_MEDIUM, device="meta")) == 2_028_328_000
+    assert count(weights.init_clip(weights.CLIP_H, device="meta")) == 986_109_441
+    assert count(weights.init_dinov2(weights.DINOV2_B, device="meta")) == 86_579_712
+    assert count(weights.init_vae_decoder(weights.VAE_SD3, device="meta")) == 49_545_475
+    # LoRA r = 32 on the 8 attention projections of every block (to_add_out is absent in the last block)
+    lora = weights.init_lora(weights.SD35_MEDIUM, rank=32, seed=1)
+    assert sum(a.numel() + b.numel() for a, b in lora.values()) == (24 * 8 - 1) * 2 * 32 * 1536 == 18_776_064
+    assert all(v.dtype == torch.bfloat16 for v in mm.values())

@@ -83,9 +83,10 @@ def test_mmdit_backward_matches_oracle_autograd():
                 continue
             cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), refg.flatten(), dim=0).item()
             worst = min(worst, cos - 1)
-            assert cos > 0.99, (name, cos)
             rel = (got.float().cpu() - refg).norm().item() / refg.norm().item()
-            assert rel < 0.1, (name, rel)
+            # bf16 forward + bf16 gradients through 3 blocks against the fp32 oracle's autograd
+            assert cos > 0.999, (name, cos, rel)
+            assert rel < 3e-2, (name, cos, rel)
 
 
 def test_mmdit_dual_gemm_matches_separate_launches():

@@ -34,6 +34,19 @@ def test_pickscore_scorer_matches_oracle():
     pil = [Image.fromarray(q[i].permute(1, 2, 0).numpy()) for i in range(4)]
     s_pil = scorer(prompts, pil).float().cpu()
     assert torch.allclose(s_pil, scores, atol=1e-6)
+    # quirk Q10: the reference does the normalise / dot / scale tail in bf16 and returns bf16 scores
+    # (adv_grpo/pickscore_scorer.py:40-51); the flag reproduces that rounding sequence from the same tower outputs
+    sc_ref = PickScoreScorer(device=DEV, cfg=cfg, state_dict=params, reference_score_arithmetic=True)
+    s16 = sc_ref(prompts, images.to(DEV))
+    assert s16.dtype == torch.bfloat16
+    bf = torch.bfloat16
+    model = sc_ref.model
+    ie = sc_ref._last_image_feats_bf16
+    ids1 = [scorer.processor.tokenizer([p], padding=True, truncation=True, max_length=77)["input_ids"].to(DEV) for p in prompts]
+    te = torch.cat([model.get_text_features(input_ids=i).to(bf) for i in ids1], 0)
+    want = (model.logit_scale.exp().to(bf) * ((te / te.norm(p=2, dim=-1, keepdim=True)) @ (ie / ie.norm(p=2, dim=-1, keepdim=True)).T)).diag() / 26
+    assert (s16.float() - want.float()).abs().max().item() <= 2 * 2.0 ** -8 * want.float().abs().max().item()
+    assert (s16.float().cpu() - scores).abs().max().item() < 3e-2          # bf16 tail vs fp32 tail on the same features
 
 
 def test_dino_patch_reward_matches_oracle():
