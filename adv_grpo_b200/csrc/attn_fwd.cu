@@ -1180,6 +1180,409 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pair kernel (head_dim 64, non-causal; the MMDiT joint-attention shape and the default there): ONE persistent CTA per
+// SM owns TWO 128-row query tiles of one (sample, head) and runs their softmaxes on two groups of eight quad-layout
+// warps (G0: warps 0-7, G1: warps 8-15; S/P/O of tile t in TMEM columns [256 t, 256 t + 256)).
+//
+// Why (measured, profiles/r2_attn_pair_*): K / V tiles are shared by the two query tiles (half the shared-memory and L2
+// traffic per FLOP and half the utility warps polling barriers per SM).  Two experiments on top of it were measured
+// SLOWER and removed: an explicit "exp token" (named barriers) that forced the two groups into antiphase -- one in its
+// MUFU-bound exp phase while the other loads S / publishes P -- 682 vs 757 TFLOP/s at B=16 H=24 S=1229; and a
+// stale-max fast path (exponentials of tile j > 0 from the previous max, the row max only checked afterwards: no quad
+// shuffles on the common path, but S must stay live for a possible redo -> spills) 680 TFLOP/s.  3-stage K and V rings,
+// Q double-buffered across work items, O staged in the finished item's Q buffers and written by TMA.
+struct PairCfg {
+  static constexpr int kTileBytes = BQ * 64 * 2;                       // 16 KB
+  static constexpr int kKStages = 3, kVStages = 3;
+  static constexpr int kSmemTiles = (4 + kKStages + kVStages) * kTileBytes;   // 4 Q buffers (2 items x 2 tiles)
+  static constexpr int kNumBars = 4 + 2 * kKStages + 2 * kVStages + 10;
+  static constexpr int kSmemBytes = kSmemTiles + 1024 + 8 * kNumBars + 16;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kGroupWarps = 8;
+  static constexpr int kSoftmaxWarps = 16;
+  static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;            // 640
+  // 640 threads x 96 registers at launch = 512 x kRegsSoftmax + 128 x kRegsUtility
+  static constexpr int kRegsSoftmax = 112;
+  static constexpr int kRegsUtility = 32;
+};
+
+template <int EMU>
+__global__ void __launch_bounds__(PairCfg::kThreads, 1)
+attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_o,
+                     const __grid_constant__ CUtensorMap tmap_o2, const Params p, const int n_items, const int npair,
+                     const int tma_out, const int flags) {
+  using C = PairCfg;
+  constexpr int D = 64;
+  constexpr int KS = C::kKStages, VS = C::kVStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemTiles);
+  // barrier indices (8 bytes each)
+  constexpr int I_Q_FULL = 0, I_Q_EMPTY = 2, I_K_FULL = 4, I_K_EMPTY = I_K_FULL + KS, I_V_FULL = I_K_EMPTY + KS,
+                I_V_EMPTY = I_V_FULL + VS, I_S_FULL = I_V_EMPTY + VS, I_P_FULL = I_S_FULL + 2, I_PV_DONE = I_P_FULL + 2,
+                I_S_FREE = I_PV_DONE + 2, I_O_READY = I_S_FREE + 2;
+  static_assert(I_O_READY + 2 == C::kNumBars, "barrier count");
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.S;
+  const int H = p.H;
+
+  auto item_q0 = [&](int it) { return (it % npair) * (2 * BQ); };
+  auto item_h = [&](int it) { return (it / npair) % H; };
+  auto item_b = [&](int it) { return it / (npair * H); };
+  const int nkv = (S + BKV - 1) / BKV;                         // non-causal: every item walks all K/V tiles
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[I_Q_FULL + i], 1);
+      mbar_init(&bars[I_Q_EMPTY + i], 1);
+      mbar_init(&bars[I_S_FULL + i], 1);
+      mbar_init(&bars[I_P_FULL + i], C::kGroupWarps * 32);
+      mbar_init(&bars[I_PV_DONE + i], 1);
+      mbar_init(&bars[I_S_FREE + i], C::kGroupWarps * 32);
+      mbar_init(&bars[I_O_READY + i], C::kGroupWarps * 32);
+    }
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&bars[I_K_FULL + i], 1);
+      mbar_init(&bars[I_K_EMPTY + i], 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(&bars[I_V_FULL + i], 1);
+      mbar_init(&bars[I_V_EMPTY + i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == C::kSoftmaxWarps + 1) {
+    tmem_alloc(tmem_base_smem, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  pdl_trigger();
+  pdl_wait();
+
+  auto pin = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+  const uint32_t bar0 = pin(smem_u32(bars));
+  const uint32_t q_sm = pin(smem_u32(smem));                   // 4 Q tiles: [item parity][tile]
+  const uint32_t k_sm = q_sm + 4 * C::kTileBytes, v_sm = k_sm + KS * C::kTileBytes;
+  auto B = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
+
+  if (warp >= C::kSoftmaxWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsUtility));
+    // warp-uniform loops, only the TMA / tcgen05 instructions under elect_one() (see attn_fwd_quad_kernel)
+    if (warp == C::kSoftmaxWarps) {
+      // ============================== TMA producer ==============================
+      if (elect_one()) prefetch_tmap(&tmap);
+      int k_item = blockIdx.x, k_j = 0, k_n = 0, k_g = 0;      // K cursor: item, tile in item, local item index, global tile
+      auto advance_k = [&]() {
+        if (k_item >= n_items) return;
+        if (k_j == 0) {
+          const int qb = k_n & 1;
+          mbar_wait_a(B(I_Q_EMPTY + qb), ((k_n >> 1) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(B(I_Q_FULL + qb), 2 * C::kTileBytes);
+            // rows past S (a dead second tile when the tile count is odd) are zero-filled by the TMA unit
+            for (int t = 0; t < 2; ++t)
+              tma_load_4d_a(q_sm + (2 * qb + t) * C::kTileBytes, &tmap, B(I_Q_FULL + qb), 0, 0 * H + item_h(k_item),
+                            item_q0(k_item) + t * BQ, item_b(k_item));
+          }
+        }
+        const int st = k_g % KS;
+        mbar_wait_a(B(I_K_EMPTY + st), ((k_g / KS) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(B(I_K_FULL + st), C::kTileBytes);
+          tma_load_4d_a(k_sm + st * C::kTileBytes, &tmap, B(I_K_FULL + st), 0, 1 * H + item_h(k_item), k_j * BKV,
+                        item_b(k_item));
+        }
+        ++k_g;
+        if (++k_j == nkv) {
+          k_j = 0;
+          ++k_n;
+          k_item += gridDim.x;
+        }
+      };
+      for (int i = 0; i < KS - 1; ++i) advance_k();
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int h = item_h(item), b = item_b(item);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          advance_k();                                         // K runs KS - 1 tiles ahead of V
+          const int st = g % VS;
+          mbar_wait_a(B(I_V_EMPTY + st), ((g / VS) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(B(I_V_FULL + st), C::kTileBytes);
+            tma_load_4d_a(v_sm + st * C::kTileBytes, &tmap, B(I_V_FULL + st), 0, 2 * H + h, j * BKV, b);
+          }
+        }
+      }
+    } else if (warp == C::kSoftmaxWarps + 1) {
+      // ============================== QK issuer: S_t(g) = Q_t K_g^T, t = 0, 1 ==============================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
+      const uint64_t q_d0 = make_smem_desc_sw128(q_sm, 16, 1024);
+      const uint64_t k_d0 = make_smem_desc_sw128(k_sm, 16, 1024);
+      int g = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int qb = n & 1;
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % KS;
+          const uint64_t k_d = k_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (g > 0) mbar_wait_a(B(I_S_FREE + t), (g - 1) & 1);       // S_t(g-1) is in the softmax warps' registers
+            if (t == 0) {
+              if (j == 0) mbar_wait_a(B(I_Q_FULL + qb), (n >> 1) & 1);
+              mbar_wait_a(B(I_K_FULL + st), (g / KS) & 1);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t q_d = q_d0 + (uint64_t)((2 * qb + t) * (C::kTileBytes >> 4));
+              const uint32_t s_tmem = tmem_base + 256 * t;
+              mma_ss_c<false>(s_tmem, q_d, k_d, idesc_qk);
+              mma_ss_c<true>(s_tmem, q_d + 2, k_d + 2, idesc_qk);
+              mma_ss_c<true>(s_tmem, q_d + 4, k_d + 4, idesc_qk);
+              mma_ss_c<true>(s_tmem, q_d + 6, k_d + 6, idesc_qk);
+              mma_commit_a(B(I_S_FULL + t));
+              if (t == 1) {
+                mma_commit_a(B(I_K_EMPTY + st));
+                // last QK of the item read both Q tiles; with the TMA-store epilogue the Q buffers double as the O
+                // staging tiles and are released by the store warp instead
+                if (j == nkv - 1 && !tma_out) mma_commit_a(B(I_Q_EMPTY + qb));
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (warp == C::kSoftmaxWarps + 2) {
+      // ============================== PV issuer: O_t += P_t(g) V_g (P read from TMEM) ==============================
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+      const uint64_t v_d0 = make_smem_desc_sw128(v_sm, BKV * 128, 1024);
+      int g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int st = g % VS;
+          const uint64_t v_d = v_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait_a(B(I_P_FULL + t), g & 1);
+            if (t == 0) mbar_wait_a(B(I_V_FULL + st), (g / VS) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t p_tmem = tmem_base + 256 * t + 128, o_tmem = tmem_base + 256 * t + 192;
+              if (j > 0) mma_ts_c<true>(o_tmem, p_tmem, v_d, idesc_pv);
+              else mma_ts_c<false>(o_tmem, p_tmem, v_d, idesc_pv);
+#pragma unroll
+              for (int k = 1; k < BKV / 16; ++k) mma_ts_c<true>(o_tmem, p_tmem + k * 8, v_d + (uint64_t)(k * 128), idesc_pv);
+              mma_commit_a(B(I_PV_DONE + t));
+              if (t == 1) mma_commit_a(B(I_V_EMPTY + st));
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (tma_out) {
+      // ============================== O store: staged tiles (Q buffers of the finished item) -> global by TMA ==========
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int qb = n & 1;
+        const int h = item_h(item), b = item_b(item);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait_a(B(I_O_READY + t), n & 1);
+          if (elect_one()) {
+            const int q0 = item_q0(item) + t * BQ;             // a tile fully past S is clipped away by the TMA unit
+            if (p.out2 == nullptr || q0 < p.S_split) tma_store_4d_a(&tmap_o, q_sm + (2 * qb + t) * C::kTileBytes, 0, h, q0, b);
+            else tma_store_4d_a(&tmap_o2, q_sm + (2 * qb + t) * C::kTileBytes, 0, h, q0 - p.S_split, b);
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          tma_store_wait_read();                               // both staged tiles have been read: reload the Q buffers
+          mbar_arrive_a(B(I_Q_EMPTY + qb));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== softmax / epilogue: group t = warp / 8 owns query tile t ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsSoftmax));
+    const int t = warp >> 3;
+    const int wl = warp & 7;
+    const int lane0 = (wl & 3) * 32 + (wl >> 2) * 16;         // first TMEM lane (= tile row) of this warp's 16 rows
+    const int row0 = lane0 + (lane >> 2);                      // this thread: rows row0 and row0 + 8
+    const int cq = lane & 3;                                   // columns 8k + 2 cq + {0, 1}
+    const uint32_t s_tmem = pin(tmem_base + 256 * t + (static_cast<uint32_t>(lane0) << 16));
+    const uint32_t p_tmem = s_tmem + 128;
+    const uint32_t o_tmem = s_tmem + 192;
+    const uint32_t a_s_full = B(I_S_FULL + t), a_p_full = B(I_P_FULL + t), a_pv_done = B(I_PV_DONE + t),
+                   a_s_free = B(I_S_FREE + t), a_o_ready = B(I_O_READY + t);
+    const float sl2 = p.scale_log2;
+    const float2 sc2 = make_float2(sl2, sl2);
+    constexpr float kNegBig = -1.0e30f;                        // finite "-inf" for the running max: no special cases
+    auto finish_item = [&](int item, int n, const float2 (&l2)[2], const float (&m)[2]) {
+      const int h = item_h(item), b = item_b(item);
+      const int q_idx0 = item_q0(item) + t * BQ + row0;
+      float inv_l[2], lse2[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float l = l2[r].x + l2[r].y;
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        inv_l[r] = l > 0.f ? __frcp_rn(l) : 0.f;
+        lse2[r] = (m[r] + __log2f(l)) * 0.6931471805599453f;
+      }
+      const uint32_t stage = q_sm + (2 * (n & 1) + t) * C::kTileBytes;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[16];                                        // o[4k + 2r + c] = O[row0 + 8r][32 hh + 8k + 2cq + c]
+        tmem_ld_16x256b_x4(o_tmem + 32 * hh, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = row0 + 8 * r;
+          if (tma_out) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sts_u32(stage + row * 128 + (((4 * hh + k) ^ (row & 7)) << 4) + 4 * cq,
+                      pack_bf16(__uint_as_float(o[4 * k + 2 * r]) * inv_l[r], __uint_as_float(o[4 * k + 2 * r + 1]) * inv_l[r]));
+          } else {
+            const int q_idx = q_idx0 + 8 * r;
+            if (q_idx < S) {
+              __nv_bfloat16* orow;
+              if (p.out2 == nullptr) orow = p.out + (((int64_t)b * S + q_idx) * H + h) * D;
+              else if (q_idx < p.S_split) orow = p.out + (((int64_t)b * p.S_split + q_idx) * H + h) * D;
+              else orow = p.out2 + (((int64_t)b * (S - p.S_split) + (q_idx - p.S_split)) * H + h) * D;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint32_t*>(orow + 32 * hh + 8 * k + 2 * cq) =
+                    pack_bf16(__uint_as_float(o[4 * k + 2 * r]) * inv_l[r], __uint_as_float(o[4 * k + 2 * r + 1]) * inv_l[r]);
+            }
+          }
+        }
+      }
+      tc_fence_before();      // O is in registers: orders the TMEM reads before the next PV(0) (issued after p_full)
+      if (tma_out) {
+        fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA store
+        mbar_arrive_a(a_o_ready);
+      }
+      if (p.lse && cq == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+          if (q_idx0 + 8 * r < S) p.lse[((int64_t)b * H + h) * S + q_idx0 + 8 * r] = lse2[r];
+      }
+    };
+
+    int g = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      float m[2] = {kNegBig, kNegBig};                         // running max (scaled, log2 domain)
+      float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // running denominators (this thread's columns)
+      for (int j = 0; j < nkv; ++j, ++g) {
+        mbar_wait_a(a_s_full, g & 1);
+        tc_fence_after();
+        uint32_t sa[32], sb[32];                               // s?[4k + 2r + c] = S[row0 + 8r][(64 if B) + 8k + 2cq + c]
+        tmem_ld_16x256b_x8(s_tmem, sa);
+        tmem_ld_16x256b_x8(s_tmem + 64, sb);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_a(a_s_free);
+        const int lim = S - j * BKV;                           // columns >= lim are past the sequence end
+        if (lim < BKV) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int col = 8 * k + 2 * cq + c;
+              if (col >= lim) { sa[4 * k + c] = 0xff800000u; sa[4 * k + 2 + c] = 0xff800000u; }          // -inf
+              if (col + 64 >= lim) { sb[4 * k + c] = 0xff800000u; sb[4 * k + 2 + c] = 0xff800000u; }
+            }
+        }
+        float alpha[2];
+        float2 nm2[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float mx0 = kNegBig, mx1 = kNegBig;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[4 * k + 2 * r]), __uint_as_float(sa[4 * k + 2 * r + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sb[4 * k + 2 * r]), __uint_as_float(sb[4 * k + 2 * r + 1])));
+          }
+          float mx = fmaxf(mx0, mx1);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float mn = fmaxf(m[r], mx * sl2);
+          if (mn - m[r] <= kRescaleThreshold) mn = m[r];       // lazy rescale (never taken on the first tile: m = -1e30)
+          alpha[r] = ex2(m[r] - mn);                           // 1 when the max is kept, 0 on the first tile
+          nm2[r] = make_float2(-mn, -mn);
+          m[r] = mn;
+        }
+        // ---- p = exp2(s * scale - m), bf16 pairs; does not depend on PV(g-1) ----
+        uint32_t pk[32];                                       // pk[2k + r] = P[row0 + 8r][cols 8k + 2cq, +1], k < 16
+        float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const uint32_t(&sv)[32] = hb ? sb : sa;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[4 * k + 2 * r]), __uint_as_float(sv[4 * k + 2 * r + 1])),
+                                          sc2, nm2[r]);
+              float2 e;
+              if ((2 * k + r) % 4 < EMU) {
+                e = ex2_poly2(x);
+              } else {
+                e.x = ex2(x.x);
+                e.y = ex2(x.y);
+              }
+              sum2[r] = __fadd2_rn(sum2[r], e);
+              pk[16 * hb + 2 * k + r] = pack_bf16(e.x, e.y);
+            }
+        }
+        // PV(g-1) reads P(g-1) from the columns P(g) overwrites; O may only be rescaled between PV(g-1) and PV(g).
+        // For the first tile of an item the epilogue of the previous item already consumed that phase.
+        if (j > 0) {
+          mbar_wait_a(a_pv_done, (g - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[16];                                  // o[4k + 2r + c] = O[row0 + 8r][32 hh + 8k + 2cq + c]
+              tmem_ld_16x256b_x4(o_tmem + 32 * hh, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha[(i >> 1) & 1]);
+              tmem_st_16x256b_x4(o_tmem + 32 * hh, o);
+            }
+          }
+        }
+        tmem_st_16x128b_x16(p_tmem, pk);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l2[r] = __ffma2_rn(l2[r], make_float2(alpha[r], alpha[r]), sum2[r]);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_a(a_p_full);
+      }
+      // ---- epilogue (the QK warp is already computing S of the next item) ----
+      mbar_wait_a(a_pv_done, (g - 1) & 1);
+      tc_fence_after();
+      finish_item(item, n, l2, m);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::kSoftmaxWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 long long* g_attn_trace = nullptr;   // debug: set by advgrpo_debug_set_attn_trace; consumed by dispatch variant 19
 
 template <int EMU, bool TRACE = false>
@@ -1234,6 +1637,61 @@ int launch_quad(const void* qkv, void* out, void* out2, int64_t S_split, float* 
   }
   ADVGRPO_CUDA_CALL(launch_chain(attn_fwd_quad_kernel<EMU, TRACE>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmap,
                                  tmap_o, tmap_o2, p, (int)items, nqt, tma_out));
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+template <int EMU>
+int launch_pair(const void* qkv, void* out, void* out2, int64_t S_split, float* lse, int64_t B, int64_t S, int64_t H,
+                float scale, int flags, cudaStream_t st) {
+  using C = PairCfg;
+  CUtensorMap tmap;
+  const uint64_t dims[4] = {64, (uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+  const uint64_t strides[4] = {0, 64 * 2, (uint64_t)(3 * H * 64) * 2, (uint64_t)(S * 3 * H * 64) * 2};
+  const uint32_t box[4] = {64, 1, BQ, 1};
+  int rc = make_tmap_bf16(&tmap, qkv, 4, dims, strides, box, true);
+  if (rc != ADVGRPO_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_pair_kernel<EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  Params p;
+  p.out = (__nv_bfloat16*)out;
+  p.out2 = (__nv_bfloat16*)out2;
+  p.S_split = (int)S_split;
+  p.lse = lse;
+  p.S = (int)S;
+  p.H = (int)H;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = 0;
+  p.park = 0;
+  p.bias = nullptr;
+  p.trace = nullptr;
+  const int nqt = (int)((S + BQ - 1) / BQ);
+  const int npair = (nqt + 1) / 2;
+  const int64_t items = (int64_t)npair * H * B;
+  ADVGRPO_CHECK_ARG(items < (int64_t)1 << 30, "attn_fwd: too many work items");
+  int grid = sm_count();
+  if (grid > items) grid = (int)items;
+  static const int tma_env = getenv("ADVGRPO_ATTN_TMA_OUT") ? atoi(getenv("ADVGRPO_ATTN_TMA_OUT")) : 1;
+  const int tma_out = (tma_env && (out2 == nullptr || S_split % BQ == 0)) ? 1 : 0;
+  CUtensorMap tmap_o = tmap, tmap_o2 = tmap;
+  if (tma_out) {
+    const int64_t S1 = out2 ? S_split : S;
+    const uint64_t od[4] = {64, (uint64_t)H, (uint64_t)S1, (uint64_t)B};
+    const uint64_t os[4] = {0, 64 * 2, (uint64_t)(H * 64) * 2, (uint64_t)(S1 * H * 64) * 2};
+    rc = make_tmap_bf16(&tmap_o, out, 4, od, os, box, true);
+    if (rc != ADVGRPO_OK) return rc;
+    if (out2) {
+      const uint64_t od2[4] = {64, (uint64_t)H, (uint64_t)(S - S_split), (uint64_t)B};
+      const uint64_t os2[4] = {0, 64 * 2, (uint64_t)(H * 64) * 2, (uint64_t)((S - S_split) * H * 64) * 2};
+      rc = make_tmap_bf16(&tmap_o2, out2, 4, od2, os2, box, true);
+      if (rc != ADVGRPO_OK) return rc;
+    }
+  }
+  ADVGRPO_CUDA_CALL(launch_chain(attn_fwd_pair_kernel<EMU>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, 1, tmap, tmap_o,
+                                 tmap_o2, p, (int)items, npair, tma_out, flags));
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
@@ -1339,8 +1797,13 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 18: return launch_quad<2>(ADVGRPO_ATTN_ARGS);
       case 19: return launch_quad<1, true>(ADVGRPO_ATTN_ARGS);   // timeline trace (debug)
       case 20: return launch_persist<64, 1>(ADVGRPO_ATTN_ARGS);   // round-1 default (thread-per-row persistent kernel)
+      // pair kernel (one CTA per SM, two query tiles in antiphase); non-causal only
+      case 21: if (!causal) return launch_pair<1>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
+      case 22: if (!causal) return launch_pair<2>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
+      case 23: if (!causal) return launch_pair<0>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
       default: return launch_quad<1>(ADVGRPO_ATTN_ARGS);          // fastest measured (profiles/r2_*)
     }
+    return launch_quad<1>(ADVGRPO_ATTN_ARGS);   // pair variants asked for a causal problem
   }
   if (D == 128) return variant == 1 ? launch<128, 1, 0>(ADVGRPO_ATTN_ARGS) : launch_persist<128, 0>(ADVGRPO_ATTN_ARGS);
   return set_error(ADVGRPO_ERR_UNSUPPORTED, "attn_fwd: head_dim %lld not in {64, 128}", (long long)D);

@@ -213,6 +213,26 @@ def probe_attn_quad():
         _attn(v, S=1024, causal=True)
 
 
+def probe_attn_pair():
+    """Correctness of the pair kernel (one CTA per SM, two query tiles in antiphase), variants 21-25."""
+    import torch
+    from adv_grpo_b200 import ops
+    for v in (21, 22, 23, 24, 25):
+        for S in (128, 77, 256, 461, 1229, 1370):
+            _attn(v, S=S)
+    # many items per CTA + split output (image / text row ranges), vs the quad kernel bit for bit?  (no: different
+    # summation order of the row sums is identical, the exp token does not change arithmetic) -> compare numerically
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, S, H = 16, 1229, 24
+    qkv = torch.randn(B, S, 3, H, 64, device="cuda", generator=g).bfloat16()
+    ref, lse_ref = ops.attention_fwd(qkv, variant=17)
+    for v in (21, 22):
+        out, lse = ops.attention_fwd(qkv, variant=v)
+        torch.cuda.synchronize()
+        print(f"pair variant {v} vs quad at B=16 S=1229 H=24: max |d out| {(out.float() - ref.float()).abs().max().item():.3e} "
+              f"max |d lse| {(lse - lse_ref).abs().max().item():.3e}  equal {torch.equal(out, ref)}", flush=True)
+
+
 def _time_attn(B, S, H, D, variant, iters=10):
     import torch
     from adv_grpo_b200 import ops
@@ -233,7 +253,7 @@ def _time_attn(B, S, H, D, variant, iters=10):
 def probe_perf_attn():
     import torch
     for (B, S, H) in ((16, 1229, 24), (16, 1024, 24), (4, 4301, 24), (32, 1370, 12)):
-        for variant in (3, 0, 16, 17, 18):
+        for variant in (0, 17, 21, 22, 23, 24, 25):
             ms, tf = _time_attn(B, S, H, 64, variant)
             print(f"attn fwd B={B} S={S} H={H} variant {variant}: {ms:.3f} ms  {tf:.1f} TFLOP/s", flush=True)
         qkv = torch.randn(B, S, 3, H, 64, device="cuda").bfloat16()
