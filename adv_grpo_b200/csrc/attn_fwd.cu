@@ -1238,7 +1238,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[I_Q_FULL + i], 1);
-      mbar_init(&bars[I_Q_EMPTY + i], 1);
+      mbar_init(&bars[I_Q_EMPTY + i], tma_out ? 1 : 2);        // store warp, or the last QK of both groups' issuers
       mbar_init(&bars[I_S_FULL + i], 1);
       mbar_init(&bars[I_P_FULL + i], C::kGroupWarps * 32);
       mbar_init(&bars[I_PV_DONE + i], 1);
@@ -1247,11 +1247,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&bars[I_K_FULL + i], 1);
-      mbar_init(&bars[I_K_EMPTY + i], 1);
+      mbar_init(&bars[I_K_EMPTY + i], 2);                      // QK of both groups read the stage
     }
     for (int i = 0; i < VS; ++i) {
       mbar_init(&bars[I_V_FULL + i], 1);
-      mbar_init(&bars[I_V_EMPTY + i], 1);
+      mbar_init(&bars[I_V_EMPTY + i], 2);                      // PV of both groups read the stage
     }
     fence_barrier_init();
   }
@@ -1320,70 +1320,69 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           }
         }
       }
-    } else if (warp == C::kSoftmaxWarps + 1) {
-      // ============================== QK issuer: S_t(g) = Q_t K_g^T, t = 0, 1 ==============================
+    } else if (warp <= C::kSoftmaxWarps + 2) {
+      // ============================== MMA issuer of group t: S_t(g) = Q_t K_g^T and O_t += P_t(g) V_g ==================
+      // One issuer warp per softmax group, so the two groups are coupled only through the K / V stages: with a single
+      // QK warp and a single PV warp walking (tile 0, tile 1) in fixed order, the group that ran ahead waited for the
+      // other's s_free / p_full (ncu: 5.8 % of the softmax warps' time at the s_full wait).  Issue order per group
+      // follows its softmax: s_free(g) -> QK(g+1), then p_full(g) -> PV(g).
+      const int t = warp - (C::kSoftmaxWarps + 1);
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
-      const uint64_t q_d0 = make_smem_desc_sw128(q_sm, 16, 1024);
-      const uint64_t k_d0 = make_smem_desc_sw128(k_sm, 16, 1024);
-      int g = 0, n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-        const int qb = n & 1;
-        for (int j = 0; j < nkv; ++j, ++g) {
-          const int st = g % KS;
-          const uint64_t k_d = k_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (g > 0) mbar_wait_a(B(I_S_FREE + t), (g - 1) & 1);       // S_t(g-1) is in the softmax warps' registers
-            if (t == 0) {
-              if (j == 0) mbar_wait_a(B(I_Q_FULL + qb), (n >> 1) & 1);
-              mbar_wait_a(B(I_K_FULL + st), (g / KS) & 1);
-            }
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t q_d = q_d0 + (uint64_t)((2 * qb + t) * (C::kTileBytes >> 4));
-              const uint32_t s_tmem = tmem_base + 256 * t;
-              mma_ss_c<false>(s_tmem, q_d, k_d, idesc_qk);
-              mma_ss_c<true>(s_tmem, q_d + 2, k_d + 2, idesc_qk);
-              mma_ss_c<true>(s_tmem, q_d + 4, k_d + 4, idesc_qk);
-              mma_ss_c<true>(s_tmem, q_d + 6, k_d + 6, idesc_qk);
-              mma_commit_a(B(I_S_FULL + t));
-              if (t == 1) {
-                mma_commit_a(B(I_K_EMPTY + st));
-                // last QK of the item read both Q tiles; with the TMA-store epilogue the Q buffers double as the O
-                // staging tiles and are released by the store warp instead
-                if (j == nkv - 1 && !tma_out) mma_commit_a(B(I_Q_EMPTY + qb));
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
-    } else if (warp == C::kSoftmaxWarps + 2) {
-      // ============================== PV issuer: O_t += P_t(g) V_g (P read from TMEM) ==============================
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);
+      const uint64_t q_d0 = make_smem_desc_sw128(q_sm + t * C::kTileBytes, 16, 1024);
+      const uint64_t k_d0 = make_smem_desc_sw128(k_sm, 16, 1024);
       const uint64_t v_d0 = make_smem_desc_sw128(v_sm, BKV * 128, 1024);
-      int g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int j = 0; j < nkv; ++j, ++g) {
-          const int st = g % VS;
-          const uint64_t v_d = v_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait_a(B(I_P_FULL + t), g & 1);
-            if (t == 0) mbar_wait_a(B(I_V_FULL + st), (g / VS) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t p_tmem = tmem_base + 256 * t + 128, o_tmem = tmem_base + 256 * t + 192;
-              if (j > 0) mma_ts_c<true>(o_tmem, p_tmem, v_d, idesc_pv);
-              else mma_ts_c<false>(o_tmem, p_tmem, v_d, idesc_pv);
-#pragma unroll
-              for (int k = 1; k < BKV / 16; ++k) mma_ts_c<true>(o_tmem, p_tmem + k * 8, v_d + (uint64_t)(k * 128), idesc_pv);
-              mma_commit_a(B(I_PV_DONE + t));
-              if (t == 1) mma_commit_a(B(I_V_EMPTY + st));
-            }
-            __syncwarp();
-          }
+      const uint32_t s_tmem = tmem_base + 256 * t, p_tmem = s_tmem + 128, o_tmem = s_tmem + 192;
+      const uint32_t a_s_full = B(I_S_FULL + t), a_s_free = B(I_S_FREE + t), a_p_full = B(I_P_FULL + t),
+                     a_pv_done = B(I_PV_DONE + t);
+      const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int total = my_items * nkv;                        // K/V tiles this CTA walks
+      // QK(gq): gq = global tile index, (nq, jq) = (local item, tile in item)
+      auto issue_qk = [&](int gq, int nq, int jq) {
+        const int qb = nq & 1, st = gq % KS;
+        if (jq == 0) mbar_wait_a(B(I_Q_FULL + qb), (nq >> 1) & 1);
+        mbar_wait_a(B(I_K_FULL + st), (gq / KS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t q_d = q_d0 + (uint64_t)(2 * qb * (C::kTileBytes >> 4));
+          const uint64_t k_d = k_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+          mma_ss_c<false>(s_tmem, q_d, k_d, idesc_qk);
+          mma_ss_c<true>(s_tmem, q_d + 2, k_d + 2, idesc_qk);
+          mma_ss_c<true>(s_tmem, q_d + 4, k_d + 4, idesc_qk);
+          mma_ss_c<true>(s_tmem, q_d + 6, k_d + 6, idesc_qk);
+          mma_commit_a(a_s_full);
+          mma_commit_a(B(I_K_EMPTY + st));
+          // last QK of the item read the Q tile; with the TMA-store epilogue the Q buffers double as the O staging tiles
+          // and are released by the store warp instead
+          if (jq == nkv - 1 && !tma_out) mma_commit_a(B(I_Q_EMPTY + qb));
         }
+        __syncwarp();
+      };
+      if (total > 0) issue_qk(0, 0, 0);
+      int n = 0, j = 0;
+      for (int g = 0; g < total; ++g) {
+        int n1 = n, j1 = j + 1;
+        if (j1 == nkv) { j1 = 0; ++n1; }
+        if (g + 1 < total) {
+          mbar_wait_a(a_s_free, g & 1);                        // S_t(g) is in the softmax warps' registers
+          issue_qk(g + 1, n1, j1);
+        }
+        const int st = g % VS;
+        mbar_wait_a(a_p_full, g & 1);
+        mbar_wait_a(B(I_V_FULL + st), (g / VS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t v_d = v_d0 + (uint64_t)(st * (C::kTileBytes >> 4));
+          if (j > 0) mma_ts_c<true>(o_tmem, p_tmem, v_d, idesc_pv);
+          else mma_ts_c<false>(o_tmem, p_tmem, v_d, idesc_pv);
+#pragma unroll
+          for (int k = 1; k < BKV / 16; ++k) mma_ts_c<true>(o_tmem, p_tmem + k * 8, v_d + (uint64_t)(k * 128), idesc_pv);
+          mma_commit_a(a_pv_done);
+          mma_commit_a(B(I_V_EMPTY + st));
+        }
+        __syncwarp();
+        n = n1;
+        j = j1;
       }
     } else if (tma_out) {
       // ============================== O store: staged tiles (Q buffers of the finished item) -> global by TMA ==========
@@ -1479,6 +1478,12 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     };
 
     int g = 0, n = 0;
+    // The epilogue of a finished item is DEFERRED into the first tile of the next one (between its exponentials and its
+    // P store): waiting for the last PV right after publishing the last P exposed the whole p_full -> issue -> MMA ->
+    // commit chain once per item (ncu: 5.7 % of the softmax warps' time).
+    float m_prev[2] = {0.f, 0.f};
+    float2 l2_prev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    int item_prev = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       float m[2] = {kNegBig, kNegBig};                         // running max (scaled, log2 domain)
       float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // running denominators (this thread's columns)
@@ -1521,6 +1526,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           nm2[r] = make_float2(-mn, -mn);
           m[r] = mn;
         }
+        // the PV(g-1) barrier is polled BEFORE the exponentials (a try_wait costs ~100 clocks even when the phase is
+        // complete; here that latency hides under the exp stream) and only re-polled afterwards if it was not done yet
+        const bool pv_ok = g > 0 ? mbar_try_wait_a(a_pv_done, (g - 1) & 1) : true;
         // ---- p = exp2(s * scale - m), bf16 pairs; does not depend on PV(g-1) ----
         uint32_t pk[32];                                       // pk[2k + r] = P[row0 + 8r][cols 8k + 2cq, +1], k < 16
         float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -1544,12 +1552,14 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
               pk[16 * hb + 2 * k + r] = pack_bf16(e.x, e.y);
             }
         }
-        // PV(g-1) reads P(g-1) from the columns P(g) overwrites; O may only be rescaled between PV(g-1) and PV(g).
-        // For the first tile of an item the epilogue of the previous item already consumed that phase.
-        if (j > 0) {
-          mbar_wait_a(a_pv_done, (g - 1) & 1);
+        // PV(g-1) reads P(g-1) from the columns P(g) overwrites; O may only be rescaled (or, for the first tile of an
+        // item, read out by the previous item's epilogue) between PV(g-1) and PV(g).
+        if (g > 0) {
+          if (!pv_ok) mbar_wait_a(a_pv_done, (g - 1) & 1);
           tc_fence_after();
-          if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
+          if (j == 0) {
+            finish_item(item_prev, n - 1, l2_prev, m_prev);
+          } else if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t o[16];                                  // o[4k + 2r + c] = O[row0 + 8r][32 hh + 8k + 2cq + c]
@@ -1568,10 +1578,17 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         tc_fence_before();
         mbar_arrive_a(a_p_full);
       }
-      // ---- epilogue (the QK warp is already computing S of the next item) ----
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        m_prev[r] = m[r];
+        l2_prev[r] = l2[r];
+      }
+      item_prev = item;
+    }
+    if (n > 0) {                                               // epilogue of this CTA's last item
       mbar_wait_a(a_pv_done, (g - 1) & 1);
       tc_fence_after();
-      finish_item(item, n, l2, m);
+      finish_item(item_prev, n - 1, l2_prev, m_prev);
     }
   }
 
@@ -1801,7 +1818,10 @@ int attn_fwd_dispatch(const void* qkv, void* out, void* out2, int64_t S_split, f
       case 21: if (!causal) return launch_pair<1>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
       case 22: if (!causal) return launch_pair<2>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
       case 23: if (!causal) return launch_pair<0>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st); break;
-      default: return launch_quad<1>(ADVGRPO_ATTN_ARGS);          // fastest measured (profiles/r2_*)
+      default:
+        // fastest measured (profiles/r2_*): the pair kernel whenever there are two query tiles to pair up
+        if (!causal && S > BQ) return launch_pair<1>(qkv, out, out2, S_split, lse, B, S, H, scale, 0, st);
+        return launch_quad<1>(ADVGRPO_ATTN_ARGS);
     }
     return launch_quad<1>(ADVGRPO_ATTN_ARGS);   // pair variants asked for a causal problem
   }

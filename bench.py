@@ -452,7 +452,7 @@ def run_ours(args):
                 "algorithmic_bytes": 2.0 * (M * K + N * K + M * K2 + N * K2 + M * N),
                 "peak_source": f"{src} burst bf16 (kernel timed alone)",
                 # north_star's graded contraction: the joint text-image attention of one MMDiT block
-                "attention_fwd": {"bound": "tensor", "kernel": f"attn_fwd_quad_kernel (B={bsz} H=24 S={S} D=64, image/text "
+                "attention_fwd": {"bound": "tensor", "kernel": f"attn_fwd_pair_kernel (B={bsz} H=24 S={S} D=64, image/text "
                                   "output split)", "achieved": attn_flops / ms_attn / 1e9, "peak": peak_burst,
                                   "unit": "TFLOP/s", "frac": attn_flops / ms_attn / 1e9 / peak_burst,
                                   "traffic": tr_af if args.config in (2, 3, 5) else None, "traffic_source": tr_af_src,

@@ -313,6 +313,14 @@ def test_pickscore_discriminator_last_block_grads_match_oracle_autograd():
         got = prm.grad.float().cpu()
         if refg.norm().item() < 1e-12:
             continue
+        if name == "self_attn.k_proj.bias":
+            # softmax is invariant to a constant added to every key: the exact gradient of the key bias is ZERO, and both
+            # sides hold only rounding noise (fp32 noise on the oracle side, bf16 noise here) -- compare magnitudes with
+            # the query bias, whose gradient is real
+            qref = p32[pre + "self_attn.q_proj.bias"].grad.norm().item()
+            assert refg.norm().item() < 1e-3 * qref and got.norm().item() < 0.1 * qref, (name, got.norm().item(), qref)
+            checked += 1
+            continue
         cos = torch.nn.functional.cosine_similarity(got.flatten(), refg.flatten(), dim=0).item()
         rel = (got - refg).norm().item() / refg.norm().item()
         # 31 frozen bf16 blocks with seeded random weights feed the trainable block (the same amplification the rollout
