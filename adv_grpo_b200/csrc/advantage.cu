@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024) group_advantage_kernel(const float* __re
                                                                int mode, double* __restrict__ adv,
                                                                double* __restrict__ stats) {
   __shared__ double scratch[32];
-  __shared__ double col_std[16];
+  __shared__ double col_std[64];
   // column statistics (np.std(rewards, axis=0): population std, two-pass)
   for (int64_t t = 0; t < T; ++t) {
     double s = 0.0;
@@ -152,6 +152,101 @@ __global__ void __launch_bounds__(1024) group_advantage_kernel(const float* __re
   }
 }
 
+// type == 'grpo' (the only one the two scripts use), N <= kFastMaxN: the O(N^2) part -- who is in my group? -- runs ONCE per
+// row out of shared memory (first row with the same 128-bit digest = the group's leader), the T column statistics are
+// reduced by one warp each instead of 2 T block-wide reductions, and the group mean / std are computed once per
+// (group, column) by the leader's owner thread (members visited in ascending row order: the same summation order, hence
+// the same doubles, as the general kernel above) instead of once per (row, column).  Single CTA: the data is N T floats.
+constexpr int kFastMaxN = 8192;
+__global__ void __launch_bounds__(1024) group_advantage_grpo_kernel(const float* __restrict__ r,
+                                                                    const uint64_t* __restrict__ h1,
+                                                                    const uint64_t* __restrict__ h2, int N, int T,
+                                                                    int global_std, double* __restrict__ adv,
+                                                                    double* __restrict__ stats, double* __restrict__ gm,
+                                                                    double* __restrict__ gs) {
+  extern __shared__ __align__(16) uint8_t adv_smem[];
+  uint64_t* sh1 = reinterpret_cast<uint64_t*>(adv_smem);
+  uint64_t* sh2 = sh1 + N;
+  int* lead = reinterpret_cast<int*>(sh2 + N);
+  __shared__ double scratch[32];
+  __shared__ double col_std[64];
+  const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+  for (int i = tid; i < N; i += nth) { sh1[i] = h1[i]; sh2[i] = h2[i]; }
+  __syncthreads();
+  for (int i = tid; i < N; i += nth) {
+    const uint64_t a = sh1[i], b = sh2[i];
+    int j = 0;
+    while (!(sh1[j] == a && sh2[j] == b)) ++j;          // terminates at j == i at the latest
+    lead[i] = j;
+  }
+  // np.std(rewards, axis=0): population std, two-pass, one warp per column
+  for (int t = warp; t < T; t += nw) {
+    double s = 0.0;
+    for (int i = lane; i < N; i += 32) s += (double)r[(int64_t)i * T + t];
+    const double mean = warp_sum(s) / (double)N;
+    double q = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const double d = (double)r[(int64_t)i * T + t] - mean;
+      q += d * d;
+    }
+    q = warp_sum(q);
+    if (lane == 0) col_std[t] = sqrt(q / (double)N);
+  }
+  __syncthreads();
+  double n_groups = 0.0, zero_std = 0.0, std_sum = 0.0;
+  for (int p = tid; p < N * T; p += nth) {
+    const int i = p / T, t = p - i * T;
+    if (lead[i] != i) continue;
+    double s = 0.0;
+    int cnt = 0;
+    bool all_equal = true;
+    const float r0 = r[(int64_t)i * T + t];
+    for (int j = i; j < N; ++j)
+      if (lead[j] == i) {
+        const float v = r[(int64_t)j * T + t];
+        s += (double)v;
+        ++cnt;
+        all_equal &= (v == r0);
+      }
+    const double mean = s / (double)cnt;
+    double sd = col_std[t];
+    if (!global_std || (t == 0 && stats)) {
+      double q = 0.0;
+      for (int j = i; j < N; ++j)
+        if (lead[j] == i) {
+          const double d = (double)r[(int64_t)j * T + t] - mean;
+          q += d * d;
+        }
+      const double gsd = sqrt(q / (double)cnt);
+      if (!global_std) sd = gsd;
+      if (t == 0) {                                      // calculate_zero_std_ratio on column 0 ('ori_avg')
+        n_groups += 1.0;
+        std_sum += all_equal ? 0.0 : gsd;
+        zero_std += all_equal ? 1.0 : 0.0;
+      }
+    }
+    gm[p] = mean;
+    gs[p] = sd;
+  }
+  __syncthreads();
+  for (int p = tid; p < N * T; p += nth) {
+    const int i = p / T, t = p - i * T;
+    const int l = lead[i] * T + t;
+    adv[p] = ((double)r[p] - gm[l]) / (gs[l] + 1e-4);     // stat_tracking.py:41-47
+  }
+  if (stats) {
+    n_groups = block_sum_d(n_groups, scratch);
+    zero_std = block_sum_d(zero_std, scratch);
+    std_sum = block_sum_d(std_sum, scratch);
+    if (tid == 0) {
+      stats[0] = n_groups;
+      stats[1] = (double)N / n_groups;
+      stats[2] = zero_std / n_groups;
+      stats[3] = std_sum / n_groups;
+    }
+  }
+}
+
 // One warp; B is a per-rank micro-batch (8..64).
 __global__ void grpo_clip_loss_kernel(const float* __restrict__ lp, const float* __restrict__ lp_old,
                                       const double* __restrict__ adv, int64_t adv_stride, int64_t B,
@@ -207,8 +302,8 @@ using namespace advgrpo;
 extern "C" {
 
 size_t advgrpo_group_advantage_workspace_bytes(int64_t N, int64_t T) {
-  (void)T;
-  return (size_t)N * 2 * sizeof(uint64_t) + 16;
+  // two 64-bit digests per row + group mean / std per (row, column)
+  return (size_t)N * 2 * sizeof(uint64_t) + (size_t)N * (size_t)(T > 0 ? T : 1) * 2 * sizeof(double) + 16;
 }
 
 int advgrpo_group_advantage_mode(const float* rewards, const int64_t* group_keys, int64_t key_len,
@@ -218,8 +313,8 @@ int advgrpo_group_advantage_mode(const float* rewards, const int64_t* group_keys
   ADVGRPO_CHECK_ARG(rewards && group_keys && advantages, "group_advantage: null pointer");
   ADVGRPO_CHECK_ARG(mode >= ADVGRPO_ADV_GRPO && mode <= ADVGRPO_ADV_DPO, "group_advantage: unknown mode %d", mode);
   ADVGRPO_CHECK_ARG(mode != ADVGRPO_ADV_DPO || T == 1, "group_advantage: mode 'dpo' needs 1-D rewards (T = 1)");
-  ADVGRPO_CHECK_ARG(N >= 0 && T >= 1 && T <= 16 && key_len >= 1,
-                    "group_advantage: need N >= 0, 1 <= T <= 16, key_len >= 1 (got N=%lld T=%lld key_len=%lld)",
+  ADVGRPO_CHECK_ARG(N >= 0 && T >= 1 && T <= 64 && key_len >= 1,
+                    "group_advantage: need N >= 0, 1 <= T <= 64, key_len >= 1 (got N=%lld T=%lld key_len=%lld)",
                     (long long)N, (long long)T, (long long)key_len);
   if (N == 0) return ADVGRPO_OK;
   if (!workspace || workspace_bytes < advgrpo_group_advantage_workspace_bytes(N, T))
@@ -230,8 +325,22 @@ int advgrpo_group_advantage_mode(const float* rewards, const int64_t* group_keys
   const int warps = 8;
   hash_rows_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, st>>>(group_keys, key_len, N, h1, h2);
   ADVGRPO_CUDA_LAUNCH_CHECK();
-  int threads = N >= 1024 ? 1024 : (int)(((N + 31) / 32) * 32);
-  group_advantage_kernel<<<1, threads, 0, st>>>(rewards, h1, h2, N, T, global_std, mode, advantages, stats);
+  if (mode == ADVGRPO_ADV_GRPO && N <= kFastMaxN) {
+    double* gm = (double*)(h2 + N);
+    double* gs = gm + N * T;
+    const size_t smem = (size_t)N * 20;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(group_advantage_grpo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastMaxN * 20));
+      attr_set = true;
+    }
+    int64_t work = N * T;
+    int threads = work >= 1024 ? 1024 : (int)(((work + 31) / 32) * 32);
+    group_advantage_grpo_kernel<<<1, threads, smem, st>>>(rewards, h1, h2, (int)N, (int)T, global_std, advantages, stats, gm, gs);
+  } else {
+    int threads = N >= 1024 ? 1024 : (int)(((N + 31) / 32) * 32);
+    group_advantage_kernel<<<1, threads, 0, st>>>(rewards, h1, h2, N, T, global_std, mode, advantages, stats);
+  }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

@@ -20,6 +20,7 @@
 // Replaces autograd through F.scaled_dot_product_attention at
 // scripts/train_sd3_fast_pickscore.py:1165 (MMDiT joint attention and attn2 in the replay step).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -46,7 +47,17 @@ constexpr int OFF_DQ = OFF_DS + 2 * kDsBytes;             // 1
 constexpr int OFF_STAT = OFF_DQ + kDqBytes;               // QSTAGES
 constexpr int OFF_BAR = OFF_STAT + QSTAGES * kStatBytes;
 constexpr int kSmemBytes = OFF_BAR + 256 + 1024;
-constexpr int kThreads = 512;   // 14 working warps + 2 idle ones so that every setmaxnreg warpgroup is complete
+// NWG compute warpgroups split the 128 query columns of a tile (thread = kv row): 2 x 64 columns (176 registers per compute
+// thread, 8 compute warps) or 4 x 32 columns (96 registers, 16 compute warps: four per SM sub-partition hide the TMEM /
+// LDS / MUFU latencies the 8-warp version exposed -- ncu r2: issue slots 31 % busy, compute warps 25 % long-scoreboard).
+// Warps: [0, 4 NWG) compute, then 4 dQ-drain warps, then TMA, MMA and 2 idle warps (every setmaxnreg group is complete).
+template <int NWG> struct BCfg {
+  static constexpr int kComputeWarps = 4 * NWG;
+  static constexpr int kThreads = (kComputeWarps + 8) * 32;
+  static constexpr int kRegsCompute = NWG == 2 ? 176 : 96;   // 512 x 128 = 256 x 176 + 128 x 88 + 128 x 72
+  static constexpr int kRegsDrain = NWG == 2 ? 88 : 48;      // 768 x 80  = 512 x 96 + 128 x 48 + 128 x 48
+  static constexpr int kRegsUtility = NWG == 2 ? 72 : 48;
+};
 constexpr int COL_S = 0, COL_DP = 128, COL_P = 256, COL_DV = 320, COL_DK = 384, COL_DQ = 448;
 
 struct BParams {
@@ -58,9 +69,13 @@ struct BParams {
   int causal;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NWG>
+__global__ void __launch_bounds__(BCfg<NWG>::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const BParams p) {
+  using C = BCfg<NWG>;
+  constexpr int CW = C::kComputeWarps;                 // compute warps; drain = CW..CW+3, TMA = CW+4, MMA = CW+5
+  constexpr int NCT = CW * 32;                         // compute threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -95,11 +110,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_init(&bar_q_empty[i], 1);
     }
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, 256);
-    mbar_init(bar_p_full, 256);
+    mbar_init(bar_s_free, NCT);
+    mbar_init(bar_p_full, NCT);
     mbar_init(bar_pv_done, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_ds_full[i], 256);
+      mbar_init(&bar_ds_full[i], NCT);
       mbar_init(&bar_ds_empty[i], 1);
     }
     mbar_init(bar_dq_full, 1);
@@ -107,7 +122,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(bar_dkv_full, 1);
     fence_barrier_init();
   }
-  if (warp == 13) {
+  if (warp == CW + 5) {
     tmem_alloc(tmem_base_smem, 512);
     tmem_relinquish();
   }
@@ -121,9 +136,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   // register re-balancing (setmaxnreg is per 4-warp group): 256 compute threads x 176 + 128 drain x 88 + 128 utility x 72
   // = 512 x 128, the registers at launch
-  if (warp >= 12) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-  if (warp == 12) {
+  if (warp >= CW + 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsUtility));
+  if (warp == CW + 4) {
     // ============================== TMA producer ==============================
     // (utility warps run their loops warp-uniformly; only the TMA / tcgen05 instructions sit under elect_one(): under
     //  a divergent `lane == 0` branch ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop)
@@ -148,31 +163,63 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 13) {
-    // ============================== MMA issuer ==============================
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(T, T, 0, 0);     // A K-major, B K-major, N = 128
-      constexpr uint32_t idesc_kn = make_idesc_bf16(T, D, 0, 1);    // A K-major (smem or TMEM), B MN-major
-      constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
-      const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
-      const uint32_t q_s0 = smem_u32(smem + OFF_Q), do_s0 = smem_u32(smem + OFF_DO), ds_s0 = smem_u32(smem + OFF_DS);
-      // descriptors built once; per MMA only the 16-byte-unit start address is advanced (2048 B -> 128, 32 B -> 2)
+  } else {
+    // ============================== MMA issuers ==============================
+    // Two issuer warps: CW+5 issues the FRONT half of a tile (S^T = K Q^T, dP^T = V dO^T), CW+6 the BACK half
+    // (dV += P^T dO, dK += dS^T Q, dQ = dS K).  With a single issuer (round 1) S^T / dP^T of tile it+1 could only be issued
+    // after the back half of tile it-1, whose ~250 instructions of descriptor rebuilding, modulo arithmetic and barrier polls
+    // ran in ONE serial stream: ncu r2 showed that warp executing ~440 instructions per tile with no dominant stall, i.e. it
+    // was the critical path (compute warps 12 % at the s_full wait, tensor pipe 32 %).  Descriptors are built once; per tile
+    // only the 16-byte-unit start address moves (stage * 1024, dS buffer * 2048, K step offsets as immediates).
+    constexpr uint32_t idesc_s = make_idesc_bf16(T, T, 0, 0);     // A K-major, B K-major, N = 128
+    constexpr uint32_t idesc_kn = make_idesc_bf16(T, D, 0, 1);    // A K-major (smem or TMEM), B MN-major
+    constexpr uint32_t idesc_mn = (make_idesc_bf16(T, D, 1, 1));  // A MN-major, B MN-major
+    const uint32_t k_s = smem_u32(smem + OFF_K), v_s = smem_u32(smem + OFF_V);
+    const uint32_t q_s0 = smem_u32(smem + OFF_Q), do_s0 = smem_u32(smem + OFF_DO), ds_s0 = smem_u32(smem + OFF_DS);
+    if (warp == CW + 5) {
       const uint64_t k_kmaj = make_smem_desc_sw128(k_s, 16, 1024), v_kmaj = make_smem_desc_sw128(v_s, 16, 1024);
+      const uint64_t q_k0 = make_smem_desc_sw128(q_s0, 16, 1024), do_k0 = make_smem_desc_sw128(do_s0, 16, 1024);
+      mbar_wait(bar_kv_full, 0);
+      int st = 0, ph = 0;                                         // Q / dO stage of tile `it` and its phase bit
+      for (int it = 0; it < nq; ++it) {
+        mbar_wait(&bar_q_full[st], ph);
+        if (it > 0) mbar_wait(bar_s_free, (it - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t q_k = q_k0 + (uint64_t)(st * (kTile >> 4)), do_k = do_k0 + (uint64_t)(st * (kTile >> 4));
+          mma_ss_c<false>(tmem_base + COL_S, k_kmaj, q_k, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_S, k_kmaj + 2, q_k + 2, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_S, k_kmaj + 4, q_k + 4, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_S, k_kmaj + 6, q_k + 6, idesc_s);
+          mma_ss_c<false>(tmem_base + COL_DP, v_kmaj, do_k, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_DP, v_kmaj + 2, do_k + 2, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_DP, v_kmaj + 4, do_k + 4, idesc_s);
+          mma_ss_c<true>(tmem_base + COL_DP, v_kmaj + 6, do_k + 6, idesc_s);
+          mma_commit(bar_s_full);
+        }
+        __syncwarp();
+        if (++st == QSTAGES) { st = 0; ph ^= 1; }
+      }
+    } else if (warp == CW + 6) {
       const uint64_t k_mn = make_smem_desc_sw128(k_s, 16384, 1024);
-      auto back_half = [&](int it) {
-        const int st = it % QSTAGES, bb = it & 1;
-        const uint64_t q_mn = make_smem_desc_sw128(q_s0 + st * kTile, 16384, 1024);
-        const uint64_t do_mn = make_smem_desc_sw128(do_s0 + st * kTile, 16384, 1024);
-        const uint64_t ds_k = make_smem_desc_sw128(ds_s0 + bb * kDsBytes, 16, 1024);
-        const uint64_t ds_mn = make_smem_desc_sw128(ds_s0 + bb * kDsBytes, 16384, 1024);
+      const uint64_t q_mn0 = make_smem_desc_sw128(q_s0, 16384, 1024), do_mn0 = make_smem_desc_sw128(do_s0, 16384, 1024);
+      const uint64_t ds_k0 = make_smem_desc_sw128(ds_s0, 16, 1024), ds_mn0 = make_smem_desc_sw128(ds_s0, 16384, 1024);
+      mbar_wait(bar_kv_full, 0);                                  // K (dQ's B operand) landed: observed by this thread too
+      int st = 0, ph = 0;
+      for (int it = 0; it < nq; ++it) {
+        const int bb = it & 1;
+        mbar_wait(&bar_q_full[st], ph);                           // Q / dO of this tile (long complete; acquire for this thread)
+        const uint64_t q_mn = q_mn0 + (uint64_t)(st * (kTile >> 4)), do_mn = do_mn0 + (uint64_t)(st * (kTile >> 4));
+        const uint64_t ds_k = ds_k0 + (uint64_t)(bb * (kDsBytes >> 4)), ds_mn = ds_mn0 + (uint64_t)(bb * (kDsBytes >> 4));
         // dV += P^T dO
         mbar_wait(bar_p_full, it & 1);
         tc_fence_after();
         if (elect_one()) {
+          if (it > 0) mma_ts_c<true>(tmem_base + COL_DV, tmem_base + COL_P, do_mn, idesc_kn);
+          else mma_ts_c<false>(tmem_base + COL_DV, tmem_base + COL_P, do_mn, idesc_kn);
 #pragma unroll
-          for (int k = 0; k < T / 16; ++k)
-            mma_ts(tmem_base + COL_DV, tmem_base + COL_P + k * 8, do_mn + (uint64_t)(k * 128), idesc_kn,
-                   (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 1; k < T / 16; ++k)
+            mma_ts_c<true>(tmem_base + COL_DV, tmem_base + COL_P + k * 8, do_mn + (uint64_t)(k * 128), idesc_kn);
           mma_commit(bar_pv_done);
         }
         __syncwarp();
@@ -180,10 +227,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mbar_wait(&bar_ds_full[bb], (it >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
+          if (it > 0) mma_ss_c<true>(tmem_base + COL_DK, ds_k, q_mn, idesc_kn);
+          else mma_ss_c<false>(tmem_base + COL_DK, ds_k, q_mn, idesc_kn);
 #pragma unroll
-          for (int k = 0; k < T / 16; ++k)
-            mma_ss(tmem_base + COL_DK, ds_k + (uint64_t)((k / 4) * 1024 + (k % 4) * 2), q_mn + (uint64_t)(k * 128), idesc_kn,
-                   (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 1; k < T / 16; ++k)
+            mma_ss_c<true>(tmem_base + COL_DK, ds_k + (uint64_t)((k / 4) * 1024 + (k % 4) * 2), q_mn + (uint64_t)(k * 128), idesc_kn);
         }
         __syncwarp();
         // dQ = dS K   (fresh accumulator every query tile)
@@ -192,44 +240,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           tc_fence_after();
         }
         if (elect_one()) {
+          mma_ss_c<false>(tmem_base + COL_DQ, ds_mn, k_mn, idesc_mn);
 #pragma unroll
-          for (int k = 0; k < T / 16; ++k)
-            mma_ss(tmem_base + COL_DQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mn, k > 0 ? 1u : 0u);
+          for (int k = 1; k < T / 16; ++k)
+            mma_ss_c<true>(tmem_base + COL_DQ, ds_mn + (uint64_t)(k * 128), k_mn + (uint64_t)(k * 128), idesc_mn);
           mma_commit(&bar_ds_empty[bb]);
           mma_commit(bar_dq_full);
           mma_commit(&bar_q_empty[st]);
         }
         __syncwarp();
-      };
-      mbar_wait(bar_kv_full, 0);
-      for (int it = 0; it < nq; ++it) {
-        const int st = it % QSTAGES;
-        mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);
-        if (it > 0) mbar_wait(bar_s_free, (it - 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t q_k = make_smem_desc_sw128(q_s0 + st * kTile, 16, 1024);
-          const uint64_t do_k = make_smem_desc_sw128(do_s0 + st * kTile, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k)
-            mma_ss(tmem_base + COL_S, k_kmaj + (uint64_t)(k * 2), q_k + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < D / 16; ++k)
-            mma_ss(tmem_base + COL_DP, v_kmaj + (uint64_t)(k * 2), do_k + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-          mma_commit(bar_s_full);
-        }
-        __syncwarp();
-        if (it > 0) back_half(it - 1);
+        if (++st == QSTAGES) { st = 0; ph ^= 1; }
       }
-      if (nq > 0) back_half(nq - 1);
       if (elect_one()) mma_commit(bar_dkv_full);
       __syncwarp();
     }
   }
-  } else if (warp < 8) {
+  } else if (warp < CW) {
     // ============================== compute: P^T and dS^T ==============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    const int wg = warp / 4;                          // which half of the query columns
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsCompute));
+    constexpr int NCH = 4 / NWG;                      // 32-column chunks of the query axis per thread
+    const int wg = warp / 4;                          // which slice of the query columns
     const int row = (warp % 4) * 32 + lane;           // kv row inside the tile == TMEM lane
     const int kv_idx = kv0 + row;
     const bool kv_ok = kv_idx < S;
@@ -242,33 +272,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int i = i_begin + it;
       const int st = it % QSTAGES, bb = it & 1;
       const float* lse2 = reinterpret_cast<const float*>(smem + OFF_STAT + st * kStatBytes);
-      const uint32_t ds_row = smem_u32(smem + OFF_DS + bb * kDsBytes + wg * 16384 + row * 128);   // 64-col block = wg
+      const uint32_t ds_base = smem_u32(smem + OFF_DS + bb * kDsBytes + row * 128);   // + 16384 per 64-column block
       const uint32_t stat_s = smem_u32(lse2);          // lse2[128] then delta[128] (explicit shared-space loads)
       mbar_wait(&bar_q_full[st], (it / QSTAGES) & 1);     // lse2 / delta visible
       mbar_wait(bar_s_full, it & 1);
       tc_fence_after();
-      // my 64 query columns of S^T and dP^T -> registers in one go, then release both TMEM regions at once: the MMA
+      // my query columns of S^T and dP^T -> registers in one go, then release both TMEM regions at once: the MMA
       // warp issues S^T / dP^T of the NEXT query tile while this tile's exponentials are still running (they were
       // serialised behind the whole tile before: ncu showed 12 % of the compute warps' time waiting on s_full)
-      uint32_t rs[2][32], rp[2][32];
+      uint32_t rs[NCH][32], rp[NCH][32];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        tmem_ld32(t_s + (wg * 2 + cc) * 32, rs[cc]);
-        tmem_ld32(t_dp + (wg * 2 + cc) * 32, rp[cc]);
+      for (int cc = 0; cc < NCH; ++cc) {
+        tmem_ld32(t_s + (wg * NCH + cc) * 32, rs[cc]);
+        tmem_ld32(t_dp + (wg * NCH + cc) * 32, rp[cc]);
       }
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(bar_s_free);
-      // P^T and dS^T of both chunks into registers first: the exponentials do not depend on the dV MMA of the previous
+      // P^T and dS^T of all chunks into registers first: the exponentials do not depend on the dV MMA of the previous
       // tile, which is still reading P^T(it-1) from the TMEM columns the stores below overwrite
-      uint32_t pk[2][16], dk[2][16];
+      uint32_t pk[NCH][16], dk[NCH][16];
       // element-wise masking (causal diagonal tile, kv rows beyond S) only where a tile needs it: the common tile
       // runs 5 instructions per element (FFMA, MUFU.EX2, FADD, FMUL, half a pack pair) instead of ~19
       const bool masked = !kv_ok_tile || ((p.causal & 1) && i * T < kv0 + T);
       if (masked) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = wg * 2 + cc;                    // 32-column chunk of the query axis
+        for (int cc = 0; cc < NCH; ++cc) {
+          const int c = wg * NCH + cc;                  // 32-column chunk of the query axis
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
@@ -294,8 +324,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       } else {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = wg * 2 + cc;
+        for (int cc = 0; cc < NCH; ++cc) {
+          const int c = wg * NCH + cc;
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 l4 = lds_f4(stat_s + (c * 32 + e) * 4);
@@ -318,13 +348,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (it >= 2) mbar_wait(&bar_ds_empty[bb], ((it - 2) >> 1) & 1);   // dS buffer free (dK / dQ MMAs of tile it-2 done)
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        tmem_st16(t_p + (wg * 2 + cc) * 16, pk[cc]);
-        // dS^T row: 64 bytes of this chunk = four 16-byte pieces, hand swizzled (128B pattern)
+      for (int cc = 0; cc < NCH; ++cc) {
+        const int c = wg * NCH + cc;
+        tmem_st16(t_p + c * 16, pk[cc]);
+        // dS^T row: 64 bytes of this chunk = four 16-byte pieces inside 64-column block c / 2, hand swizzled (128B pattern)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int piece = cc * 4 + k;
-          sts_u4(ds_row + ((piece ^ (row & 7)) * 16),
+          const int piece = (c & 1) * 4 + k;
+          sts_u4(ds_base + (c >> 1) * 16384 + ((piece ^ (row & 7)) * 16),
                  make_uint4(dk[cc][4 * k], dk[cc][4 * k + 1], dk[cc][4 * k + 2], dk[cc][4 * k + 3]));
         }
       }
@@ -334,22 +365,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       fence_proxy_async_smem();
       mbar_arrive(&bar_ds_full[bb]);
     }
-    // ---- epilogue: dV (warpgroup 0) and dK (warpgroup 1) -> bf16 ----
+    // ---- epilogue: dV (first half of the warpgroups) and dK (second half) -> bf16, 64 / (NWG / 2) columns per thread ----
     {
       mbar_wait(bar_dkv_full, 0);
       tc_fence_after();
+      constexpr int ECH = 4 / NWG;                      // 32-column chunks of the 64-wide dV / dK row per thread
       __nv_bfloat16* base = p.dqkv + ((int64_t)b * S + kv_idx) * 3 * p.H * D;
-      const int which = wg;                           // 0: dV, 1: dK
-      const uint32_t t_acc = tmem_base + (which == 0 ? COL_DV : COL_DK) + lane_addr;
+      const int which = wg / (NWG / 2);                 // 0: dV, 1: dK
+      const int col0 = (wg % (NWG / 2)) * (ECH * 32);
+      const uint32_t t_acc = tmem_base + (which == 0 ? COL_DV : COL_DK) + lane_addr + col0;
       const float sc = which == 0 ? 1.0f : p.scale;
-      __nv_bfloat16* dst = base + ((which == 0 ? 2 : 1) * p.H + h) * D;
-      uint32_t r[2][32];
-      tmem_ld32(t_acc, r[0]);
-      tmem_ld32(t_acc + 32, r[1]);
+      __nv_bfloat16* dst = base + ((which == 0 ? 2 : 1) * p.H + h) * D + col0;
+      uint32_t r[ECH][32];
+#pragma unroll
+      for (int c = 0; c < ECH; ++c) tmem_ld32(t_acc + c * 32, r[c]);
       tmem_wait_ld();
       if (kv_ok) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < ECH; ++c)
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 v;
@@ -362,34 +395,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
   } else {
-    // ============================== dQ drain (warps 8-11) ==============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ============================== dQ drain (4 warps after the compute warps) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsDrain));
     const int row = (warp % 4) * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t t_dq = tmem_base + COL_DQ + (static_cast<uint32_t>((warp % 4) * 32) << 16);
     uint8_t* stage = smem + OFF_DQ;
-    const int tid = threadIdx.x - 256;
+    const int tid = threadIdx.x - NCT;
     for (int it = 0; it < nq; ++it) {
       const int i = i_begin + it;
       mbar_wait(bar_dq_full, it & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(t_dq, r0);
-      tmem_ld32(t_dq + 32, r1);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(bar_dq_free);
-      // two [128 rows x 32 fp32] boxes through ONE 16 KB staging tile (128B-swizzled rows), one after the other
+      // two [128 rows x 32 fp32] boxes through ONE 16 KB staging tile (128B-swizzled rows), one after the other; the
+      // TMEM columns are released as soon as the second half is in registers
       const int grow = (int)(stat_row + (int64_t)i * T);
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r[32];
+        tmem_ld32(t_dq + hf * 32, r);
+        tmem_wait_ld();
+        if (hf == 1) {
+          tc_fence_before();
+          mbar_arrive(bar_dq_free);
+        }
         if (tid == 0) tma_store_wait_read();          // the previous reduce finished reading the staging tile
         named_bar_sync(1, 128);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t* r = hf == 0 ? r0 : r1;
-          sts_u4(smem_u32(stage) + row * 128 + ((k ^ (row & 7)) * 16),
-                 make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
-        }
+        for (int k = 0; k < 8; ++k)
+          sts_u4(smem_u32(stage) + row * 128 + ((k ^ (row & 7)) * 16), make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (tid == 0 && !(p.causal & 2)) {   // bit 1: timing experiment only (skip the dQ reduce)
@@ -403,7 +435,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == CW + 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -518,9 +550,12 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
     rc = make_tmap(&tm_dq, dq_acc, 2, dims3, str3, box3, true, true);
     if (rc) return rc;
   }
+  // 16 compute warps (4 x 32 query columns) by default; ADVGRPO_ATTN_BWD_WG=2 selects the 8-warp layout (measurement)
+  static const int nwg = (getenv("ADVGRPO_ATTN_BWD_WG") && atoi(getenv("ADVGRPO_ATTN_BWD_WG")) == 2) ? 2 : 4;
   static bool attr_set = false;
   if (!attr_set) {
-    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ADVGRPO_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   BParams p;
@@ -532,7 +567,11 @@ int advgrpo_attn_bwd(const void* qkv, const void* out, const void* dout, const f
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   dim3 grid((unsigned)(sp / T), (unsigned)H, (unsigned)B);
-  ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_kernel, grid, dim3(kThreads), kSmemBytes, st, 1, tm_qkv, tm_do, tm_dq, p));
+  if (nwg == 2) {
+    ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_kernel<2>, grid, dim3(BCfg<2>::kThreads), kSmemBytes, st, 1, tm_qkv, tm_do, tm_dq, p));
+  } else {
+    ADVGRPO_CUDA_CALL(launch_chain(attn_bwd_kernel<4>, grid, dim3(BCfg<4>::kThreads), kSmemBytes, st, 1, tm_qkv, tm_do, tm_dq, p));
+  }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   {
     const int64_t groups = B * H * S;

@@ -18,7 +18,7 @@ constexpr int kWarpsPerBlock = 8;
 // AFFINE: plain LayerNorm with per-channel weight / bias (`scale` = weight, `shift` = bias, mod_stride 0):
 // y = n * weight + bias instead of n * (1 + scale) + shift.
 template <int NV, bool AFFINE = false>  // D = NV * 256
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ shift,
                        const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift2,
                        const __nv_bfloat16* __restrict__ scale2, int64_t mod_stride,
@@ -32,40 +32,54 @@ ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   const int lane = threadIdx.x & 31;
   const int64_t b = row / S;
   const __nv_bfloat16* xr = x + row * D;
-  float v[NV][8];
+  // The row stays PACKED in registers (NV x 16 bytes per lane) and is unpacked once per pass: 24 registers instead of 48
+  // at width 1536, so four 8-warp blocks (64 registers per thread) instead of three (80) are resident per SM and a third
+  // more row loads are in flight (ncu r2: 34 % of the warp slots active, 4.4 TB/s).  Same fp32 operations in the same
+  // order as before: bit-identical output.
+  bf16x8 raw[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    unpack8(*reinterpret_cast<const bf16x8*>(xr + (i * 32 + lane) * 8), v[i]);
+  for (int i = 0; i < NV; ++i) raw[i] = *reinterpret_cast<const bf16x8*>(xr + (i * 32 + lane) * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[i][j];
+  for (int i = 0; i < NV; ++i) {
+    float v[8];
+    unpack8(raw[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
   }
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) {
+    float v[8];
+    unpack8(raw[i], v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[i][j] -= mean;
-      q = fmaf(v[i][j], v[i][j], q);
+      const float d = v[j] - mean;
+      q = fmaf(d, d, q);
     }
+  }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
   const __nv_bfloat16* sh = shift + b * mod_stride;
   const __nv_bfloat16* sc = scale + b * mod_stride;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int off = (i * 32 + lane) * 8;
-    float fsh[8], fsc[8], o[8];
+    float v[8], fsh[8], fsc[8], o[8];
+    unpack8(raw[i], v);
     unpack8(*reinterpret_cast<const bf16x8*>(sh + off), fsh);
     unpack8(*reinterpret_cast<const bf16x8*>(sc + off), fsc);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, AFFINE ? fsc[j] : 1.0f + fsc[j], fsh[j]);
+    for (int j = 0; j < 8; ++j) {
+      v[j] -= mean;
+      o[j] = fmaf(v[j] * rstd, AFFINE ? fsc[j] : 1.0f + fsc[j], fsh[j]);
+    }
     *reinterpret_cast<bf16x8*>(y + row * D + off) = pack8(o);
     if (!AFFINE && y2) {
       unpack8(*reinterpret_cast<const bf16x8*>(shift2 + b * mod_stride + off), fsh);
       unpack8(*reinterpret_cast<const bf16x8*>(scale2 + b * mod_stride + off), fsc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[i][j] * rstd, 1.0f + fsc[j], fsh[j]);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j] * rstd, 1.0f + fsc[j], fsh[j]);
       *reinterpret_cast<bf16x8*>(y2 + row * D + off) = pack8(o);
     }
   }

@@ -32,18 +32,41 @@ __device__ __forceinline__ StepCoef step_coef(const float* timesteps, int64_t t_
   const float t = timesteps[t_count == 1 ? 0 : b];
   // diffusers index_for_timestep: the 2nd match if the timestep occurs more than once
   int first = -1, second = -1;
-  for (int i = 0; i < T; ++i) {
-    if (sched_t[i] == t) {
-      if (first < 0) first = i;
-      else if (second < 0) second = i;
-    }
-  }
-  int idx = second >= 0 ? second : first;
   StepCoef k;
-  k.valid = idx >= 0;
-  if (!k.valid) idx = 0;
-  k.sigma = sigmas[idx];
-  k.sigma_prev = sigmas[idx + 1];
+  float sigma_max = 0.f;
+  if (T <= 31) {
+    // the whole schedule fits one warp: lane i holds sched_t[i] and sigmas[i] (T + 1 entries), the match is a ballot and
+    // the coefficients come by shuffle -- ONE global round trip instead of the three dependent ones (timestep -> scan ->
+    // sigmas[idx]) that made up a third of this launch-latency-bound kernel at rollout sizes (profiles/r2_hbm_kernels)
+    const int lane = threadIdx.x & 31;
+    const float tl = lane < T ? sched_t[lane] : 0.f;
+    const float sg = lane <= T ? sigmas[lane] : 0.f;
+    unsigned m = __ballot_sync(0xffffffffu, lane < T && tl == t);
+    if (m) {
+      first = __ffs(m) - 1;
+      m &= m - 1;
+      if (m) second = __ffs(m) - 1;
+    }
+    int idx = second >= 0 ? second : first;
+    k.valid = idx >= 0;
+    if (!k.valid) idx = 0;
+    k.sigma = __shfl_sync(0xffffffffu, sg, idx);
+    k.sigma_prev = __shfl_sync(0xffffffffu, sg, idx + 1);
+    sigma_max = __shfl_sync(0xffffffffu, sg, 1);
+  } else {
+    for (int i = 0; i < T; ++i) {
+      if (sched_t[i] == t) {
+        if (first < 0) first = i;
+        else if (second < 0) second = i;
+      }
+    }
+    int idx = second >= 0 ? second : first;
+    k.valid = idx >= 0;
+    if (!k.valid) idx = 0;
+    k.sigma = sigmas[idx];
+    k.sigma_prev = sigmas[idx + 1];
+    sigma_max = mode == 1 ? sigmas[1] : 0.f;               // Flow-SDE only (the API requires T >= 2 there)
+  }
   k.std = __fmul_rn(k.sigma_prev, sin_level);
   k.c = __fsqrt_rn(__fsub_rn(__fmul_rn(k.sigma_prev, k.sigma_prev), __fmul_rn(k.std, k.std)));
   k.one_m_sigma = __fsub_rn(1.0f, k.sigma);
@@ -53,7 +76,6 @@ __device__ __forceinline__ StepCoef step_coef(const float* timesteps, int64_t t_
   k.ax = k.cv = k.dt = 0.f;
   if (mode == 1) {
     // sde.py:46-53 in torch's fp32 op order (every scalar below is a [B,1,1,1] fp32 tensor in the reference)
-    const float sigma_max = sigmas[1];
     const float den = __fsub_rn(1.0f, k.sigma == 1.0f ? sigma_max : k.sigma);
     k.std = __fmul_rn(__fsqrt_rn(__fdiv_rn(k.sigma, den)), noise_level);
     k.dt = __fsub_rn(k.sigma_prev, k.sigma);
@@ -101,9 +123,11 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t ctr, float (&z)[
   for (int i = 0; i < 2; ++i) {
     float u1 = fmaf((float)r[2 * i], kInv, kInv * 0.5f);   // (0, 1]
     float u2 = fmaf((float)r[2 * i + 1], kInv, kInv * 0.5f);
-    float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    // fast-math Box-Muller (MUFU lg2 / sqrt / sin / cos, ~2^-21 absolute error on the normals): the IEEE logf / sqrtf /
+    // sincospif sequence cost ~50 instructions per pair and made the rollout form of this kernel issue-bound
+    float rad, s, c;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
+    __sincosf(6.283185307179586f * u2, &s, &c);
     z[2 * i] = rad * c;
     z[2 * i + 1] = rad * s;
   }
