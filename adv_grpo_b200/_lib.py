@@ -49,6 +49,8 @@ SIGNATURES = {
     "advgrpo_gemm_bf16_dual": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P,
                                        _P, _P, _P, _P]),
     "advgrpo_row_gate_mul": (c_int, [_P, _P, _I64, _I64, _P, _I64, _I64, _P]),
+    "advgrpo_gemm_tn_skinny_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "advgrpo_gemm_tn_skinny": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I, _P, _SZ, _P]),
     "advgrpo_gemm_qkv_norm": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64,
                                       _F, _P]),
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
@@ -96,7 +98,7 @@ def load():
 
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
+_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2, "advgrpo_gemm_tn_skinny": 2,
                      "advgrpo_device_check": 0}
 _launches = [0]
 

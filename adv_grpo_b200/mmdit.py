@@ -16,7 +16,7 @@ i.e. diffusers' `SD3Transformer2DModel` wrapped by the peft LoRA of
 
 Gradients flow to the LoRA A/B matrices only (everything else is frozen); the backward of each
 linear is dX = dY W (one tcgen05 GEMM against the pre-transposed weight, plus the LoRA term as a
-second product); the tiny LoRA weight gradients are plain library GEMMs (cuBLAS via torch.matmul).
+second product); the LoRA weight gradients dt^T x / dy^T t are the skinny split-K TN kernel (ops.gemm_tn_skinny).
 
 State-dict names follow diffusers / peft so released checkpoints map one to one.
 """
@@ -97,9 +97,9 @@ class _LinearFn(torch.autograd.Function):
             dt = ops.gemm(dy2, lora_w2.t().contiguous())               # dY (sB) -> [M, r_pad]
             x2 = x.reshape(-1, x.shape[-1])
             if ctx.needs_input_grad[4]:
-                da = (dt.t() @ x2)                                     # [r_pad, K]   (library GEMM)
+                da = ops.gemm_tn_skinny(dt, x2)                        # dt^T x -> [r_pad, K]   (tcgen05 split-K TN kernel)
             if ctx.needs_input_grad[5]:
-                dw2 = (dy2.t() @ t.reshape(-1, t.shape[-1]))           # [N, r_pad]   (library GEMM)
+                dw2 = ops.gemm_tn_skinny(t.reshape(-1, t.shape[-1]), dy2, transpose_out=True)   # dy^T t -> [N, r_pad]
         if ctx.needs_input_grad[0]:
             wt = wt_holder()
             if dt is not None:
@@ -155,9 +155,9 @@ class _DualLinearFn(torch.autograd.Function):
             for i in range(2):
                 x2 = xs[i].reshape(-1, xs[i].shape[-1])
                 if ctx.needs_input_grad[8 + i]:
-                    das[i] = dts[i].t() @ x2
+                    das[i] = ops.gemm_tn_skinny(dts[i], x2)
                 if ctx.needs_input_grad[10 + i]:
-                    dws[i] = dy2[i].t() @ ts[i].reshape(-1, ts[i].shape[-1])
+                    dws[i] = ops.gemm_tn_skinny(ts[i].reshape(-1, ts[i].shape[-1]), dy2[i], transpose_out=True)
         dx0 = dx1 = None
         need0, need1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need0 and need1:
@@ -584,7 +584,7 @@ class SD3Transformer2DModel(torch.nn.Module):
         x = x + self._pos_cache[key]
         # conditioning vector and every block's adaLN modulation in one GEMM
         te = timestep_embedding(timestep.to(self.device_)).to(bf)
-        lin = lambda n, v: F.linear(v, p[n + ".weight"], p[n + ".bias"])
+        lin = lambda n, v: ops.gemm(v.contiguous(), p[n + ".weight"], bias=p[n + ".bias"])   # B-row conditioning MLPs
         temb = lin("time_text_embed.timestep_embedder.linear_2", F.silu(lin("time_text_embed.timestep_embedder.linear_1", te)))
         temb = temb + lin("time_text_embed.text_embedder.linear_2",
                           F.silu(lin("time_text_embed.text_embedder.linear_1", pooled_projections.to(bf))))

@@ -453,6 +453,23 @@ def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, ga
     return c2d.reshape(*lead, N)
 
 
+def gemm_tn_skinny(a, b, transpose_out=False):
+    """a^T @ b over the leading (token) axis: a bf16 [Kt, Ms] (Ms <= 256), b bf16 [Kt, Nb] -> bf16 [Ms, Nb] (or [Nb, Ms]).
+    The LoRA weight-gradient products dt^T x and (dy^T t = (t^T dy)^T) on the tcgen05 split-K kernel."""
+    _need_cuda(a, b)
+    a, b = _bf16c(a), _bf16c(b)
+    Kt, Ms = a.shape
+    Kt2, Nb = b.shape
+    if Kt != Kt2:
+        raise _lib.AdvGrpoError(f"gemm_tn_skinny: row counts differ ({Kt} vs {Kt2})")
+    out = torch.empty((Nb, Ms) if transpose_out else (Ms, Nb), dtype=torch.bfloat16, device=a.device)
+    ws_bytes = _lib.query("advgrpo_gemm_tn_skinny_workspace_bytes", Kt, Ms, Nb)
+    ws = _workspace("gemm_tn", ws_bytes, a.device)
+    _lib.call("advgrpo_gemm_tn_skinny", _ptr(a), _ptr(b), _ptr(out), Kt, Ms, Nb, int(bool(transpose_out)), _ptr(ws),
+              ws.numel(), _stream())
+    return out
+
+
 def row_gate_mul(x, gate, rows_per_gate):
     """x [M, N] bf16 (any leading shape) * gate[m // rows_per_gate] (gate [G, N], row-strided) in one pass."""
     _need_cuda(x, gate)

@@ -333,3 +333,25 @@ def test_gemm_gelu_grad_epilogue_and_row_gate_mul(ops, variant):
     torch.nn.functional.gelu(zz, approximate="tanh").backward(acc)
     assert _rel_err(got, zz.grad) < 6e-3
     assert _rel_err(got2[0], zz.grad) < 6e-3 and _rel_err(got2[1], zz.grad[:100]) < 6e-3
+
+
+# ------------------------------------------------------------------ skinny TN GEMM (LoRA weight gradients)
+@pytest.mark.parametrize("Kt,Ms,Nb", [(16384, 128, 1536), (3280, 64, 1536), (16384, 64, 6144), (2460, 128, 4608),
+                                      (100, 64, 64), (77, 32, 136), (5000, 256, 264)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_gemm_tn_skinny_matches_fp32(ops, Kt, Ms, Nb, transpose):
+    """dt^T x and (t^T dy)^T of the LoRA backward (peft lora.Linear autograd behind train_sd3_fast_pickscore.py:1165):
+    contraction over the token axis with deterministic split-K, vs the fp32 product of the same bf16 operands."""
+    g = torch.Generator(device=DEV).manual_seed(Kt + Ms)
+    a = torch.randn(Kt, Ms, device=DEV, generator=g).bfloat16()
+    b = torch.randn(Kt, Nb, device=DEV, generator=g).bfloat16()
+    out = ops.gemm_tn_skinny(a, b, transpose_out=transpose)
+    out2 = ops.gemm_tn_skinny(a, b, transpose_out=transpose)
+    assert torch.equal(out, out2)                               # fixed summation order: bit-reproducible
+    ref = a.float().t() @ b.float()
+    if transpose:
+        ref = ref.t()
+    assert out.shape == ref.shape
+    # fp32 accumulation, one bf16 rounding of the result
+    assert (out.float() - ref).abs().max().item() < 6e-3 * ref.abs().max().item() + 1e-3
+
