@@ -98,7 +98,7 @@ def load():
 
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
-_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2, "advgrpo_gemm_tn_skinny": 2,
+_KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
                      "advgrpo_device_check": 0}
 _launches = [0]
 

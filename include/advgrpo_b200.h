@@ -265,8 +265,9 @@ int advgrpo_row_gate_mul(const void* x, const void* gate, int64_t gate_stride, i
  * of the replay backward -- peft lora.Linear's autograd through `loss.backward()` at train_sd3_fast_pickscore.py:1165:
  *   C[m, n] = sum_k A[k, m] * B[k, n],   A bf16 [Kt, Ms] (Ms <= 256, multiple of 8), B bf16 [Kt, Nb] (Nb multiple of 8)
  *   grad lora_A = dt^T x  (A = dt [tokens, r], B = x [tokens, K]);   grad lora_B^T = t^T dy, written transposed
- * out: bf16 [Ms, Nb], or [Nb, Ms] when transpose_out != 0.  fp32 accumulation; the split-K partial tiles are summed in a
- * fixed order (bit-reproducible).  workspace: advgrpo_gemm_tn_skinny_workspace_bytes(...) bytes, 16-byte aligned. */
+ * out: bf16 [Ms, Nb], or [Nb, Ms] when transpose_out != 0.  fp32 accumulation; split-K over an 8-CTA cluster whose partial
+ * tiles are summed through distributed shared memory in a fixed order (bit-reproducible).  workspace: none needed today
+ * (advgrpo_gemm_tn_skinny_workspace_bytes returns 0; the arguments stay in the ABI). */
 size_t advgrpo_gemm_tn_skinny_workspace_bytes(int64_t Kt, int64_t Ms, int64_t Nb);
 int advgrpo_gemm_tn_skinny(const void* a, const void* b, void* out, int64_t Kt, int64_t Ms, int64_t Nb, int transpose_out,
                            void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
