@@ -561,3 +561,24 @@ def test_layer_norm_affine_matches_torch_fp32(ops, rows, D, eps):
     xg = x.to(DEV).float().requires_grad_()
     ops.layer_norm(xg, w.to(DEV).float(), b.to(DEV).float(), eps).sum().backward()
     assert xg.grad is not None
+
+
+def test_stat_tracker_device_path_counts_distinct_prompts_and_handles_long_T(ops):
+    """`update_device` (gathered prompt-id rows on the device): `get_stats()` reports the reference's
+    (avg group size, trained_prompt_num = distinct prompts ever seen, stat_tracking.py:36-37,72-75) across epochs, and the
+    fast grpo kernel accepts T = 20 columns (config 4 trains on up to num_steps timesteps)."""
+    from adv_grpo_b200.stat_tracking import PerPromptStatTracker
+    tr = PerPromptStatTracker(global_std=True, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    T = 20
+    for epoch, base in enumerate((0, 2)):                                # prompts {0,1,2,3} then {2,3,4,5}
+        ids = (torch.arange(32, device=DEV) // 8 + base)[:, None].expand(32, 256).contiguous()
+        r = torch.randn(32, device=DEV, generator=g)[:, None].repeat(1, T)
+        adv = tr.update_device(ids, r)
+        rr = r.double().reshape(4, 8, T)
+        ref = ((rr - rr.mean(1, keepdim=True)) / (r.double().std(0, unbiased=False) + 1e-4)).reshape(32, T)
+        assert (adv - ref).abs().max().item() < 1e-9
+        size, seen = tr.get_stats()
+        assert size == 8.0 and seen == (4 if epoch == 0 else 6)
+        tr.clear()
+
