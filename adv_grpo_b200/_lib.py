@@ -61,6 +61,18 @@ SIGNATURES = {
     "advgrpo_conv2d_nhwc_tf32": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
     "advgrpo_add_bias_nhwc": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "advgrpo_upsample_nearest2x_nhwc": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _P]),
+    "advgrpo_gather_rows_l2norm": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _I, _F, _P]),
+    "advgrpo_head_logits": (c_int, [_P, _P, _P, _P, _I64, _I64, _I, _P]),
+    "advgrpo_dino_hybrid_score": (c_int, [_P, _P, _I64, _I64, _F, _I, _P]),
+    "advgrpo_dino_hinge_loss": (c_int, [_P, _P, _P, _I64, _I64, _I64, _F, _P]),
+    "advgrpo_head_dz": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
+    "advgrpo_col_sum_workspace_bytes": (_SZ, [_I64, _I64]),
+    "advgrpo_col_sum": (c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _P, _SZ, _P]),
+    "advgrpo_pickscore_head": (c_int, [_P, _P, _P, _P, _I, _P, _I64, _I64, _I64, _I, _P]),
+    "advgrpo_layer_norm_affine_bwd_workspace_bytes": (_SZ, [_I64, _I64]),
+    "advgrpo_layer_norm_affine_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P, _SZ, _P]),
+    "advgrpo_adam_torch_order": (c_int, [_P, _P, _P, _P, _I64, _I, _I, _D, _D, _D, _D, _I64, _I, _P]),
+    "advgrpo_row_softmax_f32": (c_int, [_P, _P, _I64, _I64, _F, _I, _P]),
 }
 # test/bench hooks that are exported but not part of include/advgrpo_b200.h
 _EXTRA = {
@@ -99,7 +111,7 @@ def load():
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
-                     "advgrpo_device_check": 0}
+                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_device_check": 0}
 _launches = [0]
 
 

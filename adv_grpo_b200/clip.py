@@ -6,8 +6,12 @@
 The module tree and parameter names are those of transformers' CLIPModel, so a PickScore_v1 state
 dict loads as is.  Frozen layers run on the tcgen05 kernels (packed weights, rebuilt when a
 parameter's version counter changes); layers with requires_grad parameters under grad mode (the last
-`tune_layer` vision blocks during the discriminator step) run as plain PyTorch modules so autograd
-reaches them -- library GEMMs on < 4% of the tower.
+`tune_layer` vision blocks during the discriminator step) run through differentiable native ops: affine LayerNorm
+(`ops.layer_norm`, native dx / d weight / d bias), every Linear on the tcgen05 GEMM with weight gradients on the
+split-K TN kernel and bias gradients on the column-sum kernel (`ops.linear`), the MLP with the erf-GELU and its
+derivative fused into GEMM epilogues (`ops.mlp_gelu`).  Only the head_dim-80 softmax(QK^T)V core of those one or two
+blocks goes through torch's SDPA (forward + backward): the D = 64 attention-backward kernel's TMEM layout has no room
+for a 128-wide head.
 """
 import torch
 import torch.nn.functional as F
@@ -59,25 +63,25 @@ class CLIPEncoderLayer(nn.Module):
             return self._fast()(x, causal)
         B, S, W = x.shape
         hd = W // self.heads
-        h = self.layer_norm1(x)
-        a = self.self_attn
-        q, k, v = (l(h).view(B, S, self.heads, hd).transpose(1, 2) for l in (a.q_proj, a.k_proj, a.v_proj))
+        ln1, ln2, a, m = self.layer_norm1, self.layer_norm2, self.self_attn, self.mlp
+        h = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
+        q, k, v = (ops.linear(h, l.weight, l.bias).view(B, S, self.heads, hd).transpose(1, 2)
+                   for l in (a.q_proj, a.k_proj, a.v_proj))
         o = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, S, W)
-        x = x + a.out_proj(o)
-        return x + self.mlp.fc2(F.gelu(self.mlp.fc1(self.layer_norm2(x))))
+        x = x + ops.linear(o, a.out_proj.weight, a.out_proj.bias)
+        return x + ops.mlp_gelu(ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps), m.fc1.weight, m.fc1.bias,
+                                m.fc2.weight, m.fc2.bias)
 
 
 def _ln(mod, x):
-    """Affine LayerNorm on the native kernel; autograd's node only while the discriminator trains this module (A14)."""
-    if torch.is_grad_enabled() and (x.requires_grad or mod.weight.requires_grad):
-        return mod(x)
-    return ops.layer_norm(x.contiguous(), mod.weight.detach(), mod.bias.detach(), mod.eps)
+    """Affine LayerNorm on the native kernel (forward and, under autograd, backward: A14)."""
+    return ops.layer_norm(x.contiguous(), mod.weight, mod.bias, mod.eps)
 
 
 def _proj(lin, x):
-    """Bias-free projection of the pooled token on the tcgen05 GEMM; nn.Linear only under autograd."""
+    """Bias-free projection of the pooled token on the tcgen05 GEMM (differentiable through `ops.linear`)."""
     if torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad):
-        return lin(x)
+        return ops.linear(x.contiguous(), lin.weight)
     return ops.gemm(x.contiguous(), lin.weight.detach())
 
 

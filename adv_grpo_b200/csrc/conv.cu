@@ -29,7 +29,8 @@ constexpr int CBK = 32;    // fp32 channels per K block (128 bytes)
 // stages its own patch and HALF of the weight tile, which halves the per-CTA operand traffic and allows 5 stages.
 template <int BN, int MT, bool TWO = false>
 struct CCfg {
-  static constexpr int kStages = TWO ? 5 : ((BN * MT >= 256) ? 3 : 5);
+  // stage = MT x 16 KB of pixels + BN x 128 B of weights; + 64 KB of staging tiles: 208-224 KB of shared memory
+  static constexpr int kStages = TWO ? 5 : ((BN * MT >= 256) ? 3 : ((BN == 32 && MT == 2) ? 4 : 5));
   static constexpr int kABytes = MT * CBM * 128;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -340,9 +341,11 @@ int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, 
   p.bw = bw; p.bh = bh;
   p.tiles_x = (int)((W + bw - 1) / bw);
   p.tiles_y = (int)((H + bh - 1) / bh);
-  const int BN = Cout >= 256 ? 256 : 128;
+  // 32-column tiles for the decoder's conv_out (3 output channels zero-padded to 32): a 128-column tile would spend 4x the
+  // tensor-core time on zero filters (g_conv_variant 2 = test hook: keep the 128-column tiles)
+  const int BN = Cout >= 256 ? 256 : ((Cout <= 32 && g_conv_variant != 2) ? 32 : 128);
   const bool pair = BN == 256 && H >= 2 * bh && g_conv_variant != 1;
-  const int MT = (BN == 128 && H >= 2 * bh) ? 2 : 1;
+  const int MT = (BN <= 128 && H >= 2 * bh) ? 2 : 1;
   const int rows = pair ? 2 : MT;                                          // patches stacked per tile
   p.tiles_y = (int)((H + bh * rows - 1) / (bh * rows));
   p.tiles_n = (int)((Cout + BN - 1) / BN);
@@ -367,6 +370,10 @@ int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, 
   if (rc) return rc;
   if (pair) return launch_conv<256, 1, true>(mx, mw, my, p, (cudaStream_t)stream);
   if (BN == 256) return launch_conv<256, 1, false>(mx, mw, my, p, (cudaStream_t)stream);
+  if (BN == 32) {
+    if (MT == 2) return launch_conv<32, 2, false>(mx, mw, my, p, (cudaStream_t)stream);
+    return launch_conv<32, 1, false>(mx, mw, my, p, (cudaStream_t)stream);
+  }
   if (MT == 2) return launch_conv<128, 2, false>(mx, mw, my, p, (cudaStream_t)stream);
   return launch_conv<128, 1, false>(mx, mw, my, p, (cudaStream_t)stream);
 }

@@ -112,9 +112,24 @@ __device__ __forceinline__ float gelu_tanh_grad(float z) {
   return fmaf(0.5f * z * fmaf(-t, t, 1.0f), du, fmaf(0.5f, t, 0.5f));
 }
 
+// d/dz of the erf GELU: Phi(z) + z phi(z) = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi)   (same A-S 7.1.26 erf)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float z = fabsf(x) * 0.7071067811865476f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2(-1.4426950408889634f * z * z);          // exp(-x^2 / 2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float cdf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 // EC = epilogue class (compile time, so each instantiation only carries the registers its epilogues need):
 //   0 = plain / bias / GELU variants (+ optional pre-activation store), 1 = epilogues with a prefetched auxiliary
-//   tile (GATE_RESIDUAL, GELU_TANH_GRAD), 2 = QKNORM (per-sample tiling, 3-D maps)
+//   tile (GATE_RESIDUAL, GELU_TANH_GRAD, GELU_ERF_GRAD), 2 = QKNORM (per-sample tiling, 3-D maps)
 template <int BN, bool TWO, int EC>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
@@ -272,7 +287,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint8_t* tstage = stage + team * (2 * BM * 128);
     uint64_t* tbar_res = bar_res + 2 * team;
     constexpr bool has_res = EC == 1;                                         // auxiliary tile prefetched like the residual
-    const bool is_ggrad = has_res && p.epilogue == ADVGRPO_EPI_GELU_TANH_GRAD;   // C = acc * gelu'(z)
+    const bool is_ggrad = has_res && (p.epilogue == ADVGRPO_EPI_GELU_TANH_GRAD ||
+                                      p.epilogue == ADVGRPO_EPI_GELU_ERF_GRAD);   // C = acc * gelu'(z)
     const bool is_gelu = EC == 0 && (p.epilogue == ADVGRPO_EPI_GELU_TANH || p.epilogue == ADVGRPO_EPI_GELU_ERF ||
                                      p.epilogue == ADVGRPO_EPI_QUICK_GELU);
     constexpr bool is_qkn = EC == 2;
@@ -452,7 +468,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               float zz[8];
               unpack8(lds_bf16x8(sp), zz);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] *= gelu_tanh_grad(zz[j]);
+              for (int j = 0; j < 8; ++j)
+                f[j] *= p.epilogue == ADVGRPO_EPI_GELU_TANH_GRAD ? gelu_tanh_grad(zz[j]) : gelu_erf_grad(zz[j]);
             } else if (has_res) {
               float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rr[8];
               if (grow) unpack8(gv[q], gg);
@@ -556,9 +573,9 @@ int check_prob(const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int epilogue
                           aligned16(q.residual) && aligned16(q.gate),
                       "gemm_bf16: GATE_RESIDUAL needs residual, gate, rows_per_gate");
   }
-  if (epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) {
+  if (epilogue == ADVGRPO_EPI_GELU_TANH_GRAD || epilogue == ADVGRPO_EPI_GELU_ERF_GRAD) {
     ADVGRPO_CHECK_ARG(q.residual && q.ldr % 8 == 0 && aligned16(q.residual),
-                      "gemm_bf16: GELU_TANH_GRAD needs the pre-activation in `residual`");
+                      "gemm_bf16: GELU_*_GRAD needs the pre-activation in `residual`");
   }
   (void)N; (void)K;
   return ADVGRPO_OK;
@@ -624,7 +641,8 @@ int make_maps(Maps& m, const ProbArgs& q, int64_t N, int64_t K, int64_t K2, int 
   }
   rc = make_tmap_bf16(&m.c, q.C, 2, dc, sc, bc, true);
   if (rc) return rc;
-  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) {
+  if (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD ||
+      epilogue == ADVGRPO_EPI_GELU_ERF_GRAD) {
     const uint64_t sr[2] = {0, (uint64_t)q.ldr * 2};
     rc = make_tmap_bf16(&m.r, q.residual, 2, dc, sr, bc, true);
     if (rc) return rc;
@@ -659,7 +677,7 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   ADVGRPO_CHECK_ARG(K % 64 == 0 && N % 8 == 0 && K2 % 64 == 0,
                     "gemm_bf16: K and K2 must be multiples of 64 and N of 8 (K=%lld K2=%lld N=%lld)", (long long)K,
                     (long long)K2, (long long)N);
-  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 6, "gemm_bf16: unknown epilogue %d", epilogue);
+  ADVGRPO_CHECK_ARG(epilogue >= 0 && epilogue <= 7, "gemm_bf16: unknown epilogue %d", epilogue);
   for (int i = 0; i < nprob; ++i) {
     int rc = check_prob(probs[i], N, K, K2, epilogue);
     if (rc) return rc;
@@ -717,7 +735,8 @@ int gemm_run(const ProbArgs* probs, int nprob, int64_t N, int64_t K, int64_t K2,
   p.epilogue = epilogue;
   p.HD = (int)HD;
   p.eps = eps;
-  const int ec = (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD) ? 1
+  const int ec = (epilogue == ADVGRPO_EPI_GATE_RESIDUAL || epilogue == ADVGRPO_EPI_GELU_TANH_GRAD ||
+                  epilogue == ADVGRPO_EPI_GELU_ERF_GRAD) ? 1
                  : (epilogue == ADVGRPO_EPI_QKNORM ? 2 : 0);
 #define ADVGRPO_GEMM_DISPATCH(BNV, TWOV)                                   \
   switch (ec) {                                                            \

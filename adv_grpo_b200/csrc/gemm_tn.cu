@@ -211,9 +211,9 @@ int advgrpo_gemm_tn_skinny(const void* a, const void* b, void* out, int64_t Kt, 
                            void* workspace, size_t workspace_bytes, advgrpo_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
   ADVGRPO_CHECK_ARG(a && b && out, "gemm_tn_skinny: null pointer");
-  ADVGRPO_CHECK_ARG(Kt >= 1 && Ms >= 1 && Ms <= 256 && Nb >= 1 && Ms % 8 == 0 && Nb % 8 == 0 && Kt < ((int64_t)1 << 30) &&
+  ADVGRPO_CHECK_ARG(Kt >= 1 && Ms >= 1 && Ms <= 16384 && Nb >= 1 && Ms % 8 == 0 && Nb % 8 == 0 && Kt < ((int64_t)1 << 30) &&
                         Nb < ((int64_t)1 << 24),
-                    "gemm_tn_skinny: need 1 <= Ms <= 256, Ms %% 8 == 0, Nb %% 8 == 0 (got Kt=%lld Ms=%lld Nb=%lld)", (long long)Kt,
+                    "gemm_tn_skinny: need 1 <= Ms <= 16384, Ms %% 8 == 0, Nb %% 8 == 0 (got Kt=%lld Ms=%lld Nb=%lld)", (long long)Kt,
                     (long long)Ms, (long long)Nb);
   ADVGRPO_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(out), "gemm_tn_skinny: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;

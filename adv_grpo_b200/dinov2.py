@@ -57,18 +57,30 @@ class DINOHead(torch.nn.Module):
         return self.layers(x)
 
 
+def _head_params(head):
+    head = head.module if hasattr(head, "module") else head                 # DDP(head), train_sd3_fast_dino_patch.py:749
+    l = head.layers
+    return l[0].weight, l[0].bias, l[2].weight, l[2].bias
+
+
 def dino_hinge_d_loss(head, feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight=0.3):
     """Discriminator (head) loss of `train_sd3_fast_dino_patch.py:186-219`: hinge loss on the CLS token of real / fake
     images plus `patch_loss_weight` x the hinge loss on the sampled patch tokens (`idx_*` [B, n] = the torch.randint
-    draws of :199-200; NO L2 normalisation in the D step, unlike the reward path).  Returns (loss, accuracy)."""
-    relu = torch.nn.functional.relu
-    hp = next(head.parameters())
-    fr, ff = feats_real.to(hp.dtype), feats_fake.to(hp.dtype)
-    lr_, lf_ = head(fr[:, 0]).squeeze(-1), head(ff[:, 0]).squeeze(-1)
-    image_loss = 0.5 * (relu(1.0 - lr_).mean() + relu(1.0 + lf_).mean())
-    D = fr.shape[-1]
-    sr = torch.gather(fr[:, 1:], 1, idx_real.unsqueeze(-1).expand(-1, -1, D))
-    sf = torch.gather(ff[:, 1:], 1, idx_fake.unsqueeze(-1).expand(-1, -1, D))
-    patch_loss = 0.5 * (relu(1.0 - head(sr).squeeze(-1)).mean() + relu(1.0 + head(sf).squeeze(-1)).mean())
-    acc = 0.5 * ((lr_ > 0).float().mean() + (lf_ < 0).float().mean())
-    return image_loss + patch_loss_weight * patch_loss, acc
+    draws of :199-200; NO L2 normalisation in the D step, unlike the reward path).  Returns (loss, accuracy); everything
+    -- token gather, Linear + GELU (tcgen05 GEMM), Linear(1), hinge, and the gradients of the four head parameters that
+    `loss.backward()` deposits -- runs on the native kernels (`ops.dino_head_hinge_loss`, csrc/heads.cu)."""
+    return ops.dino_head_hinge_loss(_head_params(head), feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight)
+
+
+def dino_patch_scores(head, feats, idx, cls_weight=0.7):
+    """Reward path of `adv_grpo/rewards.py:399-421` behind `forward_features`: CLS + sampled patch tokens, L2-normalised,
+    through the head, `cls_weight * cls + (1 - cls_weight) * mean(patch)`.  Returns (hybrid [B], cls [B], patch [B, n])."""
+    w1, b1, w2, b2 = _head_params(head)
+    B, n = idx.shape
+    rows = ops.gather_rows_l2norm(feats, idx, l2norm=True, eps=1e-6)
+    bf16_head = w1.dtype == torch.bfloat16
+    logits, _, _ = ops.dino_head_forward((w1, b1, w2, b2), rows, bf16_head)
+    hybrid = ops.dino_hybrid_score(logits, B, n, cls_weight, bf16_head)
+    per = logits.view(B, 1 + n)
+    out_dtype = w1.dtype
+    return hybrid.to(out_dtype), per[:, 0].to(out_dtype), per[:, 1:].to(out_dtype)

@@ -266,24 +266,56 @@ def ln_modulate(x, shift, scale, shift2=None, scale2=None, eps=1e-6):
     return _LnModulate.apply(x, shift, scale, shift2, scale2, eps)
 
 
-def layer_norm(x, weight, bias, eps):
-    """Affine LayerNorm over the last dim of the reward towers' blocks (bf16, width a multiple of 256) on the
-    `ln_modulate` kernel.  Inference only: when a gradient is needed (the discriminator step trains the last CLIP
-    blocks, train_sd3_fast_pickscore.py:151-183) autograd's own LayerNorm node is used."""
-    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad)
+def _layer_norm_fwd(x, weight, bias, eps):
     D = x.shape[-1]
-    if needs_grad:                     # discriminator training of the last CLIP block only (A14): autograd's LayerNorm
-        return torch.nn.functional.layer_norm(x, (D,), weight, bias, eps)
     _need_cuda(x, weight, bias)
     if D % 256 or D > 2048:
         raise ValueError(f"layer_norm: width {D} is not supported by the native kernel (multiple of 256, <= 2048); "
                          "there is no PyTorch fallback")
     x, weight, bias = _bf16c(x), _bf16c(weight), _bf16c(bias)
-    x = x.contiguous()
     y = torch.empty_like(x)
-    _lib.call("advgrpo_layer_norm_affine", _ptr(x), _ptr(weight.contiguous()), _ptr(bias.contiguous()), _ptr(y),
-              x.numel() // D, D, float(eps), _stream())
+    _lib.call("advgrpo_layer_norm_affine", _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), x.numel() // D, D, float(eps), _stream())
     return y
+
+
+class _LayerNormAffine(torch.autograd.Function):
+    """Affine LayerNorm with a native backward (dx, and d weight / d bias when they are trainable): the LayerNorms of the
+    CLIP vision blocks the PickScore discriminator step trains (train_sd3_fast_pickscore.py:1016-1029)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _bf16c(x)
+        ctx.save_for_backward(x, weight)
+        ctx.eps = float(eps)
+        ctx.param_dtype = weight.dtype
+        return _layer_norm_fwd(x, weight.detach().to(torch.bfloat16), bias.detach().to(torch.bfloat16), eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dy = _bf16c(dy)
+        want_p = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx = torch.empty_like(x)
+        dwb = torch.empty((2, D), dtype=torch.float32, device=x.device) if want_p else None
+        ws = None
+        if want_p:
+            ws = _workspace("ln_bwd", _lib.query("advgrpo_layer_norm_affine_bwd_workspace_bytes", rows, D), x.device)
+        _lib.call("advgrpo_layer_norm_affine_bwd", _ptr(x), _ptr(_bf16c(weight.detach().to(torch.bfloat16))), _ptr(dy), _ptr(dx),
+                  _ptr(dwb), None if dwb is None else dwb[1].data_ptr(), rows, D, ctx.eps, _ptr(ws),
+                  0 if ws is None else ws.numel(), _stream())
+        dw = dwb[0].to(ctx.param_dtype) if ctx.needs_input_grad[1] else None
+        db = dwb[1].to(ctx.param_dtype) if ctx.needs_input_grad[2] else None
+        return (dx if ctx.needs_input_grad[0] else None), dw, db, None
+
+
+def layer_norm(x, weight, bias, eps):
+    """Affine LayerNorm over the last dim of the reward towers' blocks (bf16, width a multiple of 256) on the
+    `ln_modulate` kernel; differentiable (native backward) when the input or the parameters require a gradient."""
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad):
+        return _LayerNormAffine.apply(x, weight, bias, eps)
+    return _layer_norm_fwd(x.contiguous(), weight.detach(), bias.detach(), eps)
 
 
 # --------------------------------------------------------------------------- q/k RMSNorm + concat
@@ -425,6 +457,7 @@ def set_gemm_variant(v):
 
 
 EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF, EPI_GATE_RESIDUAL, EPI_QUICK_GELU, EPI_GELU_TANH_GRAD = 0, 1, 2, 3, 5, 6
+EPI_GELU_ERF_GRAD = 7
 
 
 def gemm(a, w, bias=None, a2=None, w2=None, epilogue=EPI_NONE, residual=None, gate=None,
@@ -467,6 +500,229 @@ def gemm_tn_skinny(a, b, transpose_out=False):
     ws = _workspace("gemm_tn", ws_bytes, a.device)
     _lib.call("advgrpo_gemm_tn_skinny", _ptr(a), _ptr(b), _ptr(out), Kt, Ms, Nb, int(bool(transpose_out)), _ptr(ws),
               ws.numel(), _stream())
+    return out
+
+
+def gemm_tn(a, b, out=None):
+    """a^T @ b over the leading (row) axis for ANY widths: a bf16 [R, M], b bf16 [R, N] -> bf16 [M, N] -- the weight
+    gradient dy^T x of a trainable Linear (discriminator step) on the same tcgen05 split-K kernel as the LoRA products."""
+    _need_cuda(a, b)
+    a, b = _bf16c(a), _bf16c(b)
+    R, M = a.shape
+    R2, N = b.shape
+    if R != R2:
+        raise _lib.AdvGrpoError(f"gemm_tn: row counts differ ({R} vs {R2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    elif out.shape != (M, N) or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise _lib.AdvGrpoError("gemm_tn: out must be a contiguous bf16 [M, N] tensor")
+    _lib.call("advgrpo_gemm_tn_skinny", _ptr(a), _ptr(b), _ptr(out), R, M, N, 0, None, 0, _stream())
+    return out
+
+
+def col_sum(a, b=None, row_scale=None):
+    """f32 [C] = sum_r row_scale[r] * a[r, c] * b[r, c] (b / row_scale optional, not both); a, b bf16 [R, C]."""
+    _need_cuda(a)
+    a = _bf16c(a)
+    R, C = a.shape
+    b = None if b is None else _bf16c(b)
+    if row_scale is not None:
+        row_scale = row_scale.to(torch.float32).contiguous()
+    out = torch.empty(C, dtype=torch.float32, device=a.device)
+    ws = _workspace("col_sum", _lib.query("advgrpo_col_sum_workspace_bytes", R, C), a.device)
+    _lib.call("advgrpo_col_sum", _ptr(a), C, _ptr(b), C, _ptr(row_scale), _ptr(out), R, C, _ptr(ws), ws.numel(), _stream())
+    return out
+
+
+def _w16(t):
+    """bf16 view of a parameter for the tensor-core kernels (fp32 modules are cast per call; bf16 ones are used as is)."""
+    t = t.detach()
+    return (t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)).contiguous()
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM with a native backward: dx = dy W (the same kernel on the transposed weight),
+    dW = dy^T x (`gemm_tn`), db = column sums of dy (`col_sum`)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _bf16c(x).reshape(-1, x.shape[-1])
+        w = _w16(weight)
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, weight.dtype, None if bias is None else bias.dtype)
+        y = gemm(x2, w, bias=None if bias is None else _w16(bias))
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        shape, wdt, bdt = ctx.meta
+        dy2 = _bf16c(dy).reshape(-1, w.shape[0])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, w.t().contiguous()).reshape(shape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm_tn(dy2, x2).to(wdt)
+        if bdt is not None and ctx.needs_input_grad[2]:
+            db = col_sum(dy2).to(bdt)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """Differentiable nn.Linear on the native kernels (bf16 compute, fp32 accumulation).  in / out features multiples of 64."""
+    return _Linear.apply(x, weight, bias)
+
+
+class _MlpGelu(torch.autograd.Function):
+    """fc2(GELU_erf(fc1(x))) of a ViT block with the activation fused into the fc1 epilogue and its derivative into the
+    epilogue of the fc2 input-gradient GEMM (no elementwise pass, the hidden activation's gradient never exists in HBM)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = _bf16c(x).reshape(-1, x.shape[-1])
+        w1h, w2h = _w16(w1), _w16(w2)
+        z = torch.empty((x2.shape[0], w1h.shape[0]), dtype=torch.bfloat16, device=x2.device)
+        a = gemm(x2, w1h, bias=_w16(b1), epilogue=EPI_GELU_ERF, preact_out=z)
+        y = gemm(a, w2h, bias=_w16(b2))
+        ctx.save_for_backward(x2, w1h, w2h, z, a)
+        ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return y.reshape(*x.shape[:-1], w2h.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1h, w2h, z, a = ctx.saved_tensors
+        shape, w1dt, b1dt, w2dt, b2dt = ctx.meta
+        dy2 = _bf16c(dy).reshape(-1, w2h.shape[0])
+        dz = gemm(dy2, w2h.t().contiguous(), epilogue=EPI_GELU_ERF_GRAD, residual=z)
+        dx = gemm(dz, w1h.t().contiguous()).reshape(shape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm_tn(dz, x2).to(w1dt) if ctx.needs_input_grad[1] else None
+        db1 = col_sum(dz).to(b1dt) if ctx.needs_input_grad[2] else None
+        dw2 = gemm_tn(dy2, a).to(w2dt) if ctx.needs_input_grad[3] else None
+        db2 = col_sum(dy2).to(b2dt) if ctx.needs_input_grad[4] else None
+        return dx, dw1, db1, dw2, db2
+
+
+def mlp_gelu(x, w1, b1, w2, b2):
+    return _MlpGelu.apply(x, w1, b1, w2, b2)
+
+
+# --------------------------------------------------------------------------- score heads / discriminator step
+def gather_rows_l2norm(feats, idx, l2norm, eps=1e-6):
+    """feats bf16 [B, T, D], idx int64 [B, n] -> bf16 [B * (1 + n), D]: CLS row then the n patch rows 1 + idx per image,
+    optionally L2-normalised (`x / (|x| + eps)` with the bf16 rounding order of rewards.py:411-412)."""
+    _need_cuda(feats, idx)
+    feats = _bf16c(feats)
+    B, T, D = feats.shape
+    idx = idx.to(torch.int64).contiguous()
+    n = idx.shape[1]
+    out = torch.empty((B * (1 + n), D), dtype=torch.bfloat16, device=feats.device)
+    _lib.call("advgrpo_gather_rows_l2norm", _ptr(feats), _ptr(idx), _ptr(out), B, T, n, D, int(bool(l2norm)), float(eps), _stream())
+    return out
+
+
+def head_logits(a, w2, b2, round_bf16):
+    a = _bf16c(a)
+    R, Hd = a.shape
+    logits = torch.empty(R, dtype=torch.float32, device=a.device)
+    _lib.call("advgrpo_head_logits", _ptr(a), _ptr(w2), _ptr(b2), _ptr(logits), R, Hd, int(bool(round_bf16)), _stream())
+    return logits
+
+
+def dino_hybrid_score(logits, B, n, cls_weight, round_bf16):
+    hybrid = torch.empty(B, dtype=torch.float32, device=logits.device)
+    _lib.call("advgrpo_dino_hybrid_score", _ptr(logits), _ptr(hybrid), B, n, float(cls_weight), int(bool(round_bf16)), _stream())
+    return hybrid
+
+
+def dino_head_forward(head_params, rows, round_bf16, want_preact=False):
+    """DINOHead (Linear -> GELU -> Linear(1), train_sd3_fast_dino_patch.py:592-603) on the kernels: tcgen05 GEMM with the
+    erf-GELU epilogue, then the row-dot kernel.  head_params = (w1, b1, w2, b2) in any float dtype.  Returns
+    (logits f32 [R], a, z) with z = the pre-activation (None unless want_preact)."""
+    w1, b1, w2, b2 = (_w16(t) for t in head_params)
+    z = torch.empty((rows.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=rows.device) if want_preact else None
+    a = gemm(rows, w1, bias=b1, epilogue=EPI_GELU_ERF, preact_out=z)
+    return head_logits(a, w2.reshape(-1), b2.reshape(-1), round_bf16), a, z
+
+
+class _DinoHeadHinge(torch.autograd.Function):
+    """Discriminator loss of train_dino (train_sd3_fast_dino_patch.py:186-219) with the gradients of the four head
+    parameters computed natively in the forward pass (the loss is closed-form in the logits): gather -> GEMM + GELU ->
+    row-dot -> hinge -> dz -> (gemm_tn, col_sum).  Returns (loss, accuracy)."""
+
+    @staticmethod
+    def forward(ctx, w1, b1, w2, b2, feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight):
+        feats = torch.cat([feats_real, feats_fake]).to(torch.bfloat16)
+        idx = torch.cat([idx_real, idx_fake])
+        Br, Bf, n = feats_real.shape[0], feats_fake.shape[0], idx.shape[1]
+        rows = gather_rows_l2norm(feats, idx, l2norm=False)                 # the D step does not normalise the tokens
+        bf16_head = w1.dtype == torch.bfloat16
+        logits, a, z = dino_head_forward((w1, b1, w2, b2), rows, bf16_head, want_preact=True)
+        dl = torch.empty_like(logits)
+        out3 = torch.empty(3, dtype=torch.float32, device=logits.device)
+        _lib.call("advgrpo_dino_hinge_loss", _ptr(logits), _ptr(dl), _ptr(out3), Br, Bf, n, float(patch_loss_weight), _stream())
+        w2h = _w16(w2).reshape(-1)
+        dz = torch.empty_like(z)
+        _lib.call("advgrpo_head_dz", _ptr(dl), _ptr(w2h), _ptr(z), _ptr(dz), z.shape[0], z.shape[1], _stream())
+        dw1 = gemm_tn(dz, rows).to(w1.dtype)
+        db1 = col_sum(dz).to(b1.dtype)
+        dw2 = col_sum(a, row_scale=dl).reshape(w2.shape).to(w2.dtype)
+        db2 = out3[2].reshape(b2.shape).to(b2.dtype)
+        ctx.save_for_backward(dw1, db1, dw2, db2)
+        ctx.mark_non_differentiable(out3)
+        return out3[0].clone(), out3
+
+    @staticmethod
+    def backward(ctx, g_loss, _g):
+        dw1, db1, dw2, db2 = ctx.saved_tensors
+        g = g_loss.to(torch.float32)
+        sc = lambda t: (t.float() * g).to(t.dtype)
+        return sc(dw1), sc(db1), sc(dw2), sc(db2), None, None, None, None, None
+
+
+def dino_head_hinge_loss(head_params, feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight=0.3):
+    """Returns (loss, accuracy); `loss.backward()` deposits the native gradients in the head parameters."""
+    loss, out3 = _DinoHeadHinge.apply(*head_params, feats_real, feats_fake, idx_real, idx_fake, patch_loss_weight)
+    return loss, out3[1]
+
+
+def pickscore_head(img_feat, txt_feat, txt_index, logit_scale, bf16_arithmetic):
+    """scores f32 [B] = exp(logit_scale) * cos(img[b], txt[txt_index[b]]) / 26 (pickscore_scorer.py:44-51)."""
+    _need_cuda(img_feat, txt_feat)
+    img_feat, txt_feat = _bf16c(img_feat), _bf16c(txt_feat)
+    B, D = img_feat.shape
+    ls = logit_scale.detach()
+    if ls.dtype not in (torch.bfloat16, torch.float32):
+        ls = ls.float()
+    scores = torch.empty(B, dtype=torch.float32, device=img_feat.device)
+    ti = None if txt_index is None else txt_index.to(torch.int64).contiguous()
+    _lib.call("advgrpo_pickscore_head", _ptr(img_feat), _ptr(txt_feat), _ptr(ti), _ptr(ls), int(ls.dtype == torch.bfloat16),
+              _ptr(scores), B, txt_feat.shape[0], D, int(bool(bf16_arithmetic)), _stream())
+    return scores
+
+
+def adam_torch_order(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, zero_grad=False):
+    """In-place torch.optim.Adam update of one tensor (bf16 or fp32 parameter with moments of the same dtype) in torch's
+    multi-tensor op order, rounding to the parameter dtype after every op (csrc/heads.cu)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not t.is_contiguous() or t.numel() != n or t.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("adam_torch_order: contiguous bf16 / fp32 tensors of one size expected")
+    if exp_avg.dtype != param.dtype or exp_avg_sq.dtype != param.dtype:
+        raise ValueError("adam_torch_order: the moments carry the parameter's dtype (as torch.optim.Adam creates them)")
+    _lib.call("advgrpo_adam_torch_order", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n,
+              int(param.dtype == torch.bfloat16), int(grad.dtype == torch.bfloat16), float(lr), float(betas[0]),
+              float(betas[1]), float(eps), int(step), int(bool(zero_grad)), _stream())
+
+
+def row_softmax_f32(x, scale=1.0, round_tf32=False, out=None):
+    """softmax(scale * x) over the last dim of an fp32 matrix (in place when out is x)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise _lib.AdvGrpoError("row_softmax_f32 expects a contiguous float32 tensor")
+    cols = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    _lib.call("advgrpo_row_softmax_f32", _ptr(x), _ptr(out), x.numel() // cols, cols, float(scale), int(bool(round_tf32)), _stream())
     return out
 
 

@@ -172,9 +172,8 @@ class PickScoreScorer(torch.nn.Module):
             image_embs = self._image_tower(pixel_values)
         else:
             image_embs = model.get_image_features(pixel_values=pixel_values)
-        self._last_image_feats_bf16 = image_embs.to(torch.bfloat16)
-        image_embs = image_embs.float()
-        image_embs = image_embs / image_embs.norm(p=2, dim=-1, keepdim=True)
+        image_embs = image_embs.to(torch.bfloat16)
+        self._last_image_feats_bf16 = image_embs
         # the text tower is frozen: one forward per distinct prompt, cached across calls (generated and
         # reference images of a group share the prompt; the reference recomputes it for every image)
         tver = sum(p._version for p in model.text_model.parameters())
@@ -183,23 +182,14 @@ class PickScoreScorer(torch.nn.Module):
             hit = self._text_cache.get(pr)
             if hit is None or hit[0] != tver:
                 ids = self.processor.tokenizer([pr], padding=True, truncation=True, max_length=77)["input_ids"].to(self.device)
-                t16 = model.get_text_features(input_ids=ids).to(torch.bfloat16)
-                t = t16.float()
                 if len(self._text_cache) > 4096:
                     self._text_cache.clear()
-                hit = (tver, t / t.norm(p=2, dim=-1, keepdim=True), t16 / t16.norm(p=2, dim=-1, keepdim=True))
+                hit = (tver, model.get_text_features(input_ids=ids).to(torch.bfloat16))
                 self._text_cache[pr] = hit
             feats.append(hit[1])
-        text_embs = torch.cat(feats, 0)
-        index = torch.tensor([uniq.index(p) for p in prompt], device=self.device)
-        if self.reference_score_arithmetic:
-            bf = torch.bfloat16
-            # bf16 features were divided by their bf16 norms in the reference; redo that tail from the bf16 tower outputs
-            ie = self._last_image_feats_bf16
-            ie = ie / ie.norm(p=2, dim=-1, keepdim=True)
-            te = torch.cat([self._text_cache[pr][2] for pr in uniq], 0)[index]
-            # diag of `text_embs @ image_embs.T`: a bf16 matmul (fp32 products and accumulation, ONE rounding to bf16)
-            s_bf = model.logit_scale.exp().to(bf) * torch.bmm(te[:, None, :], ie[:, :, None]).reshape(-1)
-            return s_bf / 26
-        scores = model.logit_scale.exp().float() * (text_embs[index] * image_embs).sum(-1)
-        return scores / 26
+        text_embs = feats[0] if len(feats) == 1 else torch.cat(feats, 0)
+        index = None if len(uniq) == 1 else torch.tensor([uniq.index(p) for p in prompt], device=self.device)
+        # score tail (pickscore_scorer.py:44-51) as ONE kernel: L2 norms, row dot, exp(logit_scale) / 26 -- in fp32 on the
+        # bf16 tower outputs by default, or with the reference's bf16 rounding sequence and dtype (quirk Q10)
+        scores = ops.pickscore_head(image_embs, text_embs, index, model.logit_scale, self.reference_score_arithmetic)
+        return scores.to(torch.bfloat16) if self.reference_score_arithmetic else scores

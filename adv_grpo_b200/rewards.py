@@ -49,6 +49,8 @@ def pickscore_cotrain_score(device):
 
 
 def dino_patch_cotrain_score(device, n_patches=64):
+    from .dinov2 import dino_patch_scores
+
     def _fn(scorer, head, images, prompts, metadata, cls_weight=0.7):
         images = _to_unit_tensor(images, device)
         if images.dtype == torch.uint8:
@@ -56,19 +58,13 @@ def dino_patch_cotrain_score(device, n_patches=64):
         pix = ops.dino_preprocess(images, 518)                        # rewards.py:379-391 fused
         with torch.no_grad():
             feats = scorer.forward_features(pix)                       # [B, N+1, D]
-        cls_emb, patch_emb = feats[:, 0, :], feats[:, 1:, :]
-        B, N, D = patch_emb.shape
+        N = feats.shape[1] - 1
         n_select = min(n_patches, N)
-        idx = torch.randint(0, N, (B, n_select), device=feats.device)  # rewards.py:406
-        sampled = torch.gather(patch_emb, 1, idx.unsqueeze(-1).expand(-1, -1, D))
-        hp = next(head.parameters())
-        cls_emb = (cls_emb / (cls_emb.norm(dim=-1, keepdim=True) + 1e-6)).to(hp.dtype)
-        sampled = (sampled / (sampled.norm(dim=-1, keepdim=True) + 1e-6)).to(hp.dtype)
-        cls_score = head(cls_emb).squeeze(-1)
-        patch_scores = head(sampled).squeeze(-1)
-        hybrid = cls_weight * cls_score + (1 - cls_weight) * patch_scores.mean(dim=1)
-        return hybrid.detach(), {"cls_score": cls_score.detach(), "patch_scores": patch_scores.detach(),
-                                 "patch_indices": idx.detach(), "cls_weight": cls_weight}
+        idx = torch.randint(0, N, (feats.shape[0], n_select), device=feats.device)   # rewards.py:406
+        # gather + L2-norm (+1e-6) + DINOHead + 0.7 / 0.3 mix on the native kernels (rewards.py:408-419)
+        hybrid, cls_score, patch_scores = dino_patch_scores(head, feats, idx, cls_weight)
+        return hybrid, {"cls_score": cls_score, "patch_scores": patch_scores, "patch_indices": idx,
+                        "cls_weight": cls_weight}
 
     return _fn
 

@@ -1,19 +1,21 @@
 """SD3 VAE decoder (`pipeline.vae` of the reference: `fast.py:667-669`, kept in fp32 like
 `train_sd3_fast_pickscore.py:481`) + the `VaeImageProcessor.postprocess(output_type='pt')` step.
 
-Channels-last fp32 end to end.  Every 3x3 / 1x1 convolution with >= 32 channels on both sides (33 of the 35) runs on
-the tcgen05 TF32 implicit-GEMM kernel of csrc/conv.cu (TF32 tensor cores with fp32 accumulation, like the reference's
-fp32 VAE under cudnn.allow_tf32); conv_in (16 input channels) and conv_out (3 output channels) are library calls.
+Channels-last fp32 end to end.  EVERY convolution runs on the tcgen05 TF32 implicit-GEMM kernel of csrc/conv.cu (TF32
+tensor cores with fp32 accumulation, like the reference's fp32 VAE under cudnn.allow_tf32); conv_in (16 input channels)
+and conv_out (3 output channels) are zero-padded to the kernel's 32-channel granule (conv_out on 32-column tiles).
 Everything between the convolutions is fused into our streaming kernels so that no tensor makes an extra HBM round trip:
   * GroupNorm + SiLU in two passes, with the PRECEDING convolution's bias folded into the statistics/apply
     (the convolutions run bias-free: no separate bias pass, no NCHW<->NHWC copies around group_norm);
   * residual add + conv2 bias (+ shortcut bias) in one pass;
   * nearest 2x upsampling as one vectorised pass; GroupNorm-apply and upsample hand their outputs over as TF32 values
     (round to nearest) so the tensor core's operand truncation is exact;
-  * the single-head mid-block attention as two TF32 batched GEMMs + softmax instead of an fp32 SIMT fmha.
+  * the single-head mid-block attention on the same kernel: the q / k / v / out projections are 1x1 convolutions, the
+    scores Q K^T are a 1x1 convolution whose "weights" are the sample's K matrix, V^T comes out of a 1x1 convolution of
+    the V weight matrix against the tokens, softmax is one fp32 row kernel (csrc/heads.cu) that hands P over as TF32
+    values, and P V is a 1x1 convolution with V^T as the weights -- no library GEMM, no fp32 SIMT fmha.
 diffusers state-dict names."""
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .weights import VAE_SD3
@@ -63,17 +65,30 @@ class AutoencoderKL:
     def _conv(self, name, x, pad=1, bias=True):
         w = self.p[name + ".weight"]
         Cout, Cin, k, _ = w.shape
-        if self.native_conv and self.fused and Cin % 32 == 0 and Cout % 32 == 0 and k in (1, 3) and pad == k // 2:
-            key = name + ".packed_tf32"
-            if key not in self.p:
-                self.p[key] = ops.pack_conv_weight_tf32(w)
-            return ops.conv2d_nhwc_tf32(x, self.p[key], self.p[name + ".bias"] if bias else None, k)
-        # conv_in (16 input channels) and conv_out (3 output channels) are the two documented library calls (cuDNN,
-        # 0.3 % of the decoder FLOPs); any other shape the native kernel cannot take is an error, not a silent fallback
-        if name not in ("decoder.conv_in", "decoder.conv_out") and self.native_conv:
+        if not (self.native_conv and self.fused and k in (1, 3) and pad == k // 2):
             raise ValueError(f"convolution {name} ({Cin} -> {Cout}, k={k}, pad={pad}) is not supported by conv_tf32_kernel "
-                             "(channels must be multiples of 32, k in {1, 3}, pad = k // 2)")
-        return F.conv2d(x, w, self.p[name + ".bias"] if bias else None, padding=pad)
+                             "(k in {1, 3}, pad = k // 2); there is no PyTorch fallback")
+        cin_p, cout_p = -(-Cin // 32) * 32, -(-Cout // 32) * 32
+        key = name + ".packed_tf32"
+        if key not in self.p:
+            if (cin_p, cout_p) != (Cin, Cout):          # conv_in: 16 -> 32 zero input channels; conv_out: 3 -> 32 zero filters
+                wp = torch.zeros(cout_p, cin_p, k, k, dtype=w.dtype, device=w.device)
+                wp[:Cout, :Cin] = w
+                w = wp
+                bp = torch.zeros(cout_p, dtype=w.dtype, device=w.device)
+                bp[:Cout] = self.p[name + ".bias"]
+                self.p[name + ".fused_bias"] = bp
+            self.p[key] = ops.pack_conv_weight_tf32(w)
+        if cin_p != Cin:
+            xp = torch.empty((x.shape[0], cin_p, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                             memory_format=torch.channels_last).zero_()
+            xp[:, :Cin] = x
+            x = xp
+        b = None
+        if bias:
+            b = self.p[name + ".fused_bias"] if cout_p != Cout or cin_p != Cin else self.p[name + ".bias"]
+        y = ops.conv2d_nhwc_tf32(x, self.p[key], b, k)
+        return y if cout_p == Cout else y[:, :Cout]
 
     def _resnet(self, pre, x):
         p = self.p
@@ -95,18 +110,39 @@ class AutoencoderKL:
             bias = p[key]
         return ops.add_bias_nhwc(x, h, bias)
 
+    def _lin_w(self, name):
+        """nn.Linear weight [Cout, Cin] as a packed 1x1-convolution weight (TF32-rounded)."""
+        key = name + ".packed_tf32"
+        if key not in self.p:
+            w = self.p[name + ".weight"]
+            self.p[key] = ops.pack_conv_weight_tf32(w.reshape(w.shape[0], w.shape[1], 1, 1))
+        return self.p[key]
+
     def _mid_attn(self, pre, x):
         p = self.p
         B, C, H, W = x.shape
-        h = self._gn(pre + ".group_norm", x)
-        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)                       # NHWC storage: a view, no copy
-        q, k, v = (F.linear(h, p[f"{pre}.to_{n}.weight"], p[f"{pre}.to_{n}.bias"]) for n in "qkv")
-        # single-head attention over the 64 x 64 latent grid (1 % of the decoder FLOPs): two TF32 cuBLAS batched GEMMs
-        # + softmax, the third documented library call of the decoder
-        s = torch.bmm(q * (C ** -0.5), k.transpose(1, 2))
-        o = torch.bmm(torch.softmax(s, dim=-1), v)
-        o = F.linear(o, p[pre + ".to_out.0.weight"], p[pre + ".to_out.0.bias"])
-        o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                         # logical NCHW, channels_last strides
+        S = H * W
+        h = self._gn(pre + ".group_norm", x)                                   # TF32-rounded tokens, NHWC = [B, S, C]
+        q = ops.conv2d_nhwc_tf32(h, self._lin_w(pre + ".to_q"), p[pre + ".to_q.bias"], 1)
+        k = ops.conv2d_nhwc_tf32(h, self._lin_w(pre + ".to_k"), p[pre + ".to_k.bias"], 1)
+        o = torch.empty_like(q, memory_format=torch.channels_last)
+        o_rows = o.permute(0, 2, 3, 1)                                         # [B, H, W, C] view of the NHWC storage
+        k_rows = k.permute(0, 2, 3, 1).reshape(B, S, C)
+        h_rows = h.permute(0, 2, 3, 1).reshape(B, S, C)
+        # the V weight matrix as a "C-pixel image" [1, C, C / cw, cw]: a 1x1 convolution of it against the tokens
+        # (weights = h[b], [S, C]) yields V^T [C, S] directly, the K-major operand the P V product needs
+        cw = min(C, 128)
+        wv_img = self._lin_w(pre + ".to_v").view(1, C // cw, cw, C).permute(0, 3, 1, 2)
+        for b in range(B):                                                     # single head, per sample: K / V are weights
+            s = ops.conv2d_nhwc_tf32(q[b:b + 1], k_rows[b], None, 1)           # [1, S(keys), H, W]: scores[query, key]
+            s_rows = s.permute(0, 2, 3, 1).reshape(S, S)
+            ops.row_softmax_f32(s_rows, scale=C ** -0.5, round_tf32=True, out=s_rows)
+            vt = ops.conv2d_nhwc_tf32(wv_img, h_rows[b], None, 1)              # [1, S, C / cw, cw] = V^T (bias-free)
+            vt = vt.permute(0, 2, 3, 1).reshape(C, S)
+            # rows of P sum to one, so the V bias passes through the attention unchanged: it is this product's bias
+            ob = ops.conv2d_nhwc_tf32(s, vt, p[pre + ".to_v.bias"], 1)         # [1, C, H, W]
+            o_rows[b].copy_(ob.permute(0, 2, 3, 1)[0])
+        o = ops.conv2d_nhwc_tf32(o, self._lin_w(pre + ".to_out.0"), p[pre + ".to_out.0.bias"], 1)
         return ops.add_bias_nhwc(x, o, None)
 
     def _upsample(self, x):

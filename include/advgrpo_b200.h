@@ -293,6 +293,8 @@ int advgrpo_gemm_tn_skinny(const void* a, const void* b, void* out, int64_t Kt, 
 #define ADVGRPO_EPI_QUICK_GELU 5 /* x * sigmoid(1.702 x): the CLIP-L text encoder of encode_prompt */
 #define ADVGRPO_EPI_GELU_TANH_GRAD 6 /* C = acc * gelu_tanh'(z), z = bf16 [M, N] passed as `residual` (ld ldr): the backward
                                         of a GELU feed-forward, dz = (dy W2) * gelu'(z), without a separate elementwise pass */
+#define ADVGRPO_EPI_GELU_ERF_GRAD 7  /* the same with the erf GELU's derivative (CLIP-H / DINOv2 MLPs: the discriminator step's
+                                        backward through the trainable vision blocks, train_sd3_fast_pickscore.py:1016-1029) */
 int advgrpo_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* A2,
                       int64_t lda2, const void* W2, int64_t ldw2, int64_t K2, const void* bias,
                       void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int epilogue,
@@ -381,6 +383,66 @@ int advgrpo_upsample_nearest2x_nhwc(const float* x, float* y, int64_t B, int64_t
  */
 int advgrpo_conv2d_nhwc_tf32(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t H, int64_t W,
                              int64_t Cin, int64_t Cout, int ksize, advgrpo_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * A8a / A8b score heads and the A14 / A15 discriminator step (`score_head_{pickscore,dino_patch}`).
+ *
+ * advgrpo_gather_rows_l2norm: feats bf16 [B, T, D] (DINOv2 `forward_features`: token 0 = CLS) and idx int64 [B, n]
+ *   (the torch.randint draw of adv_grpo/rewards.py:406 / train_sd3_fast_dino_patch.py:199-200) -> out bf16 [B (1 + n), D]:
+ *   row b (1 + n) is the CLS token, the next n rows are patch tokens 1 + idx[b, :].  l2norm != 0: every row is divided by
+ *   (|row| + eps) with the bf16 rounding order of `x / (x.norm(dim=-1, keepdim=True) + 1e-6)` on bf16 tensors
+ *   (rewards.py:411-412; the D step of train_dino does not normalise: l2norm = 0).
+ * advgrpo_head_logits: logits f32 [R] = a[R, Hd] . w2[Hd] + b2 -- the Linear(hidden, 1) of DINOHead
+ *   (train_sd3_fast_dino_patch.py:592-603); `a` = GELU(Linear(in, hidden)) from advgrpo_gemm_bf16 (GELU_ERF epilogue).
+ *   round_bf16: round the logit to bf16 (the reference head is a bf16 module, train_sd3_fast_dino_patch.py:745).
+ * advgrpo_dino_hybrid_score: hybrid[b] = cls_weight * logit[b, 0] + (1 - cls_weight) * mean_j logit[b, 1 + j]
+ *   (rewards.py:414-419).
+ * advgrpo_dino_hinge_loss: the discriminator loss of train_dino (train_sd3_fast_dino_patch.py:186-219) on logits
+ *   [(B_real + B_fake), 1 + n] (real images first): out3 = {loss, accuracy on the CLS logits, sum of dlogits};
+ *   dlogits f32 [R] = d loss / d logit.
+ * advgrpo_head_dz: dz bf16 [R, Hd] = (dlogits[r] * w2[:]) * gelu_erf'(z[r, :]): backward through Linear(hidden, 1) + GELU.
+ * advgrpo_col_sum: out f32 [C] = sum_r scale[r] * a[r, c] * b[r, c] (b, scale optional, not both): bias gradients and the
+ *   head's d w2 = sum_r dlogits[r] a[r, :]; deterministic two-stage reduction.  a, b bf16, leading dimensions lda / ldb.
+ */
+int advgrpo_gather_rows_l2norm(const void* feats, const int64_t* idx, void* out, int64_t B, int64_t T, int64_t n, int64_t D,
+                               int l2norm, float eps, advgrpo_stream_t stream);
+int advgrpo_head_logits(const void* a, const void* w2, const void* b2, float* logits, int64_t R, int64_t Hd, int round_bf16,
+                        advgrpo_stream_t stream);
+int advgrpo_dino_hybrid_score(const float* logits, float* hybrid, int64_t B, int64_t n, float cls_weight, int round_bf16,
+                              advgrpo_stream_t stream);
+int advgrpo_dino_hinge_loss(const float* logits, float* dlogits, float* out3, int64_t B_real, int64_t B_fake, int64_t n,
+                            float patch_loss_weight, advgrpo_stream_t stream);
+int advgrpo_head_dz(const float* dlogits, const void* w2, const void* z, void* dz, int64_t R, int64_t Hd,
+                    advgrpo_stream_t stream);
+size_t advgrpo_col_sum_workspace_bytes(int64_t rows, int64_t C);
+int advgrpo_col_sum(const void* a, int64_t lda, const void* b, int64_t ldb, const float* row_scale, float* out, int64_t rows,
+                    int64_t C, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
+/* PickScore score tail (adv_grpo/pickscore_scorer.py:44-51): scores[b] = exp(logit_scale) * <img[b] / |img[b]|,
+ * txt[i] / |txt[i]|> / 26 with i = txt_index[b] (NULL: b % n_txt).  img bf16 [B, D], txt bf16 [n_txt, D]; logit_scale is a
+ * DEVICE scalar (bf16 or f32: no host read).  bf16_arithmetic != 0 reproduces the reference's bf16 model: norms, quotients,
+ * the dot product, the scaling and the division by 26 are each rounded to bf16 (quirk Q10); 0 = fp32 tail. */
+int advgrpo_pickscore_head(const void* img_feat, const void* txt_feat, const int64_t* txt_index, const void* logit_scale,
+                           int logit_scale_is_bf16, float* scores, int64_t B, int64_t n_txt, int64_t D, int bf16_arithmetic,
+                           advgrpo_stream_t stream);
+/* Backward of the affine LayerNorm of a trainable CLIP block (train_sd3_fast_pickscore.py:1016-1029): dx bf16 [rows, D];
+ * dweight / dbias f32 [D] (both NULL when the LayerNorm parameters are frozen).  D a multiple of 8, <= 2048. */
+size_t advgrpo_layer_norm_affine_bwd_workspace_bytes(int64_t rows, int64_t D);
+int advgrpo_layer_norm_affine_bwd(const void* x, const void* weight, const void* dy, void* dx, float* dweight, float* dbias,
+                                  int64_t rows, int64_t D, float eps, void* workspace, size_t workspace_bytes,
+                                  advgrpo_stream_t stream);
+/* The discriminator optimizers (`torch.optim.Adam(params, lr=config.d_lr, betas=(0.5, 0.999))`, train_sd3_fast_pickscore.py:658,
+ * train_sd3_fast_dino_patch.py:750) as one pass per tensor in torch's multi-tensor op order (lerp_, mul_, addcmul_, sqrt,
+ * div_, add_, addcdiv_), rounding to the parameter dtype after every op: bf16 parameters with bf16 moments follow the
+ * reference's arithmetic.  param / exp_avg / exp_avg_sq: bf16 or f32 [n] (param_is_bf16); grad bf16 or f32 (grad_is_bf16);
+ * step >= 1 is the step count AFTER this update; zero_grad != 0 clears the gradient in the same pass. */
+int advgrpo_adam_torch_order(void* param, void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, int param_is_bf16,
+                             int grad_is_bf16, double lr, double beta1, double beta2, double eps, int64_t step, int zero_grad,
+                             advgrpo_stream_t stream);
+/* y = softmax(scale * x) over fp32 rows (in place allowed), optionally rounded to TF32: the probability matrix of the VAE
+ * decoder's single-head mid-block attention (diffusers AutoencoderKL, sd3_pipeline_with_logprob_fast.py:669) between the two
+ * TF32 tensor-core products advgrpo_conv2d_nhwc_tf32 computes (scores = 1x1 convolution with K as the weights). */
+int advgrpo_row_softmax_f32(const float* x, float* y, int64_t rows, int64_t cols, float scale, int round_tf32,
+                            advgrpo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -426,13 +426,15 @@ def test_vae_decoder_matches_oracle_at_true_widths():
     # the convolutions run in TF32 (tcgen05 kind::tf32 here, cuDNN TF32 in the reference's fp32 VAE under PyTorch's
     # default cudnn.allow_tf32): bound our deviation from the fp32 oracle by that of the library TF32 path on the
     # same decoder, and report both
-    vae.native_conv = False
+    # library TF32 path: the oracle's own decoder (torch convolutions / matmuls) on the GPU with TF32 allowed
+    prev_mm = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        lib = VaeImageProcessor().postprocess(vae.decode(z.to(DEV) / 1.5305 + 0.0609)[0], output_type="pt").cpu()
+        lib = vae_o.decode_latents_to_image({k: v.to(DEV) for k, v in vp.items()}, z.to(DEV)).cpu()
     finally:
         torch.backends.cudnn.allow_tf32 = prev
-        vae.native_conv = True
+        torch.backends.cuda.matmul.allow_tf32 = prev_mm
     err, err_lib = (got - ref).abs().max().item(), (lib - ref).abs().max().item()
     print(f"VAE decode max |err| vs fp32 oracle: tcgen05 TF32 {err:.2e}, cuDNN TF32 {err_lib:.2e}")
     assert err < max(2e-3, 2.0 * err_lib), (err, err_lib)
@@ -555,12 +557,23 @@ def test_layer_norm_affine_matches_torch_fp32(ops, rows, D, eps):
     ref = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), eps)
     err = (y.float().cpu() - ref).abs()
     assert (err <= ref.abs() * 2.0 ** -8 + 1e-6).all(), err.max()
-    # 3-D input keeps its shape; a tensor that needs a gradient goes through autograd's LayerNorm
+    # 3-D input keeps its shape
     x3 = x.to(DEV).view(1, rows, D)
     assert ops.layer_norm(x3, w.to(DEV), b.to(DEV), eps).shape == x3.shape
-    xg = x.to(DEV).float().requires_grad_()
-    ops.layer_norm(xg, w.to(DEV).float(), b.to(DEV).float(), eps).sum().backward()
-    assert xg.grad is not None
+    # native backward (A14: the LayerNorms of the trainable CLIP blocks): dx, d weight, d bias vs torch fp32 autograd
+    xg, wg, bg = (t.to(DEV).clone().requires_grad_() for t in (x, w, b))
+    dy = torch.randn(rows, D, generator=g).bfloat16()
+    ops.layer_norm(xg, wg, bg, eps).backward(dy.to(DEV))
+    xr, wr, br = (t.float().clone().requires_grad_() for t in (x, w, b))
+    torch.nn.functional.layer_norm(xr, (D,), wr, br, eps).backward(dy.float())
+    for got, ref_g in ((xg.grad, xr.grad), (wg.grad, wr.grad), (bg.grad, br.grad)):
+        assert got.dtype == torch.bfloat16
+        rel = (got.float().cpu() - ref_g).norm().item() / max(ref_g.norm().item(), 1e-12)
+        assert rel < 6e-3, rel                                   # one bf16 rounding of the result
+    # frozen parameters (post_layernorm during the D step): only dx
+    xg2 = x.to(DEV).clone().requires_grad_()
+    ops.layer_norm(xg2, w.to(DEV), b.to(DEV), eps).backward(dy.to(DEV))
+    assert torch.equal(xg2.grad, xg.grad)
 
 
 def test_stat_tracker_device_path_counts_distinct_prompts_and_handles_long_T(ops):
