@@ -73,6 +73,8 @@ SIGNATURES = {
     "advgrpo_layer_norm_affine_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P, _SZ, _P]),
     "advgrpo_adam_torch_order": (c_int, [_P, _P, _P, _P, _I64, _I, _I, _D, _D, _D, _D, _I64, _I, _P]),
     "advgrpo_row_softmax_f32": (c_int, [_P, _P, _I64, _I64, _F, _I, _P]),
+    "advgrpo_attn_small_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P]),
+    "advgrpo_attn_small_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P]),
 }
 # test/bench hooks that are exported but not part of include/advgrpo_b200.h
 _EXTRA = {
@@ -111,7 +113,7 @@ def load():
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
-                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_device_check": 0}
+                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_device_check": 0}
 _launches = [0]
 
 

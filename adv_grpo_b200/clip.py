@@ -9,12 +9,12 @@ parameter's version counter changes); layers with requires_grad parameters under
 `tune_layer` vision blocks during the discriminator step) run through differentiable native ops: affine LayerNorm
 (`ops.layer_norm`, native dx / d weight / d bias), every Linear on the tcgen05 GEMM with weight gradients on the
 split-K TN kernel and bias gradients on the column-sum kernel (`ops.linear`), the MLP with the erf-GELU and its
-derivative fused into GEMM epilogues (`ops.mlp_gelu`).  Only the head_dim-80 softmax(QK^T)V core of those one or two
-blocks goes through torch's SDPA (forward + backward): the D = 64 attention-backward kernel's TMEM layout has no room
-for a 128-wide head.
+derivative fused into GEMM epilogues (`ops.mlp_gelu`), and the 257-token, head_dim-80 softmax(QK^T)V core with its backward
+on the shared-memory-resident short-sequence kernel (`ops.attention_small`, csrc/attn_small.cu: the D = 64 tcgen05
+attention-backward kernel's TMEM layout has no room for a 128-wide head).  No torch SDPA / nn.Linear / LayerNorm call is
+left on the discriminator step.
 """
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import ops, vit
@@ -65,9 +65,8 @@ class CLIPEncoderLayer(nn.Module):
         hd = W // self.heads
         ln1, ln2, a, m = self.layer_norm1, self.layer_norm2, self.self_attn, self.mlp
         h = ops.layer_norm(x, ln1.weight, ln1.bias, ln1.eps)
-        q, k, v = (ops.linear(h, l.weight, l.bias).view(B, S, self.heads, hd).transpose(1, 2)
-                   for l in (a.q_proj, a.k_proj, a.v_proj))
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, S, W)
+        q, k, v = (ops.linear(h, l.weight, l.bias).view(B, S, self.heads, hd) for l in (a.q_proj, a.k_proj, a.v_proj))
+        o = ops.attention_small(q, k, v, scale=hd ** -0.5, causal=causal).reshape(B, S, W)
         x = x + ops.linear(o, a.out_proj.weight, a.out_proj.bias)
         return x + ops.mlp_gelu(ops.layer_norm(x, ln2.weight, ln2.bias, ln2.eps), m.fc1.weight, m.fc1.bias,
                                 m.fc2.weight, m.fc2.bias)

@@ -450,6 +450,41 @@ def attention(qkv, scale=None, causal=False):
     return attention_fwd(qkv, scale, causal, want_lse=False)[0]
 
 
+class _AttentionSmall(torch.autograd.Function):
+    """softmax(scale q k^T) v for short sequences / odd head sizes with a native backward (csrc/attn_small.cu): the
+    attention core of the trainable CLIP-H vision blocks (257 tokens, head_dim 80) in the PickScore discriminator step."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal):
+        q, k, v = _bf16c(q), _bf16c(k), _bf16c(v)
+        B, S, H, Dh = q.shape
+        o = torch.empty_like(q)
+        lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+        _lib.call("advgrpo_attn_small_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, S, H, Dh, float(scale),
+                  int(bool(causal)), _stream())
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (float(scale), int(bool(causal)))
+        return o
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, o, lse = ctx.saved_tensors
+        B, S, H, Dh = q.shape
+        dout = _bf16c(dout)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty_like(lse)
+        _lib.call("advgrpo_attn_small_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(dout), _ptr(lse), _ptr(delta), _ptr(dq),
+                  _ptr(dk), _ptr(dv), B, S, H, Dh, ctx.meta[0], ctx.meta[1], _stream())
+        return dq, dk, dv, None, None
+
+
+def attention_small(q, k, v, scale=None, causal=False):
+    """q, k, v bf16 [B, S, H, Dh] (Dh even, <= 128; S * Dh bounded by shared memory) -> o bf16 [B, S, H, Dh]; differentiable."""
+    _need_cuda(q, k, v)
+    scale = (1.0 / math.sqrt(q.shape[-1])) if scale is None else scale
+    return _AttentionSmall.apply(q, k, v, scale, causal)
+
+
 # --------------------------------------------------------------------------- GEMM
 def set_gemm_variant(v):
     """Test/bench hook: 0 = auto (CTA pairs when the shape allows), 1 = single-CTA tiles only."""

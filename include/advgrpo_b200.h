@@ -444,6 +444,19 @@ int advgrpo_adam_torch_order(void* param, void* grad, void* exp_avg, void* exp_a
 int advgrpo_row_softmax_f32(const float* x, float* y, int64_t rows, int64_t cols, float scale, int round_tf32,
                             advgrpo_stream_t stream);
 
+/* Differentiable attention for short sequences and head sizes outside the tcgen05 backward kernel (CLIP-ViT-H/14: 257
+ * tokens, head_dim 80): the softmax(Q K^T) V core of the vision blocks the PickScore discriminator step trains
+ * (train_sd3_fast_pickscore.py:1016-1029; F.scaled_dot_product_attention inside transformers' CLIPAttention and its
+ * autograd).  fp32 arithmetic on the CUDA cores with K / V (backward: also Q / dO) of one (sample, head) resident in
+ * shared memory; q, k, v, o, dout, dq, dk, dv: bf16 [B, S, H, Dh] (the projections' [B, S, H * Dh] outputs viewed per
+ * head); lse, delta: f32 [B, H, S] (delta is scratch written by the backward).  Dh even, <= 128; S * Dh bounded by the
+ * 227 KB of shared memory (ADVGRPO_ERR_UNSUPPORTED beyond: S <= 544 at Dh = 80).  causal != 0: key j <= query i. */
+int advgrpo_attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t H,
+                           int64_t Dh, float scale, int causal, advgrpo_stream_t stream);
+int advgrpo_attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                           float* delta, void* dq, void* dk, void* dv, int64_t B, int64_t S, int64_t H, int64_t Dh, float scale,
+                           int causal, advgrpo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -264,3 +264,29 @@ def test_vae_mid_attention_matches_fp64():
     ref = x.double() + o.reshape(2, 16, 16, 512).permute(0, 3, 1, 2)
     err = (got.double() - ref).abs().max().item()
     assert err <= 4e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("B,S,H,Dh", [(2, 257, 16, 80), (3, 50, 4, 64), (1, 512, 2, 80), (2, 33, 3, 128), (1, 1, 1, 16), (2, 77, 16, 64)])
+def test_attention_small_fwd_bwd_matches_torch_fp32(ops, B, S, H, Dh, causal):
+    """The attention core of the trainable CLIP-H blocks (A14): forward and all three input gradients vs fp32 torch SDPA
+    on the same bf16 values; outputs are one bf16 rounding of fp32 results."""
+    g = torch.Generator(device=DEV).manual_seed(S + Dh)
+    q, k, v, do = (torch.randn(B, S, H, Dh, device=DEV, generator=g).bfloat16() for _ in range(4))
+    qg, kg, vg = (t.clone().requires_grad_() for t in (q, k, v))
+    o = ops.attention_small(qg, kg, vg, causal=causal)
+    o.backward(do)
+    qr, kr, vr = (t.float().transpose(1, 2).clone().requires_grad_() for t in (q, k, v))
+    ref = torch.nn.functional.scaled_dot_product_attention(qr, kr, vr, is_causal=causal)
+    ref.backward(do.float().transpose(1, 2))
+    assert o.shape == (B, S, H, Dh) and o.dtype == torch.bfloat16
+    assert _rel(o, ref.transpose(1, 2)) < 5e-3
+    for got, r in ((qg.grad, qr.grad), (kg.grad, kr.grad), (vg.grad, vr.grad)):
+        assert _rel(got, r.transpose(1, 2)) < 6e-3, _rel(got, r.transpose(1, 2))
+
+
+def test_attention_small_rejects_what_does_not_fit(ops):
+    from adv_grpo_b200 import _lib
+    q = torch.zeros(1, 4096, 1, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.AdvGrpoError):
+        ops.attention_small(q, q, q)
