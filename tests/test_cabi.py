@@ -75,6 +75,15 @@ def test_empty_inputs_are_noops_or_clean_errors():
         ("advgrpo_row_gate_mul", (buf, buf, 1536, 1, buf, 0, 1536, None)),
         ("advgrpo_qk_norm_concat_fwd", (buf, None, buf, buf, None, None, buf, 0, 16, 0, 24, 64, 1e-6, None)),
         ("advgrpo_clip_adamw", (buf, buf, buf, buf, 0, 3e-4, 0.9, 0.999, 1e-8, 1e-4, 1, 1.0, 1, None, None, 0, None)),
+        # score heads / discriminator step (csrc/heads.cu): an empty batch of images / rows / parameters is a no-op
+        ("advgrpo_gather_rows_l2norm", (buf, buf, buf, 0, 1370, 64, 768, 1, 1e-6, None)),
+        ("advgrpo_head_logits", (buf, buf, buf, buf, 0, 512, 1, None)),
+        ("advgrpo_dino_hybrid_score", (buf, buf, 0, 64, 0.7, 1, None)),
+        ("advgrpo_head_dz", (buf, buf, buf, buf, 0, 512, None)),
+        ("advgrpo_pickscore_head", (buf, buf, None, buf, 1, buf, 0, 1, 1024, 0, None)),
+        ("advgrpo_adam_torch_order", (buf, buf, buf, buf, 0, 1, 1, 5e-6, 0.5, 0.999, 1e-8, 1, 0, None)),
+        ("advgrpo_row_softmax_f32", (buf, buf, 0, 4096, 1.0, 1, None)),
+        ("advgrpo_col_sum", (buf, 512, None, 0, None, buf, 0, 0, None, 0, None)),
     ]
     for name, args in ok:
         assert _lib.call(name, *args) == 0, name
@@ -84,6 +93,13 @@ def test_empty_inputs_are_noops_or_clean_errors():
         ("advgrpo_conv2d_nhwc_tf32", (buf, buf, None, buf, 0, 8, 8, 64, 64, 3, None)),
         ("advgrpo_dino_preprocess", (buf, 0, 0, 64, 64, 518, buf, buf, buf, None)),
         ("advgrpo_upsample_nearest2x_nhwc", (buf, buf, 0, 8, 8, 64, None)),
+        ("advgrpo_gather_rows_l2norm", (buf, buf, buf, 2, 1370, 64, 770, 1, 1e-6, None)),            # D not a multiple of 8
+        ("advgrpo_dino_hinge_loss", (buf, buf, buf, 0, 4, 64, 0.3, None)),                           # no real images
+        ("advgrpo_adam_torch_order", (buf, buf, buf, buf, 16, 1, 1, 5e-6, 0.5, 0.999, 1e-8, 0, 0, None)),   # step 0
+        ("advgrpo_layer_norm_affine_bwd", (buf, buf, buf, buf, buf, None, 4, 1280, 1e-5, None, 0, None)),   # dweight without dbias
+        ("advgrpo_attn_small_fwd", (buf, buf, buf, buf, None, 1, 257, 16, 81, 0.1, 0, None)),        # odd head_dim
+        ("advgrpo_attn_small_bwd", (buf, buf, buf, buf, buf, buf, buf, buf, buf, buf, 1, 4096, 1, 64, 0.125, 0, None)),  # too long
+        ("advgrpo_row_softmax_f32", (buf, buf, 3, 6, 1.0, 0, None)),                                 # cols not a multiple of 4
     ]
     for name, args in bad:
         with pytest.raises(_lib.AdvGrpoError):

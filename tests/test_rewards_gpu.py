@@ -43,7 +43,8 @@ def test_pickscore_scorer_matches_oracle():
     model = sc_ref.model
     ie = sc_ref._last_image_feats_bf16
     ids1 = [scorer.processor.tokenizer([p], padding=True, truncation=True, max_length=77)["input_ids"].to(DEV) for p in prompts]
-    te = torch.cat([model.get_text_features(input_ids=i).to(bf) for i in ids1], 0)
+    with torch.no_grad():                     # the frozen fast path the scorer itself uses (same tower outputs)
+        te = torch.cat([model.get_text_features(input_ids=i).to(bf) for i in ids1], 0)
     want = (model.logit_scale.exp().to(bf) * ((te / te.norm(p=2, dim=-1, keepdim=True)) @ (ie / ie.norm(p=2, dim=-1, keepdim=True)).T)).diag() / 26
     assert (s16.float() - want.float()).abs().max().item() <= 2 * 2.0 ** -8 * want.float().abs().max().item()
     assert (s16.float().cpu() - scores).abs().max().item() < 3e-2          # bf16 tail vs fp32 tail on the same features
