@@ -10,7 +10,7 @@ Everything between the collectives stays on the device: no `.cpu().numpy()` of r
 decode of prompt ids, no float64 host advantages.
 """
 import math
-
+import os
 import warnings
 
 import torch
@@ -292,8 +292,14 @@ class GRPOTrainer:
             loss, acc = dino_hinge_d_loss(self.head, fr, ff, ir, if_, 0.3)               # train_dino:186-219
             self.last_info["d_acc"] = acc.detach()
             params = list(self.head.parameters())
+        trace = os.environ.get("ADVGRPO_TRACE_DSTEP", "0") == "1"      # CUDA-event split of the D step into last_info
+        if trace:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record()
         self.optimizer_D.zero_grad()
         loss.backward()
+        if trace:
+            evs[1].record()
         if self.world > 1 and self.sync_discriminator:
             flat = torch.cat([p.grad.reshape(-1).float() for p in params])
             dist.all_reduce(flat)
@@ -302,7 +308,14 @@ class GRPOTrainer:
             for p in params:
                 p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
                 off += p.numel()
+        if trace:
+            evs[2].record()
         self.optimizer_D.step()
+        if trace:
+            evs[3].record()
+            torch.cuda.synchronize()
+            self.last_info["d_step_ms"] = dict(backward=evs[0].elapsed_time(evs[1]), grad_sync=evs[1].elapsed_time(evs[2]),
+                                               optimizer=evs[2].elapsed_time(evs[3]))
         return loss.detach()
 
     # ------------------------------------------------------------------ generator step

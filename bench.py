@@ -394,6 +394,8 @@ def run_ours(args):
               "update": ev[2].elapsed_time(ev[3])}
     if spec["train_d"]:
         phases["discriminator_update"] = ev[3].elapsed_time(ev[4])
+        if "d_step_ms" in trainer.last_info:                       # ADVGRPO_TRACE_DSTEP=1: backward / grad sync / optimizer
+            phases["discriminator_update_split"] = trainer.last_info["d_step_ms"]
     del smp, adv
     samples = world * nb * gsz * args.steps
     value = samples / (ms_dev / 1e3)
