@@ -330,3 +330,73 @@ def test_pickscore_discriminator_last_block_grads_match_oracle_autograd():
         assert cos > 0.95 and rel < 0.35, (name, cos, rel)
         checked += 1
     assert checked >= 10
+
+
+def test_config4_shape_replay_logprob_and_loss_match_oracle():
+    """BASELINE config 4 shape (SD3.5-medium TRUE size, 1024x1024 = 4096 + 205 joint tokens, 20 denoise steps, CFG 4.5,
+    noise 0.8): the GPU rolls out one CFG pair; the first trained transition is replayed teacher-forced by the GPU path and
+    by the fp32 CPU oracle on the GPU's own stored latents (train_sd3_fast_pickscore.py:233-267,1104-1123).  Same bars as
+    the config-2 test: prev_sample_mean within 1e-2 of the latent range per element, replay log-prob within 2e-3 absolute,
+    clipped GRPO step loss within 1e-3 relative.  This is the S = 4301 joint attention (24 heads) and every GEMM at
+    M = 2 x 4301 inside the full model, not an isolated kernel."""
+    from adv_grpo_b200 import ops, weights
+    from adv_grpo_b200.config import ConfigDict
+    from adv_grpo_b200.diffusers_patch.sd3_pipeline_with_logprob_fast import pipeline_with_logprob_random
+    from adv_grpo_b200.mmdit import SD3Transformer2DModel
+    from adv_grpo_b200.pipeline import StableDiffusion3Pipeline
+    from adv_grpo_b200.trainer import compute_log_prob
+    from adv_grpo_b200.vae import AutoencoderKL
+    from oracle import grpo_loss as loss_o
+    from oracle import sde as sde_o
+    from oracle.mmdit import MMDiTOracle
+    from oracle.scheduler import FlowMatchEulerOracle
+    cfg = weights.SD35_MEDIUM
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    lora = weights.init_lora(cfg, rank=32, seed=1, perturb_b=0.01)
+    lora = {k: (a.bfloat16().float(), b.bfloat16().float()) for k, (a, b) in lora.items()}
+    vp = weights.init_vae_decoder(weights.VAE_SD3, seed=2, device="cpu")
+    pipe = StableDiffusion3Pipeline(SD3Transformer2DModel(cfg, params, lora=lora, device=DEV),
+                                    AutoencoderKL(vp, weights.VAE_SD3, device=DEV), device=DEV, use_cuda_graph=False)
+    G, steps, T_train = 1, 20, 1
+    g = torch.Generator().manual_seed(23)
+    pe = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    pp = torch.randn(1, 2048, generator=g).bfloat16()
+    ne = torch.randn(1, 205, 4096, generator=g).bfloat16()
+    npool = torch.randn(1, 2048, generator=g).bfloat16()
+    lat = torch.randn(G, 16, 128, 128, generator=g).bfloat16()
+    noises = [torch.randn(G, 16, 128, 128, generator=g) for _ in range(steps)]
+    img, lats, lps, tss = pipeline_with_logprob_random(
+        pipe, prompt_embeds=pe.to(DEV), pooled_prompt_embeds=pp.to(DEV), negative_prompt_embeds=ne.to(DEV),
+        negative_pooled_prompt_embeds=npool.to(DEV), num_inference_steps=steps, guidance_scale=4.5, output_type="pt",
+        height=1024, width=1024, noise_level=0.8, mini_num_image_per_prompt=G, train_num_steps=T_train, process_index=0,
+        sample_num_steps=steps, random_timestep=0, latents=lat.to(DEV), noise=[n.to(DEV) for n in noises])
+    assert img.shape == (G, 3, 1024, 1024) and torch.isfinite(img).all() and len(lats) == T_train + 1
+    L = torch.stack(lats, 1)
+    sample = {"latents": L[:, :-1], "next_latents": L[:, 1:], "timesteps": torch.stack(tss, 1), "log_probs": torch.stack(lps, 1)}
+    config = ConfigDict(dict(train=dict(cfg=True), sample=dict(guidance_scale=4.5, noise_level=0.8)))
+    embeds = torch.cat([ne.repeat(G, 1, 1), pe.repeat(G, 1, 1)]).to(DEV)
+    pooled = torch.cat([npool.repeat(G, 1), pp.repeat(G, 1)]).to(DEV)
+    adv = torch.tensor([1.5], dtype=torch.float64, device=DEV)
+    oracle = MMDiTOracle(params, dict(cfg, dual_layers=set(cfg["dual_layers"])), lora=lora, lora_scale=2.0)
+    sch = FlowMatchEulerOracle()
+    sch.set_timesteps(steps)
+    j = 0
+    with torch.no_grad():
+        _, lp, mean, _ = compute_log_prob(pipe.transformer, pipe, sample, j, embeds, pooled, config, want_mean=True)
+        loss, stats = ops.grpo_clip_loss(lp, sample["log_probs"][:, j], adv, 1e-5, 5.0)
+        x = sample["latents"][:, j].cpu().float()
+        t = sch.timesteps[j].expand(2 * G)
+        pred = oracle.forward(torch.cat([x, x]), t, embeds.cpu().float(), pooled.cpu().float())
+        u, c = pred.chunk(2)
+        v = u + 4.5 * (c - u)
+        _, lp_o, mean_o, _ = sde_o.sde_step_with_logprob_new(sch.sigmas, [j] * G, v, x, 0.8,
+                                                             prev_sample=sample["next_latents"][:, j].cpu().float())
+        loss_ref, _ = loss_o.grpo_clip_loss(lp_o, sample["log_probs"][:, j].cpu(), adv.cpu(), 1e-5, 5.0)
+    rng = mean_o.abs().max().item()
+    d = (mean.float().cpu() - mean_o).abs()
+    print(f"config-4 replay: max |d mean| = {d.max().item() / rng:.2e} of range, mean {d.mean().item() / rng:.2e}, "
+          f"|d logp| = {(lp.cpu() - lp_o).abs().max().item():.2e}, loss {loss.item():.6e} vs {loss_ref.item():.6e}")
+    assert d.max().item() <= 1e-2 * rng, (d.max().item(), rng)
+    assert d.mean().item() <= 3e-3 * rng, (d.mean().item(), rng)
+    assert (lp.cpu() - lp_o).abs().max().item() < 2e-3, (lp.cpu(), lp_o)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
