@@ -53,6 +53,15 @@ def load_adapter_dir(path):
     return {k.replace(".lora_A.default.", ".lora_A.").replace(".lora_B.default.", ".lora_B."): v for k, v in sd.items()}, config
 
 
+def save_full_transformer(transformer, path):
+    """`transformer.save_pretrained(path)` of a fully fine-tuned model (`config.use_lora = False`): diffusers layout,
+    `diffusion_pytorch_model.safetensors` with the diffusers parameter names (fp32 master weights)."""
+    from safetensors.torch import save_file
+    os.makedirs(path, exist_ok=True)
+    tensors = {k: v.detach().to("cpu").contiguous() for k, v in transformer.full_state_dict().items()}
+    save_file(tensors, os.path.join(path, "diffusion_pytorch_model.safetensors"), metadata={"format": "pt"})
+
+
 def save_lora(transformer, path):
     """`peft_model.save_pretrained(path)` for `SD3Transformer2DModel` (fp32 master LoRA factors)."""
     targets = sorted({n.split(".", 2)[2] for n in transformer._lora_names})

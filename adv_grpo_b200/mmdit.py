@@ -242,6 +242,26 @@ class _LoraPackFn(torch.autograd.Function):
         return gp.index_select(0, layout["inv"]).float() * layout["scale"], None
 
 
+class _MasterUnpack(torch.autograd.Function):
+    """Full fine-tuning (`config.use_lora = False`, train_sd3_fast_pickscore.py:488): the ONE flat fp32 master parameter
+    -> the model's bf16 working weights as autograd leaves-by-proxy.  Forward hands out aliases of the working copies
+    (no copy: they were refreshed from the master after the last optimizer step); backward adds every weight's bf16
+    gradient into its fp32 view of `master.grad` in place (a view-based unpack would materialise a zero tensor of the
+    whole 2.2 B-element buffer per weight)."""
+
+    @staticmethod
+    def forward(ctx, master, model):
+        ctx.model = model
+        return tuple(model.p[n].detach() for n in model._full_names)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        for gv, g in zip(ctx.model._full_grad_views, grads):
+            if g is not None:
+                gv.add_(g.reshape(gv.shape))
+        return None, None
+
+
 class _WT:
     """Lazily materialised transposed copy of a frozen weight (only layers that back-propagate
     to their input ever build one)."""
@@ -349,6 +369,7 @@ class SD3Transformer2DModel(torch.nn.Module):
         self._lora_cache = None
         self._lora_dirty = False
         self._lora_enabled = True
+        self.full_finetune = False       # config.use_lora = False: enable_full_finetune()
 
     # ------------------------------------------------------------------ peft-like surface
     def to(self, *args, **kwargs):
@@ -362,7 +383,9 @@ class SD3Transformer2DModel(torch.nn.Module):
 
     def trainable_parameters(self):
         """The single flat LoRA parameter (optimizer / clipping / EMA / all-reduce work on one tensor); the per-layer
-        factors are `lora_A[key]` / `lora_B[key]` views of it."""
+        factors are `lora_A[key]` / `lora_B[key]` views of it.  Under full fine-tuning: the flat fp32 master of every weight."""
+        if self.full_finetune:
+            return [self.full_master]
         return [self.lora_flat]
 
     def lora_state_dict(self):
@@ -376,6 +399,9 @@ class SD3Transformer2DModel(torch.nn.Module):
     def save_pretrained(self, path):
         """peft adapter directory (`adapter_config.json` + `adapter_model.safetensors`), as `save_ckpt` of
         `train_sd3_fast_pickscore.py:389-398` writes it."""
+        if self.full_finetune:
+            from .checkpoint import save_full_transformer
+            return save_full_transformer(self, path)
         from .checkpoint import save_lora
         save_lora(self, path)
 
@@ -446,6 +472,10 @@ class SD3Transformer2DModel(torch.nn.Module):
         return [{k: (tensors[ia], tensors[iw]) for k, (ia, iw) in entry.items()} for entry in self._lora_layout["keys"]]
 
     def _pack_lora(self):
+        if self.full_finetune:
+            if self._lora_dirty:
+                self._refresh_from_master()
+            return [dict() for _ in self.blocks]
         if not self.lora_rank or not self._lora_enabled or self._lora_layout is None:
             return [dict() for _ in self.blocks]
         if torch.is_grad_enabled() and self.lora_flat.requires_grad:
@@ -461,6 +491,160 @@ class SD3Transformer2DModel(torch.nn.Module):
                 torch._foreach_copy_(self._lora_cache_tensors, list(tensors))
         self._lora_dirty = False
         return self._lora_cache
+
+    # ------------------------------------------------------------------ full (non-LoRA) fine-tuning, SURVEY.md section 8f-4
+    def enable_full_finetune(self):
+        """`config.use_lora = False` (train_sd3_fast_pickscore.py:488: no peft wrapper, every transformer parameter is
+        trained).  Mixed precision the B200 way: ONE flat fp32 master buffer holds every weight (the optimizer, gradient
+        clipping, EMA and the gradient all-reduce work on that one tensor, exactly as they do on the flat LoRA
+        parameter), the bf16 working copies the kernels read are refreshed from it in place after every optimizer step
+        (so captured CUDA graphs stay valid).  Rollout and replay both run `_forward_full` -- the same kernels and the
+        same rounding points in both directions, which `ratio = exp(logp - logp_old) = 1` at `clip_range = 1e-5` needs."""
+        if self.full_finetune:
+            return self
+        names = sorted(self.p)
+        self._full_names = names
+        self._lora_enabled = False
+        self.lora_flat.requires_grad_(False)
+        flat = torch.cat([self.p[n].reshape(-1).float() for n in names])
+        self.full_master = torch.nn.Parameter(flat.contiguous())
+        self.full_master.grad = torch.zeros_like(self.full_master)
+        self._full_views, self._full_grad_views = [], []
+        off = 0
+        for n in names:
+            k, shape = self.p[n].numel(), self.p[n].shape
+            self._full_views.append(self.full_master.data[off:off + k].view(shape))
+            self._full_grad_views.append(self.full_master.grad[off:off + k].view(shape))
+            off += k
+        self.full_finetune = True
+        self._lora_dirty = False
+        return self
+
+    def full_state_dict(self):
+        """diffusers-named fp32 weights (views of the master buffer)."""
+        return dict(zip(self._full_names, self._full_views))
+
+    @torch.no_grad()
+    def _refresh_from_master(self):
+        """master (fp32) -> bf16 working copies -> the packed operands of the fused no-grad path, all IN PLACE."""
+        torch._foreach_copy_([self.p[n] for n in self._full_names], self._full_views)
+        p = self.p
+        for blk in self.blocks:
+            b = f"transformer_blocks.{blk['idx']}"
+            for key, names in (("qkv", ("attn.to_q", "attn.to_k", "attn.to_v")),
+                               ("cqkv", ("attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj")),
+                               ("qkv2", ("attn2.to_q", "attn2.to_k", "attn2.to_v"))):
+                if "w_" + key in blk:
+                    torch.cat([p[f"{b}.{n}.weight"] for n in names], 0, out=blk["w_" + key])
+                    torch.cat([p[f"{b}.{n}.bias"] for n in names], 0, out=blk["b_" + key])
+            for key in [k for k in blk if k.startswith("wt_")]:
+                if blk[key].wt is not None:
+                    blk[key].wt.copy_(blk[key].w.t())
+        L = len(self.blocks)
+        ada_w = [p[f"transformer_blocks.{i}.{n}.linear.weight"] for i in range(L) for n in ("norm1", "norm1_context")]
+        ada_b = [p[f"transformer_blocks.{i}.{n}.linear.bias"] for i in range(L) for n in ("norm1", "norm1_context")]
+        torch.cat(ada_w + [p["norm_out.linear.weight"]], 0, out=self.ada_w)
+        torch.cat(ada_b + [p["norm_out.linear.bias"]], 0, out=self.ada_b)
+        if self.w_patch.data_ptr() != p["pos_embed.proj.weight"].data_ptr():
+            self.w_patch.copy_(p["pos_embed.proj.weight"].reshape(self.d, -1))
+        if hasattr(self, "_proj_wt_holder") and self._proj_wt_holder.wt is not None:
+            self._proj_wt_holder.wt.copy_(p["proj_out.weight"].t())
+        self._lora_dirty = False
+
+    def _forward_full(self, hidden_states, timestep, encoder_hidden_states, pooled_projections, upto=None):
+        """The same network as `forward`, written for gradients to EVERY parameter: each Linear is `ops.linear`
+        (tcgen05 GEMM forward, dX on the same kernel, dW on the split-K TN kernel, db on the column-sum kernel), the joint
+        attention is `ops.attention` (tcgen05 forward and backward); the adaLN modulation, gates, per-head RMSNorm and
+        GELU(tanh) are torch elementwise ops so that autograd carries their parameter gradients (shift / scale / gate
+        vectors -> the adaLN linears -> the timestep / pooled-text embedders; RMSNorm weights)."""
+        if self._lora_dirty:
+            self._refresh_from_master()
+        cfg, d, bf = self.cfg, self.d, torch.bfloat16
+        H, D, ps = cfg["heads"], cfg["head_dim"], cfg["patch_size"]
+        if torch.is_grad_enabled() and self.full_master.requires_grad:
+            W = dict(zip(self._full_names, _MasterUnpack.apply(self.full_master, self)))
+        else:
+            W = self.p
+        lin = lambda name, v: ops.linear(v, W[name + ".weight"], W.get(name + ".bias"))
+
+        def ln_mod(v, shift, scale):
+            n = F.layer_norm(v.float(), (d,), eps=1e-6)
+            return (n * (1.0 + scale.float()[:, None]) + shift.float()[:, None]).to(bf)
+
+        def rms(v, w):                                         # v [B, S, H, D]
+            vf = v.float()
+            return (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()).to(bf)
+
+        def heads(v):
+            return v.view(v.shape[0], v.shape[1], H, D)
+
+        def attn(pre, xq, cq=None, ctx_out=True):
+            q, k, v = (heads(lin(f"{pre}.to_{n}", xq)) for n in "qkv")
+            if cfg["qk_norm"]:
+                q, k = rms(q, W[f"{pre}.norm_q.weight"]), rms(k, W[f"{pre}.norm_k.weight"])
+            if cq is not None:
+                aq, ak, av = (heads(lin(f"{pre}.add_{n}_proj", cq)) for n in "qkv")
+                if cfg["qk_norm"]:
+                    aq, ak = rms(aq, W[f"{pre}.norm_added_q.weight"]), rms(ak, W[f"{pre}.norm_added_k.weight"])
+                q, k, v = torch.cat([q, aq], 1), torch.cat([k, ak], 1), torch.cat([v, av], 1)      # [image, text]
+            o = ops.attention(torch.stack([q, k, v], dim=2).contiguous())                         # [B, S, H, D]
+            o = o.reshape(o.shape[0], o.shape[1], d)
+            if cq is None:
+                return lin(f"{pre}.to_out.0", o), None
+            n = xq.shape[1]
+            return lin(f"{pre}.to_out.0", o[:, :n]), (lin(f"{pre}.to_add_out", o[:, n:]) if ctx_out else None)
+
+        def ff(pre, v):
+            return lin(f"{pre}.net.2", F.gelu(lin(f"{pre}.net.0.proj", v), approximate="tanh"))
+
+        B, C, Hh, Ww = hidden_states.shape
+        h, w = Hh // ps, Ww // ps
+        xp = hidden_states.to(bf).reshape(B, C, h, ps, w, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * h * w, C * ps * ps)
+        key = (h, w)
+        if key not in self._pos_cache:
+            self._pos_cache[key] = cropped_pos_embed(d, h, w, cfg["pos_embed_max_size"], cfg["base_size"], self.device_).to(bf)
+        x = ops.linear(xp.contiguous(), W["pos_embed.proj.weight"].reshape(d, -1), W["pos_embed.proj.bias"]).reshape(B, h * w, d)
+        x = x + self._pos_cache[key]
+        te = timestep_embedding(timestep.to(self.device_)).to(bf)
+        temb = lin("time_text_embed.timestep_embedder.linear_2", F.silu(lin("time_text_embed.timestep_embedder.linear_1", te)))
+        temb = temb + lin("time_text_embed.text_embedder.linear_2",
+                          F.silu(lin("time_text_embed.text_embedder.linear_1", pooled_projections.to(bf))))
+        st = F.silu(temb)
+        c = lin("context_embedder", encoder_hidden_states.to(bf).contiguous())
+        L = cfg["num_layers"]
+        for i in range(L if upto is None else upto):
+            pre, last, dual = f"transformer_blocks.{i}", i == L - 1, i in cfg["dual_layers"]
+            e = lin(f"{pre}.norm1.linear", st)
+            if dual:
+                sh, sc, g, sh_m, sc_m, g_m, sh2, sc2, g2 = e.chunk(9, dim=1)
+            else:
+                sh, sc, g, sh_m, sc_m, g_m = e.chunk(6, dim=1)
+            x1 = ln_mod(x, sh, sc)
+            ce = lin(f"{pre}.norm1_context.linear", st)
+            if last:                                           # AdaLayerNormContinuous: (scale, shift)
+                csc, csh = ce.chunk(2, dim=1)
+            else:
+                csh, csc, cg, csh_m, csc_m, cg_m = ce.chunk(6, dim=1)
+            c1 = ln_mod(c, csh, csc)
+            a, ca = attn(f"{pre}.attn", x1, c1, ctx_out=not last)
+            x_in = x
+            x = x + g[:, None] * a
+            if dual:
+                a2, _ = attn(f"{pre}.attn2", ln_mod(x_in, sh2, sc2))
+                x = x + g2[:, None] * a2
+            x = x + g_m[:, None] * ff(f"{pre}.ff", ln_mod(x, sh_m, sc_m))
+            if last:
+                c = None
+                continue
+            c = c + cg[:, None] * ca
+            c = c + cg_m[:, None] * ff(f"{pre}.ff_context", ln_mod(c, csh_m, csc_m))
+        if upto is not None:
+            return x, c
+        sc, sh = lin("norm_out.linear", st).chunk(2, dim=1)
+        x = lin("proj_out", ln_mod(x, sh, sc))
+        cin = cfg["in_channels"]
+        x = x.reshape(B, h, w, ps, ps, cin).permute(0, 5, 1, 3, 2, 4).reshape(B, cin, h * ps, w * ps)
+        return (x,)
 
     # ------------------------------------------------------------------ building blocks
     def _lin(self, x, blk, key, lora_pack=None, epilogue=ops.EPI_NONE, residual=None, gate=None, rows=1):
@@ -569,6 +753,8 @@ class SD3Transformer2DModel(torch.nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, hidden_states, timestep, encoder_hidden_states, pooled_projections,
                 joint_attention_kwargs=None, return_dict=False, upto=None):
+        if self.full_finetune:
+            return self._forward_full(hidden_states, timestep, encoder_hidden_states, pooled_projections, upto=upto)
         cfg, p, d = self.cfg, self.p, self.d
         ps = cfg["patch_size"]
         B, C, Hh, Ww = hidden_states.shape

@@ -148,7 +148,13 @@ class GRPOTrainer:
         self.reference_image_fn = reference_image_fn or self._synthetic_reference
         self.sync_discriminator = sync_discriminator
         s, t = config.sample, config.train
-        if t.get("lora_path", None):                                       # resume, train_pick:506-509
+        if not config.get("use_lora", True):                               # train_pick:488: every transformer weight trains
+            if t.beta > 0:
+                raise NotImplementedError("train.beta > 0 needs the adapter-disabled reference forward (train_pick:1105-1108), "
+                                          "which only exists with use_lora=True")
+            self.transformer.enable_full_finetune()
+            graph_train = False                                            # the full-gradient replay runs eagerly
+        elif t.get("lora_path", None):                                     # resume, train_pick:506-509
             self.transformer.load_adapter(t.lora_path)
         self.params = self.transformer.trainable_parameters()
         # clip_grad_norm_ + AdamW.step + zero_grad of train_pick:1165-1171 as one native call on the flat parameter

@@ -258,6 +258,8 @@ def run_ours(args):
     cfg.sample.num_batches_per_epoch = nb
     cfg.train.gradient_accumulation_steps = max(nb // 2, 1)   # 2 optimizer steps per step, like the reference epoch
     cfg.train_d = spec["train_d"]
+    if args.full_finetune:
+        cfg.use_lora = False
     scorer = head = None
     if args.config in (2, 5):
         from adv_grpo_b200.pickscore_scorer import PickScoreScorer
@@ -488,7 +490,9 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": spec["workload"].format(nb=nb), "baseline_config": args.config,
+            "config": {"workload": spec["workload"].format(nb=nb) + (" -- FULL fine-tuning (use_lora=False), not LoRA"
+                                                                    if args.full_finetune else ""),
+                       "baseline_config": args.config,
                        "groups_per_step_all_ranks": nb * world,
                        "l2": "per-step working set (4.4 GB weights + activations) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"},
@@ -516,6 +520,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: fixed groups per rank (default); strong: 16 groups per step split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-finetune", action="store_true",
+                    help="config.use_lora = False (SURVEY 8f-4): every transformer weight trains; not a BASELINE config")
     ap.add_argument("--cpu-budget", type=float, default=150.0,
                     help="--impl reference: wall-clock bound (s) of the timed CPU samples (init excluded)")
     args = ap.parse_args()

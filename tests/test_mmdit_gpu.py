@@ -118,3 +118,60 @@ def test_mmdit_fused_feed_forward_node_matches_unfused_autograd():
     cos = torch.nn.functional.cosine_similarity(grads[0], grads[1], dim=0)
     assert cos > 0.999, cos
     assert (grads[0] - grads[1]).abs().max() <= 0.03 * grads[1].abs().max()
+
+
+def test_full_finetune_forward_and_all_parameter_grads_match_oracle():
+    """`config.use_lora = False` (train_sd3_fast_pickscore.py:488): every transformer parameter
+    trains.  Forward of the full-gradient path vs the fp32 oracle, gradients of EVERY diffusers-named parameter (read from
+    the flat fp32 master's .grad views) vs the oracle's autograd, and bit-equality of the no-grad (rollout) and grad-mode
+    (replay) forwards, which `ratio = 1` at `clip_range = 1e-5` relies on."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.mmdit import SD3Transformer2DModel
+    from oracle.mmdit import MMDiTOracle
+    cfg = weights.MMDIT_TINY
+    params = weights.init_mmdit(cfg, seed=0, device="cpu", dtype=torch.bfloat16)
+    model = SD3Transformer2DModel(cfg, params, lora_rank=32, lora_alpha=64, device=DEV).enable_full_finetune()
+    assert [p.numel() for p in model.trainable_parameters()] == [sum(v.numel() for v in params.values())]
+    oracle = MMDiTOracle(params, dict(cfg, dual_layers=set(cfg["dual_layers"])), lora=None)
+    for k in oracle.p:
+        oracle.p[k].requires_grad_(True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 16, 16, generator=g).bfloat16()
+    t = torch.tensor([960.1293, 500.0])
+    ctx = torch.randn(2, 13, cfg["joint_dim"], generator=g).bfloat16()
+    pooled = torch.randn(2, cfg["pooled_dim"], generator=g).bfloat16()
+    wgt = torch.randn(x.shape, generator=g)
+    args = (x.to(DEV), t.to(DEV), ctx.to(DEV), pooled.to(DEV))
+    with torch.no_grad():
+        rollout = model(*args)[0]
+    out = model(*args)[0]
+    assert out.requires_grad and torch.equal(out.detach(), rollout)
+    (out.float() * wgt.to(DEV)).sum().backward()
+    ref = oracle.forward(x.float(), t, ctx.float(), pooled.float())
+    (ref * wgt).sum().backward()
+    err = (out.detach().float().cpu() - ref.detach()).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-2, err
+    grads = dict(zip(model._full_names, model._full_grad_views))
+    checked, worst = 0, (1.0, "")
+    for name, p_o in oracle.p.items():
+        got = grads[name].float().cpu()
+        if p_o.grad is None or p_o.grad.norm().item() == 0:      # e.g. the last block's unused context output projection
+            assert got.abs().max().item() == 0, name
+            continue
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), p_o.grad.flatten(), dim=0).item()
+        rel = (got - p_o.grad).norm().item() / p_o.grad.norm().item()
+        worst = min(worst, (cos, name))
+        # bf16 forward / backward through 3 blocks vs the fp32 oracle's autograd (same bars as the LoRA-gradient test,
+        # one notch wider in rel for the small-norm bias / RMS-weight vectors)
+        assert cos > 0.995 and rel < 0.1, (name, cos, rel)
+        checked += 1
+    assert checked >= len(oracle.p) - 8, (checked, len(oracle.p), worst)
+    # optimizer step on the master -> in-place refresh of the working weights on the next forward
+    from adv_grpo_b200.optim import FlatClipAdamW
+    opt = FlatClipAdamW(model.trainable_parameters(), lr=1e-3, weight_decay=0.0, max_grad_norm=1.0)
+    opt.step()
+    model.invalidate_lora_cache()
+    assert model.full_master.grad.abs().max().item() == 0
+    with torch.no_grad():
+        after = model(*args)[0]
+    assert not torch.equal(after, rollout)

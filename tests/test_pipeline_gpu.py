@@ -235,3 +235,28 @@ def test_trainer_evaluate_is_deterministic_ode_and_restores_weights():
     # rank runs equally sized batches); the padded prompt is masked out of the metrics
     assert img1.shape == (2, 3, 128, 128)
     assert all(torch.equal(a, b) for a, b in zip(live, tr.params))      # EMA swapped out again
+
+
+def test_grpo_epoch_full_finetune():
+    """One GRPO epoch with `config.use_lora = False`: the trainer switches the transformer to full fine-tuning (flat fp32
+    master of every weight under the same clip + AdamW kernel), the replay ratio stays 1 (same forward in rollout and
+    replay), and the master weights move."""
+    from adv_grpo_b200 import weights
+    from adv_grpo_b200.config import load_config
+    from adv_grpo_b200.pickscore_scorer import PickScoreScorer
+    from adv_grpo_b200.trainer import GRPOTrainer
+    pipe, cfg, *_ = _tiny_pipeline(True)
+    c = load_config("pickscore_cotrain_sd3_fast")
+    c.use_lora = False
+    c.resolution, c.sample.num_steps, c.sample.mini_num_image_per_prompt = 128, 4, 2
+    c.sample.num_batches_per_epoch, c.train.gradient_accumulation_steps, c.train_d = 2, 1, False
+    tr = GRPOTrainer(c, pipe, [f"a photo of object number {i}" for i in range(7)],
+                     scorer=PickScoreScorer(device=DEV, cfg=weights.CLIP_TINY), device=DEV)
+    assert pipe.transformer.full_finetune and tr.micro_step is None
+    assert tr.params[0].numel() == sum(v.numel() for v in pipe.transformer.p.values())
+    before = tr.params[0].detach().clone()
+    info = tr.run_epoch()
+    assert torch.isfinite(info["loss"]) and info["approx_kl"].item() < 1e-4          # ratio == 1 up to quirk Q4 (bf16 latents)
+    assert not torch.equal(before, tr.params[0])
+    info = tr.run_epoch()
+    assert torch.isfinite(info["loss"])
