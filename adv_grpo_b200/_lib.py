@@ -56,6 +56,8 @@ SIGNATURES = {
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_clip_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "advgrpo_pil_resize_bilinear_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
+    "advgrpo_pil_resize_bilinear_u8": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "advgrpo_group_norm_workspace_bytes": (_SZ, [_I64, _I64]),
     "advgrpo_group_norm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P, _SZ, _P]),
     "advgrpo_conv2d_nhwc_tf32": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _P]),
@@ -113,7 +115,7 @@ def load():
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
-                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_device_check": 0}
+                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_device_check": 0}
 _launches = [0]
 
 

@@ -22,14 +22,20 @@ __device__ __forceinline__ double pil_bicubic(double x) {
   return 0.0;
 }
 
+__device__ __forceinline__ double pil_bilinear(double x) {      // Pillow bilinear_filter (support 1)
+  if (x < 0.0) x = -x;
+  return x < 1.0 ? __dsub_rn(1.0, x) : 0.0;
+}
+
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for one axis.  One thread per output index.
+// filter: 0 = BICUBIC (support 2), 1 = BILINEAR (support 1).
 __global__ void pil_coeffs_kernel(int in_size, int out_size, int ksize, int* __restrict__ bounds,
-                                  int* __restrict__ kk) {
+                                  int* __restrict__ kk, int filter = 0) {
   const int xx = blockIdx.x * blockDim.x + threadIdx.x;
   if (xx >= out_size) return;
   const double scale = (double)in_size / (double)out_size;
   const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = 2.0 * filterscale;
+  const double support = (filter == 1 ? 1.0 : 2.0) * filterscale;
   const double center = __dmul_rn((double)xx + 0.5, scale);
   const double ss = 1.0 / filterscale;
   int xmin = (int)(center - support + 0.5);
@@ -40,7 +46,8 @@ __global__ void pil_coeffs_kernel(int in_size, int out_size, int ksize, int* __r
   double w[64];
   double ww = 0.0;
   for (int x = 0; x < xmax; ++x) {
-    w[x] = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+    const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    w[x] = filter == 1 ? pil_bilinear(arg) : pil_bicubic(arg);
     ww = __dadd_rn(ww, w[x]);
   }
   for (int x = 0; x < ksize; ++x) {
@@ -110,6 +117,46 @@ __global__ void pil_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int 
   else pixels[o] = n;
 }
 
+// ---- reference-image resize (train_sd3_fast_pickscore.py:791-797: transforms.Resize((S, S)) on a PIL image + ToTensor) ----
+// horizontal pass on the interleaved RGB bytes PIL decodes: u8 [H, W, 3] -> u8 [3, H, out_w]
+__global__ void pil_horizontal_hwc_kernel(const uint8_t* __restrict__ img, int H, int W, int out_w, int ksize,
+                                          const int* __restrict__ bounds, const int* __restrict__ kk,
+                                          uint8_t* __restrict__ tmp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)H * out_w) return;
+  const int y = (int)(idx / out_w), xx = (int)(idx % out_w);
+  const int xmin = bounds[xx * 2], xmax = bounds[xx * 2 + 1];
+  const uint8_t* row = img + ((int64_t)y * W + xmin) * 3;
+  int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+  for (int x = 0; x < xmax; ++x) {
+    const int k = kk[xx * ksize + x];
+    s0 += (int)row[3 * x] * k;
+    s1 += (int)row[3 * x + 1] * k;
+    s2 += (int)row[3 * x + 2] * k;
+  }
+  const int64_t o = (int64_t)y * out_w + xx, plane = (int64_t)H * out_w;
+  tmp[o] = clip8(s0);
+  tmp[plane + o] = clip8(s1);
+  tmp[2 * plane + o] = clip8(s2);
+}
+
+// vertical pass + ToTensor: u8 [3, H, out_w] -> f32 [3, out_h, out_w] = v / 255 (and optionally the bytes themselves)
+__global__ void pil_vertical_totensor_kernel(const uint8_t* __restrict__ tmp, int H, int out_h, int out_w, int ksize,
+                                             const int* __restrict__ bounds, const int* __restrict__ kk,
+                                             float* __restrict__ out, uint8_t* __restrict__ u8_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.y;
+  if (idx >= (int64_t)out_h * out_w) return;
+  const int yy = (int)(idx / out_w), xx = (int)(idx % out_w);
+  const int ymin = bounds[yy * 2], ymax = bounds[yy * 2 + 1];
+  int ss0 = 1 << (kPrecisionBits - 1);
+  for (int y = 0; y < ymax; ++y) ss0 += (int)tmp[((int64_t)plane * H + ymin + y) * out_w + xx] * kk[yy * ksize + y];
+  const uint8_t v = clip8(ss0);
+  const int64_t o = ((int64_t)plane * out_h + yy) * out_w + xx;
+  if (u8_out) u8_out[o] = v;
+  out[o] = __fdiv_rn((float)v, 255.0f);                        // ToTensor: byte_tensor.float().div(255)
+}
+
 __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   const float A = -0.75f;
   float x = t + 1.0f;
@@ -160,10 +207,10 @@ __global__ void dino_preprocess_kernel(const InT* __restrict__ img, int H, int W
   pixels[((int64_t)plane * out + oy) * out + ox] = __float2bfloat16_rn((acc - mean3[ch]) / std3[ch]);
 }
 
-int pil_ksize(int in_size, int out_size) {
+int pil_ksize(int in_size, int out_size, double filter_support = 2.0) {
   double scale = (double)in_size / (double)out_size;
   double fs = scale < 1.0 ? 1.0 : scale;
-  return (int)ceil(2.0 * fs) * 2 + 1;
+  return (int)ceil(filter_support * fs) * 2 + 1;
 }
 
 }  // namespace
@@ -213,6 +260,41 @@ int advgrpo_clip_preprocess(const void* images, int images_u8, int64_t B, int64_
     pil_vertical_kernel<float><<<g2, 256, 0, st>>>(tmp, (int)H, (int)out, ks, bounds, kk, mean3, std3, (float*)pixels, u8_out);
   else
     pil_vertical_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>(tmp, (int)H, (int)out, ks, bounds, kk, mean3, std3, (__nv_bfloat16*)pixels, u8_out);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  return ADVGRPO_OK;
+}
+
+static size_t pil_coeff_bytes(int out, int ks) { return (((size_t)out * (ks + 2) * sizeof(int)) + 255) & ~(size_t)255; }
+
+size_t advgrpo_pil_resize_bilinear_workspace_bytes(int64_t H, int64_t W, int64_t out_h, int64_t out_w) {
+  const int ksx = pil_ksize((int)W, (int)out_w, 1.0), ksy = pil_ksize((int)H, (int)out_h, 1.0);
+  return pil_coeff_bytes((int)out_w, ksx) + pil_coeff_bytes((int)out_h, ksy) + (size_t)3 * H * out_w + 256;
+}
+
+int advgrpo_pil_resize_bilinear_u8(const uint8_t* img_hwc, int64_t H, int64_t W, int64_t out_h, int64_t out_w, float* out_chw,
+                                   uint8_t* u8_out_chw, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(img_hwc && out_chw, "pil_resize_bilinear_u8: null pointer");
+  ADVGRPO_CHECK_ARG(H >= 1 && W >= 1 && out_h >= 1 && out_w >= 1 && H < (1 << 15) && W < (1 << 15) && out_h < (1 << 15) &&
+                        out_w < (1 << 15),
+                    "pil_resize_bilinear_u8: bad sizes H=%lld W=%lld -> %lld x %lld", (long long)H, (long long)W, (long long)out_h,
+                    (long long)out_w);
+  const int ksx = pil_ksize((int)W, (int)out_w, 1.0), ksy = pil_ksize((int)H, (int)out_h, 1.0);
+  ADVGRPO_CHECK_ARG(ksx <= 64 && ksy <= 64, "pil_resize_bilinear_u8: downscale factor above 31 is not supported");
+  if (!workspace || workspace_bytes < advgrpo_pil_resize_bilinear_workspace_bytes(H, W, out_h, out_w))
+    return set_error(ADVGRPO_ERR_WORKSPACE, "pil_resize_bilinear_u8: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* bx = (int*)workspace;
+  int* kx = bx + 2 * out_w;
+  int* by = (int*)((uint8_t*)workspace + pil_coeff_bytes((int)out_w, ksx));
+  int* ky = by + 2 * out_h;
+  uint8_t* tmp = (uint8_t*)workspace + pil_coeff_bytes((int)out_w, ksx) + pil_coeff_bytes((int)out_h, ksy);
+  pil_coeffs_kernel<<<(unsigned)((out_w + 127) / 128), 128, 0, st>>>((int)W, (int)out_w, ksx, bx, kx, 1);
+  pil_coeffs_kernel<<<(unsigned)((out_h + 127) / 128), 128, 0, st>>>((int)H, (int)out_h, ksy, by, ky, 1);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  pil_horizontal_hwc_kernel<<<(unsigned)((H * out_w + 255) / 256), 256, 0, st>>>(img_hwc, (int)H, (int)W, (int)out_w, ksx, bx, kx, tmp);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  pil_vertical_totensor_kernel<<<dim3((unsigned)((out_h * out_w + 255) / 256), 3), 256, 0, st>>>(tmp, (int)H, (int)out_h, (int)out_w, ksy,
+                                                                                                by, ky, out_chw, u8_out_chw);
   ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }

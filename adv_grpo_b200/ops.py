@@ -909,6 +909,22 @@ def clip_preprocess(images, out_size=224, dtype=torch.bfloat16, want_u8=False):
     return (pix, u8) if want_u8 else pix
 
 
+def pil_resize_bilinear(img_hwc_u8, out_h, out_w, want_u8=False):
+    """uint8 [H, W, 3] (a decoded PIL RGB image, on the device) -> float32 [3, out_h, out_w] in [0, 1]: Pillow's
+    antialiased BILINEAR `resize` + torchvision `ToTensor()` bit for bit (train_sd3_fast_pickscore.py:791-797)."""
+    _need_cuda(img_hwc_u8)
+    if img_hwc_u8.dtype != torch.uint8 or img_hwc_u8.dim() != 3 or img_hwc_u8.shape[2] != 3:
+        raise _lib.AdvGrpoError("pil_resize_bilinear expects a uint8 [H, W, 3] tensor")
+    img = img_hwc_u8.contiguous()
+    H, W, _ = img.shape
+    dev = img.device
+    out = torch.empty((3, out_h, out_w), dtype=torch.float32, device=dev)
+    u8 = torch.empty((3, out_h, out_w), dtype=torch.uint8, device=dev) if want_u8 else None
+    ws = _workspace("pil_resize", _lib.query("advgrpo_pil_resize_bilinear_workspace_bytes", H, W, out_h, out_w), dev)
+    _lib.call("advgrpo_pil_resize_bilinear_u8", _ptr(img), H, W, out_h, out_w, _ptr(out), _ptr(u8), _ptr(ws), ws.numel(), _stream())
+    return (out, u8) if want_u8 else out
+
+
 def dino_preprocess(images, out_size=518):
     """[B,3,H,W] (bf16 or f32, [0,1]) -> bicubic out x out, ImageNet-normalised, bf16."""
     _need_cuda(images)

@@ -1,9 +1,12 @@
 """Reference ("real") images of the adversarial loop: the `{prompt: [file, ...]}` index JSON (`config.json_path`,
 README.md:114-128 of the reference) and the per-batch loading of `scripts/train_sd3_fast_pickscore.py:705-707,
 773-799`: `Image.open(root / name).convert("RGB")` -> `transforms.Resize((512, 512))` (PIL bilinear with Pillow's
-antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  Host-side I/O as in the reference (the
-decode is a CPU plugin there too); results are cached per prompt because the files never change, which the reference
-does not do (it re-opens every file of the prompt for every batch).  SURVEY.md section 8f rank 3."""
+antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  The file read and the entropy decode
+(Huffman / inflate) are host I/O as in the reference; with a CUDA device the decoded bytes go to the GPU as they are and
+the antialiased bilinear resize + ToTensor run there (`ops.pil_resize_bilinear`, Pillow bit-exact) -- the per-image
+PIL resize, the costliest host step after the decode, leaves the sampling loop.  Results are cached per prompt because
+the files never change, which the reference does not do (it re-opens every file of the prompt for every batch).
+SURVEY.md section 8f rank 3."""
 import json
 import os
 
@@ -30,7 +33,11 @@ class ReferenceImageIndex:
             if self.default_image is None:
                 raise FileNotFoundError(f"reference image {path} could not be opened ({e}) and no default_image is set")
             img = Image.open(self.default_image).convert("RGB")
-        img = img.resize((self.size, self.size), Image.BILINEAR)       # torchvision Resize on a PIL image
+        if torch.device(self.device).type == "cuda":                   # bytes -> device, resize + ToTensor on the GPU
+            from . import ops
+            raw = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).to(self.device)
+            return ops.pil_resize_bilinear(raw, self.size, self.size)
+        img = img.resize((self.size, self.size), Image.BILINEAR)       # CPU device (host tests): torchvision Resize on PIL
         arr = np.asarray(img, dtype=np.uint8)                          # HWC
         return torch.from_numpy(arr.copy()).permute(2, 0, 1).float().div_(255.0)   # ToTensor()
 

@@ -344,6 +344,15 @@ int advgrpo_clip_preprocess(const void* images, int images_u8, int64_t B, int64_
                             const float* mean3, const float* std3, void* pixels, int pixels_f32,
                             uint8_t* u8_out, void* workspace, size_t workspace_bytes,
                             advgrpo_stream_t stream);
+/* Reference ("real") images of the adversarial loop: `transforms.Resize((S, S))` on the decoded PIL
+ * image + `ToTensor()` (scripts/train_sd3_fast_pickscore.py:791-797) on the device.  img_hwc: the interleaved RGB bytes
+ * `Image.open(path).convert("RGB")` yields, uint8 [H, W, 3] of ANY size; out_chw: f32 [3, out_h, out_w] = byte / 255.
+ * Pillow's antialiased BILINEAR resample bit for bit (ImagingResample: triangle filter of support max(1, in / out),
+ * horizontal then vertical pass with an 8-bit intermediate, 22-bit fixed-point coefficients).  u8_out_chw (optional): the
+ * resized bytes, uint8 [3, out_h, out_w].  The entropy (Huffman / inflate) decode of the file stays a host step. */
+size_t advgrpo_pil_resize_bilinear_workspace_bytes(int64_t H, int64_t W, int64_t out_h, int64_t out_w);
+int advgrpo_pil_resize_bilinear_u8(const uint8_t* img_hwc, int64_t H, int64_t W, int64_t out_h, int64_t out_w, float* out_chw,
+                                   uint8_t* u8_out_chw, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
 /* A8b preprocessing (adv_grpo/rewards.py:379-391): bicubic (A = -0.75, align_corners =
  * False, no antialias) resize to out x out, ImageNet normalisation, cast to bf16. */
 int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64_t H, int64_t W,

@@ -595,3 +595,37 @@ def test_stat_tracker_device_path_counts_distinct_prompts_and_handles_long_T(ops
         assert size == 8.0 and seen == (4 if epoch == 0 else 6)
         tr.clear()
 
+
+
+# ------------------------------------------------------------------ 8f-3 reference-image resize (Pillow BILINEAR + ToTensor)
+@pytest.mark.parametrize("H,W,out", [(480, 640, 512), (200, 300, 512), (512, 512, 512), (1500, 1000, 512), (37, 53, 64),
+                                     (2048, 3072, 1024)])
+def test_pil_resize_bilinear_bit_exact_with_pillow(ops, H, W, out):
+    """transforms.Resize((S, S)) on a PIL image + ToTensor() (train_sd3_fast_pickscore.py:791-797) on the device: every
+    resized byte equals Pillow's antialiased BILINEAR resize (down- and up-scaling, non-square inputs), and the float
+    output is byte / 255 in float32."""
+    from PIL import Image
+    rng = np.random.default_rng(H + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((out, out), Image.BILINEAR))            # [out, out, 3]
+    got, u8 = ops.pil_resize_bilinear(torch.from_numpy(img).to(DEV), out, out, want_u8=True)
+    assert torch.equal(u8.cpu(), torch.from_numpy(ref.copy()).permute(2, 0, 1))
+    assert torch.equal(got.cpu(), torch.from_numpy(ref.copy()).permute(2, 0, 1).float().div(255.0))
+
+
+def test_reference_image_index_gpu_path_equals_pil_path(tmp_path):
+    """ReferenceImageIndex on a CUDA device (host decode, device resize) returns exactly what the PIL path returns, for a
+    JPEG and a PNG of different sizes, including the missing-file fallback."""
+    import json
+    from PIL import Image
+    from adv_grpo_b200.reference_images import ReferenceImageIndex
+    rng = np.random.default_rng(3)
+    Image.fromarray(rng.integers(0, 256, (300, 420, 3), dtype=np.uint8)).save(tmp_path / "a.jpg", quality=90)
+    Image.fromarray(rng.integers(0, 256, (640, 512, 3), dtype=np.uint8)).save(tmp_path / "b.png")
+    Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(tmp_path / "default.png")
+    (tmp_path / "index.json").write_text(json.dumps({"a cat": ["a.jpg", "b.png", "missing.jpg"]}))
+    kw = dict(size=256, default_image=str(tmp_path / "default.png"))
+    gpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device=DEV, **kw)("a cat")
+    cpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device="cpu", **kw)("a cat")
+    assert gpu.is_cuda and gpu.shape == (3, 3, 256, 256) and gpu.dtype == torch.float32
+    assert torch.equal(gpu.cpu(), cpu)
