@@ -62,6 +62,17 @@ CONFIGS = {
 STRONG_GROUPS = 16
 
 
+def config_dict(config_id, nb, world, full_finetune=False):
+    """The `config` object of the JSON line; both arms (ours and `--impl reference`) print the SAME object."""
+    spec = CONFIGS[config_id]
+    return {"workload": spec["workload"].format(nb=nb) + (" -- FULL fine-tuning (use_lora=False), not LoRA"
+                                                           if full_finetune else ""),
+            "baseline_config": config_id,
+            "groups_per_step_all_ranks": nb * world,
+            "l2": "per-step working set (4.4 GB weights + activations) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -194,7 +205,9 @@ def run_reference(args):
             "steps_executed": len(vals),
             "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SD3.5-medium LoRA 512x512, 10 steps, G=8, PickScore reward (config 2)"},
+            # the same config object as the GPU arm prints for this launch (the CPU arm is one process on rank 0's host cores;
+            # its per-sample time does not depend on how many groups a step holds)
+            "config": config_dict(2, CONFIGS[2]["groups"], max(int(os.environ.get("WORLD_SIZE", "1")), 1)),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -490,12 +503,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": spec["workload"].format(nb=nb) + (" -- FULL fine-tuning (use_lora=False), not LoRA"
-                                                                    if args.full_finetune else ""),
-                       "baseline_config": args.config,
-                       "groups_per_step_all_ranks": nb * world,
-                       "l2": "per-step working set (4.4 GB weights + activations) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world} (prompt groups sharded, LoRA-grad all-reduce)"},
+            "config": config_dict(args.config, nb, world, args.full_finetune),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels,
