@@ -553,10 +553,11 @@ class SD3Transformer2DModel(torch.nn.Module):
 
     def _forward_full(self, hidden_states, timestep, encoder_hidden_states, pooled_projections, upto=None):
         """The same network as `forward`, written for gradients to EVERY parameter: each Linear is `ops.linear`
-        (tcgen05 GEMM forward, dX on the same kernel, dW on the split-K TN kernel, db on the column-sum kernel), the joint
-        attention is `ops.attention` (tcgen05 forward and backward); the adaLN modulation, gates, per-head RMSNorm and
-        GELU(tanh) are torch elementwise ops so that autograd carries their parameter gradients (shift / scale / gate
-        vectors -> the adaLN linears -> the timestep / pooled-text embedders; RMSNorm weights)."""
+        (tcgen05 GEMM forward, dX on the same kernel, dW on the split-K TN kernel, db on the column-sum kernel), the
+        feed-forwards are `ops.mlp_gelu` (GELU and its derivative in GEMM epilogues), the joint attention is
+        `ops.attention` (tcgen05 forward and backward), LayerNorm-modulate and per-head RMSNorm + concat run on their native
+        forward / activation-gradient kernels and add the gradients of their parameters (shift / scale vectors, RMS
+        weights) by torch reductions in the backward; only the gated residual adds are torch elementwise ops."""
         if self._lora_dirty:
             self._refresh_from_master()
         cfg, d, bf = self.cfg, self.d, torch.bfloat16
@@ -566,28 +567,25 @@ class SD3Transformer2DModel(torch.nn.Module):
         else:
             W = self.p
         lin = lambda name, v: ops.linear(v, W[name + ".weight"], W.get(name + ".bias"))
+        ln_mod = ops.ln_modulate_full                          # native forward / dx; shift / scale gradients by reduction
 
-        def ln_mod(v, shift, scale):
-            n = F.layer_norm(v.float(), (d,), eps=1e-6)
-            return (n * (1.0 + scale.float()[:, None]) + shift.float()[:, None]).to(bf)
-
-        def rms(v, w):                                         # v [B, S, H, D]
-            vf = v.float()
-            return (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()).to(bf)
-
-        def heads(v):
-            return v.view(v.shape[0], v.shape[1], H, D)
+        def qkv_of(pre, names, v):
+            """One GEMM for the three projections (their weights concatenated: autograd splits the gradient back)."""
+            wcat = torch.cat([W[f"{pre}.{n}.weight"] for n in names], 0)
+            bcat = torch.cat([W[f"{pre}.{n}.bias"] for n in names], 0)
+            return ops.linear(v, wcat, bcat)
 
         def attn(pre, xq, cq=None, ctx_out=True):
-            q, k, v = (heads(lin(f"{pre}.to_{n}", xq)) for n in "qkv")
+            qkv_x = qkv_of(pre, ("to_q", "to_k", "to_v"), xq)
+            qkv_c = None if cq is None else qkv_of(pre, ("add_q_proj", "add_k_proj", "add_v_proj"), cq)
+            nw = lambda n: W.get(f"{pre}.{n}.weight") if cfg["qk_norm"] else None
             if cfg["qk_norm"]:
-                q, k = rms(q, W[f"{pre}.norm_q.weight"]), rms(k, W[f"{pre}.norm_k.weight"])
-            if cq is not None:
-                aq, ak, av = (heads(lin(f"{pre}.add_{n}_proj", cq)) for n in "qkv")
-                if cfg["qk_norm"]:
-                    aq, ak = rms(aq, W[f"{pre}.norm_added_q.weight"]), rms(ak, W[f"{pre}.norm_added_k.weight"])
-                q, k, v = torch.cat([q, aq], 1), torch.cat([k, ak], 1), torch.cat([v, av], 1)      # [image, text]
-            o = ops.attention(torch.stack([q, k, v], dim=2).contiguous())                         # [B, S, H, D]
+                joint = ops.qk_norm_concat_full(qkv_x, qkv_c, nw("norm_q"), nw("norm_k"),
+                                                None if cq is None else nw("norm_added_q"),
+                                                None if cq is None else nw("norm_added_k"), H, D)
+            else:
+                joint = ops.qk_norm_concat(qkv_x, qkv_c, None, None, None, None, H, D)
+            o = ops.attention(joint)                                                              # [B, S, H, D]
             o = o.reshape(o.shape[0], o.shape[1], d)
             if cq is None:
                 return lin(f"{pre}.to_out.0", o), None
@@ -595,7 +593,10 @@ class SD3Transformer2DModel(torch.nn.Module):
             return lin(f"{pre}.to_out.0", o[:, :n]), (lin(f"{pre}.to_add_out", o[:, n:]) if ctx_out else None)
 
         def ff(pre, v):
-            return lin(f"{pre}.net.2", F.gelu(lin(f"{pre}.net.0.proj", v), approximate="tanh"))
+            return ops.mlp_gelu(v, W[f"{pre}.net.0.proj.weight"], W[f"{pre}.net.0.proj.bias"], W[f"{pre}.net.2.weight"],
+                                W[f"{pre}.net.2.bias"], approximate="tanh")
+
+        gated = lambda res, gate, branch: torch.addcmul(res, gate[:, None], branch)               # res + gate * branch
 
         B, C, Hh, Ww = hidden_states.shape
         h, w = Hh // ps, Ww // ps
@@ -628,16 +629,16 @@ class SD3Transformer2DModel(torch.nn.Module):
             c1 = ln_mod(c, csh, csc)
             a, ca = attn(f"{pre}.attn", x1, c1, ctx_out=not last)
             x_in = x
-            x = x + g[:, None] * a
+            x = gated(x, g, a)
             if dual:
                 a2, _ = attn(f"{pre}.attn2", ln_mod(x_in, sh2, sc2))
-                x = x + g2[:, None] * a2
-            x = x + g_m[:, None] * ff(f"{pre}.ff", ln_mod(x, sh_m, sc_m))
+                x = gated(x, g2, a2)
+            x = gated(x, g_m, ff(f"{pre}.ff", ln_mod(x, sh_m, sc_m)))
             if last:
                 c = None
                 continue
-            c = c + cg[:, None] * ca
-            c = c + cg_m[:, None] * ff(f"{pre}.ff_context", ln_mod(c, csh_m, csc_m))
+            c = gated(c, cg, ca)
+            c = gated(c, cg_m, ff(f"{pre}.ff_context", ln_mod(c, csh_m, csc_m)))
         if upto is not None:
             return x, c
         sc, sh = lin("norm_out.linear", st).chunk(2, dim=1)

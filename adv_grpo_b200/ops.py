@@ -310,6 +310,77 @@ class _LayerNormAffine(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), dw, db, None
 
 
+class _LnModulateFull(torch.autograd.Function):
+    """`ln_modulate` for full fine-tuning: the same forward kernel, and a backward that also returns the gradients of the
+    shift / scale vectors (they come from TRAINABLE adaLN linears there): dx on the native kernel, d shift = sum_t dy,
+    d scale = sum_t dy * xhat as torch reductions over the token axis."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale, eps):
+        x = _bf16c(x)
+        B, S, D = x.shape
+        y = torch.empty_like(x)
+        _lib.call("advgrpo_ln_modulate_fwd", _ptr(x), _ptr(shift), _ptr(scale), None, None, shift.stride(0), _ptr(y), None,
+                  B, S, D, float(eps), _stream())
+        ctx.save_for_backward(x, scale)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        B, S, D = x.shape
+        dy = _bf16c(dy)
+        dx = torch.empty_like(x)
+        _lib.call("advgrpo_ln_modulate_bwd", _ptr(x), _ptr(scale), None, scale.stride(0), _ptr(dy), None, _ptr(dx), 0, B, S, D,
+                  ctx.eps, _stream())
+        dyf = dy.float()
+        dshift = dyf.sum(1).to(torch.bfloat16)
+        xhat = torch.nn.functional.layer_norm(x.float(), (D,), eps=ctx.eps)
+        dscale = (dyf * xhat).sum(1).to(torch.bfloat16)
+        return dx, dshift, dscale, None
+
+
+def ln_modulate_full(x, shift, scale, eps=1e-6):
+    """LayerNorm(no affine)(x) * (1 + scale[:, None]) + shift[:, None] with gradients to x, shift AND scale."""
+    for m in (shift, scale):
+        if m.stride(-1) != 1 or m.dtype != torch.bfloat16 or m.stride(0) != shift.stride(0):
+            raise _lib.AdvGrpoError("modulation chunks must be bf16 row views of one [B, k*D] matrix")
+    return _LnModulateFull.apply(x, shift, scale, eps)
+
+
+class _QkNormConcatFull(torch.autograd.Function):
+    """`qk_norm_concat` for full fine-tuning: native forward and activation gradients; the gradients of the four per-head
+    RMSNorm weight vectors (d w[c] = sum over tokens and heads of dy * xhat) as torch reductions."""
+
+    @staticmethod
+    def forward(ctx, qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D, eps):
+        out = _QkNormConcat.forward(ctx, qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt = ctx.saved_tensors
+        H, D, eps = ctx.meta
+        d_img, d_txt = _QkNormConcat.backward(ctx, dout)[:2]
+        B, S_img, _ = qkv_img.shape
+
+        def wgrad(src, dy_rows, sec):
+            x = src.view(src.shape[0], src.shape[1], 3, H, D)[:, :, sec].float()
+            xhat = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+            return (dy_rows[:, :, sec].float() * xhat).sum((0, 1, 2)).to(torch.bfloat16)
+
+        dq_i, dk_i = wgrad(qkv_img, dout[:, :S_img], 0), wgrad(qkv_img, dout[:, :S_img], 1)
+        dq_t = dk_t = None
+        if qkv_txt is not None:
+            dq_t, dk_t = wgrad(qkv_txt, dout[:, S_img:], 0), wgrad(qkv_txt, dout[:, S_img:], 1)
+        return d_img, d_txt, dq_i, dk_i, dq_t, dk_t, None, None, None
+
+
+def qk_norm_concat_full(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D=64, eps=1e-6):
+    return _QkNormConcatFull.apply(qkv_img, qkv_txt, wq_img, wk_img, wq_txt, wk_txt, H, D, eps)
+
+
 def layer_norm(x, weight, bias, eps):
     """Affine LayerNorm over the last dim of the reward towers' blocks (bf16, width a multiple of 256) on the
     `ln_modulate` kernel; differentiable (native backward) when the input or the parameters require a gradient."""
@@ -613,32 +684,36 @@ class _MlpGelu(torch.autograd.Function):
     epilogue of the fc2 input-gradient GEMM (no elementwise pass, the hidden activation's gradient never exists in HBM)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, tanh):
         x2 = _bf16c(x).reshape(-1, x.shape[-1])
         w1h, w2h = _w16(w1), _w16(w2)
-        z = torch.empty((x2.shape[0], w1h.shape[0]), dtype=torch.bfloat16, device=x2.device)
-        a = gemm(x2, w1h, bias=_w16(b1), epilogue=EPI_GELU_ERF, preact_out=z)
+        need = any(ctx.needs_input_grad)
+        z = torch.empty((x2.shape[0], w1h.shape[0]), dtype=torch.bfloat16, device=x2.device) if need else None
+        a = gemm(x2, w1h, bias=_w16(b1), epilogue=EPI_GELU_TANH if tanh else EPI_GELU_ERF, preact_out=z)
         y = gemm(a, w2h, bias=_w16(b2))
-        ctx.save_for_backward(x2, w1h, w2h, z, a)
-        ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        if need:
+            ctx.save_for_backward(x2, w1h, w2h, z, a)
+        ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype, bool(tanh))
         return y.reshape(*x.shape[:-1], w2h.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
         x2, w1h, w2h, z, a = ctx.saved_tensors
-        shape, w1dt, b1dt, w2dt, b2dt = ctx.meta
+        shape, w1dt, b1dt, w2dt, b2dt, tanh = ctx.meta
         dy2 = _bf16c(dy).reshape(-1, w2h.shape[0])
-        dz = gemm(dy2, w2h.t().contiguous(), epilogue=EPI_GELU_ERF_GRAD, residual=z)
+        dz = gemm(dy2, w2h.t().contiguous(), epilogue=EPI_GELU_TANH_GRAD if tanh else EPI_GELU_ERF_GRAD, residual=z)
         dx = gemm(dz, w1h.t().contiguous()).reshape(shape) if ctx.needs_input_grad[0] else None
         dw1 = gemm_tn(dz, x2).to(w1dt) if ctx.needs_input_grad[1] else None
         db1 = col_sum(dz).to(b1dt) if ctx.needs_input_grad[2] else None
         dw2 = gemm_tn(dy2, a).to(w2dt) if ctx.needs_input_grad[3] else None
         db2 = col_sum(dy2).to(b2dt) if ctx.needs_input_grad[4] else None
-        return dx, dw1, db1, dw2, db2
+        return dx, dw1, db1, dw2, db2, None
 
 
-def mlp_gelu(x, w1, b1, w2, b2):
-    return _MlpGelu.apply(x, w1, b1, w2, b2)
+def mlp_gelu(x, w1, b1, w2, b2, approximate="none"):
+    """fc2(GELU(fc1(x))) with a native forward and backward (all four parameter gradients); approximate = "none" (erf:
+    CLIP / DINOv2) or "tanh" (the MMDiT feed-forward)."""
+    return _MlpGelu.apply(x, w1, b1, w2, b2, approximate == "tanh")
 
 
 # --------------------------------------------------------------------------- score heads / discriminator step
