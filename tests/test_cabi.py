@@ -56,9 +56,20 @@ def test_ops_refuse_cpu_tensors():
     from adv_grpo_b200 import ops
     with pytest.raises(_lib.AdvGrpoError, match="CUDA"):
         ops.group_advantage(torch.zeros(4), torch.zeros(4, dtype=torch.int64))
-    from adv_grpo_b200.optim import FlatClipAdamW
+    from adv_grpo_b200.optim import FlatClipAdamW, TorchOrderAdam
     with pytest.raises(ValueError, match="CUDA"):
         FlatClipAdamW([torch.nn.Parameter(torch.zeros(8))])
+    with pytest.raises(ValueError, match="CUDA"):
+        TorchOrderAdam([torch.nn.Parameter(torch.zeros(8))])
+    # the discriminator-step / score-head ops have no CPU path either
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    for call in (lambda: ops.col_sum(x), lambda: ops.gemm_tn(x, x), lambda: ops.linear(x, x),
+                 lambda: ops.attention_small(x.view(1, 4, 1, 64), x.view(1, 4, 1, 64), x.view(1, 4, 1, 64)),
+                 lambda: ops.gather_rows_l2norm(x.view(1, 4, 64), torch.zeros(1, 2, dtype=torch.int64), True),
+                 lambda: ops.pil_resize_bilinear(torch.zeros(8, 8, 3, dtype=torch.uint8), 4, 4),
+                 lambda: ops.row_softmax_f32(torch.zeros(2, 8))):
+        with pytest.raises(_lib.AdvGrpoError, match="CUDA"):
+            call()
 
 
 def test_empty_inputs_are_noops_or_clean_errors():
