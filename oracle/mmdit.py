@@ -61,6 +61,20 @@ def rms_norm(x, w, eps=1e-6):
     return (x * torch.rsqrt(var + eps)).to(w.dtype) * w
 
 
+def ada_layer_norm_zero(x, e):
+    """diffusers AdaLayerNormZero (call site fast.py:630-637): e = linear(silu(temb)) [B, 6 d] chunks as (shift_msa, scale_msa,
+    gate_msa, shift_mlp, scale_mlp, gate_mlp); returns the modulated input of the attention and the remaining four vectors."""
+    sh, sc, g, sh_m, sc_m, g_m = e.chunk(6, dim=1)
+    return layer_norm(x) * (1 + sc[:, None]) + sh[:, None], g, sh_m, sc_m, g_m
+
+
+def ada_layer_norm_continuous(x, e):
+    """diffusers AdaLayerNormContinuous (norm_out, and norm1_context of the context_pre_only last block): e = linear(silu(temb))
+    [B, 2 d] chunks as (SCALE, SHIFT) -- the opposite order of AdaLayerNormZero."""
+    sc, sh = e.chunk(2, dim=1)
+    return layer_norm(x) * (1 + sc)[:, None] + sh[:, None]
+
+
 class MMDiTOracle:
     def __init__(self, params, cfg, lora=None, lora_scale=2.0, dtype=torch.float32):
         """params: diffusers-named dict. cfg: dict(num_layers, heads, head_dim, dual_layers,
@@ -114,19 +128,17 @@ class MMDiTOracle:
         last = i == self.cfg["num_layers"] - 1
         dual = i in self.cfg["dual_layers"]
         e = self.lin(f"{pre}.norm1.linear", F.silu(temb))
-        if dual:
-            sh, sc, g, sh_m, sc_m, g_m, sh2, sc2, g2 = e.chunk(9, dim=1)
-        else:
-            sh, sc, g, sh_m, sc_m, g_m = e.chunk(6, dim=1)
         nx = layer_norm(x)
-        x1 = nx * (1 + sc[:, None]) + sh[:, None]
+        if dual:                                               # SD35AdaLayerNormZeroX: the six AdaLayerNormZero chunks + three for attn2
+            x1, g, sh_m, sc_m, g_m = ada_layer_norm_zero(x, e[:, :6 * x.shape[-1]])
+            sh2, sc2, g2 = e[:, 6 * x.shape[-1]:].chunk(3, dim=1)
+        else:
+            x1, g, sh_m, sc_m, g_m = ada_layer_norm_zero(x, e)
         ce = self.lin(f"{pre}.norm1_context.linear", F.silu(temb))
         if last:                                               # AdaLayerNormContinuous: scale, shift
-            csc, csh = ce.chunk(2, dim=1)
-            c1 = layer_norm(c) * (1 + csc)[:, None] + csh[:, None]
+            c1 = ada_layer_norm_continuous(c, ce)
         else:
-            csh, csc, cg, csh_m, csc_m, cg_m = ce.chunk(6, dim=1)
-            c1 = layer_norm(c) * (1 + csc[:, None]) + csh[:, None]
+            c1, cg, csh_m, csc_m, cg_m = ada_layer_norm_zero(c, ce)
         a, ca = self._attn(f"{pre}.attn", x1, c1, ctx_out=not last)
         x = x + g[:, None] * a
         if dual:
@@ -161,8 +173,7 @@ class MMDiTOracle:
             x, c = self.block(i, x, c, temb)
         if upto is not None:
             return x, c
-        sc, sh = self.lin("norm_out.linear", F.silu(temb)).chunk(2, dim=1)
-        x = layer_norm(x) * (1 + sc)[:, None] + sh[:, None]
+        x = ada_layer_norm_continuous(x, self.lin("norm_out.linear", F.silu(temb)))
         x = self.lin("proj_out", x)
         x = x.reshape(B, h, w, ps, ps, cfg["in_channels"])
         x = torch.einsum("nhwpqc->nchpwq", x).reshape(B, cfg["in_channels"], h * ps, w * ps)

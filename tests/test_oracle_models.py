@@ -305,3 +305,34 @@ def test_scheduler_shift_is_the_flux_time_shift():
     want = sampling.time_shift(math.log(3.0), 1.0, s)
     assert torch.allclose(sch.sigmas[:-1].double(), want, atol=1e-6)
     assert sch.sigmas[-1] == 0 and torch.allclose(sch.timesteps, sch.sigmas[:-1] * 1000)
+
+
+def test_mmdit_adaln_chunk_orders_match_transformers_dit_modules():
+    """Independent pin of the two adaLN conventions the oracle restates from diffusers: transformers ships, inside the
+    Qwen2.5-Omni token2wav DiT, module-for-module descendants of diffusers' `AdaLayerNormZero` (chunks = shift_msa,
+    scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp; LayerNorm without affine, eps 1e-6; `linear(silu(emb))`) and of
+    `AdaLayerNormContinuous` as used for the final layer (chunks = SCALE, SHIFT -- the opposite order).  Same weights, same
+    inputs: `oracle.mmdit.ada_layer_norm_zero` / `ada_layer_norm_continuous` (used by every block and by norm_out /
+    the last block's norm1_context) must reproduce them."""
+    import pytest
+    qo = pytest.importorskip("transformers.models.qwen2_5_omni.modeling_qwen2_5_omni")
+    from oracle import mmdit as mm
+    torch.manual_seed(0)
+    d, B, S = 64, 3, 7
+    x, temb = torch.randn(B, S, d), torch.randn(B, d)
+    zero = qo.Qwen2_5_OmniAdaLayerNormZero(d)
+    with torch.no_grad():
+        ref = zero(x, emb=temb)
+        e = torch.nn.functional.linear(torch.nn.functional.silu(temb), zero.linear.weight, zero.linear.bias)
+        got = mm.ada_layer_norm_zero(x, e)
+    assert len(ref) == len(got) == 5
+    for r, g in zip(ref, got):                                   # modulated x, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        assert torch.allclose(r, g, atol=1e-6)
+    final = qo.Qwen2_5_OmniAdaLayerNormZero_Final(d)
+    with torch.no_grad():
+        ref_f = final(x, temb)
+        e2 = torch.nn.functional.linear(torch.nn.functional.silu(temb), final.linear.weight, final.linear.bias)
+        got_f = mm.ada_layer_norm_continuous(x, e2)
+        swapped = mm.layer_norm(x) * (1 + e2.chunk(2, dim=1)[1])[:, None] + e2.chunk(2, dim=1)[0][:, None]
+    assert torch.allclose(ref_f, got_f, atol=1e-6)
+    assert not torch.allclose(ref_f, swapped, atol=1e-3)         # the order matters: (shift, scale) would be caught
