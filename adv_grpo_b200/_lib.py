@@ -56,6 +56,11 @@ SIGNATURES = {
     "advgrpo_clip_preprocess_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_clip_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "advgrpo_dino_preprocess": (c_int, [_P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "advgrpo_jpeg_parse": (c_int, [_P, _SZ, _P]),
+    "advgrpo_jpeg_coef_count": (_SZ, [_P]),
+    "advgrpo_jpeg_entropy_decode": (c_int, [_P, _SZ, _P, _P]),
+    "advgrpo_jpeg_workspace_bytes": (_SZ, [_P]),
+    "advgrpo_jpeg_idct_to_rgb": (c_int, [_P, _P, _P, _P, _P, _SZ, _P]),
     "advgrpo_pil_resize_bilinear_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_pil_resize_bilinear_u8": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "advgrpo_group_norm_workspace_bytes": (_SZ, [_I64, _I64]),
@@ -87,6 +92,14 @@ _EXTRA = {
     "advgrpo_debug_set_attn_trace": (None, [_P]),
 }
 
+class JpegInfo(ctypes.Structure):
+    """`advgrpo_jpeg_info` of include/advgrpo_b200.h."""
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("ncomp", ctypes.c_int32),
+                ("h", ctypes.c_int32 * 3), ("v", ctypes.c_int32 * 3), ("tq", ctypes.c_int32 * 3),
+                ("blocks_w", ctypes.c_int32 * 3), ("blocks_h", ctypes.c_int32 * 3),
+                ("restart_interval", ctypes.c_int32), ("supported", ctypes.c_int32)]
+
+
 _lib = None
 
 
@@ -115,7 +128,8 @@ def load():
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
-                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_device_check": 0}
+                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_jpeg_parse": 0, "advgrpo_jpeg_entropy_decode": 0,
+                     "advgrpo_jpeg_idct_to_rgb": 4, "advgrpo_device_check": 0}
 _launches = [0]
 
 

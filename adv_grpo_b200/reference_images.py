@@ -1,10 +1,11 @@
 """Reference ("real") images of the adversarial loop: the `{prompt: [file, ...]}` index JSON (`config.json_path`,
 README.md:114-128 of the reference) and the per-batch loading of `scripts/train_sd3_fast_pickscore.py:705-707,
 773-799`: `Image.open(root / name).convert("RGB")` -> `transforms.Resize((512, 512))` (PIL bilinear with Pillow's
-antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  The file read and the entropy decode
-(Huffman / inflate) are host I/O as in the reference; with a CUDA device the decoded bytes go to the GPU as they are and
-the antialiased bilinear resize + ToTensor run there (`ops.pil_resize_bilinear`, Pillow bit-exact) -- the per-image
-PIL resize, the costliest host step after the decode, leaves the sampling loop.  Results are cached per prompt because
+antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  With a CUDA device: baseline JPEG files are
+entropy-decoded by the library's own host Huffman decoder and everything after that (inverse DCT, chroma upsampling,
+colour conversion: `jpeg.decode_jpeg_to_device`, libjpeg / Pillow bit-exact) runs on the GPU; other formats (PNG,
+progressive or CMYK JPEG) are decoded by Pillow on the host and their bytes uploaded; the antialiased bilinear resize +
+ToTensor always run on the GPU (`ops.pil_resize_bilinear`, Pillow bit-exact).  Results are cached per prompt because
 the files never change, which the reference does not do (it re-opens every file of the prompt for every batch).
 SURVEY.md section 8f rank 3."""
 import json
@@ -27,14 +28,26 @@ class ReferenceImageIndex:
 
     def _load(self, path):
         from PIL import Image
+        cuda = torch.device(self.device).type == "cuda"
+        if cuda:                                                       # baseline JPEG: host Huffman decode, the rest on the GPU
+            from . import _lib, jpeg, ops
+            raw = None
+            try:
+                with open(path, "rb") as f:
+                    data = f.read()
+                if data[:2] == b"\xff\xd8":
+                    raw = jpeg.decode_jpeg_to_device(data, self.device)   # None: progressive / CMYK / ... -> Pillow below
+            except (OSError, _lib.AdvGrpoError):
+                raw = None                                             # unreadable / corrupt: Pillow decides (and falls back)
+            if raw is not None:
+                return ops.pil_resize_bilinear(raw, self.size, self.size)
         try:
             img = Image.open(path).convert("RGB")
         except Exception as e:                                         # train_pick:781-786: fall back to the default image
             if self.default_image is None:
                 raise FileNotFoundError(f"reference image {path} could not be opened ({e}) and no default_image is set")
             img = Image.open(self.default_image).convert("RGB")
-        if torch.device(self.device).type == "cuda":                   # bytes -> device, resize + ToTensor on the GPU
-            from . import ops
+        if cuda:                                                       # decoded bytes -> device, resize + ToTensor on the GPU
             raw = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).to(self.device)
             return ops.pil_resize_bilinear(raw, self.size, self.size)
         img = img.resize((self.size, self.size), Image.BILINEAR)       # CPU device (host tests): torchvision Resize on PIL

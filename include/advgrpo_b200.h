@@ -353,6 +353,29 @@ int advgrpo_clip_preprocess(const void* images, int images_u8, int64_t B, int64_
 size_t advgrpo_pil_resize_bilinear_workspace_bytes(int64_t H, int64_t W, int64_t out_h, int64_t out_w);
 int advgrpo_pil_resize_bilinear_u8(const uint8_t* img_hwc, int64_t H, int64_t W, int64_t out_h, int64_t out_w, float* out_chw,
                                    uint8_t* u8_out_chw, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
+/* Baseline JPEG decode of the reference images (`Image.open(fpath).convert("RGB")`,
+ * scripts/train_sd3_fast_pickscore.py:773-786), hybrid: marker parse + sequential Huffman entropy decode on the HOST (plain C++
+ * inside this library), dequantisation + islow integer IDCT + fancy chroma upsampling + YCbCr -> RGB on the DEVICE.
+ * Bit-exact with libjpeg(-turbo)'s default settings, i.e. with Pillow, for baseline / extended-sequential 8-bit Huffman
+ * files, grayscale or YCbCr with 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, with or without restart intervals.
+ * advgrpo_jpeg_parse fills `info` (host call); info->supported == 0 marks a valid file outside that subset (progressive,
+ * arithmetic, 12-bit, CMYK / RGB-coded, multi-scan): the caller keeps its host decoder for it -- the return value is still 0.
+ * advgrpo_jpeg_entropy_decode (host call): coefs_host int16 [advgrpo_jpeg_coef_count(info)] = per component
+ * [blocks_h, blocks_w, 64] quantised coefficients in natural order; qtabs_host uint16 [3 * 64] natural-order tables.
+ * advgrpo_jpeg_idct_to_rgb: device pointers of the same two arrays -> rgb_hwc_dev uint8 [height, width, 3]. */
+typedef struct {
+  int32_t width, height, ncomp;
+  int32_t h[3], v[3], tq[3];          /* sampling factors and quantisation-table ids per component */
+  int32_t blocks_w[3], blocks_h[3];   /* block grid per component, padded to whole MCUs */
+  int32_t restart_interval;
+  int32_t supported;
+} advgrpo_jpeg_info;
+int advgrpo_jpeg_parse(const uint8_t* file, size_t nbytes, advgrpo_jpeg_info* info);
+size_t advgrpo_jpeg_coef_count(const advgrpo_jpeg_info* info);
+int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coefs_host, uint16_t* qtabs_host);
+size_t advgrpo_jpeg_workspace_bytes(const advgrpo_jpeg_info* info);
+int advgrpo_jpeg_idct_to_rgb(const int16_t* coefs_dev, const uint16_t* qtabs_dev, const advgrpo_jpeg_info* info,
+                             uint8_t* rgb_hwc_dev, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
 /* A8b preprocessing (adv_grpo/rewards.py:379-391): bicubic (A = -0.75, align_corners =
  * False, no antialias) resize to out x out, ImageNet normalisation, cast to bf16. */
 int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64_t H, int64_t W,

@@ -629,3 +629,23 @@ def test_reference_image_index_gpu_path_equals_pil_path(tmp_path):
     cpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device="cpu", **kw)("a cat")
     assert gpu.is_cuda and gpu.shape == (3, 3, 256, 256) and gpu.dtype == torch.float32
     assert torch.equal(gpu.cpu(), cpu)
+
+
+# ------------------------------------------------------------------ 8f-3 JPEG decode (host Huffman + device IDCT / colour)
+@pytest.mark.parametrize("h,w,kw", [(512, 512, dict(quality=90, subsampling=2)), (768, 1024, dict(quality=85, subsampling=2)),
+                                    (333, 517, dict(quality=75, subsampling=1)), (600, 401, dict(quality=95, subsampling=0)),
+                                    (480, 640, dict(quality=60, subsampling=2, restart_marker_blocks=4)),
+                                    (257, 129, dict(quality=80, gray=True)), (1, 1, dict(quality=90, subsampling=2)),
+                                    (17, 9, dict(quality=100, subsampling=2))])
+def test_jpeg_decode_bit_exact_with_pillow(h, w, kw):
+    """`Image.open(path).convert("RGB")` (train_sd3_fast_pickscore.py:779) on the device: every byte equals Pillow's decode."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import jpeg as jpeg_b
+    from jpeg_util import _jpeg_bytes
+    data = _jpeg_bytes(h, w, seed=h + w, **kw)
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+    got = jpeg_b.decode_jpeg_to_device(data, DEV)
+    assert got.dtype == torch.uint8 and got.shape == (h, w, 3)
+    assert torch.equal(got.cpu(), torch.from_numpy(ref.copy()))
+    assert jpeg_b.decode_jpeg_to_device(_jpeg_bytes(32, 32, progressive=True), DEV) is None

@@ -336,3 +336,51 @@ def test_mmdit_adaln_chunk_orders_match_transformers_dit_modules():
         swapped = mm.layer_norm(x) * (1 + e2.chunk(2, dim=1)[1])[:, None] + e2.chunk(2, dim=1)[0][:, None]
     assert torch.allclose(ref_f, got_f, atol=1e-6)
     assert not torch.allclose(ref_f, swapped, atol=1e-3)         # the order matters: (shift, scale) would be caught
+
+
+from jpeg_util import _jpeg_bytes  # noqa: E402
+
+
+JPEG_CASES = [((64, 64), dict(quality=90, subsampling=0)), ((48, 80), dict(quality=75, subsampling=2)),
+              ((37, 53), dict(quality=85, subsampling=2)), ((33, 47), dict(quality=60, subsampling=1)),
+              ((17, 9), dict(quality=80, subsampling=2)), ((40, 40), dict(quality=50, subsampling=2, restart_marker_blocks=2)),
+              ((1, 1), dict(quality=90, subsampling=2)), ((8, 2), dict(quality=90, subsampling=1)),
+              ((24, 40), dict(quality=100, subsampling=0)), ((30, 45), dict(quality=80, gray=True))]
+
+
+def test_jpeg_oracle_matches_pillow():
+    """oracle/jpeg.py (numpy restatement of libjpeg's default baseline decode: Huffman, islow IDCT, fancy upsampling, YCbCr
+    tables) returns exactly Pillow's pixels -- the pin of the oracle the GPU decoder is tested against -- for 4:4:4, 4:2:2,
+    4:2:0, grayscale, odd sizes down to 1x1 and restart intervals; progressive files are reported unsupported."""
+    import io
+    import pytest
+    from PIL import Image
+    from oracle import jpeg as jpeg_o
+    for (h, w), kw in JPEG_CASES:
+        data = _jpeg_bytes(h, w, seed=h + w, **kw)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        assert np.array_equal(jpeg_o.decode_rgb(data), ref), ((h, w), kw)
+    with pytest.raises(jpeg_o.JpegUnsupported):
+        jpeg_o.decode_rgb(_jpeg_bytes(16, 16, progressive=True))
+
+
+def test_jpeg_host_entropy_decoder_matches_oracle():
+    """The library's host Huffman decoder (csrc/jpeg.cu, plain C++; runs without a GPU) yields the oracle's coefficient
+    blocks and quantisation tables bit for bit, and classifies unsupported files without raising."""
+    from adv_grpo_b200 import jpeg as jpeg_b
+    from oracle import jpeg as jpeg_o
+    for (h, w), kw in JPEG_CASES:
+        data = _jpeg_bytes(h, w, seed=h + w, **kw)
+        info = jpeg_o.parse(data)
+        ref = jpeg_o.entropy_decode(data, info)
+        got, qt, gi = jpeg_b.coefficients_as_numpy(data)
+        assert gi.supported == 1 and (gi.height, gi.width) == (h, w) and gi.ncomp == len(ref)
+        for c in range(gi.ncomp):
+            assert np.array_equal(got[c], ref[c]), ((h, w), kw, c)
+            assert np.array_equal(qt[c], info["q"][info["frame"]["comps"][c]["tq"]])
+    assert jpeg_b.jpeg_info(_jpeg_bytes(16, 16, progressive=True)).supported == 0
+    assert jpeg_b.coefficients_as_numpy(_jpeg_bytes(16, 16, progressive=True))[0] is None
+    import pytest
+    from adv_grpo_b200 import _lib
+    with pytest.raises(_lib.AdvGrpoError):
+        jpeg_b.jpeg_info(b"not a jpeg at all")
