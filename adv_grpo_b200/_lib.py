@@ -78,6 +78,8 @@ SIGNATURES = {
     "advgrpo_pickscore_head": (c_int, [_P, _P, _P, _P, _I, _P, _I64, _I64, _I64, _I, _P]),
     "advgrpo_layer_norm_affine_bwd_workspace_bytes": (_SZ, [_I64, _I64]),
     "advgrpo_layer_norm_affine_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P, _SZ, _P]),
+    "advgrpo_ln_modulation_grads_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "advgrpo_ln_modulation_grads": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _F, _P, _SZ, _P]),
     "advgrpo_adam_torch_order": (c_int, [_P, _P, _P, _P, _I64, _I, _I, _D, _D, _D, _D, _I64, _I, _P]),
     "advgrpo_row_softmax_f32": (c_int, [_P, _P, _I64, _I64, _F, _I, _P]),
     "advgrpo_attn_small_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _F, _I, _P]),
@@ -128,7 +130,7 @@ def load():
 
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
-                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_jpeg_parse": 0, "advgrpo_jpeg_entropy_decode": 0,
+                     "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_ln_modulation_grads": 3, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_jpeg_parse": 0, "advgrpo_jpeg_entropy_decode": 0,
                      "advgrpo_jpeg_idct_to_rgb": 4, "advgrpo_device_check": 0}
 _launches = [0]
 

@@ -235,7 +235,9 @@ int advgrpo_gemm_tn_skinny(const void* a, const void* b, void* out, int64_t Kt, 
     attr_set = true;
   }
   static const int bn_env = getenv("ADVGRPO_GEMM_TN_BN") ? atoi(getenv("ADVGRPO_GEMM_TN_BN")) : 0;
-  const int bn = bn_env == 128 || bn_env == 256 ? bn_env : (Nb >= 3072 ? 256 : 128);
+  // 256-column tiles when B is wide (its 128-column tiles would re-read the A tile as often as B itself) or when A is a
+  // full weight-gradient operand (Ms >= 512: the grid already has hundreds of clusters, halving A's re-reads wins)
+  const int bn = bn_env == 128 || bn_env == 256 ? bn_env : ((Nb >= 3072 || (Ms >= 512 && Nb >= 256)) ? 256 : 128);
   dim3 grid((unsigned)(((Nb + bn - 1) / bn) * CL), 1, (unsigned)((Ms + BM - 1) / BM));
   if (bn == 256) {
     ADVGRPO_CUDA_CALL(launch_chain(gemm_tn_kernel<256>, grid, dim3(kThreads), TnCfg<256>::kSmem, st, CL, tm_a, tm_b,

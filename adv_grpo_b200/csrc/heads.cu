@@ -7,6 +7,9 @@
 //   * dino_hinge           : hinge loss of train_dino (train_sd3_fast_dino_patch.py:186-219), accuracy, d loss / d logit
 //   * head_dz              : dz = (dl w2) * gelu_erf'(z) -- backward through Linear(hidden, 1) and the GELU in one pass
 //   * col_sum              : sum_r s[r] a[r, c] b[r, c] (bias gradients, dw2 of the head), deterministic two-stage reduction
+//   * ln_modulation_grads  : per-sample d shift = sum_t dy, d scale = sum_t dy * xhat of an adaLN LayerNorm-modulate (full
+//                            fine-tuning: the modulation vectors come from trainable linears), row statistics + segmented
+//                            column sums
 //   * layer_norm_affine_bwd: dx of an affine LayerNorm + d weight / d bias (the trainable CLIP blocks of the PickScore
 //                            discriminator step, scripts/train_sd3_fast_pickscore.py:1016-1029)
 //   * adam_torch_order     : torch.optim.Adam's multi-tensor update (the discriminator optimizers, train_pick:658,
@@ -185,6 +188,15 @@ col_sum_partial_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, const _
                        const float* __restrict__ s, const float2* __restrict__ stats, float* __restrict__ partial,
                        int64_t rows, int64_t C, int64_t rows_per_block) {
   __shared__ float sm[(MODE == 2 ? 2 : 1) * kWarps * 256];
+  // blockIdx.z = segment (rows [z * rows, (z + 1) * rows) of the matrices, its own slab of partials): per-sample sums
+  {
+    const int64_t seg = blockIdx.z;
+    a += seg * rows * lda;
+    if (b) b += seg * rows * ldb;
+    if (s) s += seg * rows;
+    if (stats) stats += seg * rows;
+    partial += seg * (int64_t)(MODE == 2 ? 2 : 1) * gridDim.y * C;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t c0 = (int64_t)blockIdx.x * 256 + lane * 8;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
@@ -241,6 +253,9 @@ __global__ void col_sum_finish_kernel(const float* __restrict__ partial, float* 
                                       int64_t C, int ny) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  partial += (int64_t)blockIdx.y * (out1 ? 2 : 1) * ny * C;      // blockIdx.y = segment
+  out0 += (int64_t)blockIdx.y * C;
+  if (out1) out1 += (int64_t)blockIdx.y * C;
   float t = 0.f, t2 = 0.f;
   for (int y = 0; y < ny; ++y) {
     t += partial[(int64_t)y * C + c];
@@ -253,6 +268,35 @@ __global__ void col_sum_finish_kernel(const float* __restrict__ partial, float* 
 int col_sum_ny(int64_t rows) {
   int64_t ny = (rows + 63) / 64;
   return (int)(ny < 1 ? 1 : (ny > 64 ? 64 : ny));
+}
+
+// per-row LayerNorm statistics (mean, rstd) of a bf16 [rows, D] matrix, one warp per row
+__global__ void __launch_bounds__(kWarps * 32)
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, int64_t rows, int D, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  float s = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * D + v * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * D + v * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = f[k] - mean;
+      q = fmaf(d, d, q);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
 // ------------------------------------------------------------------------------------------------ affine LayerNorm bwd
@@ -598,6 +642,37 @@ int advgrpo_layer_norm_affine_bwd(const void* x, const void* weight, const void*
     col_sum_finish_kernel<<<(unsigned)((D + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, dweight, dbias, D, ny);
     ADVGRPO_CUDA_LAUNCH_CHECK();
   }
+  return ADVGRPO_OK;
+}
+
+size_t advgrpo_ln_modulation_grads_workspace_bytes(int64_t nseg, int64_t rows_per_seg, int64_t D) {
+  const int ny = col_sum_ny(rows_per_seg);
+  return (((size_t)(nseg * rows_per_seg) * sizeof(float2) + 255) & ~(size_t)255) + (size_t)nseg * 2 * ny * (size_t)D * sizeof(float) + 256;
+}
+
+int advgrpo_ln_modulation_grads(const void* x, const void* dy, float* dshift, float* dscale, int64_t nseg, int64_t rows_per_seg,
+                                int64_t D, float eps, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(x && dy && dshift && dscale, "ln_modulation_grads: null pointer");
+  ADVGRPO_CHECK_ARG(nseg >= 1 && nseg < 65536 && rows_per_seg >= 1 && D >= 8 && D % 8 == 0,
+                    "ln_modulation_grads: bad sizes nseg=%lld rows_per_seg=%lld D=%lld", (long long)nseg, (long long)rows_per_seg,
+                    (long long)D);
+  ADVGRPO_CHECK_ARG(aligned16(x) && aligned16(dy), "ln_modulation_grads: tensors must be 16-byte aligned");
+  ADVGRPO_CHECK_ARG(workspace && workspace_bytes >= advgrpo_ln_modulation_grads_workspace_bytes(nseg, rows_per_seg, D),
+                    "ln_modulation_grads: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = nseg * rows_per_seg;
+  float2* stats = (float2*)workspace;
+  float* part = (float*)((uint8_t*)workspace + (((size_t)rows * sizeof(float2) + 255) & ~(size_t)255));
+  row_stats_kernel<<<(unsigned)((rows + kWarps - 1) / kWarps), kWarps * 32, 0, st>>>((const __nv_bfloat16*)x, stats, rows, (int)D, eps);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  const int ny = col_sum_ny(rows_per_seg);
+  const int64_t rpb = (rows_per_seg + ny - 1) / ny;
+  dim3 grid((unsigned)((D + 255) / 256), (unsigned)ny, (unsigned)nseg);
+  col_sum_partial_kernel<2><<<grid, kWarps * 32, 0, st>>>((const __nv_bfloat16*)dy, D, (const __nv_bfloat16*)x, D, nullptr, stats, part,
+                                                         rows_per_seg, D, rpb);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  col_sum_finish_kernel<<<dim3((unsigned)((D + 255) / 256), (unsigned)nseg), 256, 0, st>>>(part, dscale, dshift, D, ny);
+  ADVGRPO_CUDA_LAUNCH_CHECK();
   return ADVGRPO_OK;
 }
 

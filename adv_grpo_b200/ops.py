@@ -312,8 +312,8 @@ class _LayerNormAffine(torch.autograd.Function):
 
 class _LnModulateFull(torch.autograd.Function):
     """`ln_modulate` for full fine-tuning: the same forward kernel, and a backward that also returns the gradients of the
-    shift / scale vectors (they come from TRAINABLE adaLN linears there): dx on the native kernel, d shift = sum_t dy,
-    d scale = sum_t dy * xhat as torch reductions over the token axis."""
+    shift / scale vectors (they come from TRAINABLE adaLN linears there): dx on the native kernel, d shift = sum_t dy and
+    d scale = sum_t dy * xhat per sample on the row-statistics + segmented column-sum kernels (csrc/heads.cu)."""
 
     @staticmethod
     def forward(ctx, x, shift, scale, eps):
@@ -334,11 +334,11 @@ class _LnModulateFull(torch.autograd.Function):
         dx = torch.empty_like(x)
         _lib.call("advgrpo_ln_modulate_bwd", _ptr(x), _ptr(scale), None, scale.stride(0), _ptr(dy), None, _ptr(dx), 0, B, S, D,
                   ctx.eps, _stream())
-        dyf = dy.float()
-        dshift = dyf.sum(1).to(torch.bfloat16)
-        xhat = torch.nn.functional.layer_norm(x.float(), (D,), eps=ctx.eps)
-        dscale = (dyf * xhat).sum(1).to(torch.bfloat16)
-        return dx, dshift, dscale, None
+        grads = torch.empty((2, B, D), dtype=torch.float32, device=x.device)          # [d shift | d scale]
+        ws = _workspace("ln_mod_grads", _lib.query("advgrpo_ln_modulation_grads_workspace_bytes", B, S, D), x.device)
+        _lib.call("advgrpo_ln_modulation_grads", _ptr(x), _ptr(dy), _ptr(grads), grads[1].data_ptr(), B, S, D, ctx.eps,
+                  _ptr(ws), ws.numel(), _stream())
+        return dx, grads[0].to(torch.bfloat16), grads[1].to(torch.bfloat16), None
 
 
 def ln_modulate_full(x, shift, scale, eps=1e-6):

@@ -462,6 +462,13 @@ size_t advgrpo_layer_norm_affine_bwd_workspace_bytes(int64_t rows, int64_t D);
 int advgrpo_layer_norm_affine_bwd(const void* x, const void* weight, const void* dy, void* dx, float* dweight, float* dbias,
                                   int64_t rows, int64_t D, float eps, void* workspace, size_t workspace_bytes,
                                   advgrpo_stream_t stream);
+/* Gradients of the adaLN modulation vectors of one LayerNorm-modulate under full fine-tuning (config.use_lora = False,
+ * train_sd3_fast_pickscore.py:488: the adaLN linears train): for each of nseg samples (rows_per_seg tokens each)
+ * dshift[s, :] = sum_t dy[s, t, :] and dscale[s, :] = sum_t dy[s, t, :] * xhat[s, t, :], xhat = LayerNorm(no affine, eps)(x).
+ * x, dy: bf16 [nseg * rows_per_seg, D]; outputs f32 [nseg, D]. */
+size_t advgrpo_ln_modulation_grads_workspace_bytes(int64_t nseg, int64_t rows_per_seg, int64_t D);
+int advgrpo_ln_modulation_grads(const void* x, const void* dy, float* dshift, float* dscale, int64_t nseg, int64_t rows_per_seg,
+                                int64_t D, float eps, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
 /* The discriminator optimizers (`torch.optim.Adam(params, lr=config.d_lr, betas=(0.5, 0.999))`, train_sd3_fast_pickscore.py:658,
  * train_sd3_fast_dino_patch.py:750) as one pass per tensor in torch's multi-tensor op order (lerp_, mul_, addcmul_, sqrt,
  * div_, add_, addcdiv_), rounding to the parameter dtype after every op: bf16 parameters with bf16 moments follow the

@@ -290,3 +290,24 @@ def test_attention_small_rejects_what_does_not_fit(ops):
     q = torch.zeros(1, 4096, 1, 64, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(_lib.AdvGrpoError):
         ops.attention_small(q, q, q)
+
+
+@pytest.mark.parametrize("B,S,D", [(2, 77, 1536), (16, 1024, 1536), (3, 5, 256)])
+def test_ln_modulate_full_grads_match_torch_fp32(ops, B, S, D):
+    """LayerNorm-modulate with gradients to x AND to the per-sample shift / scale vectors (full fine-tuning): native forward,
+    native dx, row-statistics + segmented column sums for d shift / d scale, vs fp32 torch autograd."""
+    g = torch.Generator(device=DEV).manual_seed(B + S)
+    x = (torch.randn(B, S, D, device=DEV, generator=g) * 2 + 0.3).bfloat16()
+    mod = (0.3 * torch.randn(B, 6 * D, device=DEV, generator=g)).bfloat16()
+    dy = torch.randn(B, S, D, device=DEV, generator=g).bfloat16()
+    xg, mg = x.clone().requires_grad_(), mod.clone().requires_grad_()
+    sh, sc = mg[:, D:2 * D], mg[:, 4 * D:5 * D]                          # row views of one [B, 6 D] matrix, like adaLN chunks
+    y = ops.ln_modulate_full(xg, sh, sc)
+    y.backward(dy)
+    xr, mr = x.float().requires_grad_(), mod.float().requires_grad_()
+    yr = torch.nn.functional.layer_norm(xr, (D,), eps=1e-6) * (1 + mr[:, None, 4 * D:5 * D]) + mr[:, None, D:2 * D]
+    yr.backward(dy.float())
+    assert _rel(y, yr) < 5e-3 and _rel(xg.grad, xr.grad) < 6e-3
+    assert _rel(mg.grad[:, D:2 * D], mr.grad[:, D:2 * D]) < 6e-3           # d shift
+    assert _rel(mg.grad[:, 4 * D:5 * D], mr.grad[:, 4 * D:5 * D]) < 6e-3   # d scale
+    assert mg.grad[:, :D].abs().max().item() == 0
