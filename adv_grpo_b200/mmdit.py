@@ -569,15 +569,17 @@ class SD3Transformer2DModel(torch.nn.Module):
         lin = lambda name, v: ops.linear(v, W[name + ".weight"], W.get(name + ".bias"))
         ln_mod = ops.ln_modulate_full                          # native forward / dx; shift / scale gradients by reduction
 
-        def qkv_of(pre, names, v):
+        def qkv_of(pre, names, v, wt):
             """One GEMM for the three projections (their weights concatenated: autograd splits the gradient back)."""
             wcat = torch.cat([W[f"{pre}.{n}.weight"] for n in names], 0)
             bcat = torch.cat([W[f"{pre}.{n}.bias"] for n in names], 0)
-            return ops.linear(v, wcat, bcat)
+            return ops.linear(v, wcat, bcat, wt=wt)
 
-        def attn(pre, xq, cq=None, ctx_out=True):
-            qkv_x = qkv_of(pre, ("to_q", "to_k", "to_v"), xq)
-            qkv_c = None if cq is None else qkv_of(pre, ("add_q_proj", "add_k_proj", "add_v_proj"), cq)
+        def attn(blk, pre, xq, cq=None, ctx_out=True):
+            # wt_*: the blocks' lazily built, in-place refreshed transposes (the dX operands), shared with the fused path
+            two = pre.endswith("attn2")
+            qkv_x = qkv_of(pre, ("to_q", "to_k", "to_v"), xq, blk["wt_qkv2" if two else "wt_qkv"])
+            qkv_c = None if cq is None else qkv_of(pre, ("add_q_proj", "add_k_proj", "add_v_proj"), cq, blk["wt_cqkv"])
             nw = lambda n: W.get(f"{pre}.{n}.weight") if cfg["qk_norm"] else None
             if cfg["qk_norm"]:
                 joint = ops.qk_norm_concat_full(qkv_x, qkv_c, nw("norm_q"), nw("norm_k"),
@@ -587,14 +589,17 @@ class SD3Transformer2DModel(torch.nn.Module):
                 joint = ops.qk_norm_concat(qkv_x, qkv_c, None, None, None, None, H, D)
             o = ops.attention(joint)                                                              # [B, S, H, D]
             o = o.reshape(o.shape[0], o.shape[1], d)
+            lin_t = lambda name, v, key: ops.linear(v, W[name + ".weight"], W.get(name + ".bias"), wt=blk[key])
             if cq is None:
-                return lin(f"{pre}.to_out.0", o), None
+                return lin_t(f"{pre}.to_out.0", o, "wt_out2" if two else "wt_out"), None
             n = xq.shape[1]
-            return lin(f"{pre}.to_out.0", o[:, :n]), (lin(f"{pre}.to_add_out", o[:, n:]) if ctx_out else None)
+            return (lin_t(f"{pre}.to_out.0", o[:, :n], "wt_out"),
+                    lin_t(f"{pre}.to_add_out", o[:, n:], "wt_cout") if ctx_out else None)
 
-        def ff(pre, v):
+        def ff(blk, pre, v):
+            c_ = "c" if pre.endswith("ff_context") else ""
             return ops.mlp_gelu(v, W[f"{pre}.net.0.proj.weight"], W[f"{pre}.net.0.proj.bias"], W[f"{pre}.net.2.weight"],
-                                W[f"{pre}.net.2.bias"], approximate="tanh")
+                                W[f"{pre}.net.2.bias"], approximate="tanh", w1t=blk[f"wt_{c_}ff1"], w2t=blk[f"wt_{c_}ff2"])
 
         gated = lambda res, gate, branch: torch.addcmul(res, gate[:, None], branch)               # res + gate * branch
 
@@ -615,6 +620,7 @@ class SD3Transformer2DModel(torch.nn.Module):
         L = cfg["num_layers"]
         for i in range(L if upto is None else upto):
             pre, last, dual = f"transformer_blocks.{i}", i == L - 1, i in cfg["dual_layers"]
+            blk = self.blocks[i]
             e = lin(f"{pre}.norm1.linear", st)
             if dual:
                 sh, sc, g, sh_m, sc_m, g_m, sh2, sc2, g2 = e.chunk(9, dim=1)
@@ -627,18 +633,18 @@ class SD3Transformer2DModel(torch.nn.Module):
             else:
                 csh, csc, cg, csh_m, csc_m, cg_m = ce.chunk(6, dim=1)
             c1 = ln_mod(c, csh, csc)
-            a, ca = attn(f"{pre}.attn", x1, c1, ctx_out=not last)
+            a, ca = attn(blk, f"{pre}.attn", x1, c1, ctx_out=not last)
             x_in = x
             x = gated(x, g, a)
             if dual:
-                a2, _ = attn(f"{pre}.attn2", ln_mod(x_in, sh2, sc2))
+                a2, _ = attn(blk, f"{pre}.attn2", ln_mod(x_in, sh2, sc2))
                 x = gated(x, g2, a2)
-            x = gated(x, g_m, ff(f"{pre}.ff", ln_mod(x, sh_m, sc_m)))
+            x = gated(x, g_m, ff(blk, f"{pre}.ff", ln_mod(x, sh_m, sc_m)))
             if last:
                 c = None
                 continue
             c = gated(c, cg, ca)
-            c = gated(c, cg_m, ff(f"{pre}.ff_context", ln_mod(c, csh_m, csc_m)))
+            c = gated(c, cg_m, ff(blk, f"{pre}.ff_context", ln_mod(c, csh_m, csc_m)))
         if upto is not None:
             return x, c
         sc, sh = lin("norm_out.linear", st).chunk(2, dim=1)

@@ -651,11 +651,12 @@ class _Linear(torch.autograd.Function):
     dW = dy^T x (`gemm_tn`), db = column sums of dy (`col_sum`)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, wt=None):
         x2 = _bf16c(x).reshape(-1, x.shape[-1])
         w = _w16(weight)
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, weight.dtype, None if bias is None else bias.dtype)
+        ctx.wt = wt                                      # optional callable -> cached contiguous W^T (the dX operand)
         y = gemm(x2, w, bias=None if bias is None else _w16(bias))
         return y.reshape(*x.shape[:-1], w.shape[0])
 
@@ -666,17 +667,18 @@ class _Linear(torch.autograd.Function):
         dy2 = _bf16c(dy).reshape(-1, w.shape[0])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, w.t().contiguous()).reshape(shape)
+            dx = gemm(dy2, ctx.wt() if ctx.wt is not None else w.t().contiguous()).reshape(shape)
         if ctx.needs_input_grad[1]:
             dw = gemm_tn(dy2, x2).to(wdt)
         if bdt is not None and ctx.needs_input_grad[2]:
             db = col_sum(dy2).to(bdt)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x, weight, bias=None):
-    """Differentiable nn.Linear on the native kernels (bf16 compute, fp32 accumulation).  in / out features multiples of 64."""
-    return _Linear.apply(x, weight, bias)
+def linear(x, weight, bias=None, wt=None):
+    """Differentiable nn.Linear on the native kernels (bf16 compute, fp32 accumulation).  in / out features multiples of 64.
+    `wt`: optional callable returning a cached contiguous transpose of the weight for the input-gradient GEMM."""
+    return _Linear.apply(x, weight, bias, wt)
 
 
 class _MlpGelu(torch.autograd.Function):
@@ -684,7 +686,7 @@ class _MlpGelu(torch.autograd.Function):
     epilogue of the fc2 input-gradient GEMM (no elementwise pass, the hidden activation's gradient never exists in HBM)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, tanh):
+    def forward(ctx, x, w1, b1, w2, b2, tanh, w1t=None, w2t=None):
         x2 = _bf16c(x).reshape(-1, x.shape[-1])
         w1h, w2h = _w16(w1), _w16(w2)
         need = any(ctx.needs_input_grad)
@@ -694,6 +696,7 @@ class _MlpGelu(torch.autograd.Function):
         if need:
             ctx.save_for_backward(x2, w1h, w2h, z, a)
         ctx.meta = (x.shape, w1.dtype, b1.dtype, w2.dtype, b2.dtype, bool(tanh))
+        ctx.wts = (w1t, w2t)
         return y.reshape(*x.shape[:-1], w2h.shape[0])
 
     @staticmethod
@@ -701,19 +704,21 @@ class _MlpGelu(torch.autograd.Function):
         x2, w1h, w2h, z, a = ctx.saved_tensors
         shape, w1dt, b1dt, w2dt, b2dt, tanh = ctx.meta
         dy2 = _bf16c(dy).reshape(-1, w2h.shape[0])
-        dz = gemm(dy2, w2h.t().contiguous(), epilogue=EPI_GELU_TANH_GRAD if tanh else EPI_GELU_ERF_GRAD, residual=z)
-        dx = gemm(dz, w1h.t().contiguous()).reshape(shape) if ctx.needs_input_grad[0] else None
+        w1t, w2t = ctx.wts
+        dz = gemm(dy2, w2t() if w2t is not None else w2h.t().contiguous(),
+                  epilogue=EPI_GELU_TANH_GRAD if tanh else EPI_GELU_ERF_GRAD, residual=z)
+        dx = gemm(dz, w1t() if w1t is not None else w1h.t().contiguous()).reshape(shape) if ctx.needs_input_grad[0] else None
         dw1 = gemm_tn(dz, x2).to(w1dt) if ctx.needs_input_grad[1] else None
         db1 = col_sum(dz).to(b1dt) if ctx.needs_input_grad[2] else None
         dw2 = gemm_tn(dy2, a).to(w2dt) if ctx.needs_input_grad[3] else None
         db2 = col_sum(dy2).to(b2dt) if ctx.needs_input_grad[4] else None
-        return dx, dw1, db1, dw2, db2, None
+        return dx, dw1, db1, dw2, db2, None, None, None
 
 
-def mlp_gelu(x, w1, b1, w2, b2, approximate="none"):
+def mlp_gelu(x, w1, b1, w2, b2, approximate="none", w1t=None, w2t=None):
     """fc2(GELU(fc1(x))) with a native forward and backward (all four parameter gradients); approximate = "none" (erf:
-    CLIP / DINOv2) or "tanh" (the MMDiT feed-forward)."""
-    return _MlpGelu.apply(x, w1, b1, w2, b2, approximate == "tanh")
+    CLIP / DINOv2) or "tanh" (the MMDiT feed-forward).  w1t / w2t: optional callables returning cached transposes."""
+    return _MlpGelu.apply(x, w1, b1, w2, b2, approximate == "tanh", w1t, w2t)
 
 
 # --------------------------------------------------------------------------- score heads / discriminator step
