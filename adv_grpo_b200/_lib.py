@@ -99,7 +99,7 @@ class JpegInfo(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("ncomp", ctypes.c_int32),
                 ("h", ctypes.c_int32 * 3), ("v", ctypes.c_int32 * 3), ("tq", ctypes.c_int32 * 3),
                 ("blocks_w", ctypes.c_int32 * 3), ("blocks_h", ctypes.c_int32 * 3),
-                ("restart_interval", ctypes.c_int32), ("supported", ctypes.c_int32)]
+                ("restart_interval", ctypes.c_int32), ("supported", ctypes.c_int32), ("progressive", ctypes.c_int32)]
 
 
 _lib = None

@@ -8,11 +8,14 @@
 //           per pixel, coalesced byte stores.
 // Bit-exact with libjpeg(-turbo)'s default decompression settings (JDCT_ISLOW, do_fancy_upsampling), i.e. with what Pillow
 // returns for the same file: jidctint.c (CONST_BITS 13, PASS1_BITS 2), jdsample.c h2v1 / h2v2_fancy_upsample, jdcolor.c
-// build_ycc_rgb_table.  Files outside the supported subset (progressive, arithmetic, 12-bit, CMYK / RGB colour spaces,
-// non-interleaved scans, chroma factors other than 1x1) are reported as unsupported by advgrpo_jpeg_parse and stay on the
-// caller's host decoder.
+// build_ycc_rgb_table.  Sequential (SOF0 / SOF1) and PROGRESSIVE (SOF2: DC / AC first and refinement scans with end-of-band
+// runs, jdphuff.c) Huffman files; files outside the supported subset (arithmetic, lossless, 12-bit, CMYK / RGB colour spaces,
+// non-interleaved sequential scans, chroma factors other than 1x1) are reported as unsupported by advgrpo_jpeg_parse and stay
+// on the caller's host decoder.
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -33,13 +36,22 @@ struct HuffTable {
   uint16_t fast[512];
 };
 
+struct Scan {
+  int ns;                      // components in the scan
+  int ci[3], td[3], ta[3];     // component index (frame order) and DC / AC table selectors, per scan component
+  int ss, se, ah, al;          // spectral selection and successive approximation (0, 63, 0, 0 for sequential files)
+  int ri;                      // restart interval in force
+  size_t ecs;                  // offset of the entropy-coded segment
+  int dc_idx[4], ac_idx[4];    // Huffman tables in force (indices into Parsed::pool; -1 = undefined)
+};
+
 struct Parsed {
   advgrpo_jpeg_info info;
   uint16_t qt[4][64];          // natural order
   bool qt_present[4];
-  HuffTable dc[4], ac[4];
-  int td[3], ta[3];
-  size_t ecs;                  // offset of the entropy-coded segment
+  std::vector<HuffTable> pool; // every DHT definition met (tables may be redefined between scans)
+  int cur_dc[4], cur_ac[4];
+  std::vector<Scan> scans;
 };
 
 void build_huff(HuffTable& t) {
@@ -70,22 +82,30 @@ void build_huff(HuffTable& t) {
 int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
   memset(&P.info, 0, sizeof(P.info));
   memset(P.qt_present, 0, sizeof(P.qt_present));
-  for (int i = 0; i < 4; ++i) P.dc[i].present = P.ac[i].present = false;
+  for (int i = 0; i < 4; ++i) P.cur_dc[i] = P.cur_ac[i] = -1;
+  P.pool.clear();
+  P.scans.clear();
   if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: not a JPEG file (no SOI)");
   size_t pos = 2;
   bool have_frame = false, saw_jfif = false, saw_adobe = false;
-  int adobe_transform = -1, comp_id[3] = {0, 0, 0};
+  int adobe_transform = -1, comp_id[3] = {0, 0, 0}, ri = 0;
   auto unsupported = [&](const char* why) {
     P.info.supported = 0;
     set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_parse: %s", why);
     return 1;
   };
-  while (pos + 4 <= n) {
-    if (d[pos] != 0xFF) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: marker expected at byte %zu", pos);
+  while (pos + 2 <= n) {
+    if (d[pos] != 0xFF) {                        // entropy-coded bytes of the previous scan: on to the next marker
+      if (P.scans.empty()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: marker expected at byte %zu", pos);
+      ++pos;
+      continue;
+    }
     const uint8_t m = d[pos + 1];
     if (m == 0xFF) { ++pos; continue; }
+    if (m == 0x00 || (m >= 0xD0 && m <= 0xD7)) { pos += 2; continue; }   // stuffed byte / RSTn inside a scan
     pos += 2;
-    if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+    if (m == 0x01) continue;
+    if (m == 0xD9) break;                        // EOI
     if (pos + 2 > n) break;
     const size_t ln = ((size_t)d[pos] << 8) | d[pos + 1];
     if (ln < 2 || pos + ln > n) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: truncated segment");
@@ -101,9 +121,10 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
         P.qt_present[tq] = true;
         i += 65;
       }
-    } else if (m == 0xC0 || m == 0xC1) {
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
       if (sl < 6) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: short SOF");
       if (s[0] != 8) return unsupported("sample precision other than 8 bits");
+      P.info.progressive = m == 0xC2;
       P.info.height = (s[1] << 8) | s[2];
       P.info.width = (s[3] << 8) | s[4];
       P.info.ncomp = s[5];
@@ -117,24 +138,27 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
         P.info.tq[c] = s[8 + 3 * c];
         if (P.info.tq[c] > 3) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad quantisation table id");
       }
+      if (P.info.ncomp == 1) P.info.h[0] = P.info.v[0] = 1;      // a single-component image is never interleaved
       have_frame = true;
-    } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xC7) || (m >= 0xC9 && m <= 0xCB) || (m >= 0xCD && m <= 0xCF)) {
-      return unsupported("progressive / lossless / arithmetic-coded JPEG");
+    } else if (m == 0xC3 || (m >= 0xC5 && m <= 0xC7) || (m >= 0xC9 && m <= 0xCB) || (m >= 0xCD && m <= 0xCF)) {
+      return unsupported("lossless / hierarchical / arithmetic-coded JPEG");
     } else if (m == 0xC4) {
       size_t i = 0;
       while (i + 17 <= sl) {
         const int tc = s[i] >> 4, th = s[i] & 15;
         if (tc > 1 || th > 3) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DHT id");
-        HuffTable& t = tc ? P.ac[th] : P.dc[th];
+        HuffTable t;
         int nsym = 0;
         for (int k = 0; k < 16; ++k) { t.counts[k] = s[i + 1 + k]; nsym += t.counts[k]; }
         if (nsym > 256 || i + 17 + nsym > sl) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DHT");
         memcpy(t.symbols, s + i + 17, nsym);
         build_huff(t);
+        P.pool.push_back(t);
+        (tc ? P.cur_ac : P.cur_dc)[th] = (int)P.pool.size() - 1;
         i += 17 + nsym;
       }
     } else if (m == 0xDD) {
-      if (sl >= 2) P.info.restart_interval = (s[0] << 8) | s[1];
+      if (sl >= 2) ri = (s[0] << 8) | s[1];
     } else if (m == 0xE0 && sl >= 5 && !memcmp(s, "JFIF", 5)) {
       saw_jfif = true;
     } else if (m == 0xEE && sl >= 12 && !memcmp(s, "Adobe", 5)) {
@@ -142,46 +166,66 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
       adobe_transform = s[11];
     } else if (m == 0xDA) {
       if (!have_frame) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: SOS before SOF");
-      if (sl < 1 || s[0] != P.info.ncomp) return unsupported("non-interleaved (multi-scan) file");
-      for (int c = 0; c < P.info.ncomp; ++c) {
+      Scan sc;
+      memset(&sc, 0, sizeof(sc));
+      sc.ns = sl >= 1 ? s[0] : 0;
+      if (sc.ns < 1 || sc.ns > P.info.ncomp || sl < (size_t)(4 + 2 * sc.ns)) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad SOS");
+      if (!P.info.progressive && sc.ns != P.info.ncomp) return unsupported("non-interleaved sequential (multi-scan) file");
+      for (int c = 0; c < sc.ns; ++c) {
         int idx = -1;
         for (int k = 0; k < P.info.ncomp; ++k)
           if (comp_id[k] == s[1 + 2 * c]) idx = k;
         if (idx < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: SOS names an unknown component");
-        P.td[idx] = s[2 + 2 * c] >> 4;
-        P.ta[idx] = s[2 + 2 * c] & 15;
-        if (P.td[idx] > 3 || P.ta[idx] > 3 || !P.dc[P.td[idx]].present || !P.ac[P.ta[idx]].present)
+        sc.ci[c] = idx;
+        sc.td[c] = s[2 + 2 * c] >> 4;
+        sc.ta[c] = s[2 + 2 * c] & 15;
+        if (sc.td[c] > 3 || sc.ta[c] > 3) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad table selector");
+      }
+      sc.ss = s[1 + 2 * sc.ns];
+      sc.se = s[2 + 2 * sc.ns];
+      sc.ah = s[3 + 2 * sc.ns] >> 4;
+      sc.al = s[3 + 2 * sc.ns] & 15;
+      if (!P.info.progressive) { sc.ss = 0; sc.se = 63; sc.ah = sc.al = 0; }
+      if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || (sc.ss == 0 && sc.se != 0 && P.info.progressive) ||
+          (sc.ss > 0 && sc.ns != 1))
+        return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad progressive scan parameters");
+      for (int c = 0; c < sc.ns; ++c) {
+        const bool need_dc = sc.ss == 0 && sc.ah == 0, need_ac = sc.se > 0;
+        if ((need_dc && P.cur_dc[sc.td[c]] < 0) || (need_ac && P.cur_ac[sc.ta[c]] < 0))
           return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: scan refers to a missing Huffman table");
       }
-      P.ecs = pos + ln;
-      // colour space as libjpeg's default_decompress_parms decides it
-      if (P.info.ncomp == 3) {
-        bool ycc = true;
-        if (saw_jfif) ycc = true;
-        else if (saw_adobe) ycc = adobe_transform == 1;
-        else if (comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B') ycc = false;
-        if (!ycc) return unsupported("RGB-coded JPEG (no YCbCr transform)");
-        if (P.info.h[1] != 1 || P.info.v[1] != 1 || P.info.h[2] != 1 || P.info.v[2] != 1)
-          return unsupported("chroma sampling factors other than 1x1");
-        if (!((P.info.h[0] == 1 && P.info.v[0] == 1) || (P.info.h[0] == 2 && P.info.v[0] == 1) || (P.info.h[0] == 2 && P.info.v[0] == 2)))
-          return unsupported("luma sampling other than 1x1, 2x1, 2x2");
-      } else {
-        P.info.h[0] = P.info.v[0] = 1;          // a single-component scan is never interleaved: one block per MCU
-      }
-      for (int c = 0; c < P.info.ncomp; ++c)
-        if (!P.qt_present[P.info.tq[c]]) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: missing quantisation table");
-      const int hmax = P.info.h[0], vmax = P.info.v[0];
-      const int mcux = (P.info.width + 8 * hmax - 1) / (8 * hmax), mcuy = (P.info.height + 8 * vmax - 1) / (8 * vmax);
-      for (int c = 0; c < P.info.ncomp; ++c) {
-        P.info.blocks_w[c] = mcux * P.info.h[c];
-        P.info.blocks_h[c] = mcuy * P.info.v[c];
-      }
-      P.info.supported = 1;
-      return 0;
+      for (int k = 0; k < 4; ++k) { sc.dc_idx[k] = P.cur_dc[k]; sc.ac_idx[k] = P.cur_ac[k]; }
+      sc.ri = ri;
+      sc.ecs = pos + ln;
+      P.scans.push_back(sc);
+      if (!P.info.progressive) break;
     }
     pos += ln;
   }
-  return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: no SOS marker");
+  if (P.scans.empty()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: no SOS marker");
+  // colour space as libjpeg's default_decompress_parms decides it
+  if (P.info.ncomp == 3) {
+    bool ycc = true;
+    if (saw_jfif) ycc = true;
+    else if (saw_adobe) ycc = adobe_transform == 1;
+    else if (comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B') ycc = false;
+    if (!ycc) return unsupported("RGB-coded JPEG (no YCbCr transform)");
+    if (P.info.h[1] != 1 || P.info.v[1] != 1 || P.info.h[2] != 1 || P.info.v[2] != 1)
+      return unsupported("chroma sampling factors other than 1x1");
+    if (!((P.info.h[0] == 1 && P.info.v[0] == 1) || (P.info.h[0] == 2 && P.info.v[0] == 1) || (P.info.h[0] == 2 && P.info.v[0] == 2)))
+      return unsupported("luma sampling other than 1x1, 2x1, 2x2");
+  }
+  for (int c = 0; c < P.info.ncomp; ++c)
+    if (!P.qt_present[P.info.tq[c]]) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: missing quantisation table");
+  const int hmax = P.info.h[0], vmax = P.info.v[0];
+  const int mcux = (P.info.width + 8 * hmax - 1) / (8 * hmax), mcuy = (P.info.height + 8 * vmax - 1) / (8 * vmax);
+  for (int c = 0; c < P.info.ncomp; ++c) {
+    P.info.blocks_w[c] = mcux * P.info.h[c];
+    P.info.blocks_h[c] = mcuy * P.info.v[c];
+  }
+  P.info.restart_interval = P.scans[0].ri;
+  P.info.supported = 1;
+  return 0;
 }
 
 struct BitReader {
@@ -207,6 +251,13 @@ struct BitReader {
   }
   inline uint32_t peek(int k) { return (uint32_t)(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; cnt -= k; }
+  inline int get_bits(int k) {                           // k <= 16
+    if (!k) return 0;
+    if (cnt < k) fill();
+    const int v = (int)peek(k);
+    skip(k);
+    return v;
+  }
   inline int receive_extend(int t) {
     if (!t) return 0;
     if (cnt < t) fill();
@@ -405,6 +456,165 @@ size_t advgrpo_jpeg_coef_count(const advgrpo_jpeg_info* info) {
   return n;
 }
 
+namespace {
+
+// sequential scan: one interleaved pass over the MCUs
+int decode_sequential(const uint8_t* file, size_t nbytes, const Parsed& P, int16_t* coefs, const size_t* off) {
+  const advgrpo_jpeg_info& I = P.info;
+  const Scan& sc = P.scans[0];
+  BitReader br{file, nbytes, sc.ecs, 0, 0, false};
+  int pred[3] = {0, 0, 0};
+  const int mcux = I.blocks_w[0] / I.h[0], mcuy = I.blocks_h[0] / I.v[0];
+  int n = 0;
+  for (int my = 0; my < mcuy; ++my)
+    for (int mx = 0; mx < mcux; ++mx) {
+      if (sc.ri && n && n % sc.ri == 0) {
+        br.restart();
+        pred[0] = pred[1] = pred[2] = 0;
+      }
+      ++n;
+      for (int k = 0; k < sc.ns; ++k) {
+        const int c = sc.ci[k];
+        const HuffTable& dct = P.pool[sc.dc_idx[sc.td[k]]];
+        const HuffTable& act = P.pool[sc.ac_idx[sc.ta[k]]];
+        for (int by = 0; by < I.v[c]; ++by)
+          for (int bx = 0; bx < I.h[c]; ++bx) {
+            int16_t* blk = coefs + off[c] + ((size_t)(my * I.v[c] + by) * I.blocks_w[c] + (mx * I.h[c] + bx)) * 64;
+            const int t = br.decode(dct);
+            if (t < 0 || t > 11) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt DC code");
+            pred[c] += br.receive_extend(t);
+            blk[0] = (int16_t)pred[c];
+            for (int kk = 1; kk < 64;) {
+              const int rs = br.decode(act);
+              if (rs < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code");
+              const int r = rs >> 4, sz = rs & 15;
+              if (sz == 0) {
+                if (r != 15) break;
+                kk += 16;
+                continue;
+              }
+              kk += r;
+              if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+              blk[kZigzag[kk]] = (int16_t)br.receive_extend(sz);
+              ++kk;
+            }
+          }
+      }
+    }
+  return ADVGRPO_OK;
+}
+
+// progressive file (ITU T.81 annex G, libjpeg jdphuff.c): the scans accumulate into the coefficient blocks
+int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int16_t* coefs, const size_t* off) {
+  const advgrpo_jpeg_info& I = P.info;
+  const int hmax = I.h[0], vmax = I.v[0];
+  const int mcux = I.blocks_w[0] / hmax, mcuy = I.blocks_h[0] / vmax;
+  for (const Scan& sc : P.scans) {
+    BitReader br{file, nbytes, sc.ecs, 0, 0, false};
+    int pred[3] = {0, 0, 0};
+    int eobrun = 0;
+    // units: MCUs of an interleaved scan, or the component's own blocks (ceil(w_c / 8) x ceil(h_c / 8)) otherwise
+    int ux_n = mcux, uy_n = mcuy;
+    if (sc.ns == 1) {
+      const int c = sc.ci[0];
+      const int wc = (I.width * I.h[c] + hmax - 1) / hmax, hc = (I.height * I.v[c] + vmax - 1) / vmax;
+      ux_n = (wc + 7) / 8;
+      uy_n = (hc + 7) / 8;
+    }
+    const int p1 = 1 << sc.al, m1 = -(1 << sc.al);
+    int n = 0;
+    for (int uy = 0; uy < uy_n; ++uy)
+      for (int ux = 0; ux < ux_n; ++ux) {
+        if (sc.ri && n && n % sc.ri == 0) {
+          br.restart();
+          pred[0] = pred[1] = pred[2] = 0;
+          eobrun = 0;
+        }
+        ++n;
+        for (int k = 0; k < sc.ns; ++k) {
+          const int c = sc.ci[k];
+          const int nby = sc.ns == 1 ? 1 : I.v[c], nbx = sc.ns == 1 ? 1 : I.h[c];
+          for (int by = 0; by < nby; ++by)
+            for (int bx = 0; bx < nbx; ++bx) {
+              const int brow = sc.ns == 1 ? uy : uy * I.v[c] + by, bcol = sc.ns == 1 ? ux : ux * I.h[c] + bx;
+              int16_t* blk = coefs + off[c] + ((size_t)brow * I.blocks_w[c] + bcol) * 64;
+              if (sc.ss == 0) {                                   // DC scan
+                if (sc.ah == 0) {
+                  const int t = br.decode(P.pool[sc.dc_idx[sc.td[k]]]);
+                  if (t < 0 || t > 11) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt DC code");
+                  pred[c] += br.receive_extend(t);
+                  blk[0] = (int16_t)(pred[c] * (1 << sc.al));
+                } else if (br.get_bits(1)) {
+                  blk[0] = (int16_t)(blk[0] | p1);
+                }
+                continue;
+              }
+              const HuffTable& act = P.pool[sc.ac_idx[sc.ta[k]]];
+              if (sc.ah == 0) {                                   // AC first scan
+                if (eobrun > 0) { --eobrun; continue; }
+                for (int kk = sc.ss; kk <= sc.se;) {
+                  const int rs = br.decode(act);
+                  if (rs < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code");
+                  const int r = rs >> 4, sz = rs & 15;
+                  if (sz) {
+                    kk += r;
+                    if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+                    blk[kZigzag[kk]] = (int16_t)(br.receive_extend(sz) * (1 << sc.al));
+                    ++kk;
+                  } else if (r == 15) {
+                    kk += 16;
+                  } else {
+                    eobrun = (1 << r) + br.get_bits(r) - 1;
+                    break;
+                  }
+                }
+                continue;
+              }
+              // AC refinement scan (jdphuff.c decode_mcu_AC_refine)
+              int kk = sc.ss;
+              if (eobrun == 0) {
+                while (kk <= sc.se) {
+                  const int rs = br.decode(act);
+                  if (rs < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code");
+                  int r = rs >> 4;
+                  const int sz = rs & 15;
+                  int val = 0;
+                  if (sz) {
+                    val = br.get_bits(1) ? p1 : m1;                // the size is always 1 in a refinement scan
+                  } else if (r != 15) {
+                    eobrun = (1 << r) + br.get_bits(r);
+                    break;
+                  }
+                  while (kk <= sc.se) {                            // skip r still-zero coefficients, refining the others
+                    int16_t& co = blk[kZigzag[kk]];
+                    if (co != 0) {
+                      if (br.get_bits(1) && (co & p1) == 0) co = (int16_t)(co + (co >= 0 ? p1 : m1));
+                    } else {
+                      if (r == 0) break;
+                      --r;
+                    }
+                    ++kk;
+                  }
+                  if (val && kk <= sc.se) blk[kZigzag[kk]] = (int16_t)val;
+                  ++kk;
+                }
+              }
+              if (eobrun > 0) {                                    // the rest of the band: correction bits only
+                for (; kk <= sc.se; ++kk) {
+                  int16_t& co = blk[kZigzag[kk]];
+                  if (co != 0 && br.get_bits(1) && (co & p1) == 0) co = (int16_t)(co + (co >= 0 ? p1 : m1));
+                }
+                --eobrun;
+              }
+            }
+        }
+      }
+  }
+  return ADVGRPO_OK;
+}
+
+}  // namespace
+
 int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coefs_host, uint16_t* qtabs_host) {
   ADVGRPO_CHECK_ARG(file && coefs_host && qtabs_host, "jpeg_entropy_decode: null pointer");
   Parsed* P = new Parsed();
@@ -421,45 +631,7 @@ int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coe
     for (int k = 0; k < 64; ++k) qtabs_host[c * 64 + k] = P->qt[I.tq[c]][k];
   }
   memset(coefs_host, 0, total * sizeof(int16_t));
-  BitReader br{file, nbytes, P->ecs, 0, 0, false};
-  int pred[3] = {0, 0, 0};
-  const int mcux = I.blocks_w[0] / I.h[0], mcuy = I.blocks_h[0] / I.v[0];
-  int n = 0;
-  rc = ADVGRPO_OK;
-  for (int my = 0; my < mcuy && rc == ADVGRPO_OK; ++my)
-    for (int mx = 0; mx < mcux && rc == ADVGRPO_OK; ++mx) {
-      if (I.restart_interval && n && n % I.restart_interval == 0) {
-        br.restart();
-        pred[0] = pred[1] = pred[2] = 0;
-      }
-      ++n;
-      for (int c = 0; c < I.ncomp && rc == ADVGRPO_OK; ++c) {
-        const HuffTable& dct = P->dc[P->td[c]];
-        const HuffTable& act = P->ac[P->ta[c]];
-        for (int by = 0; by < I.v[c] && rc == ADVGRPO_OK; ++by)
-          for (int bx = 0; bx < I.h[c]; ++bx) {
-            int16_t* blk = coefs_host + off[c] + ((size_t)(my * I.v[c] + by) * I.blocks_w[c] + (mx * I.h[c] + bx)) * 64;
-            int t = br.decode(dct);
-            if (t < 0 || t > 11) { rc = set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt DC code"); break; }
-            pred[c] += br.receive_extend(t);
-            blk[0] = (int16_t)pred[c];
-            for (int k = 1; k < 64;) {
-              const int rs = br.decode(act);
-              if (rs < 0) { rc = set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code"); break; }
-              const int r = rs >> 4, sz = rs & 15;
-              if (sz == 0) {
-                if (r != 15) break;
-                k += 16;
-                continue;
-              }
-              k += r;
-              if (k > 63) { rc = set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range"); break; }
-              blk[kZigzag[k]] = (int16_t)br.receive_extend(sz);
-              ++k;
-            }
-          }
-      }
-    }
+  rc = I.progressive ? decode_progressive(file, nbytes, *P, coefs_host, off) : decode_sequential(file, nbytes, *P, coefs_host, off);
   delete P;
   return rc;
 }

@@ -1,8 +1,8 @@
-"""Baseline JPEG files -> RGB bytes on the device: the reference opens every reference image with
+"""JPEG files (sequential and progressive Huffman) -> RGB bytes on the device: the reference opens every reference image with
 `Image.open(fpath).convert("RGB")` on the host (`scripts/train_sd3_fast_pickscore.py:773-786`).  Here the file bytes are
 entropy-decoded by the library's own host Huffman decoder (`advgrpo_jpeg_entropy_decode`, plain C++), the coefficient
 blocks go to the GPU, and the inverse DCT, chroma upsampling and colour conversion run there (`csrc/jpeg.cu`), bit-exact
-with libjpeg / Pillow.  Files outside the supported subset (progressive, CMYK, ...) return None: the caller keeps Pillow for
+with libjpeg / Pillow.  Files outside the supported subset (arithmetic-coded, CMYK, ...) return None: the caller keeps Pillow for
 them -- an explicit, per-file host decode, not a silent fallback of a kernel."""
 import ctypes
 

@@ -356,10 +356,11 @@ int advgrpo_pil_resize_bilinear_u8(const uint8_t* img_hwc, int64_t H, int64_t W,
 /* Baseline JPEG decode of the reference images (`Image.open(fpath).convert("RGB")`,
  * scripts/train_sd3_fast_pickscore.py:773-786), hybrid: marker parse + sequential Huffman entropy decode on the HOST (plain C++
  * inside this library), dequantisation + islow integer IDCT + fancy chroma upsampling + YCbCr -> RGB on the DEVICE.
- * Bit-exact with libjpeg(-turbo)'s default settings, i.e. with Pillow, for baseline / extended-sequential 8-bit Huffman
- * files, grayscale or YCbCr with 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, with or without restart intervals.
- * advgrpo_jpeg_parse fills `info` (host call); info->supported == 0 marks a valid file outside that subset (progressive,
- * arithmetic, 12-bit, CMYK / RGB-coded, multi-scan): the caller keeps its host decoder for it -- the return value is still 0.
+ * Bit-exact with libjpeg(-turbo)'s default settings, i.e. with Pillow, for baseline / extended-sequential AND progressive
+ * 8-bit Huffman files, grayscale or YCbCr with 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, with or without restart intervals.
+ * advgrpo_jpeg_parse fills `info` (host call); info->supported == 0 marks a valid file outside that subset (arithmetic,
+ * lossless, 12-bit, CMYK / RGB-coded, multi-scan sequential): the caller keeps its host decoder for it -- the return value is
+ * still 0.
  * advgrpo_jpeg_entropy_decode (host call): coefs_host int16 [advgrpo_jpeg_coef_count(info)] = per component
  * [blocks_h, blocks_w, 64] quantised coefficients in natural order; qtabs_host uint16 [3 * 64] natural-order tables.
  * advgrpo_jpeg_idct_to_rgb: device pointers of the same two arrays -> rgb_hwc_dev uint8 [height, width, 3]. */
@@ -369,6 +370,7 @@ typedef struct {
   int32_t blocks_w[3], blocks_h[3];   /* block grid per component, padded to whole MCUs */
   int32_t restart_interval;
   int32_t supported;
+  int32_t progressive;                /* SOF2: several scans accumulate into the coefficient blocks */
 } advgrpo_jpeg_info;
 int advgrpo_jpeg_parse(const uint8_t* file, size_t nbytes, advgrpo_jpeg_info* info);
 size_t advgrpo_jpeg_coef_count(const advgrpo_jpeg_info* info);

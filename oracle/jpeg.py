@@ -19,21 +19,25 @@ class JpegUnsupported(ValueError):
 
 
 def parse(data):
-    """Marker walk of a baseline (SOF0) or extended-sequential Huffman (SOF1, 8-bit) file.  Returns a dict with the frame
-    geometry, quantisation tables, Huffman tables, restart interval and the offset of the entropy-coded segment."""
+    """Marker walk of a baseline (SOF0), extended-sequential (SOF1) or progressive (SOF2) 8-bit Huffman file.  Returns a dict
+    with the frame geometry, the quantisation tables and, per scan, its component selectors, spectral / successive-
+    approximation parameters, the Huffman tables and restart interval in force, and the offset of its entropy-coded data."""
     if data[:2] != b"\xff\xd8":
         raise JpegUnsupported("not a JPEG (no SOI)")
-    pos, q, huff, frame, ri, adobe_transform = 2, {}, {}, None, 0, None
+    pos, q, huff, frame, ri, adobe_transform, scans, progressive = 2, {}, {}, None, 0, None, [], False
     while pos < len(data):
         if data[pos] != 0xFF:
-            raise JpegUnsupported("marker expected")
+            pos += 1                                    # entropy-coded bytes of the previous scan: skip to the next marker
+            continue
         m = data[pos + 1]
+        if m == 0x00 or m == 0xFF or 0xD0 <= m <= 0xD7:  # stuffed byte / fill / RSTn inside entropy-coded data
+            pos += 1 if m == 0xFF else 2
+            continue
         pos += 2
-        if m == 0xFF:                                   # fill byte
-            pos -= 1
+        if m == 0x01:
             continue
-        if m in (0x01,) or 0xD0 <= m <= 0xD7:
-            continue
+        if m == 0xD9:                                   # EOI
+            break
         ln = (data[pos] << 8) | data[pos + 1]
         seg = data[pos + 2:pos + ln]
         if m == 0xDB:                                   # DQT
@@ -46,14 +50,15 @@ def parse(data):
                 t[ZIGZAG] = np.frombuffer(seg[i + 1:i + 65], dtype=np.uint8)
                 q[tq] = t
                 i += 65
-        elif m in (0xC0, 0xC1):                         # SOF0 / SOF1
+        elif m in (0xC0, 0xC1, 0xC2):                   # SOF0 / SOF1 / SOF2
             if seg[0] != 8:
                 raise JpegUnsupported("sample precision != 8")
+            progressive = m == 0xC2
             h, w, n = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4], seg[5]
             comps = [dict(id=seg[6 + 3 * c], h=seg[7 + 3 * c] >> 4, v=seg[7 + 3 * c] & 15, tq=seg[8 + 3 * c]) for c in range(n)]
             frame = dict(height=h, width=w, comps=comps)
-        elif m in (0xC2, 0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
-            raise JpegUnsupported("progressive / lossless / arithmetic JPEG")
+        elif m in (0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
+            raise JpegUnsupported("lossless / arithmetic / hierarchical JPEG")
         elif m == 0xC4:                                 # DHT
             i = 0
             while i < len(seg):
@@ -68,12 +73,20 @@ def parse(data):
             adobe_transform = seg[11]
         elif m == 0xDA:                                 # SOS
             ns = seg[0]
-            scan = [dict(id=seg[1 + 2 * c], td=seg[2 + 2 * c] >> 4, ta=seg[2 + 2 * c] & 15) for c in range(ns)]
-            if frame is None or ns != len(frame["comps"]):
-                raise JpegUnsupported("non-interleaved multi-scan file")
-            return dict(frame=frame, q=q, huff=huff, ri=ri, scan=scan, ecs=pos + ln, adobe_transform=adobe_transform)
+            sel = [dict(id=seg[1 + 2 * c], td=seg[2 + 2 * c] >> 4, ta=seg[2 + 2 * c] & 15) for c in range(ns)]
+            ss, se, ah, al = seg[1 + 2 * ns], seg[2 + 2 * ns], seg[3 + 2 * ns] >> 4, seg[3 + 2 * ns] & 15
+            if frame is None:
+                raise JpegUnsupported("SOS before SOF")
+            if not progressive and ns != len(frame["comps"]):
+                raise JpegUnsupported("non-interleaved sequential file")
+            scans.append(dict(sel=sel, ss=ss, se=se, ah=ah, al=al, huff=dict(huff), ri=ri, ecs=pos + ln))
+            if not progressive:
+                break
         pos += ln
-    raise JpegUnsupported("no SOS")
+    if not scans:
+        raise JpegUnsupported("no SOS")
+    return dict(frame=frame, q=q, huff=scans[0]["huff"], ri=scans[0]["ri"], scan=scans[0]["sel"], ecs=scans[0]["ecs"],
+                adobe_transform=adobe_transform, progressive=progressive, scans=scans)
 
 
 def _build_decoder(counts, symbols):
@@ -136,6 +149,8 @@ def entropy_decode(data, info):
     hmax, vmax = max(c["h"] for c in comps), max(c["v"] for c in comps)
     mcux, mcuy = -(-fr["width"] // (8 * hmax)), -(-fr["height"] // (8 * vmax))
     out = [np.zeros((mcuy * c["v"], mcux * c["h"], 64), dtype=np.int16) for c in comps]
+    if info.get("progressive"):
+        return _entropy_decode_progressive(data, info, out, mcux, mcuy, hmax, vmax)
     dec = {k: _build_decoder(*v) for k, v in info["huff"].items()}
     sel = {s["id"]: s for s in info["scan"]}
     br = _Bits(data, info["ecs"])
@@ -178,6 +193,114 @@ def entropy_decode(data, info):
                             k += r
                             blk[ZIGZAG[k]] = _extend(br.bits(sz), sz)
                             k += 1
+    return out
+
+
+def _entropy_decode_progressive(data, info, out, mcux, mcuy, hmax, vmax):
+    """ITU T.81 annex G (libjpeg jdphuff.c): DC first / refinement scans (possibly interleaved) and single-component AC
+    first / refinement scans with end-of-band runs; coefficients accumulate over the scans in `out` (natural order)."""
+    fr = info["frame"]
+    comps = fr["comps"]
+    idx_of = {c["id"]: i for i, c in enumerate(comps)}
+    for sc in info["scans"]:
+        dec = {k: _build_decoder(*v) for k, v in sc["huff"].items()}
+        br = _Bits(data, sc["ecs"])
+        ss, se, ah, al = sc["ss"], sc["se"], sc["ah"], sc["al"]
+        cis = [idx_of[s["id"]] for s in sc["sel"]]
+
+        def sym(tbl):
+            code = 0
+            for length in range(1, 17):
+                code = (code << 1) | br.bit()
+                s_ = tbl.get((length, code))
+                if s_ is not None:
+                    return s_
+            raise ValueError("bad Huffman code")
+
+        # the units of the scan: MCUs for an interleaved scan, the component's own blocks (ceil(w_c / 8) x ceil(h_c / 8))
+        # for a single-component scan
+        if len(cis) > 1:
+            units = [(my, mx) for my in range(mcuy) for mx in range(mcux)]
+        else:
+            c = comps[cis[0]]
+            wc = -(-(fr["width"] * c["h"]) // hmax)
+            hc = -(-(fr["height"] * c["v"]) // vmax)
+            units = [(by, bx) for by in range(-(-hc // 8)) for bx in range(-(-wc // 8))]
+        pred = [0] * len(comps)
+        eobrun = 0
+        for n, (uy, ux) in enumerate(units):
+            if sc["ri"] and n and n % sc["ri"] == 0:
+                br.restart()
+                pred = [0] * len(comps)
+                eobrun = 0
+            if len(cis) > 1:
+                blocks = [(ci, uy * comps[ci]["v"] + by, ux * comps[ci]["h"] + bx) for ci in cis
+                          for by in range(comps[ci]["v"]) for bx in range(comps[ci]["h"])]
+            else:
+                blocks = [(cis[0], uy, ux)]
+            for ci, by, bx in blocks:
+                blk = out[ci][by, bx]
+                sel = next(s for s in sc["sel"] if idx_of[s["id"]] == ci)
+                if ss == 0:                                       # DC scan
+                    if ah == 0:
+                        t = sym(dec[(0, sel["td"])])
+                        pred[ci] += _extend(br.bits(t), t)
+                        blk[0] = pred[ci] * (1 << al)
+                    elif br.bit():
+                        blk[0] |= (1 << al)
+                    continue
+                act = dec[(1, sel["ta"])]
+                if ah == 0:                                       # AC first scan
+                    if eobrun > 0:
+                        eobrun -= 1
+                        continue
+                    k = ss
+                    while k <= se:
+                        rs = sym(act)
+                        r, sz = rs >> 4, rs & 15
+                        if sz:
+                            k += r
+                            blk[ZIGZAG[k]] = _extend(br.bits(sz), sz) * (1 << al)
+                            k += 1
+                        elif r == 15:
+                            k += 16
+                        else:
+                            eobrun = (1 << r) + (br.bits(r) if r else 0) - 1
+                            break
+                    continue
+                # AC refinement scan (jdphuff.c decode_mcu_AC_refine)
+                p1, m1 = 1 << al, -(1 << al)
+                k = ss
+                if eobrun == 0:
+                    while k <= se:
+                        rs = sym(act)
+                        r, sz = rs >> 4, rs & 15
+                        val = 0
+                        if sz:
+                            val = p1 if br.bit() else m1          # size is always 1 here
+                        elif r != 15:
+                            eobrun = (1 << r) + (br.bits(r) if r else 0)
+                            break
+                        while k <= se:                             # skip r zero-history coefficients, refining the others
+                            z = ZIGZAG[k]
+                            if blk[z] != 0:
+                                if br.bit() and (blk[z] & p1) == 0:
+                                    blk[z] += p1 if blk[z] >= 0 else m1
+                            else:
+                                if r == 0:
+                                    break
+                                r -= 1
+                            k += 1
+                        if val and k <= se:
+                            blk[ZIGZAG[k]] = val
+                        k += 1
+                if eobrun > 0:                                     # the rest of the band: only correction bits
+                    while k <= se:
+                        z = ZIGZAG[k]
+                        if blk[z] != 0 and br.bit() and (blk[z] & p1) == 0:
+                            blk[z] += p1 if blk[z] >= 0 else m1
+                        k += 1
+                    eobrun -= 1
     return out
 
 

@@ -14,3 +14,11 @@ def _jpeg_bytes(h, w, seed=0, gray=False, **kw):
     buf = io.BytesIO()
     Image.fromarray(img[..., 0] if gray else img).save(buf, format="JPEG", **kw)
     return buf.getvalue()
+
+
+def _cmyk_jpeg():
+    """A 4-component (CMYK) JPEG: valid, but outside the decoder's subset."""
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(np.full((16, 16, 4), 100, dtype=np.uint8), mode="CMYK").save(buf, format="JPEG")
+    return buf.getvalue()

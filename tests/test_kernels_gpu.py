@@ -636,7 +636,10 @@ def test_reference_image_index_gpu_path_equals_pil_path(tmp_path):
                                     (333, 517, dict(quality=75, subsampling=1)), (600, 401, dict(quality=95, subsampling=0)),
                                     (480, 640, dict(quality=60, subsampling=2, restart_marker_blocks=4)),
                                     (257, 129, dict(quality=80, gray=True)), (1, 1, dict(quality=90, subsampling=2)),
-                                    (17, 9, dict(quality=100, subsampling=2))])
+                                    (17, 9, dict(quality=100, subsampling=2)),
+                                    (512, 768, dict(quality=85, subsampling=2, progressive=True)),
+                                    (301, 203, dict(quality=92, subsampling=1, progressive=True)),
+                                    (480, 640, dict(quality=70, subsampling=0, progressive=True, restart_marker_blocks=8))])
 def test_jpeg_decode_bit_exact_with_pillow(h, w, kw):
     """`Image.open(path).convert("RGB")` (train_sd3_fast_pickscore.py:779) on the device: every byte equals Pillow's decode."""
     import io
@@ -648,4 +651,5 @@ def test_jpeg_decode_bit_exact_with_pillow(h, w, kw):
     got = jpeg_b.decode_jpeg_to_device(data, DEV)
     assert got.dtype == torch.uint8 and got.shape == (h, w, 3)
     assert torch.equal(got.cpu(), torch.from_numpy(ref.copy()))
-    assert jpeg_b.decode_jpeg_to_device(_jpeg_bytes(32, 32, progressive=True), DEV) is None
+    from jpeg_util import _cmyk_jpeg
+    assert jpeg_b.decode_jpeg_to_device(_cmyk_jpeg(), DEV) is None

@@ -338,20 +338,24 @@ def test_mmdit_adaln_chunk_orders_match_transformers_dit_modules():
     assert not torch.allclose(ref_f, swapped, atol=1e-3)         # the order matters: (shift, scale) would be caught
 
 
-from jpeg_util import _jpeg_bytes  # noqa: E402
+from jpeg_util import _cmyk_jpeg, _jpeg_bytes  # noqa: E402
 
 
 JPEG_CASES = [((64, 64), dict(quality=90, subsampling=0)), ((48, 80), dict(quality=75, subsampling=2)),
               ((37, 53), dict(quality=85, subsampling=2)), ((33, 47), dict(quality=60, subsampling=1)),
               ((17, 9), dict(quality=80, subsampling=2)), ((40, 40), dict(quality=50, subsampling=2, restart_marker_blocks=2)),
               ((1, 1), dict(quality=90, subsampling=2)), ((8, 2), dict(quality=90, subsampling=1)),
-              ((24, 40), dict(quality=100, subsampling=0)), ((30, 45), dict(quality=80, gray=True))]
+              ((24, 40), dict(quality=100, subsampling=0)), ((30, 45), dict(quality=80, gray=True)),
+              # progressive (SOF2): DC / AC first + refinement scans, end-of-band runs
+              ((48, 80), dict(quality=75, subsampling=2, progressive=True)), ((33, 47), dict(quality=60, subsampling=1, progressive=True)),
+              ((37, 53), dict(quality=95, subsampling=0, progressive=True)), ((30, 45), dict(quality=80, gray=True, progressive=True)),
+              ((40, 40), dict(quality=50, subsampling=2, progressive=True, restart_marker_blocks=2))]
 
 
 def test_jpeg_oracle_matches_pillow():
     """oracle/jpeg.py (numpy restatement of libjpeg's default baseline decode: Huffman, islow IDCT, fancy upsampling, YCbCr
     tables) returns exactly Pillow's pixels -- the pin of the oracle the GPU decoder is tested against -- for 4:4:4, 4:2:2,
-    4:2:0, grayscale, odd sizes down to 1x1 and restart intervals; progressive files are reported unsupported."""
+    4:2:0, grayscale, odd sizes down to 1x1, restart intervals, sequential and progressive files; CMYK is reported unsupported."""
     import io
     import pytest
     from PIL import Image
@@ -361,7 +365,7 @@ def test_jpeg_oracle_matches_pillow():
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         assert np.array_equal(jpeg_o.decode_rgb(data), ref), ((h, w), kw)
     with pytest.raises(jpeg_o.JpegUnsupported):
-        jpeg_o.decode_rgb(_jpeg_bytes(16, 16, progressive=True))
+        jpeg_o.decode_rgb(_cmyk_jpeg())
 
 
 def test_jpeg_host_entropy_decoder_matches_oracle():
@@ -378,8 +382,9 @@ def test_jpeg_host_entropy_decoder_matches_oracle():
         for c in range(gi.ncomp):
             assert np.array_equal(got[c], ref[c]), ((h, w), kw, c)
             assert np.array_equal(qt[c], info["q"][info["frame"]["comps"][c]["tq"]])
-    assert jpeg_b.jpeg_info(_jpeg_bytes(16, 16, progressive=True)).supported == 0
-    assert jpeg_b.coefficients_as_numpy(_jpeg_bytes(16, 16, progressive=True))[0] is None
+    assert jpeg_b.jpeg_info(_jpeg_bytes(16, 16, progressive=True)).progressive == 1
+    assert jpeg_b.jpeg_info(_cmyk_jpeg()).supported == 0
+    assert jpeg_b.coefficients_as_numpy(_cmyk_jpeg())[0] is None
     import pytest
     from adv_grpo_b200 import _lib
     with pytest.raises(_lib.AdvGrpoError):
