@@ -385,12 +385,14 @@ struct ColorArgs {
   const uint8_t* cr;
   int ys, cs;              // row strides of the luma / chroma planes
   int W, H, wd, hd;        // image size, valid chroma size (ceil(W / 2), ceil(H / 2) where subsampled)
-  int mode;                // 0 = gray, 1 = 4:4:4, 2 = h2v1 fancy, 3 = h2v2 fancy
+  int mode;                // 0 = gray, 1 = 4:4:4, 2 = h2v1 fancy, 3 = h2v2 fancy, 4 = h2v1 replicate, 5 = h2v2 replicate
 };
 
 __device__ __forceinline__ int chroma_at(const uint8_t* c, int cs, int x, int y, const ColorArgs& a) {
   if (a.mode == 1) return c[(int64_t)y * cs + x];
   const int cx = x >> 1;
+  if (a.mode == 4) return c[(int64_t)y * cs + cx];            // jdsample.c h2v1_upsample / h2v2_upsample: plain replication
+  if (a.mode == 5) return c[(int64_t)(y >> 1) * cs + cx];
   if (a.mode == 2) {                                          // jdsample.c h2v1_fancy_upsample
     const int p = c[(int64_t)y * cs + cx];
     if (x & 1) return x == 2 * a.wd - 1 ? p : (3 * p + c[(int64_t)y * cs + cx + 1] + 2) >> 2;
@@ -674,6 +676,7 @@ int advgrpo_jpeg_idct_to_rgb(const int16_t* coefs_dev, const uint16_t* qtabs_dev
   a.mode = info->ncomp == 1 ? 0 : (info->h[0] == 1 ? 1 : (info->v[0] == 1 ? 2 : 3));
   a.wd = a.mode >= 2 ? (info->width + 1) / 2 : info->width;
   a.hd = a.mode == 3 ? (info->height + 1) / 2 : info->height;
+  if (a.mode >= 2 && a.wd <= 2) a.mode += 2;   // jinit_upsampler: the fancy (triangle) filters only when downsampled_width > 2
   const int64_t npx = (int64_t)a.W * a.H;
   jpeg_color_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(a, rgb_hwc_dev);
   ADVGRPO_CUDA_LAUNCH_CHECK();

@@ -1,4 +1,4 @@
-"""Oracle (test infrastructure only): baseline JPEG decode restated in numpy, bit for bit what libjpeg(-turbo) -- i.e.
+"""Oracle (test infrastructure only): JPEG decode (sequential and progressive Huffman) restated in numpy, bit for bit what libjpeg(-turbo) -- i.e.
 Pillow's `Image.open(path).convert("RGB")` at `scripts/train_sd3_fast_pickscore.py:779` -- produces with its default
 settings: sequential Huffman entropy decoding (ITU T.81 F.2.2), dequantisation + the "islow" integer inverse DCT
 (jidctint.c: 13-bit constants, 2 extra bits after the column pass), "fancy" triangle chroma upsampling for 4:2:0 / 4:2:2
@@ -363,10 +363,9 @@ def _planes(info, coefs):
 def _h2v1_fancy(p, w_down):
     """jdsample.c h2v1_fancy_upsample on rows of width w_down -> 2 w_down"""
     p = p[:, :w_down].astype(np.int32)
+    if w_down <= 2:                                       # jinit_upsampler: fancy only when downsampled_width > 2
+        return np.repeat(p, 2, axis=1)
     out = np.zeros((p.shape[0], 2 * w_down), dtype=np.int32)
-    if w_down == 1:
-        out[:, 0] = out[:, 1] = p[:, 0]
-        return out
     left = np.concatenate([p[:, :1], p[:, :-1]], axis=1)
     right = np.concatenate([p[:, 1:], p[:, -1:]], axis=1)
     out[:, 0::2] = (3 * p + left + 1) >> 2
@@ -380,21 +379,20 @@ def _h2v2_fancy(p, w_down, h_down):
     """jdsample.c h2v2_fancy_upsample: vertical 3:1 blend with the nearer neighbouring row (edge rows replicated by the
     main controller's context handling), then the horizontal triangle with the 8 / 7 rounding pair."""
     p = p[:h_down, :w_down].astype(np.int32)
+    if w_down <= 2:                                       # jinit_upsampler: plain 2x2 replication for very narrow planes
+        return np.repeat(np.repeat(p, 2, axis=0), 2, axis=1)
     up = np.concatenate([p[:1], p[:-1]], axis=0)
     dn = np.concatenate([p[1:], p[-1:]], axis=0)
     out = np.zeros((2 * h_down, 2 * w_down), dtype=np.int32)
     for v, other in ((0, up), (1, dn)):
         s = 3 * p + other                                        # "colsum" of every column
-        if w_down == 1:
-            o = np.stack([(s[:, 0] * 4 + 8) >> 4, (s[:, 0] * 4 + 7) >> 4], axis=1)
-        else:
-            o = np.zeros((h_down, 2 * w_down), dtype=np.int32)
-            last = np.concatenate([s[:, :1], s[:, :-1]], axis=1)
-            nxt = np.concatenate([s[:, 1:], s[:, -1:]], axis=1)
-            o[:, 0::2] = (3 * s + last + 8) >> 4
-            o[:, 1::2] = (3 * s + nxt + 7) >> 4
-            o[:, 0] = (s[:, 0] * 4 + 8) >> 4
-            o[:, -1] = (s[:, -1] * 4 + 7) >> 4
+        o = np.zeros((h_down, 2 * w_down), dtype=np.int32)
+        last = np.concatenate([s[:, :1], s[:, :-1]], axis=1)
+        nxt = np.concatenate([s[:, 1:], s[:, -1:]], axis=1)
+        o[:, 0::2] = (3 * s + last + 8) >> 4
+        o[:, 1::2] = (3 * s + nxt + 7) >> 4
+        o[:, 0] = (s[:, 0] * 4 + 8) >> 4
+        o[:, -1] = (s[:, -1] * 4 + 7) >> 4
         out[v::2] = o
     return out
 
@@ -412,12 +410,12 @@ def ycc_to_rgb(y, cb, cr):
     return np.clip(np.stack([r, g, b], axis=-1), 0, 255).astype(np.uint8)
 
 
-def decode_rgb(data):
-    """bytes of a baseline JPEG -> uint8 [H, W, 3], equal to np.asarray(Image.open(...).convert("RGB"))."""
-    info = parse(data)
+def assemble_rgb(info, coefs):
+    """Back end shared by `decode_rgb` and the tests of the library's host entropy decoder: per-component coefficient
+    blocks -> uint8 [H, W, 3]."""
     fr = info["frame"]
     H, W, comps = fr["height"], fr["width"], fr["comps"]
-    planes = _planes(info, entropy_decode(data, info))
+    planes = _planes(info, coefs)
     if len(comps) == 1:
         g = planes[0][:H, :W]
         return np.stack([g, g, g], axis=-1)
@@ -438,3 +436,12 @@ def decode_rgb(data):
     else:
         raise JpegUnsupported(f"luma sampling {hs[0]}x{vs[0]}")
     return ycc_to_rgb(y, cb, cr)
+
+
+def decode_rgb(data):
+    """bytes of a sequential or progressive Huffman JPEG -> uint8 [H, W, 3], equal to
+    np.asarray(Image.open(...).convert("RGB"))."""
+    info = parse(data)
+    if len(info["frame"]["comps"]) not in (1, 3):
+        raise JpegUnsupported("component count other than 1 or 3")
+    return assemble_rgb(info, entropy_decode(data, info))

@@ -639,7 +639,10 @@ def test_reference_image_index_gpu_path_equals_pil_path(tmp_path):
                                     (17, 9, dict(quality=100, subsampling=2)),
                                     (512, 768, dict(quality=85, subsampling=2, progressive=True)),
                                     (301, 203, dict(quality=92, subsampling=1, progressive=True)),
-                                    (480, 640, dict(quality=70, subsampling=0, progressive=True, restart_marker_blocks=8))])
+                                    (480, 640, dict(quality=70, subsampling=0, progressive=True, restart_marker_blocks=8)),
+                                    # narrow planes: libjpeg replicates instead of the triangle filter when ceil(W / 2) <= 2
+                                    (47, 3, dict(quality=100, subsampling=2)), (16, 4, dict(quality=90, subsampling=1)),
+                                    (30, 2, dict(quality=80, subsampling=2, progressive=True)), (9, 5, dict(quality=90, subsampling=2))])
 def test_jpeg_decode_bit_exact_with_pillow(h, w, kw):
     """`Image.open(path).convert("RGB")` (train_sd3_fast_pickscore.py:779) on the device: every byte equals Pillow's decode."""
     import io

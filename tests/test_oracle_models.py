@@ -349,7 +349,9 @@ JPEG_CASES = [((64, 64), dict(quality=90, subsampling=0)), ((48, 80), dict(quali
               # progressive (SOF2): DC / AC first + refinement scans, end-of-band runs
               ((48, 80), dict(quality=75, subsampling=2, progressive=True)), ((33, 47), dict(quality=60, subsampling=1, progressive=True)),
               ((37, 53), dict(quality=95, subsampling=0, progressive=True)), ((30, 45), dict(quality=80, gray=True, progressive=True)),
-              ((40, 40), dict(quality=50, subsampling=2, progressive=True, restart_marker_blocks=2))]
+              ((40, 40), dict(quality=50, subsampling=2, progressive=True, restart_marker_blocks=2)),
+              # narrow planes: plain replication instead of the triangle filter when ceil(W / 2) <= 2 (jinit_upsampler)
+              ((47, 3), dict(quality=100, subsampling=2)), ((16, 4), dict(quality=90, subsampling=1)), ((9, 5), dict(quality=90, subsampling=2))]
 
 
 def test_jpeg_oracle_matches_pillow():
@@ -389,3 +391,39 @@ def test_jpeg_host_entropy_decoder_matches_oracle():
     from adv_grpo_b200 import _lib
     with pytest.raises(_lib.AdvGrpoError):
         jpeg_b.jpeg_info(b"not a jpeg at all")
+
+
+def test_jpeg_host_decoder_fuzz_against_pillow():
+    """Randomised files (noise / flat / patterned content, quality 1..100, every sampling mode, sequential and progressive,
+    restart intervals, optimised Huffman tables): the library's host entropy decoder + the oracle's numpy back end (the
+    arithmetic the GPU kernels implement) reproduce Pillow's pixels exactly."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import jpeg as jpeg_b
+    from oracle import jpeg as jpeg_o
+    rng = np.random.default_rng(123)
+    for _ in range(24):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == 1:
+            img = np.full((h, w, 3), int(rng.integers(0, 256)), dtype=np.uint8)
+        else:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([(xx * 3 + yy) % 256, (yy * 5) % 256, (xx * yy) % 256], -1).astype(np.uint8)
+        kw = dict(quality=int(rng.choice([1, 10, 35, 75, 90, 100])), subsampling=int(rng.integers(0, 3)),
+                  progressive=bool(rng.integers(0, 2)))
+        if rng.integers(0, 3) == 0:
+            kw["restart_marker_blocks"] = int(rng.integers(1, 5))
+        if rng.integers(0, 4) == 0:
+            kw["optimize"] = True
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format="JPEG", **kw)
+        data = buf.getvalue()
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        coefs, _, info = jpeg_b.coefficients_as_numpy(data)
+        assert coefs is not None and (info.height, info.width) == (h, w), kw
+        oinfo = jpeg_o.parse(data)
+        got = jpeg_o.assemble_rgb(oinfo, coefs)
+        assert np.array_equal(got, ref), ((h, w), kw)
