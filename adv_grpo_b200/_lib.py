@@ -61,6 +61,11 @@ SIGNATURES = {
     "advgrpo_jpeg_entropy_decode": (c_int, [_P, _SZ, _P, _P]),
     "advgrpo_jpeg_workspace_bytes": (_SZ, [_P]),
     "advgrpo_jpeg_idct_to_rgb": (c_int, [_P, _P, _P, _P, _P, _SZ, _P]),
+    "advgrpo_png_parse": (c_int, [_P, _SZ, _P]),
+    "advgrpo_png_raw_bytes": (_SZ, [_P]),
+    "advgrpo_png_inflate": (c_int, [_P, _SZ, _P, _P]),
+    "advgrpo_png_workspace_bytes": (_SZ, [_P]),
+    "advgrpo_png_unfilter_to_rgb": (c_int, [_P, _P, _P, _P, _P, _SZ, _P]),
     "advgrpo_pil_resize_bilinear_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
     "advgrpo_pil_resize_bilinear_u8": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "advgrpo_group_norm_workspace_bytes": (_SZ, [_I64, _I64]),
@@ -102,6 +107,12 @@ class JpegInfo(ctypes.Structure):
                 ("restart_interval", ctypes.c_int32), ("supported", ctypes.c_int32), ("progressive", ctypes.c_int32)]
 
 
+class PngInfo(ctypes.Structure):
+    """`advgrpo_png_info` of include/advgrpo_b200.h."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("width", "height", "bit_depth", "color_type", "interlace", "channels", "rowbytes",
+                                              "palette_entries", "supported")]
+
+
 _lib = None
 
 
@@ -131,7 +142,7 @@ def load():
 # kernels launched per successful entry-point call (bench.py's `gpu_launches` claim)
 _KERNELS_PER_CALL = {"advgrpo_group_norm_silu_nhwc": 2, "advgrpo_attn_bwd": 3, "advgrpo_clip_preprocess": 3, "advgrpo_group_advantage": 2, "advgrpo_group_advantage_mode": 2, "advgrpo_clip_adamw": 2,
                      "advgrpo_col_sum": 2, "advgrpo_layer_norm_affine_bwd": 3, "advgrpo_attn_small_bwd": 2, "advgrpo_ln_modulation_grads": 3, "advgrpo_pil_resize_bilinear_u8": 4, "advgrpo_jpeg_parse": 0, "advgrpo_jpeg_entropy_decode": 0,
-                     "advgrpo_jpeg_idct_to_rgb": 4, "advgrpo_device_check": 0}
+                     "advgrpo_jpeg_idct_to_rgb": 4, "advgrpo_png_parse": 0, "advgrpo_png_inflate": 0, "advgrpo_png_unfilter_to_rgb": 2, "advgrpo_device_check": 0}
 _launches = [0]
 
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libadvgrpo_b200.so")
 SOURCES = ["core.cu", "sde_step.cu", "advantage.cu", "norm.cu", "preprocess.cu", "attn_fwd.cu",
-           "attn_bwd.cu", "gemm.cu", "gemm_tn.cu", "groupnorm.cu", "conv.cu", "optim.cu", "heads.cu", "attn_small.cu", "jpeg.cu"]
+           "attn_bwd.cu", "gemm.cu", "gemm_tn.cu", "groupnorm.cu", "conv.cu", "optim.cu", "heads.cu", "attn_small.cu", "jpeg.cu", "png.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

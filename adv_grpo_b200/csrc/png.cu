@@ -1,0 +1,391 @@
+// PNG decode of the reference ("real") images (the reference images of the adversarial loop ARE PNG
+// files -- README.md:114-128 of the reference -- opened with `Image.open(fpath).convert("RGB")`,
+// scripts/train_sd3_fast_pickscore.py:773-786), hybrid:
+//   host  : chunk walk (IHDR / PLTE / IDAT / IEND) and zlib INFLATE of the concatenated IDAT stream (RFC 1950 / 1951: stored,
+//           fixed and dynamic Huffman blocks, LZ77 window copies) -- a serial bit-stream problem, plain C++ in this library,
+//           no zlib / libpng;
+//   device: scan-line UNFILTERING (PNG 1.2 section 6: None / Sub / Up / Average / Paeth).  A reconstructed byte depends on its
+//           left, upper and upper-left neighbours, so rows cannot be processed independently; the kernel runs an anti-diagonal
+//           WAVEFRONT: thread r owns row r of a band of up to 1024 rows and at step t reconstructs pixel t - r; the pixel above
+//           arrives from the neighbouring thread through shared memory (double-buffered by step parity), left / upper-left
+//           stay in registers; W + rows - 1 steps of one barrier each.  Then conversion to interleaved RGB bytes (truecolour:
+//           in place; alpha dropped; greyscale replicated; palette looked up), as Pillow's convert("RGB") does.
+// Non-interlaced 8-bit files of every colour type; other files (Adam7, 1/2/4/16-bit) are reported unsupported by
+// advgrpo_png_parse and stay on the caller's host decoder.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace advgrpo {
+namespace {
+
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+int png_channels(int ct) { return ct == 0 ? 1 : ct == 2 ? 3 : ct == 3 ? 1 : ct == 4 ? 2 : ct == 6 ? 4 : 0; }
+
+struct PngParsed {
+  advgrpo_png_info info;
+  std::vector<std::pair<size_t, size_t>> idat;   // (offset, length) of every IDAT body
+  uint8_t palette[768];
+};
+
+// 0 ok, negative error; info.supported says whether this decoder takes the file
+int parse_png(const uint8_t* d, size_t n, PngParsed& P) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  memset(&P.info, 0, sizeof(P.info));
+  memset(P.palette, 0, sizeof(P.palette));
+  P.idat.clear();
+  if (n < 8 || memcmp(d, sig, 8)) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: not a PNG file");
+  size_t pos = 8;
+  bool have_ihdr = false, have_plte = false;
+  while (pos + 12 <= n) {
+    const size_t ln = be32(d + pos);
+    const uint8_t* typ = d + pos + 4;
+    if (pos + 12 + ln > n) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: truncated chunk");
+    const uint8_t* body = d + pos + 8;
+    if (!memcmp(typ, "IHDR", 4)) {
+      if (ln < 13) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: short IHDR");
+      P.info.width = (int32_t)be32(body);
+      P.info.height = (int32_t)be32(body + 4);
+      P.info.bit_depth = body[8];
+      P.info.color_type = body[9];
+      P.info.interlace = body[12];
+      have_ihdr = true;
+    } else if (!memcmp(typ, "PLTE", 4)) {
+      const size_t k = ln < 768 ? ln : 768;
+      memcpy(P.palette, body, k);
+      P.info.palette_entries = (int32_t)(k / 3);
+      have_plte = true;
+    } else if (!memcmp(typ, "IDAT", 4)) {
+      P.idat.push_back({pos + 8, ln});
+    } else if (!memcmp(typ, "IEND", 4)) {
+      break;
+    }
+    pos += 12 + ln;
+  }
+  if (!have_ihdr || P.idat.empty()) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: missing IHDR or IDAT");
+  if (P.info.width < 1 || P.info.height < 1 || P.info.width > (1 << 15) || P.info.height > (1 << 15))
+    return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad image size");
+  P.info.channels = png_channels(P.info.color_type);
+  if (!P.info.channels) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad colour type");
+  P.info.rowbytes = P.info.width * P.info.channels;
+  P.info.supported = P.info.bit_depth == 8 && P.info.interlace == 0 && (P.info.color_type != 3 || have_plte);
+  return ADVGRPO_OK;
+}
+
+// ---- inflate (RFC 1951), LSB-first bit reader over the concatenated IDAT bodies -------------------------------------------
+struct InBits {
+  const uint8_t* d;
+  const std::vector<std::pair<size_t, size_t>>* segs;
+  size_t seg, off;
+  uint64_t acc;
+  int cnt;
+  bool eof;
+  int next_byte() {
+    while (seg < segs->size() && off >= (*segs)[seg].second) { ++seg; off = 0; }
+    if (seg >= segs->size()) { eof = true; return 0; }
+    return d[(*segs)[seg].first + off++];
+  }
+  inline void need(int k) {
+    while (cnt < k) { acc |= (uint64_t)next_byte() << cnt; cnt += 8; }
+  }
+  inline uint32_t bits(int k) {
+    if (!k) return 0;
+    need(k);
+    const uint32_t v = (uint32_t)(acc & ((1ull << k) - 1));
+    acc >>= k;
+    cnt -= k;
+    return v;
+  }
+  inline void align_byte() { const int r = cnt & 7; acc >>= r; cnt -= r; }
+};
+
+struct HuffDec {
+  uint16_t count[16], symbol[288];
+  uint16_t fast[1024];      // index = next 10 bits (LSB first); (length << 9) | symbol, 0 = longer / invalid
+  bool build(const uint8_t* lengths, int n) {
+    memset(count, 0, sizeof(count));
+    for (int i = 0; i < n; ++i) count[lengths[i]]++;
+    if (count[0] == n) { memset(fast, 0, sizeof(fast)); return true; }          // no codes (allowed for distances)
+    int left = 1;
+    for (int l = 1; l < 16; ++l) {
+      left <<= 1;
+      left -= count[l];
+      if (left < 0) return false;                                              // over-subscribed
+    }
+    uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
+    for (int i = 0; i < n; ++i)
+      if (lengths[i]) symbol[offs[lengths[i]]++] = (uint16_t)i;
+    // fast table: canonical codes, bit-reversed (deflate packs Huffman codes starting from their most significant bit)
+    memset(fast, 0, sizeof(fast));
+    int code = 0, idx = 0;
+    for (int l = 1; l <= 10; ++l) {
+      for (int i = 0; i < count[l]; ++i, ++code, ++idx) {
+        int rev = 0;
+        for (int b = 0; b < l; ++b) rev |= ((code >> b) & 1) << (l - 1 - b);
+        for (int f = rev; f < 1024; f += 1 << l) fast[f] = (uint16_t)((l << 9) | symbol[idx]);
+      }
+      code <<= 1;
+    }
+    return true;
+  }
+  inline int decode(InBits& br) const {
+    br.need(15);
+    const uint16_t f = fast[br.acc & 1023];
+    if (f) { br.acc >>= (f >> 9); br.cnt -= (f >> 9); return f & 511; }
+    int code = 0, first = 0, index = 0;                                        // canonical bit-by-bit (codes of 11..15 bits)
+    for (int l = 1; l < 16; ++l) {
+      code |= (int)(br.acc & 1);
+      br.acc >>= 1;
+      br.cnt -= 1;
+      const int c = count[l];
+      if (code - c < first) return symbol[index + (code - first)];
+      index += c;
+      first += c;
+      first <<= 1;
+      code <<= 1;
+    }
+    return -1;
+  }
+};
+
+int inflate_stream(InBits& br, uint8_t* out, size_t out_cap, size_t* out_len) {
+  static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  HuffDec* lit = new HuffDec();
+  HuffDec* dist = new HuffDec();
+  size_t o = 0;
+  int rc = ADVGRPO_OK;
+  auto fail = [&](const char* why) { rc = set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: %s", why); };
+  for (bool last = false; !last && rc == ADVGRPO_OK;) {
+    last = br.bits(1);
+    const int type = (int)br.bits(2);
+    if (type == 0) {
+      br.align_byte();
+      const uint32_t len = br.bits(16), nlen = br.bits(16);
+      if ((len ^ 0xFFFF) != nlen) { fail("stored block length check"); break; }
+      if (o + len > out_cap) { fail("output overflow"); break; }
+      for (uint32_t i = 0; i < len; ++i) out[o++] = (uint8_t)br.bits(8);
+      continue;
+    }
+    if (type == 3) { fail("reserved block type"); break; }
+    uint8_t lengths[320];
+    if (type == 1) {
+      for (int i = 0; i < 144; ++i) lengths[i] = 8;
+      for (int i = 144; i < 256; ++i) lengths[i] = 9;
+      for (int i = 256; i < 280; ++i) lengths[i] = 7;
+      for (int i = 280; i < 288; ++i) lengths[i] = 8;
+      lit->build(lengths, 288);
+      for (int i = 0; i < 30; ++i) lengths[i] = 5;
+      dist->build(lengths, 30);
+    } else {
+      const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+      if (nlen > 286 || ndist > 30) { fail("bad table sizes"); break; }
+      uint8_t cl[19];
+      memset(cl, 0, sizeof(cl));
+      for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
+      HuffDec* lencode = new HuffDec();
+      if (!lencode->build(cl, 19)) { delete lencode; fail("bad code-length code"); break; }
+      int idx = 0;
+      while (idx < nlen + ndist) {
+        int sym = lencode->decode(br);
+        if (sym < 0) { fail("bad code-length symbol"); break; }
+        if (sym < 16) { lengths[idx++] = (uint8_t)sym; continue; }
+        int rep, val = 0;
+        if (sym == 16) {
+          if (idx == 0) { fail("repeat without a previous length"); break; }
+          val = lengths[idx - 1];
+          rep = 3 + (int)br.bits(2);
+        } else if (sym == 17) rep = 3 + (int)br.bits(3);
+        else rep = 11 + (int)br.bits(7);
+        if (idx + rep > nlen + ndist) { fail("too many lengths"); break; }
+        while (rep--) lengths[idx++] = (uint8_t)val;
+      }
+      delete lencode;
+      if (rc != ADVGRPO_OK) break;
+      if (!lit->build(lengths, nlen) || !dist->build(lengths + nlen, ndist)) { fail("bad Huffman table"); break; }
+    }
+    for (;;) {
+      const int sym = lit->decode(br);
+      if (sym < 0) { fail("bad literal / length code"); break; }
+      if (sym < 256) {
+        if (o >= out_cap) { fail("output overflow"); break; }
+        out[o++] = (uint8_t)sym;
+      } else if (sym == 256) {
+        break;
+      } else {
+        const int ls = sym - 257;
+        if (ls >= 29) { fail("bad length symbol"); break; }
+        const int len = lbase[ls] + (int)br.bits(lext[ls]);
+        const int ds = dist->decode(br);
+        if (ds < 0 || ds >= 30) { fail("bad distance code"); break; }
+        const size_t dd = dbase[ds] + br.bits(dext[ds]);
+        if (dd > o) { fail("distance beyond the start of the output"); break; }
+        if (o + len > out_cap) { fail("output overflow"); break; }
+        for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dd];
+      }
+    }
+  }
+  delete lit;
+  delete dist;
+  *out_len = o;
+  return rc;
+}
+
+// ---- device: wavefront unfilter + RGB conversion ---------------------------------------------------------------------------
+__device__ __forceinline__ int paeth(int a, int b, int c) {
+  const int p = a + b - c;
+  const int pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+  return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// raw: [H, 1 + rowbytes] filtered scan lines; rows: [H, rowbytes] reconstructed bytes.  ONE block; thread r = row band0 + r.
+template <int BPP>
+__global__ void __launch_bounds__(1024)
+png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows, int W, int H) {
+  __shared__ uint32_t up_sm[2][1024];                       // the pixel each row reconstructed in the previous step, by parity
+  const int r = threadIdx.x, R = blockDim.x;
+  const int64_t rowbytes = (int64_t)W * BPP;
+  for (int band0 = 0; band0 < H; band0 += R) {
+    const int y = band0 + r;
+    const bool live = y < H;
+    const int rows_here = min(R, H - band0);
+    const uint8_t* in = raw + (int64_t)(live ? y : 0) * (1 + rowbytes);
+    uint8_t* out = rows + (int64_t)(live ? y : 0) * rowbytes;
+    const uint8_t* prior = rows + (int64_t)(y - 1) * rowbytes;      // only read by the first row of a band (y > 0)
+    const int ft = live ? in[0] : 0;
+    uint32_t left = 0, upleft = 0;                            // packed BPP bytes
+    const int steps = W + rows_here - 1;
+    for (int t = 0; t < steps; ++t) {
+      const int px = t - r;
+      uint32_t rec = 0;
+      if (live && px >= 0 && px < W) {
+        uint32_t up = 0;
+        if (r > 0) up = up_sm[(t + 1) & 1][r - 1];            // written by row r - 1 in step t - 1
+        else if (y > 0) {
+#pragma unroll
+          for (int k = 0; k < BPP; ++k) up |= (uint32_t)prior[(int64_t)px * BPP + k] << (8 * k);
+        }
+#pragma unroll
+        for (int k = 0; k < BPP; ++k) {
+          const int x = in[1 + (int64_t)px * BPP + k];
+          const int a = (left >> (8 * k)) & 255, b = (up >> (8 * k)) & 255, c = (upleft >> (8 * k)) & 255;
+          int pr = 0;
+          if (ft == 1) pr = a;
+          else if (ft == 2) pr = b;
+          else if (ft == 3) pr = (a + b) >> 1;
+          else if (ft == 4) pr = paeth(a, b, c);
+          const int v = (x + pr) & 255;
+          rec |= (uint32_t)v << (8 * k);
+          out[(int64_t)px * BPP + k] = (uint8_t)v;
+        }
+        left = rec;
+        upleft = up;
+      }
+      up_sm[t & 1][r] = rec;
+      __syncthreads();
+    }
+    __syncthreads();                                          // the band's last row is complete in global memory
+  }
+}
+
+// rows [H, W * ch] -> rgb [H, W, 3]: ct 6 drops alpha, ct 0 / 4 replicate grey, ct 3 looks the palette up
+__global__ void __launch_bounds__(256)
+png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb, int64_t npx,
+                  int ch, int color_type) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npx) return;
+  const uint8_t* p = rows + i * ch;
+  uint8_t r, g, b;
+  if (color_type == 6) { r = p[0]; g = p[1]; b = p[2]; }
+  else if (color_type == 3) { r = palette[3 * p[0]]; g = palette[3 * p[0] + 1]; b = palette[3 * p[0] + 2]; }
+  else { r = g = b = p[0]; }
+  rgb[3 * i] = r;
+  rgb[3 * i + 1] = g;
+  rgb[3 * i + 2] = b;
+}
+
+}  // namespace
+}  // namespace advgrpo
+
+using namespace advgrpo;
+
+extern "C" {
+
+int advgrpo_png_parse(const uint8_t* file, size_t nbytes, advgrpo_png_info* info) {
+  ADVGRPO_CHECK_ARG(file && info, "png_parse: null pointer");
+  PngParsed* P = new PngParsed();
+  const int rc = parse_png(file, nbytes, *P);
+  *info = P->info;
+  delete P;
+  return rc;
+}
+
+size_t advgrpo_png_raw_bytes(const advgrpo_png_info* info) {
+  if (!info || !info->supported) return 0;
+  return (size_t)info->height * (1 + (size_t)info->rowbytes);
+}
+
+int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, uint8_t* palette_host) {
+  ADVGRPO_CHECK_ARG(file && raw_host && palette_host, "png_inflate: null pointer");
+  PngParsed* P = new PngParsed();
+  int rc = parse_png(file, nbytes, *P);
+  if (rc == ADVGRPO_OK && !P->info.supported) rc = set_error(ADVGRPO_ERR_UNSUPPORTED, "png_inflate: file is outside the supported subset");
+  if (rc != ADVGRPO_OK) { delete P; return rc; }
+  memcpy(palette_host, P->palette, 768);
+  InBits br{file, &P->idat, 0, 0, 0, 0, false};
+  const uint32_t cmf = br.bits(8), flg = br.bits(8);                       // zlib header (RFC 1950)
+  if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) {
+    delete P;
+    return set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: bad zlib header");
+  }
+  const size_t want = advgrpo_png_raw_bytes(&P->info);
+  size_t got = 0;
+  rc = inflate_stream(br, raw_host, want, &got);
+  if (rc == ADVGRPO_OK && got != want) rc = set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: %zu bytes of image data, %zu expected", got, want);
+  delete P;
+  return rc;
+}
+
+size_t advgrpo_png_workspace_bytes(const advgrpo_png_info* info) {
+  if (!info || !info->supported) return 0;
+  return (size_t)info->height * (size_t)info->rowbytes + 256;
+}
+
+int advgrpo_png_unfilter_to_rgb(const uint8_t* raw_dev, const uint8_t* palette_dev, const advgrpo_png_info* info,
+                                uint8_t* rgb_hwc_dev, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream) {
+  ADVGRPO_CHECK_ARG(raw_dev && info && rgb_hwc_dev, "png_unfilter_to_rgb: null pointer");
+  ADVGRPO_CHECK_ARG(info->supported && info->width >= 1 && info->height >= 1 && info->channels >= 1 && info->channels <= 4,
+                    "png_unfilter_to_rgb: unsupported file (advgrpo_png_parse reported supported = 0)");
+  ADVGRPO_CHECK_ARG(info->color_type != 3 || palette_dev, "png_unfilter_to_rgb: palette image without a palette");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool direct = info->color_type == 2;                  // truecolour: the reconstructed rows ARE the RGB bytes
+  uint8_t* rows = direct ? rgb_hwc_dev : (uint8_t*)workspace;
+  if (!direct && (!workspace || workspace_bytes < advgrpo_png_workspace_bytes(info)))
+    return set_error(ADVGRPO_ERR_WORKSPACE, "png_unfilter_to_rgb: workspace too small");
+  int threads = info->height < 1024 ? ((info->height + 31) / 32) * 32 : 1024;
+  switch (info->channels) {
+    case 1: png_unfilter_kernel<1><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
+    case 2: png_unfilter_kernel<2><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
+    case 3: png_unfilter_kernel<3><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
+    default: png_unfilter_kernel<4><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
+  }
+  ADVGRPO_CUDA_LAUNCH_CHECK();
+  if (!direct) {
+    const int64_t npx = (int64_t)info->width * info->height;
+    png_to_rgb_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(rows, palette_dev, rgb_hwc_dev, npx, info->channels,
+                                                                    info->color_type);
+    ADVGRPO_CUDA_LAUNCH_CHECK();
+  }
+  return ADVGRPO_OK;
+}
+
+}  // extern "C"

@@ -1,11 +1,13 @@
 """Reference ("real") images of the adversarial loop: the `{prompt: [file, ...]}` index JSON (`config.json_path`,
 README.md:114-128 of the reference) and the per-batch loading of `scripts/train_sd3_fast_pickscore.py:705-707,
 773-799`: `Image.open(root / name).convert("RGB")` -> `transforms.Resize((512, 512))` (PIL bilinear with Pillow's
-antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  With a CUDA device: JPEG files (sequential or
-progressive) are
-entropy-decoded by the library's own host Huffman decoder and everything after that (inverse DCT, chroma upsampling,
-colour conversion: `jpeg.decode_jpeg_to_device`, libjpeg / Pillow bit-exact) runs on the GPU; other formats (PNG,
-arithmetic-coded or CMYK JPEG) are decoded by Pillow on the host and their bytes uploaded; the antialiased bilinear resize +
+antialiasing) -> `ToTensor()` ([0,1] float32, CHW) -> stacked on the device.  With a CUDA device: PNG files (what the
+reference's reference-image generator writes) are inflated by the library's own host inflate and unfiltered + converted to
+RGB on the GPU (`png.decode_png_to_device`); JPEG files (sequential or progressive) are entropy-decoded by the library's own
+host Huffman decoder and everything after that (inverse DCT, chroma upsampling, colour conversion:
+`jpeg.decode_jpeg_to_device`) runs on the GPU -- both byte-exact with Pillow; files outside those decoders' subsets
+(interlaced / 16-bit PNG, arithmetic-coded or CMYK JPEG, other formats) are decoded by Pillow on the host and their bytes
+uploaded; the antialiased bilinear resize +
 ToTensor always run on the GPU (`ops.pil_resize_bilinear`, Pillow bit-exact).  Results are cached per prompt because
 the files never change, which the reference does not do (it re-opens every file of the prompt for every batch).
 SURVEY.md section 8f rank 3."""
@@ -31,12 +33,14 @@ class ReferenceImageIndex:
         from PIL import Image
         cuda = torch.device(self.device).type == "cuda"
         if cuda:                                                       # baseline JPEG: host Huffman decode, the rest on the GPU
-            from . import _lib, jpeg, ops
+            from . import _lib, jpeg, ops, png
             raw = None
             try:
                 with open(path, "rb") as f:
                     data = f.read()
-                if data[:2] == b"\xff\xd8":
+                if data[:8] == b"\x89PNG\r\n\x1a\n":                       # the reference images of the loop are PNG files
+                    raw = png.decode_png_to_device(data, self.device)     # None: interlaced / sub-byte / 16-bit -> Pillow below
+                elif data[:2] == b"\xff\xd8":
                     raw = jpeg.decode_jpeg_to_device(data, self.device)   # None: CMYK / arithmetic / ... -> Pillow below
             except (OSError, _lib.AdvGrpoError):
                 raw = None                                             # unreadable / corrupt: Pillow decides (and falls back)

@@ -378,6 +378,26 @@ int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coe
 size_t advgrpo_jpeg_workspace_bytes(const advgrpo_jpeg_info* info);
 int advgrpo_jpeg_idct_to_rgb(const int16_t* coefs_dev, const uint16_t* qtabs_dev, const advgrpo_jpeg_info* info,
                              uint8_t* rgb_hwc_dev, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
+/* PNG decode of the reference images (the adversarial loop's reference images are PNG files, README.md:114-128 of the
+ * reference; `Image.open(fpath).convert("RGB")`, scripts/train_sd3_fast_pickscore.py:773-786), hybrid: chunk walk + zlib inflate
+ * of the IDAT stream on the HOST (plain C++ in this library: stored / fixed / dynamic Huffman blocks, LZ77 copies), scan-line
+ * unfiltering (None / Sub / Up / Average / Paeth) as an anti-diagonal wavefront + conversion to interleaved RGB on the
+ * DEVICE.  Byte-exact with Pillow for non-interlaced 8-bit files of every colour type (truecolour, truecolour + alpha: alpha
+ * dropped, greyscale (+ alpha): replicated, palette: looked up).  advgrpo_png_parse (host) fills `info`; supported == 0 marks
+ * a valid file outside that subset (Adam7, 1 / 2 / 4 / 16-bit): the caller keeps its host decoder for it.
+ * advgrpo_png_inflate (host): raw_host uint8 [advgrpo_png_raw_bytes(info)] = height x (1 filter byte + rowbytes) filtered scan
+ * lines, palette_host uint8 [768].  advgrpo_png_unfilter_to_rgb: device copies of both -> rgb_hwc_dev uint8 [height, width, 3]
+ * (workspace: advgrpo_png_workspace_bytes, unused for truecolour). */
+typedef struct {
+  int32_t width, height, bit_depth, color_type, interlace;
+  int32_t channels, rowbytes, palette_entries, supported;
+} advgrpo_png_info;
+int advgrpo_png_parse(const uint8_t* file, size_t nbytes, advgrpo_png_info* info);
+size_t advgrpo_png_raw_bytes(const advgrpo_png_info* info);
+int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, uint8_t* palette_host);
+size_t advgrpo_png_workspace_bytes(const advgrpo_png_info* info);
+int advgrpo_png_unfilter_to_rgb(const uint8_t* raw_dev, const uint8_t* palette_dev, const advgrpo_png_info* info,
+                                uint8_t* rgb_hwc_dev, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream);
 /* A8b preprocessing (adv_grpo/rewards.py:379-391): bicubic (A = -0.75, align_corners =
  * False, no antialias) resize to out x out, ImageNet normalisation, cast to bf16. */
 int advgrpo_dino_preprocess(const void* images, int images_f32, int64_t B, int64_t H, int64_t W,

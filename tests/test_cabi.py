@@ -112,6 +112,8 @@ def test_empty_inputs_are_noops_or_clean_errors():
         ("advgrpo_attn_small_bwd", (buf, buf, buf, buf, buf, buf, buf, buf, buf, buf, 1, 4096, 1, 64, 0.125, 0, None)),  # too long
         ("advgrpo_row_softmax_f32", (buf, buf, 3, 6, 1.0, 0, None)),                                 # cols not a multiple of 4
         ("advgrpo_jpeg_parse", (None, 0, None)),                                                     # null pointers
+        ("advgrpo_png_parse", (None, 0, None)),
+        ("advgrpo_png_unfilter_to_rgb", (buf, buf, None, buf, buf, 1 << 20, None)),                  # no header info
         ("advgrpo_jpeg_idct_to_rgb", (buf, buf, None, buf, buf, 1 << 20, None)),                     # no frame info
         ("advgrpo_pil_resize_bilinear_u8", (buf, 0, 640, 512, 512, buf, None, buf, 1 << 20, None)),  # empty image
         ("advgrpo_pil_resize_bilinear_u8", (buf, 480, 640, 512, 512, buf, None, buf, 16, None)),     # workspace too small

@@ -656,3 +656,35 @@ def test_jpeg_decode_bit_exact_with_pillow(h, w, kw):
     assert torch.equal(got.cpu(), torch.from_numpy(ref.copy()))
     from jpeg_util import _cmyk_jpeg
     assert jpeg_b.decode_jpeg_to_device(_cmyk_jpeg(), DEV) is None
+
+
+# ------------------------------------------------------------------ 8f-3 PNG decode (host inflate + device wavefront unfilter)
+@pytest.mark.parametrize("h,w,mode", [(512, 512, "RGB"), (300, 1500, "RGB"), (1500, 300, "RGB"), (2100, 64, "RGBA"),
+                                      (257, 129, "L"), (100, 100, "LA"), (333, 517, "P"), (1, 1, "RGB"), (1025, 3, "RGB")])
+def test_png_decode_bit_exact_with_pillow(h, w, mode):
+    """`Image.open(path).convert("RGB")` (train_sd3_fast_pickscore.py:779; the reference images are PNG files) on the device:
+    every byte equals Pillow's decode -- all colour types, images taller than one 1024-row wavefront band."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import png as png_b
+    from png_util import pillow_png
+    data = pillow_png(h, w, mode, seed=h + w)
+    ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+    got = png_b.decode_png_to_device(data, DEV)
+    assert got is not None and got.dtype == torch.uint8 and got.shape == (h, w, 3)
+    assert torch.equal(got.cpu(), torch.from_numpy(ref.copy()))
+
+
+@pytest.mark.parametrize("ct", [0, 2, 3, 4, 6])
+def test_png_decode_all_filter_types(ct):
+    """Hand-assembled files: random filter type per row (None / Sub / Up / Average / Paeth -- Pillow's encoder never emits
+    Average), stored and compressed deflate blocks, IDAT split into 100-byte chunks; 1300 rows = two wavefront bands."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import png as png_b
+    from png_util import handmade_png
+    for h, w, level, split, kind in ((1300, 37, 6, 100, 0), (64, 200, 0, None, 1), (5, 1, 9, 5, 2)):
+        data, _ = handmade_png(h, w, ct, seed=ct + h, level=level, split=split, kind=kind)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        got = png_b.decode_png_to_device(data, DEV)
+        assert torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (h, w, ct)
