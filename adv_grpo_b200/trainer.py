@@ -9,7 +9,6 @@ ranks (each rank rolls out whole G-sample groups); NCCL is used only for
 Everything between the collectives stays on the device: no `.cpu().numpy()` of rewards, no tokenizer
 decode of prompt ids, no float64 host advantages.
 """
-import math
 import os
 import warnings
 
