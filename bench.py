@@ -154,7 +154,7 @@ def cpu_reference_sample(steps=1, warmup=0, verbose=False, budget_s=None):
     t = torch.full((2,), 500.0)
     ctx = torch.randn(2, 205, 4096, generator=g)
     pooled = torch.randn(2, 2048, generator=g)
-    results = []
+    results, step_wall = [], []
     t_start = time.perf_counter()
     for it in range(warmup + steps):
         # bounded run: the CPU timings repeat to ~2 %, so once the wall budget is spent the remaining steps
@@ -182,11 +182,13 @@ def cpu_reference_sample(steps=1, warmup=0, verbose=False, budget_s=None):
                   f"-> {per_sample:.1f}s/sample", file=sys.stderr)
         if it >= warmup:
             results.append(1.0 / per_sample)
+            step_wall.append(t_fwd + t_fb + t_vae + t_clip)        # what this bounded step actually took on the host
     desc = ("oracle (torch fp32 restatement of the reference path) on host cores: timed 1 MMDiT fwd at B=2 (one CFG "
             "pair), 1 fwd+bwd at B=2, 1 VAE decode, 1 PickScore image fwd at SD3.5-M/512px shapes; per-sample time = "
             "10*fwd + 2*(fwd+bwd) + vae + 2*clip (extrapolated by step counts)")
     if len(results) < steps:
         desc += f"; {len(results)} of {steps} requested steps executed within the {budget_s:.0f} s wall budget"
+    cpu_reference_sample.last_step_wall_s = step_wall
     return results, cores, desc
 
 
@@ -203,7 +205,10 @@ def run_reference(args):
     v = statistics.mean(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "steps_executed": len(vals),
-            "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
+            # ms_per_step = the measured wall time of one bounded step (the timed sample); `value` extrapolates that sample to
+            # a whole GRPO sample by the step counts, ms_per_sample_extrapolated = 1000 / value
+            "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.mean(cpu_reference_sample.last_step_wall_s),
+            "ms_per_sample_extrapolated": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             # the same config object as the GPU arm prints for this launch (the CPU arm is one process on rank 0's host cores;
             # its per-sample time does not depend on how many groups a step holds)
