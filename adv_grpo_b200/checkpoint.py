@@ -106,7 +106,7 @@ def save_ckpt(save_dir, transformer, global_step, ema=None, trainable_parameters
         ema.copy_ema_to(trainable_parameters, store_temp=True)
         transformer.invalidate_lora_cache()
     try:
-        save_lora(transformer, root)
+        transformer.save_pretrained(root)            # the LoRA adapter directory, or the full weights under use_lora = False
     finally:
         if use_ema and ema is not None:
             ema.copy_temp_to(trainable_parameters)

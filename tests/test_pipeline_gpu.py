@@ -260,3 +260,11 @@ def test_grpo_epoch_full_finetune():
     assert not torch.equal(before, tr.params[0])
     info = tr.run_epoch()
     assert torch.isfinite(info["loss"])
+    # save_ckpt under full fine-tuning writes the diffusers-named weights (fp32 master), not a LoRA adapter
+    import os
+    import tempfile
+    from safetensors.torch import load_file
+    with tempfile.TemporaryDirectory() as d:
+        root = tr.save_ckpt(d)
+        sd = load_file(os.path.join(root, "diffusion_pytorch_model.safetensors"))
+        assert set(sd) == set(pipe.transformer.p) and sd["proj_out.weight"].dtype == torch.float32
