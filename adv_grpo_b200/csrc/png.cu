@@ -10,8 +10,9 @@
 //           arrives from the neighbouring thread through shared memory (double-buffered by step parity), left / upper-left
 //           stay in registers; W + rows - 1 steps of one barrier each.  Then conversion to interleaved RGB bytes (truecolour:
 //           in place; alpha dropped; greyscale replicated; palette looked up), as Pillow's convert("RGB") does.
-// Non-interlaced 8-bit files of every colour type; other files (Adam7, 1/2/4/16-bit) are reported unsupported by
-// advgrpo_png_parse and stay on the caller's host decoder.
+// Non-interlaced files of every colour type and bit depth Pillow maps onto 8-bit RGB (1 / 2 / 4 / 8 / 16-bit greyscale, 8 / 16-bit
+// truecolour (+ alpha), 1..8-bit palette, 8-bit greyscale + alpha); Adam7-interlaced files and 16-bit greyscale + alpha are
+// reported unsupported by advgrpo_png_parse and stay on the caller's host decoder.
 #include <stdlib.h>
 #include <string.h>
 
@@ -71,8 +72,12 @@ int parse_png(const uint8_t* d, size_t n, PngParsed& P) {
     return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad image size");
   P.info.channels = png_channels(P.info.color_type);
   if (!P.info.channels) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad colour type");
-  P.info.rowbytes = P.info.width * P.info.channels;
-  P.info.supported = P.info.bit_depth == 8 && P.info.interlace == 0 && (P.info.color_type != 3 || have_plte);
+  const int bd = P.info.bit_depth, ct = P.info.color_type;
+  const bool depth_ok = (ct == 0 && (bd == 1 || bd == 2 || bd == 4 || bd == 8 || bd == 16)) || ((ct == 2 || ct == 6) && (bd == 8 || bd == 16)) ||
+                        (ct == 3 && (bd == 1 || bd == 2 || bd == 4 || bd == 8)) || (ct == 4 && bd == 8);
+  if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad bit depth");
+  P.info.rowbytes = (int32_t)(((int64_t)P.info.width * P.info.channels * bd + 7) / 8);
+  P.info.supported = depth_ok && P.info.interlace == 0 && (ct != 3 || have_plte);
   return ADVGRPO_OK;
 }
 
@@ -248,10 +253,11 @@ __device__ __forceinline__ int paeth(int a, int b, int c) {
 }
 
 // raw: [H, 1 + rowbytes] filtered scan lines; rows: [H, rowbytes] reconstructed bytes.  ONE block; thread r = row band0 + r.
+// BPP = bytes per complete pixel as the filters see it (1 for sub-byte depths, 6 / 8 for 16-bit truecolour); W = rowbytes / BPP.
 template <int BPP>
 __global__ void __launch_bounds__(1024)
 png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows, int W, int H) {
-  __shared__ uint32_t up_sm[2][1024];                       // the pixel each row reconstructed in the previous step, by parity
+  __shared__ uint64_t up_sm[2][1024];                       // the pixel each row reconstructed in the previous step, by parity
   const int r = threadIdx.x, R = blockDim.x;
   const int64_t rowbytes = (int64_t)W * BPP;
   for (int band0 = 0; band0 < H; band0 += R) {
@@ -262,29 +268,29 @@ png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows,
     uint8_t* out = rows + (int64_t)(live ? y : 0) * rowbytes;
     const uint8_t* prior = rows + (int64_t)(y - 1) * rowbytes;      // only read by the first row of a band (y > 0)
     const int ft = live ? in[0] : 0;
-    uint32_t left = 0, upleft = 0;                            // packed BPP bytes
+    uint64_t left = 0, upleft = 0;                            // packed BPP bytes
     const int steps = W + rows_here - 1;
     for (int t = 0; t < steps; ++t) {
       const int px = t - r;
-      uint32_t rec = 0;
+      uint64_t rec = 0;
       if (live && px >= 0 && px < W) {
-        uint32_t up = 0;
+        uint64_t up = 0;
         if (r > 0) up = up_sm[(t + 1) & 1][r - 1];            // written by row r - 1 in step t - 1
         else if (y > 0) {
 #pragma unroll
-          for (int k = 0; k < BPP; ++k) up |= (uint32_t)prior[(int64_t)px * BPP + k] << (8 * k);
+          for (int k = 0; k < BPP; ++k) up |= (uint64_t)prior[(int64_t)px * BPP + k] << (8 * k);
         }
 #pragma unroll
         for (int k = 0; k < BPP; ++k) {
           const int x = in[1 + (int64_t)px * BPP + k];
-          const int a = (left >> (8 * k)) & 255, b = (up >> (8 * k)) & 255, c = (upleft >> (8 * k)) & 255;
+          const int a = (int)((left >> (8 * k)) & 255), b = (int)((up >> (8 * k)) & 255), c = (int)((upleft >> (8 * k)) & 255);
           int pr = 0;
           if (ft == 1) pr = a;
           else if (ft == 2) pr = b;
           else if (ft == 3) pr = (a + b) >> 1;
           else if (ft == 4) pr = paeth(a, b, c);
           const int v = (x + pr) & 255;
-          rec |= (uint32_t)v << (8 * k);
+          rec |= (uint64_t)v << (8 * k);
           out[(int64_t)px * BPP + k] = (uint8_t)v;
         }
         left = rec;
@@ -297,20 +303,35 @@ png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows,
   }
 }
 
-// rows [H, W * ch] -> rgb [H, W, 3]: ct 6 drops alpha, ct 0 / 4 replicate grey, ct 3 looks the palette up
+// rows [H, rowbytes] -> rgb [H, W, 3], as Pillow's convert("RGB"): sub-byte samples unpacked MSB first (greyscale scaled to
+// 0..255, palette indices looked up), 16-bit truecolour keeps the high byte of every sample, 16-bit greyscale is CLIPPED to 255
+// (Pillow's I;16 -> RGB), alpha dropped, grey replicated.
 __global__ void __launch_bounds__(256)
-png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb, int64_t npx,
-                  int ch, int color_type) {
+png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb, int W, int H,
+                  int64_t rowbytes, int ch, int color_type, int bd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npx) return;
-  const uint8_t* p = rows + i * ch;
-  uint8_t r, g, b;
-  if (color_type == 6) { r = p[0]; g = p[1]; b = p[2]; }
-  else if (color_type == 3) { r = palette[3 * p[0]]; g = palette[3 * p[0] + 1]; b = palette[3 * p[0] + 2]; }
-  else { r = g = b = p[0]; }
-  rgb[3 * i] = r;
-  rgb[3 * i + 1] = g;
-  rgb[3 * i + 2] = b;
+  if (i >= (int64_t)W * H) return;
+  const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+  const uint8_t* row = rows + (int64_t)y * rowbytes;
+  int v[3];
+  if (bd < 8) {
+    const int bit = x * bd;
+    const int s = (row[bit >> 3] >> (8 - bd - (bit & 7))) & ((1 << bd) - 1);
+    if (color_type == 3) { v[0] = palette[3 * s]; v[1] = palette[3 * s + 1]; v[2] = palette[3 * s + 2]; }
+    else v[0] = v[1] = v[2] = s * (255 / ((1 << bd) - 1));
+  } else {
+    const int sb = bd >> 3;                                   // bytes per sample
+    const uint8_t* p = row + (int64_t)x * ch * sb;
+    if (color_type == 2 || color_type == 6) { v[0] = p[0]; v[1] = p[sb]; v[2] = p[2 * sb]; }
+    else if (color_type == 3) { v[0] = palette[3 * p[0]]; v[1] = palette[3 * p[0] + 1]; v[2] = palette[3 * p[0] + 2]; }
+    else {
+      const int g = sb == 2 ? min(p[0] * 256 + p[1], 255) : p[0];
+      v[0] = v[1] = v[2] = g;
+    }
+  }
+  rgb[3 * i] = (uint8_t)v[0];
+  rgb[3 * i + 1] = (uint8_t)v[1];
+  rgb[3 * i + 2] = (uint8_t)v[2];
 }
 
 }  // namespace
@@ -363,26 +384,34 @@ size_t advgrpo_png_workspace_bytes(const advgrpo_png_info* info) {
 int advgrpo_png_unfilter_to_rgb(const uint8_t* raw_dev, const uint8_t* palette_dev, const advgrpo_png_info* info,
                                 uint8_t* rgb_hwc_dev, void* workspace, size_t workspace_bytes, advgrpo_stream_t stream) {
   ADVGRPO_CHECK_ARG(raw_dev && info && rgb_hwc_dev, "png_unfilter_to_rgb: null pointer");
-  ADVGRPO_CHECK_ARG(info->supported && info->width >= 1 && info->height >= 1 && info->channels >= 1 && info->channels <= 4,
+  ADVGRPO_CHECK_ARG(info->supported && info->width >= 1 && info->height >= 1 && info->channels >= 1 && info->channels <= 4 &&
+                        info->rowbytes >= 1,
                     "png_unfilter_to_rgb: unsupported file (advgrpo_png_parse reported supported = 0)");
   ADVGRPO_CHECK_ARG(info->color_type != 3 || palette_dev, "png_unfilter_to_rgb: palette image without a palette");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool direct = info->color_type == 2;                  // truecolour: the reconstructed rows ARE the RGB bytes
+  const bool direct = info->color_type == 2 && info->bit_depth == 8;   // 8-bit truecolour: the reconstructed rows ARE the RGB bytes
   uint8_t* rows = direct ? rgb_hwc_dev : (uint8_t*)workspace;
   if (!direct && (!workspace || workspace_bytes < advgrpo_png_workspace_bytes(info)))
     return set_error(ADVGRPO_ERR_WORKSPACE, "png_unfilter_to_rgb: workspace too small");
-  int threads = info->height < 1024 ? ((info->height + 31) / 32) * 32 : 1024;
-  switch (info->channels) {
-    case 1: png_unfilter_kernel<1><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
-    case 2: png_unfilter_kernel<2><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
-    case 3: png_unfilter_kernel<3><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
-    default: png_unfilter_kernel<4><<<1, threads, 0, st>>>(raw_dev, rows, info->width, info->height); break;
+  const int threads = info->height < 1024 ? ((info->height + 31) / 32) * 32 : 1024;
+  const int bits = info->channels * info->bit_depth;
+  const int fbpp = bits >= 8 ? bits / 8 : 1;                   // bytes per complete pixel (PNG 1.2 section 6.2), at least 1
+  const int units = info->rowbytes / fbpp;
+  switch (fbpp) {
+    case 1: png_unfilter_kernel<1><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    case 2: png_unfilter_kernel<2><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    case 3: png_unfilter_kernel<3><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    case 4: png_unfilter_kernel<4><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    case 6: png_unfilter_kernel<6><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    case 8: png_unfilter_kernel<8><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
+    default: return set_error(ADVGRPO_ERR_UNSUPPORTED, "png_unfilter_to_rgb: %d bytes per pixel", fbpp);
   }
   ADVGRPO_CUDA_LAUNCH_CHECK();
   if (!direct) {
     const int64_t npx = (int64_t)info->width * info->height;
-    png_to_rgb_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(rows, palette_dev, rgb_hwc_dev, npx, info->channels,
-                                                                    info->color_type);
+    png_to_rgb_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(rows, palette_dev, rgb_hwc_dev, info->width, info->height,
+                                                                    (int64_t)info->rowbytes, info->channels, info->color_type,
+                                                                    info->bit_depth);
     ADVGRPO_CUDA_LAUNCH_CHECK();
   }
   return ADVGRPO_OK;

@@ -1,6 +1,6 @@
 """Oracle (test infrastructure only): PNG decode restated in numpy -- what Pillow's `Image.open(path).convert("RGB")`
 (`scripts/train_sd3_fast_pickscore.py:779`; the reference images of the adversarial loop are PNG files, README.md:114-128 of
-the reference) returns for non-interlaced 8-bit files: chunk walk (PNG 1.2 section 5), zlib inflate of the concatenated
+the reference) returns for non-interlaced files: chunk walk (PNG 1.2 section 5), zlib inflate of the concatenated
 IDAT data (Python's `zlib` is the pin for the library's own inflate), scan-line unfiltering (section 6: None / Sub / Up /
 Average / Paeth, byte-wise modulo 256) and conversion to RGB (truecolour, truecolour + alpha: alpha dropped; greyscale:
 replicated; palette: looked up).  Pinned to Pillow in tests/test_oracle_models.py::test_png_oracle_matches_pillow.
@@ -43,14 +43,22 @@ CHANNELS = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
 
 
 def check_supported(info):
+    bd, ct = info["bit_depth"], info["color_type"]
     if info["interlace"]:
         raise PngUnsupported("Adam7-interlaced PNG")
-    if info["bit_depth"] != 8:
-        raise PngUnsupported("bit depth other than 8")
-    if info["color_type"] not in CHANNELS:
+    if ct not in CHANNELS:
         raise PngUnsupported("bad colour type")
-    if info["color_type"] == 3 and info["palette"] is None:
+    ok = {0: (1, 2, 4, 8, 16), 2: (8, 16), 3: (1, 2, 4, 8), 4: (8,), 6: (8, 16)}[ct]
+    if bd not in ok:
+        raise PngUnsupported(f"bit depth {bd} with colour type {ct}")
+    if ct == 3 and info["palette"] is None:
         raise PngUnsupported("palette image without PLTE")
+
+
+def geometry(info):
+    """-> (bytes per scan line, bytes per complete pixel as the filters see it: at least 1)"""
+    bits = CHANNELS[info["color_type"]] * info["bit_depth"]
+    return (info["width"] * bits + 7) // 8, max(1, bits // 8)
 
 
 def unfilter(raw, height, rowbytes, bpp):
@@ -87,15 +95,27 @@ def unfilter(raw, height, rowbytes, bpp):
 
 
 def to_rgb(rows, info):
-    h, w, ct = info["height"], info["width"], info["color_type"]
-    px = rows.reshape(h, w, CHANNELS[ct])
+    """What Pillow's convert("RGB") yields: sub-byte samples are unpacked (MSB first) -- greyscale scaled to 0..255 (x 255 / 85 /
+    17), palette indices looked up; 16-bit truecolour keeps the high byte of every sample, 16-bit greyscale (mode I;16) is
+    CLIPPED to 255; alpha is dropped."""
+    h, w, ct, bd = info["height"], info["width"], info["color_type"], info["bit_depth"]
+    ch = CHANNELS[ct]
+    if bd < 8:
+        bits = np.unpackbits(rows, axis=1)[:, :w * bd].reshape(h, w, bd)
+        px = (bits * (1 << np.arange(bd - 1, -1, -1))).sum(-1).astype(np.int32)[..., None]
+        if ct == 0:
+            px = px * (255 // ((1 << bd) - 1))
+    elif bd == 16:
+        s16 = rows.reshape(h, w, ch, 2).astype(np.int32)
+        px = np.minimum(s16[..., 0] * 256 + s16[..., 1], 255) if ct == 0 else s16[..., 0]
+    else:
+        px = rows.reshape(h, w, ch).astype(np.int32)
+    px = px.astype(np.uint8)
     if ct == 2:
         return px.copy()
     if ct == 6:
         return px[..., :3].copy()                        # Image.convert("RGB") drops the alpha channel
-    if ct == 0:
-        return np.repeat(px, 3, axis=2)
-    if ct == 4:
+    if ct in (0, 4):
         return np.repeat(px[..., :1], 3, axis=2)
     pal = np.zeros((256, 3), dtype=np.uint8)
     pal[:len(info["palette"])] = info["palette"]
@@ -106,7 +126,6 @@ def decode_rgb(data):
     """bytes of a PNG file -> uint8 [H, W, 3], equal to np.asarray(Image.open(...).convert("RGB"))."""
     info = parse(data)
     check_supported(info)
-    ch = CHANNELS[info["color_type"]]
-    rowbytes = info["width"] * ch
+    rowbytes, bpp = geometry(info)
     raw = zlib.decompress(info["idat"])
-    return to_rgb(unfilter(raw, info["height"], rowbytes, ch), info)
+    return to_rgb(unfilter(raw, info["height"], rowbytes, bpp), info)

@@ -13,22 +13,22 @@ def _chunk(t, b):
     return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xFFFFFFFF)
 
 
-def handmade_png(h, w, ct, seed=0, level=6, split=None, kind=0):
+def handmade_png(h, w, ct, seed=0, level=6, split=None, kind=0, bd=8, interlace=0):
     """A PNG whose rows carry random filter types; returns the file bytes (the pixels are whatever the filters reconstruct)."""
     rng = np.random.default_rng(seed)
-    ch = CH[ct]
+    rb = (w * CH[ct] * bd + 7) // 8
     if kind == 0:
-        body = rng.integers(0, 256, (h, w * ch), dtype=np.uint8)
+        body = rng.integers(0, 256, (h, rb), dtype=np.uint8)
     elif kind == 1:
-        body = (np.add.outer(np.arange(h) * 3, np.arange(w * ch) * 2) % 256).astype(np.uint8)
+        body = (np.add.outer(np.arange(h) * 3, np.arange(rb) * 2) % 256).astype(np.uint8)
     else:
-        body = np.full((h, w * ch), 7, np.uint8)
+        body = np.full((h, rb), 7, np.uint8)
     ft = rng.integers(0, 5, (h, 1), dtype=np.uint8)
     raw = np.concatenate([ft, body], 1).tobytes()
     comp = zlib.compress(raw, level)
     idats = [comp] if not split else [comp[i:i + split] for i in range(0, len(comp), split)]
     plte = _chunk(b"PLTE", rng.integers(0, 256, 768, dtype=np.uint8).tobytes()) if ct == 3 else b""
-    return (b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ct, 0, 0, 0)) + plte +
+    return (b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, bd, ct, 0, 0, interlace)) + plte +
             b"".join(_chunk(b"IDAT", c) for c in idats) + _chunk(b"IEND", b"")), raw
 
 

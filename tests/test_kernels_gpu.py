@@ -688,3 +688,20 @@ def test_png_decode_all_filter_types(ct):
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         got = png_b.decode_png_to_device(data, DEV)
         assert torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (h, w, ct)
+
+
+@pytest.mark.parametrize("ct,bd", [(0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8)])
+def test_png_decode_every_bit_depth(ct, bd):
+    """Sub-byte greyscale (scaled to 0..255) and palette samples, 16-bit greyscale (Pillow clips I;16 to 255) and 16-bit
+    truecolour (+ alpha; the high byte of every sample): what Pillow's convert("RGB") returns, with random filter types
+    (filter pixels of 1, 2, 6 and 8 bytes) and 1100 rows = two wavefront bands."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import png as png_b
+    from png_util import handmade_png
+    for h, w, kind in ((1100, 29, 0), (7, 130, 1)):
+        data, _ = handmade_png(h, w, ct, seed=ct * 17 + bd + h, bd=bd, kind=kind)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        got = png_b.decode_png_to_device(data, DEV)
+        assert got is not None and torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (ct, bd, h, w)
+    assert png_b.decode_png_to_device(handmade_png(8, 8, 2, interlace=1)[0], DEV) is None

@@ -433,7 +433,7 @@ def test_png_oracle_and_host_inflate_match_pillow_and_zlib():
     """oracle/png.py (numpy restatement: chunk walk, unfiltering incl. Average and Paeth, RGB conversion) returns exactly
     Pillow's pixels, and the library's host inflate (csrc/png.cu, plain C++; runs without a GPU) returns exactly zlib's bytes --
     Pillow-written files of every colour type and hand-assembled files with random filter types, stored / fixed / dynamic
-    deflate blocks and split IDAT chunks; interlaced and sub-byte files are classified unsupported."""
+    deflate blocks and split IDAT chunks, every supported bit depth; interlaced files are classified unsupported."""
     import io
     import pytest
     from PIL import Image
@@ -457,12 +457,18 @@ def test_png_oracle_and_host_inflate_match_pillow_and_zlib():
         assert got_raw.numpy().tobytes() == zlib.decompress(png_o.parse(data)["idat"])
         if raw is not None:
             assert got_raw.numpy().tobytes() == raw
-    tiny_palette = pillow_png(4, 4, "P")                 # Pillow packs a small palette image into < 8 bits per pixel
-    info = png_b.png_info(tiny_palette)
-    if info.bit_depth != 8:
-        assert info.supported == 0 and png_b.inflate(tiny_palette)[0] is None
+    # every bit depth Pillow maps onto 8-bit RGB: sub-byte greyscale / palette, 16-bit greyscale (clipped) and truecolour
+    for t, (ct, bd) in enumerate(((0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4))):
+        data, raw = handmade_png(9 + t, 21 - t, ct, seed=100 + t, bd=bd, kind=t % 2)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        assert np.array_equal(png_o.decode_rgb(data), ref), (ct, bd)
+        got_raw, _, info = png_b.inflate(data)
+        assert info.supported == 1 and got_raw.numpy().tobytes() == raw
+    # outside the subset: Adam7 interlacing, 16-bit greyscale + alpha
+    for data in (handmade_png(8, 8, 2, interlace=1)[0], handmade_png(8, 8, 4, bd=16)[0]):
+        assert png_b.png_info(data).supported == 0 and png_b.inflate(data)[0] is None
         with pytest.raises(png_o.PngUnsupported):
-            png_o.decode_rgb(tiny_palette)
+            png_o.decode_rgb(data)
     from adv_grpo_b200 import _lib
     with pytest.raises(_lib.AdvGrpoError):
         png_b.png_info(b"definitely not a png")
