@@ -11,8 +11,9 @@
 //           stay in registers; W + rows - 1 steps of one barrier each.  Then conversion to interleaved RGB bytes (truecolour:
 //           in place; alpha dropped; greyscale replicated; palette looked up), as Pillow's convert("RGB") does.
 // Non-interlaced files of every colour type and bit depth Pillow maps onto 8-bit RGB (1 / 2 / 4 / 8 / 16-bit greyscale, 8 / 16-bit
-// truecolour (+ alpha), 1..8-bit palette, 8-bit greyscale + alpha); Adam7-interlaced files and 16-bit greyscale + alpha are
-// reported unsupported by advgrpo_png_parse and stay on the caller's host decoder.
+// truecolour (+ alpha), 1..8-bit palette, 8-bit greyscale + alpha), non-interlaced or Adam7-interlaced (seven reduced images,
+// each unfiltered on its own and scattered into place); 16-bit greyscale + alpha is reported unsupported by advgrpo_png_parse
+// and stays on the caller's host decoder.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,6 +27,28 @@ namespace {
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 int png_channels(int ct) { return ct == 0 ? 1 : ct == 2 ? 3 : ct == 3 ? 1 : ct == 4 ? 2 : ct == 6 ? 4 : 0; }
+
+// Adam7 (PNG 1.2 section 8.2): pass p covers pixels (x0 + i dx, y0 + j dy)
+const int kAdam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+
+struct PngPass { int x0, y0, dx, dy, w, h; int64_t rowbytes; };
+
+// the reduced images of an interlaced file (or the one full image of a non-interlaced one) that are not empty
+int png_passes(const advgrpo_png_info& I, PngPass* out) {
+  const int bits = I.channels * I.bit_depth;
+  if (!I.interlace) {
+    out[0] = {0, 0, 1, 1, I.width, I.height, (int64_t)I.rowbytes};
+    return 1;
+  }
+  int n = 0;
+  for (int p = 0; p < 7; ++p) {
+    const int x0 = kAdam7[p][0], y0 = kAdam7[p][1], dx = kAdam7[p][2], dy = kAdam7[p][3];
+    const int w = (I.width - x0 + dx - 1) / dx, h = (I.height - y0 + dy - 1) / dy;
+    if (w <= 0 || h <= 0) continue;
+    out[n++] = {x0, y0, dx, dy, w, h, ((int64_t)w * bits + 7) / 8};
+  }
+  return n;
+}
 
 struct PngParsed {
   advgrpo_png_info info;
@@ -77,7 +100,7 @@ int parse_png(const uint8_t* d, size_t n, PngParsed& P) {
                         (ct == 3 && (bd == 1 || bd == 2 || bd == 4 || bd == 8)) || (ct == 4 && bd == 8);
   if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad bit depth");
   P.info.rowbytes = (int32_t)(((int64_t)P.info.width * P.info.channels * bd + 7) / 8);
-  P.info.supported = depth_ok && P.info.interlace == 0 && (ct != 3 || have_plte);
+  P.info.supported = depth_ok && (P.info.interlace == 0 || P.info.interlace == 1) && (ct != 3 || have_plte);
   return ADVGRPO_OK;
 }
 
@@ -308,10 +331,11 @@ png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows,
 // (Pillow's I;16 -> RGB), alpha dropped, grey replicated.
 __global__ void __launch_bounds__(256)
 png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ palette, uint8_t* __restrict__ rgb, int W, int H,
-                  int64_t rowbytes, int ch, int color_type, int bd) {
+                  int64_t rowbytes, int ch, int color_type, int bd, int x0, int y0, int dx, int dy, int out_w) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)W * H) return;
   const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+  const int64_t o = ((int64_t)(y0 + y * dy) * out_w + (x0 + x * dx)) * 3;      // Adam7: scatter the reduced image into place
   const uint8_t* row = rows + (int64_t)y * rowbytes;
   int v[3];
   if (bd < 8) {
@@ -329,9 +353,9 @@ png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ 
       v[0] = v[1] = v[2] = g;
     }
   }
-  rgb[3 * i] = (uint8_t)v[0];
-  rgb[3 * i + 1] = (uint8_t)v[1];
-  rgb[3 * i + 2] = (uint8_t)v[2];
+  rgb[o] = (uint8_t)v[0];
+  rgb[o + 1] = (uint8_t)v[1];
+  rgb[o + 2] = (uint8_t)v[2];
 }
 
 }  // namespace
@@ -352,7 +376,11 @@ int advgrpo_png_parse(const uint8_t* file, size_t nbytes, advgrpo_png_info* info
 
 size_t advgrpo_png_raw_bytes(const advgrpo_png_info* info) {
   if (!info || !info->supported) return 0;
-  return (size_t)info->height * (1 + (size_t)info->rowbytes);
+  PngPass ps[7];
+  const int np = png_passes(*info, ps);
+  size_t n = 0;
+  for (int p = 0; p < np; ++p) n += (size_t)ps[p].h * (1 + (size_t)ps[p].rowbytes);
+  return n;
 }
 
 int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, uint8_t* palette_host) {
@@ -378,7 +406,7 @@ int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, u
 
 size_t advgrpo_png_workspace_bytes(const advgrpo_png_info* info) {
   if (!info || !info->supported) return 0;
-  return (size_t)info->height * (size_t)info->rowbytes + 256;
+  return advgrpo_png_raw_bytes(info) + 256;                  // the reconstructed scan lines of every pass (upper bound)
 }
 
 int advgrpo_png_unfilter_to_rgb(const uint8_t* raw_dev, const uint8_t* palette_dev, const advgrpo_png_info* info,
@@ -389,30 +417,39 @@ int advgrpo_png_unfilter_to_rgb(const uint8_t* raw_dev, const uint8_t* palette_d
                     "png_unfilter_to_rgb: unsupported file (advgrpo_png_parse reported supported = 0)");
   ADVGRPO_CHECK_ARG(info->color_type != 3 || palette_dev, "png_unfilter_to_rgb: palette image without a palette");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool direct = info->color_type == 2 && info->bit_depth == 8;   // 8-bit truecolour: the reconstructed rows ARE the RGB bytes
-  uint8_t* rows = direct ? rgb_hwc_dev : (uint8_t*)workspace;
+  const bool direct = info->color_type == 2 && info->bit_depth == 8 && !info->interlace;   // rows ARE the RGB bytes
   if (!direct && (!workspace || workspace_bytes < advgrpo_png_workspace_bytes(info)))
     return set_error(ADVGRPO_ERR_WORKSPACE, "png_unfilter_to_rgb: workspace too small");
-  const int threads = info->height < 1024 ? ((info->height + 31) / 32) * 32 : 1024;
   const int bits = info->channels * info->bit_depth;
   const int fbpp = bits >= 8 ? bits / 8 : 1;                   // bytes per complete pixel (PNG 1.2 section 6.2), at least 1
-  const int units = info->rowbytes / fbpp;
-  switch (fbpp) {
-    case 1: png_unfilter_kernel<1><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    case 2: png_unfilter_kernel<2><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    case 3: png_unfilter_kernel<3><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    case 4: png_unfilter_kernel<4><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    case 6: png_unfilter_kernel<6><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    case 8: png_unfilter_kernel<8><<<1, threads, 0, st>>>(raw_dev, rows, units, info->height); break;
-    default: return set_error(ADVGRPO_ERR_UNSUPPORTED, "png_unfilter_to_rgb: %d bytes per pixel", fbpp);
-  }
-  ADVGRPO_CUDA_LAUNCH_CHECK();
-  if (!direct) {
-    const int64_t npx = (int64_t)info->width * info->height;
-    png_to_rgb_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(rows, palette_dev, rgb_hwc_dev, info->width, info->height,
-                                                                    (int64_t)info->rowbytes, info->channels, info->color_type,
-                                                                    info->bit_depth);
+  PngPass ps[7];
+  const int np = png_passes(*info, ps);
+  size_t raw_off = 0, row_off = 0;
+  for (int p = 0; p < np; ++p) {
+    const PngPass& q = ps[p];
+    const uint8_t* raw_p = raw_dev + raw_off;
+    uint8_t* rows = direct ? rgb_hwc_dev : (uint8_t*)workspace + row_off;
+    const int threads = q.h < 1024 ? ((q.h + 31) / 32) * 32 : 1024;
+    const int units = (int)(q.rowbytes / fbpp);
+    switch (fbpp) {
+      case 1: png_unfilter_kernel<1><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      case 2: png_unfilter_kernel<2><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      case 3: png_unfilter_kernel<3><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      case 4: png_unfilter_kernel<4><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      case 6: png_unfilter_kernel<6><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      case 8: png_unfilter_kernel<8><<<1, threads, 0, st>>>(raw_p, rows, units, q.h); break;
+      default: return set_error(ADVGRPO_ERR_UNSUPPORTED, "png_unfilter_to_rgb: %d bytes per pixel", fbpp);
+    }
     ADVGRPO_CUDA_LAUNCH_CHECK();
+    if (!direct) {
+      const int64_t npx = (int64_t)q.w * q.h;
+      png_to_rgb_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(rows, palette_dev, rgb_hwc_dev, q.w, q.h, q.rowbytes,
+                                                                      info->channels, info->color_type, info->bit_depth, q.x0,
+                                                                      q.y0, q.dx, q.dy, info->width);
+      ADVGRPO_CUDA_LAUNCH_CHECK();
+    }
+    raw_off += (size_t)q.h * (1 + (size_t)q.rowbytes);
+    row_off += (size_t)q.h * (size_t)q.rowbytes;
   }
   return ADVGRPO_OK;
 }

@@ -2,8 +2,8 @@
 (README.md:114-128 of the reference) that the scripts open with `Image.open(fpath).convert("RGB")` on the host
 (`scripts/train_sd3_fast_pickscore.py:773-786`).  Here the IDAT stream is inflated by the library's own host inflate
 (`advgrpo_png_inflate`, plain C++), the filtered scan lines go to the GPU, and unfiltering (a wavefront over the image's
-anti-diagonals) and the conversion to RGB run there (`csrc/png.cu`), byte-exact with Pillow.  Files outside the supported
-subset (Adam7-interlaced, 16-bit greyscale + alpha) return None: the caller keeps Pillow for them."""
+anti-diagonals; once per reduced image of an Adam7-interlaced file) and the conversion to RGB run there (`csrc/png.cu`),
+byte-exact with Pillow.  Files outside the supported subset (16-bit greyscale + alpha) return None: the caller keeps Pillow for them."""
 import ctypes
 
 import torch

@@ -1,6 +1,6 @@
 """Oracle (test infrastructure only): PNG decode restated in numpy -- what Pillow's `Image.open(path).convert("RGB")`
 (`scripts/train_sd3_fast_pickscore.py:779`; the reference images of the adversarial loop are PNG files, README.md:114-128 of
-the reference) returns for non-interlaced files: chunk walk (PNG 1.2 section 5), zlib inflate of the concatenated
+the reference) returns for non-interlaced and Adam7-interlaced files: chunk walk (PNG 1.2 section 5), zlib inflate of the concatenated
 IDAT data (Python's `zlib` is the pin for the library's own inflate), scan-line unfiltering (section 6: None / Sub / Up /
 Average / Paeth, byte-wise modulo 256) and conversion to RGB (truecolour, truecolour + alpha: alpha dropped; greyscale:
 replicated; palette: looked up).  Pinned to Pillow in tests/test_oracle_models.py::test_png_oracle_matches_pillow.
@@ -44,8 +44,8 @@ CHANNELS = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
 
 def check_supported(info):
     bd, ct = info["bit_depth"], info["color_type"]
-    if info["interlace"]:
-        raise PngUnsupported("Adam7-interlaced PNG")
+    if info["interlace"] not in (0, 1):
+        raise PngUnsupported("unknown interlace method")
     if ct not in CHANNELS:
         raise PngUnsupported("bad colour type")
     ok = {0: (1, 2, 4, 8, 16), 2: (8, 16), 3: (1, 2, 4, 8), 4: (8,), 6: (8, 16)}[ct]
@@ -122,10 +122,27 @@ def to_rgb(rows, info):
     return pal[px[..., 0]]
 
 
+ADAM7 = ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2))   # x0, y0, dx, dy
+
+
 def decode_rgb(data):
     """bytes of a PNG file -> uint8 [H, W, 3], equal to np.asarray(Image.open(...).convert("RGB"))."""
     info = parse(data)
     check_supported(info)
-    rowbytes, bpp = geometry(info)
     raw = zlib.decompress(info["idat"])
-    return to_rgb(unfilter(raw, info["height"], rowbytes, bpp), info)
+    if not info["interlace"]:
+        rowbytes, bpp = geometry(info)
+        return to_rgb(unfilter(raw, info["height"], rowbytes, bpp), info)
+    # Adam7 (PNG 1.2 section 8.2): seven reduced images, each with its own filtered scan lines, scattered into place
+    out = np.zeros((info["height"], info["width"], 3), dtype=np.uint8)
+    off = 0
+    for x0, y0, dx, dy in ADAM7:
+        pw, ph = -(-(info["width"] - x0) // dx), -(-(info["height"] - y0) // dy)
+        if pw <= 0 or ph <= 0:
+            continue
+        sub = dict(info, width=pw, height=ph)
+        rowbytes, bpp = geometry(sub)
+        n = ph * (1 + rowbytes)
+        out[y0::dy, x0::dx] = to_rgb(unfilter(raw[off:off + n], ph, rowbytes, bpp), sub)
+        off += n
+    return out

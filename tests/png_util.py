@@ -13,18 +13,27 @@ def _chunk(t, b):
     return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xFFFFFFFF)
 
 
+ADAM7 = ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2))
+
+
 def handmade_png(h, w, ct, seed=0, level=6, split=None, kind=0, bd=8, interlace=0):
-    """A PNG whose rows carry random filter types; returns the file bytes (the pixels are whatever the filters reconstruct)."""
+    """A PNG whose rows carry random filter types (the pixels are whatever the filters reconstruct); with interlace=1 the seven
+    Adam7 reduced images each get their own scan lines.  Returns (file bytes, the filtered scan-line stream)."""
     rng = np.random.default_rng(seed)
-    rb = (w * CH[ct] * bd + 7) // 8
-    if kind == 0:
-        body = rng.integers(0, 256, (h, rb), dtype=np.uint8)
-    elif kind == 1:
-        body = (np.add.outer(np.arange(h) * 3, np.arange(rb) * 2) % 256).astype(np.uint8)
-    else:
-        body = np.full((h, rb), 7, np.uint8)
-    ft = rng.integers(0, 5, (h, 1), dtype=np.uint8)
-    raw = np.concatenate([ft, body], 1).tobytes()
+    passes = [(w, h)] if not interlace else [(-(-(w - x0) // dx), -(-(h - y0) // dy)) for x0, y0, dx, dy in ADAM7]
+    raw = b""
+    for pw, ph in passes:
+        if pw <= 0 or ph <= 0:
+            continue
+        rb = (pw * CH[ct] * bd + 7) // 8
+        if kind == 0:
+            body = rng.integers(0, 256, (ph, rb), dtype=np.uint8)
+        elif kind == 1:
+            body = (np.add.outer(np.arange(ph) * 3, np.arange(rb) * 2) % 256).astype(np.uint8)
+        else:
+            body = np.full((ph, rb), 7, np.uint8)
+        ft = rng.integers(0, 5, (ph, 1), dtype=np.uint8)
+        raw += np.concatenate([ft, body], 1).tobytes()
     comp = zlib.compress(raw, level)
     idats = [comp] if not split else [comp[i:i + split] for i in range(0, len(comp), split)]
     plte = _chunk(b"PLTE", rng.integers(0, 256, 768, dtype=np.uint8).tobytes()) if ct == 3 else b""

@@ -704,4 +704,19 @@ def test_png_decode_every_bit_depth(ct, bd):
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         got = png_b.decode_png_to_device(data, DEV)
         assert got is not None and torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (ct, bd, h, w)
-    assert png_b.decode_png_to_device(handmade_png(8, 8, 2, interlace=1)[0], DEV) is None
+    assert png_b.decode_png_to_device(handmade_png(8, 8, 4, bd=16)[0], DEV) is None      # 16-bit greyscale + alpha: Pillow's job
+
+
+@pytest.mark.parametrize("ct,bd", [(2, 8), (6, 8), (0, 8), (0, 2), (3, 4), (3, 8), (2, 16), (4, 8)])
+def test_png_decode_adam7_interlaced(ct, bd):
+    """Adam7-interlaced files: each of the seven reduced images is unfiltered by its own wavefront and scattered into place;
+    sizes from 1 x 1 (one pass) to 1300 rows (the last pass alone spans 650 rows)."""
+    import io
+    from PIL import Image
+    from adv_grpo_b200 import png as png_b
+    from png_util import handmade_png
+    for h, w in ((1300, 21), (37, 150), (1, 1), (2, 3), (8, 8), (5, 4)):
+        data, _ = handmade_png(h, w, ct, seed=ct * 31 + bd + h, bd=bd, interlace=1)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        got = png_b.decode_png_to_device(data, DEV)
+        assert got is not None and torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (ct, bd, h, w)

@@ -433,7 +433,7 @@ def test_png_oracle_and_host_inflate_match_pillow_and_zlib():
     """oracle/png.py (numpy restatement: chunk walk, unfiltering incl. Average and Paeth, RGB conversion) returns exactly
     Pillow's pixels, and the library's host inflate (csrc/png.cu, plain C++; runs without a GPU) returns exactly zlib's bytes --
     Pillow-written files of every colour type and hand-assembled files with random filter types, stored / fixed / dynamic
-    deflate blocks and split IDAT chunks, every supported bit depth; interlaced files are classified unsupported."""
+    deflate blocks and split IDAT chunks, every supported bit depth, Adam7-interlaced files."""
     import io
     import pytest
     from PIL import Image
@@ -464,11 +464,19 @@ def test_png_oracle_and_host_inflate_match_pillow_and_zlib():
         assert np.array_equal(png_o.decode_rgb(data), ref), (ct, bd)
         got_raw, _, info = png_b.inflate(data)
         assert info.supported == 1 and got_raw.numpy().tobytes() == raw
-    # outside the subset: Adam7 interlacing, 16-bit greyscale + alpha
-    for data in (handmade_png(8, 8, 2, interlace=1)[0], handmade_png(8, 8, 4, bd=16)[0]):
-        assert png_b.png_info(data).supported == 0 and png_b.inflate(data)[0] is None
-        with pytest.raises(png_o.PngUnsupported):
-            png_o.decode_rgb(data)
+    # Adam7-interlaced files: seven reduced images with their own scan lines
+    for t, (ct, bd) in enumerate(((2, 8), (6, 8), (0, 4), (3, 2), (2, 16), (0, 8))):
+        for h, w in ((19 + t, 23 - t), (3, 2), (1, 1), (8, 9)):
+            data, raw = handmade_png(h, w, ct, seed=200 + t + h, bd=bd, interlace=1)
+            ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+            assert np.array_equal(png_o.decode_rgb(data), ref), (ct, bd, h, w)
+            got_raw, _, info = png_b.inflate(data)
+            assert info.supported == 1 and info.interlace == 1 and got_raw.numpy().tobytes() == raw
+    # outside the subset: 16-bit greyscale + alpha
+    data = handmade_png(8, 8, 4, bd=16)[0]
+    assert png_b.png_info(data).supported == 0 and png_b.inflate(data)[0] is None
+    with pytest.raises(png_o.PngUnsupported):
+        png_o.decode_rgb(data)
     from adv_grpo_b200 import _lib
     with pytest.raises(_lib.AdvGrpoError):
         png_b.png_info(b"definitely not a png")
