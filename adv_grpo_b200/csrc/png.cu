@@ -10,10 +10,9 @@
 //           arrives from the neighbouring thread through shared memory (double-buffered by step parity), left / upper-left
 //           stay in registers; W + rows - 1 steps of one barrier each.  Then conversion to interleaved RGB bytes (truecolour:
 //           in place; alpha dropped; greyscale replicated; palette looked up), as Pillow's convert("RGB") does.
-// Non-interlaced files of every colour type and bit depth Pillow maps onto 8-bit RGB (1 / 2 / 4 / 8 / 16-bit greyscale, 8 / 16-bit
-// truecolour (+ alpha), 1..8-bit palette, 8-bit greyscale + alpha), non-interlaced or Adam7-interlaced (seven reduced images,
-// each unfiltered on its own and scattered into place); 16-bit greyscale + alpha is reported unsupported by advgrpo_png_parse
-// and stays on the caller's host decoder.
+// Every colour type and bit depth of PNG 1.2 (1 / 2 / 4 / 8 / 16-bit greyscale, 8 / 16-bit greyscale + alpha, 8 / 16-bit
+// truecolour (+ alpha), 1..8-bit palette), non-interlaced or Adam7-interlaced (seven reduced images, each unfiltered on its
+// own and scattered into place).
 #include <stdlib.h>
 #include <string.h>
 
@@ -97,7 +96,7 @@ int parse_png(const uint8_t* d, size_t n, PngParsed& P) {
   if (!P.info.channels) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad colour type");
   const int bd = P.info.bit_depth, ct = P.info.color_type;
   const bool depth_ok = (ct == 0 && (bd == 1 || bd == 2 || bd == 4 || bd == 8 || bd == 16)) || ((ct == 2 || ct == 6) && (bd == 8 || bd == 16)) ||
-                        (ct == 3 && (bd == 1 || bd == 2 || bd == 4 || bd == 8)) || (ct == 4 && bd == 8);
+                        (ct == 3 && (bd == 1 || bd == 2 || bd == 4 || bd == 8)) || (ct == 4 && (bd == 8 || bd == 16));
   if (bd != 1 && bd != 2 && bd != 4 && bd != 8 && bd != 16) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad bit depth");
   P.info.rowbytes = (int32_t)(((int64_t)P.info.width * P.info.channels * bd + 7) / 8);
   P.info.supported = depth_ok && (P.info.interlace == 0 || P.info.interlace == 1) && (ct != 3 || have_plte);
@@ -349,7 +348,7 @@ png_to_rgb_kernel(const uint8_t* __restrict__ rows, const uint8_t* __restrict__ 
     if (color_type == 2 || color_type == 6) { v[0] = p[0]; v[1] = p[sb]; v[2] = p[2 * sb]; }
     else if (color_type == 3) { v[0] = palette[3 * p[0]]; v[1] = palette[3 * p[0] + 1]; v[2] = palette[3 * p[0] + 2]; }
     else {
-      const int g = sb == 2 ? min(p[0] * 256 + p[1], 255) : p[0];
+      const int g = (sb == 2 && color_type == 0) ? min(p[0] * 256 + p[1], 255) : p[0];   // I;16 is clipped, LA;16B keeps the high byte
       v[0] = v[1] = v[2] = g;
     }
   }

@@ -3,7 +3,7 @@
 (`scripts/train_sd3_fast_pickscore.py:773-786`).  Here the IDAT stream is inflated by the library's own host inflate
 (`advgrpo_png_inflate`, plain C++), the filtered scan lines go to the GPU, and unfiltering (a wavefront over the image's
 anti-diagonals; once per reduced image of an Adam7-interlaced file) and the conversion to RGB run there (`csrc/png.cu`),
-byte-exact with Pillow.  Files outside the supported subset (16-bit greyscale + alpha) return None: the caller keeps Pillow for them."""
+byte-exact with Pillow.  Files the decoder does not take (malformed headers) return None: the caller hands them to Pillow, which reports the error."""
 import ctypes
 
 import torch

@@ -6,7 +6,7 @@ reference's reference-image generator writes) are inflated by the library's own 
 RGB on the GPU (`png.decode_png_to_device`); JPEG files (sequential or progressive) are entropy-decoded by the library's own
 host Huffman decoder and everything after that (inverse DCT, chroma upsampling, colour conversion:
 `jpeg.decode_jpeg_to_device`) runs on the GPU -- both byte-exact with Pillow; files outside those decoders' subsets
-(16-bit greyscale + alpha PNG, arithmetic-coded or CMYK JPEG, other formats) are decoded by Pillow on the host and their bytes
+(arithmetic-coded or CMYK JPEG, other formats) are decoded by Pillow on the host and their bytes
 uploaded; the antialiased bilinear resize +
 ToTensor always run on the GPU (`ops.pil_resize_bilinear`, Pillow bit-exact).  Results are cached per prompt because
 the files never change, which the reference does not do (it re-opens every file of the prompt for every batch).

@@ -384,8 +384,8 @@ int advgrpo_jpeg_idct_to_rgb(const int16_t* coefs_dev, const uint16_t* qtabs_dev
  * unfiltering (None / Sub / Up / Average / Paeth) as an anti-diagonal wavefront + conversion to interleaved RGB on the
  * DEVICE.  Byte-exact with Pillow for non-interlaced and Adam7-interlaced files of every colour type (truecolour, truecolour + alpha: alpha
  * dropped, greyscale (+ alpha): replicated, palette: looked up) at every bit depth Pillow maps onto 8-bit RGB (1 / 2 / 4 / 8 /
- * 16-bit greyscale, 8 / 16-bit truecolour (+ alpha), 1..8-bit palette).  advgrpo_png_parse (host) fills `info`; supported == 0
- * marks a valid file outside that subset (16-bit greyscale + alpha): the caller keeps its host decoder for it.
+ * 16-bit greyscale, 8 / 16-bit greyscale + alpha and truecolour (+ alpha), 1..8-bit palette).  advgrpo_png_parse (host) fills `info`;
+ * supported == 0 marks a file this decoder does not take (a depth / colour-type pair PNG does not define, a palette image without PLTE).
  * advgrpo_png_inflate (host): raw_host uint8 [advgrpo_png_raw_bytes(info)] = height x (1 filter byte + rowbytes) filtered scan
  * lines (interlaced: the same for each of the seven reduced images, concatenated), palette_host uint8 [768].  advgrpo_png_unfilter_to_rgb: device copies of both -> rgb_hwc_dev uint8 [height, width, 3]
  * (workspace: advgrpo_png_workspace_bytes, unused for truecolour). */

@@ -48,7 +48,7 @@ def check_supported(info):
         raise PngUnsupported("unknown interlace method")
     if ct not in CHANNELS:
         raise PngUnsupported("bad colour type")
-    ok = {0: (1, 2, 4, 8, 16), 2: (8, 16), 3: (1, 2, 4, 8), 4: (8,), 6: (8, 16)}[ct]
+    ok = {0: (1, 2, 4, 8, 16), 2: (8, 16), 3: (1, 2, 4, 8), 4: (8, 16), 6: (8, 16)}[ct]
     if bd not in ok:
         raise PngUnsupported(f"bit depth {bd} with colour type {ct}")
     if ct == 3 and info["palette"] is None:
@@ -96,8 +96,8 @@ def unfilter(raw, height, rowbytes, bpp):
 
 def to_rgb(rows, info):
     """What Pillow's convert("RGB") yields: sub-byte samples are unpacked (MSB first) -- greyscale scaled to 0..255 (x 255 / 85 /
-    17), palette indices looked up; 16-bit truecolour keeps the high byte of every sample, 16-bit greyscale (mode I;16) is
-    CLIPPED to 255; alpha is dropped."""
+    17), palette indices looked up; 16-bit truecolour and 16-bit greyscale + alpha (raw mode LA;16B) keep the high byte of every
+    sample, 16-bit greyscale (mode I;16) is CLIPPED to 255; alpha is dropped."""
     h, w, ct, bd = info["height"], info["width"], info["color_type"], info["bit_depth"]
     ch = CHANNELS[ct]
     if bd < 8:

@@ -690,10 +690,10 @@ def test_png_decode_all_filter_types(ct):
         assert torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (h, w, ct)
 
 
-@pytest.mark.parametrize("ct,bd", [(0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8)])
+@pytest.mark.parametrize("ct,bd", [(0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8), (4, 16)])
 def test_png_decode_every_bit_depth(ct, bd):
     """Sub-byte greyscale (scaled to 0..255) and palette samples, 16-bit greyscale (Pillow clips I;16 to 255) and 16-bit
-    truecolour (+ alpha; the high byte of every sample): what Pillow's convert("RGB") returns, with random filter types
+    truecolour (+ alpha) and greyscale + alpha (the high byte of every sample): what Pillow's convert("RGB") returns, with random filter types
     (filter pixels of 1, 2, 6 and 8 bytes) and 1100 rows = two wavefront bands."""
     import io
     from PIL import Image
@@ -704,10 +704,10 @@ def test_png_decode_every_bit_depth(ct, bd):
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         got = png_b.decode_png_to_device(data, DEV)
         assert got is not None and torch.equal(got.cpu(), torch.from_numpy(ref.copy())), (ct, bd, h, w)
-    assert png_b.decode_png_to_device(handmade_png(8, 8, 4, bd=16)[0], DEV) is None      # 16-bit greyscale + alpha: Pillow's job
+    assert png_b.decode_png_to_device(handmade_png(8, 8, 2, bd=4)[0], DEV) is None      # 4-bit truecolour does not exist in PNG
 
 
-@pytest.mark.parametrize("ct,bd", [(2, 8), (6, 8), (0, 8), (0, 2), (3, 4), (3, 8), (2, 16), (4, 8)])
+@pytest.mark.parametrize("ct,bd", [(2, 8), (6, 8), (0, 8), (0, 2), (3, 4), (3, 8), (2, 16), (4, 8), (4, 16), (6, 16)])
 def test_png_decode_adam7_interlaced(ct, bd):
     """Adam7-interlaced files: each of the seven reduced images is unfiltered by its own wavefront and scattered into place;
     sizes from 1 x 1 (one pass) to 1300 rows (the last pass alone spans 650 rows)."""

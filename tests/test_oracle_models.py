@@ -458,22 +458,22 @@ def test_png_oracle_and_host_inflate_match_pillow_and_zlib():
         if raw is not None:
             assert got_raw.numpy().tobytes() == raw
     # every bit depth Pillow maps onto 8-bit RGB: sub-byte greyscale / palette, 16-bit greyscale (clipped) and truecolour
-    for t, (ct, bd) in enumerate(((0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4))):
+    for t, (ct, bd) in enumerate(((0, 1), (0, 2), (0, 4), (0, 16), (2, 16), (6, 16), (3, 1), (3, 2), (3, 4), (4, 16))):
         data, raw = handmade_png(9 + t, 21 - t, ct, seed=100 + t, bd=bd, kind=t % 2)
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         assert np.array_equal(png_o.decode_rgb(data), ref), (ct, bd)
         got_raw, _, info = png_b.inflate(data)
         assert info.supported == 1 and got_raw.numpy().tobytes() == raw
     # Adam7-interlaced files: seven reduced images with their own scan lines
-    for t, (ct, bd) in enumerate(((2, 8), (6, 8), (0, 4), (3, 2), (2, 16), (0, 8))):
+    for t, (ct, bd) in enumerate(((2, 8), (6, 8), (0, 4), (3, 2), (2, 16), (0, 8), (4, 16))):
         for h, w in ((19 + t, 23 - t), (3, 2), (1, 1), (8, 9)):
             data, raw = handmade_png(h, w, ct, seed=200 + t + h, bd=bd, interlace=1)
             ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
             assert np.array_equal(png_o.decode_rgb(data), ref), (ct, bd, h, w)
             got_raw, _, info = png_b.inflate(data)
             assert info.supported == 1 and info.interlace == 1 and got_raw.numpy().tobytes() == raw
-    # outside the subset: 16-bit greyscale + alpha
-    data = handmade_png(8, 8, 4, bd=16)[0]
+    # a depth / colour-type pair PNG does not define (4-bit truecolour): classified, not decoded
+    data = handmade_png(8, 8, 2, bd=4)[0]
     assert png_b.png_info(data).supported == 0 and png_b.inflate(data)[0] is None
     with pytest.raises(png_o.PngUnsupported):
         png_o.decode_rgb(data)
