@@ -26,6 +26,9 @@ const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+// Pillow refuses files beyond 2 x Image.MAX_IMAGE_PIXELS (DecompressionBombError); the host decoders use the same bound
+const int64_t kMaxPixels = 2 * (int64_t)89478485;
+
 struct HuffTable {
   bool present = false;
   uint8_t counts[16];
@@ -54,13 +57,17 @@ struct Parsed {
   std::vector<Scan> scans;
 };
 
-void build_huff(HuffTable& t) {
-  int code = 0, k = 0;
+// false: the code lengths over-subscribe the code space (not a prefix code) -- a corrupt DHT segment
+bool build_huff(HuffTable& t) {
+  int code = 0, k = 0, lmax = 0;
+  for (int l = 1; l <= 16; ++l)
+    if (t.counts[l - 1]) lmax = l;
   for (int l = 1; l <= 16; ++l) {
     t.valptr[l] = k;
     t.mincode[l] = code;
     code += t.counts[l - 1];
     k += t.counts[l - 1];
+    if (l <= lmax && code >= (1 << l)) return false;     // jdhuff.c jpeg_make_d_derived_tbl: the all-ones code is not allowed either
     t.maxcode[l] = t.counts[l - 1] ? code - 1 : -1;
     code <<= 1;
   }
@@ -76,6 +83,7 @@ void build_huff(HuffTable& t) {
     code <<= 1;
   }
   t.present = true;
+  return true;
 }
 
 // returns 0 ok, 1 unsupported (info.supported = 0), negative error
@@ -89,6 +97,9 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
   size_t pos = 2;
   bool have_frame = false, saw_jfif = false, saw_adobe = false;
   int adobe_transform = -1, comp_id[3] = {0, 0, 0}, ri = 0;
+  int coef_bits[3][64];
+  for (int c = 0; c < 3; ++c)
+    for (int k = 0; k < 64; ++k) coef_bits[c][k] = -1;
   auto unsupported = [&](const char* why) {
     P.info.supported = 0;
     set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_parse: %s", why);
@@ -112,6 +123,7 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
     const uint8_t* s = d + pos + 2;
     const size_t sl = ln - 2;
     if (m == 0xDB) {
+      if (!P.scans.empty()) return unsupported("quantisation table redefined between scans");
       size_t i = 0;
       while (i + 65 <= sl) {
         const int pq = s[i] >> 4, tq = s[i] & 15;
@@ -121,16 +133,20 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
         P.qt_present[tq] = true;
         i += 65;
       }
+      if (i != sl) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DQT length");
     } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
       if (sl < 6) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: short SOF");
+      if (have_frame) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: more than one SOF marker");
       if (s[0] != 8) return unsupported("sample precision other than 8 bits");
       P.info.progressive = m == 0xC2;
       P.info.height = (s[1] << 8) | s[2];
       P.info.width = (s[3] << 8) | s[4];
       P.info.ncomp = s[5];
       if (P.info.ncomp != 1 && P.info.ncomp != 3) return unsupported("component count other than 1 or 3 (CMYK / YCCK)");
-      if (sl < (size_t)(6 + 3 * P.info.ncomp) || P.info.width < 1 || P.info.height < 1)
+      if (sl != (size_t)(6 + 3 * P.info.ncomp) || P.info.width < 1 || P.info.height < 1)
         return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad SOF");
+      if ((int64_t)P.info.width * P.info.height > kMaxPixels)
+        return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: image larger than %lld pixels", (long long)kMaxPixels);
       for (int c = 0; c < P.info.ncomp; ++c) {
         comp_id[c] = s[6 + 3 * c];
         P.info.h[c] = s[7 + 3 * c] >> 4;
@@ -152,30 +168,41 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
         for (int k = 0; k < 16; ++k) { t.counts[k] = s[i + 1 + k]; nsym += t.counts[k]; }
         if (nsym > 256 || i + 17 + nsym > sl) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DHT");
         memcpy(t.symbols, s + i + 17, nsym);
-        build_huff(t);
+        if (!tc)
+          for (int k = 0; k < nsym; ++k)
+            if (t.symbols[k] > 15) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: DC Huffman symbol beyond 15");
+        if (!build_huff(t)) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: DHT code lengths are not a prefix code");
         P.pool.push_back(t);
         (tc ? P.cur_ac : P.cur_dc)[th] = (int)P.pool.size() - 1;
         i += 17 + nsym;
       }
+      if (i != sl) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DHT length");
     } else if (m == 0xDD) {
-      if (sl >= 2) ri = (s[0] << 8) | s[1];
-    } else if (m == 0xE0 && sl >= 5 && !memcmp(s, "JFIF", 5)) {
+      if (sl != 2) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad DRI length");
+      ri = (s[0] << 8) | s[1];
+    } else if (m == 0xE0 && sl >= 14 && !memcmp(s, "JFIF", 5)) {
       saw_jfif = true;
     } else if (m == 0xEE && sl >= 12 && !memcmp(s, "Adobe", 5)) {
       saw_adobe = true;
       adobe_transform = s[11];
-    } else if (m == 0xDA) {
+    } else if ((m >= 0xE0 && m <= 0xEF) || m == 0xFE || m == 0xDC) {
+      // APPn / COM / DNL: skipped (jdmarker.c skip_variable)
+    } else if (m != 0xDA) {
+      return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: unexpected marker 0xFF%02X", (int)m);   // libjpeg: JERR_UNKNOWN_MARKER / SOI_DUPLICATE
+    } else {
       if (!have_frame) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: SOS before SOF");
       Scan sc;
       memset(&sc, 0, sizeof(sc));
       sc.ns = sl >= 1 ? s[0] : 0;
-      if (sc.ns < 1 || sc.ns > P.info.ncomp || sl < (size_t)(4 + 2 * sc.ns)) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad SOS");
+      if (sc.ns < 1 || sc.ns > P.info.ncomp || sl != (size_t)(4 + 2 * sc.ns)) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad SOS");
       if (!P.info.progressive && sc.ns != P.info.ncomp) return unsupported("non-interleaved sequential (multi-scan) file");
       for (int c = 0; c < sc.ns; ++c) {
         int idx = -1;
         for (int k = 0; k < P.info.ncomp; ++k)
           if (comp_id[k] == s[1 + 2 * c]) idx = k;
         if (idx < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: SOS names an unknown component");
+        for (int k = 0; k < c; ++k)
+          if (sc.ci[k] == idx) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: SOS names a component twice");
         sc.ci[c] = idx;
         sc.td[c] = s[2 + 2 * c] >> 4;
         sc.ta[c] = s[2 + 2 * c] & 15;
@@ -187,8 +214,10 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
       sc.al = s[3 + 2 * sc.ns] & 15;
       if (!P.info.progressive) { sc.ss = 0; sc.se = 63; sc.ah = sc.al = 0; }
       if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || (sc.ss == 0 && sc.se != 0 && P.info.progressive) ||
-          (sc.ss > 0 && sc.ns != 1))
+          (sc.ss > 0 && sc.ns != 1) || (sc.ah != 0 && sc.al != sc.ah - 1))
         return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad progressive scan parameters");
+      for (int c = 0; c < sc.ns; ++c)                 // jdphuff.c start_pass_phuff_decoder: precision each coefficient has reached
+        for (int k = sc.ss; k <= sc.se; ++k) coef_bits[sc.ci[c]][k] = sc.al;
       for (int c = 0; c < sc.ns; ++c) {
         const bool need_dc = sc.ss == 0 && sc.ah == 0, need_ac = sc.se > 0;
         if ((need_dc && P.cur_dc[sc.td[c]] < 0) || (need_ac && P.cur_ac[sc.ta[c]] < 0))
@@ -203,6 +232,17 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
     pos += ln;
   }
   if (P.scans.empty()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: no SOS marker");
+  {                                              // Pillow refuses a file that ends before its EOI marker ("image file is truncated")
+    bool eoi = false;
+    for (size_t i = P.scans.back().ecs; i + 1 < n && !eoi; ++i) eoi = d[i] == 0xFF && d[i + 1] == 0xD9;
+    if (!eoi) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: truncated file (no EOI marker after the last scan)");
+  }
+  // A progressive file that stops before every coefficient reached full precision: libjpeg would smooth the blocks
+  // (jdcoefct.c smoothing_ok / decompress_smooth_data); this decoder leaves such files to the caller's host decoder.
+  if (P.info.progressive)
+    for (int c = 0; c < P.info.ncomp; ++c)
+      for (int k = 0; k < 64; ++k)
+        if (coef_bits[c][k] != 0) return unsupported("progressive file with an incomplete scan script");
   // colour space as libjpeg's default_decompress_parms decides it
   if (P.info.ncomp == 3) {
     bool ycc = true;
@@ -234,20 +274,32 @@ struct BitReader {
   uint64_t acc;
   int cnt;
   bool hit_marker;
+  int fake = 0;                                          // zero bits fed behind a marker / the end of the file (the tail of acc)
+  int next_rst = 0;
   void fill() {
     while (cnt <= 56) {
       uint8_t b = 0;
+      bool real = false;
       if (!hit_marker && p < n) {
         b = d[p++];
+        real = true;
         if (b == 0xFF) {
           const uint8_t nx = p < n ? d[p] : 0xD9;
           if (nx == 0) ++p;
-          else { hit_marker = true; --p; b = 0; }       // stay on the marker, feed zeros (libjpeg does the same)
+          else { hit_marker = true; --p; b = 0; real = false; }   // stay on the marker, feed zeros
         }
       }
+      if (!real) fake += 8;
       acc |= (uint64_t)b << (56 - cnt);
       cnt += 8;
     }
+  }
+  // The segment ended exactly where the decoder stopped: no bit was taken from behind the marker and less than one byte of
+  // (padding) bits is left in front of it.  libjpeg decodes such streams too, with a warning ("premature end of data segment",
+  // "extraneous bytes before marker") and its own recovery; this decoder refuses them so that the caller's host decoder decides.
+  bool clean_end() {
+    if (cnt < fake || cnt - fake >= 8) return false;
+    return hit_marker || (p + 1 < n && d[p] == 0xFF && d[p + 1] != 0);
   }
   inline uint32_t peek(int k) { return (uint32_t)(acc >> (64 - k)); }
   inline void skip(int k) { acc <<= k; cnt -= k; }
@@ -279,10 +331,12 @@ struct BitReader {
     }
     return -1;
   }
-  void restart() {                                       // byte-align, skip to just behind the next RSTn
-    acc = 0; cnt = 0; hit_marker = false;
-    while (p + 1 < n && !(d[p] == 0xFF && d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7)) ++p;
+  bool restart() {                                       // byte-align; the next marker must be the RSTn that is due
+    if (!clean_end() || p + 1 >= n || d[p] != 0xFF || d[p + 1] != 0xD0 + (next_rst & 7)) return false;
+    ++next_rst;
+    acc = 0; cnt = 0; fake = 0; hit_marker = false;
     p += 2;
+    return true;
   }
 };
 
@@ -471,7 +525,7 @@ int decode_sequential(const uint8_t* file, size_t nbytes, const Parsed& P, int16
   for (int my = 0; my < mcuy; ++my)
     for (int mx = 0; mx < mcux; ++mx) {
       if (sc.ri && n && n % sc.ri == 0) {
-        br.restart();
+        if (!br.restart()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: restart marker not where it is due");
         pred[0] = pred[1] = pred[2] = 0;
       }
       ++n;
@@ -503,6 +557,11 @@ int decode_sequential(const uint8_t* file, size_t nbytes, const Parsed& P, int16
           }
       }
     }
+  if (!br.clean_end()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: the entropy-coded segment does not end with the last MCU");
+  size_t q = br.p;                                       // on the marker that ended the segment: it must be EOI (fill bytes allowed)
+  while (q + 1 < nbytes && file[q] == 0xFF && file[q + 1] == 0xFF) ++q;
+  if (q + 1 >= nbytes || file[q] != 0xFF || file[q + 1] != 0xD9)
+    return set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_entropy_decode: more segments behind the scan of a sequential file");
   return ADVGRPO_OK;
 }
 
@@ -528,7 +587,7 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
     for (int uy = 0; uy < uy_n; ++uy)
       for (int ux = 0; ux < ux_n; ++ux) {
         if (sc.ri && n && n % sc.ri == 0) {
-          br.restart();
+          if (!br.restart()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: restart marker not where it is due");
           pred[0] = pred[1] = pred[2] = 0;
           eobrun = 0;
         }
@@ -597,7 +656,10 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
                     }
                     ++kk;
                   }
-                  if (val && kk <= sc.se) blk[kZigzag[kk]] = (int16_t)val;
+                  if (val) {                                       // a new coefficient behind the band: only a corrupt stream does that
+                    if (kk > sc.se) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: refinement scan runs out of its band");
+                    blk[kZigzag[kk]] = (int16_t)val;
+                  }
                   ++kk;
                 }
               }
@@ -611,6 +673,7 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
             }
         }
       }
+    if (!br.clean_end()) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: a scan's entropy-coded segment does not end with its last block");
   }
   return ADVGRPO_OK;
 }
@@ -634,6 +697,23 @@ int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coe
   }
   memset(coefs_host, 0, total * sizeof(int16_t));
   rc = I.progressive ? decode_progressive(file, nbytes, *P, coefs_host, off) : decode_sequential(file, nbytes, *P, coefs_host, off);
+  // Dequantised coefficients of 8-bit samples have an L2 norm of at most 1024 per block, so a column's absolute sum stays below
+  // 2897 (+ quantisation error).  Beyond 4096 the file is corrupt, and libjpeg-turbo's 16-bit SIMD inverse DCT (which Pillow
+  // runs) starts to wrap / saturate where the 32-bit arithmetic of the device kernel does not: leave those to the host decoder.
+  for (int c = 0; c < I.ncomp && rc == ADVGRPO_OK; ++c) {
+    const uint16_t* q = P->qt[I.tq[c]];
+    const int16_t* blk = coefs_host + off[c];
+    const size_t nb = (size_t)I.blocks_w[c] * I.blocks_h[c];
+    for (size_t b = 0; b < nb && rc == ADVGRPO_OK; ++b, blk += 64) {
+      int col[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < 64; ++k) {
+        const int v = (int)blk[k] * (int)q[k];
+        col[k & 7] += v < 0 ? -v : v;
+      }
+      for (int k = 0; k < 8; ++k)
+        if (col[k] > 4096) rc = set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_entropy_decode: coefficients beyond the range of 8-bit samples");
+    }
+  }
   delete P;
   return rc;
 }

@@ -25,6 +25,52 @@ namespace {
 
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
+// CRC-32 of a chunk's type + data (PNG 1.2 section 3.4), eight bytes per step
+struct CrcTables {
+  uint32_t t[8][256];
+  CrcTables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      t[0][i] = c;
+    }
+    for (int s = 1; s < 8; ++s)
+      for (uint32_t i = 0; i < 256; ++i) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 255];
+  }
+};
+
+uint32_t crc32_of(const uint8_t* p, size_t n) {
+  static const CrcTables T;
+  uint32_t c = 0xFFFFFFFFu;
+  for (; n >= 8; n -= 8, p += 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = T.t[7][lo & 255] ^ T.t[6][(lo >> 8) & 255] ^ T.t[5][(lo >> 16) & 255] ^ T.t[4][lo >> 24] ^ T.t[3][hi & 255] ^
+        T.t[2][(hi >> 8) & 255] ^ T.t[1][(hi >> 16) & 255] ^ T.t[0][hi >> 24];
+  }
+  for (; n; --n, ++p) c = T.t[0][(c ^ *p) & 255] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+// Adler-32 of the inflated data (RFC 1950), modulo deferred over runs of 5552 bytes
+uint32_t adler32_of(const uint8_t* p, size_t n) {
+  uint32_t a = 1, b = 0;
+  while (n) {
+    size_t k = n < 5552 ? n : 5552;
+    n -= k;
+    for (; k >= 8; k -= 8, p += 8) {
+      a += p[0]; b += a; a += p[1]; b += a; a += p[2]; b += a; a += p[3]; b += a;
+      a += p[4]; b += a; a += p[5]; b += a; a += p[6]; b += a; a += p[7]; b += a;
+    }
+    for (; k; --k) { a += *p++; b += a; }
+    a %= 65521u;
+    b %= 65521u;
+  }
+  return (b << 16) | a;
+}
+
 int png_channels(int ct) { return ct == 0 ? 1 : ct == 2 ? 3 : ct == 3 ? 1 : ct == 4 ? 2 : ct == 6 ? 4 : 0; }
 
 // Adam7 (PNG 1.2 section 8.2): pass p covers pixels (x0 + i dx, y0 + j dy)
@@ -63,35 +109,53 @@ int parse_png(const uint8_t* d, size_t n, PngParsed& P) {
   P.idat.clear();
   if (n < 8 || memcmp(d, sig, 8)) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: not a PNG file");
   size_t pos = 8;
-  bool have_ihdr = false, have_plte = false;
+  bool have_ihdr = false, have_plte = false, have_iend = false, idat_closed = false;
+  // The chunk walk is stricter than Pillow's (which skips the IDAT and trailing CRCs): whatever it refuses goes to the caller's
+  // host decoder, so a file this decoder takes is one every decoder agrees on.
   while (pos + 12 <= n) {
     const size_t ln = be32(d + pos);
     const uint8_t* typ = d + pos + 4;
-    if (pos + 12 + ln > n) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: truncated chunk");
+    if (ln > 0x7FFFFFFFu || pos + 12 + ln > n) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: truncated chunk");
+    for (int k = 0; k < 4; ++k)
+      if (!((typ[k] >= 'A' && typ[k] <= 'Z') || (typ[k] >= 'a' && typ[k] <= 'z'))) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad chunk type");
+    if (crc32_of(typ, 4 + ln) != be32(d + pos + 8 + ln)) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: chunk checksum mismatch (%.4s)", (const char*)typ);
     const uint8_t* body = d + pos + 8;
+    const bool is_idat = !memcmp(typ, "IDAT", 4);
+    if (!have_ihdr && memcmp(typ, "IHDR", 4)) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: the first chunk is not IHDR");
+    if (!P.idat.empty() && !is_idat) idat_closed = true;
     if (!memcmp(typ, "IHDR", 4)) {
-      if (ln < 13) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: short IHDR");
+      if (ln != 13 || have_ihdr) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad IHDR");
       P.info.width = (int32_t)be32(body);
       P.info.height = (int32_t)be32(body + 4);
       P.info.bit_depth = body[8];
       P.info.color_type = body[9];
+      if (body[10] != 0 || body[11] != 0) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: unknown compression / filter method");
       P.info.interlace = body[12];
+      if (be32(body) > (1u << 15) || be32(body + 4) > (1u << 15)) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad image size");
       have_ihdr = true;
     } else if (!memcmp(typ, "PLTE", 4)) {
-      const size_t k = ln < 768 ? ln : 768;
-      memcpy(P.palette, body, k);
-      P.info.palette_entries = (int32_t)(k / 3);
+      if (have_plte || !P.idat.empty() || ln == 0 || ln > 768 || ln % 3) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad PLTE");
+      memcpy(P.palette, body, ln);
+      P.info.palette_entries = (int32_t)(ln / 3);
       have_plte = true;
-    } else if (!memcmp(typ, "IDAT", 4)) {
+    } else if (is_idat) {
+      if (idat_closed) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: IDAT chunks are not consecutive");
       P.idat.push_back({pos + 8, ln});
     } else if (!memcmp(typ, "IEND", 4)) {
+      have_iend = true;
       break;
+    } else if (!memcmp(typ, "acTL", 4)) {
+      P.info.supported = 0;                                   // animated PNG: Pillow's frame logic decides
+      return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: animated PNG");
     }
     pos += 12 + ln;
   }
+  if (!have_iend) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: no IEND chunk (truncated file)");
   if (!have_ihdr || P.idat.empty()) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: missing IHDR or IDAT");
   if (P.info.width < 1 || P.info.height < 1 || P.info.width > (1 << 15) || P.info.height > (1 << 15))
     return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad image size");
+  if ((int64_t)P.info.width * P.info.height > 2 * (int64_t)89478485)      // Pillow's DecompressionBombError bound
+    return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: image larger than 178956970 pixels");
   P.info.channels = png_channels(P.info.color_type);
   if (!P.info.channels) return set_error(ADVGRPO_ERR_BAD_ARG, "png_parse: bad colour type");
   const int bd = P.info.bit_depth, ct = P.info.color_type;
@@ -111,9 +175,10 @@ struct InBits {
   uint64_t acc;
   int cnt;
   bool eof;
+  int fake = 0;                                 // zero bits fed behind the end of the data (the top of acc): cnt < fake = some were used
   int next_byte() {
     while (seg < segs->size() && off >= (*segs)[seg].second) { ++seg; off = 0; }
-    if (seg >= segs->size()) { eof = true; return 0; }
+    if (seg >= segs->size()) { eof = true; fake += 8; return 0; }
     return d[(*segs)[seg].first + off++];
   }
   inline void need(int k) {
@@ -133,16 +198,20 @@ struct InBits {
 struct HuffDec {
   uint16_t count[16], symbol[288];
   uint16_t fast[1024];      // index = next 10 bits (LSB first); (length << 9) | symbol, 0 = longer / invalid
-  bool build(const uint8_t* lengths, int n) {
+  // complete_or_single: zlib's rule (inftrees.c) -- an incomplete code is an error unless it is a literal / distance code
+  // made of one single 1-bit code; false for the fixed distance code (30 of 32 codes)
+  bool build(const uint8_t* lengths, int n, bool is_code_length_code = false, bool check_complete = true) {
     memset(count, 0, sizeof(count));
     for (int i = 0; i < n; ++i) count[lengths[i]]++;
-    if (count[0] == n) { memset(fast, 0, sizeof(fast)); return true; }          // no codes (allowed for distances)
-    int left = 1;
+    if (count[0] == n) { memset(fast, 0, sizeof(fast)); return true; }          // no codes: decoding one reports the error
+    int left = 1, max_len = 0;
     for (int l = 1; l < 16; ++l) {
       left <<= 1;
       left -= count[l];
       if (left < 0) return false;                                              // over-subscribed
+      if (count[l]) max_len = l;
     }
+    if (check_complete && left > 0 && (is_code_length_code || max_len != 1)) return false;
     uint16_t offs[16];
     offs[1] = 0;
     for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
@@ -212,7 +281,7 @@ int inflate_stream(InBits& br, uint8_t* out, size_t out_cap, size_t* out_len) {
       for (int i = 280; i < 288; ++i) lengths[i] = 8;
       lit->build(lengths, 288);
       for (int i = 0; i < 30; ++i) lengths[i] = 5;
-      dist->build(lengths, 30);
+      dist->build(lengths, 30, false, false);
     } else {
       const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
       if (nlen > 286 || ndist > 30) { fail("bad table sizes"); break; }
@@ -220,7 +289,7 @@ int inflate_stream(InBits& br, uint8_t* out, size_t out_cap, size_t* out_len) {
       memset(cl, 0, sizeof(cl));
       for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
       HuffDec* lencode = new HuffDec();
-      if (!lencode->build(cl, 19)) { delete lencode; fail("bad code-length code"); break; }
+      if (!lencode->build(cl, 19, true)) { delete lencode; fail("bad code-length code"); break; }
       int idx = 0;
       while (idx < nlen + ndist) {
         int sym = lencode->decode(br);
@@ -238,6 +307,7 @@ int inflate_stream(InBits& br, uint8_t* out, size_t out_cap, size_t* out_len) {
       }
       delete lencode;
       if (rc != ADVGRPO_OK) break;
+      if (lengths[256] == 0) { fail("no end-of-block code"); break; }
       if (!lit->build(lengths, nlen) || !dist->build(lengths + nlen, ndist)) { fail("bad Huffman table"); break; }
     }
     for (;;) {
@@ -391,7 +461,7 @@ int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, u
   memcpy(palette_host, P->palette, 768);
   InBits br{file, &P->idat, 0, 0, 0, 0, false};
   const uint32_t cmf = br.bits(8), flg = br.bits(8);                       // zlib header (RFC 1950)
-  if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) {
+  if ((cmf & 15) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) {
     delete P;
     return set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: bad zlib header");
   }
@@ -399,6 +469,20 @@ int advgrpo_png_inflate(const uint8_t* file, size_t nbytes, uint8_t* raw_host, u
   size_t got = 0;
   rc = inflate_stream(br, raw_host, want, &got);
   if (rc == ADVGRPO_OK && got != want) rc = set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: %zu bytes of image data, %zu expected", got, want);
+  if (rc == ADVGRPO_OK) {                                      // zlib trailer: Adler-32 of the inflated data, big-endian
+    br.align_byte();
+    uint32_t sum = 0;
+    for (int k = 0; k < 4; ++k) sum = (sum << 8) | br.bits(8);
+    if (br.cnt < br.fake || sum != adler32_of(raw_host, got)) rc = set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: Adler-32 mismatch");
+  }
+  if (rc == ADVGRPO_OK) {                                      // every scan line starts with a filter type 0..4 (PNG 1.2 section 6.1)
+    PngPass ps[7];
+    const int np = png_passes(P->info, ps);
+    const uint8_t* line = raw_host;
+    for (int q = 0; q < np && rc == ADVGRPO_OK; ++q)
+      for (int y = 0; y < ps[q].h; ++y, line += 1 + ps[q].rowbytes)
+        if (*line > 4) { rc = set_error(ADVGRPO_ERR_BAD_ARG, "png_inflate: filter type %d", (int)*line); break; }
+  }
   delete P;
   return rc;
 }

@@ -359,8 +359,11 @@ int advgrpo_pil_resize_bilinear_u8(const uint8_t* img_hwc, int64_t H, int64_t W,
  * Bit-exact with libjpeg(-turbo)'s default settings, i.e. with Pillow, for baseline / extended-sequential AND progressive
  * 8-bit Huffman files, grayscale or YCbCr with 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling, with or without restart intervals.
  * advgrpo_jpeg_parse fills `info` (host call); info->supported == 0 marks a valid file outside that subset (arithmetic,
- * lossless, 12-bit, CMYK / RGB-coded, multi-scan sequential): the caller keeps its host decoder for it -- the return value is
- * still 0.
+ * lossless, 12-bit, CMYK / RGB-coded, multi-scan sequential, progressive scripts that stop short of full precision): the caller
+ * keeps its host decoder for it -- the return value is still 0.  The host functions treat the file as untrusted and take only streams
+ * every decoder reads the same way: a scan segment that does not end on its last block, a restart marker out of sequence, a missing
+ * EOI, a Huffman table libjpeg refuses, an unknown marker, or coefficients beyond the range of 8-bit samples is an error
+ * (ADVGRPO_ERR_BAD_ARG / _UNSUPPORTED), never a guess.
  * advgrpo_jpeg_entropy_decode (host call): coefs_host int16 [advgrpo_jpeg_coef_count(info)] = per component
  * [blocks_h, blocks_w, 64] quantised coefficients in natural order; qtabs_host uint16 [3 * 64] natural-order tables.
  * advgrpo_jpeg_idct_to_rgb: device pointers of the same two arrays -> rgb_hwc_dev uint8 [height, width, 3]. */
@@ -386,6 +389,8 @@ int advgrpo_jpeg_idct_to_rgb(const int16_t* coefs_dev, const uint16_t* qtabs_dev
  * dropped, greyscale (+ alpha): replicated, palette: looked up) at every bit depth Pillow maps onto 8-bit RGB (1 / 2 / 4 / 8 /
  * 16-bit greyscale, 8 / 16-bit greyscale + alpha and truecolour (+ alpha), 1..8-bit palette).  advgrpo_png_parse (host) fills `info`;
  * supported == 0 marks a file this decoder does not take (a depth / colour-type pair PNG does not define, a palette image without PLTE).
+ * The host functions treat the file as untrusted: every chunk checksum, the chunk order, zlib's code-completeness rules, the Adler-32
+ * trailer and the filter types are verified, and any violation is ADVGRPO_ERR_BAD_ARG (the caller's host decoder then decides).
  * advgrpo_png_inflate (host): raw_host uint8 [advgrpo_png_raw_bytes(info)] = height x (1 filter byte + rowbytes) filtered scan
  * lines (interlaced: the same for each of the seven reduced images, concatenated), palette_host uint8 [768].  advgrpo_png_unfilter_to_rgb: device copies of both -> rgb_hwc_dev uint8 [height, width, 3]
  * (workspace: advgrpo_png_workspace_bytes, unused for truecolour). */
