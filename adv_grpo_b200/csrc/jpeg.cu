@@ -28,6 +28,10 @@ const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
 
 // Pillow refuses files beyond 2 x Image.MAX_IMAGE_PIXELS (DecompressionBombError); the host decoders use the same bound
 const int64_t kMaxPixels = 2 * (int64_t)89478485;
+// Dequantised coefficients of 8-bit samples have an L2 norm of at most 1024 per block, so the absolute sum of a column stays
+// below 2897 (+ quantisation error).  Beyond 4096 the file is corrupt, and libjpeg-turbo's 16-bit SIMD inverse DCT (which Pillow
+// runs) starts to wrap / saturate where the 32-bit arithmetic of the device kernel does not: such files go to the host decoder.
+const int kMaxColumnSum = 4096;
 
 struct HuffTable {
   bool present = false;
@@ -37,6 +41,8 @@ struct HuffTable {
   int32_t mincode[17], maxcode[18], valptr[17];
   // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
   uint16_t fast[512];
+  // AC tables, 10-bit lookahead over code + magnitude bits together: (value << 16) | (run << 8) | total bits, 0 = take the long way
+  int32_t fast_ac[1024];
 };
 
 struct Scan {
@@ -81,6 +87,15 @@ bool build_huff(HuffTable& t) {
       for (int f = 0; f < (1 << (9 - l)); ++f) t.fast[base + f] = (uint16_t)((l << 8) | t.symbols[k]);
     }
     code <<= 1;
+  }
+  for (int i = 0; i < 1024; ++i) {
+    t.fast_ac[i] = 0;
+    const uint16_t f = t.fast[i >> 1];
+    const int len = f >> 8, run = (f >> 4) & 15, mag = f & 15;
+    if (!f || !mag || len + mag > 10) continue;
+    int v = ((i << len) & 1023) >> (10 - mag);
+    if (v < (1 << (mag - 1))) v -= (1 << mag) - 1;
+    t.fast_ac[i] = (int32_t)((uint32_t)v << 16) | (run << 8) | (len + mag);
   }
   t.present = true;
   return true;
@@ -276,7 +291,22 @@ struct BitReader {
   bool hit_marker;
   int fake = 0;                                          // zero bits fed behind a marker / the end of the file (the tail of acc)
   int next_rst = 0;
-  void fill() {
+  inline void fill() {
+    if (!hit_marker && p + 8 <= n && cnt <= 56) {          // eight bytes at once when none of them is 0xFF
+      uint64_t v;
+      memcpy(&v, d + p, 8);
+      if (((~v - 0x0101010101010101ull) & v & 0x8080808080808080ull) == 0) {
+        v = __builtin_bswap64(v);
+        const int take = (64 - cnt) >> 3;
+        acc |= (v >> (64 - 8 * take)) << (64 - cnt - 8 * take);
+        cnt += 8 * take;
+        p += take;
+        return;
+      }
+    }
+    fill_bytewise();
+  }
+  void fill_bytewise() {
     while (cnt <= 56) {
       uint8_t b = 0;
       bool real = false;
@@ -533,14 +563,31 @@ int decode_sequential(const uint8_t* file, size_t nbytes, const Parsed& P, int16
         const int c = sc.ci[k];
         const HuffTable& dct = P.pool[sc.dc_idx[sc.td[k]]];
         const HuffTable& act = P.pool[sc.ac_idx[sc.ta[k]]];
+        const uint16_t* qt = P.qt[I.tq[c]];
         for (int by = 0; by < I.v[c]; ++by)
           for (int bx = 0; bx < I.h[c]; ++bx) {
             int16_t* blk = coefs + off[c] + ((size_t)(my * I.v[c] + by) * I.blocks_w[c] + (mx * I.h[c] + bx)) * 64;
+            memset(blk, 0, 64 * sizeof(int16_t));
+            int col[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // column sums of |coefficient x quantiser| (kMaxColumnSum)
+            auto put = [&](int nat, int v) {
+              blk[nat] = (int16_t)v;
+              const int m = (int)(int16_t)v * (int)qt[nat];
+              col[nat & 7] += m < 0 ? -m : m;
+            };
             const int t = br.decode(dct);
             if (t < 0 || t > 11) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt DC code");
             pred[c] += br.receive_extend(t);
-            blk[0] = (int16_t)pred[c];
+            put(0, pred[c]);
             for (int kk = 1; kk < 64;) {
+              if (br.cnt < 16) br.fill();
+              const int32_t fa = act.fast_ac[br.peek(10)];
+              if (fa) {                                           // code and magnitude bits in one lookup
+                kk += (fa >> 8) & 15;
+                if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+                put(kZigzag[kk++], fa >> 16);
+                br.skip(fa & 255);
+                continue;
+              }
               const int rs = br.decode(act);
               if (rs < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code");
               const int r = rs >> 4, sz = rs & 15;
@@ -551,9 +598,12 @@ int decode_sequential(const uint8_t* file, size_t nbytes, const Parsed& P, int16
               }
               kk += r;
               if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
-              blk[kZigzag[kk]] = (int16_t)br.receive_extend(sz);
+              put(kZigzag[kk], br.receive_extend(sz));
               ++kk;
             }
+            for (int q = 0; q < 8; ++q)
+              if (col[q] > kMaxColumnSum)
+                return set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_entropy_decode: coefficients beyond the range of 8-bit samples");
           }
       }
     }
@@ -614,6 +664,15 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
               if (sc.ah == 0) {                                   // AC first scan
                 if (eobrun > 0) { --eobrun; continue; }
                 for (int kk = sc.ss; kk <= sc.se;) {
+                  if (br.cnt < 16) br.fill();
+                  const int32_t fa = act.fast_ac[br.peek(10)];
+                  if (fa) {
+                    kk += (fa >> 8) & 15;
+                    if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+                    blk[kZigzag[kk++]] = (int16_t)((fa >> 16) * (1 << sc.al));
+                    br.skip(fa & 255);
+                    continue;
+                  }
                   const int rs = br.decode(act);
                   if (rs < 0) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: corrupt AC code");
                   const int r = rs >> 4, sz = rs & 15;
@@ -695,23 +754,26 @@ int advgrpo_jpeg_entropy_decode(const uint8_t* file, size_t nbytes, int16_t* coe
     total += (size_t)I.blocks_w[c] * I.blocks_h[c] * 64;
     for (int k = 0; k < 64; ++k) qtabs_host[c * 64 + k] = P->qt[I.tq[c]][k];
   }
-  memset(coefs_host, 0, total * sizeof(int16_t));
-  rc = I.progressive ? decode_progressive(file, nbytes, *P, coefs_host, off) : decode_sequential(file, nbytes, *P, coefs_host, off);
-  // Dequantised coefficients of 8-bit samples have an L2 norm of at most 1024 per block, so a column's absolute sum stays below
-  // 2897 (+ quantisation error).  Beyond 4096 the file is corrupt, and libjpeg-turbo's 16-bit SIMD inverse DCT (which Pillow
-  // runs) starts to wrap / saturate where the 32-bit arithmetic of the device kernel does not: leave those to the host decoder.
-  for (int c = 0; c < I.ncomp && rc == ADVGRPO_OK; ++c) {
-    const uint16_t* q = P->qt[I.tq[c]];
-    const int16_t* blk = coefs_host + off[c];
-    const size_t nb = (size_t)I.blocks_w[c] * I.blocks_h[c];
-    for (size_t b = 0; b < nb && rc == ADVGRPO_OK; ++b, blk += 64) {
-      int col[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int k = 0; k < 64; ++k) {
-        const int v = (int)blk[k] * (int)q[k];
-        col[k & 7] += v < 0 ? -v : v;
+  if (!I.progressive) {
+    rc = decode_sequential(file, nbytes, *P, coefs_host, off);       // zeroes each block and checks its range as it goes
+  } else {
+    memset(coefs_host, 0, total * sizeof(int16_t));
+    rc = decode_progressive(file, nbytes, *P, coefs_host, off);
+    for (int c = 0; c < I.ncomp && rc == ADVGRPO_OK; ++c) {             // the scans accumulate: range check (kMaxColumnSum) at the end
+      const uint16_t* q = P->qt[I.tq[c]];
+      const int16_t* blk = coefs_host + off[c];
+      const size_t nb = (size_t)I.blocks_w[c] * I.blocks_h[c];
+      for (size_t b = 0; b < nb && rc == ADVGRPO_OK; ++b, blk += 64) {
+        int col[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < 8; ++r)
+          for (int k = 0; k < 8; ++k) {
+            const int v = (int)blk[8 * r + k] * (int)q[8 * r + k];
+            col[k] += v < 0 ? -v : v;
+          }
+        for (int k = 0; k < 8; ++k)
+          if (col[k] > kMaxColumnSum)
+            rc = set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_entropy_decode: coefficients beyond the range of 8-bit samples");
       }
-      for (int k = 0; k < 8; ++k)
-        if (col[k] > 4096) rc = set_error(ADVGRPO_ERR_UNSUPPORTED, "jpeg_entropy_decode: coefficients beyond the range of 8-bit samples");
     }
   }
   delete P;

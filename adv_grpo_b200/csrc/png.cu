@@ -182,6 +182,17 @@ struct InBits {
     return d[(*segs)[seg].first + off++];
   }
   inline void need(int k) {
+    if (cnt >= k) return;
+    if (seg < segs->size() && off + 8 <= (*segs)[seg].second) {      // eight bytes of the current IDAT body at once
+      uint64_t v;
+      memcpy(&v, d + (*segs)[seg].first + off, 8);                 // little-endian host (x86-64 / aarch64)
+      const int adv = (63 - cnt) >> 3;
+      acc |= v << cnt;
+      cnt += 8 * adv;
+      off += adv;
+      acc &= (1ull << cnt) - 1;                                    // cnt <= 63: drop the bits of bytes not consumed yet
+      return;
+    }
     while (cnt < k) { acc |= (uint64_t)next_byte() << cnt; cnt += 8; }
   }
   inline uint32_t bits(int k) {
@@ -327,7 +338,14 @@ int inflate_stream(InBits& br, uint8_t* out, size_t out_cap, size_t* out_len) {
         const size_t dd = dbase[ds] + br.bits(dext[ds]);
         if (dd > o) { fail("distance beyond the start of the output"); break; }
         if (o + len > out_cap) { fail("output overflow"); break; }
-        for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dd];
+        if (dd >= 8 && o + len + 8 <= out_cap) {                     // eight bytes per step; may run up to 7 bytes past o + len
+          const uint8_t* src = out + o - dd;
+          uint8_t* dst = out + o;
+          for (int i = 0; i < len; i += 8) memcpy(dst + i, src + i, 8);
+          o += len;
+        } else {
+          for (int i = 0; i < len; ++i, ++o) out[o] = out[o - dd];
+        }
       }
     }
   }
