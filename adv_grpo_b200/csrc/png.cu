@@ -380,8 +380,24 @@ png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows,
     const int ft = live ? in[0] : 0;
     uint64_t left = 0, upleft = 0;                            // packed BPP bytes
     const int steps = W + rows_here - 1;
+    // The filtered bytes of a pixel are fetched four steps before the wavefront reaches it (a queue of four packed pixels in
+    // registers), so the global-memory latency of the row-strided loads is off the step's critical path.
+    auto fetch = [&](int p) -> uint64_t {
+      uint64_t v = 0;
+      if (live && p >= 0 && p < W) {
+#pragma unroll
+        for (int k = 0; k < BPP; ++k) v |= (uint64_t)in[1 + (int64_t)p * BPP + k] << (8 * k);
+      }
+      return v;
+    };
+    uint64_t q0 = fetch(-r), q1 = fetch(1 - r), q2 = fetch(2 - r), q3 = fetch(3 - r);
     for (int t = 0; t < steps; ++t) {
       const int px = t - r;
+      const uint64_t cur = q0;                                // the filtered bytes of pixel px
+      q0 = q1;
+      q1 = q2;
+      q2 = q3;
+      q3 = fetch(px + 4);
       uint64_t rec = 0;
       if (live && px >= 0 && px < W) {
         uint64_t up = 0;
@@ -392,7 +408,7 @@ png_unfilter_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ rows,
         }
 #pragma unroll
         for (int k = 0; k < BPP; ++k) {
-          const int x = in[1 + (int64_t)px * BPP + k];
+          const int x = (int)((cur >> (8 * k)) & 255);
           const int a = (int)((left >> (8 * k)) & 255), b = (int)((up >> (8 * k)) & 255), c = (int)((upleft >> (8 * k)) & 255);
           int pr = 0;
           if (ft == 1) pr = a;

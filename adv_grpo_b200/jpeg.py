@@ -40,6 +40,11 @@ def decode_jpeg_to_device(data, device="cuda"):
     coefs, qt, info = entropy_decode(data)
     if coefs is None:
         return None
+    return idct_on_device(coefs, qt, info, device)
+
+
+def idct_on_device(coefs, qt, info, device="cuda"):
+    """Device step: the output of `entropy_decode` (host tensors) -> uint8 [H, W, 3] on `device`."""
     dev = torch.device(device)
     coefs_d, qt_d = coefs.to(dev, non_blocking=True), qt.to(dev, non_blocking=True)
     rgb = torch.empty((info.height, info.width, 3), dtype=torch.uint8, device=dev)

@@ -37,6 +37,11 @@ def decode_png_to_device(data, device="cuda"):
     raw, pal, info = inflate(data)
     if raw is None:
         return None
+    return unfilter_on_device(raw, pal, info, device)
+
+
+def unfilter_on_device(raw, pal, info, device="cuda"):
+    """Device step: the output of `inflate` (host tensors) -> uint8 [H, W, 3] on `device`."""
     dev = torch.device(device)
     raw_d, pal_d = raw.to(dev, non_blocking=True), pal.to(dev, non_blocking=True)
     rgb = torch.empty((info.height, info.width, 3), dtype=torch.uint8, device=dev)

@@ -9,8 +9,8 @@ host Huffman decoder and everything after that (inverse DCT, chroma upsampling, 
 (arithmetic-coded or CMYK JPEG, other formats) are decoded by Pillow on the host and their bytes
 uploaded; the antialiased bilinear resize +
 ToTensor always run on the GPU (`ops.pil_resize_bilinear`, Pillow bit-exact).  Results are cached per prompt because
-the files never change, which the reference does not do (it re-opens every file of the prompt for every batch).
-SURVEY.md section 8f rank 3."""
+the files never change, which the reference does not do (it re-opens every file of the prompt for every batch), and
+the host stages of a prompt's files run in parallel on a thread pool.  SURVEY.md section 8f rank 3."""
 import json
 import os
 
@@ -19,45 +19,75 @@ import torch
 
 
 class ReferenceImageIndex:
-    def __init__(self, json_path, image_root, size=512, device="cuda", default_image=None, cache=True):
+    def __init__(self, json_path, image_root, size=512, device="cuda", default_image=None, cache=True, host_threads=None):
         with open(json_path, "r", encoding="utf-8") as f:
             self.index = json.load(f)                                  # train_pick:705-707
         self.root, self.size, self.device = image_root, int(size), device
         self.default_image = default_image                            # the reference hard-codes a fallback file (:784)
         self._cache = {} if cache else None
+        self.host_threads = min(8, os.cpu_count() or 1) if host_threads is None else int(host_threads)
+        self._pool = None
 
     def __contains__(self, prompt):
         return prompt in self.index
 
-    def _load(self, path):
+    def _host_stage(self, path):
+        """Everything that needs no GPU, safe to run on a worker thread (the C calls and Pillow release the GIL): read the
+        file and run the library's host inflate / Huffman decode, or Pillow for what they do not take.
+        -> ("png", raw, palette, info) | ("jpeg", coefs, qtabs, info) | ("rgb", uint8 ndarray [H, W, 3])"""
         from PIL import Image
-        cuda = torch.device(self.device).type == "cuda"
-        if cuda:                                                       # baseline JPEG: host Huffman decode, the rest on the GPU
-            from . import _lib, jpeg, ops, png
-            raw = None
+        if torch.device(self.device).type == "cuda":
+            from . import _lib, jpeg, png
             try:
                 with open(path, "rb") as f:
                     data = f.read()
                 if data[:8] == b"\x89PNG\r\n\x1a\n":                       # the reference images of the loop are PNG files
-                    raw = png.decode_png_to_device(data, self.device)     # None: outside the subset -> Pillow below
+                    raw, pal, info = png.inflate(data)
+                    if raw is not None:
+                        return ("png", raw, pal, info)
                 elif data[:2] == b"\xff\xd8":
-                    raw = jpeg.decode_jpeg_to_device(data, self.device)   # None: CMYK / arithmetic / ... -> Pillow below
+                    coefs, qt, info = jpeg.entropy_decode(data)
+                    if coefs is not None:
+                        return ("jpeg", coefs, qt, info)
             except (OSError, _lib.AdvGrpoError):
-                raw = None                                             # unreadable / corrupt: Pillow decides (and falls back)
-            if raw is not None:
-                return ops.pil_resize_bilinear(raw, self.size, self.size)
+                pass                                                   # unreadable / corrupt / outside the subset: Pillow decides
         try:
             img = Image.open(path).convert("RGB")
         except Exception as e:                                         # train_pick:781-786: fall back to the default image
             if self.default_image is None:
                 raise FileNotFoundError(f"reference image {path} could not be opened ({e}) and no default_image is set")
             img = Image.open(self.default_image).convert("RGB")
-        if cuda:                                                       # decoded bytes -> device, resize + ToTensor on the GPU
-            raw = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).to(self.device)
-            return ops.pil_resize_bilinear(raw, self.size, self.size)
-        img = img.resize((self.size, self.size), Image.BILINEAR)       # CPU device (host tests): torchvision Resize on PIL
+        return ("rgb", np.asarray(img, dtype=np.uint8))
+
+    def _device_stage(self, item):
+        from PIL import Image
+        if torch.device(self.device).type == "cuda":
+            from . import jpeg, ops, png
+            if item[0] == "png":                                       # wavefront unfiltering + RGB conversion on the GPU
+                raw = png.unfilter_on_device(item[1], item[2], item[3], self.device)
+            elif item[0] == "jpeg":                                    # inverse DCT, chroma upsampling, colour conversion on the GPU
+                raw = jpeg.idct_on_device(item[1], item[2], item[3], self.device)
+            else:                                                      # decoded by Pillow: bytes -> device
+                raw = torch.from_numpy(item[1].copy()).to(self.device)
+            return ops.pil_resize_bilinear(raw, self.size, self.size)  # resize + ToTensor on the GPU
+        img = Image.fromarray(item[1]).resize((self.size, self.size), Image.BILINEAR)   # CPU device (host tests): Resize on PIL
         arr = np.asarray(img, dtype=np.uint8)                          # HWC
         return torch.from_numpy(arr.copy()).permute(2, 0, 1).float().div_(255.0)   # ToTensor()
+
+    def _load(self, path):
+        return self._device_stage(self._host_stage(path))
+
+    def _load_many(self, paths):
+        """The host stages of a prompt's files run side by side on a small thread pool (entropy decoding is serial per file
+        and is most of the time: 8 files of 1024 x 1024 take 8 x 12 ms one after the other); the device stages follow in
+        order on the caller's thread and stream."""
+        if len(paths) < 2 or self.host_threads < 2:
+            return [self._load(p) for p in paths]
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.host_threads, thread_name_prefix="refimg")
+        futures = [self._pool.submit(self._host_stage, p) for p in paths]
+        return [self._device_stage(f.result()) for f in futures]
 
     def __call__(self, prompt, n=None):
         """-> float32 [len(files) or n, 3, size, size] in [0, 1] on the device (train_pick:797-799).  With `n`, the
@@ -68,7 +98,7 @@ class ReferenceImageIndex:
             t = self._cache[prompt]
         else:
             files = self.index[prompt]
-            t = torch.stack([self._load(os.path.join(self.root, f)) for f in files]).to(self.device, torch.float32)
+            t = torch.stack(self._load_many([os.path.join(self.root, f) for f in files])).to(self.device, torch.float32)
             if self._cache is not None:
                 self._cache[prompt] = t
         if n is not None and t.shape[0] != n:

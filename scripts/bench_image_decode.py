@@ -55,3 +55,24 @@ for size in (1024, 2048):
         raw = dec(data, DEV)
         print(f"{name} {size}x{size} ({len(data) / 1e6:.2f} MB): Pillow path {timed(lambda: pil_path(data)):.1f} ms, hybrid path "
               f"{timed(ours):.1f} ms wall (device resize alone {dev_ms(lambda: ops.pil_resize_bilinear(raw, 512, 512)):.3f} ms)")
+
+# one prompt = 8 reference files (mini_num_image_per_prompt): host stages one after the other vs on the thread pool
+import json  # noqa: E402
+import tempfile  # noqa: E402
+
+from adv_grpo_b200.reference_images import ReferenceImageIndex  # noqa: E402
+
+tmp = tempfile.mkdtemp()
+names = []
+for i in range(8):
+    names.append(f"r{i}.png")
+    with open(os.path.join(tmp, names[-1]), "wb") as f:
+        f.write(pillow_png(1024, 1024, "RGB", seed=100 + i))
+with open(os.path.join(tmp, "index.json"), "w") as f:
+    json.dump({"p": names}, f)
+for label, kw in (("Pillow on the host, one file after the other (reference)", dict(device="cpu", host_threads=1)),
+                  ("Pillow on the host, 8 threads", dict(device="cpu")), ("hybrid, host stages serial", dict(device=DEV, host_threads=1)),
+                  ("hybrid, host stages on 8 threads", dict(device=DEV))):
+    idx = ReferenceImageIndex(os.path.join(tmp, "index.json"), tmp, size=512, cache=False, **kw)
+    fn = (lambda: idx("p").to(DEV)) if kw["device"] == "cpu" else (lambda: idx("p"))
+    print(f"prompt with 8 x 1024x1024 PNG -> [8, 3, 512, 512] on the device: {label} {timed(fn, n=3):.1f} ms ({os.cpu_count()} host cores)")

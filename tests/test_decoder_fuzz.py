@@ -208,3 +208,29 @@ def test_accepted_png_mutants_equal_pillow():
         got = pixels(raw, pal, info)
         assert ref is not None and ref.shape == got.shape and np.array_equal(ref, got), f"mutant {it} of seed {it % len(seeds)}"
     assert taken > 100
+
+
+def test_host_decoders_are_thread_safe():
+    """`ReferenceImageIndex` runs the host stages of a prompt's files on a thread pool: the same files decoded from eight
+    threads at once give the bytes a serial pass gives (per-thread error string, no shared state in the decoders)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from adv_grpo_b200 import _lib, jpeg as jpeg_b, png as png_b
+    from jpeg_util import _jpeg_bytes
+    from png_util import handmade_png
+    jobs = [("p", handmade_png(150 + 7 * i, 200 - 5 * i, (2, 6, 0, 3)[i % 4], seed=i, interlace=i % 2)[0]) for i in range(8)]
+    jobs += [("j", _jpeg_bytes(160 + 8 * i, 200 - 8 * i, seed=i, quality=85, subsampling=i % 3, progressive=bool(i % 2))) for i in range(8)]
+    jobs += [("p", b"\x89PNG\r\n\x1a\n" + b"garbage" * 9), ("j", b"\xff\xd8" + b"garbage" * 9)]
+
+    def run(job):
+        kind, data = job
+        try:
+            out = png_b.inflate(data) if kind == "p" else jpeg_b.entropy_decode(data)
+        except _lib.AdvGrpoError as e:
+            return str(e)
+        return out[0].numpy().tobytes()
+
+    serial = [run(j) for j in jobs]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for _ in range(3):
+            assert list(ex.map(run, jobs)) == serial
+    assert "png" in serial[-2] and "jpeg" in serial[-1]

@@ -623,12 +623,20 @@ def test_reference_image_index_gpu_path_equals_pil_path(tmp_path):
     Image.fromarray(rng.integers(0, 256, (300, 420, 3), dtype=np.uint8)).save(tmp_path / "a.jpg", quality=90)
     Image.fromarray(rng.integers(0, 256, (640, 512, 3), dtype=np.uint8)).save(tmp_path / "b.png")
     Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(tmp_path / "default.png")
-    (tmp_path / "index.json").write_text(json.dumps({"a cat": ["a.jpg", "b.png", "missing.jpg"]}))
+    Image.fromarray(rng.integers(0, 256, (200, 333, 3), dtype=np.uint8)).save(tmp_path / "c.jpg", quality=80, progressive=True)
+    Image.fromarray(rng.integers(0, 256, (90, 70), dtype=np.uint8)).save(tmp_path / "d.png")
+    Image.fromarray(np.full((16, 16, 4), 100, dtype=np.uint8), mode="CMYK").save(tmp_path / "e.jpg")      # Pillow's job
+    bad = bytearray((tmp_path / "b.png").read_bytes())
+    bad[-14] ^= 0xFF                                                   # damaged IDAT checksum: refused here, Pillow does not check it
+    (tmp_path / "f.png").write_bytes(bytes(bad))
+    files = ["a.jpg", "b.png", "missing.jpg", "c.jpg", "d.png", "e.jpg", "f.png", "a.jpg"]
+    (tmp_path / "index.json").write_text(json.dumps({"a cat": files}))
     kw = dict(size=256, default_image=str(tmp_path / "default.png"))
-    gpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device=DEV, **kw)("a cat")
+    gpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device=DEV, **kw)("a cat")      # host stages on a thread pool
+    one = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device=DEV, host_threads=1, **kw)("a cat")
     cpu = ReferenceImageIndex(str(tmp_path / "index.json"), str(tmp_path), device="cpu", **kw)("a cat")
-    assert gpu.is_cuda and gpu.shape == (3, 3, 256, 256) and gpu.dtype == torch.float32
-    assert torch.equal(gpu.cpu(), cpu)
+    assert gpu.is_cuda and gpu.shape == (len(files), 3, 256, 256) and gpu.dtype == torch.float32
+    assert torch.equal(gpu.cpu(), cpu) and torch.equal(one.cpu(), cpu)
 
 
 # ------------------------------------------------------------------ 8f-3 JPEG decode (host Huffman + device IDCT / colour)
