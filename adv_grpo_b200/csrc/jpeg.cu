@@ -12,6 +12,11 @@
 // runs, jdphuff.c) Huffman files; files outside the supported subset (arithmetic, lossless, 12-bit, CMYK / RGB colour spaces,
 // non-interleaved sequential scans, chroma factors other than 1x1) are reported as unsupported by advgrpo_jpeg_parse and stay
 // on the caller's host decoder.
+// The file bytes are untrusted.  The host half never reads or writes outside its buffers (fuzzed under AddressSanitizer,
+// tests/fuzz/fuzz_image_decoders.cpp) and takes only streams that every decoder reads the same way: a scan segment that does
+// not end on its last block, a restart marker out of sequence, a missing EOI, a Huffman table libjpeg refuses, an unknown
+// marker, an incomplete progressive script or coefficients beyond the range of 8-bit samples is an error, so that whatever
+// this decoder accepts comes out as Pillow decodes it (tests/test_decoder_fuzz.py).
 #include <stdlib.h>
 #include <string.h>
 

@@ -13,6 +13,9 @@
 // Every colour type and bit depth of PNG 1.2 (1 / 2 / 4 / 8 / 16-bit greyscale, 8 / 16-bit greyscale + alpha, 8 / 16-bit
 // truecolour (+ alpha), 1..8-bit palette), non-interlaced or Adam7-interlaced (seven reduced images, each unfiltered on its
 // own and scattered into place).
+// The file bytes are untrusted: the host half checks every chunk checksum, the chunk order, zlib's code-completeness rules, the
+// Adler-32 trailer and the filter types, and is fuzzed under AddressSanitizer and differentially against Pillow
+// (tests/fuzz/fuzz_image_decoders.cpp, tests/test_decoder_fuzz.py).
 #include <stdlib.h>
 #include <string.h>
 
