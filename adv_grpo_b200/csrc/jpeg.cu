@@ -173,6 +173,8 @@ int parse_jpeg(const uint8_t* d, size_t n, Parsed& P) {
         P.info.v[c] = s[7 + 3 * c] & 15;
         P.info.tq[c] = s[8 + 3 * c];
         if (P.info.tq[c] > 3) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: bad quantisation table id");
+        if (P.info.h[c] < 1 || P.info.h[c] > 4 || P.info.v[c] < 1 || P.info.v[c] > 4)      // jdinput.c: JERR_BAD_SAMPLING
+          return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_parse: sampling factor outside 1..4");
       }
       if (P.info.ncomp == 1) P.info.h[0] = P.info.v[0] = 1;      // a single-component image is never interleaved
       have_frame = true;
@@ -625,6 +627,11 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
   const advgrpo_jpeg_info& I = P.info;
   const int hmax = I.h[0], vmax = I.v[0];
   const int mcux = I.blocks_w[0] / hmax, mcuy = I.blocks_h[0] / vmax;
+  // Per block, the zigzag index of the last AC coefficient written so far: everything behind it is still zero, so the
+  // refinement scans (which walk a block's band once per scan) stop there instead of reading 63 coefficients of every block.
+  size_t total_blocks = 0;
+  for (int c = 0; c < I.ncomp; ++c) total_blocks += (size_t)I.blocks_w[c] * I.blocks_h[c];
+  std::vector<uint8_t> last_nz(total_blocks, 0);
   for (const Scan& sc : P.scans) {
     BitReader br{file, nbytes, sc.ecs, 0, 0, false};
     int pred[3] = {0, 0, 0};
@@ -654,6 +661,7 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
             for (int bx = 0; bx < nbx; ++bx) {
               const int brow = sc.ns == 1 ? uy : uy * I.v[c] + by, bcol = sc.ns == 1 ? ux : ux * I.h[c] + bx;
               int16_t* blk = coefs + off[c] + ((size_t)brow * I.blocks_w[c] + bcol) * 64;
+              uint8_t& last = last_nz[(size_t)(blk - coefs) / 64];
               if (sc.ss == 0) {                                   // DC scan
                 if (sc.ah == 0) {
                   const int t = br.decode(P.pool[sc.dc_idx[sc.td[k]]]);
@@ -674,6 +682,7 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
                   if (fa) {
                     kk += (fa >> 8) & 15;
                     if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+                    if (kk > last) last = (uint8_t)kk;
                     blk[kZigzag[kk++]] = (int16_t)((fa >> 16) * (1 << sc.al));
                     br.skip(fa & 255);
                     continue;
@@ -684,6 +693,7 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
                   if (sz) {
                     kk += r;
                     if (kk > 63) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: coefficient index out of range");
+                    if (kk > last) last = (uint8_t)kk;
                     blk[kZigzag[kk]] = (int16_t)(br.receive_extend(sz) * (1 << sc.al));
                     ++kk;
                   } else if (r == 15) {
@@ -711,6 +721,10 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
                     break;
                   }
                   while (kk <= sc.se) {                            // skip r still-zero coefficients, refining the others
+                    if (kk > last) {                               // nothing but zeros from here on: jump
+                      kk = r > sc.se - kk ? sc.se + 1 : kk + r;
+                      break;
+                    }
                     int16_t& co = blk[kZigzag[kk]];
                     if (co != 0) {
                       if (br.get_bits(1) && (co & p1) == 0) co = (int16_t)(co + (co >= 0 ? p1 : m1));
@@ -722,13 +736,14 @@ int decode_progressive(const uint8_t* file, size_t nbytes, const Parsed& P, int1
                   }
                   if (val) {                                       // a new coefficient behind the band: only a corrupt stream does that
                     if (kk > sc.se) return set_error(ADVGRPO_ERR_BAD_ARG, "jpeg_entropy_decode: refinement scan runs out of its band");
+                    if (kk > last) last = (uint8_t)kk;
                     blk[kZigzag[kk]] = (int16_t)val;
                   }
                   ++kk;
                 }
               }
               if (eobrun > 0) {                                    // the rest of the band: correction bits only
-                for (; kk <= sc.se; ++kk) {
+                for (const int end = sc.se < last ? sc.se : last; kk <= end; ++kk) {
                   int16_t& co = blk[kZigzag[kk]];
                   if (co != 0 && br.get_bits(1) && (co & p1) == 0) co = (int16_t)(co + (co >= 0 ? p1 : m1));
                 }
