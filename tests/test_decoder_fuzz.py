@@ -234,3 +234,25 @@ def test_host_decoders_are_thread_safe():
         for _ in range(3):
             assert list(ex.map(run, jobs)) == serial
     assert "png" in serial[-2] and "jpeg" in serial[-1]
+
+
+def test_host_decoder_on_the_gpu_suite_files():
+    """The files of `test_kernels_gpu.py::test_jpeg_decode_bit_exact_with_pillow` (restart intervals, progressive scripts,
+    narrow planes, 1 x 1), host half only: the library's coefficients pushed through the numpy oracle's back end equal Pillow,
+    so a change of the host decoder is checked here without a GPU."""
+    import numpy as np
+    from adv_grpo_b200 import jpeg as jpeg_b
+    from jpeg_util import _jpeg_bytes
+    from oracle import jpeg as jpeg_o
+    cases = [(512, 512, dict(quality=90, subsampling=2)), (333, 517, dict(quality=75, subsampling=1)), (600, 401, dict(quality=95, subsampling=0)),
+             (480, 640, dict(quality=60, subsampling=2, restart_marker_blocks=4)), (257, 129, dict(quality=80, gray=True)),
+             (1, 1, dict(quality=90, subsampling=2)), (17, 9, dict(quality=100, subsampling=2)),
+             (512, 768, dict(quality=85, subsampling=2, progressive=True)), (301, 203, dict(quality=92, subsampling=1, progressive=True)),
+             (480, 640, dict(quality=70, subsampling=0, progressive=True, restart_marker_blocks=8)),
+             (47, 3, dict(quality=100, subsampling=2)), (16, 4, dict(quality=90, subsampling=1)),
+             (30, 2, dict(quality=80, subsampling=2, progressive=True)), (9, 5, dict(quality=90, subsampling=2))]
+    for h, w, kw in cases:
+        data = _jpeg_bytes(h, w, seed=h + w, **kw)
+        coefs, _, info = jpeg_b.coefficients_as_numpy(data)
+        assert coefs is not None and (info.height, info.width) == (h, w), (h, w, kw)
+        assert np.array_equal(jpeg_o.assemble_rgb(jpeg_o.parse(data), coefs), _pillow_rgb(data)), (h, w, kw)
