@@ -49,6 +49,18 @@ def test_bad_arguments_return_error_codes_not_crashes():
     with pytest.raises(_lib.AdvGrpoError, match="step"):
         _lib.call("advgrpo_clip_adamw", 16, 16, 16, 16, 16, 3e-4, 0.9, 0.999, 1e-8, 1e-4, 0, 1.0, 1, None, None, 0, None)
     assert _lib.query("advgrpo_clip_adamw_workspace_bytes", 1 << 20) >= 8
+    # the host halves of the image decoders: null pointers, empty and one-byte files
+    import ctypes
+    png_info, jpeg_info = _lib.PngInfo(), _lib.JpegInfo()
+    one = (ctypes.c_uint8 * 1)(0xFF)
+    for name, args in (("advgrpo_png_parse", (None, 0, ctypes.byref(png_info))), ("advgrpo_png_parse", (one, 1, None)),
+                       ("advgrpo_png_parse", (one, 1, ctypes.byref(png_info))), ("advgrpo_jpeg_parse", (None, 0, ctypes.byref(jpeg_info))),
+                       ("advgrpo_jpeg_parse", (one, 1, ctypes.byref(jpeg_info))), ("advgrpo_png_inflate", (None, 0, None, None)),
+                       ("advgrpo_jpeg_entropy_decode", (None, 0, None, None))):
+        with pytest.raises(_lib.AdvGrpoError):
+            _lib.call(name, *args)
+    for name in ("advgrpo_png_raw_bytes", "advgrpo_png_workspace_bytes", "advgrpo_jpeg_coef_count", "advgrpo_jpeg_workspace_bytes"):
+        assert _lib.query(name, None) == 0
 
 
 def test_ops_refuse_cpu_tensors():
